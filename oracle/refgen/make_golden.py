@@ -1,0 +1,108 @@
+#!/usr/bin/env python
+"""
+oracle/refgen/make_golden.py -- regenerate tests/golden/*.npz from the UNMODIFIED reference.
+
+Needs the reference CPU build of SURVEY.md Appendix A (no-CUDA static libs + octvr_dump):
+    REFBUILD (default /tmp/refbuild) = cmake build dir, REFSRC (default /tmp/refsrc) = the source copy
+    it was configured from (identical to /root/reference except the nine CMake policy edits).
+Run here (build container); the fixtures it writes are committed, so neither the GPU box nor the
+test-suite ever needs /root/reference.
+
+    python oracle/refgen/make_golden.py
+"""
+import json
+import os
+import struct
+import subprocess
+import sys
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+GOLD = os.path.join(ROOT, "tests", "golden")
+B = os.environ.get("REFBUILD", "/tmp/refbuild")
+S = os.environ.get("REFSRC", "/tmp/refsrc")
+TMP = os.environ.get("GOLDTMP", "/tmp/gold")
+sys.path.insert(0, os.path.join(ROOT, "oracle"))
+
+MODS = "core imgproc stitching features2d flann calib3d imgcodecs videoio highgui ml objdetect octvr".split()
+LIBS = "-lopencv_octvr -lopencv_stitching -lopencv_calib3d -lopencv_features2d -lopencv_flann -lopencv_imgcodecs " \
+       "-lopencv_imgproc -lopencv_core".split()
+DEPTH = {0: np.uint8, 1: np.int8, 2: np.uint16, 3: np.int16, 4: np.int32, 5: np.float32, 6: np.float64}
+
+
+def compile_tool(name):
+    exe = os.path.join(TMP, name)
+    inc = ["-I" + B] + ["-I%s/modules/%s/include" % (S, m) for m in MODS]
+    cmd = ["/usr/bin/g++", "-std=c++11", "-O2", "-w"] + inc + [os.path.join(HERE, name + ".cpp"), "-o", exe,
+           "-L%s/lib" % B] + LIBS + ["-L%s/3rdparty/lib" % B, "-llibjpeg", "-llibpng", "-lzlib", "-lpthread", "-ldl"]
+    subprocess.check_call(cmd)
+    return exe
+
+
+def read_container(path):
+    out = {}
+    with open(path, "rb") as f:
+        while True:
+            h = f.read(4)
+            if not h:
+                break
+            nl, = struct.unpack("<I", h)
+            name = f.read(nl).decode()
+            depth, cn, rows, cols = struct.unpack("<IIQQ", f.read(24))
+            dt = np.dtype(DEPTH[depth])
+            a = np.frombuffer(f.read(rows * cols * cn * dt.itemsize), dtype=dt)
+            out[name] = a.reshape(rows, cols, cn) if cn > 1 else a.reshape(rows, cols)
+    return out
+
+
+def main():
+    os.makedirs(TMP, exist_ok=True)
+    import oracle as O
+    rigs_dir = os.path.join(GOLD, "rigs")
+    widths = json.load(open(os.path.join(rigs_dir, "widths.json")))
+    dump = os.path.join(B, "bin", "octvr_dump")
+    for rig, w in widths.items():
+        dat = os.path.join(TMP, rig + ".dat")
+        subprocess.check_call([dump, "-w", str(w), "-o", dat, os.path.join(rigs_dir, rig + ".json")],
+                              stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
+        t = O.load_dat(dat)
+        arrs = {"out_size": np.array(t.out_size, np.int64), "n": np.array(len(t.inputs))}
+        for i, d in enumerate(t.inputs):
+            arrs["roi%d" % i] = np.array(d["roi"], np.int64)
+            arrs["map1_%d" % i], arrs["map2_%d" % i], arrs["mask%d" % i] = d["map1"], d["map2"], d["mask"]
+            if d["vignette"] is not None:
+                arrs["vig%d" % i] = d["vignette"]
+            arrs["seam%d" % i] = t.seam_masks[i]
+        np.savez_compressed(os.path.join(GOLD, "tmpl_%s.npz" % rig), **arrs)
+        print("template", rig, t.out_size, len(t.inputs))
+
+    gbin = os.path.join(TMP, "golden.bin")
+    subprocess.check_call([compile_tool("ref_golden"), gbin])
+    np.savez_compressed(os.path.join(GOLD, "primitives.npz"), **read_container(gbin))
+    print("primitives ok")
+
+    st = compile_tool("ref_stitch")
+    cases = [  # name, rig, in_w, in_h, blend, gain, kind
+        ("rig3_feather5_gain_noise", "rig3", 320, 240, -5, 1, "noise"),
+        ("rig3_feather1_nogain_smooth", "rig3", 320, 240, -1, 0, "smooth"),
+        ("rig3_mb16_gain_smooth", "rig3", 320, 240, 16, 1, "smooth"),
+        ("rig3_mb8_nogain_noise", "rig3", 320, 240, 8, 0, "noise"),
+        ("rig3_noblend_noise", "rig3", 320, 240, 0, 0, "noise"),
+        ("rig2s_feather3_gain_smooth", "rig2s", 192, 108, -3, 1, "smooth"),
+        ("masks_feather2_gain_noise", "masks", 320, 240, -2, 1, "noise"),
+    ]
+    for name, rig, iw, ih, blend, gain, kind in cases:
+        out = os.path.join(TMP, name + ".bin")
+        subprocess.check_call([st, os.path.join(TMP, rig + ".dat"), str(iw), str(ih), str(blend), str(gain), kind, out],
+                              stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
+        c = read_container(out)
+        keep = {k: v for k, v in c.items() if not k.startswith("warped") or name.startswith("rig3_feather5")}
+        keep["meta"] = np.array([iw, ih, blend, gain, 1 if kind == "noise" else 0], np.int64)
+        np.savez_compressed(os.path.join(GOLD, "stitch_%s.npz" % name), **keep)
+        print("stitch", name, {k: v.shape for k, v in keep.items() if k.startswith("result") or k == "gains"})
+
+
+if __name__ == "__main__":
+    main()
