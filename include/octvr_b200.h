@@ -1,0 +1,144 @@
+/*
+ * octvr_b200.h -- C ABI of the B200-native octvr stitch path (liboctvr_b200.so).
+ *
+ * Drop-in boundary for the per-frame stitching hot path of blahgeek/OpenCV-octVR's
+ * modules/octvr.  Plain pointers and sizes only; no OpenCV, no torch types.  Every entry
+ * point names the reference interface it replaces (paths relative to the reference tree).
+ * All functions return OCTVR_OK (0) or a negative octvr_status; octvr_last_error() gives the
+ * message of the calling thread's last failure.  The C++ shim include/octvr.hpp turns these
+ * into the exception types the reference throws.
+ *
+ * There is NO CPU fallback: every compute entry point needs a CUDA device (sm_100a) and
+ * fails with OCTVR_ERR_CUDA otherwise.
+ *
+ * Conventions that differ between the reference's GPU and CPU paths follow the CPU path
+ * (SURVEY.md section 8c): pixel index u*W (not the texture's u*W-0.5), cv::remap's 1/32-px
+ * fixed-point bilinear, limited-range BT.601 integer colour, 16-bit CPU MultiBandBlender.
+ */
+#ifndef OCTVR_B200_H
+#define OCTVR_B200_H
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef int octvr_status;
+enum {
+    OCTVR_OK = 0,
+    OCTVR_ERR_INVALID = -1,   /* bad argument / shape (reference: CV_Assert -> cv::Exception) */
+    OCTVR_ERR_FORMAT = -2,    /* bad .dat magic / JSON (reference: throw std::string, template.cpp:30,33,53,262) */
+    OCTVR_ERR_CUDA = -3,      /* CUDA runtime failure or no device (reference: assert(false) without HAVE_CUDA, mapper.cpp:188,321) */
+    OCTVR_ERR_UNSUPPORTED = -4/* camera model used in an unsupported direction (reference: throw NotImplemented, camera.hpp:92-103) */
+};
+const char* octvr_last_error(void);
+const char* octvr_version(void);
+
+/* ------------------------------------------------------------------ templates
+ * vr::MapperTemplate (include/octvr.hpp:48-91, src/template.cpp). */
+typedef struct octvr_template octvr_template;
+
+/* explicit MapperTemplate(std::ifstream&) -- "VRv11" loader, template.cpp:258-314 */
+octvr_status octvr_template_load_dat(const void* bytes, size_t n, octvr_template** out);
+octvr_status octvr_template_load_file(const char* path, octvr_template** out);
+/* MapperTemplate::dump, template.cpp:206-256 (creates seam masks first if absent, like :207-208) */
+octvr_status octvr_template_dump_file(octvr_template* t, const char* path);
+
+/* MapperTemplate(to, to_opts, width, height) + add_input(...) per "inputs"/"overlays" entry
+ * (+ create_masks() when with_seam_masks) from the JSON schema apps/octvr/dump.cpp:71-127 reads.
+ * Map generation (template.cpp:46-153, camera.cpp:189-315, cameras/ *) runs as a CUDA kernel on
+ * `device` in f64.  width or height <= 0 -> derived from the output model's aspect ratio. */
+octvr_status octvr_template_build_json(const char* json, int width, int height, int use_roi,
+                                       int with_seam_masks, int device, octvr_template** out);
+
+/* Assemble a template from caller-made tables (what a reference-side shim holding a
+ * vr::MapperTemplate passes in): per input i roi = rois_xywh[4i..], map1/map2 (f32, roi_h x roi_w,
+ * normalised [0,1), -1 = no source), mask (u8), optional seam mask (u8, may be NULL array or NULL
+ * entries), optional vignette (f32 vig_h x vig_w, NULL = none).  Arrays are copied. */
+octvr_status octvr_template_from_arrays(int out_w, int out_h, int n_inputs, const int* rois_xywh,
+                                        const float* const* map1, const float* const* map2,
+                                        const uint8_t* const* mask, const uint8_t* const* seam_mask,
+                                        const float* const* vignette, int vig_w, int vig_h,
+                                        octvr_template** out);
+/* MapperTemplate::create_masks() with no images (DistanceSeamFinder), template.cpp:155-204 */
+octvr_status octvr_template_create_masks(octvr_template* t);
+
+octvr_status octvr_template_out_size(const octvr_template* t, int* w, int* h);
+int          octvr_template_num_inputs(const octvr_template* t);
+int          octvr_template_num_overlays(const octvr_template* t);
+/* index < num_inputs: inputs[index]; else overlay_inputs[index - num_inputs]. Host pointers, owned by t.
+ * seam_mask / vignette may come back NULL. */
+octvr_status octvr_template_input(const octvr_template* t, int index, int roi_xywh[4],
+                                  const float** map1, const float** map2, const uint8_t** mask,
+                                  const uint8_t** seam_mask, const float** vignette, int vig_wh[2]);
+void         octvr_template_destroy(octvr_template* t);
+
+/* --------------------------------------------------------------------- frames */
+/* 8-bit 4:2:0 frame as three plane pointers.  uv_pixel_stride 1 = planar (I420, and octvr's
+ * packed "U|V side by side under Y" layout of mapper.hpp:75-83: u = base + H*pitch, v = u + W/2,
+ * all pitches = W); 2 = semi-planar NV12 (v = u + 1).  Width and height must be even
+ * (async.cpp:44-46). */
+typedef struct octvr_frame {
+    uint8_t* y; uint8_t* u; uint8_t* v;
+    size_t y_pitch, u_pitch, v_pitch;
+    int uv_pixel_stride;
+} octvr_frame;
+
+/* --------------------------------------------------------------------- mapper
+ * vr::Mapper (src/mapper.hpp:29-95, src/mapper.cpp:47-323). */
+typedef struct octvr_mapper octvr_mapper;
+
+/* Mapper(const MapperTemplate&, std::vector<cv::Size> in_sizes, int blend, bool enable_gain_compensator,
+ *        cv::Size scale_output):  blend > 0 multiband width, < 0 feather border, 0 none (mapper.hpp:69-71);
+ * in_sizes_wh = {w0,h0,w1,h1,...} for inputs then overlays; scale_w/h = 0 keeps the template size. */
+octvr_status octvr_mapper_create(const octvr_template* t, const int* in_sizes_wh, int n_in,
+                                 int blend, int enable_gain, int scale_w, int scale_h,
+                                 int device, octvr_mapper** out);
+/* void Mapper::stitch(std::vector<GpuMat>& inputs, GpuMat& output, GpuMat& preview, std::vector<double> gains)
+ * mapper.cpp:193-323.  DEVICE pointers; asynchronous on `stream` (a cudaStream_t, NULL = default).
+ * gains = NULL computes gains from this frame (when enabled); otherwise n_gains predefined gains
+ * (async.cpp:75-86).  preview_rgb may be NULL. */
+octvr_status octvr_mapper_stitch(octvr_mapper* m, const octvr_frame* d_inputs, int n_inputs,
+                                 const octvr_frame* d_output, uint8_t* d_preview_rgb, size_t preview_pitch,
+                                 int preview_w, int preview_h, const double* gains, int n_gains, void* stream);
+/* Same with Mapper::stitch's packed single-plane layout (W x 1.5H, mapper.hpp:75-83). */
+octvr_status octvr_mapper_stitch_packed(octvr_mapper* m, const uint8_t* const* d_inputs, const size_t* in_pitch,
+                                        int n_inputs, uint8_t* d_output, size_t out_pitch,
+                                        const double* gains, int n_gains, void* stream);
+/* RGB888 result of the last stitch at template size (Mapper::result, mapper.hpp:66), device->host copy, synchronous. */
+octvr_status octvr_mapper_result_rgb(octvr_mapper* m, uint8_t* h_rgb, size_t pitch);
+/* std::vector<double> Mapper::gains() const, mapper.hpp:85-87.  Synchronises the last stitch's stream. */
+octvr_status octvr_mapper_gains(octvr_mapper* m, double* out, int n);
+/* Bookkeeping for the roofline: P = covered (pixel,camera) pairs, sum of ROI areas, bytes of the
+ * packed device tables one stitch reads, kernels launched per stitch. */
+octvr_status octvr_mapper_stats(const octvr_mapper* m, int64_t* pairs, int64_t* roi_area,
+                                int64_t* table_bytes, int* launches_per_stitch);
+/* time (ms, CUDA events on the stitch stream) the named stage of the LAST stitch took; stage =
+ * "convert" | "gain" | "blend" | "total".  Only valid when octvr_mapper_set_profiling(m, 1). */
+octvr_status octvr_mapper_set_profiling(octvr_mapper* m, int on);
+octvr_status octvr_mapper_stage_ms(octvr_mapper* m, const char* stage, float* ms);
+void         octvr_mapper_destroy(octvr_mapper* m);
+
+/* ---------------------------------------------------------------------- async
+ * vr::AsyncMultiMapper (include/octvr.hpp:103-121, src/async.cpp). Host planes in, host planes out. */
+typedef struct octvr_async octvr_async;
+
+/* AsyncMultiMapper::New(mts, in_sizes, out_size, blend_modes, gain_modes, output_regions, preview_size)
+ * async.cpp:195-350.  regions_xywh are fractions of the output frame (async.cpp:181-185). */
+octvr_status octvr_async_create(const octvr_template* const* tmpls, int n_out,
+                                const int* in_sizes_wh, int n_in, int out_w, int out_h,
+                                const int* blend_modes, const int* gain_modes, const double* regions_xywh,
+                                int preview_w, int preview_h, int device, octvr_async** out);
+/* push(inputs, output): HOST frames; caller keeps them alive and untouched until the matching pop
+ * returns (async.cpp:174-189). */
+octvr_status octvr_async_push(octvr_async* a, const octvr_frame* h_inputs, int n_inputs, const octvr_frame* h_output);
+/* pop(): blocks until the oldest pushed frame is complete (async.cpp:191-193). */
+octvr_status octvr_async_pop(octvr_async* a);
+octvr_status octvr_async_fps(octvr_async* a, double* fps);
+void         octvr_async_destroy(octvr_async* a);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,71 @@
+// csrc/kernels.cuh -- launch interfaces of the per-frame CUDA kernels (sm_100a).
+#pragma once
+#include "common.h"
+
+namespace ob {
+
+// ---- K_convert: planar/semi-planar 4:2:0 -> RGBX8888 (one u32 per source pixel), optional vignette ----
+struct CamSrc {
+    const uint8_t* y; const uint8_t* u; const uint8_t* v;
+    uint32_t y_pitch, u_pitch, v_pitch;
+    int uv_step;              // 1 planar, 2 NV12
+    int w, h;
+    uint32_t* rgbx;           // w*h, pitch = w pixels
+    const float* vignette;    // w*h f32 or null
+    int aligned4;             // y rows 4-byte aligned and w % 4 == 0
+};
+struct ConvertParams {
+    CamSrc cam[MAX_CAMS];
+    int n;
+    int block_start[MAX_CAMS + 1];   // prefix sum of CTAs per camera
+};
+void launch_convert(const ConvertParams& p, cudaStream_t s);
+
+// ---- K_gain: working-scale statistics, least-squares solve, exact gain tables ----
+struct GainCam {
+    int sx, sy, sw, sh;        // working-scale ROI (mapper.cpp:95-99)
+    uint32_t off;              // offset of this camera in smask / gcoord / sq
+};
+struct GainParams {
+    GainCam cam[MAX_CAMS];
+    const uint32_t* rgbx[MAX_CAMS];
+    int src_pitch[MAX_CAMS];
+    int n;
+    uint32_t total;            // sum of sw*sh
+    const uint8_t* smask;      // linearly resized masks (mapper.cpp:113-114)
+    const uint2* gcoord;       // table entry of the NEAREST-resized pixel (mapper.cpp:235-237)
+    int* sq;                   // out: r^2+g^2+b^2 per working-scale pixel, -1 where smask != 255
+    // pair reduction
+    int n_pairs, chunks;       // pairs (i<=j) x chunks CTAs
+    double* partial;           // [n_pairs*chunks][3] : count, sum_i, sum_j
+    unsigned int* ticket;
+    double* gains;             // [n] f64 (Mapper::gains())
+    float* gain_f32;           // [n] verified f32 multiplier
+    int* gain_flag;            // [n] 1 -> use the LUT
+    uint8_t* gain_lut;         // [n][256] exact sat_u8(rint(v*g)) in f64
+};
+void launch_gain_norms(const GainParams& p, cudaStream_t s);
+void launch_gain_reduce_solve(const GainParams& p, cudaStream_t s);
+void launch_gain_finalize(const GainParams& p, cudaStream_t s);   // gains[] already set (predefined gains)
+
+// ---- K_blend: fused remap (1/32-px fixed-point bilinear) + gain + weighted accumulate + normalise
+//      + RGB -> YUV 4:2:0 store ----
+struct BlendParams {
+    const uint32_t* rgbx[MAX_CAMS];
+    int src_pitch[MAX_CAMS];
+    const uint32_t* tile_job_start;   // [tiles+1]
+    const uint8_t* job_cam;           // [jobs]
+    const uint2* coords;              // [jobs*TILE_PX]
+    const float* weights;             // [jobs*TILE_PX]
+    int tiles_x, tiles_y, out_w, out_h;
+    uint8_t* oy; uint8_t* ou; uint8_t* ov;
+    uint32_t oy_pitch, ou_pitch, ov_pitch;
+    int uv_step;
+    uint8_t* rgb_out; uint32_t rgb_pitch;     // optional RGB888 result
+    const float* gain_f32; const int* gain_flag; const uint8_t* gain_lut;
+    int use_gain;
+    float inv_n;
+};
+void launch_blend(const BlendParams& p, cudaStream_t s);
+
+}  // namespace ob

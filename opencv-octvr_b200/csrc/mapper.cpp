@@ -1,0 +1,395 @@
+// csrc/mapper.cpp -- vr::Mapper (modules/octvr/src/mapper.{hpp,cpp}) behind the C ABI:
+// construction packs the template into tile-compacted device tables, stitch() launches the
+// per-frame kernels on the caller's stream.  No CPU fallback: a missing device is an error.
+#include "mapper.h"
+#include "prep.h"
+#include <algorithm>
+#include <cmath>
+#include <cstring>
+#include <memory>
+
+using namespace ob;
+
+namespace ob {
+
+template <class T> static T* dev_upload(const T* h, size_t n)
+{
+    T* d = nullptr;
+    OB_CUDA(cudaMalloc(&d, std::max<size_t>(n, 1) * sizeof(T)));
+    if (n) OB_CUDA(cudaMemcpy(d, h, n * sizeof(T), cudaMemcpyHostToDevice));
+    return d;
+}
+template <class T> static T* dev_alloc(size_t n, bool zero = false)
+{
+    T* d = nullptr;
+    OB_CUDA(cudaMalloc(&d, std::max<size_t>(n, 1) * sizeof(T)));
+    if (zero) OB_CUDA(cudaMemset(d, 0, std::max<size_t>(n, 1) * sizeof(T)));
+    return d;
+}
+
+// table entry for one ROI pixel: fixed-point source position -> tap offset, fractions, border bits
+static inline uint2 make_entry(int32_t sx, int32_t sy, int src_w, int src_h, bool valid)
+{
+    if (!valid) return make_uint2(0u, 0u);
+    int ix = sx >> 5, iy = sy >> 5;
+    ix = std::min(32767, std::max(-32768, ix));           // saturate_cast<short> (imgwarp.cpp:4394-4395)
+    iy = std::min(32767, std::max(-32768, iy));
+    const uint32_t fx = (uint32_t)(sx & 31), fy = (uint32_t)(sy & 31);
+    const bool x0 = ix >= 0 && ix < src_w, x1 = ix + 1 >= 0 && ix + 1 < src_w;
+    const bool y0 = iy >= 0 && iy < src_h, y1 = iy + 1 >= 0 && iy + 1 < src_h;
+    const uint32_t taps = (uint32_t)(x0 && y0) | ((uint32_t)(x1 && y0) << 1) | ((uint32_t)(x0 && y1) << 2) | ((uint32_t)(x1 && y1) << 3);
+    if (taps == 0) return make_uint2(0u, 0u);             // every tap outside: contributes 0, same as skipping
+    uint32_t flags = C_VALID;
+    if (taps != 15u) flags |= C_BORDER | (taps << C_TAP_SHIFT);
+    const int off = iy * src_w + ix;                      // may be "negative" for border entries; only inside taps are read
+    return make_uint2((uint32_t)off, fx | (fy << 5) | flags);
+}
+
+}  // namespace ob
+
+octvr_mapper::~octvr_mapper()
+{
+    cudaSetDevice(device);
+    for (auto p : d_rgbx) cudaFree(p);
+    for (auto p : d_vig) cudaFree(p);
+    cudaFree(d_tile_job_start); cudaFree(d_job_cam); cudaFree(d_coords); cudaFree(d_weights);
+    cudaFree(d_smask); cudaFree(d_gcoord); cudaFree(d_sq); cudaFree(d_partial); cudaFree(d_ticket);
+    cudaFree(d_gains); cudaFree(d_gain_f32); cudaFree(d_gain_flag); cudaFree(d_gain_lut); cudaFree(d_rgb);
+    if (h_gains) cudaFreeHost(h_gains);
+    for (auto& e : ev) if (e) cudaEventDestroy(e);
+    ob::multiband_destroy(mb);
+}
+
+static void build_mapper(octvr_mapper& m, const octvr_template& t, const int* in_sizes, int n_in,
+                         int blend, bool enable_gain, int scale_w, int scale_h)
+{
+    const int n = (int)t.inputs.size();
+    OB_CHECK(n >= 1 && n <= MAX_CAMS, "1..16 inputs supported");
+    OB_CHECK(n_in == n + (int)t.overlays.size(), "in_sizes must list every input and overlay");
+    if (!t.overlays.empty()) fail(OCTVR_ERR_UNSUPPORTED, "overlay inputs are not implemented yet");
+    if ((scale_w || scale_h) && (scale_w != t.out_w || scale_h != t.out_h))
+        fail(OCTVR_ERR_UNSUPPORTED, "scale_output != template size is not implemented yet");
+    if (n == 1) { enable_gain = false; blend = 0; }        // mapper.cpp:78-82
+    m.n = n; m.out_w = t.out_w; m.out_h = t.out_h; m.blend = blend; m.gain = enable_gain;
+    OB_CHECK(t.out_w % 2 == 0 && t.out_h % 2 == 0, "output size must be even (4:2:0)");
+    for (int i = 0; i < n; i++) {
+        int w = in_sizes[2 * i], h = in_sizes[2 * i + 1];
+        OB_CHECK(w > 0 && h > 0 && w % 2 == 0 && h % 2 == 0, "input sizes must be positive and even (async.cpp:44-46)");
+        OB_CHECK((int64_t)w * h < (int64_t)1 << 30, "input too large");
+        m.in_w.push_back(w); m.in_h.push_back(h);
+    }
+
+    // ---- per-camera source planes ----
+    for (int i = 0; i < n; i++) {
+        m.d_rgbx.push_back(dev_alloc<uint32_t>((size_t)m.in_w[i] * m.in_h[i] + 4));
+        float* dv = nullptr;
+        if (!t.inputs[i].vignette.empty()) {               // mapper.cpp:108-112
+            Img<float> v = resize_linear(t.inputs[i].vignette, m.in_w[i], m.in_h[i]);
+            dv = dev_upload(v.d.data(), v.d.size());
+        }
+        m.d_vig.push_back(dv);
+    }
+
+    // ---- fixed-point coordinates and blend weights per ROI pixel ----
+    std::vector<Img<int32_t>> sx(n), sy(n);
+    for (int i = 0; i < n; i++) quantise_map(t.inputs[i].map1, t.inputs[i].map2, m.in_w[i], m.in_h[i], sx[i], sy[i]);
+    m.pairs = 0; m.roi_area = 0;
+    for (int i = 0; i < n; i++) {
+        m.roi_area += (int64_t)t.inputs[i].roi.w * t.inputs[i].roi.h;
+        for (uint8_t v : t.inputs[i].mask.d) m.pairs += v != 0;
+    }
+
+    if (blend > 0) {
+        m.mb = ob::multiband_create(m, t, sx, sy);
+    } else {
+        std::vector<Img<float>> W = blend < 0 ? feather_weights(t.inputs, -blend) : overwrite_weights(t.inputs);
+        m.inv_n = blend < 0 ? (float)(1.0 / n) : 1.f;
+
+        // ---- tile-compacted tables ----
+        const int tiles_x = (t.out_w + TILE_W - 1) / TILE_W, tiles_y = (t.out_h + TILE_H - 1) / TILE_H;
+        const int ntiles = tiles_x * tiles_y;
+        m.tiles_x = tiles_x; m.tiles_y = tiles_y;
+        std::vector<uint8_t> used((size_t)ntiles * n, 0);  // [tile][cam]
+        for (int i = 0; i < n; i++) {
+            const TInput& in = t.inputs[i];
+            for (int y = 0; y < in.roi.h; y++) {
+                const uint8_t* mk = in.mask.row(y);
+                const float* wr = W[i].row(y);
+                const int ty = (in.roi.y + y) / TILE_H;
+                for (int x = 0; x < in.roi.w; x++)
+                    if (mk[x] && wr[x] != 0.f) used[((size_t)ty * tiles_x + (in.roi.x + x) / TILE_W) * n + i] = 1;
+            }
+        }
+        std::vector<uint32_t> job_start(ntiles + 1, 0);
+        std::vector<uint8_t> job_cam;
+        for (int tl = 0; tl < ntiles; tl++) {
+            job_start[tl] = (uint32_t)job_cam.size();
+            for (int i = 0; i < n; i++) if (used[(size_t)tl * n + i]) job_cam.push_back((uint8_t)i);
+        }
+        job_start[ntiles] = (uint32_t)job_cam.size();
+        const size_t njobs = job_cam.size();
+        OB_CHECK(njobs * TILE_PX < ((size_t)1 << 32), "table too large");
+        std::vector<uint2> coords(njobs * TILE_PX);
+        std::vector<float> weights(njobs * TILE_PX);
+        for (int tl = 0; tl < ntiles; tl++) {
+            const int tx = tl % tiles_x, ty = tl / tiles_x;
+            for (uint32_t j = job_start[tl]; j < job_start[tl + 1]; j++) {
+                const int i = job_cam[j];
+                const TInput& in = t.inputs[i];
+                for (int p = 0; p < TILE_PX; p++) {
+                    const int gx = tx * TILE_W + (p & (TILE_W - 1)), gy = ty * TILE_H + (p / TILE_W);
+                    const int lx = gx - in.roi.x, ly = gy - in.roi.y;
+                    uint2 e = make_uint2(0u, 0u);
+                    float w = 0.f;
+                    if (lx >= 0 && ly >= 0 && lx < in.roi.w && ly < in.roi.h && gx < t.out_w && gy < t.out_h) {
+                        w = W[i].row(ly)[lx];
+                        e = make_entry(sx[i].row(ly)[lx], sy[i].row(ly)[lx], m.in_w[i], m.in_h[i], in.mask.row(ly)[lx] != 0 && w != 0.f);
+                    }
+                    coords[(size_t)j * TILE_PX + p] = e;
+                    weights[(size_t)j * TILE_PX + p] = w;
+                }
+            }
+        }
+        m.njobs = njobs;
+        m.d_tile_job_start = dev_upload(job_start.data(), job_start.size());
+        m.d_job_cam = dev_upload(job_cam.data(), job_cam.size());
+        m.d_coords = dev_upload(coords.data(), coords.size());
+        m.d_weights = dev_upload(weights.data(), weights.size());
+        m.table_bytes = (int64_t)(coords.size() * sizeof(uint2) + weights.size() * sizeof(float) + job_cam.size() + job_start.size() * 4);
+    }
+
+    // ---- gain compensation tables (mapper.cpp:94-99,113-114,235-237) ----
+    if (enable_gain) {
+        const double ws = std::min(1.0, std::sqrt(0.1 * 1e6 / ((double)t.out_w * t.out_h)));
+        GainParams& g = m.gp;
+        memset(&g, 0, sizeof(g));
+        g.n = n;
+        std::vector<uint8_t> smask;
+        std::vector<uint2> gcoord;
+        uint32_t off = 0;
+        for (int i = 0; i < n; i++) {
+            const TInput& in = t.inputs[i];
+            GainCam& c = g.cam[i];
+            c.sx = (int)(in.roi.x * ws); c.sy = (int)(in.roi.y * ws); c.sw = (int)(in.roi.w * ws); c.sh = (int)(in.roi.h * ws);
+            OB_CHECK(c.sw > 0 && c.sh > 0, "working-scale ROI is empty");
+            c.off = off;
+            Img<uint8_t> sm = resize_linear(in.mask, c.sw, c.sh);
+            smask.insert(smask.end(), sm.d.begin(), sm.d.end());
+            const double ifx = 1. / ((double)c.sw / in.roi.w), ify = 1. / ((double)c.sh / in.roi.h);   // resizeNN
+            for (int dy = 0; dy < c.sh; dy++) {
+                const int ly = std::min((int)std::floor(dy * ify), in.roi.h - 1);
+                for (int dx = 0; dx < c.sw; dx++) {
+                    const int lx = std::min((int)std::floor(dx * ifx), in.roi.w - 1);
+                    gcoord.push_back(make_entry(sx[i].row(ly)[lx], sy[i].row(ly)[lx], m.in_w[i], m.in_h[i], in.mask.row(ly)[lx] != 0));
+                }
+            }
+            off += (uint32_t)c.sw * c.sh;
+        }
+        g.total = off;
+        g.n_pairs = n * (n + 1) / 2;
+        g.chunks = 8;
+        m.d_smask = dev_upload(smask.data(), smask.size());
+        m.d_gcoord = dev_upload(gcoord.data(), gcoord.size());
+        m.d_sq = dev_alloc<int>(off);
+        m.d_partial = dev_alloc<double>((size_t)g.n_pairs * g.chunks * 3, true);
+        m.d_ticket = dev_alloc<unsigned int>(1, true);
+        m.d_gains = dev_alloc<double>(MAX_CAMS, true);
+        m.d_gain_f32 = dev_alloc<float>(MAX_CAMS, true);
+        m.d_gain_flag = dev_alloc<int>(MAX_CAMS, true);
+        m.d_gain_lut = dev_alloc<uint8_t>(MAX_CAMS * 256, true);
+        OB_CUDA(cudaMallocHost(&m.h_gains, sizeof(double) * MAX_CAMS));
+        g.smask = m.d_smask; g.gcoord = m.d_gcoord; g.sq = m.d_sq; g.partial = m.d_partial; g.ticket = m.d_ticket;
+        g.gains = m.d_gains; g.gain_f32 = m.d_gain_f32; g.gain_flag = m.d_gain_flag; g.gain_lut = m.d_gain_lut;
+        for (int i = 0; i < n; i++) { g.rgbx[i] = m.d_rgbx[i]; g.src_pitch[i] = m.in_w[i]; }
+        m.table_bytes += (int64_t)(smask.size() + gcoord.size() * sizeof(uint2));
+    }
+    for (auto& e : m.ev) OB_CUDA(cudaEventCreate(&e));
+}
+
+static void check_frame(const octvr_frame& f, int w, int h, const char* what)
+{
+    OB_CHECK(f.y && f.u && f.v, what);
+    OB_CHECK(f.y_pitch >= (size_t)w && f.uv_pixel_stride >= 1 && f.uv_pixel_stride <= 2, what);
+    OB_CHECK(f.u_pitch >= (size_t)(w / 2) * f.uv_pixel_stride && f.v_pitch >= (size_t)(w / 2) * f.uv_pixel_stride, what);
+    (void)h;
+}
+
+static void do_stitch(octvr_mapper& m, const octvr_frame* in, int n_in, const octvr_frame* out,
+                      const double* gains, int n_gains, cudaStream_t s)
+{
+    OB_CHECK(n_in == m.n, "wrong number of input frames");           // mapper.cpp:208
+    OB_CUDA(cudaSetDevice(m.device));
+    for (int i = 0; i < m.n; i++) check_frame(in[i], m.in_w[i], m.in_h[i], "bad input frame");
+    if (out) check_frame(*out, m.out_w, m.out_h, "bad output frame");
+    OB_CHECK(out || m.keep_rgb, "no output requested");
+    if (m.profiling) OB_CUDA(cudaEventRecord(m.ev[0], s));
+
+    ConvertParams cp;
+    memset(&cp, 0, sizeof(cp));
+    cp.n = m.n;
+    int blocks = 0;
+    for (int i = 0; i < m.n; i++) {
+        CamSrc& c = cp.cam[i];
+        c.y = in[i].y; c.u = in[i].u; c.v = in[i].v;
+        c.y_pitch = (uint32_t)in[i].y_pitch; c.u_pitch = (uint32_t)in[i].u_pitch; c.v_pitch = (uint32_t)in[i].v_pitch;
+        c.uv_step = in[i].uv_pixel_stride; c.w = m.in_w[i]; c.h = m.in_h[i];
+        c.rgbx = m.d_rgbx[i]; c.vignette = m.d_vig[i];
+        c.aligned4 = ((uintptr_t)c.y % 4 == 0) && (c.y_pitch % 4 == 0) && (c.w % 4 == 0);
+        cp.block_start[i] = blocks;
+        blocks += ((c.w + 255) / 256) * ((c.h + 7) / 8);
+    }
+    cp.block_start[m.n] = blocks;
+    launch_convert(cp, s);
+    if (m.profiling) OB_CUDA(cudaEventRecord(m.ev[1], s));
+
+    if (m.gain) {
+        if (!gains) {
+            launch_gain_norms(m.gp, s);
+            launch_gain_reduce_solve(m.gp, s);
+        } else {
+            OB_CHECK(n_gains == m.n, "gains size must equal the number of inputs");
+            // the previous frame may still be reading h_gains: wait for it before overwriting
+            if (m.last_stream_valid) OB_CUDA(cudaStreamSynchronize(m.last_stream));
+            memcpy(m.h_gains, gains, sizeof(double) * m.n);
+            OB_CUDA(cudaMemcpyAsync(m.d_gains, m.h_gains, sizeof(double) * m.n, cudaMemcpyHostToDevice, s));
+            launch_gain_finalize(m.gp, s);
+        }
+    }
+    if (m.profiling) OB_CUDA(cudaEventRecord(m.ev[2], s));
+
+    if (m.keep_rgb && !m.d_rgb) m.d_rgb = dev_alloc<uint8_t>((size_t)m.out_w * m.out_h * 3, true);
+    if (m.mb) {
+        ob::multiband_stitch(m, out, s);
+    } else {
+        BlendParams bp;
+        memset(&bp, 0, sizeof(bp));
+        for (int i = 0; i < m.n; i++) { bp.rgbx[i] = m.d_rgbx[i]; bp.src_pitch[i] = m.in_w[i]; }
+        bp.tile_job_start = m.d_tile_job_start; bp.job_cam = m.d_job_cam; bp.coords = m.d_coords; bp.weights = m.d_weights;
+        bp.tiles_x = m.tiles_x; bp.tiles_y = m.tiles_y; bp.out_w = m.out_w; bp.out_h = m.out_h;
+        if (out) {
+            bp.oy = out->y; bp.ou = out->u; bp.ov = out->v;
+            bp.oy_pitch = (uint32_t)out->y_pitch; bp.ou_pitch = (uint32_t)out->u_pitch; bp.ov_pitch = (uint32_t)out->v_pitch;
+            bp.uv_step = out->uv_pixel_stride;
+        }
+        bp.rgb_out = m.keep_rgb ? m.d_rgb : nullptr; bp.rgb_pitch = (uint32_t)m.out_w * 3;
+        bp.gain_f32 = m.d_gain_f32; bp.gain_flag = m.d_gain_flag; bp.gain_lut = m.d_gain_lut;
+        bp.use_gain = m.gain ? 1 : 0;
+        bp.inv_n = m.inv_n;
+        launch_blend(bp, s);
+    }
+    if (m.profiling) OB_CUDA(cudaEventRecord(m.ev[3], s));
+    OB_CUDA(cudaGetLastError());
+    m.last_stream = s; m.last_stream_valid = true;
+}
+
+extern "C" {
+
+octvr_status octvr_mapper_create(const octvr_template* t, const int* in_sizes_wh, int n_in, int blend,
+                                 int enable_gain, int scale_w, int scale_h, int device, octvr_mapper** out)
+{
+    return guard([&] {
+        OB_CHECK(t && in_sizes_wh && out, "null argument");
+        int count = 0;
+        cudaError_t e = cudaGetDeviceCount(&count);
+        if (e != cudaSuccess || count <= 0 || device < 0 || device >= count)
+            fail(OCTVR_ERR_CUDA, "no usable CUDA device (the stitch path has no CPU fallback)");
+        OB_CUDA(cudaSetDevice(device));
+        std::unique_ptr<octvr_mapper> m(new octvr_mapper);
+        m->device = device;
+        build_mapper(*m, *t, in_sizes_wh, n_in, blend, enable_gain != 0, scale_w, scale_h);
+        *out = m.release();
+    });
+}
+
+octvr_status octvr_mapper_stitch(octvr_mapper* m, const octvr_frame* d_inputs, int n_inputs, const octvr_frame* d_output,
+                                 uint8_t* d_preview_rgb, size_t preview_pitch, int preview_w, int preview_h,
+                                 const double* gains, int n_gains, void* stream)
+{
+    return guard([&] {
+        OB_CHECK(m && d_inputs, "null argument");
+        (void)preview_pitch; (void)preview_w; (void)preview_h;
+        if (d_preview_rgb) fail(OCTVR_ERR_UNSUPPORTED, "preview output is not implemented yet");
+        do_stitch(*m, d_inputs, n_inputs, d_output, gains, n_gains, (cudaStream_t)stream);
+    });
+}
+
+octvr_status octvr_mapper_stitch_packed(octvr_mapper* m, const uint8_t* const* d_inputs, const size_t* in_pitch, int n_inputs,
+                                        uint8_t* d_output, size_t out_pitch, const double* gains, int n_gains, void* stream)
+{
+    return guard([&] {
+        OB_CHECK(m && d_inputs && in_pitch && d_output, "null argument");
+        OB_CHECK(n_inputs == m->n, "wrong number of input frames");
+        std::vector<octvr_frame> f(n_inputs);
+        for (int i = 0; i < n_inputs; i++) {              // mapper.cpp:222-226
+            uint8_t* b = const_cast<uint8_t*>(d_inputs[i]);
+            f[i].y = b; f[i].u = b + (size_t)m->in_h[i] * in_pitch[i]; f[i].v = f[i].u + m->in_w[i] / 2;
+            f[i].y_pitch = f[i].u_pitch = f[i].v_pitch = in_pitch[i]; f[i].uv_pixel_stride = 1;
+        }
+        octvr_frame o;                                     // mapper.cpp:296-302
+        o.y = d_output; o.u = d_output + (size_t)m->out_h * out_pitch; o.v = o.u + m->out_w / 2;
+        o.y_pitch = o.u_pitch = o.v_pitch = out_pitch; o.uv_pixel_stride = 1;
+        do_stitch(*m, f.data(), n_inputs, &o, gains, n_gains, (cudaStream_t)stream);
+    });
+}
+
+octvr_status octvr_mapper_set_keep_rgb(octvr_mapper* m, int on)
+{
+    return guard([&] { OB_CHECK(m, "null argument"); m->keep_rgb = on != 0; });
+}
+
+octvr_status octvr_mapper_result_rgb(octvr_mapper* m, uint8_t* h_rgb, size_t pitch)
+{
+    return guard([&] {
+        OB_CHECK(m && h_rgb && pitch >= (size_t)m->out_w * 3, "bad argument");
+        OB_CHECK(m->d_rgb, "no RGB result: call octvr_mapper_set_keep_rgb(m, 1) before stitching");
+        OB_CUDA(cudaSetDevice(m->device));
+        if (m->last_stream_valid) OB_CUDA(cudaStreamSynchronize(m->last_stream));
+        OB_CUDA(cudaMemcpy2D(h_rgb, pitch, m->d_rgb, (size_t)m->out_w * 3, (size_t)m->out_w * 3, m->out_h, cudaMemcpyDeviceToHost));
+    });
+}
+
+octvr_status octvr_mapper_gains(octvr_mapper* m, double* out, int n)
+{
+    return guard([&] {
+        OB_CHECK(m && out, "null argument");
+        if (!m->gain) { for (int i = 0; i < n; i++) out[i] = 1.0; return; }   // mapper.hpp:85-87 returns {} ; we report unity
+        OB_CHECK(n == m->n, "gains size must equal the number of inputs");
+        OB_CUDA(cudaSetDevice(m->device));
+        if (m->last_stream_valid) OB_CUDA(cudaStreamSynchronize(m->last_stream));
+        OB_CUDA(cudaMemcpy(out, m->d_gains, sizeof(double) * n, cudaMemcpyDeviceToHost));
+    });
+}
+
+octvr_status octvr_mapper_stats(const octvr_mapper* m, int64_t* pairs, int64_t* roi_area, int64_t* table_bytes, int* launches)
+{
+    return guard([&] {
+        OB_CHECK(m, "null argument");
+        if (pairs) *pairs = m->pairs;
+        if (roi_area) *roi_area = m->roi_area;
+        if (table_bytes) *table_bytes = m->table_bytes;
+        if (launches) *launches = m->mb ? ob::multiband_launches(*m) + 1 + (m->gain ? 2 : 0) : 2 + (m->gain ? 2 : 0);
+    });
+}
+
+octvr_status octvr_mapper_set_profiling(octvr_mapper* m, int on)
+{
+    return guard([&] { OB_CHECK(m, "null argument"); m->profiling = on != 0; });
+}
+
+octvr_status octvr_mapper_stage_ms(octvr_mapper* m, const char* stage, float* ms)
+{
+    return guard([&] {
+        OB_CHECK(m && stage && ms && m->profiling && m->last_stream_valid, "profiling not enabled or nothing stitched");
+        OB_CUDA(cudaSetDevice(m->device));
+        OB_CUDA(cudaEventSynchronize(m->ev[3]));
+        std::string s(stage);
+        int a = 0, b = 3;
+        if (s == "convert") { a = 0; b = 1; } else if (s == "gain") { a = 1; b = 2; } else if (s == "blend") { a = 2; b = 3; }
+        else if (s != "total") fail(OCTVR_ERR_INVALID, "unknown stage " + s);
+        OB_CUDA(cudaEventElapsedTime(ms, m->ev[a], m->ev[b]));
+    });
+}
+
+void octvr_mapper_destroy(octvr_mapper* m) { delete m; }
+
+}  // extern "C"

@@ -1,0 +1,53 @@
+// csrc/mapper.h -- state behind octvr_mapper (vr::Mapper, modules/octvr/src/mapper.hpp:29-95).
+#pragma once
+#include "common.h"
+#include "kernels.cuh"
+#include "template.h"
+
+namespace ob { struct Multiband; }
+
+struct octvr_mapper {
+    int device = 0;
+    int n = 0, out_w = 0, out_h = 0, blend = 0;
+    bool gain = false;
+    std::vector<int> in_w, in_h;
+    float inv_n = 1.f;
+    // per-camera RGBX planes (written by K_convert every frame) and optional full-size vignette maps
+    std::vector<uint32_t*> d_rgbx;
+    std::vector<float*> d_vig;
+    // tile-compacted tables (feather / no-blend)
+    int tiles_x = 0, tiles_y = 0;
+    size_t njobs = 0;
+    uint32_t* d_tile_job_start = nullptr;
+    uint8_t* d_job_cam = nullptr;
+    uint2* d_coords = nullptr;
+    float* d_weights = nullptr;
+    // gain compensation
+    ob::GainParams gp;
+    uint8_t* d_smask = nullptr; uint2* d_gcoord = nullptr; int* d_sq = nullptr; double* d_partial = nullptr;
+    unsigned int* d_ticket = nullptr; double* d_gains = nullptr; float* d_gain_f32 = nullptr;
+    int* d_gain_flag = nullptr; uint8_t* d_gain_lut = nullptr; double* h_gains = nullptr;
+    // optional RGB result (Mapper::result)
+    bool keep_rgb = false;
+    uint8_t* d_rgb = nullptr;
+    // multiband state (blend > 0)
+    ob::Multiband* mb = nullptr;
+    // bookkeeping
+    int64_t pairs = 0, roi_area = 0, table_bytes = 0;
+    bool profiling = false;
+    cudaEvent_t ev[4] = { nullptr, nullptr, nullptr, nullptr };
+    cudaStream_t last_stream = nullptr;
+    bool last_stream_valid = false;
+    ~octvr_mapper();
+};
+
+namespace ob {
+// multiband.cu
+Multiband* multiband_create(octvr_mapper& m, const octvr_template& t,
+                            const std::vector<Img<int32_t>>& sx, const std::vector<Img<int32_t>>& sy);
+void multiband_stitch(octvr_mapper& m, const octvr_frame* out, cudaStream_t s);
+int multiband_launches(const octvr_mapper& m);
+void multiband_destroy(Multiband* mb);
+}  // namespace ob
+
+extern "C" octvr_status octvr_mapper_set_keep_rgb(octvr_mapper* m, int on);

@@ -1,0 +1,29 @@
+// csrc/prep.h -- init-time host preparation (runs once per Mapper / template, like the reference's
+// own CPU init in blenders.cpp:531-572 and template.cpp:155-204).
+#pragma once
+#include "common.h"
+
+namespace ob {
+
+// cv::distanceTransform(mask, DIST_L2, 3): two-pass 3x3 chamfer in 16.16 fixed point
+// (imgproc/src/distransform.cpp:69-139).
+Img<float> chamfer_l2(const Img<uint8_t>& mask);
+// cv::resize(..., INTER_LINEAR) for 8UC1 (imgwarp.cpp:3224-3500,1387-1500) and 32FC1.
+Img<uint8_t> resize_linear(const Img<uint8_t>& src, int dw, int dh);
+Img<float> resize_linear(const Img<float>& src, int dw, int dh);
+// cv::pyrDown for 32FC1 (pyramids.cpp:849-964 incl. the SSE association of :143-185)
+Img<float> pyrdown_f32(const Img<float>& src);
+
+// FeatherGPUBlender ctor recipe (stitching/src/blenders.cpp:531-572): W_i = N*max(DT_i-border,0)/(1e-5+sum)
+std::vector<Img<float>> feather_weights(const std::vector<TInput>& in, int border);
+// blend == 0: masked copies in camera order (mapper.cpp:269-275) == weight 1 for the LAST covering camera
+std::vector<Img<float>> overwrite_weights(const std::vector<TInput>& in);
+// MapperTemplate::create_masks() without images (template.cpp:155-204, seam_finders.cpp:86-133)
+std::vector<Img<uint8_t>> distance_seam_masks(const std::vector<TInput>& in, int out_w);
+
+// cv::remap coordinate quantisation for planar f32 maps (imgwarp.cpp:4383-4442) applied to
+// fl32(map * size) (template.cpp:175-176).  Returns 1/32-px fixed point sx, sy.
+void quantise_map(const Img<float>& map1, const Img<float>& map2, int src_w, int src_h,
+                  Img<int32_t>& sx, Img<int32_t>& sy);
+
+}  // namespace ob
