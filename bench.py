@@ -1,0 +1,313 @@
+#!/usr/bin/env python
+"""
+bench.py -- octvr stitch hot path on B200: equirect output Mpix/s (BASELINE.json metric).
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--workload c2|c1|c3] [--impl ours|reference]
+
+A "step" is one stitched output frame: N camera frames (synthetic, device-resident ring of 8 distinct
+frames per camera) -> one equirectangular 4:2:0 frame through liboctvr_b200.so.  N=1 workload = C2
+(6 x 2704x1520 -> 4096x2048, gain + feather) -- the configuration BASELINE.json's target is quoted on.
+With --gpus N > 1 (torchrun, one rank per GPU) every rank stitches its own stream (frame sharding,
+SURVEY.md 8e: no data-path collective), value = frames of all ranks / max-over-ranks time.
+--impl reference times the CPU oracle port of the reference's CPU path on the host cores.
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+import numpy as np  # noqa: E402
+
+WORKLOADS = {
+    # name: (rig, blend, gain, description)
+    "c1": ("rig2", -1, True, "C1 2x1920x1080 fisheye -> 2048x1024 equirect, gain + feather(1)"),
+    "c2": ("rig6", -1, True, "C2 6x2704x1520 -> 4096x2048 equirect, gain + feather(1)"),
+    "c3": ("rig6", 64, True, "C3 6x2704x1520 -> 4096x2048 equirect, gain + 5-band multiband"),
+}
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        return json.load(open(p)).get("hbm_gbs", 6650.0), "measured"
+    return 6650.0, "fallback"
+
+
+class ClockSampler:
+    """nvidia-smi clocks/throttle reasons sampled during the timed region (B200_PROFILING.md)."""
+
+    def __init__(self, index):
+        self.rows = []
+        self.proc = None
+        q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
+            "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(index), "--query-gpu=" + q, "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm = [float(r[0]) for r in self.rows if len(r) >= 6 and r[0].replace(".", "").isdigit()]
+        mx = [float(r[1]) for r in self.rows if len(r) >= 6 and r[1].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = sorted({names[k] for r in self.rows if len(r) >= 6 for k in range(4) if r[2 + k].lower().startswith("active")})
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": reasons,
+                "samples": len(sm)}
+
+
+def alg_bytes(in_sizes, out_size, pairs, roi_area, blend):
+    """B_alg = I + T + O (+ M for multiband)."""
+    I = sum(w * h * 3 // 2 for w, h in in_sizes)
+    O_ = out_size[0] * out_size[1] * 3 // 2
+    if blend > 0:
+        M = 2 * (4 / 3) * roi_area * 4 + 2 * (4 / 3) * out_size[0] * out_size[1] * 6 + (4 / 3) * roi_area * 4
+        return I + 8 * pairs + O_ + M
+    return I + 12 * pairs + O_
+
+
+def make_template(vr, cfg, width, device):
+    """Tables come from the product's own GPU map generation (octvr_template_build_json)."""
+    return vr.MapperTemplate.from_json(cfg, width, -1, use_roi=True, with_seam_masks=True, device=device)
+
+
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    import octvr_b200 as vr
+    import util
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    torch.cuda.set_device(local)
+    rig, blend, gain, desc = WORKLOADS[args.workload]
+    cfg, width, in_size = util.named_rig(rig)
+    n = len(cfg["inputs"])
+    iw, ih = in_size
+    t0 = time.time()
+    tmpl = make_template(vr, cfg, width, local)
+    t_tmpl = time.time() - t0
+    m = vr.Mapper(tmpl, [in_size] * n, blend=blend, enable_gain_compensator=gain, device=local)
+    W, H = tmpl.out_size
+    st = m.stats()
+
+    RING = 8
+    ring = []
+    for k in range(RING):     # distinct noise frames, Mapper's packed layout, resident in HBM
+        fr = []
+        for c in range(n):
+            y, u, v = util.i420_planes(util.noise_frame(c, iw, ih, seed=1234 + 7919 * k + 104729 * rank), iw, ih)
+            fr.append(torch.from_numpy(np.concatenate([y, np.concatenate([u, v], 1)], 0)).cuda())
+        ring.append(fr)
+    out = torch.zeros((H * 3 // 2, W), dtype=torch.uint8, device="cuda")
+    stream = torch.cuda.current_stream()
+
+    def step(k):
+        m.stitch_packed(ring[k % RING], out, stream=stream)
+
+    for k in range(args.warmup):
+        step(k)
+    torch.cuda.synchronize()
+
+    # per-stage split (separate, untimed pass)
+    m.set_profiling(True)
+    stage = {"convert": [], "gain": [], "blend": []}
+    for k in range(10):
+        step(k)
+        for s in stage:
+            stage[s].append(m.stage_ms(s))
+    m.set_profiling(False)
+    torch.cuda.synchronize()
+
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    sampler = ClockSampler(local) if rank == 0 else None
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    for k in range(args.steps):
+        step(k)
+    e1.record(stream)
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1)
+    clocks = sampler.stop() if sampler else None
+    if world > 1:
+        tt = torch.tensor([ms], device="cuda")
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        ms = float(tt.item())
+
+    # end to end through the host-facing API (AsyncMultiMapper: host planes in, host planes out)
+    e2e = None
+    try:
+        e2e = run_e2e(vr, util, tmpl, cfg, in_size, blend, gain, local, min(args.steps, 60), world)
+    except vr.OctvrError as ex:
+        e2e = {"value": None, "unit": "Mpix/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0, "error": str(ex)}
+
+    if rank != 0:
+        return
+    ms_per_step = ms / args.steps
+    frames = args.steps * world
+    mpix = W * H * frames / (ms * 1e-3) / 1e6
+    B = alg_bytes([in_size] * n, (W, H), st["pairs"], st["roi_area"], blend)
+    peak, how = peaks()
+    # dominant kernel = the fused blend kernel; its algorithmic bytes = tables + output (the convert
+    # kernel owns the input bytes), duration from CUDA events on the launch stream
+    blend_ms = statistics.median(stage["blend"])
+    blend_bytes = (12 if blend <= 0 else 8) * st["pairs"] + W * H * 3 // 2
+    ach = blend_bytes / (blend_ms * 1e-3) / 1e9
+    line = {
+        "metric": "equirect output Mpix/s", "value": round(mpix, 1), "unit": "Mpix/s", "n_gpus": world,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(ms_per_step, 5), "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
+        "frames_per_s": round(frames / (ms * 1e-3), 1),
+        "config": {"workload": desc, "inputs": "%dx%dx%d I420 (octvr packed layout), ring of %d distinct noise frames per camera resident in HBM" % (n, iw, ih, RING),
+                   "output": "%dx%d 4:2:0" % (W, H), "l2": "working set per step (%.0f MB tables + %.0f MB frames) exceeds the 126 MB L2; no flush" % (st["table_bytes"] / 1e6, n * iw * ih * 1.5 / 1e6),
+                   "pairs_P": st["pairs"], "roi_area": st["roi_area"], "sharding": "one independent stream per GPU (frame sharding, no collective)" if world > 1 else "single GPU",
+                   "template_build_s": round(t_tmpl, 2)},
+        "alg_bytes_per_frame": int(B), "table_bytes_per_frame": st["table_bytes"],
+        "frac_of_hbm_roofline": {"whole_step_vs_measured_%.0f" % peak: round(B / (ms_per_step * 1e-3) / 1e9 / peak, 4),
+                                 "whole_step_vs_8000": round(B / (ms_per_step * 1e-3) / 1e9 / 8000.0, 4)},
+        "stage_ms": {k: round(statistics.median(v), 5) for k, v in stage.items()},
+        "roofline": {"bound": "hbm", "kernel": "k_blend", "achieved": round(ach, 1), "peak": peak, "peak_source": how, "unit": "GB/s",
+                     "frac": round(ach / peak, 4), "traffic": None,
+                     "alg_bytes_per_launch": int(blend_bytes), "ms_per_launch": round(blend_ms, 5)},
+        "gpu_launches": st["launches_per_stitch"] * args.steps,
+        "clocks": clocks, "e2e": e2e,
+    }
+    if not args.no_cpu:
+        line["cpu_baseline"] = cpu_baseline(args.workload, budget_s=20.0)
+    print(json.dumps(line))
+
+
+def run_e2e(vr, util, tmpl, cfg, in_size, blend, gain, device, steps, world):
+    """Same metric through AsyncMultiMapper.push/pop with HOST frames: H2D + stitch + D2H every step."""
+    import torch
+    n = len(cfg["inputs"])
+    iw, ih = in_size
+    W, H = tmpl.out_size
+    am = vr.AsyncMultiMapper([tmpl], [in_size] * n, (W, H), [blend], [0 if gain else -1], [(0.0, 0.0, 1.0, 1.0)], (0, 0), device=device)
+    RING = 4
+    hin = []
+    for k in range(RING):
+        fr = []
+        for c in range(n):
+            buf = torch.from_numpy(util.noise_frame(c, iw, ih, seed=99 + k)).pin_memory().numpy()
+            fr.append(util.i420_planes(buf, iw, ih))
+        hin.append(fr)
+    houts = [torch.zeros(W * H * 3 // 2, dtype=torch.uint8).pin_memory().numpy() for _ in range(RING)]
+    hout = [util.i420_planes(o, W, H) for o in houts]
+    depth = 3
+    for k in range(depth):      # warm-up / fill
+        am.push(hin[k % RING], hout[k % RING])
+    for k in range(depth):
+        am.pop()
+    t0 = time.perf_counter()
+    inflight = 0
+    for k in range(steps):
+        am.push(hin[k % RING], hout[k % RING])
+        inflight += 1
+        if inflight == depth:
+            am.pop()
+            inflight -= 1
+    while inflight:
+        am.pop()
+        inflight -= 1
+    dt = time.perf_counter() - t0
+    am.close()
+    if world > 1:
+        import torch.distributed as dist
+        tt = torch.tensor([dt], device="cuda")
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        dt = float(tt.item())
+    return {"value": round(W * H * steps * world / dt / 1e6, 1), "unit": "Mpix/s", "frames_per_s": round(steps * world / dt, 1),
+            "h2d_bytes_per_step": n * iw * ih * 3 // 2, "d2h_bytes_per_step": W * H * 3 // 2,
+            "api": "AsyncMultiMapper.push/pop (pinned host planes, 3 frames in flight)", "steps": steps}
+
+
+def cpu_baseline(workload, budget_s=20.0, steps=None, warmup=1):
+    """The reference's CPU path (oracle port: oracle/liborc.so, OpenMP on all host cores) on the same workload."""
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import oracle as O
+    import util
+    rig, blend, gain, desc = WORKLOADS[workload]
+    cfg, width, in_size = util.named_rig(rig)
+    n = len(cfg["inputs"])
+    iw, ih = in_size
+    ot = O.build_template(cfg, width)
+    so = O.StitchOracle(ot, [in_size] * n, blend=blend, enable_gain=gain)
+    frames = [util.i420_planes(util.noise_frame(c, iw, ih), iw, ih) for c in range(n)]
+    for _ in range(warmup):
+        so.stitch(frames)
+    times = []
+    t_start = time.perf_counter()
+    while True:
+        t0 = time.perf_counter()
+        so.stitch(frames)
+        times.append(time.perf_counter() - t0)
+        if steps is not None and len(times) >= steps:
+            break
+        if steps is None and (time.perf_counter() - t_start > budget_s or len(times) >= 10):
+            break
+    W, H = ot.out_size
+    med = statistics.median(times)
+    return {"value": round(W * H / med / 1e6, 2), "unit": "Mpix/s", "cores": O.num_threads(), "kind": "port",
+            "frames_per_s": round(1.0 / med, 3), "ms_per_frame": round(med * 1e3, 1),
+            "sample": "%d full frames of %s (median), after %d warm-up" % (len(times), desc, warmup)}
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    rig, blend, gain, desc = WORKLOADS[args.workload]
+    steps = max(1, min(args.steps, 8))
+    cb = cpu_baseline(args.workload, steps=steps, warmup=max(1, min(args.warmup, 2)))
+    line = {"impl": "reference", "metric": "equirect output Mpix/s", "value": cb["value"], "unit": "Mpix/s",
+            "n_gpus": int(os.environ.get("WORLD_SIZE", "1")), "steps": steps, "warmup": max(1, min(args.warmup, 2)),
+            "ms_per_step": cb["ms_per_frame"], "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8",
+            "data": "synthetic", "config": {"workload": desc, "note": "reference CPU path = oracle port (reference needs cmake + generated headers; unbuildable by the allowed recipe)"},
+            "cpu_baseline": cb, "e2e": {"value": cb["value"], "unit": "Mpix/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--warmup", type=int, default=20)
+    ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS))
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -62,8 +62,8 @@ struct TInput {
 // ---- device-side table layout ------------------------------------------------
 // Output is cut into TILE_W x TILE_H tiles; a "job" is one (tile, camera) pair that has at least
 // one contributing pixel.  Job j owns entries [j*TILE_PX, (j+1)*TILE_PX) of the coord and weight
-// streams, so one CTA reads its tables as dense, fully coalesced 2 KB + 1 KB chunks.
-constexpr int TILE_W = 32, TILE_H = 8, TILE_PX = TILE_W * TILE_H;
+// streams, so one CTA reads its tables as dense, fully coalesced 4 KB + 2 KB chunks.
+constexpr int TILE_W = 32, TILE_H = 16, TILE_PX = TILE_W * TILE_H;
 // coord.x : pixel offset (iy * src_pitch_px + ix) of the top-left bilinear tap in the camera's RGBX plane
 // coord.y : bits 0-4 fx, 5-9 fy (1/32 px fractions, imgwarp.cpp:4383-4442), 10 VALID, 11 BORDER (some tap
 //           outside the source), 12-15 per-tap inside bits (t00,t01,t10,t11)

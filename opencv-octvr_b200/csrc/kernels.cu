@@ -61,12 +61,6 @@ __device__ __forceinline__ float gain_apply_f32(float v, float g32)
 // ------------------------------------------------------------------------------------------------
 // K_convert
 // ------------------------------------------------------------------------------------------------
-__device__ __forceinline__ uint32_t yuv_to_rgbx(int Y, int ruv, int guv, int buv)
-{
-    const int yy = max(Y - 16, 0) * 1220542;
-    return (uint32_t)clamp255((yy + ruv) >> 20) | ((uint32_t)clamp255((yy + guv) >> 20) << 8) |
-           ((uint32_t)clamp255((yy + buv) >> 20) << 16);
-}
 __device__ __forceinline__ uint32_t vignette_rgbx(uint32_t p, float k)
 {
     // cudaarithm mul_mat.cu:198-213 : saturate_cast<uchar>(u8 * f32), round-to-nearest-even
@@ -76,60 +70,98 @@ __device__ __forceinline__ uint32_t vignette_rgbx(uint32_t p, float k)
     return (uint32_t)r | ((uint32_t)g << 8) | ((uint32_t)b << 16);
 }
 
-// one thread: 4 px x 2 rows (two chroma samples).  CTA = 64 x 4 threads = 256 x 8 px.
+// L2 residency hints: the RGBX planes (98 MB for the 6 x 2.7K rig) are written here and gathered by
+// K_blend right after -- keep them in the 126 MB L2 (evict_last); the table stream that K_blend reads
+// once per frame is marked evict_first so it does not push them out.
+__device__ __forceinline__ uint64_t policy_evict_last()
+{
+    uint64_t p;
+    asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(p));
+    return p;
+}
+__device__ __forceinline__ uint64_t policy_evict_first()
+{
+    uint64_t p;
+    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p));
+    return p;
+}
+__device__ __forceinline__ void st_v4_hint(uint32_t* ptr, uint4 v, uint64_t pol)
+{
+    asm volatile("st.global.L2::cache_hint.v4.u32 [%0], {%1, %2, %3, %4}, %5;" ::"l"(ptr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w), "l"(pol) : "memory");
+}
+
+__device__ __forceinline__ uint32_t yuv_px(uint32_t Y, int ruv, int guv, int buv)
+{
+    const int yy = max((int)Y - 16, 0) * 1220542;
+    return (uint32_t)__vimin_s32_relu((yy + ruv) >> 20, 255) | ((uint32_t)__vimin_s32_relu((yy + guv) >> 20, 255) << 8) |
+           ((uint32_t)__vimin_s32_relu((yy + buv) >> 20, 255) << 16);
+}
+
+// one thread: 8 px x 2 rows (four chroma samples).  CTA = 32 x 8 threads = 256 x 16 px.
+// grid = (ceil(max_w/256), ceil(max_h/16), cameras); CTAs outside a smaller camera exit at once.
 __global__ void __launch_bounds__(256) k_convert(const ConvertParams p)
 {
-    int ci = 0;
-    #pragma unroll 1
-    while (ci + 1 < p.n && (int)blockIdx.x >= p.block_start[ci + 1]) ci++;
-    const CamSrc& c = p.cam[ci];
-    const int lb = blockIdx.x - p.block_start[ci];
-    const int bx_n = (c.w + 255) >> 8;
-    const int bx = lb % bx_n, by = lb / bx_n;
-    const int x0 = (bx << 8) + (threadIdx.x << 2);
-    const int y0 = (by << 3) + (threadIdx.y << 1);
+    const CamSrc& c = p.cam[blockIdx.z];
+    const int x0 = (blockIdx.x << 8) + (threadIdx.x << 3);
+    const int y0 = (blockIdx.y << 4) + (threadIdx.y << 1);
     if (x0 >= c.w || y0 >= c.h) return;
-
+    const int w = c.w;
     const uint8_t* yr0 = c.y + (size_t)y0 * c.y_pitch + x0;
     const uint8_t* yr1 = yr0 + c.y_pitch;
     const uint8_t* ur = c.u + (size_t)(y0 >> 1) * c.u_pitch + (size_t)(x0 >> 1) * c.uv_step;
     const uint8_t* vr = c.v + (size_t)(y0 >> 1) * c.v_pitch + (size_t)(x0 >> 1) * c.uv_step;
-    uint32_t* o0 = c.rgbx + (size_t)y0 * c.w + x0;
-    uint32_t* o1 = o0 + c.w;
+    uint32_t* o0 = c.rgbx + (size_t)y0 * w + x0;
+    uint32_t* o1 = o0 + w;
+    const float* vg = c.vignette;
 
-    if (c.aligned4) {
-        const uint32_t ya = __ldg(reinterpret_cast<const uint32_t*>(yr0));
-        const uint32_t yb = __ldg(reinterpret_cast<const uint32_t*>(yr1));
-        uint32_t a[4], b[4];
+    if (c.aligned4 && x0 + 8 <= w) {
+        const uint2 ya = __ldg(reinterpret_cast<const uint2*>(yr0));
+        const uint2 yb = __ldg(reinterpret_cast<const uint2*>(yr1));
+        uint32_t ub, vb;                                   // four U and four V samples
+        if (c.uv_step == 1) {
+            ub = __ldg(reinterpret_cast<const uint32_t*>(ur));
+            vb = __ldg(reinterpret_cast<const uint32_t*>(vr));
+        } else {                                           // NV12: U0 V0 U1 V1 U2 V2 U3 V3
+            const uint2 uv = __ldg(reinterpret_cast<const uint2*>(ur));
+            ub = __byte_perm(uv.x, uv.y, 0x6420);
+            vb = __byte_perm(uv.x, uv.y, 0x7531);
+        }
+        uint32_t a[8], b[8];
         #pragma unroll
-        for (int k = 0; k < 2; k++) {
-            const int u = (int)__ldg(ur + k * c.uv_step) - 128, v = (int)__ldg(vr + k * c.uv_step) - 128;
+        for (int k = 0; k < 4; k++) {
+            const int u = (int)((ub >> (8 * k)) & 255u) - 128, v = (int)((vb >> (8 * k)) & 255u) - 128;
             const int ruv = (1 << 19) + 1673527 * v;
             const int guv = (1 << 19) - 852492 * v - 409993 * u;
             const int buv = (1 << 19) + 2116026 * u;
-            a[2 * k] = yuv_to_rgbx((ya >> (16 * k)) & 255, ruv, guv, buv);
-            a[2 * k + 1] = yuv_to_rgbx((ya >> (16 * k + 8)) & 255, ruv, guv, buv);
-            b[2 * k] = yuv_to_rgbx((yb >> (16 * k)) & 255, ruv, guv, buv);
-            b[2 * k + 1] = yuv_to_rgbx((yb >> (16 * k + 8)) & 255, ruv, guv, buv);
+            const uint32_t wa = k < 2 ? ya.x : ya.y, wb = k < 2 ? yb.x : yb.y;
+            const int sh = 16 * (k & 1);
+            a[2 * k] = yuv_px((wa >> sh) & 255u, ruv, guv, buv);
+            a[2 * k + 1] = yuv_px((wa >> (sh + 8)) & 255u, ruv, guv, buv);
+            b[2 * k] = yuv_px((wb >> sh) & 255u, ruv, guv, buv);
+            b[2 * k + 1] = yuv_px((wb >> (sh + 8)) & 255u, ruv, guv, buv);
         }
-        if (c.vignette) {
-            const float4 k0 = __ldg(reinterpret_cast<const float4*>(c.vignette + (size_t)y0 * c.w + x0));
-            const float4 k1 = __ldg(reinterpret_cast<const float4*>(c.vignette + (size_t)(y0 + 1) * c.w + x0));
-            a[0] = vignette_rgbx(a[0], k0.x); a[1] = vignette_rgbx(a[1], k0.y); a[2] = vignette_rgbx(a[2], k0.z); a[3] = vignette_rgbx(a[3], k0.w);
-            b[0] = vignette_rgbx(b[0], k1.x); b[1] = vignette_rgbx(b[1], k1.y); b[2] = vignette_rgbx(b[2], k1.z); b[3] = vignette_rgbx(b[3], k1.w);
+        if (vg) {
+            #pragma unroll
+            for (int k = 0; k < 8; k++) {
+                a[k] = vignette_rgbx(a[k], __ldg(vg + (size_t)y0 * w + x0 + k));
+                b[k] = vignette_rgbx(b[k], __ldg(vg + (size_t)(y0 + 1) * w + x0 + k));
+            }
         }
-        *reinterpret_cast<uint4*>(o0) = make_uint4(a[0], a[1], a[2], a[3]);
-        *reinterpret_cast<uint4*>(o1) = make_uint4(b[0], b[1], b[2], b[3]);
+        const uint64_t pol = policy_evict_last();
+        st_v4_hint(o0, make_uint4(a[0], a[1], a[2], a[3]), pol);
+        st_v4_hint(o0 + 4, make_uint4(a[4], a[5], a[6], a[7]), pol);
+        st_v4_hint(o1, make_uint4(b[0], b[1], b[2], b[3]), pol);
+        st_v4_hint(o1 + 4, make_uint4(b[4], b[5], b[6], b[7]), pol);
     } else {
-        for (int k = 0; k < 4 && x0 + k < c.w; k++) {
+        for (int k = 0; k < 8 && x0 + k < w; k++) {
             const int u = (int)__ldg(ur + (k >> 1) * c.uv_step) - 128, v = (int)__ldg(vr + (k >> 1) * c.uv_step) - 128;
             const int ruv = (1 << 19) + 1673527 * v;
             const int guv = (1 << 19) - 852492 * v - 409993 * u;
             const int buv = (1 << 19) + 2116026 * u;
-            uint32_t a = yuv_to_rgbx(__ldg(yr0 + k), ruv, guv, buv), b = yuv_to_rgbx(__ldg(yr1 + k), ruv, guv, buv);
-            if (c.vignette) {
-                a = vignette_rgbx(a, __ldg(c.vignette + (size_t)y0 * c.w + x0 + k));
-                b = vignette_rgbx(b, __ldg(c.vignette + (size_t)(y0 + 1) * c.w + x0 + k));
+            uint32_t a = yuv_px(__ldg(yr0 + k), ruv, guv, buv), b = yuv_px(__ldg(yr1 + k), ruv, guv, buv);
+            if (vg) {
+                a = vignette_rgbx(a, __ldg(vg + (size_t)y0 * w + x0 + k));
+                b = vignette_rgbx(b, __ldg(vg + (size_t)(y0 + 1) * w + x0 + k));
             }
             o0[k] = a; o1[k] = b;
         }
@@ -138,7 +170,7 @@ __global__ void __launch_bounds__(256) k_convert(const ConvertParams p)
 
 void launch_convert(const ConvertParams& p, cudaStream_t s)
 {
-    k_convert<<<p.block_start[p.n], dim3(64, 4), 0, s>>>(p);
+    k_convert<<<dim3(p.grid_x, p.grid_y, p.n), dim3(32, 8), 0, s>>>(p);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -256,13 +288,15 @@ __device__ void gain_tables(const GainParams& p)
     }
 }
 
-// CTA (pair, chunk): masked sums over the pair's overlap rectangle; the last CTA to finish reduces
-// the partials in a fixed order, solves for the gains and builds the gain tables.  256 threads.
+// CTA (pair, chunk): masked sums over the pair's overlap rectangle (32 x 8 threads striding the
+// rectangle, no divisions); the last CTA to finish reduces the partials in a fixed order (one thread
+// per pair), solves for the gains and builds the gain tables.
 __global__ void __launch_bounds__(256) k_gain_reduce_solve(const GainParams p)
 {
     __shared__ double red[3][8];
     __shared__ double Nm[MAX_CAMS * MAX_CAMS], Im[MAX_CAMS * MAX_CAMS], A[MAX_CAMS * MAX_CAMS], bb[MAX_CAMS];
     __shared__ bool is_last;
+    const int tid = threadIdx.x, lx = tid & 31, ly = tid >> 5;
     const int pair = blockIdx.x / p.chunks, chunk = blockIdx.x % p.chunks;
     int i = 0, rem = pair;
     while (rem >= p.n - i) { rem -= p.n - i; i++; }
@@ -271,23 +305,22 @@ __global__ void __launch_bounds__(256) k_gain_reduce_solve(const GainParams p)
     const int x_tl = max(a.sx, b.sx), y_tl = max(a.sy, b.sy);
     const int x_br = min(a.sx + a.sw, b.sx + b.sw), y_br = min(a.sy + a.sh, b.sy + b.sh);
     double cnt = 0, s1 = 0, s2 = 0;
-    if (x_tl < x_br && y_tl < y_br) {
-        const int rw = x_br - x_tl, area = rw * (y_br - y_tl);
-        for (int t = chunk * 256 + threadIdx.x; t < area; t += p.chunks * 256) {
-            const int x = x_tl + t % rw, y = y_tl + t / rw;
-            const int qa = p.sq[a.off + (y - a.sy) * a.sw + (x - a.sx)];
-            const int qb = p.sq[b.off + (y - b.sy) * b.sw + (x - b.sx)];
+    for (int y = y_tl + chunk * 8 + ly; y < y_br; y += p.chunks * 8) {
+        const int* ra = p.sq + a.off + (y - a.sy) * a.sw - a.sx;
+        const int* rb = p.sq + b.off + (y - b.sy) * b.sw - b.sx;
+        for (int x = x_tl + lx; x < x_br; x += 32) {
+            const int qa = __ldg(ra + x), qb = __ldg(rb + x);
             if (qa >= 0 && qb >= 0) { cnt += 1; s1 += sqrt((double)qa); s2 += sqrt((double)qb); }
         }
     }
     cnt = warp_sum(cnt); s1 = warp_sum(s1); s2 = warp_sum(s2);
-    if ((threadIdx.x & 31) == 0) { red[0][threadIdx.x >> 5] = cnt; red[1][threadIdx.x >> 5] = s1; red[2][threadIdx.x >> 5] = s2; }
+    if (lx == 0) { red[0][ly] = cnt; red[1][ly] = s1; red[2][ly] = s2; }
     __syncthreads();
-    if (threadIdx.x == 0) {
+    if (tid == 0) {
         double c = 0, u = 0, w = 0;
         for (int k = 0; k < 8; k++) { c += red[0][k]; u += red[1][k]; w += red[2][k]; }
         double* o = p.partial + (size_t)blockIdx.x * 3;
-        o[0] = c; o[1] = u; o[2] = w;
+        __stcg(o, c); __stcg(o + 1, u); __stcg(o + 2, w);
         __threadfence();
         const unsigned int t = atomicInc(p.ticket, gridDim.x - 1);   // wraps to 0: self-resetting
         is_last = (t == gridDim.x - 1);
@@ -295,29 +328,30 @@ __global__ void __launch_bounds__(256) k_gain_reduce_solve(const GainParams p)
     __syncthreads();
     if (!is_last) return;
     __threadfence();
-    if (threadIdx.x == 0) {
-        const int n = p.n;
-        for (int k = 0; k < n * n; k++) { Nm[k] = 0; Im[k] = 0; }
-        int pr = 0;
-        for (int ii = 0; ii < n; ii++)
-            for (int jj = ii; jj < n; jj++, pr++) {
-                const GainCam ca = p.cam[ii], cb = p.cam[jj];
-                const bool overlap = max(ca.sx, cb.sx) < min(ca.sx + ca.sw, cb.sx + cb.sw) &&
-                                     max(ca.sy, cb.sy) < min(ca.sy + ca.sh, cb.sy + cb.sh);
-                if (!overlap) continue;
-                double c = 0, u = 0, w = 0;
-                for (int k = 0; k < p.chunks; k++) {
-                    const volatile double* o = p.partial + ((size_t)pr * p.chunks + k) * 3;
-                    c += o[0]; u += o[1]; w += o[2];
-                }
-                const double nn = c > 1 ? c : 1;      // N = max(1, countNonZero)
-                Nm[ii * n + jj] = Nm[jj * n + ii] = nn;
-                Im[ii * n + jj] = u / nn;
-                Im[jj * n + ii] = w / nn;
+    const int n = p.n;
+    for (int k = tid; k < n * n; k += 256) { Nm[k] = 0; Im[k] = 0; }
+    __syncthreads();
+    if (tid < p.n_pairs) {
+        int ii = 0, r2 = tid;
+        while (r2 >= n - ii) { r2 -= n - ii; ii++; }
+        const int jj = ii + r2;
+        const GainCam ca = p.cam[ii], cb = p.cam[jj];
+        const bool overlap = max(ca.sx, cb.sx) < min(ca.sx + ca.sw, cb.sx + cb.sw) &&
+                             max(ca.sy, cb.sy) < min(ca.sy + ca.sh, cb.sy + cb.sh);
+        if (overlap) {                                   // otherwise N = I = 0 (exposure_compensate.cpp:105)
+            double c = 0, u = 0, w = 0;
+            for (int k = 0; k < p.chunks; k++) {
+                const double* o = p.partial + ((size_t)tid * p.chunks + k) * 3;
+                c += __ldcg(o); u += __ldcg(o + 1); w += __ldcg(o + 2);
             }
-        gain_solve(n, Nm, Im, A, bb, p.gains);
-        __threadfence();
+            const double nn = c > 1 ? c : 1;             // N = max(1, countNonZero)
+            Nm[ii * n + jj] = nn; Nm[jj * n + ii] = nn;
+            Im[ii * n + jj] = u / nn;
+            if (jj != ii) Im[jj * n + ii] = w / nn;
+        }
     }
+    __syncthreads();
+    if (tid == 0) { gain_solve(n, Nm, Im, A, bb, p.gains); __threadfence(); }
     __syncthreads();
     gain_tables(p);
 }
@@ -336,75 +370,159 @@ void launch_gain_finalize(const GainParams& p, cudaStream_t s) { k_gain_finalize
 
 // ------------------------------------------------------------------------------------------------
 // K_blend : one CTA per 32x8 output tile, one thread per output pixel.  For each camera that covers
-// the tile ("job") a thread reads its table entry (8 B coords + 4 B weight, coalesced), gathers four
-// RGBX taps, interpolates, applies the gain and accumulates trunc(v * W) in registers.  The pixel is
-// normalised, converted to YUV 4:2:0 and stored once -- no intermediate image touches DRAM.
+// the tile ("job") a thread reads its table entry (8 B coords + 4 B weight, coalesced, streamed past
+// L2 with evict_first), gathers four RGBX taps, interpolates, applies the gain and accumulates
+// trunc(v * W) in registers.  The pixel is normalised, converted to YUV 4:2:0 and stored once -- no
+// intermediate image touches DRAM.  Per-job constants (source plane, pitch, gain) are staged in
+// shared memory once per CTA.
 // ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(TILE_PX) k_blend(const BlendParams p)
-{
-    const int tile = blockIdx.x;
-    const int tx = tile % p.tiles_x, ty = tile / p.tiles_x;
-    const int tid = threadIdx.x;
-    const int x = tx * TILE_W + (tid & (TILE_W - 1)), y = ty * TILE_H + (tid >> 5);
-    const uint32_t j0 = __ldg(p.tile_job_start + tile), j1 = __ldg(p.tile_job_start + tile + 1);
+struct JobInfo { const uint32_t* src; int pitch; uint32_t gain; };   // gain: f32 bits, 0xFFFFFFFF -> use the LUT
+static_assert(sizeof(JobInfo) == 16, "JobInfo is read with one 128-bit shared load");
 
-    // accumulators hold sum of (2^23-biased) floor(v*W) bit patterns; the bias is removed at the end
-    uint32_t ar = 0, ag = 0, ab = 0, nacc = 0;
-    uint2 c = make_uint2(0, 0);
-    float w = 0.f;
-    if (j0 < j1) { c = __ldg(p.coords + (size_t)j0 * TILE_PX + tid); w = __ldg(p.weights + (size_t)j0 * TILE_PX + tid); }
-    for (uint32_t j = j0; j < j1; j++) {
-        const uint2 cc = c;
-        const float ww = w;
-        if (j + 1 < j1) {                                  // prefetch the next job's entry
-            c = __ldg(p.coords + (size_t)(j + 1) * TILE_PX + tid);
-            w = __ldg(p.weights + (size_t)(j + 1) * TILE_PX + tid);
+__device__ __forceinline__ uint2 ld_stream_u2(const uint2* ptr, uint64_t pol)
+{
+    uint2 v;
+    asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.v2.u32 {%0, %1}, [%2], %3;" : "=r"(v.x), "=r"(v.y) : "l"(ptr), "l"(pol));
+    return v;
+}
+__device__ __forceinline__ float ld_stream_f(const float* ptr, uint64_t pol)
+{
+    float v;
+    asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.f32 %0, [%1], %2;" : "=f"(v) : "l"(ptr), "l"(pol));
+    return v;
+}
+
+// accumulate one table entry into the pixel's sums
+__device__ __forceinline__ void blend_pair(const JobInfo& ji, uint2 cc, float ww, const uint8_t* __restrict__ lut_base,
+                                           uint32_t t00, uint32_t t01, uint32_t t10, uint32_t t11,
+                                           uint32_t& ar, uint32_t& ag, uint32_t& ab)
+{
+    int r, g, b;
+    bilerp_rgbx(t00, t01, t10, t11, cc.y & 31u, (cc.y >> 5) & 31u, r, g, b);
+    float rf = (float)r, gf = (float)g, bf = (float)b;
+    if (ji.gain != 0u) {
+        if (ji.gain != 0xFFFFFFFFu) {
+            const float g32 = __int_as_float((int)ji.gain);
+            rf = gain_apply_f32(rf, g32); gf = gain_apply_f32(gf, g32); bf = gain_apply_f32(bf, g32);
+        } else {
+            const uint8_t* lut = lut_base + (ji.pitch >> 24) * 256;
+            rf = (float)__ldg(lut + r); gf = (float)__ldg(lut + g); bf = (float)__ldg(lut + b);
         }
-        if (!(cc.y & C_VALID)) continue;
-        const int cam = __ldg(p.job_cam + j);
-        uint32_t t00, t01, t10, t11;
-        fetch_taps(p.rgbx[cam], p.src_pitch[cam], cc, t00, t01, t10, t11);
-        int r, g, b;
-        bilerp_rgbx(t00, t01, t10, t11, cc.y & 31u, (cc.y >> 5) & 31u, r, g, b);
-        float rf, gf, bf;
-        if (p.use_gain) {
-            if (__ldg(p.gain_flag + cam) == 0) {
-                const float g32 = __ldg(p.gain_f32 + cam);
-                rf = gain_apply_f32((float)r, g32); gf = gain_apply_f32((float)g, g32); bf = gain_apply_f32((float)b, g32);
-            } else {
-                const uint8_t* lut = p.gain_lut + cam * 256;
-                rf = (float)__ldg(lut + r); gf = (float)__ldg(lut + g); bf = (float)__ldg(lut + b);
-            }
-        } else { rf = (float)r; gf = (float)g; bf = (float)b; }
-        // (short)(v * W): f32 product, truncated (v*W >= 0 so floor == trunc)
-        ar += (uint32_t)__float_as_int(__fadd_rd(__fmul_rn(rf, ww), MAGIC_RD));
-        ag += (uint32_t)__float_as_int(__fadd_rd(__fmul_rn(gf, ww), MAGIC_RD));
-        ab += (uint32_t)__float_as_int(__fadd_rd(__fmul_rn(bf, ww), MAGIC_RD));
-        nacc++;
     }
-    if (x >= p.out_w || y >= p.out_h) return;
-    const uint32_t bias = nacc * 0x4B000000u;
-    // dst_16s.convertTo(CV_8UC3, 1.0/N): sat_u8(rint((float)acc * (float)(1/N)))
-    const int R = min(__float2int_rn(__fmul_rn((float)(int)(ar - bias), p.inv_n)), 255);
-    const int G = min(__float2int_rn(__fmul_rn((float)(int)(ag - bias), p.inv_n)), 255);
-    const int B = min(__float2int_rn(__fmul_rn((float)(int)(ab - bias), p.inv_n)), 255);
-    if (p.rgb_out) {
-        uint8_t* o = p.rgb_out + (size_t)y * p.rgb_pitch + 3 * x;
-        o[0] = (uint8_t)R; o[1] = (uint8_t)G; o[2] = (uint8_t)B;
+    // (short)(v * W): f32 product, truncated (v*W >= 0 so floor == trunc); 2^23 bias removed in the same add.
+    // Entries that do not contribute carry W = 0 and a harmless offset, so the loop needs no validity branch.
+    ar += (uint32_t)__float_as_int(__fadd_rd(__fmul_rn(rf, ww), MAGIC_RD)) - 0x4B000000u;
+    ag += (uint32_t)__float_as_int(__fadd_rd(__fmul_rn(gf, ww), MAGIC_RD)) - 0x4B000000u;
+    ab += (uint32_t)__float_as_int(__fadd_rd(__fmul_rn(bf, ww), MAGIC_RD)) - 0x4B000000u;
+}
+
+// dst_16s.convertTo(CV_8UC3, 1.0/N): sat_u8(rint((float)acc * (float)(1/N))), packed R | G<<8 | B<<16
+__device__ __forceinline__ uint32_t normalise_px(uint32_t ar, uint32_t ag, uint32_t ab, float inv_n)
+{
+    const int R = min(__float2int_rn(__fmul_rn((float)(int)ar, inv_n)), 255);
+    const int G = min(__float2int_rn(__fmul_rn((float)(int)ag, inv_n)), 255);
+    const int B = min(__float2int_rn(__fmul_rn((float)(int)ab, inv_n)), 255);
+    return (uint32_t)R | ((uint32_t)G << 8) | ((uint32_t)B << 16);
+}
+__device__ __forceinline__ uint32_t luma(uint32_t px)
+{
+    return (269484u * (px & 255u) + 528482u * ((px >> 8) & 255u) + 102760u * ((px >> 16) & 255u) + (1u << 19) + (16u << 20)) >> 20;
+}
+
+// CTA = one 32 x 16 output tile, 256 threads, TWO pixels per thread (rows r and r+8) so every job
+// iteration keeps two independent table->gather chains in flight; the next job's table entries are
+// prefetched before the current job's arithmetic.
+__global__ void __launch_bounds__(256) k_blend(const BlendParams p)
+{
+    __shared__ JobInfo s_job[MAX_CAMS];
+    __shared__ uint32_t s_px[TILE_H][TILE_W + 1];
+    const int tid = threadIdx.x, lx = tid & 31, ly = tid >> 5;
+    const int tile = blockIdx.y * p.tiles_x + blockIdx.x;
+    const uint32_t j0 = __ldg(p.tile_job_start + tile);
+    const int nj = (int)(__ldg(p.tile_job_start + tile + 1) - j0);
+    if (tid < nj) {
+        const int cam = __ldg(p.job_cam + j0 + tid);
+        JobInfo ji;
+        ji.src = p.rgbx[cam]; ji.pitch = p.src_pitch[cam];
+        ji.gain = 0xFFFFFFFFu;
+        if (!p.use_gain) ji.gain = 0u;
+        else if (__ldg(p.gain_flag + cam) == 0) ji.gain = (uint32_t)__float_as_int(__ldg(p.gain_f32 + cam));
+        if (ji.gain == 0xFFFFFFFFu) ji.pitch |= cam << 24;          // LUT path needs the camera id (pitch < 2^24)
+        s_job[tid] = ji;
     }
+    __syncthreads();
+
+    const uint64_t pol = policy_evict_first();
+    const uint2* cp = p.coords + (size_t)j0 * TILE_PX + tid;
+    const float* wp = p.weights + (size_t)j0 * TILE_PX + tid;
+    uint32_t ar0 = 0, ag0 = 0, ab0 = 0, ar1 = 0, ag1 = 0, ab1 = 0;      // sums of floor(v*W) for the two pixels
+    uint2 c0 = make_uint2(0, 0), c1 = make_uint2(0, 0);
+    float w0 = 0.f, w1 = 0.f;
+    if (nj > 0) {
+        c0 = ld_stream_u2(cp, pol); c1 = ld_stream_u2(cp + 256, pol);
+        w0 = ld_stream_f(wp, pol); w1 = ld_stream_f(wp + 256, pol);
+    }
+    #pragma unroll 1
+    for (int k = 0; k < nj; k++) {
+        const JobInfo ji = s_job[k];
+        const uint2 a0 = c0, a1 = c1;
+        const float v0 = w0, v1 = w1;
+        uint32_t t00, t01, t10, t11, u00, u01, u10, u11;
+        fetch_taps(ji.src, ji.pitch & 0xFFFFFF, a0, t00, t01, t10, t11);
+        fetch_taps(ji.src, ji.pitch & 0xFFFFFF, a1, u00, u01, u10, u11);
+        if (k + 1 < nj) {
+            cp += TILE_PX; wp += TILE_PX;
+            c0 = ld_stream_u2(cp, pol); c1 = ld_stream_u2(cp + 256, pol);
+            w0 = ld_stream_f(wp, pol); w1 = ld_stream_f(wp + 256, pol);
+        }
+        blend_pair(ji, a0, v0, p.gain_lut, t00, t01, t10, t11, ar0, ag0, ab0);
+        blend_pair(ji, a1, v1, p.gain_lut, u00, u01, u10, u11, ar1, ag1, ab1);
+    }
+    const uint32_t px0 = normalise_px(ar0, ag0, ab0, p.inv_n), px1 = normalise_px(ar1, ag1, ab1, p.inv_n);
+    s_px[ly][lx] = px0;
+    s_px[ly + 8][lx] = px1;
+    __syncthreads();
+
+    // ---- store phase: threads re-mapped so each writes packed, coalesced words ----
+    const int tx0 = blockIdx.x * TILE_W, ty0 = blockIdx.y * TILE_H;
     if (p.oy) {
-        p.oy[(size_t)y * p.oy_pitch + x] = (uint8_t)((269484 * R + 528482 * G + 102760 * B + (1 << 19) + (16 << 20)) >> 20);
-        if (((x | y) & 1) == 0) {
-            const size_t co = (size_t)(x >> 1) * p.uv_step;
-            p.ou[(size_t)(y >> 1) * p.ou_pitch + co] = (uint8_t)((-155188 * R - 305135 * G + 460324 * B + (1 << 19) + (128 << 20)) >> 20);
-            p.ov[(size_t)(y >> 1) * p.ov_pitch + co] = (uint8_t)((460324 * R - 385875 * G - 74448 * B + (1 << 19) + (128 << 20)) >> 20);
+        if (tid < 128) {                         // luma: 16 rows x 8 groups of 4 px -> one 32-bit store each
+            const int row = tid >> 3, gx = (tid & 7) << 2;
+            const int x = tx0 + gx, y = ty0 + row;
+            if (y < p.out_h && x < p.out_w) {
+                const uint32_t yv = luma(s_px[row][gx]) | (luma(s_px[row][gx + 1]) << 8) | (luma(s_px[row][gx + 2]) << 16) | (luma(s_px[row][gx + 3]) << 24);
+                uint8_t* o = p.oy + (size_t)y * p.oy_pitch + x;
+                if (x + 3 < p.out_w && (((uintptr_t)o) & 3) == 0) *reinterpret_cast<uint32_t*>(o) = yv;
+                else for (int k = 0; k < 4 && x + k < p.out_w; k++) o[k] = (uint8_t)(yv >> (8 * k));
+            }
+        } else {                                 // chroma: 8 rows x 16 samples, top-left pixel of each 2x2
+            const int t = tid - 128, row = t >> 4, cx = t & 15;
+            const int x = tx0 + 2 * cx, y = ty0 + 2 * row;
+            if (y < p.out_h && x < p.out_w) {
+                const uint32_t px = s_px[2 * row][2 * cx];
+                const int R = px & 255u, G = (px >> 8) & 255u, B = (px >> 16) & 255u;
+                const size_t co = (size_t)(x >> 1) * p.uv_step;
+                p.ou[(size_t)(y >> 1) * p.ou_pitch + co] = (uint8_t)((-155188 * R - 305135 * G + 460324 * B + (1 << 19) + (128 << 20)) >> 20);
+                p.ov[(size_t)(y >> 1) * p.ov_pitch + co] = (uint8_t)((460324 * R - 385875 * G - 74448 * B + (1 << 19) + (128 << 20)) >> 20);
+            }
+        }
+    }
+    if (p.rgb_out) {
+        #pragma unroll
+        for (int h = 0; h < 2; h++) {
+            const int x = tx0 + lx, y = ty0 + ly + 8 * h;
+            if (x < p.out_w && y < p.out_h) {
+                const uint32_t px = h ? px1 : px0;
+                uint8_t* o = p.rgb_out + (size_t)y * p.rgb_pitch + 3 * x;
+                o[0] = (uint8_t)px; o[1] = (uint8_t)(px >> 8); o[2] = (uint8_t)(px >> 16);
+            }
         }
     }
 }
 
 void launch_blend(const BlendParams& p, cudaStream_t s)
 {
-    k_blend<<<p.tiles_x * p.tiles_y, TILE_PX, 0, s>>>(p);
+    k_blend<<<dim3(p.tiles_x, p.tiles_y), 256, 0, s>>>(p);
 }
 
 }  // namespace ob

@@ -17,7 +17,7 @@ struct CamSrc {
 struct ConvertParams {
     CamSrc cam[MAX_CAMS];
     int n;
-    int block_start[MAX_CAMS + 1];   // prefix sum of CTAs per camera
+    int grid_x, grid_y;              // ceil(max w / 256), ceil(max h / 16)
 };
 void launch_convert(const ConvertParams& p, cudaStream_t s);
 

@@ -28,6 +28,8 @@ template <class T> static T* dev_alloc(size_t n, bool zero = false)
 }
 
 // table entry for one ROI pixel: fixed-point source position -> tap offset, fractions, border bits
+// Entries that do not contribute are {offset 0, no flags}: the blend kernel runs them branch-free with
+// weight 0 (reads source pixel 0, adds floor(v*0) = 0); the gain kernel checks C_VALID.
 static inline uint2 make_entry(int32_t sx, int32_t sy, int src_w, int src_h, bool valid)
 {
     if (!valid) return make_uint2(0u, 0u);
@@ -145,6 +147,7 @@ static void build_mapper(octvr_mapper& m, const octvr_template& t, const int* in
                         w = W[i].row(ly)[lx];
                         e = make_entry(sx[i].row(ly)[lx], sy[i].row(ly)[lx], m.in_w[i], m.in_h[i], in.mask.row(ly)[lx] != 0 && w != 0.f);
                     }
+                    if (!(e.y & C_VALID)) w = 0.f;
                     coords[(size_t)j * TILE_PX + p] = e;
                     weights[(size_t)j * TILE_PX + p] = w;
                 }
@@ -187,7 +190,7 @@ static void build_mapper(octvr_mapper& m, const octvr_template& t, const int* in
         }
         g.total = off;
         g.n_pairs = n * (n + 1) / 2;
-        g.chunks = 8;
+        g.chunks = 16;
         m.d_smask = dev_upload(smask.data(), smask.size());
         m.d_gcoord = dev_upload(gcoord.data(), gcoord.size());
         m.d_sq = dev_alloc<int>(off);
@@ -227,18 +230,19 @@ static void do_stitch(octvr_mapper& m, const octvr_frame* in, int n_in, const oc
     ConvertParams cp;
     memset(&cp, 0, sizeof(cp));
     cp.n = m.n;
-    int blocks = 0;
     for (int i = 0; i < m.n; i++) {
         CamSrc& c = cp.cam[i];
         c.y = in[i].y; c.u = in[i].u; c.v = in[i].v;
         c.y_pitch = (uint32_t)in[i].y_pitch; c.u_pitch = (uint32_t)in[i].u_pitch; c.v_pitch = (uint32_t)in[i].v_pitch;
         c.uv_step = in[i].uv_pixel_stride; c.w = m.in_w[i]; c.h = m.in_h[i];
         c.rgbx = m.d_rgbx[i]; c.vignette = m.d_vig[i];
-        c.aligned4 = ((uintptr_t)c.y % 4 == 0) && (c.y_pitch % 4 == 0) && (c.w % 4 == 0);
-        cp.block_start[i] = blocks;
-        blocks += ((c.w + 255) / 256) * ((c.h + 7) / 8);
+        const bool chroma_ok = c.uv_step == 1
+            ? ((uintptr_t)c.u % 4 == 0 && (uintptr_t)c.v % 4 == 0 && c.u_pitch % 4 == 0 && c.v_pitch % 4 == 0)
+            : ((uintptr_t)c.u % 8 == 0 && c.u_pitch % 8 == 0 && c.v == c.u + 1);
+        c.aligned4 = ((uintptr_t)c.y % 8 == 0) && (c.y_pitch % 8 == 0) && (c.w % 4 == 0) && chroma_ok;
+        cp.grid_x = std::max(cp.grid_x, (c.w + 255) / 256);
+        cp.grid_y = std::max(cp.grid_y, (c.h + 15) / 16);
     }
-    cp.block_start[m.n] = blocks;
     launch_convert(cp, s);
     if (m.profiling) OB_CUDA(cudaEventRecord(m.ev[1], s));
 

@@ -35,14 +35,18 @@ def smooth_frame(cam, w, h):
     yc = np.arange(h // 2)[:, None]
     U = np.clip(np.rint(128 + 40 * np.sin(2 * math.pi * xc / (w // 2) * 2) + 0 * yc), 0, 255).astype(np.uint8)
     V = np.clip(np.rint(128 - 40 * np.cos(2 * math.pi * yc / (h // 2) * 3) + 0 * xc), 0, 255).astype(np.uint8)
-    f[h:h + h // 4] = U.reshape(h // 4, w)
-    f[h + h // 4:] = V.reshape(h // 4, w)
+    a = f.reshape(-1)
+    q = (w // 2) * (h // 2)
+    a[w * h:w * h + q] = U.ravel()
+    a[w * h + q:] = V.ravel()
     return f
 
 
 def i420_planes(f, w, h):
     """standard I420 (1.5h, w) buffer -> y (h,w), u (h/2,w/2), v (h/2,w/2) views."""
-    return f[:h], f[h:h + h // 4].reshape(h // 2, w // 2), f[h + h // 4:].reshape(h // 2, w // 2)
+    a = f.reshape(-1)
+    q = (w // 2) * (h // 2)
+    return a[:w * h].reshape(h, w), a[w * h:w * h + q].reshape(h // 2, w // 2), a[w * h + q:w * h + 2 * q].reshape(h // 2, w // 2)
 
 
 def rig_json(name):
