@@ -176,29 +176,6 @@ void launch_convert(const ConvertParams& p, cudaStream_t s)
 // ------------------------------------------------------------------------------------------------
 // K_gain
 // ------------------------------------------------------------------------------------------------
-// one thread per working-scale pixel of every camera: remap that one pixel, store r^2+g^2+b^2
-__global__ void __launch_bounds__(256) k_gain_norms(const GainParams p)
-{
-    const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
-    if (t >= p.total) return;
-    int ci = 0;
-    #pragma unroll 1
-    while (ci + 1 < p.n && t >= p.cam[ci + 1].off) ci++;
-    int out = -1;
-    if (__ldg(p.smask + t) == 255) {               // CPU compensator's intersect rule (exposure_compensate.cpp:71-78,112)
-        out = 0;
-        const uint2 c = __ldg(p.gcoord + t);
-        if (c.y & C_VALID) {
-            uint32_t t00, t01, t10, t11;
-            fetch_taps(p.rgbx[ci], p.src_pitch[ci], c, t00, t01, t10, t11);
-            int r, g, b;
-            bilerp_rgbx(t00, t01, t10, t11, c.y & 31u, (c.y >> 5) & 31u, r, g, b);
-            out = r * r + g * g + b * b;
-        }
-    }
-    p.sq[t] = out;
-}
-
 __device__ __forceinline__ double warp_sum(double v)
 {
     #pragma unroll
@@ -206,144 +183,232 @@ __device__ __forceinline__ double warp_sum(double v)
     return v;
 }
 
-// exposure_compensate.cpp:138-153 + core LU / closed forms (matrix_decomp.cpp:52-109, lapack.cpp:1080-1170)
-__device__ void gain_solve(int n, const double* Nm, const double* Im, double* A, double* b, double* g)
+// exposure_compensate.cpp:138-153 (normal equations) + cv::solve: closed forms for n <= 3 (core/src/lapack.cpp:
+// 1080-1170), LU with partial pivoting otherwise (matrix_decomp.cpp:52-109).  Executed by ONE WARP: lane = row
+// while building, lane = column during elimination.  Multiplies and adds are kept separate (__dmul_rn /
+// __dadd_rn, no FMA contraction) so every element sees the same operation sequence as the x86 reference.
+// Aug is the n x (n+1) augmented matrix [A | b] in shared memory.
+__device__ void gain_solve_warp(int n, const double* Nm, const double* Im, double* Aug, double* g)
 {
+    const int lane = threadIdx.x & 31, ld = n + 1;
     const double alpha = 0.01, beta = 100;
-    for (int i = 0; i < n; i++) { b[i] = 0; for (int j = 0; j < n; j++) A[i * n + j] = 0; }
-    for (int i = 0; i < n; i++)
+    if (lane < n) {
+        const int i = lane;
+        double bi = 0, aii = 0;
         for (int j = 0; j < n; j++) {
-            b[i] += beta * Nm[i * n + j];
-            A[i * n + i] += beta * Nm[i * n + j];
-            if (j == i) continue;
-            A[i * n + i] += 2 * alpha * Im[i * n + j] * Im[i * n + j] * Nm[i * n + j];
-            A[i * n + j] -= 2 * alpha * Im[i * n + j] * Im[j * n + i] * Nm[i * n + j];
+            const double nij = Nm[i * n + j];
+            bi = __dadd_rn(bi, __dmul_rn(beta, nij));
+            aii = __dadd_rn(aii, __dmul_rn(beta, nij));
+            double aij = 0;
+            if (j != i) {
+                const double iij = Im[i * n + j], iji = Im[j * n + i];
+                aii = __dadd_rn(aii, __dmul_rn(__dmul_rn(__dmul_rn(2 * alpha, iij), iij), nij));
+                aij = -__dmul_rn(__dmul_rn(__dmul_rn(2 * alpha, iij), iji), nij);
+                Aug[i * ld + j] = aij;
+            }
         }
+        Aug[i * ld + i] = aii;
+        Aug[i * ld + n] = bi;
+    }
+    __syncwarp();
+    #define S(i, j) Aug[(i) * ld + (j)]
+    #define Bv(i) Aug[(i) * ld + n]
+    #define MUL __dmul_rn
+    #define SUB(a, b) __dadd_rn((a), -(b))
+    #define ADD __dadd_rn
+    if (n == 1) { if (lane == 0) g[0] = Bv(0) / S(0, 0); return; }
     if (n == 2) {
-        double d = 1. / (A[0] * A[3] - A[1] * A[2]);
-        g[0] = (b[0] * A[3] - b[1] * A[1]) * d;
-        g[1] = (b[1] * A[0] - b[0] * A[2]) * d;
+        if (lane == 0) {
+            double d = SUB(MUL(S(0,0), S(1,1)), MUL(S(0,1), S(1,0)));
+            d = 1. / d;
+            g[0] = MUL(SUB(MUL(Bv(0), S(1,1)), MUL(Bv(1), S(0,1))), d);
+            g[1] = MUL(SUB(MUL(Bv(1), S(0,0)), MUL(Bv(0), S(1,0))), d);
+        }
         return;
     }
     if (n == 3) {
-        #define S(i, j) A[(i) * 3 + (j)]
-        double d = S(0,0) * (S(1,1) * S(2,2) - S(1,2) * S(2,1)) - S(0,1) * (S(1,0) * S(2,2) - S(1,2) * S(2,0)) +
-                   S(0,2) * (S(1,0) * S(2,1) - S(1,1) * S(2,0));
-        d = 1. / d;
-        g[0] = ((S(1,1) * S(2,2) - S(1,2) * S(2,1)) * b[0] + (S(0,2) * S(2,1) - S(0,1) * S(2,2)) * b[1] + (S(0,1) * S(1,2) - S(0,2) * S(1,1)) * b[2]) * d;
-        g[1] = ((S(1,2) * S(2,0) - S(1,0) * S(2,2)) * b[0] + (S(0,0) * S(2,2) - S(0,2) * S(2,0)) * b[1] + (S(0,2) * S(1,0) - S(0,0) * S(1,2)) * b[2]) * d;
-        g[2] = ((S(1,0) * S(2,1) - S(1,1) * S(2,0)) * b[0] + (S(0,1) * S(2,0) - S(0,0) * S(2,1)) * b[1] + (S(0,0) * S(1,1) - S(0,1) * S(1,0)) * b[2]) * d;
-        #undef S
+        if (lane == 0) {
+            double d = ADD(SUB(MUL(S(0,0), SUB(MUL(S(1,1), S(2,2)), MUL(S(1,2), S(2,1)))),
+                               MUL(S(0,1), SUB(MUL(S(1,0), S(2,2)), MUL(S(1,2), S(2,0))))),
+                           MUL(S(0,2), SUB(MUL(S(1,0), S(2,1)), MUL(S(1,1), S(2,0)))));
+            d = 1. / d;
+            g[0] = MUL(ADD(ADD(MUL(SUB(MUL(S(1,1), S(2,2)), MUL(S(1,2), S(2,1))), Bv(0)), MUL(SUB(MUL(S(0,2), S(2,1)), MUL(S(0,1), S(2,2))), Bv(1))),
+                           MUL(SUB(MUL(S(0,1), S(1,2)), MUL(S(0,2), S(1,1))), Bv(2))), d);
+            g[1] = MUL(ADD(ADD(MUL(SUB(MUL(S(1,2), S(2,0)), MUL(S(1,0), S(2,2))), Bv(0)), MUL(SUB(MUL(S(0,0), S(2,2)), MUL(S(0,2), S(2,0))), Bv(1))),
+                           MUL(SUB(MUL(S(0,2), S(1,0)), MUL(S(0,0), S(1,2))), Bv(2))), d);
+            g[2] = MUL(ADD(ADD(MUL(SUB(MUL(S(1,0), S(2,1)), MUL(S(1,1), S(2,0))), Bv(0)), MUL(SUB(MUL(S(0,1), S(2,0)), MUL(S(0,0), S(2,1))), Bv(1))),
+                           MUL(SUB(MUL(S(0,0), S(1,1)), MUL(S(0,1), S(1,0))), Bv(2))), d);
+        }
         return;
     }
-    for (int i = 0; i < n; i++) {                    // LU with partial pivoting
+    for (int i = 0; i < n; i++) {
         int k = i;
-        for (int j = i + 1; j < n; j++) if (fabs(A[j * n + i]) > fabs(A[k * n + i])) k = j;
-        if (k != i) {
-            for (int j = i; j < n; j++) { double t = A[i * n + j]; A[i * n + j] = A[k * n + j]; A[k * n + j] = t; }
-            double t = b[i]; b[i] = b[k]; b[k] = t;
-        }
-        double d = -1 / A[i * n + i];
+        for (int j = i + 1; j < n; j++) if (fabs(S(j, i)) > fabs(S(k, i))) k = j;     // uniform: every lane reads the same
+        if (k != i && lane <= n) { const double t = S(i, lane); S(i, lane) = S(k, lane); S(k, lane) = t; }
+        __syncwarp();
+        const double d = -1 / S(i, i);
         for (int j = i + 1; j < n; j++) {
-            double al = A[j * n + i] * d;
-            for (int kk = i + 1; kk < n; kk++) A[j * n + kk] += al * A[i * n + kk];
-            b[j] += al * b[i];
+            const double al = MUL(S(j, i), d);
+            __syncwarp();
+            if (lane > i && lane <= n) S(j, lane) = ADD(S(j, lane), MUL(al, S(i, lane)));
         }
-        A[i * n + i] = -d;
+        __syncwarp();
+        if (lane == 0) S(i, i) = -d;
+        __syncwarp();
     }
-    for (int i = n - 1; i >= 0; i--) {
-        double s = b[i];
-        for (int k = i + 1; k < n; k++) s -= A[i * n + k] * b[k];
-        b[i] = s * A[i * n + i];
+    if (lane == 0) {
+        for (int i = n - 1; i >= 0; i--) {
+            double sacc = Bv(i);
+            for (int k = i + 1; k < n; k++) sacc = SUB(sacc, MUL(S(i, k), Bv(k)));
+            Bv(i) = MUL(sacc, S(i, i));
+        }
+        for (int i = 0; i < n; i++) g[i] = Bv(i);
     }
-    for (int i = 0; i < n; i++) g[i] = b[i];
+    #undef S
+    #undef Bv
+    #undef MUL
+    #undef SUB
+    #undef ADD
 }
 
 // Per camera: the exact u8 gain LUT in f64, and an f32 multiplier for which the single-FMA formula of
 // gain_apply_f32() reproduces that LUT for all 256 inputs (searched within +-2 ulp of (float)g).
-// If none exists the camera is flagged and the blend kernel reads the LUT instead.  256 threads.
+// If none exists the camera is flagged and the blend kernel reads the LUT instead.  256 threads = 256 inputs.
 __device__ void gain_tables(const GainParams& p)
 {
-    const int v = threadIdx.x;
+    __shared__ unsigned int s_ok[MAX_CAMS];
+    const int v = threadIdx.x;                               // called by threads 0..255 only
+    if (v < MAX_CAMS) s_ok[v] = 0x1Fu;
+    asm volatile("bar.sync 1, 256;");
     for (int c = 0; c < p.n; c++) {
-        const double g = p.gains[c];
+        const double g = __ldcg(p.gains + c);
         const int exact = clamp255(__double2int_rn((double)v * g));
         p.gain_lut[c * 256 + v] = (uint8_t)exact;
-        int chosen = -1;
-        const float g0 = (float)g;
+        unsigned int ok = 0u;
         if (g > 0. && g < 4096.) {
-            #pragma unroll 1
-            for (int k = 0; k < 5 && chosen < 0; k++) {
+            const float g0 = (float)g;
+            #pragma unroll
+            for (int k = 0; k < 5; k++) {                   // candidate k: (float)g + {0,+1,-1,+2,-2} ulp
                 const int step = (k == 0) ? 0 : (k & 1) ? (k + 1) / 2 : -(k / 2);
                 const float gc = __int_as_float(__float_as_int(g0) + step);
-                const int got = (int)gain_apply_f32((float)v, gc);
-                if (__syncthreads_and(got == exact)) chosen = k;
+                if ((int)gain_apply_f32((float)v, gc) == exact) ok |= 1u << k;
             }
         }
-        if (v == 0) {
-            const int step = (chosen <= 0) ? 0 : (chosen & 1) ? (chosen + 1) / 2 : -(chosen / 2);
-            p.gain_f32[c] = __int_as_float(__float_as_int(g0) + step);
-            p.gain_flag[c] = chosen < 0 ? 1 : 0;
-        }
+        if (ok != 0x1Fu) atomicAnd(&s_ok[c], ok);
+    }
+    asm volatile("bar.sync 1, 256;");
+    if (v < p.n) {
+        const unsigned int ok = s_ok[v];
+        const int k = ok ? __ffs(ok) - 1 : 0;
+        const int step = (k == 0) ? 0 : (k & 1) ? (k + 1) / 2 : -(k / 2);
+        p.gain_f32[v] = __int_as_float(__float_as_int((float)__ldcg(p.gains + v)) + step);
+        p.gain_flag[v] = ok ? 0 : 1;
     }
 }
 
-// CTA (pair, chunk): masked sums over the pair's overlap rectangle (32 x 8 threads striding the
-// rectangle, no divisions); the last CTA to finish reduces the partials in a fixed order (one thread
-// per pair), solves for the gains and builds the gain tables.
-__global__ void __launch_bounds__(256) k_gain_reduce_solve(const GainParams p)
+// Working-scale statistics (mapper.cpp:94-99: a ~0.1 Mpix canvas) + gain solve in ONE launch.
+// A CTA takes 256-pixel chunks of the canvas.  Phase A: thread = canvas pixel; for every camera whose
+// working-scale mask is 255 there (CPU compensator's intersect rule, exposure_compensate.cpp:71-78,112) it remaps
+// that one pixel (nearest-resized position, mapper.cpp:235-237) and stores ||rgb||_2 (f64) in shared memory;
+// cameras are processed four at a time so each dependent load step has four requests in flight.
+// Phase B: warp = camera pair; lanes stride the chunk, one shuffle reduction per pair.  The last CTA to
+// finish (ticket) adds the CTA partials in a fixed order, solves for the gains (one warp) and builds the gain
+// tables.  Deterministic; no host round trip.
+constexpr int MAX_PAIRS = MAX_CAMS * (MAX_CAMS + 1) / 2;
+__device__ __forceinline__ unsigned long long gtime() { unsigned long long t; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t)); return t; }
+constexpr int GAIN_BLK = 1024;                             // one CTA per SM, 1024 canvas pixels per chunk
+__global__ void __launch_bounds__(GAIN_BLK) k_gain_stats_solve(const GainParams p)
 {
-    __shared__ double red[3][8];
-    __shared__ double Nm[MAX_CAMS * MAX_CAMS], Im[MAX_CAMS * MAX_CAMS], A[MAX_CAMS * MAX_CAMS], bb[MAX_CAMS];
+    extern __shared__ double s_nrm[];                       // [n][GAIN_BLK]
+    __shared__ double s_part[3 * MAX_PAIRS];
+    __shared__ double Nm[MAX_CAMS * MAX_CAMS], Im[MAX_CAMS * MAX_CAMS], Aug[MAX_CAMS * (MAX_CAMS + 1)];
+    __shared__ uint8_t s_pi[MAX_PAIRS], s_pj[MAX_PAIRS];
     __shared__ bool is_last;
-    const int tid = threadIdx.x, lx = tid & 31, ly = tid >> 5;
-    const int pair = blockIdx.x / p.chunks, chunk = blockIdx.x % p.chunks;
-    int i = 0, rem = pair;
-    while (rem >= p.n - i) { rem -= p.n - i; i++; }
-    const int j = i + rem;
-    const GainCam a = p.cam[i], b = p.cam[j];
-    const int x_tl = max(a.sx, b.sx), y_tl = max(a.sy, b.sy);
-    const int x_br = min(a.sx + a.sw, b.sx + b.sw), y_br = min(a.sy + a.sh, b.sy + b.sh);
-    double cnt = 0, s1 = 0, s2 = 0;
-    for (int y = y_tl + chunk * 8 + ly; y < y_br; y += p.chunks * 8) {
-        const int* ra = p.sq + a.off + (y - a.sy) * a.sw - a.sx;
-        const int* rb = p.sq + b.off + (y - b.sy) * b.sw - b.sx;
-        for (int x = x_tl + lx; x < x_br; x += 32) {
-            const int qa = __ldg(ra + x), qb = __ldg(rb + x);
-            if (qa >= 0 && qb >= 0) { cnt += 1; s1 += sqrt((double)qa); s2 += sqrt((double)qb); }
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int n = p.n, np = p.n_pairs, nq = 3 * np;
+    const unsigned long long T0 = gtime();
+    for (int q = tid; q < nq; q += GAIN_BLK) s_part[q] = 0;
+    if (tid == 0) { int q = 0; for (int i = 0; i < n; i++) for (int j = i; j < n; j++, q++) { s_pi[q] = (uint8_t)i; s_pj[q] = (uint8_t)j; } }
+    const int area = p.cw * p.ch, nchunks = (area + GAIN_BLK - 1) / GAIN_BLK;
+    for (int chunk = blockIdx.x; chunk < nchunks; chunk += gridDim.x) {
+        __syncthreads();
+        const int pix = chunk * GAIN_BLK + tid;
+        const int X = p.cx0 + pix % p.cw, Y = pix < area ? p.cy0 + pix / p.cw : -0x40000000;
+        #pragma unroll 1
+        for (int c0 = 0; c0 < n; c0 += 4) {
+            uint32_t t[4]; bool in[4]; uint2 cc[4]; uint32_t tap[4][4];
+            #pragma unroll
+            for (int u = 0; u < 4; u++) {
+                const GainCam gc = p.cam[min(c0 + u, n - 1)];
+                const int lx = X - gc.sx, ly = Y - gc.sy;
+                in[u] = c0 + u < n && lx >= 0 && ly >= 0 && lx < gc.sw && ly < gc.sh;
+                t[u] = gc.off + ly * gc.sw + lx;
+            }
+            #pragma unroll
+            for (int u = 0; u < 4; u++) in[u] = in[u] && __ldg(p.smask + t[u]) == 255;
+            #pragma unroll
+            for (int u = 0; u < 4; u++) cc[u] = in[u] ? __ldg(p.gcoord + t[u]) : make_uint2(0u, 0u);
+            #pragma unroll
+            for (int u = 0; u < 4; u++) {
+                tap[u][0] = tap[u][1] = tap[u][2] = tap[u][3] = 0u;
+                const int c = min(c0 + u, n - 1);
+                if (cc[u].y & C_VALID) fetch_taps(p.rgbx[c], p.src_pitch[c], cc[u], tap[u][0], tap[u][1], tap[u][2], tap[u][3]);
+            }
+            #pragma unroll
+            for (int u = 0; u < 4; u++) {
+                int r, g, b;
+                bilerp_rgbx(tap[u][0], tap[u][1], tap[u][2], tap[u][3], cc[u].y & 31u, (cc[u].y >> 5) & 31u, r, g, b);
+                if (c0 + u < n) s_nrm[(c0 + u) * GAIN_BLK + tid] = in[u] ? sqrt((double)(r * r + g * g + b * b)) : -1.0;
+            }
+        }
+        __syncthreads();
+        for (int q = warp; q < np; q += GAIN_BLK / 32) {
+            const double* na = s_nrm + s_pi[q] * GAIN_BLK, *nb = s_nrm + s_pj[q] * GAIN_BLK;
+            int cnt = 0; double s1 = 0, s2 = 0;
+            #pragma unroll 8
+            for (int l = lane; l < GAIN_BLK; l += 32) {
+                const double a = na[l], b = nb[l];
+                if (a >= 0 && b >= 0) { cnt++; s1 += a; s2 += b; }
+            }
+            cnt = __reduce_add_sync(0xffffffffu, cnt);
+            if (cnt) {                                      // uniform
+                s1 = warp_sum(s1); s2 = warp_sum(s2);
+                if (lane == 0) { s_part[3 * q] += (double)cnt; s_part[3 * q + 1] += s1; s_part[3 * q + 2] += s2; }
+            }
         }
     }
-    cnt = warp_sum(cnt); s1 = warp_sum(s1); s2 = warp_sum(s2);
-    if (lx == 0) { red[0][ly] = cnt; red[1][ly] = s1; red[2][ly] = s2; }
+    __syncthreads();
+    for (int q = tid; q < nq; q += GAIN_BLK) __stcg(p.partial + (size_t)blockIdx.x * nq + q, s_part[q]);
+    __threadfence();
     __syncthreads();
     if (tid == 0) {
-        double c = 0, u = 0, w = 0;
-        for (int k = 0; k < 8; k++) { c += red[0][k]; u += red[1][k]; w += red[2][k]; }
-        double* o = p.partial + (size_t)blockIdx.x * 3;
-        __stcg(o, c); __stcg(o + 1, u); __stcg(o + 2, w);
-        __threadfence();
         const unsigned int t = atomicInc(p.ticket, gridDim.x - 1);   // wraps to 0: self-resetting
         is_last = (t == gridDim.x - 1);
     }
     __syncthreads();
     if (!is_last) return;
+    const unsigned long long T1 = gtime();
     __threadfence();
-    const int n = p.n;
-    for (int k = tid; k < n * n; k += 256) { Nm[k] = 0; Im[k] = 0; }
+    for (int k = tid; k < n * n; k += GAIN_BLK) { Nm[k] = 0; Im[k] = 0; }
+    // CTA partials -> totals: one warp per value, lanes over CTAs (grid <= 160), fixed summation order
+    for (int q = warp; q < nq; q += GAIN_BLK / 32) {
+        double t[5];
+        #pragma unroll
+        for (int u = 0; u < 5; u++) {
+            const unsigned k = lane + 32 * u;
+            t[u] = k < gridDim.x ? __ldcg(p.partial + (size_t)k * nq + q) : 0.0;
+        }
+        const double v = warp_sum(((t[0] + t[1]) + (t[2] + t[3])) + t[4]);
+        if (lane == 0) s_part[q] = v;
+    }
     __syncthreads();
-    if (tid < p.n_pairs) {
-        int ii = 0, r2 = tid;
-        while (r2 >= n - ii) { r2 -= n - ii; ii++; }
-        const int jj = ii + r2;
+    if (tid < np) {
+        const int ii = s_pi[tid], jj = s_pj[tid];
         const GainCam ca = p.cam[ii], cb = p.cam[jj];
         const bool overlap = max(ca.sx, cb.sx) < min(ca.sx + ca.sw, cb.sx + cb.sw) &&
                              max(ca.sy, cb.sy) < min(ca.sy + ca.sh, cb.sy + cb.sh);
         if (overlap) {                                   // otherwise N = I = 0 (exposure_compensate.cpp:105)
-            double c = 0, u = 0, w = 0;
-            for (int k = 0; k < p.chunks; k++) {
-                const double* o = p.partial + ((size_t)tid * p.chunks + k) * 3;
-                c += __ldcg(o); u += __ldcg(o + 1); w += __ldcg(o + 2);
-            }
+            const double c = s_part[3 * tid], u = s_part[3 * tid + 1], w = s_part[3 * tid + 2];
             const double nn = c > 1 ? c : 1;             // N = max(1, countNonZero)
             Nm[ii * n + jj] = nn; Nm[jj * n + ii] = nn;
             Im[ii * n + jj] = u / nn;
@@ -351,20 +416,21 @@ __global__ void __launch_bounds__(256) k_gain_reduce_solve(const GainParams p)
         }
     }
     __syncthreads();
-    if (tid == 0) { gain_solve(n, Nm, Im, A, bb, p.gains); __threadfence(); }
+    const unsigned long long T2 = gtime();
+    if (warp == 0) { gain_solve_warp(n, Nm, Im, Aug, p.gains); __threadfence(); }
     __syncthreads();
-    gain_tables(p);
+    const unsigned long long T3 = gtime();
+    if (tid < 256) gain_tables(p);          // 256 threads = the 256 input values (named barrier inside)
+    if (tid == 0 && p.dbg) { p.dbg[0] = T0; p.dbg[1] = T1; p.dbg[2] = T2; p.dbg[3] = T3; p.dbg[4] = gtime(); }
 }
 
 __global__ void __launch_bounds__(256) k_gain_finalize(const GainParams p) { gain_tables(p); }
 
-void launch_gain_norms(const GainParams& p, cudaStream_t s)
+void launch_gain_stats_solve(const GainParams& p, cudaStream_t s)
 {
-    k_gain_norms<<<(p.total + 255) / 256, 256, 0, s>>>(p);
-}
-void launch_gain_reduce_solve(const GainParams& p, cudaStream_t s)
-{
-    k_gain_reduce_solve<<<p.n_pairs * p.chunks, 256, 0, s>>>(p);
+    const size_t smem = (size_t)p.n * GAIN_BLK * sizeof(double);
+    if (smem > 40 * 1024) cudaFuncSetAttribute(k_gain_stats_solve, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(MAX_CAMS * GAIN_BLK * sizeof(double)));
+    k_gain_stats_solve<<<p.grid, GAIN_BLK, smem, s>>>(p);
 }
 void launch_gain_finalize(const GainParams& p, cudaStream_t s) { k_gain_finalize<<<1, 256, 0, s>>>(p); }
 

@@ -34,18 +34,17 @@ struct GainParams {
     uint32_t total;            // sum of sw*sh
     const uint8_t* smask;      // linearly resized masks (mapper.cpp:113-114)
     const uint2* gcoord;       // table entry of the NEAREST-resized pixel (mapper.cpp:235-237)
-    int* sq;                   // out: r^2+g^2+b^2 per working-scale pixel, -1 where smask != 255
-    // pair reduction
-    int n_pairs, chunks;       // pairs (i<=j) x chunks CTAs
-    double* partial;           // [n_pairs*chunks][3] : count, sum_i, sum_j
+    int cx0, cy0, cw, ch;      // working-scale canvas = union of the scaled ROIs
+    int n_pairs, grid;         // pairs (i<=j); CTAs launched
+    double* partial;           // [grid][n_pairs][3] : count, sum_i, sum_j
     unsigned int* ticket;
     double* gains;             // [n] f64 (Mapper::gains())
     float* gain_f32;           // [n] verified f32 multiplier
     int* gain_flag;            // [n] 1 -> use the LUT
     uint8_t* gain_lut;         // [n][256] exact sat_u8(rint(v*g)) in f64
+    unsigned long long* dbg;   // optional: %globaltimer stamps of the last CTA (start, ticket, reduced, solved, done)
 };
-void launch_gain_norms(const GainParams& p, cudaStream_t s);
-void launch_gain_reduce_solve(const GainParams& p, cudaStream_t s);
+void launch_gain_stats_solve(const GainParams& p, cudaStream_t s);
 void launch_gain_finalize(const GainParams& p, cudaStream_t s);   // gains[] already set (predefined gains)
 
 // ---- K_blend: fused remap (1/32-px fixed-point bilinear) + gain + weighted accumulate + normalise

@@ -55,8 +55,8 @@ octvr_mapper::~octvr_mapper()
     for (auto p : d_rgbx) cudaFree(p);
     for (auto p : d_vig) cudaFree(p);
     cudaFree(d_tile_job_start); cudaFree(d_job_cam); cudaFree(d_coords); cudaFree(d_weights);
-    cudaFree(d_smask); cudaFree(d_gcoord); cudaFree(d_sq); cudaFree(d_partial); cudaFree(d_ticket);
-    cudaFree(d_gains); cudaFree(d_gain_f32); cudaFree(d_gain_flag); cudaFree(d_gain_lut); cudaFree(d_rgb);
+    cudaFree(d_smask); cudaFree(d_gcoord); cudaFree(d_partial); cudaFree(d_ticket);
+    cudaFree(d_gains); cudaFree(d_gain_f32); cudaFree(d_gain_flag); cudaFree(d_gain_lut); cudaFree(d_rgb); cudaFree(d_dbg);
     if (h_gains) cudaFreeHost(h_gains);
     for (auto& e : ev) if (e) cudaEventDestroy(e);
     ob::multiband_destroy(mb);
@@ -190,18 +190,24 @@ static void build_mapper(octvr_mapper& m, const octvr_template& t, const int* in
         }
         g.total = off;
         g.n_pairs = n * (n + 1) / 2;
-        g.chunks = 16;
+        int x0 = g.cam[0].sx, y0 = g.cam[0].sy, x1 = x0 + g.cam[0].sw, y1 = y0 + g.cam[0].sh;
+        for (int i = 1; i < n; i++) {
+            x0 = std::min(x0, g.cam[i].sx); y0 = std::min(y0, g.cam[i].sy);
+            x1 = std::max(x1, g.cam[i].sx + g.cam[i].sw); y1 = std::max(y1, g.cam[i].sy + g.cam[i].sh);
+        }
+        g.cx0 = x0; g.cy0 = y0; g.cw = x1 - x0; g.ch = y1 - y0;
+        g.grid = std::max(1, std::min(148, (g.cw * g.ch + 1023) / 1024));
         m.d_smask = dev_upload(smask.data(), smask.size());
         m.d_gcoord = dev_upload(gcoord.data(), gcoord.size());
-        m.d_sq = dev_alloc<int>(off);
-        m.d_partial = dev_alloc<double>((size_t)g.n_pairs * g.chunks * 3, true);
+        m.d_partial = dev_alloc<double>((size_t)g.n_pairs * g.grid * 3, true);
         m.d_ticket = dev_alloc<unsigned int>(1, true);
         m.d_gains = dev_alloc<double>(MAX_CAMS, true);
         m.d_gain_f32 = dev_alloc<float>(MAX_CAMS, true);
         m.d_gain_flag = dev_alloc<int>(MAX_CAMS, true);
         m.d_gain_lut = dev_alloc<uint8_t>(MAX_CAMS * 256, true);
         OB_CUDA(cudaMallocHost(&m.h_gains, sizeof(double) * MAX_CAMS));
-        g.smask = m.d_smask; g.gcoord = m.d_gcoord; g.sq = m.d_sq; g.partial = m.d_partial; g.ticket = m.d_ticket;
+        g.smask = m.d_smask; g.gcoord = m.d_gcoord; g.partial = m.d_partial; g.ticket = m.d_ticket;
+        m.d_dbg = dev_alloc<unsigned long long>(8, true); g.dbg = m.d_dbg;
         g.gains = m.d_gains; g.gain_f32 = m.d_gain_f32; g.gain_flag = m.d_gain_flag; g.gain_lut = m.d_gain_lut;
         for (int i = 0; i < n; i++) { g.rgbx[i] = m.d_rgbx[i]; g.src_pitch[i] = m.in_w[i]; }
         m.table_bytes += (int64_t)(smask.size() + gcoord.size() * sizeof(uint2));
@@ -248,8 +254,7 @@ static void do_stitch(octvr_mapper& m, const octvr_frame* in, int n_in, const oc
 
     if (m.gain) {
         if (!gains) {
-            launch_gain_norms(m.gp, s);
-            launch_gain_reduce_solve(m.gp, s);
+            launch_gain_stats_solve(m.gp, s);
         } else {
             OB_CHECK(n_gains == m.n, "gains size must equal the number of inputs");
             // the previous frame may still be reading h_gains: wait for it before overwriting
@@ -371,7 +376,7 @@ octvr_status octvr_mapper_stats(const octvr_mapper* m, int64_t* pairs, int64_t* 
         if (pairs) *pairs = m->pairs;
         if (roi_area) *roi_area = m->roi_area;
         if (table_bytes) *table_bytes = m->table_bytes;
-        if (launches) *launches = m->mb ? ob::multiband_launches(*m) + 1 + (m->gain ? 2 : 0) : 2 + (m->gain ? 2 : 0);
+        if (launches) *launches = m->mb ? ob::multiband_launches(*m) + 1 + (m->gain ? 1 : 0) : 2 + (m->gain ? 1 : 0);
     });
 }
 
@@ -391,6 +396,15 @@ octvr_status octvr_mapper_stage_ms(octvr_mapper* m, const char* stage, float* ms
         if (s == "convert") { a = 0; b = 1; } else if (s == "gain") { a = 1; b = 2; } else if (s == "blend") { a = 2; b = 3; }
         else if (s != "total") fail(OCTVR_ERR_INVALID, "unknown stage " + s);
         OB_CUDA(cudaEventElapsedTime(ms, m->ev[a], m->ev[b]));
+    });
+}
+
+octvr_status octvr_mapper_debug_gain_ns(octvr_mapper* m, unsigned long long* out5)
+{
+    return guard([&] {
+        OB_CHECK(m && out5 && m->d_dbg, "no gain stage");
+        OB_CUDA(cudaDeviceSynchronize());
+        OB_CUDA(cudaMemcpy(out5, m->d_dbg, 5 * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
     });
 }
 

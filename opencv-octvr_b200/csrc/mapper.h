@@ -24,8 +24,9 @@ struct octvr_mapper {
     float* d_weights = nullptr;
     // gain compensation
     ob::GainParams gp;
-    uint8_t* d_smask = nullptr; uint2* d_gcoord = nullptr; int* d_sq = nullptr; double* d_partial = nullptr;
+    uint8_t* d_smask = nullptr; uint2* d_gcoord = nullptr; double* d_partial = nullptr;
     unsigned int* d_ticket = nullptr; double* d_gains = nullptr; float* d_gain_f32 = nullptr;
+    unsigned long long* d_dbg = nullptr;
     int* d_gain_flag = nullptr; uint8_t* d_gain_lut = nullptr; double* h_gains = nullptr;
     // optional RGB result (Mapper::result)
     bool keep_rgb = false;
