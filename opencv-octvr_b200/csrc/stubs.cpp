@@ -1,11 +1,5 @@
 // csrc/stubs.cpp -- entry points still to be implemented this round.
 #include "template.h"
-namespace ob {
-octvr_template* template_from_json(const std::string&, int, int, bool, bool, int)
-{
-    fail(OCTVR_ERR_UNSUPPORTED, "template_build_json is not implemented yet");
-}
-}
 extern "C" {
 octvr_status octvr_async_create(const octvr_template* const*, int, const int*, int, int, int, const int*, const int*, const double*, int, int, int, octvr_async**)
 { return ob::guard([] { ob::fail(OCTVR_ERR_UNSUPPORTED, "async pipeline is not implemented yet"); }); }
