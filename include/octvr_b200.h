@@ -106,7 +106,9 @@ octvr_status octvr_mapper_stitch(octvr_mapper* m, const octvr_frame* d_inputs, i
 octvr_status octvr_mapper_stitch_packed(octvr_mapper* m, const uint8_t* const* d_inputs, const size_t* in_pitch,
                                         int n_inputs, uint8_t* d_output, size_t out_pitch,
                                         const double* gains, int n_gains, void* stream);
-/* RGB888 result of the last stitch at template size (Mapper::result, mapper.hpp:66), device->host copy, synchronous. */
+/* Keep the RGB888 result at template size (Mapper::result, mapper.hpp:66) in addition to / instead of the YUV output. */
+octvr_status octvr_mapper_set_keep_rgb(octvr_mapper* m, int on);
+/* RGB888 result of the last stitch, device->host copy, synchronous.  Needs octvr_mapper_set_keep_rgb(m, 1). */
 octvr_status octvr_mapper_result_rgb(octvr_mapper* m, uint8_t* h_rgb, size_t pitch);
 /* std::vector<double> Mapper::gains() const, mapper.hpp:85-87.  Synchronises the last stitch's stream. */
 octvr_status octvr_mapper_gains(octvr_mapper* m, double* out, int n);
@@ -117,6 +119,8 @@ octvr_status octvr_mapper_stats(const octvr_mapper* m, int64_t* pairs, int64_t* 
 /* time (ms, CUDA events on the stitch stream) the named stage of the LAST stitch took; stage =
  * "convert" | "gain" | "blend" | "total".  Only valid when octvr_mapper_set_profiling(m, 1). */
 octvr_status octvr_mapper_set_profiling(octvr_mapper* m, int on);
+/* %globaltimer stamps (ns) of the gain kernel's last CTA: start, ticket, reduced, solved, done (diagnostics). */
+octvr_status octvr_mapper_debug_gain_ns(octvr_mapper* m, unsigned long long* out5);
 octvr_status octvr_mapper_stage_ms(octvr_mapper* m, const char* stage, float* ms);
 void         octvr_mapper_destroy(octvr_mapper* m);
 

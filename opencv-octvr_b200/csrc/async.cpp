@@ -1,0 +1,277 @@
+// csrc/async.cpp -- vr::AsyncMultiMapper (modules/octvr/include/octvr.hpp:103-121, src/async.{hpp,cpp}) behind
+// the C ABI: host planes in, host planes out, BUF_SIZE = 3 frames in flight (async.cpp:261).
+//
+// The reference runs five host threads (copy-in, upload, map, download, copy-out; async.cpp:32-172,337-349).
+// Here the same five stages are expressed as CUDA stream work: push() stages the frame (or DMAs straight from
+// the caller's planes when they are already page-locked), enqueues H2D on the upload stream, the stitch of
+// every output region on the compute stream and D2H on the download stream, chained with events; pop() waits
+// for the oldest frame's last event and finishes the copy-out.  No stage ever blocks the GPU on the host.
+#include "mapper.h"
+#include <chrono>
+#include <cstring>
+#include <deque>
+#include <memory>
+#include <mutex>
+#include <thread>
+
+using namespace ob;
+
+namespace ob { void mapper_stitch_internal(octvr_mapper& m, const octvr_frame* in, int n_in, const octvr_frame* out,
+                                          const double* gains, int n_gains, const double* d_gains_src, cudaStream_t s); }
+
+namespace {
+
+struct Slot {
+    std::vector<uint8_t*> d_in;       // per camera: contiguous I420 (w x 1.5h)
+    std::vector<uint8_t*> h_in;       // pinned staging, same layout
+    uint8_t* d_out = nullptr;         // whole output frame, contiguous I420
+    uint8_t* h_out = nullptr;         // pinned staging
+    cudaEvent_t uploaded = nullptr, stitched = nullptr, done = nullptr;
+    bool busy = false;
+    octvr_frame user_out{};           // caller's output planes (filled by pop when staged)
+    bool out_staged = false;
+};
+
+bool is_pinned(const void* p)
+{
+    cudaPointerAttributes a;
+    if (cudaPointerGetAttributes(&a, p) != cudaSuccess) { cudaGetLastError(); return false; }
+    return a.type == cudaMemoryTypeHost;
+}
+
+// copy a w x h byte plane (host) with up to 8 helper threads for big planes
+void host_copy_plane(uint8_t* dst, size_t dpitch, const uint8_t* src, size_t spitch, int w, int h, int pix_step)
+{
+    auto rows = [=](int y0, int y1) {
+        for (int y = y0; y < y1; y++) {
+            const uint8_t* s = src + (size_t)y * spitch;
+            uint8_t* d = dst + (size_t)y * dpitch;
+            if (pix_step == 1) memcpy(d, s, (size_t)w);
+            else for (int x = 0; x < w; x++) d[x] = s[(size_t)x * pix_step];
+        }
+    };
+    const size_t bytes = (size_t)w * h;
+    const int nt = bytes > (1u << 20) ? 4 : 1;
+    if (nt == 1) { rows(0, h); return; }
+    std::vector<std::thread> th;
+    for (int t = 0; t < nt; t++) th.emplace_back(rows, h * t / nt, h * (t + 1) / nt);
+    for (auto& t : th) t.join();
+}
+
+}  // namespace
+
+struct octvr_async {
+    int device = 0, n_in = 0, n_out = 0, out_w = 0, out_h = 0;
+    std::vector<int> in_w, in_h;
+    std::vector<std::unique_ptr<octvr_mapper>> mappers;
+    std::vector<int> gain_modes;
+    std::vector<Rect> regions;                 // pixel rectangles of the output frame
+    static constexpr int BUF = 3;              // async.cpp:261
+    Slot slots[BUF];
+    uint64_t pushed = 0, popped = 0;
+    cudaStream_t s_up = nullptr, s_run = nullptr, s_down = nullptr;
+    std::mutex mtx;
+    // fps over the last 10 frames (async.cpp:141-147)
+    std::deque<std::chrono::steady_clock::time_point> stamps;
+    double fps = 0;
+
+    ~octvr_async()
+    {
+        cudaSetDevice(device);
+        if (s_up) cudaStreamSynchronize(s_up);
+        if (s_run) cudaStreamSynchronize(s_run);
+        if (s_down) cudaStreamSynchronize(s_down);
+        for (auto& s : slots) {
+            for (auto p : s.d_in) cudaFree(p);
+            for (auto p : s.h_in) cudaFreeHost(p);
+            cudaFree(s.d_out);
+            if (s.h_out) cudaFreeHost(s.h_out);
+            if (s.uploaded) cudaEventDestroy(s.uploaded);
+            if (s.stitched) cudaEventDestroy(s.stitched);
+            if (s.done) cudaEventDestroy(s.done);
+        }
+        mappers.clear();
+        if (s_up) cudaStreamDestroy(s_up);
+        if (s_run) cudaStreamDestroy(s_run);
+        if (s_down) cudaStreamDestroy(s_down);
+    }
+};
+
+static octvr_frame i420_frame(uint8_t* base, int w, int h)
+{
+    octvr_frame f;
+    f.y = base; f.u = base + (size_t)w * h; f.v = f.u + (size_t)(w / 2) * (h / 2);
+    f.y_pitch = (size_t)w; f.u_pitch = f.v_pitch = (size_t)(w / 2); f.uv_pixel_stride = 1;
+    return f;
+}
+
+// one plane host -> device (async).  Direct DMA from page-locked caller memory, else through the staging buffer.
+static void upload_plane(uint8_t* d_dst, uint8_t* h_stage, const uint8_t* src, size_t spitch, int pix_step, int w, int h, cudaStream_t s)
+{
+    if (pix_step == 1 && is_pinned(src)) {
+        OB_CUDA(cudaMemcpy2DAsync(d_dst, (size_t)w, src, spitch, (size_t)w, (size_t)h, cudaMemcpyHostToDevice, s));
+    } else {
+        host_copy_plane(h_stage, (size_t)w, src, spitch, w, h, pix_step);      // stage T1 (async.cpp:32-56)
+        OB_CUDA(cudaMemcpyAsync(d_dst, h_stage, (size_t)w * h, cudaMemcpyHostToDevice, s));
+    }
+}
+
+extern "C" {
+
+octvr_status octvr_async_create(const octvr_template* const* tmpls, int n_out, const int* in_sizes_wh, int n_in, int out_w, int out_h,
+                                const int* blend_modes, const int* gain_modes, const double* regions_xywh,
+                                int preview_w, int preview_h, int device, octvr_async** out)
+{
+    return guard([&] {
+        OB_CHECK(tmpls && in_sizes_wh && blend_modes && gain_modes && regions_xywh && out, "null argument");
+        OB_CHECK(n_out >= 1 && n_in >= 1, "need at least one template and one input");
+        OB_CHECK(out_w > 0 && out_h > 0 && out_w % 2 == 0 && out_h % 2 == 0, "output size must be even (async.cpp:266-267)");
+        if (preview_w > 0 || preview_h > 0) fail(OCTVR_ERR_UNSUPPORTED, "preview output is not implemented yet");
+        int count = 0;
+        if (cudaGetDeviceCount(&count) != cudaSuccess || count <= 0 || device < 0 || device >= count)
+            fail(OCTVR_ERR_CUDA, "no usable CUDA device (the stitch path has no CPU fallback)");
+        OB_CUDA(cudaSetDevice(device));
+        std::unique_ptr<octvr_async> a(new octvr_async);
+        a->device = device; a->n_in = n_in; a->n_out = n_out; a->out_w = out_w; a->out_h = out_h;
+        for (int i = 0; i < n_in; i++) { a->in_w.push_back(in_sizes_wh[2 * i]); a->in_h.push_back(in_sizes_wh[2 * i + 1]); }
+        for (int i = 0; i < n_out; i++) {
+            OB_CHECK(tmpls[i], "null template");
+            // output_regions are fractions of the output frame (async.cpp:181-185, 247-259)
+            const double* r = regions_xywh + 4 * i;
+            Rect px{ (int)(r[0] * out_w), (int)(r[1] * out_h), (int)(r[2] * out_w), (int)(r[3] * out_h) };
+            OB_CHECK(px.w > 0 && px.h > 0 && px.x >= 0 && px.y >= 0 && px.x + px.w <= out_w && px.y + px.h <= out_h, "output region outside the frame");
+            OB_CHECK(px.x % 2 == 0 && px.y % 2 == 0 && px.w % 2 == 0 && px.h % 2 == 0, "output regions must be even (4:2:0)");
+            a->regions.push_back(px);
+            const int gm = gain_modes[i];
+            OB_CHECK(gm >= -1 && gm <= i, "gain_modes[i] must be -1, i, or an earlier output (async.hpp:79)");
+            a->gain_modes.push_back(gm);
+            octvr_mapper* m = nullptr;
+            octvr_status st = octvr_mapper_create(tmpls[i], in_sizes_wh, n_in, blend_modes[i], gm >= 0 ? 1 : 0, px.w, px.h, device, &m);
+            if (st != OCTVR_OK) fail(st, octvr_last_error());
+            a->mappers.emplace_back(m);
+        }
+        OB_CUDA(cudaStreamCreateWithFlags(&a->s_up, cudaStreamNonBlocking));
+        OB_CUDA(cudaStreamCreateWithFlags(&a->s_run, cudaStreamNonBlocking));
+        OB_CUDA(cudaStreamCreateWithFlags(&a->s_down, cudaStreamNonBlocking));
+        for (auto& s : a->slots) {
+            for (int i = 0; i < n_in; i++) {
+                const size_t bytes = (size_t)a->in_w[i] * a->in_h[i] * 3 / 2;
+                uint8_t* d = nullptr; uint8_t* h = nullptr;
+                OB_CUDA(cudaMalloc(&d, bytes)); s.d_in.push_back(d);
+                OB_CUDA(cudaMallocHost(&h, bytes)); s.h_in.push_back(h);
+            }
+            const size_t ob = (size_t)out_w * out_h * 3 / 2;
+            OB_CUDA(cudaMalloc(&s.d_out, ob));
+            OB_CUDA(cudaMallocHost(&s.h_out, ob));
+            // output pre-filled with black in YUV (async.cpp:283-310): regions need not tile the frame
+            OB_CUDA(cudaMemset(s.d_out, 16, (size_t)out_w * out_h));
+            OB_CUDA(cudaMemset(s.d_out + (size_t)out_w * out_h, 128, (size_t)out_w * out_h / 2));
+            OB_CUDA(cudaEventCreateWithFlags(&s.uploaded, cudaEventDisableTiming));
+            OB_CUDA(cudaEventCreateWithFlags(&s.stitched, cudaEventDisableTiming));
+            OB_CUDA(cudaEventCreateWithFlags(&s.done, cudaEventDisableTiming));
+        }
+        *out = a.release();
+    });
+}
+
+octvr_status octvr_async_push(octvr_async* a, const octvr_frame* in, int n_inputs, const octvr_frame* out)
+{
+    return guard([&] {
+        OB_CHECK(a && in && out, "null argument");
+        OB_CHECK(n_inputs == a->n_in, "wrong number of input frames (async.cpp:176)");
+        std::lock_guard<std::mutex> lk(a->mtx);
+        OB_CHECK(a->pushed - a->popped < (uint64_t)octvr_async::BUF, "pipeline full: pop() before pushing more than 3 frames");
+        OB_CUDA(cudaSetDevice(a->device));
+        Slot& s = a->slots[a->pushed % octvr_async::BUF];
+        // T1 + T2: caller planes -> (pinned staging ->) device, on the upload stream
+        for (int i = 0; i < a->n_in; i++) {
+            const int w = a->in_w[i], h = a->in_h[i];
+            const octvr_frame& f = in[i];
+            OB_CHECK(f.y && f.u && f.v && f.y_pitch >= (size_t)w, "bad input frame");
+            uint8_t* d = s.d_in[i]; uint8_t* hs = s.h_in[i];
+            const size_t ysz = (size_t)w * h, csz = (size_t)(w / 2) * (h / 2);
+            upload_plane(d, hs, f.y, f.y_pitch, 1, w, h, a->s_up);
+            upload_plane(d + ysz, hs + ysz, f.u, f.u_pitch, f.uv_pixel_stride, w / 2, h / 2, a->s_up);
+            upload_plane(d + ysz + csz, hs + ysz + csz, f.v, f.v_pitch, f.uv_pixel_stride, w / 2, h / 2, a->s_up);
+        }
+        OB_CUDA(cudaEventRecord(s.uploaded, a->s_up));
+        // T3: every output region on the compute stream (async.cpp:70-91)
+        OB_CUDA(cudaStreamWaitEvent(a->s_run, s.uploaded, 0));
+        std::vector<octvr_frame> fin(a->n_in);
+        for (int i = 0; i < a->n_in; i++) fin[i] = i420_frame(s.d_in[i], a->in_w[i], a->in_h[i]);
+        const octvr_frame whole = i420_frame(s.d_out, a->out_w, a->out_h);
+        for (int r = 0; r < a->n_out; r++) {
+            const Rect& px = a->regions[r];
+            octvr_frame o = whole;
+            o.y += (size_t)px.y * whole.y_pitch + px.x;
+            o.u += (size_t)(px.y / 2) * whole.u_pitch + px.x / 2;
+            o.v += (size_t)(px.y / 2) * whole.v_pitch + px.x / 2;
+            const int gm = a->gain_modes[r];
+            const double* shared = (gm >= 0 && gm != r) ? a->mappers[gm]->d_gains : nullptr;   // gains of an earlier output
+            mapper_stitch_internal(*a->mappers[r], fin.data(), a->n_in, &o, nullptr, 0, shared, a->s_run);
+        }
+        OB_CUDA(cudaEventRecord(s.stitched, a->s_run));
+        // T4: device -> host on the download stream; straight into the caller's planes when they are pinned
+        OB_CUDA(cudaStreamWaitEvent(a->s_down, s.stitched, 0));
+        const int W = a->out_w, H = a->out_h;
+        const bool direct = out->uv_pixel_stride == 1 && is_pinned(out->y) && is_pinned(out->u) && is_pinned(out->v);
+        s.out_staged = !direct;
+        s.user_out = *out;
+        if (direct) {
+            OB_CUDA(cudaMemcpy2DAsync(out->y, out->y_pitch, whole.y, whole.y_pitch, (size_t)W, (size_t)H, cudaMemcpyDeviceToHost, a->s_down));
+            OB_CUDA(cudaMemcpy2DAsync(out->u, out->u_pitch, whole.u, whole.u_pitch, (size_t)W / 2, (size_t)H / 2, cudaMemcpyDeviceToHost, a->s_down));
+            OB_CUDA(cudaMemcpy2DAsync(out->v, out->v_pitch, whole.v, whole.v_pitch, (size_t)W / 2, (size_t)H / 2, cudaMemcpyDeviceToHost, a->s_down));
+        } else {
+            OB_CUDA(cudaMemcpyAsync(s.h_out, s.d_out, (size_t)W * H * 3 / 2, cudaMemcpyDeviceToHost, a->s_down));
+        }
+        OB_CUDA(cudaEventRecord(s.done, a->s_down));
+        // the next frame's upload into this slot's device buffers must not start before this stitch has read them;
+        // slots are reused only after pop(), which waits for `done` (ordered after `stitched`)
+        s.busy = true;
+        a->pushed++;
+    });
+}
+
+octvr_status octvr_async_pop(octvr_async* a)
+{
+    return guard([&] {
+        OB_CHECK(a, "null argument");
+        Slot* sp;
+        {
+            std::lock_guard<std::mutex> lk(a->mtx);
+            OB_CHECK(a->popped < a->pushed, "pop() without a matching push()");
+            sp = &a->slots[a->popped % octvr_async::BUF];
+        }
+        Slot& s = *sp;
+        OB_CUDA(cudaSetDevice(a->device));
+        OB_CUDA(cudaEventSynchronize(s.done));
+        if (s.out_staged) {                      // T5 (async.cpp:113-172)
+            const int W = a->out_w, H = a->out_h;
+            const octvr_frame& o = s.user_out;
+            const uint8_t* hy = s.h_out; const uint8_t* hu = hy + (size_t)W * H; const uint8_t* hv = hu + (size_t)(W / 2) * (H / 2);
+            host_copy_plane(o.y, o.y_pitch, hy, (size_t)W, W, H, 1);
+            for (int y = 0; y < H / 2; y++)
+                for (int x = 0; x < W / 2; x++) {
+                    o.u[(size_t)y * o.u_pitch + (size_t)x * o.uv_pixel_stride] = hu[(size_t)y * (W / 2) + x];
+                    o.v[(size_t)y * o.v_pitch + (size_t)x * o.uv_pixel_stride] = hv[(size_t)y * (W / 2) + x];
+                }
+        }
+        std::lock_guard<std::mutex> lk(a->mtx);
+        s.busy = false;
+        a->popped++;
+        auto now = std::chrono::steady_clock::now();
+        a->stamps.push_back(now);
+        if (a->stamps.size() > 11) a->stamps.pop_front();
+        if (a->stamps.size() >= 2)
+            a->fps = (double)(a->stamps.size() - 1) / std::chrono::duration<double>(a->stamps.back() - a->stamps.front()).count();
+    });
+}
+
+octvr_status octvr_async_fps(octvr_async* a, double* fps)
+{
+    return guard([&] { OB_CHECK(a && fps, "null argument"); std::lock_guard<std::mutex> lk(a->mtx); *fps = a->fps; });
+}
+
+void octvr_async_destroy(octvr_async* a) { delete a; }
+
+}  // extern "C"

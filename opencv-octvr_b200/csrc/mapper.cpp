@@ -223,8 +223,20 @@ static void check_frame(const octvr_frame& f, int w, int h, const char* what)
     (void)h;
 }
 
+namespace ob {
+void mapper_stitch_internal(octvr_mapper& m, const octvr_frame* in, int n_in, const octvr_frame* out,
+                            const double* gains, int n_gains, const double* d_gains_src, cudaStream_t s);
+}
 static void do_stitch(octvr_mapper& m, const octvr_frame* in, int n_in, const octvr_frame* out,
                       const double* gains, int n_gains, cudaStream_t s)
+{
+    ob::mapper_stitch_internal(m, in, n_in, out, gains, n_gains, nullptr, s);
+}
+
+// gains: host array of predefined gains, or d_gains_src: another mapper's device gains (gain sharing between
+// output regions, async.cpp:75-86), or neither: computed from this frame.
+void ob::mapper_stitch_internal(octvr_mapper& m, const octvr_frame* in, int n_in, const octvr_frame* out,
+                                const double* gains, int n_gains, const double* d_gains_src, cudaStream_t s)
 {
     OB_CHECK(n_in == m.n, "wrong number of input frames");           // mapper.cpp:208
     OB_CUDA(cudaSetDevice(m.device));
@@ -253,7 +265,10 @@ static void do_stitch(octvr_mapper& m, const octvr_frame* in, int n_in, const oc
     if (m.profiling) OB_CUDA(cudaEventRecord(m.ev[1], s));
 
     if (m.gain) {
-        if (!gains) {
+        if (d_gains_src) {
+            OB_CUDA(cudaMemcpyAsync(m.d_gains, d_gains_src, sizeof(double) * m.n, cudaMemcpyDeviceToDevice, s));
+            launch_gain_finalize(m.gp, s);
+        } else if (!gains) {
             launch_gain_stats_solve(m.gp, s);
         } else {
             OB_CHECK(n_gains == m.n, "gains size must equal the number of inputs");
@@ -401,6 +416,7 @@ octvr_status octvr_mapper_stage_ms(octvr_mapper* m, const char* stage, float* ms
 
 octvr_status octvr_mapper_debug_gain_ns(octvr_mapper* m, unsigned long long* out5)
 {
+    // diagnostics only
     return guard([&] {
         OB_CHECK(m && out5 && m->d_dbg, "no gain stage");
         OB_CUDA(cudaDeviceSynchronize());

@@ -51,4 +51,3 @@ int multiband_launches(const octvr_mapper& m);
 void multiband_destroy(Multiband* mb);
 }  // namespace ob
 
-extern "C" octvr_status octvr_mapper_set_keep_rgb(octvr_mapper* m, int on);
