@@ -109,7 +109,8 @@ static octvr_frame i420_frame(uint8_t* base, int w, int h)
 static void upload_plane(uint8_t* d_dst, uint8_t* h_stage, const uint8_t* src, size_t spitch, int pix_step, int w, int h, cudaStream_t s)
 {
     if (pix_step == 1 && is_pinned(src)) {
-        OB_CUDA(cudaMemcpy2DAsync(d_dst, (size_t)w, src, spitch, (size_t)w, (size_t)h, cudaMemcpyHostToDevice, s));
+        if (spitch == (size_t)w) OB_CUDA(cudaMemcpyAsync(d_dst, src, (size_t)w * h, cudaMemcpyHostToDevice, s));   // one DMA, not h row copies
+        else OB_CUDA(cudaMemcpy2DAsync(d_dst, (size_t)w, src, spitch, (size_t)w, (size_t)h, cudaMemcpyHostToDevice, s));
     } else {
         host_copy_plane(h_stage, (size_t)w, src, spitch, w, h, pix_step);      // stage T1 (async.cpp:32-56)
         OB_CUDA(cudaMemcpyAsync(d_dst, h_stage, (size_t)w * h, cudaMemcpyHostToDevice, s));
@@ -190,6 +191,11 @@ octvr_status octvr_async_push(octvr_async* a, const octvr_frame* in, int n_input
             OB_CHECK(f.y && f.u && f.v && f.y_pitch >= (size_t)w, "bad input frame");
             uint8_t* d = s.d_in[i]; uint8_t* hs = s.h_in[i];
             const size_t ysz = (size_t)w * h, csz = (size_t)(w / 2) * (h / 2);
+            if (f.uv_pixel_stride == 1 && f.y_pitch == (size_t)w && f.u_pitch == (size_t)w / 2 && f.v_pitch == (size_t)w / 2 &&
+                f.u == f.y + ysz && f.v == f.u + csz && is_pinned(f.y)) {
+                OB_CUDA(cudaMemcpyAsync(d, f.y, ysz + 2 * csz, cudaMemcpyHostToDevice, a->s_up));       // contiguous pinned I420
+                continue;
+            }
             upload_plane(d, hs, f.y, f.y_pitch, 1, w, h, a->s_up);
             upload_plane(d + ysz, hs + ysz, f.u, f.u_pitch, f.uv_pixel_stride, w / 2, h / 2, a->s_up);
             upload_plane(d + ysz + csz, hs + ysz + csz, f.v, f.v_pitch, f.uv_pixel_stride, w / 2, h / 2, a->s_up);
@@ -217,7 +223,14 @@ octvr_status octvr_async_push(octvr_async* a, const octvr_frame* in, int n_input
         const bool direct = out->uv_pixel_stride == 1 && is_pinned(out->y) && is_pinned(out->u) && is_pinned(out->v);
         s.out_staged = !direct;
         s.user_out = *out;
-        if (direct) {
+        const bool tight = out->y_pitch == (size_t)W && out->u_pitch == (size_t)W / 2 && out->v_pitch == (size_t)W / 2;
+        if (direct && tight && out->u == out->y + (size_t)W * H && out->v == out->u + (size_t)(W / 2) * (H / 2)) {
+            OB_CUDA(cudaMemcpyAsync(out->y, s.d_out, (size_t)W * H * 3 / 2, cudaMemcpyDeviceToHost, a->s_down));      // contiguous I420
+        } else if (direct && tight) {
+            OB_CUDA(cudaMemcpyAsync(out->y, whole.y, (size_t)W * H, cudaMemcpyDeviceToHost, a->s_down));
+            OB_CUDA(cudaMemcpyAsync(out->u, whole.u, (size_t)(W / 2) * (H / 2), cudaMemcpyDeviceToHost, a->s_down));
+            OB_CUDA(cudaMemcpyAsync(out->v, whole.v, (size_t)(W / 2) * (H / 2), cudaMemcpyDeviceToHost, a->s_down));
+        } else if (direct) {
             OB_CUDA(cudaMemcpy2DAsync(out->y, out->y_pitch, whole.y, whole.y_pitch, (size_t)W, (size_t)H, cudaMemcpyDeviceToHost, a->s_down));
             OB_CUDA(cudaMemcpy2DAsync(out->u, out->u_pitch, whole.u, whole.u_pitch, (size_t)W / 2, (size_t)H / 2, cudaMemcpyDeviceToHost, a->s_down));
             OB_CUDA(cudaMemcpy2DAsync(out->v, out->v_pitch, whole.v, whole.v_pitch, (size_t)W / 2, (size_t)H / 2, cudaMemcpyDeviceToHost, a->s_down));
