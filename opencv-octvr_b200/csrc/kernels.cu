@@ -7,56 +7,9 @@
 //   gain     : core/src/arithm.cpp multiply-by-scalar in f64 -> sat_u8(rint(v*g))
 //   feather  : stitching/src/cuda/blender.cu:73-98 (short)(v*W) truncation, blenders.cpp:581 (x 1/N, rint)
 #include "kernels.cuh"
+#include "device_common.cuh"
 
 namespace ob {
-
-// ------------------------------------------------------------------------------------------------
-// shared device helpers
-// ------------------------------------------------------------------------------------------------
-__device__ __forceinline__ int clamp255(int v) { return min(max(v, 0), 255); }
-
-// fixed-point bilinear of three 8-bit channels from four RGBX taps.  fx, fy in [0, 32).
-__device__ __forceinline__ void bilerp_rgbx(uint32_t t00, uint32_t t01, uint32_t t10, uint32_t t11,
-                                            uint32_t fx, uint32_t fy, int& r, int& g, int& b)
-{
-    const uint32_t wx = fx * 65535u + 32u;                 // (32-fx) | fx << 16
-    const uint32_t ay = 32u - fy, by = fy;
-    const uint32_t rg0 = __byte_perm(t00, t01, 0x5140);    // R00 R01 G00 G01
-    const uint32_t bb0 = __byte_perm(t00, t01, 0x6262);    // B00 B01 .. ..
-    const uint32_t rg1 = __byte_perm(t10, t11, 0x5140);
-    const uint32_t bb1 = __byte_perm(t10, t11, 0x6262);
-    const uint32_t hr0 = __dp2a_lo(wx, rg0, 0u), hg0 = __dp2a_hi(wx, rg0, 0u), hb0 = __dp2a_lo(wx, bb0, 0u);
-    const uint32_t hr1 = __dp2a_lo(wx, rg1, 0u), hg1 = __dp2a_hi(wx, rg1, 0u), hb1 = __dp2a_lo(wx, bb1, 0u);
-    r = (int)((hr0 * ay + hr1 * by + 512u) >> 10);
-    g = (int)((hg0 * ay + hg1 * by + 512u) >> 10);
-    b = (int)((hb0 * ay + hb1 * by + 512u) >> 10);
-}
-
-// gather the four taps for a table entry; taps outside the source contribute 0 (BORDER_CONSTANT)
-__device__ __forceinline__ void fetch_taps(const uint32_t* __restrict__ src, int pitch, uint2 c,
-                                           uint32_t& t00, uint32_t& t01, uint32_t& t10, uint32_t& t11)
-{
-    const int off = (int)c.x;
-    if (!(c.y & C_BORDER)) {
-        t00 = __ldg(src + off); t01 = __ldg(src + off + 1);
-        t10 = __ldg(src + off + pitch); t11 = __ldg(src + off + pitch + 1);
-    } else {
-        const uint32_t in = c.y >> C_TAP_SHIFT;
-        t00 = (in & 1u) ? __ldg(src + off) : 0u;
-        t01 = (in & 2u) ? __ldg(src + off + 1) : 0u;
-        t10 = (in & 4u) ? __ldg(src + off + pitch) : 0u;
-        t11 = (in & 8u) ? __ldg(src + off + pitch + 1) : 0u;
-    }
-}
-
-constexpr float MAGIC_RN = 12582912.f;   // 1.5 * 2^23 : x + MAGIC rounds x to nearest-even integer
-constexpr float MAGIC_RD = 8388608.f;    // 2^23 with round-down add : floor(x)
-
-// sat_u8(rint(v * g)) for integer v in [0,255] as a float; g32 has been verified against the f64 rule
-__device__ __forceinline__ float gain_apply_f32(float v, float g32)
-{
-    return fminf(__fadd_rn(__fmaf_rn(v, g32, MAGIC_RN), -MAGIC_RN), 255.f);
-}
 
 // ------------------------------------------------------------------------------------------------
 // K_convert

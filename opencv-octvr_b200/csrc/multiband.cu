@@ -1,12 +1,386 @@
-// csrc/multiband.cu -- CPU-MultiBandBlender-compatible Laplacian pyramid blend on the GPU.  (placeholder)
+// csrc/multiband.cu -- multiband (Laplacian pyramid) blending with the arithmetic of the reference's CPU
+// cv::detail::MultiBandBlender(false, bands, CV_32F) fed 16S images (modules/stitching/src/blenders.cpp:221-477,
+// 764-825, 881-892, 923-933; pyramids: modules/imgproc/src/pyramids.cpp:849-1060), which is the contract for
+// octvr's blend > 0 mode (Mapper passes seam masks as the blend masks, mapper.cpp:160-165).
+//
+// Static per mapper (init, host): per-camera bordered rectangles (gap 3*2^bands, aligned to 2^bands, BORDER_REFLECT
+// baked into the remap table), f32 weight Gaussian pyramids of the seam masks, summed band weights.
+// Per frame (device, all integer-exact):
+//   k_mb_warp      remap + gain of every camera into its bordered level-0 image (RGBX8888)
+//   k_mb_down      Gaussian pyramid level l -> l+1 per camera ([1 4 6 4 1]^2, (v+128)>>8, REFLECT_101), 16S
+//   k_mb_band      per destination level: sum over cameras of (short)((G_l - pyrUp(G_{l+1})) * W_l), then
+//                  (short)(sum / (sumW + 1e-5))  -- Laplacian, weighting, accumulation and normalisation fused
+//   k_mb_collapse  dst_{l-1} += pyrUp(dst_l) (saturating); the last level also masks, narrows to 8 bit and writes
+//                  RGB / YUV 4:2:0
 #include "mapper.h"
+#include "prep.h"
+#include "device_common.cuh"
+#include <algorithm>
+#include <cstring>
+#include <cmath>
+#include <memory>
+
 namespace ob {
-struct Multiband { int dummy; };
-Multiband* multiband_create(octvr_mapper&, const octvr_template&, const std::vector<Img<int32_t>>&, const std::vector<Img<int32_t>>&)
+
+constexpr int MB_MAX_LEVELS = 9;     // bands <= 8
+
+struct MbCam {
+    int x0, y0;                       // top-left of the bordered rect relative to the padded dst roi (level 0)
+    int bw, bh;                       // bordered size (level 0), multiples of 2^bands
+    unsigned long long off_g[MB_MAX_LEVELS];   // pixel offset of level l in its pool (level 0: g0 pool, else g pool)
+    unsigned long long off_w[MB_MAX_LEVELS];   // float offset of the level-l weights
+};
+
+struct MbParams {
+    int n, nb;
+    MbCam cam[MAX_CAMS];
+    int lw[MB_MAX_LEVELS], lh[MB_MAX_LEVELS];
+    unsigned long long off_d[MB_MAX_LEVELS];   // offsets of dst level l (short4 units) and dstw (floats)
+    const uint2* coords;              // per camera bordered level-0 pixel: table entry (reflection already applied)
+    uint32_t* g0;                     // level 0 images, RGBX8888
+    short4* g;                        // levels >= 1, 16S x 3 (+pad)
+    const float* w;                   // weight pyramids
+    short4* dst;                      // blended Laplacian pyramid
+    const float* dstw;                // summed band weights
+    // gain
+    const uint32_t* rgbx[MAX_CAMS]; int src_pitch[MAX_CAMS];
+    const float* gain_f32; const int* gain_flag; const uint8_t* gain_lut; int use_gain;
+    // output
+    int rx, ry, rw, rh;               // final result roi in the output frame (dst_roi_final_)
+    int out_w, out_h;
+    uint8_t* oy; uint8_t* ou; uint8_t* ov; uint32_t oy_pitch, ou_pitch, ov_pitch; int uv_step;
+    uint8_t* rgb_out; uint32_t rgb_pitch;
+};
+
+struct Multiband {
+    MbParams p;
+    uint2* d_coords = nullptr; uint32_t* d_g0 = nullptr; short4* d_g = nullptr; float* d_w = nullptr;
+    short4* d_dst = nullptr; float* d_dstw = nullptr;
+    int max_bw = 0, max_bh = 0;
+    int launches = 0;
+};
+
+// ------------------------------------------------------------------------------------------------ device
+__device__ __forceinline__ int refl101(int p, int len)
 {
-    fail(OCTVR_ERR_UNSUPPORTED, "multiband blending is not implemented yet");
+    if (len == 1) return 0;
+    while (p < 0 || p >= len) p = p < 0 ? -p : 2 * len - 2 - p;
+    return p;
 }
-void multiband_stitch(octvr_mapper&, const octvr_frame*, cudaStream_t) {}
-int multiband_launches(const octvr_mapper&) { return 0; }
-void multiband_destroy(Multiband* mb) { delete mb; }
+__device__ __forceinline__ int sat16(int v) { return min(max(v, -32768), 32767); }
+__device__ __forceinline__ int3 ld3(const short4* s, int idx) { const short4 v = __ldg(s + idx); return make_int3(v.x, v.y, v.z); }
+__device__ __forceinline__ int3 ld3(const uint32_t* s, int idx) { const uint32_t v = __ldg(s + idx); return make_int3(v & 255u, (v >> 8) & 255u, (v >> 16) & 255u); }
+__device__ __forceinline__ int3 madd3(int3 a, int3 b, int k) { return make_int3(a.x + b.x * k, a.y + b.y * k, a.z + b.z * k); }
+
+// pyramids.cpp:967-1060 (pyrUp_, FixPtCast<short,6>): value of the 2x up-sampled image at (x, y)
+template <class T> __device__ int3 pyrup_at(const T* s, int sw, int sh, int x, int y)
+{
+    const int kx = x >> 1, ky = y >> 1;
+    auto hrow = [&](int r) -> int3 {
+        const T* row = s + r * sw;
+        if (sw == 1) { const int3 a = ld3(row, 0); return make_int3(a.x * 8, a.y * 8, a.z * 8); }
+        if ((x & 1) == 0) {
+            if (kx == 0) return madd3(madd3(make_int3(0, 0, 0), ld3(row, 0), 6), ld3(row, 1), 2);
+            if (kx == sw - 1) return madd3(madd3(make_int3(0, 0, 0), ld3(row, kx - 1), 1), ld3(row, kx), 7);
+            return madd3(madd3(madd3(make_int3(0, 0, 0), ld3(row, kx - 1), 1), ld3(row, kx), 6), ld3(row, kx + 1), 1);
+        }
+        if (kx == sw - 1) return madd3(make_int3(0, 0, 0), ld3(row, kx), 8);
+        return madd3(madd3(make_int3(0, 0, 0), ld3(row, kx), 4), ld3(row, kx + 1), 4);
+    };
+    const int rp = refl101(2 * (ky + 1), 2 * sh) >> 1;
+    int3 v;
+    if ((y & 1) == 0) {
+        const int rm = refl101(2 * (ky - 1), 2 * sh) >> 1;
+        v = madd3(madd3(madd3(make_int3(0, 0, 0), hrow(rm), 1), hrow(ky), 6), hrow(rp), 1);
+    } else
+        v = madd3(madd3(make_int3(0, 0, 0), hrow(ky), 4), hrow(rp), 4);
+    return make_int3(sat16((v.x + 32) >> 6), sat16((v.y + 32) >> 6), sat16((v.z + 32) >> 6));
+}
+
+// ---- k_mb_warp: grid (ceil(max_area/256), cameras) ----
+__global__ void __launch_bounds__(256) k_mb_warp(const __grid_constant__ MbParams p)
+{
+    const int c = blockIdx.y;
+    const MbCam& cam = p.cam[c];
+    const unsigned t = blockIdx.x * 256 + threadIdx.x;
+    if (t >= (unsigned)(cam.bw * cam.bh)) return;
+    const uint2 cc = __ldg(p.coords + cam.off_g[0] + t);
+    uint32_t px = 0;
+    if (cc.y & C_VALID) {
+        uint32_t t00, t01, t10, t11;
+        fetch_taps(p.rgbx[c], p.src_pitch[c], cc, t00, t01, t10, t11);
+        int r, g, b;
+        bilerp_rgbx(t00, t01, t10, t11, cc.y & 31u, (cc.y >> 5) & 31u, r, g, b);
+        if (p.use_gain) {
+            if (__ldg(p.gain_flag + c) == 0) {
+                const float g32 = __ldg(p.gain_f32 + c);
+                r = (int)gain_apply_f32((float)r, g32); g = (int)gain_apply_f32((float)g, g32); b = (int)gain_apply_f32((float)b, g32);
+            } else {
+                const uint8_t* lut = p.gain_lut + c * 256;
+                r = __ldg(lut + r); g = __ldg(lut + g); b = __ldg(lut + b);
+            }
+        }
+        px = (uint32_t)r | ((uint32_t)g << 8) | ((uint32_t)b << 16);
+    }
+    p.g0[cam.off_g[0] + t] = px;
+}
+
+// ---- k_mb_down: level l -> l+1 for every camera.  grid (ceil(w/32), ceil(h/8), cameras) at level l+1 ----
+template <class T> __device__ __forceinline__ int3 pyrdown_at(const T* s, int sw, int sh, int x, int y)
+{
+    int xi[5], yi[5];
+    #pragma unroll
+    for (int k = 0; k < 5; k++) { xi[k] = refl101(2 * x + k - 2, sw); yi[k] = refl101(2 * y + k - 2, sh); }
+    const int kw[5] = { 1, 4, 6, 4, 1 };
+    int3 acc = make_int3(0, 0, 0);
+    #pragma unroll
+    for (int dy = 0; dy < 5; dy++) {
+        int3 row = make_int3(0, 0, 0);
+        #pragma unroll
+        for (int dx = 0; dx < 5; dx++) row = madd3(row, ld3(s, yi[dy] * sw + xi[dx]), kw[dx]);
+        acc = madd3(acc, row, kw[dy]);
+    }
+    return make_int3(sat16((acc.x + 128) >> 8), sat16((acc.y + 128) >> 8), sat16((acc.z + 128) >> 8));
+}
+
+__global__ void __launch_bounds__(256) k_mb_down(const __grid_constant__ MbParams p, int l)
+{
+    const MbCam& cam = p.cam[blockIdx.z];
+    const int sw = cam.bw >> l, sh = cam.bh >> l, dw = sw >> 1, dh = sh >> 1;
+    const int x = blockIdx.x * 32 + threadIdx.x, y = blockIdx.y * 8 + threadIdx.y;
+    if (x >= dw || y >= dh) return;
+    const int3 v = l == 0 ? pyrdown_at(p.g0 + cam.off_g[0], sw, sh, x, y) : pyrdown_at(p.g + cam.off_g[l], sw, sh, x, y);
+    p.g[cam.off_g[l + 1] + (size_t)y * dw + x] = make_short4((short)v.x, (short)v.y, (short)v.z, 0);
+}
+
+// ---- k_mb_band: one thread per pixel of destination level l ----
+__global__ void __launch_bounds__(256) k_mb_band(const __grid_constant__ MbParams p, int l)
+{
+    const int X = blockIdx.x * 32 + threadIdx.x, Y = blockIdx.y * 8 + threadIdx.y;
+    const int lw = p.lw[l], lh = p.lh[l];
+    if (X >= lw || Y >= lh) return;
+    int ar = 0, ag = 0, ab = 0;
+    for (int c = 0; c < p.n; c++) {
+        const MbCam& cam = p.cam[c];
+        const int x = X - (cam.x0 >> l), y = Y - (cam.y0 >> l);
+        const int w_l = cam.bw >> l, h_l = cam.bh >> l;
+        if (x < 0 || y < 0 || x >= w_l || y >= h_l) continue;
+        const float w = __ldg(p.w + cam.off_w[l] + (size_t)y * w_l + x);
+        if (w == 0.f) continue;                                       // (short)(lap * 0) == 0
+        int3 gl = l == 0 ? ld3(p.g0 + cam.off_g[0], y * w_l + x) : ld3(p.g + cam.off_g[l], y * w_l + x);
+        if (l < p.nb) {                                               // createLaplacePyr: pyr[l] -= pyrUp(pyr[l+1]), saturating 16S
+            const int3 up = pyrup_at(p.g + cam.off_g[l + 1], w_l >> 1, h_l >> 1, x, y);
+            gl = make_int3(sat16(gl.x - up.x), sat16(gl.y - up.y), sat16(gl.z - up.z));
+        }
+        // dst += static_cast<short>(lap * weight): f32 product truncated toward zero (blenders.cpp:418-420)
+        ar += __float2int_rz(__fmul_rn((float)gl.x, w));
+        ag += __float2int_rz(__fmul_rn((float)gl.y, w));
+        ab += __float2int_rz(__fmul_rn((float)gl.z, w));
+    }
+    const size_t di = p.off_d[l] + (size_t)Y * lw + X;
+    // normalizeUsingWeightMap (blenders.cpp:788-797): (short)(v / (w + 1e-5f))
+    const float den = __fadd_rn(__ldg(p.dstw + di), 1e-5f);
+    const short r = (short)__float2int_rz(__fdiv_rn((float)(short)ar, den));
+    const short g = (short)__float2int_rz(__fdiv_rn((float)(short)ag, den));
+    const short b = (short)__float2int_rz(__fdiv_rn((float)(short)ab, den));
+    p.dst[di] = make_short4(r, g, b, 0);
+}
+
+// ---- k_mb_collapse: dst_{l-1} = sat(pyrUp(dst_l) + dst_{l-1}), l >= 2 ----
+__global__ void __launch_bounds__(256) k_mb_collapse(const __grid_constant__ MbParams p, int l)
+{
+    const int X = blockIdx.x * 32 + threadIdx.x, Y = blockIdx.y * 8 + threadIdx.y;
+    const int w = p.lw[l - 1], h = p.lh[l - 1];
+    if (X >= w || Y >= h) return;
+    const int3 up = pyrup_at(p.dst + p.off_d[l], p.lw[l], p.lh[l], X, Y);
+    const size_t di = p.off_d[l - 1] + (size_t)Y * w + X;
+    const short4 cur = p.dst[di];
+    p.dst[di] = make_short4((short)sat16(up.x + cur.x), (short)sat16(up.y + cur.y), (short)sat16(up.z + cur.z), 0);
+}
+
+// ---- k_mb_final: level 1 -> 0 collapse fused with mask, 8-bit narrowing and the output store; one thread per
+//      OUTPUT-FRAME pixel (pixels outside the result roi are black) ----
+__global__ void __launch_bounds__(256) k_mb_final(const __grid_constant__ MbParams p)
+{
+    const int X = blockIdx.x * 32 + threadIdx.x, Y = blockIdx.y * 8 + threadIdx.y;
+    if (X >= p.out_w || Y >= p.out_h) return;
+    int R = 0, G = 0, B = 0;
+    const int x = X - p.rx, y = Y - p.ry;
+    if (x >= 0 && y >= 0 && x < p.rw && y < p.rh) {
+        const size_t di = p.off_d[0] + (size_t)y * p.lw[0] + x;
+        if (__ldg(p.dstw + di) > 1e-5f) {                              // dst_mask = dst_band_weights_[0] > WEIGHT_EPS (blenders.cpp:472)
+            short4 cur = p.dst[di];
+            int3 v = make_int3(cur.x, cur.y, cur.z);
+            if (p.nb > 0) {
+                const int3 up = pyrup_at(p.dst + p.off_d[1], p.lw[1], p.lh[1], x, y);
+                v = make_int3(sat16(up.x + v.x), sat16(up.y + v.y), sat16(up.z + v.z));
+            }
+            R = clamp255(v.x); G = clamp255(v.y); B = clamp255(v.z);   // convertTo(CV_8U)
+        }
+    }
+    if (p.rgb_out) {
+        uint8_t* o = p.rgb_out + (size_t)Y * p.rgb_pitch + 3 * X;
+        o[0] = (uint8_t)R; o[1] = (uint8_t)G; o[2] = (uint8_t)B;
+    }
+    if (p.oy) {
+        p.oy[(size_t)Y * p.oy_pitch + X] = (uint8_t)rgb_luma(R, G, B);
+        if (((X | Y) & 1) == 0) {
+            const size_t co = (size_t)(X >> 1) * p.uv_step;
+            p.ou[(size_t)(Y >> 1) * p.ou_pitch + co] = (uint8_t)rgb_cb(R, G, B);
+            p.ov[(size_t)(Y >> 1) * p.ov_pitch + co] = (uint8_t)rgb_cr(R, G, B);
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------ host
+namespace {
+inline int mirror(int p, int len)      // BORDER_REFLECT (fedcba|abcdefgh|hgfedcb)
+{
+    if (len == 1) return 0;
+    while (p < 0 || p >= len) p = p < 0 ? -p - 1 : 2 * len - 1 - p;
+    return p;
+}
+template <class T> T* upload(const std::vector<T>& v)
+{
+    T* d = nullptr;
+    OB_CUDA(cudaMalloc(&d, std::max<size_t>(v.size(), 1) * sizeof(T)));
+    if (!v.empty()) OB_CUDA(cudaMemcpy(d, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice));
+    return d;
+}
+uint2 mk_entry(int32_t sx, int32_t sy, int src_w, int src_h, bool valid)
+{
+    if (!valid) return make_uint2(0u, 0u);
+    int ix = std::min(32767, std::max(-32768, sx >> 5)), iy = std::min(32767, std::max(-32768, sy >> 5));
+    const uint32_t fx = (uint32_t)(sx & 31), fy = (uint32_t)(sy & 31);
+    const bool x0 = ix >= 0 && ix < src_w, x1 = ix + 1 >= 0 && ix + 1 < src_w, y0 = iy >= 0 && iy < src_h, y1 = iy + 1 >= 0 && iy + 1 < src_h;
+    const uint32_t taps = (uint32_t)(x0 && y0) | ((uint32_t)(x1 && y0) << 1) | ((uint32_t)(x0 && y1) << 2) | ((uint32_t)(x1 && y1) << 3);
+    if (!taps) return make_uint2(0u, 0u);
+    uint32_t flags = C_VALID;
+    if (taps != 15u) flags |= C_BORDER | (taps << C_TAP_SHIFT);
+    return make_uint2((uint32_t)(iy * src_w + ix), fx | (fy << 5) | flags);
+}
+}  // namespace
+
+Multiband* multiband_create(octvr_mapper& m, const octvr_template& t,
+                            const std::vector<Img<int32_t>>& sx, const std::vector<Img<int32_t>>& sy)
+{
+    const int n = m.n;
+    std::vector<Img<uint8_t>> seams = t.seam_masks;
+    bool have = (int)seams.size() == n;
+    for (auto& s : seams) have = have && !s.empty();
+    if (!have) seams = distance_seam_masks(t.inputs, t.out_w);       // Mapper requires mt.seam_masks (mapper.cpp:106)
+
+    std::unique_ptr<Multiband> mb(new Multiband);
+    MbParams& p = mb->p;
+    memset(&p, 0, sizeof(p));
+    const int req = int(std::ceil(std::log((double)m.blend) / std::log(2.)) - 1.);    // mapper.cpp:161
+    OB_CHECK(req >= 1, "multiband needs blend >= 3 (at least one band; blenders.cpp:595)");
+    Rect Rf = t.inputs[0].roi;
+    for (int i = 1; i < n; i++) Rf = rect_union(Rf, t.inputs[i].roi);
+    const double max_len = (double)std::max(Rf.w, Rf.h);
+    const int nb = std::min(req, (int)std::ceil(std::log(max_len) / std::log(2.0)));  // blenders.cpp:242-243
+    OB_CHECK(nb >= 0 && nb + 1 <= MB_MAX_LEVELS, "too many bands");
+    const int al = 1 << nb;
+    const int PW = Rf.w + (al - Rf.w % al) % al, PH = Rf.h + (al - Rf.h % al) % al;   // blenders.cpp:246-247
+    p.n = n; p.nb = nb;
+    p.rx = Rf.x; p.ry = Rf.y; p.rw = Rf.w; p.rh = Rf.h; p.out_w = t.out_w; p.out_h = t.out_h;
+    size_t doff = 0;
+    for (int l = 0; l <= nb; l++) {
+        p.lw[l] = l == 0 ? PW : (p.lw[l - 1] + 1) / 2; p.lh[l] = l == 0 ? PH : (p.lh[l - 1] + 1) / 2;
+        p.off_d[l] = doff; doff += (size_t)p.lw[l] * p.lh[l];
+    }
+    std::vector<float> dstw(doff, 0.f);
+    std::vector<uint2> coords;
+    std::vector<float> wts;
+    size_t g0_total = 0, g_total = 0;
+    for (int i = 0; i < n; i++) {
+        const TInput& in = t.inputs[i];
+        MbCam& c = p.cam[i];
+        // MultiBandBlender::feed geometry (blenders.cpp:306-341); dst_roi_ = (Rf.x, Rf.y, PW, PH)
+        const int gap = 3 * al;
+        int tnx = std::max(Rf.x, in.roi.x - gap), tny = std::max(Rf.y, in.roi.y - gap);
+        int bnx = std::min(Rf.x + PW, in.roi.x + in.roi.w + gap), bny = std::min(Rf.y + PH, in.roi.y + in.roi.h + gap);
+        tnx = Rf.x + (((tnx - Rf.x) >> nb) << nb); tny = Rf.y + (((tny - Rf.y) >> nb) << nb);
+        int width = bnx - tnx, height = bny - tny;
+        width += (al - width % al) % al; height += (al - height % al) % al;
+        bnx = tnx + width; bny = tny + height;
+        const int dy = std::max(bny - (Rf.y + PH), 0), dx = std::max(bnx - (Rf.x + PW), 0);
+        tnx -= dx; bnx -= dx; tny -= dy; bny -= dy;
+        const int top = in.roi.y - tny, left = in.roi.x - tnx;
+        c.x0 = tnx - Rf.x; c.y0 = tny - Rf.y; c.bw = width; c.bh = height;
+        mb->max_bw = std::max(mb->max_bw, width); mb->max_bh = std::max(mb->max_bh, height);
+        c.off_g[0] = g0_total; g0_total += (size_t)width * height;
+        for (int l = 1; l <= nb; l++) { c.off_g[l] = g_total; g_total += (size_t)(width >> l) * (height >> l); }
+        // level-0 remap table with BORDER_REFLECT baked in, and the f32 weight map (BORDER_CONSTANT 0)
+        Img<float> wmap(width, height, 0.f);
+        const float inv255 = (float)(1. / 255.);
+        coords.resize(coords.size() + (size_t)width * height);
+        uint2* ce = coords.data() + c.off_g[0];
+        for (int y = 0; y < height; y++) {
+            const int ly = mirror(y - top, in.roi.h);
+            const bool in_y = y - top >= 0 && y - top < in.roi.h;
+            for (int x = 0; x < width; x++) {
+                const int lx = mirror(x - left, in.roi.w);
+                ce[(size_t)y * width + x] = mk_entry(sx[i].row(ly)[lx], sy[i].row(ly)[lx], m.in_w[i], m.in_h[i], in.mask.row(ly)[lx] != 0);
+                if (in_y && x - left >= 0 && x - left < in.roi.w) wmap.row(y)[x] = seams[i].row(y - top)[x - left] * inv255 + 0.f;
+            }
+        }
+        Img<float> wl = std::move(wmap);
+        int xt = c.x0, yt = c.y0;
+        for (int l = 0; l <= nb; l++) {
+            c.off_w[l] = wts.size();
+            wts.insert(wts.end(), wl.d.begin(), wl.d.end());
+            for (int y = 0; y < wl.h; y++) {                        // dst_band_weights_[l](rc) += weight (blenders.cpp:421)
+                float* dr = dstw.data() + p.off_d[l] + (size_t)(yt + y) * p.lw[l] + xt;
+                const float* wr = wl.row(y);
+                for (int x = 0; x < wl.w; x++) dr[x] += wr[x];
+            }
+            if (l < nb) wl = pyrdown_f32(wl);
+            xt /= 2; yt /= 2;
+        }
+    }
+    mb->d_coords = upload(coords);
+    mb->d_w = upload(wts);
+    mb->d_dstw = upload(dstw);
+    OB_CUDA(cudaMalloc(&mb->d_g0, std::max<size_t>(g0_total, 1) * sizeof(uint32_t)));
+    OB_CUDA(cudaMalloc(&mb->d_g, std::max<size_t>(g_total, 1) * sizeof(short4)));
+    OB_CUDA(cudaMalloc(&mb->d_dst, std::max<size_t>(doff, 1) * sizeof(short4)));
+    p.coords = mb->d_coords; p.g0 = mb->d_g0; p.g = mb->d_g; p.w = mb->d_w; p.dst = mb->d_dst; p.dstw = mb->d_dstw;
+    for (int i = 0; i < n; i++) { p.rgbx[i] = m.d_rgbx[i]; p.src_pitch[i] = m.in_w[i]; }
+    m.table_bytes = (int64_t)(coords.size() * sizeof(uint2) + wts.size() * 4 + dstw.size() * 4);
+    mb->launches = 1 + nb + (nb + 1) + std::max(0, nb - 1) + 1;
+    return mb.release();
+}
+
+void multiband_stitch(octvr_mapper& m, const octvr_frame* out, cudaStream_t s)
+{
+    Multiband& mb = *m.mb;
+    MbParams p = mb.p;
+    p.gain_f32 = m.d_gain_f32; p.gain_flag = m.d_gain_flag; p.gain_lut = m.d_gain_lut; p.use_gain = m.gain ? 1 : 0;
+    if (out) {
+        p.oy = out->y; p.ou = out->u; p.ov = out->v;
+        p.oy_pitch = (uint32_t)out->y_pitch; p.ou_pitch = (uint32_t)out->u_pitch; p.ov_pitch = (uint32_t)out->v_pitch;
+        p.uv_step = out->uv_pixel_stride;
+    }
+    p.rgb_out = m.keep_rgb ? m.d_rgb : nullptr; p.rgb_pitch = (uint32_t)m.out_w * 3;
+    const int nb = p.nb, n = p.n;
+    k_mb_warp<<<dim3(((size_t)mb.max_bw * mb.max_bh + 255) / 256, n), 256, 0, s>>>(p);
+    for (int l = 0; l < nb; l++)
+        k_mb_down<<<dim3(((mb.max_bw >> (l + 1)) + 31) / 32, ((mb.max_bh >> (l + 1)) + 7) / 8, n), dim3(32, 8), 0, s>>>(p, l);
+    for (int l = nb; l >= 0; l--)
+        k_mb_band<<<dim3((p.lw[l] + 31) / 32, (p.lh[l] + 7) / 8), dim3(32, 8), 0, s>>>(p, l);
+    for (int l = nb; l >= 2; l--)
+        k_mb_collapse<<<dim3((p.lw[l - 1] + 31) / 32, (p.lh[l - 1] + 7) / 8), dim3(32, 8), 0, s>>>(p, l);
+    k_mb_final<<<dim3((p.out_w + 31) / 32, (p.out_h + 7) / 8), dim3(32, 8), 0, s>>>(p);
+}
+
+int multiband_launches(const octvr_mapper& m) { return m.mb ? m.mb->launches : 0; }
+
+void multiband_destroy(Multiband* mb)
+{
+    if (!mb) return;
+    cudaFree(mb->d_coords); cudaFree(mb->d_g0); cudaFree(mb->d_g); cudaFree(mb->d_w); cudaFree(mb->d_dst); cudaFree(mb->d_dstw);
+    delete mb;
+}
+
 }  // namespace ob
