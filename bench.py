@@ -155,10 +155,8 @@ def run_ours(args):
     torch.cuda.synchronize()
     ms = e0.elapsed_time(e1)
     clocks = sampler.stop() if sampler else None
-    if world > 1:
-        tt = torch.tensor([ms], device="cuda")
-        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-        ms = float(tt.item())
+    ms = vr.sharding.max_over_ranks(ms, device="cuda")            # timing rule: max over ranks
+    frames_all = sum(vr.sharding.gather_frame_counts(args.steps, device="cuda"))
 
     # end to end through the host-facing API (AsyncMultiMapper: host planes in, host planes out)
     e2e = None
@@ -170,14 +168,17 @@ def run_ours(args):
     if rank != 0:
         return
     ms_per_step = ms / args.steps
-    frames = args.steps * world
+    frames = frames_all
     mpix = W * H * frames / (ms * 1e-3) / 1e6
     B = alg_bytes([in_size] * n, (W, H), st["pairs"], st["roi_area"], blend)
     peak, how = peaks()
     # dominant kernel = the fused blend kernel; its algorithmic bytes = tables + output (the convert
     # kernel owns the input bytes), duration from CUDA events on the launch stream
     blend_ms = statistics.median(stage["blend"])
-    blend_bytes = (12 if blend <= 0 else 8) * st["pairs"] + W * H * 3 // 2
+    if blend > 0:    # multiband stage (k_mb_warp .. k_mb_final): everything of B_alg except the input frames
+        blend_bytes = B - n * iw * ih * 3 // 2
+    else:
+        blend_bytes = 12 * st["pairs"] + W * H * 3 // 2
     ach = blend_bytes / (blend_ms * 1e-3) / 1e9
     line = {
         "metric": "equirect output Mpix/s", "value": round(mpix, 1), "unit": "Mpix/s", "n_gpus": world,
@@ -192,7 +193,7 @@ def run_ours(args):
         "frac_of_hbm_roofline": {"whole_step_vs_measured_%.0f" % peak: round(B / (ms_per_step * 1e-3) / 1e9 / peak, 4),
                                  "whole_step_vs_8000": round(B / (ms_per_step * 1e-3) / 1e9 / 8000.0, 4)},
         "stage_ms": {k: round(statistics.median(v), 5) for k, v in stage.items()},
-        "roofline": {"bound": "hbm", "kernel": "k_blend", "achieved": round(ach, 1), "peak": peak, "peak_source": how, "unit": "GB/s",
+        "roofline": {"bound": "hbm", "kernel": "k_blend" if blend <= 0 else "multiband stage (k_mb_warp+k_mb_down+k_mb_band+k_mb_collapse+k_mb_final)", "achieved": round(ach, 1), "peak": peak, "peak_source": how, "unit": "GB/s",
                      "frac": round(ach / peak, 4), "traffic": None,
                      "alg_bytes_per_launch": int(blend_bytes), "ms_per_launch": round(blend_ms, 5)},
         "gpu_launches": st["launches_per_stitch"] * args.steps,
@@ -238,11 +239,7 @@ def run_e2e(vr, util, tmpl, cfg, in_size, blend, gain, device, steps, world):
         inflight -= 1
     dt = time.perf_counter() - t0
     am.close()
-    if world > 1:
-        import torch.distributed as dist
-        tt = torch.tensor([dt], device="cuda")
-        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-        dt = float(tt.item())
+    dt = vr.sharding.max_over_ranks(dt, device="cuda")
     return {"value": round(W * H * steps * world / dt / 1e6, 1), "unit": "Mpix/s", "frames_per_s": round(steps * world / dt, 1),
             "h2d_bytes_per_step": n * iw * ih * 3 // 2, "d2h_bytes_per_step": W * H * 3 // 2,
             "api": "AsyncMultiMapper.push/pop (pinned host planes, 3 frames in flight)", "steps": steps}

@@ -7,3 +7,4 @@ name has a hyphen; import it as `import octvr_b200` (alias module at the repo ro
 """
 from .capi import OctvrError, Frame, lib, build, LIB_PATH, SYMBOLS  # noqa: F401
 from .mapper import MapperTemplate, Mapper, AsyncMultiMapper, frame_from_planes, split_packed  # noqa: F401
+from . import sharding  # noqa: F401,E402

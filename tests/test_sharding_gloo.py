@@ -1,0 +1,49 @@
+"""Host-side multi-GPU logic on CPU: world_size-2 gloo processes agree on stream ownership, the max-over-ranks
+time and the whole-job frame count (the data path itself has no collective)."""
+import os
+import subprocess
+import sys
+import textwrap
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+WORKER = textwrap.dedent("""
+    import os, sys, json
+    sys.path.insert(0, %r)
+    import torch.distributed as dist
+    import octvr_b200 as vr
+    dist.init_process_group("gloo")
+    r, w = dist.get_rank(), dist.get_world_size()
+    mine = vr.sharding.streams_of_rank(16, r, w)
+    t = vr.sharding.max_over_ranks(1.0 + r)
+    counts = vr.sharding.gather_frame_counts(100 * len(mine))
+    bands = vr.sharding.row_bands(1920, w, 32)
+    print(json.dumps({"rank": r, "mine": mine, "t": t, "counts": counts, "bands": bands}))
+    dist.destroy_process_group()
+""") % ROOT
+
+
+def test_two_rank_gloo_sharding(tmp_path):
+    script = tmp_path / "w.py"
+    script.write_text(WORKER)
+    env = dict(os.environ, MASTER_ADDR="127.0.0.1")
+    out = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2",
+                          "--master-addr", "127.0.0.1", "--master-port", "29617", str(script)],
+                         capture_output=True, text=True, env=env, timeout=240)
+    assert out.returncode == 0, out.stderr[-2000:]
+    import json
+    rows = sorted((json.loads(l) for l in out.stdout.splitlines() if l.startswith("{")), key=lambda d: d["rank"])
+    assert len(rows) == 2
+    assert rows[0]["mine"] == list(range(0, 16, 2)) and rows[1]["mine"] == list(range(1, 16, 2))
+    assert sorted(rows[0]["mine"] + rows[1]["mine"]) == list(range(16))          # every stream owned exactly once
+    assert rows[0]["t"] == rows[1]["t"] == 2.0                                   # max over ranks
+    assert rows[0]["counts"] == rows[1]["counts"] == [800, 800]
+    assert rows[0]["bands"] == [[0, 960], [960, 1920]]
+
+
+def test_row_bands_alignment():
+    import octvr_b200 as vr
+    b = vr.sharding.row_bands(1920, 8, 32)
+    assert b[0][0] == 0 and b[-1][1] == 1920 and all(y0 % 32 == 0 and y1 % 32 == 0 for y0, y1 in b)
+    assert all(b[i][1] == b[i + 1][0] for i in range(7))
+    assert max(y1 - y0 for y0, y1 in b) - min(y1 - y0 for y0, y1 in b) <= 32
