@@ -165,6 +165,9 @@ def run_ours(args):
     except vr.OctvrError as ex:
         e2e = {"value": None, "unit": "Mpix/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0, "error": str(ex)}
 
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
     if rank != 0:
         return
     ms_per_step = ms / args.steps

@@ -539,6 +539,157 @@ __global__ void __launch_bounds__(256) k_blend(const BlendParams p)
     }
 }
 
+// ------------------------------------------------------------------------------------------------
+// K_blend_staged
+// ------------------------------------------------------------------------------------------------
+// ---- TMA + mbarrier (sm_90+ PTX; SASS: UTMALDG / SYNCS) ----
+__device__ __forceinline__ void mbar_init(uint64_t* mbar, int count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"((uint32_t)__cvta_generic_to_shared(mbar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* mbar, uint32_t bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"((uint32_t)__cvta_generic_to_shared(mbar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* mbar, uint32_t phase)
+{
+    asm volatile(
+        "{\n\t.reg .pred P1;\n\t"
+        "WAIT_LOOP:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n\t"
+        "@P1 bra DONE;\n\t"
+        "bra WAIT_LOOP;\n\t"
+        "DONE:\n\t}" ::"r"((uint32_t)__cvta_generic_to_shared(mbar)), "r"(phase) : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(void* smem_dst, const void* tmap, int x, int y, uint64_t* mbar)
+{
+    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+                 ::"r"((uint32_t)__cvta_generic_to_shared(smem_dst)), "l"((uint64_t)tmap), "r"((uint32_t)__cvta_generic_to_shared(mbar)), "r"(x), "r"(y) : "memory");
+}
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+template <int GAIN>   // 0: no gain, 1: verified f32 multiplier (LUT fallback per job if flagged)
+__global__ void __launch_bounds__(256, 7) k_blend_staged(const __grid_constant__ StagedParams p)
+{
+    __shared__ __align__(128) uint32_t s_buf[STAGE_CAP];
+    __shared__ __align__(8) uint64_t s_mbar;
+    __shared__ JobMeta s_job[MAX_CAMS];
+    __shared__ uint32_t s_gain[MAX_CAMS];
+    __shared__ uint32_t s_px[TILE_H][TILE_W + 1];
+    const int tid = threadIdx.x, lx = tid & 31, ly = tid >> 5;
+    const int tile = blockIdx.y * p.tiles_x + blockIdx.x;
+    const JobMeta* rec = p.jobs + (size_t)tile * MAX_CAMS;
+    const int nj = __ldg(&rec->grp_nj) & 0xFF;
+    const uint32_t j0 = (uint32_t)__ldg(&rec->j0);
+    if (tid < nj) {
+        const JobMeta jm = rec[tid];
+        s_job[tid] = jm;
+        uint32_t g = 0u;
+        if (GAIN) g = __ldg(p.gain_flag + jm.cam) == 0 ? (uint32_t)__float_as_int(__ldg(p.gain_f32 + jm.cam)) : 0xFFFFFFFFu;
+        s_gain[tid] = g;
+    }
+    if (tid == 0) { mbar_init(&s_mbar, 1); asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+    __syncthreads();
+
+    uint32_t ar0 = 0, ag0 = 0, ab0 = 0, ar1 = 0, ag1 = 0, ab1 = 0;
+    const uint2* ep = p.entries + (size_t)j0 * TILE_PX + tid;
+    uint2 e0 = make_uint2(0, 0), e1 = make_uint2(0, 0);
+    if (nj > 0) { e0 = __ldcs(ep); e1 = __ldcs(ep + 256); }
+    int k = 0;
+    uint32_t phase = 0;
+    while (k < nj) {                                        // one pass per job group (almost always a single group)
+        const int grp = s_job[k].grp_nj >> 8;
+        int kend = k;
+        while (kend < nj && (s_job[kend].grp_nj >> 8) == grp) kend++;
+        if (tid == 0) {                                     // one thread issues the group's TMA box loads
+            uint32_t bytes = 0;
+            for (int q = k; q < kend; q++) bytes += (uint32_t)(s_job[q].bw * s_job[q].bh) * 4u;
+            mbar_expect_tx(&s_mbar, bytes);
+            for (int q = k; q < kend; q++)
+                tma_load_2d(s_buf + s_job[q].soff, (const char*)p.tmaps + (size_t)s_job[q].tmap * 128, s_job[q].bx0, s_job[q].by0, &s_mbar);
+        }
+        mbar_wait(&s_mbar, phase);
+        phase ^= 1u;
+        #pragma unroll 1
+        for (; k < kend; k++) {
+            const uint2 a0 = e0, a1 = e1;
+            if (k + 1 < nj) { ep += TILE_PX; e0 = __ldcs(ep); e1 = __ldcs(ep + 256); }
+            const int bw = s_job[k].bw;
+            const uint32_t g = s_gain[k];
+            const uint32_t o0 = a0.x & 0xFFFFu, o1 = a1.x & 0xFFFFu;
+            const uint32_t t00 = s_buf[o0], t01 = s_buf[o0 + 1], t10 = s_buf[o0 + bw], t11 = s_buf[o0 + bw + 1];
+            const uint32_t u00 = s_buf[o1], u01 = s_buf[o1 + 1], u10 = s_buf[o1 + bw], u11 = s_buf[o1 + bw + 1];
+            int r, gg, bb;
+            float rf, gf, bf;
+            const float w0 = __int_as_float((int)a0.y), w1 = __int_as_float((int)a1.y);
+            bilerp_rgbx(t00, t01, t10, t11, (a0.x >> 16) & 31u, (a0.x >> 21) & 31u, r, gg, bb);
+            rf = (float)r; gf = (float)gg; bf = (float)bb;
+            if (GAIN) {
+                if (g != 0xFFFFFFFFu) { const float g32 = __int_as_float((int)g); rf = gain_apply_f32(rf, g32); gf = gain_apply_f32(gf, g32); bf = gain_apply_f32(bf, g32); }
+                else { const uint8_t* lut = p.gain_lut + s_job[k].cam * 256; rf = (float)__ldg(lut + r); gf = (float)__ldg(lut + gg); bf = (float)__ldg(lut + bb); }
+            }
+            ar0 += (uint32_t)__float_as_int(__fadd_rd(__fmul_rn(rf, w0), MAGIC_RD)) - 0x4B000000u;
+            ag0 += (uint32_t)__float_as_int(__fadd_rd(__fmul_rn(gf, w0), MAGIC_RD)) - 0x4B000000u;
+            ab0 += (uint32_t)__float_as_int(__fadd_rd(__fmul_rn(bf, w0), MAGIC_RD)) - 0x4B000000u;
+            bilerp_rgbx(u00, u01, u10, u11, (a1.x >> 16) & 31u, (a1.x >> 21) & 31u, r, gg, bb);
+            rf = (float)r; gf = (float)gg; bf = (float)bb;
+            if (GAIN) {
+                if (g != 0xFFFFFFFFu) { const float g32 = __int_as_float((int)g); rf = gain_apply_f32(rf, g32); gf = gain_apply_f32(gf, g32); bf = gain_apply_f32(bf, g32); }
+                else { const uint8_t* lut = p.gain_lut + s_job[k].cam * 256; rf = (float)__ldg(lut + r); gf = (float)__ldg(lut + gg); bf = (float)__ldg(lut + bb); }
+            }
+            ar1 += (uint32_t)__float_as_int(__fadd_rd(__fmul_rn(rf, w1), MAGIC_RD)) - 0x4B000000u;
+            ag1 += (uint32_t)__float_as_int(__fadd_rd(__fmul_rn(gf, w1), MAGIC_RD)) - 0x4B000000u;
+            ab1 += (uint32_t)__float_as_int(__fadd_rd(__fmul_rn(bf, w1), MAGIC_RD)) - 0x4B000000u;
+        }
+        if (k < nj) { __syncthreads(); fence_proxy_async(); }   // the stage is refilled (async proxy) by the next group
+    }
+    const uint32_t px0 = normalise_px(ar0, ag0, ab0, p.inv_n), px1 = normalise_px(ar1, ag1, ab1, p.inv_n);
+    s_px[ly][lx] = px0;
+    s_px[ly + 8][lx] = px1;
+    __syncthreads();
+
+    const int tx0 = blockIdx.x * TILE_W, ty0 = blockIdx.y * TILE_H;
+    if (p.oy) {
+        if (tid < 128) {
+            const int row = tid >> 3, gx = (tid & 7) << 2;
+            const int x = tx0 + gx, y = ty0 + row;
+            if (y < p.out_h && x < p.out_w) {
+                const uint32_t yv = luma(s_px[row][gx]) | (luma(s_px[row][gx + 1]) << 8) | (luma(s_px[row][gx + 2]) << 16) | (luma(s_px[row][gx + 3]) << 24);
+                uint8_t* o = p.oy + (size_t)y * p.oy_pitch + x;
+                if (x + 3 < p.out_w && (((uintptr_t)o) & 3) == 0) *reinterpret_cast<uint32_t*>(o) = yv;
+                else for (int q = 0; q < 4 && x + q < p.out_w; q++) o[q] = (uint8_t)(yv >> (8 * q));
+            }
+        } else {
+            const int t = tid - 128, row = t >> 4, cx = t & 15;
+            const int x = tx0 + 2 * cx, y = ty0 + 2 * row;
+            if (y < p.out_h && x < p.out_w) {
+                const uint32_t px = s_px[2 * row][2 * cx];
+                const int R = px & 255u, G = (px >> 8) & 255u, B = (px >> 16) & 255u;
+                const size_t co = (size_t)(x >> 1) * p.uv_step;
+                p.ou[(size_t)(y >> 1) * p.ou_pitch + co] = (uint8_t)rgb_cb(R, G, B);
+                p.ov[(size_t)(y >> 1) * p.ov_pitch + co] = (uint8_t)rgb_cr(R, G, B);
+            }
+        }
+    }
+    if (p.rgb_out) {
+        #pragma unroll
+        for (int h = 0; h < 2; h++) {
+            const int x = tx0 + lx, y = ty0 + ly + 8 * h;
+            if (x < p.out_w && y < p.out_h) {
+                const uint32_t px = h ? px1 : px0;
+                uint8_t* o = p.rgb_out + (size_t)y * p.rgb_pitch + 3 * x;
+                o[0] = (uint8_t)px; o[1] = (uint8_t)(px >> 8); o[2] = (uint8_t)(px >> 16);
+            }
+        }
+    }
+}
+
+void launch_blend_staged(const StagedParams& p, cudaStream_t s)
+{
+    if (p.use_gain) k_blend_staged<1><<<dim3(p.tiles_x, p.tiles_y), 256, 0, s>>>(p);
+    else k_blend_staged<0><<<dim3(p.tiles_x, p.tiles_y), 256, 0, s>>>(p);
+}
+
 void launch_blend(const BlendParams& p, cudaStream_t s)
 {
     k_blend<<<dim3(p.tiles_x, p.tiles_y), 256, 0, s>>>(p);

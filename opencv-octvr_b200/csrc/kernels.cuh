@@ -67,4 +67,32 @@ struct BlendParams {
 };
 void launch_blend(const BlendParams& p, cudaStream_t s);
 
+// ---- K_blend_staged: same arithmetic, but each job's SOURCE FOOTPRINT (bounding box of its bilinear taps in the
+//      camera's RGBX plane) is brought into shared memory by TMA (cp.async.bulk.tensor.2d, one instruction per
+//      camera, zero-filled outside the image = BORDER_CONSTANT, completion on an mbarrier) for ALL cameras of the
+//      tile at once, and the taps are read with LDS.  The table shrinks to 8 B per pair:
+//      {stage-relative tap offset | fx<<16 | fy<<21, f32 weight}. ----
+constexpr int STAGE_CAP = 6144;        // shared-memory stage capacity in pixels (24 KB): all footprints of a job group
+// One 32-byte record per (tile, slot); a tile owns MAX_CAMS consecutive slots, so the CTA finds everything it needs
+// with ONE coalesced 512-byte read (no tile -> job-list indirection).  bw x bh = TMA box (px); soff = px offset in
+// the stage; tmap = descriptor index; nj / j0 (jobs of the tile, first entry block) are replicated in every slot.
+struct JobMeta { int cam; int bx0, by0; int bw, bh; int soff; int grp_nj; int tmap; int j0; int pad[7]; };
+static_assert(sizeof(JobMeta) == 64, "JobMeta");
+struct StagedParams {
+    const uint32_t* rgbx[MAX_CAMS];
+    int src_w[MAX_CAMS], src_h[MAX_CAMS];
+    const JobMeta* jobs;              // [tiles][MAX_CAMS]
+    const void* tmaps;                // CUtensorMap[...]: one per (camera, box size) in use, 128 B each
+    const uint2* entries;             // [jobs*TILE_PX]
+    int tiles_x, tiles_y, out_w, out_h;
+    uint8_t* oy; uint8_t* ou; uint8_t* ov;
+    uint32_t oy_pitch, ou_pitch, ov_pitch;
+    int uv_step;
+    uint8_t* rgb_out; uint32_t rgb_pitch;
+    const float* gain_f32; const int* gain_flag; const uint8_t* gain_lut;
+    int use_gain;
+    float inv_n;
+};
+void launch_blend_staged(const StagedParams& p, cudaStream_t s);
+
 }  // namespace ob

@@ -3,8 +3,12 @@
 // per-frame kernels on the caller's stream.  No CPU fallback: a missing device is an error.
 #include "mapper.h"
 #include "prep.h"
+#include <cuda.h>
+#include <map>
 #include <algorithm>
 #include <cmath>
+#include <climits>
+#include <cstdlib>
 #include <cstring>
 #include <memory>
 
@@ -25,6 +29,23 @@ template <class T> static T* dev_alloc(size_t n, bool zero = false)
     OB_CUDA(cudaMalloc(&d, std::max<size_t>(n, 1) * sizeof(T)));
     if (zero) OB_CUDA(cudaMemset(d, 0, std::max<size_t>(n, 1) * sizeof(T)));
     return d;
+}
+
+// cuTensorMapEncodeTiled through the runtime's driver entry point (no -lcuda link dependency)
+typedef CUresult (*TensorMapEncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                      const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                      CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static TensorMapEncodeFn tensor_map_encoder()
+{
+    static TensorMapEncodeFn fn = nullptr;
+    if (!fn) {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess || !p)
+            fail(OCTVR_ERR_CUDA, "cuTensorMapEncodeTiled is not available in this driver");
+        fn = (TensorMapEncodeFn)p;
+    }
+    return fn;
 }
 
 // table entry for one ROI pixel: fixed-point source position -> tap offset, fractions, border bits
@@ -54,7 +75,7 @@ octvr_mapper::~octvr_mapper()
     cudaSetDevice(device);
     for (auto p : d_rgbx) cudaFree(p);
     for (auto p : d_vig) cudaFree(p);
-    cudaFree(d_tile_job_start); cudaFree(d_job_cam); cudaFree(d_coords); cudaFree(d_weights);
+    cudaFree(d_tile_job_start); cudaFree(d_job_cam); cudaFree(d_coords); cudaFree(d_weights); cudaFree(d_jobs); cudaFree(d_entries); cudaFree(d_tmaps);
     cudaFree(d_smask); cudaFree(d_gcoord); cudaFree(d_partial); cudaFree(d_ticket);
     cudaFree(d_gains); cudaFree(d_gain_f32); cudaFree(d_gain_flag); cudaFree(d_gain_lut); cudaFree(d_rgb); cudaFree(d_dbg);
     if (h_gains) cudaFreeHost(h_gains);
@@ -131,34 +152,133 @@ static void build_mapper(octvr_mapper& m, const octvr_template& t, const int* in
         job_start[ntiles] = (uint32_t)job_cam.size();
         const size_t njobs = job_cam.size();
         OB_CHECK(njobs * TILE_PX < ((size_t)1 << 32), "table too large");
-        std::vector<uint2> coords(njobs * TILE_PX);
-        std::vector<float> weights(njobs * TILE_PX);
-        for (int tl = 0; tl < ntiles; tl++) {
+        m.njobs = njobs;
+        m.d_tile_job_start = dev_upload(job_start.data(), job_start.size());
+
+        // ---- staged layout: per-job source footprint + 8-byte entries (K_blend_staged) ----
+        // eligible when every source width is a multiple of 4 px (16-byte cp.async chunks) and every job's
+        // footprint fits the shared-memory stage; otherwise the direct-gather kernel and its 12-byte tables are used
+        bool staged = true;
+        for (int i = 0; i < n; i++) staged = staged && m.in_w[i] % 4 == 0;
+        if (const char* e = getenv("OCTVR_BLEND")) { if (std::string(e) == "direct") staged = false; }
+        std::vector<JobMeta> meta(njobs);
+        for (auto& jm : meta) memset(&jm, 0, sizeof(jm));
+        std::map<uint64_t, int> tmap_index;       // (camera, box w, box h) -> descriptor slot
+        auto pixel_of = [&](int tl, int p, int i, int& lx, int& ly) {
             const int tx = tl % tiles_x, ty = tl / tiles_x;
-            for (uint32_t j = job_start[tl]; j < job_start[tl + 1]; j++) {
-                const int i = job_cam[j];
-                const TInput& in = t.inputs[i];
-                for (int p = 0; p < TILE_PX; p++) {
-                    const int gx = tx * TILE_W + (p & (TILE_W - 1)), gy = ty * TILE_H + (p / TILE_W);
-                    const int lx = gx - in.roi.x, ly = gy - in.roi.y;
-                    uint2 e = make_uint2(0u, 0u);
-                    float w = 0.f;
-                    if (lx >= 0 && ly >= 0 && lx < in.roi.w && ly < in.roi.h && gx < t.out_w && gy < t.out_h) {
-                        w = W[i].row(ly)[lx];
-                        e = make_entry(sx[i].row(ly)[lx], sy[i].row(ly)[lx], m.in_w[i], m.in_h[i], in.mask.row(ly)[lx] != 0 && w != 0.f);
+            const int gx = tx * TILE_W + (p & (TILE_W - 1)), gy = ty * TILE_H + (p / TILE_W);
+            lx = gx - t.inputs[i].roi.x; ly = gy - t.inputs[i].roi.y;
+            return lx >= 0 && ly >= 0 && lx < t.inputs[i].roi.w && ly < t.inputs[i].roi.h && gx < t.out_w && gy < t.out_h;
+        };
+        if (staged) {
+            for (int tl = 0; tl < ntiles && staged; tl++)
+                for (uint32_t j = job_start[tl]; j < job_start[tl + 1]; j++) {
+                    const int i = job_cam[j];
+                    const TInput& in = t.inputs[i];
+                    int xmin = INT32_MAX, xmax = INT32_MIN, ymin = INT32_MAX, ymax = INT32_MIN;
+                    for (int p = 0; p < TILE_PX; p++) {
+                        int lx, ly;
+                        if (!pixel_of(tl, p, i, lx, ly)) continue;
+                        const float w = W[i].row(ly)[lx];
+                        const uint2 e = make_entry(sx[i].row(ly)[lx], sy[i].row(ly)[lx], m.in_w[i], m.in_h[i], in.mask.row(ly)[lx] != 0 && w != 0.f);
+                        if (!(e.y & C_VALID)) continue;
+                        const int ix = std::min(32767, std::max(-32768, sx[i].row(ly)[lx] >> 5)), iy = std::min(32767, std::max(-32768, sy[i].row(ly)[lx] >> 5));
+                        xmin = std::min(xmin, ix); xmax = std::max(xmax, ix + 1); ymin = std::min(ymin, iy); ymax = std::max(ymax, iy + 1);
                     }
-                    if (!(e.y & C_VALID)) w = 0.f;
-                    coords[(size_t)j * TILE_PX + p] = e;
-                    weights[(size_t)j * TILE_PX + p] = w;
+                    JobMeta& jm = meta[j];
+                    jm.cam = i;
+                    if (xmin > xmax) { xmin = xmax = ymin = ymax = 0; }
+                    // TMA box: footprint size rounded up to a size class (one tensor map per camera and class in use)
+                    auto size_class = [](int v) { return v <= 64 ? (v + 7) / 8 * 8 : v <= 128 ? (v + 15) / 16 * 16 : (v + 31) / 32 * 32; };
+                    // measured on B200: the innermost TMA start coordinate must be 16-byte aligned (4 px here), else the
+                    // copy raises "illegal instruction"; negative and out-of-range coordinates are fine (zero filled)
+                    jm.bx0 = (int)std::floor(xmin / 4.0) * 4; jm.by0 = ymin;
+                    jm.bw = size_class(xmax - jm.bx0 + 1); jm.bh = size_class(ymax - ymin + 1);
+                    if (jm.bw > 256 || jm.bh > 256 || (int64_t)jm.bw * jm.bh > STAGE_CAP) { staged = false; break; }
+                    const uint64_t key = ((uint64_t)i << 32) | ((uint64_t)jm.bw << 16) | (uint64_t)jm.bh;
+                    auto it = tmap_index.find(key);
+                    if (it == tmap_index.end()) it = tmap_index.emplace(key, (int)tmap_index.size()).first;
+                    jm.tmap = it->second;
+                }
+            // pack each tile's jobs into stage-sized groups (almost always one group)
+            for (int tl = 0; tl < ntiles && staged; tl++) {
+                int grp = 0, used_px = 0;
+                for (uint32_t j = job_start[tl]; j < job_start[tl + 1]; j++) {
+                    const int area = meta[j].bw * meta[j].bh;
+                    if (used_px + area > STAGE_CAP) { grp++; used_px = 0; }
+                    meta[j].soff = used_px; meta[j].grp_nj = (grp << 8) | (int)(job_start[tl + 1] - job_start[tl]); meta[j].j0 = (int)job_start[tl];
+                    used_px += area;
                 }
             }
         }
-        m.njobs = njobs;
-        m.d_tile_job_start = dev_upload(job_start.data(), job_start.size());
-        m.d_job_cam = dev_upload(job_cam.data(), job_cam.size());
-        m.d_coords = dev_upload(coords.data(), coords.size());
-        m.d_weights = dev_upload(weights.data(), weights.size());
-        m.table_bytes = (int64_t)(coords.size() * sizeof(uint2) + weights.size() * sizeof(float) + job_cam.size() + job_start.size() * 4);
+        m.staged = staged;
+        if (staged) {
+            std::vector<uint2> entries(njobs * TILE_PX, make_uint2(0u, 0u));
+            for (int tl = 0; tl < ntiles; tl++)
+                for (uint32_t j = job_start[tl]; j < job_start[tl + 1]; j++) {
+                    const int i = job_cam[j];
+                    const TInput& in = t.inputs[i];
+                    const JobMeta& jm = meta[j];
+                    for (int p = 0; p < TILE_PX; p++) {
+                        int lx, ly;
+                        if (!pixel_of(tl, p, i, lx, ly)) continue;
+                        const float w = W[i].row(ly)[lx];
+                        const int32_t fsx = sx[i].row(ly)[lx], fsy = sy[i].row(ly)[lx];
+                        const uint2 e = make_entry(fsx, fsy, m.in_w[i], m.in_h[i], in.mask.row(ly)[lx] != 0 && w != 0.f);
+                        if (!(e.y & C_VALID)) continue;
+                        const int ix = std::min(32767, std::max(-32768, fsx >> 5)), iy = std::min(32767, std::max(-32768, fsy >> 5));
+                        const uint32_t off = (uint32_t)(jm.soff + (iy - jm.by0) * jm.bw + (ix - jm.bx0));
+                        uint32_t wbits; memcpy(&wbits, &w, 4);
+                        entries[(size_t)j * TILE_PX + p] = make_uint2(off | ((uint32_t)(fsx & 31) << 16) | ((uint32_t)(fsy & 31) << 21), wbits);
+                    }
+                }
+            // tensor maps over the mapper-owned RGBX planes (static addresses): u32 elements, no swizzle, zero OOB fill
+            std::vector<CUtensorMap> tmaps(tmap_index.size());
+            for (auto& kv : tmap_index) {
+                const int cam = (int)(kv.first >> 32), bw = (int)((kv.first >> 16) & 0xFFFF), bh = (int)(kv.first & 0xFFFF);
+                const cuuint64_t gdim[2] = { (cuuint64_t)m.in_w[cam], (cuuint64_t)m.in_h[cam] };
+                const cuuint64_t gstride[1] = { (cuuint64_t)m.in_w[cam] * 4 };
+                const cuuint32_t box[2] = { (cuuint32_t)bw, (cuuint32_t)bh };
+                const cuuint32_t estr[2] = { 1, 1 };
+                CUresult r = tensor_map_encoder()(&tmaps[kv.second], CU_TENSOR_MAP_DATA_TYPE_UINT32, 2, m.d_rgbx[cam], gdim, gstride, box, estr,
+                                                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                                                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                if (r != CUDA_SUCCESS) fail(OCTVR_ERR_CUDA, "cuTensorMapEncodeTiled failed (" + std::to_string((int)r) + ")");
+            }
+            m.d_tmaps = (void*)dev_upload(tmaps.data(), tmaps.size());
+            std::vector<JobMeta> recs((size_t)ntiles * MAX_CAMS);
+            for (auto& r : recs) memset(&r, 0, sizeof(r));
+            for (int tl = 0; tl < ntiles; tl++)
+                for (uint32_t j = job_start[tl]; j < job_start[tl + 1]; j++) recs[(size_t)tl * MAX_CAMS + (j - job_start[tl])] = meta[j];
+            m.d_jobs = dev_upload(recs.data(), recs.size());
+            m.d_entries = dev_upload(entries.data(), entries.size());
+            m.table_bytes = (int64_t)(entries.size() * sizeof(uint2) + (size_t)ntiles * 64 * 3);   // ~3 records read per tile
+            m.n_tmaps = (int)tmaps.size();
+        } else {
+            std::vector<uint2> coords(njobs * TILE_PX);
+            std::vector<float> weights(njobs * TILE_PX);
+            for (int tl = 0; tl < ntiles; tl++)
+                for (uint32_t j = job_start[tl]; j < job_start[tl + 1]; j++) {
+                    const int i = job_cam[j];
+                    const TInput& in = t.inputs[i];
+                    for (int p = 0; p < TILE_PX; p++) {
+                        int lx, ly;
+                        uint2 e = make_uint2(0u, 0u);
+                        float w = 0.f;
+                        if (pixel_of(tl, p, i, lx, ly)) {
+                            w = W[i].row(ly)[lx];
+                            e = make_entry(sx[i].row(ly)[lx], sy[i].row(ly)[lx], m.in_w[i], m.in_h[i], in.mask.row(ly)[lx] != 0 && w != 0.f);
+                        }
+                        if (!(e.y & C_VALID)) w = 0.f;
+                        coords[(size_t)j * TILE_PX + p] = e;
+                        weights[(size_t)j * TILE_PX + p] = w;
+                    }
+                }
+            m.d_job_cam = dev_upload(job_cam.data(), job_cam.size());
+            m.d_coords = dev_upload(coords.data(), coords.size());
+            m.d_weights = dev_upload(weights.data(), weights.size());
+            m.table_bytes = (int64_t)(coords.size() * sizeof(uint2) + weights.size() * sizeof(float) + job_cam.size() + job_start.size() * 4);
+        }
     }
 
     // ---- gain compensation tables (mapper.cpp:94-99,113-114,235-237) ----
@@ -284,6 +404,22 @@ void ob::mapper_stitch_internal(octvr_mapper& m, const octvr_frame* in, int n_in
     if (m.keep_rgb && !m.d_rgb) m.d_rgb = dev_alloc<uint8_t>((size_t)m.out_w * m.out_h * 3, true);
     if (m.mb) {
         ob::multiband_stitch(m, out, s);
+    } else if (m.staged) {
+        StagedParams sp;
+        memset(&sp, 0, sizeof(sp));
+        for (int i = 0; i < m.n; i++) { sp.rgbx[i] = m.d_rgbx[i]; sp.src_w[i] = m.in_w[i]; sp.src_h[i] = m.in_h[i]; }
+        sp.jobs = m.d_jobs; sp.entries = m.d_entries; sp.tmaps = m.d_tmaps;
+        sp.tiles_x = m.tiles_x; sp.tiles_y = m.tiles_y; sp.out_w = m.out_w; sp.out_h = m.out_h;
+        if (out) {
+            sp.oy = out->y; sp.ou = out->u; sp.ov = out->v;
+            sp.oy_pitch = (uint32_t)out->y_pitch; sp.ou_pitch = (uint32_t)out->u_pitch; sp.ov_pitch = (uint32_t)out->v_pitch;
+            sp.uv_step = out->uv_pixel_stride;
+        }
+        sp.rgb_out = m.keep_rgb ? m.d_rgb : nullptr; sp.rgb_pitch = (uint32_t)m.out_w * 3;
+        sp.gain_f32 = m.d_gain_f32; sp.gain_flag = m.d_gain_flag; sp.gain_lut = m.d_gain_lut;
+        sp.use_gain = m.gain ? 1 : 0;
+        sp.inv_n = m.inv_n;
+        launch_blend_staged(sp, s);
     } else {
         BlendParams bp;
         memset(&bp, 0, sizeof(bp));

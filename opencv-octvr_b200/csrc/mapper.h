@@ -22,6 +22,12 @@ struct octvr_mapper {
     uint8_t* d_job_cam = nullptr;
     uint2* d_coords = nullptr;
     float* d_weights = nullptr;
+    // staged layout (K_blend_staged)
+    bool staged = false;
+    ob::JobMeta* d_jobs = nullptr;
+    uint2* d_entries = nullptr;
+    void* d_tmaps = nullptr;
+    int n_tmaps = 0;
     // gain compensation
     ob::GainParams gp;
     uint8_t* d_smask = nullptr; uint2* d_gcoord = nullptr; double* d_partial = nullptr;
