@@ -50,13 +50,29 @@ __device__ __forceinline__ uint32_t yuv_px(uint32_t Y, int ruv, int guv, int buv
            ((uint32_t)__vimin_s32_relu((yy + buv) >> 20, 255) << 16);
 }
 
+// one converted source pixel straight from the input planes (same arithmetic as K_convert) -- used by the gain kernel
+__device__ __forceinline__ uint32_t source_px(const CamSrc& c, int x, int y)
+{
+    const int Y = __ldg(c.y + (size_t)y * c.y_pitch + x);
+    const int u = (int)__ldg(c.u + (size_t)(y >> 1) * c.u_pitch + (size_t)(x >> 1) * c.uv_step) - 128;
+    const int v = (int)__ldg(c.v + (size_t)(y >> 1) * c.v_pitch + (size_t)(x >> 1) * c.uv_step) - 128;
+    uint32_t px = yuv_px((uint32_t)Y, (1 << 19) + 1673527 * v, (1 << 19) - 852492 * v - 409993 * u, (1 << 19) + 2116026 * u);
+    if (c.vignette) px = vignette_rgbx(px, __ldg(c.vignette + (size_t)y * c.w + x));
+    return px;
+}
+
 // one thread: 8 px x 2 rows (four chroma samples).  CTA = 32 x 8 threads = 256 x 16 px.
 // grid = (ceil(max_w/256), ceil(max_h/16), cameras); CTAs outside a smaller camera exit at once.
-__global__ void __launch_bounds__(256) k_convert(const ConvertParams p)
+__device__ __forceinline__ void convert_body(const ConvertParams& p, int block)
 {
-    const CamSrc& c = p.cam[blockIdx.z];
-    const int x0 = (blockIdx.x << 8) + (threadIdx.x << 3);
-    const int y0 = (blockIdx.y << 4) + (threadIdx.y << 1);
+    // block -> (column block, row block, camera) of the (grid_x, grid_y, n) convert grid
+    const int per_cam = p.grid_x * p.grid_y;
+    const int cam = block / per_cam, rem = block - cam * per_cam;
+    const int by = rem / p.grid_x, bx = rem - by * p.grid_x;
+    const CamSrc& c = p.cam[cam];
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+    const int x0 = (bx << 8) + (tx << 3);
+    const int y0 = (by << 4) + (ty << 1);
     if (x0 >= c.w || y0 >= c.h) return;
     const int w = c.w;
     const uint8_t* yr0 = c.y + (size_t)y0 * c.y_pitch + x0;
@@ -121,10 +137,6 @@ __global__ void __launch_bounds__(256) k_convert(const ConvertParams p)
     }
 }
 
-void launch_convert(const ConvertParams& p, cudaStream_t s)
-{
-    k_convert<<<dim3(p.grid_x, p.grid_y, p.n), dim3(32, 8), 0, s>>>(p);
-}
 
 // ------------------------------------------------------------------------------------------------
 // K_gain
@@ -269,10 +281,10 @@ __device__ void gain_tables(const GainParams& p)
 // tables.  Deterministic; no host round trip.
 constexpr int MAX_PAIRS = MAX_CAMS * (MAX_CAMS + 1) / 2;
 __device__ __forceinline__ unsigned long long gtime() { unsigned long long t; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t)); return t; }
-constexpr int GAIN_BLK = 1024;                             // one CTA per SM, 1024 canvas pixels per chunk
-__global__ void __launch_bounds__(GAIN_BLK) k_gain_stats_solve(const GainParams p)
+constexpr int GAIN_BLK = 256;                              // canvas pixels per chunk = CTA size of the fused kernel
+constexpr int GAIN_BATCH = 8;
+__device__ __forceinline__ void gain_body(const GainParams& p, double* s_nrm, const unsigned gain_blocks)   // s_nrm: [n][GAIN_BLK]
 {
-    extern __shared__ double s_nrm[];                       // [n][GAIN_BLK]
     __shared__ double s_part[3 * MAX_PAIRS];
     __shared__ double Nm[MAX_CAMS * MAX_CAMS], Im[MAX_CAMS * MAX_CAMS], Aug[MAX_CAMS * (MAX_CAMS + 1)];
     __shared__ uint8_t s_pi[MAX_PAIRS], s_pj[MAX_PAIRS];
@@ -283,32 +295,39 @@ __global__ void __launch_bounds__(GAIN_BLK) k_gain_stats_solve(const GainParams 
     for (int q = tid; q < nq; q += GAIN_BLK) s_part[q] = 0;
     if (tid == 0) { int q = 0; for (int i = 0; i < n; i++) for (int j = i; j < n; j++, q++) { s_pi[q] = (uint8_t)i; s_pj[q] = (uint8_t)j; } }
     const int area = p.cw * p.ch, nchunks = (area + GAIN_BLK - 1) / GAIN_BLK;
-    for (int chunk = blockIdx.x; chunk < nchunks; chunk += gridDim.x) {
+    for (int chunk = blockIdx.x; chunk < nchunks; chunk += gain_blocks) {
         __syncthreads();
         const int pix = chunk * GAIN_BLK + tid;
         const int X = p.cx0 + pix % p.cw, Y = pix < area ? p.cy0 + pix / p.cw : -0x40000000;
         #pragma unroll 1
-        for (int c0 = 0; c0 < n; c0 += 4) {
-            uint32_t t[4]; bool in[4]; uint2 cc[4]; uint32_t tap[4][4];
+        for (int c0 = 0; c0 < n; c0 += GAIN_BATCH) {        // GAIN_BATCH cameras at a time: every dependent load step has
+            uint32_t t[GAIN_BATCH]; bool in[GAIN_BATCH]; uint2 cc[GAIN_BATCH]; uint32_t tap[GAIN_BATCH][4];   // that many requests in flight
             #pragma unroll
-            for (int u = 0; u < 4; u++) {
+            for (int u = 0; u < GAIN_BATCH; u++) {
                 const GainCam gc = p.cam[min(c0 + u, n - 1)];
                 const int lx = X - gc.sx, ly = Y - gc.sy;
                 in[u] = c0 + u < n && lx >= 0 && ly >= 0 && lx < gc.sw && ly < gc.sh;
                 t[u] = gc.off + ly * gc.sw + lx;
             }
             #pragma unroll
-            for (int u = 0; u < 4; u++) in[u] = in[u] && __ldg(p.smask + t[u]) == 255;
+            for (int u = 0; u < GAIN_BATCH; u++) cc[u] = in[u] ? __ldg(p.gcoord + t[u]) : make_uint2(0xFFFFFFFFu, 0u);
             #pragma unroll
-            for (int u = 0; u < 4; u++) cc[u] = in[u] ? __ldg(p.gcoord + t[u]) : make_uint2(0u, 0u);
+            for (int u = 0; u < GAIN_BATCH; u++) in[u] = cc[u].x != 0xFFFFFFFFu;      // marker: working-scale mask != 255 there
             #pragma unroll
-            for (int u = 0; u < 4; u++) {
+            for (int u = 0; u < GAIN_BATCH; u++) {
                 tap[u][0] = tap[u][1] = tap[u][2] = tap[u][3] = 0u;
-                const int c = min(c0 + u, n - 1);
-                if (cc[u].y & C_VALID) fetch_taps(p.rgbx[c], p.src_pitch[c], cc[u], tap[u][0], tap[u][1], tap[u][2], tap[u][3]);
+                if (cc[u].y & C_VALID) {
+                    const CamSrc& sc = p.src[min(c0 + u, n - 1)];
+                    const int ix = (int)(cc[u].x & 0xFFFFu) - 1, iy = (int)(cc[u].x >> 16) - 1;
+                    const uint32_t bits = (cc[u].y & C_BORDER) ? (cc[u].y >> C_TAP_SHIFT) : 15u;
+                    if (bits & 1u) tap[u][0] = source_px(sc, ix, iy);
+                    if (bits & 2u) tap[u][1] = source_px(sc, ix + 1, iy);
+                    if (bits & 4u) tap[u][2] = source_px(sc, ix, iy + 1);
+                    if (bits & 8u) tap[u][3] = source_px(sc, ix + 1, iy + 1);
+                }
             }
             #pragma unroll
-            for (int u = 0; u < 4; u++) {
+            for (int u = 0; u < GAIN_BATCH; u++) {
                 int r, g, b;
                 bilerp_rgbx(tap[u][0], tap[u][1], tap[u][2], tap[u][3], cc[u].y & 31u, (cc[u].y >> 5) & 31u, r, g, b);
                 if (c0 + u < n) s_nrm[(c0 + u) * GAIN_BLK + tid] = in[u] ? sqrt((double)(r * r + g * g + b * b)) : -1.0;
@@ -335,24 +354,30 @@ __global__ void __launch_bounds__(GAIN_BLK) k_gain_stats_solve(const GainParams 
     __threadfence();
     __syncthreads();
     if (tid == 0) {
-        const unsigned int t = atomicInc(p.ticket, gridDim.x - 1);   // wraps to 0: self-resetting
-        is_last = (t == gridDim.x - 1);
+        const unsigned int t = atomicInc(p.ticket, gain_blocks - 1);   // wraps to 0: self-resetting
+        is_last = (t == gain_blocks - 1);
     }
     __syncthreads();
     if (!is_last) return;
     const unsigned long long T1 = gtime();
     __threadfence();
     for (int k = tid; k < n * n; k += GAIN_BLK) { Nm[k] = 0; Im[k] = 0; }
-    // CTA partials -> totals: one warp per value, lanes over CTAs (grid <= 160), fixed summation order
-    for (int q = warp; q < nq; q += GAIN_BLK / 32) {
-        double t[5];
-        #pragma unroll
-        for (int u = 0; u < 5; u++) {
-            const unsigned k = lane + 32 * u;
-            t[u] = k < gridDim.x ? __ldcg(p.partial + (size_t)k * nq + q) : 0.0;
+    // CTA partials -> totals in a fixed order: thread = (value q, slice of the CTAs); 8 independent loads in flight
+    {
+        __shared__ double s_slice[4][3 * MAX_PAIRS];
+        for (int q = tid & 63; q < nq; q += 64) {
+            const int slice = tid >> 6;
+            double acc = 0;
+            for (unsigned k0 = slice; k0 < gain_blocks; k0 += 32) {
+                double t[8];
+                #pragma unroll
+                for (int u = 0; u < 8; u++) { const unsigned k = k0 + 4 * u; t[u] = k < gain_blocks ? __ldcg(p.partial + (size_t)k * nq + q) : 0.0; }
+                acc += ((t[0] + t[1]) + (t[2] + t[3])) + ((t[4] + t[5]) + (t[6] + t[7]));
+            }
+            s_slice[slice][q] = acc;
         }
-        const double v = warp_sum(((t[0] + t[1]) + (t[2] + t[3])) + t[4]);
-        if (lane == 0) s_part[q] = v;
+        __syncthreads();
+        for (int q = tid; q < nq; q += 256) s_part[q] = (s_slice[0][q] + s_slice[1][q]) + (s_slice[2][q] + s_slice[3][q]);
     }
     __syncthreads();
     if (tid < np) {
@@ -373,17 +398,28 @@ __global__ void __launch_bounds__(GAIN_BLK) k_gain_stats_solve(const GainParams 
     if (warp == 0) { gain_solve_warp(n, Nm, Im, Aug, p.gains); __threadfence(); }
     __syncthreads();
     const unsigned long long T3 = gtime();
-    if (tid < 256) gain_tables(p);          // 256 threads = the 256 input values (named barrier inside)
+    gain_tables(p);                         // 256 threads = the 256 input values
     if (tid == 0 && p.dbg) { p.dbg[0] = T0; p.dbg[1] = T1; p.dbg[2] = T2; p.dbg[3] = T3; p.dbg[4] = gtime(); }
 }
 
 __global__ void __launch_bounds__(256) k_gain_finalize(const GainParams p) { gain_tables(p); }
 
-void launch_gain_stats_solve(const GainParams& p, cudaStream_t s)
+// Horizontally fused front end of a frame: the first `gain_blocks` CTAs compute the gain statistics and solve (they
+// read the input planes directly, so they do not depend on the conversion), all other CTAs convert the inputs to
+// RGBX.  One launch, both parts run concurrently, no cross-stream synchronisation.
+__global__ void __launch_bounds__(256, 4) k_convert_gain(const __grid_constant__ ConvertParams cp, const __grid_constant__ GainParams gp, const unsigned gain_blocks)
 {
-    const size_t smem = (size_t)p.n * GAIN_BLK * sizeof(double);
-    if (smem > 40 * 1024) cudaFuncSetAttribute(k_gain_stats_solve, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(MAX_CAMS * GAIN_BLK * sizeof(double)));
-    k_gain_stats_solve<<<p.grid, GAIN_BLK, smem, s>>>(p);
+    extern __shared__ double s_dyn_nrm[];
+    if (blockIdx.x < gain_blocks) gain_body(gp, s_dyn_nrm, gain_blocks);
+    else convert_body(cp, (int)(blockIdx.x - gain_blocks));
+}
+
+void launch_convert_gain(const ConvertParams& cp, const GainParams* gp, cudaStream_t s)
+{
+    static const GainParams none = {};
+    const unsigned gb = gp ? (unsigned)gp->grid : 0u;
+    const size_t smem = gp ? (size_t)gp->n * GAIN_BLK * sizeof(double) : 0;
+    k_convert_gain<<<gb + (unsigned)(cp.grid_x * cp.grid_y * cp.n), 256, smem, s>>>(cp, gp ? *gp : none, gb);
 }
 void launch_gain_finalize(const GainParams& p, cudaStream_t s) { k_gain_finalize<<<1, 256, 0, s>>>(p); }
 

@@ -19,7 +19,7 @@ struct ConvertParams {
     int n;
     int grid_x, grid_y;              // ceil(max w / 256), ceil(max h / 16)
 };
-void launch_convert(const ConvertParams& p, cudaStream_t s);
+
 
 // ---- K_gain: working-scale statistics, least-squares solve, exact gain tables ----
 struct GainCam {
@@ -28,12 +28,12 @@ struct GainCam {
 };
 struct GainParams {
     GainCam cam[MAX_CAMS];
-    const uint32_t* rgbx[MAX_CAMS];
-    int src_pitch[MAX_CAMS];
+    CamSrc src[MAX_CAMS];      // this frame's input planes: the gain samples are converted on the fly, so the kernel
+                               // does not depend on K_convert and runs concurrently with it on a second stream
     int n;
     uint32_t total;            // sum of sw*sh
     const uint8_t* smask;      // linearly resized masks (mapper.cpp:113-114)
-    const uint2* gcoord;       // table entry of the NEAREST-resized pixel (mapper.cpp:235-237)
+    const uint2* gcoord;       // NEAREST-resized sample (mapper.cpp:235-237): x = (ix+1) | (iy+1)<<16 of the top-left tap, y = fx|fy<<5|flags
     int cx0, cy0, cw, ch;      // working-scale canvas = union of the scaled ROIs
     int n_pairs, grid;         // pairs (i<=j); CTAs launched
     double* partial;           // [grid][n_pairs][3] : count, sum_i, sum_j
@@ -44,7 +44,8 @@ struct GainParams {
     uint8_t* gain_lut;         // [n][256] exact sat_u8(rint(v*g)) in f64
     unsigned long long* dbg;   // optional: %globaltimer stamps of the last CTA (start, ticket, reduced, solved, done)
 };
-void launch_gain_stats_solve(const GainParams& p, cudaStream_t s);
+// gp == nullptr: conversion only
+void launch_convert_gain(const ConvertParams& cp, const GainParams* gp, cudaStream_t s);
 void launch_gain_finalize(const GainParams& p, cudaStream_t s);   // gains[] already set (predefined gains)
 
 // ---- K_blend: fused remap (1/32-px fixed-point bilinear) + gain + weighted accumulate + normalise

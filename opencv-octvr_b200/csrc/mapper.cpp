@@ -303,7 +303,13 @@ static void build_mapper(octvr_mapper& m, const octvr_template& t, const int* in
                 const int ly = std::min((int)std::floor(dy * ify), in.roi.h - 1);
                 for (int dx = 0; dx < c.sw; dx++) {
                     const int lx = std::min((int)std::floor(dx * ifx), in.roi.w - 1);
-                    gcoord.push_back(make_entry(sx[i].row(ly)[lx], sy[i].row(ly)[lx], m.in_w[i], m.in_h[i], in.mask.row(ly)[lx] != 0));
+                    uint2 e = make_entry(sx[i].row(ly)[lx], sy[i].row(ly)[lx], m.in_w[i], m.in_h[i], in.mask.row(ly)[lx] != 0);
+                    if (e.y & C_VALID) {        // the gain kernel reads the input planes directly: keep (ix, iy), not a plane offset
+                        const int ix = std::min(32767, std::max(-32768, sx[i].row(ly)[lx] >> 5)), iy = std::min(32767, std::max(-32768, sy[i].row(ly)[lx] >> 5));
+                        e.x = (uint32_t)(ix + 1) | ((uint32_t)(iy + 1) << 16);
+                    }
+                    if (sm.row(dy)[dx] != 255) e = make_uint2(0xFFFFFFFFu, 0u);     // CPU compensator's intersect rule: mask == 255
+                    gcoord.push_back(e);
                 }
             }
             off += (uint32_t)c.sw * c.sh;
@@ -316,7 +322,7 @@ static void build_mapper(octvr_mapper& m, const octvr_template& t, const int* in
             x1 = std::max(x1, g.cam[i].sx + g.cam[i].sw); y1 = std::max(y1, g.cam[i].sy + g.cam[i].sh);
         }
         g.cx0 = x0; g.cy0 = y0; g.cw = x1 - x0; g.ch = y1 - y0;
-        g.grid = std::max(1, std::min(148, (g.cw * g.ch + 1023) / 1024));
+        g.grid = std::max(1, std::min(256, (g.cw * g.ch + 255) / 256));
         m.d_smask = dev_upload(smask.data(), smask.size());
         m.d_gcoord = dev_upload(gcoord.data(), gcoord.size());
         m.d_partial = dev_alloc<double>((size_t)g.n_pairs * g.grid * 3, true);
@@ -329,10 +335,10 @@ static void build_mapper(octvr_mapper& m, const octvr_template& t, const int* in
         g.smask = m.d_smask; g.gcoord = m.d_gcoord; g.partial = m.d_partial; g.ticket = m.d_ticket;
         m.d_dbg = dev_alloc<unsigned long long>(8, true); g.dbg = m.d_dbg;
         g.gains = m.d_gains; g.gain_f32 = m.d_gain_f32; g.gain_flag = m.d_gain_flag; g.gain_lut = m.d_gain_lut;
-        for (int i = 0; i < n; i++) { g.rgbx[i] = m.d_rgbx[i]; g.src_pitch[i] = m.in_w[i]; }
         m.table_bytes += (int64_t)(smask.size() + gcoord.size() * sizeof(uint2));
     }
     for (auto& e : m.ev) OB_CUDA(cudaEventCreate(&e));
+
 }
 
 static void check_frame(const octvr_frame& f, int w, int h, const char* what)
@@ -381,16 +387,21 @@ void ob::mapper_stitch_internal(octvr_mapper& m, const octvr_frame* in, int n_in
         cp.grid_x = std::max(cp.grid_x, (c.w + 255) / 256);
         cp.grid_y = std::max(cp.grid_y, (c.h + 15) / 16);
     }
-    launch_convert(cp, s);
+    // one launch: gain statistics + solve (reading the input planes directly) in the first CTAs, conversion in the rest
+    const bool compute_gains = m.gain && !d_gains_src && !gains;
+    if (compute_gains) {
+        GainParams gp = m.gp;
+        for (int i = 0; i < m.n; i++) gp.src[i] = cp.cam[i];
+        launch_convert_gain(cp, &gp, s);
+    } else
+        launch_convert_gain(cp, nullptr, s);
     if (m.profiling) OB_CUDA(cudaEventRecord(m.ev[1], s));
 
     if (m.gain) {
         if (d_gains_src) {
             OB_CUDA(cudaMemcpyAsync(m.d_gains, d_gains_src, sizeof(double) * m.n, cudaMemcpyDeviceToDevice, s));
             launch_gain_finalize(m.gp, s);
-        } else if (!gains) {
-            launch_gain_stats_solve(m.gp, s);
-        } else {
+        } else if (gains) {
             OB_CHECK(n_gains == m.n, "gains size must equal the number of inputs");
             // the previous frame may still be reading h_gains: wait for it before overwriting
             if (m.last_stream_valid) OB_CUDA(cudaStreamSynchronize(m.last_stream));
@@ -527,7 +538,7 @@ octvr_status octvr_mapper_stats(const octvr_mapper* m, int64_t* pairs, int64_t* 
         if (pairs) *pairs = m->pairs;
         if (roi_area) *roi_area = m->roi_area;
         if (table_bytes) *table_bytes = m->table_bytes;
-        if (launches) *launches = m->mb ? ob::multiband_launches(*m) + 1 + (m->gain ? 1 : 0) : 2 + (m->gain ? 1 : 0);
+        if (launches) *launches = m->mb ? ob::multiband_launches(*m) + 1 : 2;
     });
 }
 
