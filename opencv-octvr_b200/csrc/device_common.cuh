@@ -52,6 +52,14 @@ __device__ __forceinline__ float gain_apply_f32(float v, float g32)
     return fminf(__fadd_rn(__fmaf_rn(v, g32, MAGIC_RN), -MAGIC_RN), 255.f);
 }
 
+// The same value from t = 2^23 + v (what the fused kernel's floor-by-magic-add leaves in the register):
+// fma(t, g, C) with C = MAGIC_RN - 2^23 g has the same real argument v g + MAGIC_RN as gain_apply_f32, hence the same
+// rounding, provided C is exactly representable; gain_tables() verifies both forms against the f64 rule per camera.
+__device__ __forceinline__ float gain_bias_f32(float g32) { return __fmaf_rn(-MAGIC_RD, g32, MAGIC_RN); }
+__device__ __forceinline__ float gain_apply_biased(float t, float g32, float c)
+{
+    return fminf(__fadd_rn(__fmaf_rn(t, g32, c), -MAGIC_RN), 255.f);
+}
 
 // RGB888 -> Y, U, V of cv::cvtColor(RGB2YUV_I420) (imgproc/src/color.cpp:6456-6481), no clamps needed:
 // the coefficient sums keep Y in [16,235] and U,V in [16,240] for 8-bit inputs.
@@ -66,6 +74,15 @@ __device__ __forceinline__ uint32_t rgb_cb(int R, int G, int B)
 __device__ __forceinline__ uint32_t rgb_cr(int R, int G, int B)
 {
     return (uint32_t)(460324 * R - 385875 * G - 74448 * B + (1 << 19) + (128 << 20)) >> 20;
+}
+
+// dst_16s.convertTo(CV_8UC3, 1.0/N): sat_u8(rint((float)acc * (float)(1/N))), packed R | G<<8 | B<<16
+__device__ __forceinline__ uint32_t normalise_px(uint32_t ar, uint32_t ag, uint32_t ab, float inv_n)
+{
+    const int R = min(__float2int_rn(__fmul_rn((float)(int)ar, inv_n)), 255);
+    const int G = min(__float2int_rn(__fmul_rn((float)(int)ag, inv_n)), 255);
+    const int B = min(__float2int_rn(__fmul_rn((float)(int)ab, inv_n)), 255);
+    return (uint32_t)R | ((uint32_t)G << 8) | ((uint32_t)B << 16);
 }
 
 }  // namespace ob

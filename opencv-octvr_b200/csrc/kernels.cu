@@ -256,7 +256,7 @@ __device__ void gain_tables(const GainParams& p)
             for (int k = 0; k < 5; k++) {                   // candidate k: (float)g + {0,+1,-1,+2,-2} ulp
                 const int step = (k == 0) ? 0 : (k & 1) ? (k + 1) / 2 : -(k / 2);
                 const float gc = __int_as_float(__float_as_int(g0) + step);
-                if ((int)gain_apply_f32((float)v, gc) == exact) ok |= 1u << k;
+                if ((int)gain_apply_f32((float)v, gc) == exact && (int)gain_apply_biased(MAGIC_RD + (float)v, gc, gain_bias_f32(gc)) == exact) ok |= 1u << k;
             }
         }
         if (ok != 0x1Fu) atomicAnd(&s_ok[c], ok);
@@ -471,14 +471,6 @@ __device__ __forceinline__ void blend_pair(const JobInfo& ji, uint2 cc, float ww
     ab += (uint32_t)__float_as_int(__fadd_rd(__fmul_rn(bf, ww), MAGIC_RD)) - 0x4B000000u;
 }
 
-// dst_16s.convertTo(CV_8UC3, 1.0/N): sat_u8(rint((float)acc * (float)(1/N))), packed R | G<<8 | B<<16
-__device__ __forceinline__ uint32_t normalise_px(uint32_t ar, uint32_t ag, uint32_t ab, float inv_n)
-{
-    const int R = min(__float2int_rn(__fmul_rn((float)(int)ar, inv_n)), 255);
-    const int G = min(__float2int_rn(__fmul_rn((float)(int)ag, inv_n)), 255);
-    const int B = min(__float2int_rn(__fmul_rn((float)(int)ab, inv_n)), 255);
-    return (uint32_t)R | ((uint32_t)G << 8) | ((uint32_t)B << 16);
-}
 __device__ __forceinline__ uint32_t luma(uint32_t px)
 {
     return (269484u * (px & 255u) + 528482u * ((px >> 8) & 255u) + 102760u * ((px >> 16) & 255u) + (1u << 19) + (16u << 20)) >> 20;

@@ -96,4 +96,44 @@ struct StagedParams {
 };
 void launch_blend_staged(const StagedParams& p, cudaStream_t s);
 
+// ---- K_stitch_fused: the whole feather / no-blend frame in ONE kernel, no intermediate image in HBM ----
+//      Persistent CTAs (4 per SM) walk a host-balanced list of 32x32 output tiles.  For every (tile, camera) job the
+//      CTA (1) converts the job's SOURCE BOX of the 4:2:0 input planes (L2-resident, 37 MB for the 6 x 2.7K rig)
+//      straight into an RGBX stage in shared memory (same integer BT.601 arithmetic as K_convert), (2) gathers the
+//      four bilinear taps per output pixel from that stage with LDS, interpolates (IDP.2A), applies gain and weight
+//      and accumulates in registers; the tile is then normalised, converted to YUV 4:2:0 and stored with 128-bit
+//      stores.  The 8 B/pair table entries of job k+1 arrive by a TMA bulk copy (cp.async.bulk + mbarrier) while
+//      job k is processed; the input bytes of job k+1 are prefetched into registers.
+constexpr int FT_W = 32, FT_H = 32, FT_PX = FT_W * FT_H, FT_THREADS = 256, FT_PPT = FT_PX / FT_THREADS;
+constexpr int FUSED_CAP = 8192;          // RGBX stage capacity in pixels (32 KB); a job whose box is larger is split by rows
+constexpr int FUSED_MAXJ = 32;           // jobs per tile (cameras x row splits)
+struct FJob {                            // 32 B
+    int cam;
+    int bx0, by0;                        // top-left of the source box (bx0 % 8 == 0, by0 % 2 == 0, may be negative)
+    int bw, bh;                          // box size in px (bw % 8 == 0, bh % 2 == 0, bw * bh <= FUSED_CAP)
+    int groups;                          // bw / 8: conversion items (8 px x 2 rows) per row pair
+    uint32_t rcp;                        // ceil(2^20 / groups): item -> row pair without a division
+    int nitems;                          // groups * bh / 2  (<= 2 per thread)
+};
+struct FTile { int tx, ty, nj, j0; };    // tile position (tile units), jobs, first job (entries of job j at j * FT_PX)
+struct FTileBlock { FJob job[FUSED_MAXJ]; FTile tile; };     // one self-contained record per tile, in schedule order
+static_assert(sizeof(FJob) == 32 && sizeof(FTileBlock) == 32 * FUSED_MAXJ + 16, "FTileBlock is read as uint4s");
+struct FusedParams {
+    CamSrc cam[MAX_CAMS];
+    int n;
+    const FTileBlock* blocks;            // [tiles], grouped by CTA
+    const int* bin_start;                // [grid + 1]: CTA b owns blocks [bin_start[b], bin_start[b+1])
+    const uint2* entries;                // [jobs * FT_PX]: {byte offset in the stage | fy << 16 | fx << 24, f32 weight}
+    int out_w, out_h;
+    uint8_t* oy; uint8_t* ou; uint8_t* ov;
+    uint32_t oy_pitch, ou_pitch, ov_pitch;
+    int uv_step;
+    uint8_t* rgb_out; uint32_t rgb_pitch;
+    const float* gain_f32; const int* gain_flag; const uint8_t* gain_lut;
+    int use_gain;
+    float inv_n;
+};
+int fused_ctas_per_sm();                 // occupancy of k_stitch_fused (sizes the persistent grid)
+void launch_stitch_fused(const FusedParams& p, int grid, cudaStream_t s);
+
 }  // namespace ob

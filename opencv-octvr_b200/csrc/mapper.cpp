@@ -11,6 +11,8 @@
 #include <cstdlib>
 #include <cstring>
 #include <memory>
+#include <functional>
+#include <queue>
 
 using namespace ob;
 
@@ -75,12 +77,156 @@ octvr_mapper::~octvr_mapper()
     cudaSetDevice(device);
     for (auto p : d_rgbx) cudaFree(p);
     for (auto p : d_vig) cudaFree(p);
-    cudaFree(d_tile_job_start); cudaFree(d_job_cam); cudaFree(d_coords); cudaFree(d_weights); cudaFree(d_jobs); cudaFree(d_entries); cudaFree(d_tmaps);
+    cudaFree(d_tile_job_start); cudaFree(d_job_cam); cudaFree(d_coords); cudaFree(d_weights); cudaFree(d_jobs); cudaFree(d_entries); cudaFree(d_tmaps); cudaFree(d_fblocks); cudaFree(d_fbins);
     cudaFree(d_smask); cudaFree(d_gcoord); cudaFree(d_partial); cudaFree(d_ticket);
     cudaFree(d_gains); cudaFree(d_gain_f32); cudaFree(d_gain_flag); cudaFree(d_gain_lut); cudaFree(d_rgb); cudaFree(d_dbg);
     if (h_gains) cudaFreeHost(h_gains);
     for (auto& e : ev) if (e) cudaEventDestroy(e);
     ob::multiband_destroy(mb);
+}
+
+// ---- fused layout (K_stitch_fused): 32x32 tiles, one job per (tile, camera[, row range]), each job carries the
+// bounding box of its bilinear taps in the camera's source plane (8 px x 2 row granularity, the unit of the in-kernel
+// colour conversion) and 8-byte entries {byte offset of the top-left tap inside the box | fy << 16 | fx << 24, weight}.
+// Tiles are distributed over the persistent CTAs by longest-processing-time-first bin packing.
+static bool build_fused(octvr_mapper& m, const octvr_template& t, const std::vector<Img<int32_t>>& sx, const std::vector<Img<int32_t>>& sy,
+                        const std::vector<Img<float>>& W)
+{
+    const int n = m.n;
+    const int tiles_x = (t.out_w + FT_W - 1) / FT_W, tiles_y = (t.out_h + FT_H - 1) / FT_H, ntiles = tiles_x * tiles_y;
+    struct Job { int cam, r0, r1; FJob rec; };
+    std::vector<std::vector<Job>> tile_jobs(ntiles);
+    // pixel of a tile -> (valid, tap position, weight) for camera i
+    auto sample = [&](int tl, int px, int py, int i, int& ix, int& iy, int32_t& fsx, int32_t& fsy, float& w) {
+        const TInput& in = t.inputs[i];
+        const int gx = (tl % tiles_x) * FT_W + px, gy = (tl / tiles_x) * FT_H + py;
+        const int lx = gx - in.roi.x, ly = gy - in.roi.y;
+        if (gx >= t.out_w || gy >= t.out_h || lx < 0 || ly < 0 || lx >= in.roi.w || ly >= in.roi.h) return false;
+        w = W[i].row(ly)[lx];
+        fsx = sx[i].row(ly)[lx]; fsy = sy[i].row(ly)[lx];
+        const uint2 e = make_entry(fsx, fsy, m.in_w[i], m.in_h[i], in.mask.row(ly)[lx] != 0 && w != 0.f);
+        if (!(e.y & C_VALID)) return false;
+        ix = std::min(32767, std::max(-32768, fsx >> 5)); iy = std::min(32767, std::max(-32768, fsy >> 5));
+        return true;
+    };
+    auto floor_div = [](int a, int b) { return a >= 0 ? a / b : -((-a + b - 1) / b); };
+    // box of the rows [r0, r1) of tile tl for camera i; false if no pixel contributes
+    auto make_job = [&](int tl, int i, int r0, int r1, Job& jb) {
+        int xmin = INT32_MAX, xmax = INT32_MIN, ymin = INT32_MAX, ymax = INT32_MIN;
+        for (int py = r0; py < r1; py++)
+            for (int px = 0; px < FT_W; px++) {
+                int ix, iy; int32_t fsx, fsy; float w;
+                if (!sample(tl, px, py, i, ix, iy, fsx, fsy, w)) continue;
+                xmin = std::min(xmin, ix); xmax = std::max(xmax, ix + 1); ymin = std::min(ymin, iy); ymax = std::max(ymax, iy + 1);
+            }
+        if (xmin > xmax) return false;
+        FJob& r = jb.rec;
+        memset(&r, 0, sizeof(r));
+        r.cam = i;
+        r.bx0 = floor_div(xmin, 8) * 8; r.by0 = floor_div(ymin, 2) * 2;
+        r.bw = (xmax - r.bx0 + 8) / 8 * 8; r.bh = (ymax - r.by0 + 2) / 2 * 2;
+        r.groups = r.bw / 8; r.rcp = (uint32_t)(((1u << 20) + r.groups - 1) / r.groups); r.nitems = r.groups * (r.bh / 2);
+        jb.cam = i; jb.r0 = r0; jb.r1 = r1;
+        return true;
+    };
+    bool ok = true;
+    std::function<void(int, int, int, int)> add_jobs = [&](int tl, int i, int r0, int r1) {
+        Job jb;
+        if (!make_job(tl, i, r0, r1, jb)) return;
+        const bool fits = (int64_t)jb.rec.bw * jb.rec.bh <= FUSED_CAP && jb.rec.nitems <= 2 * FT_THREADS && jb.rec.groups <= 512;
+        if (fits) { tile_jobs[tl].push_back(jb); return; }
+        if (r1 - r0 <= 1) { ok = false; return; }          // a single output row needs a box larger than the stage
+        const int mid = (r0 + r1) / 2;
+        add_jobs(tl, i, r0, mid); add_jobs(tl, i, mid, r1);
+    };
+    for (int tl = 0; tl < ntiles && ok; tl++) {
+        for (int i = 0; i < n; i++) add_jobs(tl, i, 0, FT_H);
+        if ((int)tile_jobs[tl].size() > FUSED_MAXJ) ok = false;
+    }
+    if (!ok) return false;                                 // the caller falls back to the two-kernel path
+
+    // ---- entries ----
+    size_t njobs = 0;
+    for (auto& v : tile_jobs) njobs += v.size();
+    const size_t zero_job = njobs;                         // an all-zero block for tiles nobody covers
+    std::vector<uint2> entries((njobs + 1) * FT_PX, make_uint2(0u, 0u));
+    std::vector<size_t> tile_j0(ntiles);
+    {
+        size_t j = 0;
+        for (int tl = 0; tl < ntiles; tl++) {
+            tile_j0[tl] = j;
+            for (const Job& jb : tile_jobs[tl]) {
+                const FJob& r = jb.rec;
+                for (int tid = 0; tid < FT_THREADS; tid++)
+                    for (int q = 0; q < FT_PPT; q++) {
+                        const int px = tid & 31, py = (tid >> 5) + 8 * q;
+                        if (py < jb.r0 || py >= jb.r1) continue;
+                        int ix, iy; int32_t fsx, fsy; float w;
+                        if (!sample(tl, px, py, jb.cam, ix, iy, fsx, fsy, w)) continue;
+                        const uint32_t off = (uint32_t)(((iy - r.by0) * r.bw + (ix - r.bx0)) * 4);
+                        uint32_t wbits; memcpy(&wbits, &w, 4);
+                        entries[(j * FT_THREADS + tid) * FT_PPT + q] = make_uint2(off | ((uint32_t)(fsy & 31) << 16) | ((uint32_t)(fsx & 31) << 24), wbits);
+                    }
+                j++;
+            }
+        }
+    }
+    OB_CHECK((njobs + 1) * FT_PX < ((size_t)1 << 31), "table too large");
+
+    // ---- schedule: LPT bin packing of tiles onto the persistent CTAs ----
+    int sms = 0;
+    OB_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, m.device));
+    const int per_sm = fused_ctas_per_sm();
+    if (per_sm <= 0) fail(OCTVR_ERR_CUDA, "k_stitch_fused cannot be resident on this device");
+    const int grid = std::max(1, std::min(ntiles, sms * per_sm));
+    std::vector<int64_t> cost(ntiles);
+    for (int tl = 0; tl < ntiles; tl++) {
+        int64_t c = 6000;                                  // epilogue + stores
+        for (const Job& jb : tile_jobs[tl]) c += (int64_t)FT_PX * 48 + (int64_t)jb.rec.bw * jb.rec.bh * 13 + 3000;
+        cost[tl] = c;
+    }
+    std::vector<int> order(ntiles);
+    for (int i = 0; i < ntiles; i++) order[i] = i;
+    std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return cost[a] > cost[b]; });
+    std::vector<std::vector<int>> bins(grid);
+    {
+        typedef std::pair<int64_t, int> Load;              // (load, bin): min-heap
+        std::priority_queue<Load, std::vector<Load>, std::greater<Load>> heap;
+        for (int b = 0; b < grid; b++) heap.push(Load(0, b));
+        for (int tl : order) {
+            Load l = heap.top(); heap.pop();
+            bins[l.second].push_back(tl);
+            heap.push(Load(l.first + cost[tl], l.second));
+        }
+    }
+    std::vector<FTileBlock> blocks;
+    blocks.reserve(ntiles);
+    std::vector<int> bin_start(grid + 1, 0);
+    for (int b = 0; b < grid; b++) {
+        bin_start[b] = (int)blocks.size();
+        for (int tl : bins[b]) {
+            FTileBlock B;
+            memset(&B, 0, sizeof(B));
+            B.tile.tx = tl % tiles_x; B.tile.ty = tl / tiles_x;
+            if (tile_jobs[tl].empty()) {                   // nobody covers this tile: one job with no items and zero weights
+                B.tile.nj = 1; B.tile.j0 = (int)zero_job;
+                B.job[0].bw = 8; B.job[0].bh = 2; B.job[0].groups = 1; B.job[0].rcp = 1u << 20; B.job[0].nitems = 0;
+            } else {
+                B.tile.nj = (int)tile_jobs[tl].size(); B.tile.j0 = (int)tile_j0[tl];
+                for (size_t k = 0; k < tile_jobs[tl].size(); k++) B.job[k] = tile_jobs[tl][k].rec;
+            }
+            blocks.push_back(B);
+        }
+    }
+    bin_start[grid] = (int)blocks.size();
+    m.fused = true;
+    m.fused_grid = grid;
+    m.njobs = njobs;
+    m.d_fblocks = dev_upload(blocks.data(), blocks.size());
+    m.d_fbins = dev_upload(bin_start.data(), bin_start.size());
+    m.d_entries = dev_upload(entries.data(), entries.size());
+    m.table_bytes = (int64_t)(njobs * FT_PX * sizeof(uint2) + blocks.size() * sizeof(FTileBlock));
+    return true;
 }
 
 static void build_mapper(octvr_mapper& m, const octvr_template& t, const int* in_sizes, int n_in,
@@ -104,7 +250,6 @@ static void build_mapper(octvr_mapper& m, const octvr_template& t, const int* in
 
     // ---- per-camera source planes ----
     for (int i = 0; i < n; i++) {
-        m.d_rgbx.push_back(dev_alloc<uint32_t>((size_t)m.in_w[i] * m.in_h[i] + 4));
         float* dv = nullptr;
         if (!t.inputs[i].vignette.empty()) {               // mapper.cpp:108-112
             Img<float> v = resize_linear(t.inputs[i].vignette, m.in_w[i], m.in_h[i]);
@@ -122,12 +267,23 @@ static void build_mapper(octvr_mapper& m, const octvr_template& t, const int* in
         for (uint8_t v : t.inputs[i].mask.d) m.pairs += v != 0;
     }
 
+    std::vector<Img<float>> W;
+    if (blend <= 0) {
+        W = blend < 0 ? feather_weights(t.inputs, -blend) : overwrite_weights(t.inputs);
+        m.inv_n = blend < 0 ? (float)(1.0 / n) : 1.f;
+        // fused single-kernel path (default); OCTVR_BLEND=staged|direct selects the two-kernel paths, which are also
+        // the fallback when a job does not fit the fused kernel's shared-memory stage
+        const char* mode = getenv("OCTVR_BLEND");
+        if (!mode || std::string(mode) == "fused") build_fused(m, t, sx, sy, W);
+    }
+    // RGBX planes written by K_convert: only the two-kernel and multiband paths need them
+    if (!m.fused)
+        for (int i = 0; i < n; i++) m.d_rgbx.push_back(dev_alloc<uint32_t>((size_t)m.in_w[i] * m.in_h[i] + 4));
+
     if (blend > 0) {
         m.mb = ob::multiband_create(m, t, sx, sy);
     } else {
-        std::vector<Img<float>> W = blend < 0 ? feather_weights(t.inputs, -blend) : overwrite_weights(t.inputs);
-        m.inv_n = blend < 0 ? (float)(1.0 / n) : 1.f;
-
+        if (!m.fused) {
         // ---- tile-compacted tables ----
         const int tiles_x = (t.out_w + TILE_W - 1) / TILE_W, tiles_y = (t.out_h + TILE_H - 1) / TILE_H;
         const int ntiles = tiles_x * tiles_y;
@@ -279,6 +435,7 @@ static void build_mapper(octvr_mapper& m, const octvr_template& t, const int* in
             m.d_weights = dev_upload(weights.data(), weights.size());
             m.table_bytes = (int64_t)(coords.size() * sizeof(uint2) + weights.size() * sizeof(float) + job_cam.size() + job_start.size() * 4);
         }
+        }   // !fused
     }
 
     // ---- gain compensation tables (mapper.cpp:94-99,113-114,235-237) ----
@@ -371,7 +528,7 @@ void ob::mapper_stitch_internal(octvr_mapper& m, const octvr_frame* in, int n_in
     OB_CHECK(out || m.keep_rgb, "no output requested");
     if (m.profiling) OB_CUDA(cudaEventRecord(m.ev[0], s));
 
-    ConvertParams cp;
+    ConvertParams cp;                 // also describes the input planes for the fused kernel
     memset(&cp, 0, sizeof(cp));
     cp.n = m.n;
     for (int i = 0; i < m.n; i++) {
@@ -379,7 +536,7 @@ void ob::mapper_stitch_internal(octvr_mapper& m, const octvr_frame* in, int n_in
         c.y = in[i].y; c.u = in[i].u; c.v = in[i].v;
         c.y_pitch = (uint32_t)in[i].y_pitch; c.u_pitch = (uint32_t)in[i].u_pitch; c.v_pitch = (uint32_t)in[i].v_pitch;
         c.uv_step = in[i].uv_pixel_stride; c.w = m.in_w[i]; c.h = m.in_h[i];
-        c.rgbx = m.d_rgbx[i]; c.vignette = m.d_vig[i];
+        c.rgbx = m.fused ? nullptr : m.d_rgbx[i]; c.vignette = m.d_vig[i];
         const bool chroma_ok = c.uv_step == 1
             ? ((uintptr_t)c.u % 4 == 0 && (uintptr_t)c.v % 4 == 0 && c.u_pitch % 4 == 0 && c.v_pitch % 4 == 0)
             : ((uintptr_t)c.u % 8 == 0 && c.u_pitch % 8 == 0 && c.v == c.u + 1);
@@ -388,12 +545,14 @@ void ob::mapper_stitch_internal(octvr_mapper& m, const octvr_frame* in, int n_in
         cp.grid_y = std::max(cp.grid_y, (c.h + 15) / 16);
     }
     // one launch: gain statistics + solve (reading the input planes directly) in the first CTAs, conversion in the rest
+    // (fused path: no conversion pass at all, the launch only carries the gain CTAs)
     const bool compute_gains = m.gain && !d_gains_src && !gains;
+    if (m.fused) { cp.grid_x = cp.grid_y = 0; }
     if (compute_gains) {
         GainParams gp = m.gp;
         for (int i = 0; i < m.n; i++) gp.src[i] = cp.cam[i];
         launch_convert_gain(cp, &gp, s);
-    } else
+    } else if (!m.fused)
         launch_convert_gain(cp, nullptr, s);
     if (m.profiling) OB_CUDA(cudaEventRecord(m.ev[1], s));
 
@@ -415,6 +574,23 @@ void ob::mapper_stitch_internal(octvr_mapper& m, const octvr_frame* in, int n_in
     if (m.keep_rgb && !m.d_rgb) m.d_rgb = dev_alloc<uint8_t>((size_t)m.out_w * m.out_h * 3, true);
     if (m.mb) {
         ob::multiband_stitch(m, out, s);
+    } else if (m.fused) {
+        FusedParams fp;
+        memset(&fp, 0, sizeof(fp));
+        for (int i = 0; i < m.n; i++) fp.cam[i] = cp.cam[i];
+        fp.n = m.n;
+        fp.blocks = m.d_fblocks; fp.bin_start = m.d_fbins; fp.entries = m.d_entries;
+        fp.out_w = m.out_w; fp.out_h = m.out_h;
+        if (out) {
+            fp.oy = out->y; fp.ou = out->u; fp.ov = out->v;
+            fp.oy_pitch = (uint32_t)out->y_pitch; fp.ou_pitch = (uint32_t)out->u_pitch; fp.ov_pitch = (uint32_t)out->v_pitch;
+            fp.uv_step = out->uv_pixel_stride;
+        }
+        fp.rgb_out = m.keep_rgb ? m.d_rgb : nullptr; fp.rgb_pitch = (uint32_t)m.out_w * 3;
+        fp.gain_f32 = m.d_gain_f32; fp.gain_flag = m.d_gain_flag; fp.gain_lut = m.d_gain_lut;
+        fp.use_gain = m.gain ? 1 : 0;
+        fp.inv_n = m.inv_n;
+        launch_stitch_fused(fp, m.fused_grid, s);
     } else if (m.staged) {
         StagedParams sp;
         memset(&sp, 0, sizeof(sp));
@@ -538,7 +714,7 @@ octvr_status octvr_mapper_stats(const octvr_mapper* m, int64_t* pairs, int64_t* 
         if (pairs) *pairs = m->pairs;
         if (roi_area) *roi_area = m->roi_area;
         if (table_bytes) *table_bytes = m->table_bytes;
-        if (launches) *launches = m->mb ? ob::multiband_launches(*m) + 1 : 2;
+        if (launches) *launches = m->mb ? ob::multiband_launches(*m) + 1 : m->fused ? 1 + (m->gain ? 1 : 0) : 2;
     });
 }
 

@@ -28,6 +28,11 @@ struct octvr_mapper {
     uint2* d_entries = nullptr;
     void* d_tmaps = nullptr;
     int n_tmaps = 0;
+    // fused layout (K_stitch_fused)
+    bool fused = false;
+    int fused_grid = 0;
+    ob::FTileBlock* d_fblocks = nullptr;
+    int* d_fbins = nullptr;
     // gain compensation
     ob::GainParams gp;
     uint8_t* d_smask = nullptr; uint2* d_gcoord = nullptr; double* d_partial = nullptr;

@@ -211,6 +211,12 @@ class Mapper:
         check(lib().octvr_mapper_stage_ms(self._h, stage.encode(), C.byref(ms)))
         return ms.value
 
+    def debug_gain_ns(self):
+        """%globaltimer stamps of the gain kernel's last CTA (diagnostics)."""
+        a = (C.c_ulonglong * 5)()
+        check(lib().octvr_mapper_debug_gain_ns(self._h, a))
+        return list(a)
+
     def __del__(self):
         try:
             if self._h:
