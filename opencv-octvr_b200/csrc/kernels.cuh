@@ -105,25 +105,30 @@ void launch_blend_staged(const StagedParams& p, cudaStream_t s);
 //      stores.  The 8 B/pair table entries of job k+1 arrive by a TMA bulk copy (cp.async.bulk + mbarrier) while
 //      job k is processed; the input bytes of job k+1 are prefetched into registers.
 constexpr int FT_W = 32, FT_H = 32, FT_PX = FT_W * FT_H, FT_THREADS = 256, FT_PPT = FT_PX / FT_THREADS;
-constexpr int FUSED_CAP = 8192;          // RGBX stage capacity in pixels (32 KB); a job whose box is larger is split by rows
+constexpr int FUSED_CAP = 6144;          // RGBX stage capacity in pixels (24 KB); a job whose box is larger is split by rows
 constexpr int FUSED_MAXJ = 32;           // jobs per tile (cameras x row splits)
+constexpr int FUSED_MAXITEMS = 2 * FT_THREADS;   // conversion items (8 px x 2 rows of the source box) per job
+// conversion item descriptor (u16): row pair (7 bits) | 8-px group << 7 (7 bits) | class << 14
+enum { FITEM_ZERO = 0, FITEM_FAST = 1, FITEM_SLOW = 2 };     // outside the source (-> 0), inside, straddles the border
 struct FJob {                            // 32 B
     int cam;
     int bx0, by0;                        // top-left of the source box (bx0 % 8 == 0, by0 % 2 == 0, may be negative)
-    int bw, bh;                          // box size in px (bw % 8 == 0, bh % 2 == 0, bw * bh <= FUSED_CAP)
-    int groups;                          // bw / 8: conversion items (8 px x 2 rows) per row pair
-    uint32_t rcp;                        // ceil(2^20 / groups): item -> row pair without a division
-    int nitems;                          // groups * bh / 2  (<= 2 per thread)
+    int bw;                              // box width in px (bw % 8 == 0); box area <= FUSED_CAP
+    int nitems;                          // conversion items of this job: only the 8x2 blocks some bilinear tap touches
+    uint32_t rec16;                      // this job's record in the table stream (16-byte units): FT_PX entries of 8 B
+    uint32_t rec_bytes;                  //   followed by the item list of the NEXT job of the CTA's schedule
+    int pad;
 };
-struct FTile { int tx, ty, nj, j0; };    // tile position (tile units), jobs, first job (entries of job j at j * FT_PX)
+struct FTile { int tx, ty, nj, pad; };   // tile position (tile units), jobs
 struct FTileBlock { FJob job[FUSED_MAXJ]; FTile tile; };     // one self-contained record per tile, in schedule order
 static_assert(sizeof(FJob) == 32 && sizeof(FTileBlock) == 32 * FUSED_MAXJ + 16, "FTileBlock is read as uint4s");
+struct FBin { int start, end; uint32_t head16, head_bytes; };   // a CTA's tiles [start, end) and the item list of its first job
 struct FusedParams {
     CamSrc cam[MAX_CAMS];
     int n;
     const FTileBlock* blocks;            // [tiles], grouped by CTA
-    const int* bin_start;                // [grid + 1]: CTA b owns blocks [bin_start[b], bin_start[b+1])
-    const uint2* entries;                // [jobs * FT_PX]: {byte offset in the stage | fy << 16 | fx << 24, f32 weight}
+    const FBin* bins;                    // [grid]
+    const uint4* stream;                 // job records in schedule order; entry = {byte offset in the stage | fy << 16 | fx << 24, f32 weight}
     int out_w, out_h;
     uint8_t* oy; uint8_t* ou; uint8_t* ov;
     uint32_t oy_pitch, ou_pitch, ov_pitch;

@@ -77,7 +77,7 @@ octvr_mapper::~octvr_mapper()
     cudaSetDevice(device);
     for (auto p : d_rgbx) cudaFree(p);
     for (auto p : d_vig) cudaFree(p);
-    cudaFree(d_tile_job_start); cudaFree(d_job_cam); cudaFree(d_coords); cudaFree(d_weights); cudaFree(d_jobs); cudaFree(d_entries); cudaFree(d_tmaps); cudaFree(d_fblocks); cudaFree(d_fbins);
+    cudaFree(d_tile_job_start); cudaFree(d_job_cam); cudaFree(d_coords); cudaFree(d_weights); cudaFree(d_jobs); cudaFree(d_entries); cudaFree(d_tmaps); cudaFree(d_fblocks); cudaFree(d_fbins); cudaFree(d_fstream);
     cudaFree(d_smask); cudaFree(d_gcoord); cudaFree(d_partial); cudaFree(d_ticket);
     cudaFree(d_gains); cudaFree(d_gain_f32); cudaFree(d_gain_flag); cudaFree(d_gain_lut); cudaFree(d_rgb); cudaFree(d_dbg);
     if (h_gains) cudaFreeHost(h_gains);
@@ -85,16 +85,18 @@ octvr_mapper::~octvr_mapper()
     ob::multiband_destroy(mb);
 }
 
-// ---- fused layout (K_stitch_fused): 32x32 tiles, one job per (tile, camera[, row range]), each job carries the
-// bounding box of its bilinear taps in the camera's source plane (8 px x 2 row granularity, the unit of the in-kernel
-// colour conversion) and 8-byte entries {byte offset of the top-left tap inside the box | fy << 16 | fx << 24, weight}.
-// Tiles are distributed over the persistent CTAs by longest-processing-time-first bin packing.
+// ---- fused layout (K_stitch_fused): 32x32 tiles, one job per (tile, camera[, row range]).  A job carries the bounding
+// box of its bilinear taps in the camera's source plane, the list of 8 px x 2 row blocks of that box which some tap
+// touches (the units of the in-kernel colour conversion; everything else in the box is never read) and 8-byte entries
+// {byte offset of the top-left tap inside the box | fy << 16 | fx << 24, weight}.  Tiles are distributed over the
+// persistent CTAs by longest-processing-time-first bin packing and the job records are laid out in the order in
+// which each CTA consumes them, every record followed by the item list of the CTA's next job.
 static bool build_fused(octvr_mapper& m, const octvr_template& t, const std::vector<Img<int32_t>>& sx, const std::vector<Img<int32_t>>& sy,
                         const std::vector<Img<float>>& W)
 {
     const int n = m.n;
     const int tiles_x = (t.out_w + FT_W - 1) / FT_W, tiles_y = (t.out_h + FT_H - 1) / FT_H, ntiles = tiles_x * tiles_y;
-    struct Job { int cam, r0, r1; FJob rec; };
+    struct Job { int cam, r0, r1; FJob rec; std::vector<uint16_t> items; };
     std::vector<std::vector<Job>> tile_jobs(ntiles);
     // pixel of a tile -> (valid, tap position, weight) for camera i
     auto sample = [&](int tl, int px, int py, int i, int& ix, int& iy, int32_t& fsx, int32_t& fsy, float& w) {
@@ -110,7 +112,7 @@ static bool build_fused(octvr_mapper& m, const octvr_template& t, const std::vec
         return true;
     };
     auto floor_div = [](int a, int b) { return a >= 0 ? a / b : -((-a + b - 1) / b); };
-    // box of the rows [r0, r1) of tile tl for camera i; false if no pixel contributes
+    // job for the rows [r0, r1) of tile tl and camera i: 0 = nothing contributes, 1 = ok, -1 = does not fit the stage
     auto make_job = [&](int tl, int i, int r0, int r1, Job& jb) {
         int xmin = INT32_MAX, xmax = INT32_MIN, ymin = INT32_MAX, ymax = INT32_MIN;
         for (int py = r0; py < r1; py++)
@@ -119,22 +121,43 @@ static bool build_fused(octvr_mapper& m, const octvr_template& t, const std::vec
                 if (!sample(tl, px, py, i, ix, iy, fsx, fsy, w)) continue;
                 xmin = std::min(xmin, ix); xmax = std::max(xmax, ix + 1); ymin = std::min(ymin, iy); ymax = std::max(ymax, iy + 1);
             }
-        if (xmin > xmax) return false;
+        if (xmin > xmax) return 0;
         FJob& r = jb.rec;
         memset(&r, 0, sizeof(r));
         r.cam = i;
         r.bx0 = floor_div(xmin, 8) * 8; r.by0 = floor_div(ymin, 2) * 2;
-        r.bw = (xmax - r.bx0 + 8) / 8 * 8; r.bh = (ymax - r.by0 + 2) / 2 * 2;
-        r.groups = r.bw / 8; r.rcp = (uint32_t)(((1u << 20) + r.groups - 1) / r.groups); r.nitems = r.groups * (r.bh / 2);
+        r.bw = (xmax - r.bx0 + 8) / 8 * 8;
+        const int bh = (ymax - r.by0 + 2) / 2 * 2, groups = r.bw / 8, rps = bh / 2;
+        if ((int64_t)r.bw * bh > FUSED_CAP || groups > 128 || rps > 128) return -1;
+        std::vector<uint8_t> touched((size_t)groups * rps, 0);
+        for (int py = r0; py < r1; py++)
+            for (int px = 0; px < FT_W; px++) {
+                int ix, iy; int32_t fsx, fsy; float w;
+                if (!sample(tl, px, py, i, ix, iy, fsx, fsy, w)) continue;
+                for (int dy = 0; dy < 2; dy++)
+                    for (int dx = 0; dx < 2; dx++) touched[(size_t)((iy + dy - r.by0) >> 1) * groups + ((ix + dx - r.bx0) >> 3)] = 1;
+            }
+        jb.items.clear();
+        for (int rp = 0; rp < rps; rp++)
+            for (int g = 0; g < groups; g++) {
+                if (!touched[(size_t)rp * groups + g]) continue;
+                const int x0 = r.bx0 + 8 * g, y0 = r.by0 + 2 * rp;
+                int cls = FITEM_SLOW;
+                if (x0 + 8 <= 0 || x0 >= m.in_w[i] || y0 + 2 <= 0 || y0 >= m.in_h[i]) cls = FITEM_ZERO;
+                else if (x0 >= 0 && x0 + 8 <= m.in_w[i] && y0 >= 0 && y0 + 2 <= m.in_h[i]) cls = FITEM_FAST;
+                jb.items.push_back((uint16_t)(rp | (g << 7) | (cls << 14)));
+            }
+        if ((int)jb.items.size() > FUSED_MAXITEMS) return -1;
+        r.nitems = (int)jb.items.size();
         jb.cam = i; jb.r0 = r0; jb.r1 = r1;
-        return true;
+        return 1;
     };
     bool ok = true;
     std::function<void(int, int, int, int)> add_jobs = [&](int tl, int i, int r0, int r1) {
         Job jb;
-        if (!make_job(tl, i, r0, r1, jb)) return;
-        const bool fits = (int64_t)jb.rec.bw * jb.rec.bh <= FUSED_CAP && jb.rec.nitems <= 2 * FT_THREADS && jb.rec.groups <= 512;
-        if (fits) { tile_jobs[tl].push_back(jb); return; }
+        const int st = make_job(tl, i, r0, r1, jb);
+        if (st == 0) return;
+        if (st == 1) { tile_jobs[tl].push_back(std::move(jb)); return; }
         if (r1 - r0 <= 1) { ok = false; return; }          // a single output row needs a box larger than the stage
         const int mid = (r0 + r1) / 2;
         add_jobs(tl, i, r0, mid); add_jobs(tl, i, mid, r1);
@@ -142,36 +165,13 @@ static bool build_fused(octvr_mapper& m, const octvr_template& t, const std::vec
     for (int tl = 0; tl < ntiles && ok; tl++) {
         for (int i = 0; i < n; i++) add_jobs(tl, i, 0, FT_H);
         if ((int)tile_jobs[tl].size() > FUSED_MAXJ) ok = false;
-    }
-    if (!ok) return false;                                 // the caller falls back to the two-kernel path
-
-    // ---- entries ----
-    size_t njobs = 0;
-    for (auto& v : tile_jobs) njobs += v.size();
-    const size_t zero_job = njobs;                         // an all-zero block for tiles nobody covers
-    std::vector<uint2> entries((njobs + 1) * FT_PX, make_uint2(0u, 0u));
-    std::vector<size_t> tile_j0(ntiles);
-    {
-        size_t j = 0;
-        for (int tl = 0; tl < ntiles; tl++) {
-            tile_j0[tl] = j;
-            for (const Job& jb : tile_jobs[tl]) {
-                const FJob& r = jb.rec;
-                for (int tid = 0; tid < FT_THREADS; tid++)
-                    for (int q = 0; q < FT_PPT; q++) {
-                        const int px = tid & 31, py = (tid >> 5) + 8 * q;
-                        if (py < jb.r0 || py >= jb.r1) continue;
-                        int ix, iy; int32_t fsx, fsy; float w;
-                        if (!sample(tl, px, py, jb.cam, ix, iy, fsx, fsy, w)) continue;
-                        const uint32_t off = (uint32_t)(((iy - r.by0) * r.bw + (ix - r.bx0)) * 4);
-                        uint32_t wbits; memcpy(&wbits, &w, 4);
-                        entries[(j * FT_THREADS + tid) * FT_PPT + q] = make_uint2(off | ((uint32_t)(fsy & 31) << 16) | ((uint32_t)(fsx & 31) << 24), wbits);
-                    }
-                j++;
-            }
+        if (tile_jobs[tl].empty()) {                       // nobody covers this tile: one job with no items and zero weights
+            Job jb; memset(&jb.rec, 0, sizeof(jb.rec));
+            jb.cam = -1; jb.r0 = jb.r1 = 0; jb.rec.bw = 8;
+            tile_jobs[tl].push_back(jb);
         }
     }
-    OB_CHECK((njobs + 1) * FT_PX < ((size_t)1 << 31), "table too large");
+    if (!ok) return false;                                 // the caller falls back to the two-kernel path
 
     // ---- schedule: LPT bin packing of tiles onto the persistent CTAs ----
     int sms = 0;
@@ -182,50 +182,81 @@ static bool build_fused(octvr_mapper& m, const octvr_template& t, const std::vec
     std::vector<int64_t> cost(ntiles);
     for (int tl = 0; tl < ntiles; tl++) {
         int64_t c = 6000;                                  // epilogue + stores
-        for (const Job& jb : tile_jobs[tl]) c += (int64_t)FT_PX * 48 + (int64_t)jb.rec.bw * jb.rec.bh * 13 + 3000;
+        for (const Job& jb : tile_jobs[tl]) c += (int64_t)FT_PX * 50 + (int64_t)jb.items.size() * 16 * 13 + 4000;
         cost[tl] = c;
     }
     std::vector<int> order(ntiles);
     for (int i = 0; i < ntiles; i++) order[i] = i;
     std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return cost[a] > cost[b]; });
-    std::vector<std::vector<int>> bins(grid);
+    std::vector<std::vector<int>> bin_tiles(grid);
     {
         typedef std::pair<int64_t, int> Load;              // (load, bin): min-heap
         std::priority_queue<Load, std::vector<Load>, std::greater<Load>> heap;
         for (int b = 0; b < grid; b++) heap.push(Load(0, b));
         for (int tl : order) {
             Load l = heap.top(); heap.pop();
-            bins[l.second].push_back(tl);
+            bin_tiles[l.second].push_back(tl);
             heap.push(Load(l.first + cost[tl], l.second));
         }
     }
+
+    // ---- table stream in consumption order ----
+    std::vector<uint4> stream;
     std::vector<FTileBlock> blocks;
     blocks.reserve(ntiles);
-    std::vector<int> bin_start(grid + 1, 0);
+    std::vector<FBin> bins(grid);
+    size_t njobs = 0;
+    auto append_items = [&](const std::vector<uint16_t>& items) {      // padded to 16 bytes; returns the byte count
+        const size_t n16 = (items.size() * 2 + 15) / 16, at = stream.size();
+        stream.resize(at + n16, make_uint4(0u, 0u, 0u, 0u));
+        if (!items.empty()) memcpy(&stream[at], items.data(), items.size() * 2);
+        return (uint32_t)(n16 * 16);
+    };
     for (int b = 0; b < grid; b++) {
-        bin_start[b] = (int)blocks.size();
-        for (int tl : bins[b]) {
+        std::vector<Job*> seq;
+        for (int tl : bin_tiles[b]) for (Job& jb : tile_jobs[tl]) seq.push_back(&jb);
+        bins[b].start = (int)blocks.size();
+        bins[b].head16 = (uint32_t)stream.size();
+        bins[b].head_bytes = seq.empty() ? 0u : append_items(seq[0]->items);
+        for (size_t q = 0; q < seq.size(); q++) {
+            Job& jb = *seq[q];
+            OB_CHECK(stream.size() < ((size_t)1 << 32), "table too large");
+            jb.rec.rec16 = (uint32_t)stream.size();
+            stream.resize(stream.size() + FT_PX * 8 / 16, make_uint4(0u, 0u, 0u, 0u));       // entries: filled per tile below
+            jb.rec.rec_bytes = FT_PX * 8 + (q + 1 < seq.size() ? append_items(seq[q + 1]->items) : 0u);
+            njobs++;
+        }
+        for (int tl : bin_tiles[b]) {
             FTileBlock B;
             memset(&B, 0, sizeof(B));
-            B.tile.tx = tl % tiles_x; B.tile.ty = tl / tiles_x;
-            if (tile_jobs[tl].empty()) {                   // nobody covers this tile: one job with no items and zero weights
-                B.tile.nj = 1; B.tile.j0 = (int)zero_job;
-                B.job[0].bw = 8; B.job[0].bh = 2; B.job[0].groups = 1; B.job[0].rcp = 1u << 20; B.job[0].nitems = 0;
-            } else {
-                B.tile.nj = (int)tile_jobs[tl].size(); B.tile.j0 = (int)tile_j0[tl];
-                for (size_t k = 0; k < tile_jobs[tl].size(); k++) B.job[k] = tile_jobs[tl][k].rec;
+            B.tile.tx = tl % tiles_x; B.tile.ty = tl / tiles_x; B.tile.nj = (int)tile_jobs[tl].size();
+            for (size_t k = 0; k < tile_jobs[tl].size(); k++) {
+                const Job& jb = tile_jobs[tl][k];
+                B.job[k] = jb.rec;
+                if (jb.cam < 0) { B.job[k].cam = 0; continue; }
+                uint2* ent = reinterpret_cast<uint2*>(&stream[jb.rec.rec16]);
+                for (int tid = 0; tid < FT_THREADS; tid++)
+                    for (int q = 0; q < FT_PPT; q++) {
+                        const int px = tid & 31, py = (tid >> 5) + 8 * q;
+                        if (py < jb.r0 || py >= jb.r1) continue;
+                        int ix, iy; int32_t fsx, fsy; float w;
+                        if (!sample(tl, px, py, jb.cam, ix, iy, fsx, fsy, w)) continue;
+                        const uint32_t off = (uint32_t)(((iy - jb.rec.by0) * jb.rec.bw + (ix - jb.rec.bx0)) * 4);
+                        uint32_t wbits; memcpy(&wbits, &w, 4);
+                        ent[tid * FT_PPT + q] = make_uint2(off | ((uint32_t)(fsy & 31) << 16) | ((uint32_t)(fsx & 31) << 24), wbits);
+                    }
             }
             blocks.push_back(B);
         }
+        bins[b].end = (int)blocks.size();
     }
-    bin_start[grid] = (int)blocks.size();
     m.fused = true;
     m.fused_grid = grid;
     m.njobs = njobs;
     m.d_fblocks = dev_upload(blocks.data(), blocks.size());
-    m.d_fbins = dev_upload(bin_start.data(), bin_start.size());
-    m.d_entries = dev_upload(entries.data(), entries.size());
-    m.table_bytes = (int64_t)(njobs * FT_PX * sizeof(uint2) + blocks.size() * sizeof(FTileBlock));
+    m.d_fbins = dev_upload(bins.data(), bins.size());
+    m.d_fstream = dev_upload(stream.data(), stream.size());
+    m.table_bytes = (int64_t)(stream.size() * sizeof(uint4) + blocks.size() * sizeof(FTileBlock));
     return true;
 }
 
@@ -579,7 +610,7 @@ void ob::mapper_stitch_internal(octvr_mapper& m, const octvr_frame* in, int n_in
         memset(&fp, 0, sizeof(fp));
         for (int i = 0; i < m.n; i++) fp.cam[i] = cp.cam[i];
         fp.n = m.n;
-        fp.blocks = m.d_fblocks; fp.bin_start = m.d_fbins; fp.entries = m.d_entries;
+        fp.blocks = m.d_fblocks; fp.bins = m.d_fbins; fp.stream = m.d_fstream;
         fp.out_w = m.out_w; fp.out_h = m.out_h;
         if (out) {
             fp.oy = out->y; fp.ou = out->u; fp.ov = out->v;

@@ -32,7 +32,8 @@ struct octvr_mapper {
     bool fused = false;
     int fused_grid = 0;
     ob::FTileBlock* d_fblocks = nullptr;
-    int* d_fbins = nullptr;
+    ob::FBin* d_fbins = nullptr;
+    uint4* d_fstream = nullptr;
     // gain compensation
     ob::GainParams gp;
     uint8_t* d_smask = nullptr; uint2* d_gcoord = nullptr; double* d_partial = nullptr;

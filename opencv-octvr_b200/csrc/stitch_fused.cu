@@ -17,25 +17,24 @@
 namespace ob {
 
 // ---- shared-memory map of a CTA (dynamic) ----
-constexpr int FS_RGBX = 0;                                   // FUSED_CAP u32
-constexpr int FS_ENT = FS_RGBX + FUSED_CAP * 4;              // 2 x FT_PX x 8 B (TMA bulk destination, 16-B aligned)
-constexpr int FS_META = FS_ENT + 2 * FT_PX * 8;              // 3 x FTileBlock (padded to 1056 B)
+constexpr int FS_RGBX = 0;                                   // FUSED_CAP u32: the converted source box of the current job
+constexpr int FS_YST = FS_RGBX + FUSED_CAP * 4;              // FUSED_CAP bytes: luma of the NEXT job's box (cp.async destination)
+constexpr int FS_UVST = FS_YST + FUSED_CAP;                  // FUSED_CAP / 2 bytes: its chroma (U plane | V plane, or interleaved rows)
+constexpr int FS_REC_STRIDE = FT_PX * 8 + FUSED_MAXITEMS * 2;  // a job record: 8 B entries, then the item list of the next job
+constexpr int FS_ENT = FS_UVST + FUSED_CAP / 2;              // 2 x job record (TMA bulk destination)
+constexpr int FS_META = FS_ENT + 2 * FS_REC_STRIDE;          // 3 x FTileBlock (padded to 1056 B)
 constexpr int FS_META_STRIDE = 1056;
-constexpr int FS_Y = FS_META + 3 * FS_META_STRIDE;           // 32 x 32 luma bytes
+constexpr int FS_Y = FS_META + 3 * FS_META_STRIDE;           // 32 x 32 luma bytes of the finished tile
 constexpr int FS_U = FS_Y + FT_PX;                           // 16 x 16
 constexpr int FS_V = FS_U + FT_PX / 4;
 constexpr int FS_GAIN = FS_V + FT_PX / 4;                    // MAX_CAMS x {g32, bias, flag, pad}
 constexpr int FS_MBAR = FS_GAIN + MAX_CAMS * 16;             // 2 x u64
 constexpr int FS_TOTAL = FS_MBAR + 16;
-static_assert(FS_ENT % 128 == 0 && FS_META % 16 == 0 && FS_Y % 16 == 0 && FS_MBAR % 8 == 0, "alignment");
+static_assert(FS_YST % 16 == 0 && FS_UVST % 16 == 0 && FS_ENT % 128 == 0 && FS_REC_STRIDE % 16 == 0 && FS_META % 16 == 0 && FS_Y % 16 == 0 && FS_MBAR % 8 == 0, "alignment");
+static_assert(4 * (FS_TOTAL + 1024) <= 228 * 1024, "four CTAs per SM");
+static_assert(FUSED_MAXITEMS == 2 * FT_THREADS, "at most two conversion items per thread");
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-__device__ __forceinline__ uint32_t lds_u32(uint32_t addr)
-{
-    uint32_t v;
-    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(addr));
-    return v;
-}
 __device__ __forceinline__ void f_mbar_init(uint32_t mbar, int count)
 {
     asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(mbar), "r"(count) : "memory");
@@ -60,52 +59,60 @@ __device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
                  ::"r"(dst), "l"(src), "r"(bytes), "r"(mbar) : "memory");
 }
-
-// ---- the prefetched input bytes of one conversion item: 8 px x 2 rows of Y, 4 U, 4 V ----
-struct ItemRegs { uint2 y0, y1; uint32_t u, v; };
-
-// item -> (row pair, 8-px group) of the job's source box
-__device__ __forceinline__ void item_pos(const FJob& J, int item, int& rp, int& gx)
+// per-thread asynchronous copies (SASS: LDGSTS): the input bytes of the next job go global -> shared without
+// passing through registers
+__device__ __forceinline__ void cp_async8(uint32_t dst, const void* src)
 {
-    rp = (int)(((uint32_t)item * J.rcp) >> 20);
-    gx = item - rp * J.groups;
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(dst), "l"(src) : "memory");
 }
-
-// Item load.  Fast path: the item lies inside the source and the planes allow 64/32-bit loads.  An item entirely
-// outside the source needs no bytes (mask 0 -> zeros = BORDER_CONSTANT).  Anything else (image border, unaligned
-// planes) is flagged ITEM_SLOW and converted pixel by pixel at conversion time.
-constexpr uint32_t ITEM_SLOW = 0x100u;
-__device__ __forceinline__ void load_item(const CamSrc& c, const FJob& J, int item, ItemRegs& r, uint32_t& mask)
+__device__ __forceinline__ void cp_async4(uint32_t dst, const void* src)
 {
-    int rp, gx;
-    item_pos(J, item, rp, gx);
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(dst), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
+
+// ---- conversion items: 8 px x 2 rows of the job's source box (four chroma samples), listed by the host ----
+// issue the asynchronous copies of one item's input bytes into the Y / chroma stages
+__device__ __forceinline__ void fetch_item(const CamSrc& c, const FJob& J, uint32_t desc, uint32_t yst, uint32_t uvst)
+{
+    if ((desc >> 14) != FITEM_FAST) return;
+    const int rp = desc & 127u, gx = (desc >> 7) & 127u;
     const int x0 = J.bx0 + (gx << 3), y0 = J.by0 + (rp << 1);
-    if (x0 + 8 <= 0 || x0 >= c.w || y0 < 0 || y0 >= c.h) { mask = 0u; return; }
-    if (c.aligned4 && x0 >= 0 && x0 + 8 <= c.w) {
-        const uint8_t* yp = c.y + (size_t)y0 * c.y_pitch + x0;
-        r.y0 = __ldg(reinterpret_cast<const uint2*>(yp));
-        r.y1 = __ldg(reinterpret_cast<const uint2*>(yp + c.y_pitch));
-        if (c.uv_step == 1) {
-            r.u = __ldg(reinterpret_cast<const uint32_t*>(c.u + (size_t)(y0 >> 1) * c.u_pitch + (x0 >> 1)));
-            r.v = __ldg(reinterpret_cast<const uint32_t*>(c.v + (size_t)(y0 >> 1) * c.v_pitch + (x0 >> 1)));
-        } else {                                           // NV12: U0 V0 U1 V1 U2 V2 U3 V3
-            const uint2 uv = __ldg(reinterpret_cast<const uint2*>(c.u + (size_t)(y0 >> 1) * c.u_pitch + x0));
-            r.u = __byte_perm(uv.x, uv.y, 0x6420);
-            r.v = __byte_perm(uv.x, uv.y, 0x7531);
-        }
-        mask = 0xFFu;
-    } else
-        mask = ITEM_SLOW;
+    const uint8_t* yp = c.y + (size_t)y0 * c.y_pitch + x0;
+    const uint32_t yd = yst + (uint32_t)((rp << 1) * J.bw + (gx << 3));
+    cp_async8(yd, yp);
+    cp_async8(yd + J.bw, yp + c.y_pitch);
+    if (c.uv_step == 1) {
+        const uint32_t cd = uvst + (uint32_t)(rp * (J.bw >> 1) + (gx << 2));
+        cp_async4(cd, c.u + (size_t)(y0 >> 1) * c.u_pitch + (x0 >> 1));
+        cp_async4(cd + FUSED_CAP / 4, c.v + (size_t)(y0 >> 1) * c.v_pitch + (x0 >> 1));
+    } else                                                   // NV12: U0 V0 U1 V1 U2 V2 U3 V3
+        cp_async8(uvst + (uint32_t)(rp * J.bw + (gx << 3)), c.u + (size_t)(y0 >> 1) * c.u_pitch + x0);
 }
 
-// BT.601 limited-range integer conversion of one pixel (imgproc/src/color.cpp:6087-6169), Y already clamped to >= 16
-// and the -16 folded into the chroma terms: R | G << 8 | B << 16
-__device__ __forceinline__ uint32_t yuv_px16(uint32_t Yc, int ruv, int guv, int buv)
+// BT.601 limited-range integer conversion (imgproc/src/color.cpp:6087-6169):
+//   R = sat((CY (max(Y,16) - 16) + 1673527 (V-128) + 2^19) >> 20), ...
+// evaluated as the HIGH word of a 64-bit multiply-add: (Yc << 8)(CY << 4) + (chroma term << 12) = (sum) << 12, so
+// bits 63..32 are sum >> 20 -- one IMAD.HI instead of IMAD + shift.  The byte operands arrive pre-shifted by 8 from
+// the same PRMT that extracts them; the chroma terms are 64-bit IMAD.WIDE results shared by a 2x2 block.
+constexpr int CY = 1220542, CK = (1 << 19) - 16 * CY;
+__device__ __forceinline__ int mad_hi64(uint32_t a8, int b16, long long c) { return (int)(((long long)(int)a8 * b16 + c) >> 32); }
+struct Chroma { long long r, g, b; };
+__device__ __forceinline__ Chroma chroma_terms(uint32_t U8, uint32_t V8)   // U8 = U << 8, V8 = V << 8
 {
-    const int yy = (int)Yc * 1220542;
-    const uint32_t r = (uint32_t)__vimin_s32_relu((yy + ruv) >> 20, 255);
-    const uint32_t g = (uint32_t)__vimin_s32_relu((yy + guv) >> 20, 255);
-    const uint32_t b = (uint32_t)__vimin_s32_relu((yy + buv) >> 20, 255);
+    Chroma c;
+    c.r = (long long)(int)V8 * (1673527 * 16) + (((long long)(CK - 128 * 1673527)) << 12);
+    c.g = (long long)(int)V8 * (-852492 * 16) + ((long long)(int)U8 * (-409993 * 16) + (((long long)(CK + 128 * (852492 + 409993))) << 12));
+    c.b = (long long)(int)U8 * (2116026 * 16) + (((long long)(CK - 128 * 2116026)) << 12);
+    return c;
+}
+__device__ __forceinline__ uint32_t yuv_px(uint32_t Y8, const Chroma& c)    // Y8 = Y << 8 ; returns R | G << 8 | B << 16
+{
+    const uint32_t yc = max(Y8, 16u << 8);
+    const uint32_t r = (uint32_t)__vimin_s32_relu(mad_hi64(yc, CY * 16, c.r), 255);
+    const uint32_t g = (uint32_t)__vimin_s32_relu(mad_hi64(yc, CY * 16, c.g), 255);
+    const uint32_t b = (uint32_t)__vimin_s32_relu(mad_hi64(yc, CY * 16, c.b), 255);
     return r + g * 256u + b * 65536u;
 }
 
@@ -118,19 +125,17 @@ __device__ __forceinline__ uint32_t vignette_px(uint32_t p, float k)
     return (uint32_t)r | ((uint32_t)g << 8) | ((uint32_t)b << 16);
 }
 
-// border / unaligned item: byte loads, one pixel at a time (rare)
+// border / unaligned item: byte loads from global memory, one pixel at a time (rare)
 __device__ __noinline__ void convert_item_slow(const CamSrc& c, int x0, int y0, uint32_t* d0, uint32_t* d1)
 {
     for (int k = 0; k < 8; k++) {
         const int x = x0 + k;
         uint32_t a = 0u, b = 0u;
-        if (x >= 0 && x < c.w) {
-            const int u = (int)__ldg(c.u + (size_t)(y0 >> 1) * c.u_pitch + (size_t)(x >> 1) * c.uv_step) - 128;
-            const int v = (int)__ldg(c.v + (size_t)(y0 >> 1) * c.v_pitch + (size_t)(x >> 1) * c.uv_step) - 128;
-            constexpr int K16 = 16 * 1220542;
-            const int ruv = (1 << 19) - K16 + 1673527 * v, guv = (1 << 19) - K16 - 852492 * v - 409993 * u, buv = (1 << 19) - K16 + 2116026 * u;
-            a = yuv_px16(max((uint32_t)__ldg(c.y + (size_t)y0 * c.y_pitch + x), 16u), ruv, guv, buv);
-            b = yuv_px16(max((uint32_t)__ldg(c.y + (size_t)(y0 + 1) * c.y_pitch + x), 16u), ruv, guv, buv);
+        if (x >= 0 && x < c.w && y0 >= 0 && y0 < c.h) {
+            const Chroma ch = chroma_terms((uint32_t)__ldg(c.u + (size_t)(y0 >> 1) * c.u_pitch + (size_t)(x >> 1) * c.uv_step) << 8,
+                                           (uint32_t)__ldg(c.v + (size_t)(y0 >> 1) * c.v_pitch + (size_t)(x >> 1) * c.uv_step) << 8);
+            a = yuv_px((uint32_t)__ldg(c.y + (size_t)y0 * c.y_pitch + x) << 8, ch);
+            b = yuv_px((uint32_t)__ldg(c.y + (size_t)(y0 + 1) * c.y_pitch + x) << 8, ch);
             if (c.vignette) {
                 a = vignette_px(a, __ldg(c.vignette + (size_t)y0 * c.w + x));
                 b = vignette_px(b, __ldg(c.vignette + (size_t)(y0 + 1) * c.w + x));
@@ -140,58 +145,68 @@ __device__ __noinline__ void convert_item_slow(const CamSrc& c, int x0, int y0, 
     }
 }
 
-// convert one item and store its 2 x 8 RGBX pixels into the stage (pixels outside the source become 0 = BORDER_CONSTANT)
-__device__ __forceinline__ void convert_item(const CamSrc& c, const FJob& J, int item, const ItemRegs& r, uint32_t mask, uint32_t* s_rgbx)
+// convert one item from the Y / chroma stages and store its 2 x 8 RGBX pixels into the RGBX stage
+__device__ __forceinline__ void convert_item(const CamSrc& c, const FJob& J, uint32_t desc, const uint8_t* s_yst, const uint8_t* s_uvst, uint32_t* s_rgbx)
 {
-    int rp, gx;
-    item_pos(J, item, rp, gx);
-    uint4* d0 = reinterpret_cast<uint4*>(s_rgbx + (rp << 1) * J.bw + (gx << 3));
-    uint4* d1 = reinterpret_cast<uint4*>(s_rgbx + ((rp << 1) + 1) * J.bw + (gx << 3));
-    if (mask == 0u) {
+    const int rp = desc & 127u, gx = (desc >> 7) & 127u;
+    const uint32_t cls = desc >> 14;
+    const int o0 = (rp << 1) * J.bw + (gx << 3);
+    uint4* d0 = reinterpret_cast<uint4*>(s_rgbx + o0);
+    uint4* d1 = reinterpret_cast<uint4*>(s_rgbx + o0 + J.bw);
+    if (cls == FITEM_ZERO) {                                 // BORDER_CONSTANT
         const uint4 z = make_uint4(0u, 0u, 0u, 0u);
         d0[0] = z; d0[1] = z; d1[0] = z; d1[1] = z;
         return;
     }
-    if (mask & ITEM_SLOW) {
+    if (cls == FITEM_SLOW || !c.aligned4) {
         convert_item_slow(c, J.bx0 + (gx << 3), J.by0 + (rp << 1), reinterpret_cast<uint32_t*>(d0), reinterpret_cast<uint32_t*>(d1));
         return;
     }
-    uint32_t a[8], b[8];
-    constexpr int K16 = 16 * 1220542;
+    const uint2 ya = *reinterpret_cast<const uint2*>(s_yst + o0);
+    const uint2 yb = *reinterpret_cast<const uint2*>(s_yst + o0 + J.bw);
+    uint32_t ub, vb;
+    if (c.uv_step == 1) {
+        ub = *reinterpret_cast<const uint32_t*>(s_uvst + rp * (J.bw >> 1) + (gx << 2));
+        vb = *reinterpret_cast<const uint32_t*>(s_uvst + FUSED_CAP / 4 + rp * (J.bw >> 1) + (gx << 2));
+    } else {
+        const uint2 uv = *reinterpret_cast<const uint2*>(s_uvst + rp * J.bw + (gx << 3));
+        ub = __byte_perm(uv.x, uv.y, 0x6420);
+        vb = __byte_perm(uv.x, uv.y, 0x7531);
+    }
+    const bool vig = c.vignette != nullptr;
+    const float* vg = vig ? c.vignette + (size_t)(J.by0 + (rp << 1)) * c.w + J.bx0 + (gx << 3) : nullptr;
     #pragma unroll
-    for (int k = 0; k < 4; k++) {
-        const int u = (int)((r.u >> (8 * k)) & 255u) - 128, v = (int)((r.v >> (8 * k)) & 255u) - 128;
-        const int ruv = (1 << 19) - K16 + 1673527 * v;
-        const int guv = (1 << 19) - K16 - 852492 * v - 409993 * u;
-        const int buv = (1 << 19) - K16 + 2116026 * u;
-        const uint32_t wa = k < 2 ? r.y0.x : r.y0.y, wb = k < 2 ? r.y1.x : r.y1.y;
-        const int sh = 16 * (k & 1);
-        a[2 * k] = yuv_px16(max((wa >> sh) & 255u, 16u), ruv, guv, buv);
-        a[2 * k + 1] = yuv_px16(max((wa >> (sh + 8)) & 255u, 16u), ruv, guv, buv);
-        b[2 * k] = yuv_px16(max((wb >> sh) & 255u, 16u), ruv, guv, buv);
-        b[2 * k + 1] = yuv_px16(max((wb >> (sh + 8)) & 255u, 16u), ruv, guv, buv);
+    for (int h = 0; h < 2; h++) {                            // four pixels of both rows at a time
+        const uint32_t wa = h ? ya.y : ya.x, wb = h ? yb.y : yb.x;
+        const Chroma c0 = chroma_terms(__byte_perm(ub, 0u, 0x4404 + (2 * h << 4)), __byte_perm(vb, 0u, 0x4404 + (2 * h << 4)));
+        const Chroma c1 = chroma_terms(__byte_perm(ub, 0u, 0x4414 + (2 * h << 4)), __byte_perm(vb, 0u, 0x4414 + (2 * h << 4)));
+        uint4 a, b;
+        a.x = yuv_px(__byte_perm(wa, 0u, 0x4404), c0); a.y = yuv_px(__byte_perm(wa, 0u, 0x4414), c0);
+        a.z = yuv_px(__byte_perm(wa, 0u, 0x4424), c1); a.w = yuv_px(__byte_perm(wa, 0u, 0x4434), c1);
+        b.x = yuv_px(__byte_perm(wb, 0u, 0x4404), c0); b.y = yuv_px(__byte_perm(wb, 0u, 0x4414), c0);
+        b.z = yuv_px(__byte_perm(wb, 0u, 0x4424), c1); b.w = yuv_px(__byte_perm(wb, 0u, 0x4434), c1);
+        if (vig) {
+            a.x = vignette_px(a.x, __ldg(vg + 4 * h)); a.y = vignette_px(a.y, __ldg(vg + 4 * h + 1));
+            a.z = vignette_px(a.z, __ldg(vg + 4 * h + 2)); a.w = vignette_px(a.w, __ldg(vg + 4 * h + 3));
+            b.x = vignette_px(b.x, __ldg(vg + c.w + 4 * h)); b.y = vignette_px(b.y, __ldg(vg + c.w + 4 * h + 1));
+            b.z = vignette_px(b.z, __ldg(vg + c.w + 4 * h + 2)); b.w = vignette_px(b.w, __ldg(vg + c.w + 4 * h + 3));
+        }
+        d0[h] = a; d1[h] = b;
     }
-    if (c.vignette) {
-        const int x0 = J.bx0 + (gx << 3), y0 = J.by0 + (rp << 1);
-        #pragma unroll
-        for (int k = 0; k < 8; k++)
-            {
-                a[k] = vignette_px(a[k], __ldg(c.vignette + (size_t)y0 * c.w + x0 + k));
-                b[k] = vignette_px(b[k], __ldg(c.vignette + (size_t)(y0 + 1) * c.w + x0 + k));
-            }
-    }
-    d0[0] = make_uint4(a[0], a[1], a[2], a[3]); d0[1] = make_uint4(a[4], a[5], a[6], a[7]);
-    d1[0] = make_uint4(b[0], b[1], b[2], b[3]); d1[1] = make_uint4(b[4], b[5], b[6], b[7]);
 }
 
 // one table entry: four taps from the stage, 1/32-px bilinear, gain, weight, accumulate.
-// ex = byte offset of the top-left tap in the stage | fy << 16 | fx << 24 ; ew = f32 weight bits
-template <int GAIN>
-__device__ __forceinline__ void fused_pair(uint32_t ex, uint32_t ew, uint32_t stage, uint32_t bw4, float g32, float gbias,
-                                           const uint8_t* __restrict__ lut, uint32_t& ar, uint32_t& ag, uint32_t& ab)
+// ex = byte offset of the top-left tap in the stage | fy << 16 | fx << 24 ; ew = f32 weight bits.
+// The sums of floor(v * W) are at most 255 * MAX_CAMS < 2^16: R and G share one accumulator (G in the high half), the
+// blue sums of two pixels share another.  bits(2^23 + k) * 65536 = k << 16 mod 2^32, so the high halves need no bias
+// removal and take their add on the IMAD pipe.
+template <int GAIN, bool LUT, bool BHI>
+__device__ __forceinline__ void fused_pair(uint32_t ex, uint32_t ew, const uint8_t* __restrict__ s0, const uint8_t* __restrict__ s1,
+                                           float g32, float gbias, const uint8_t* __restrict__ lut, uint32_t& arg, uint32_t& ab)
 {
-    const uint32_t a0 = stage + (ex & 0xFFFFu), a1 = a0 + bw4;
-    const uint32_t t00 = lds_u32(a0), t01 = lds_u32(a0 + 4), t10 = lds_u32(a1), t11 = lds_u32(a1 + 4);
+    const uint32_t off = ex & 0xFFFFu;
+    const uint32_t t00 = *reinterpret_cast<const uint32_t*>(s0 + off), t01 = *reinterpret_cast<const uint32_t*>(s0 + off + 4);
+    const uint32_t t10 = *reinterpret_cast<const uint32_t*>(s1 + off), t11 = *reinterpret_cast<const uint32_t*>(s1 + off + 4);
     const uint32_t fx = ex >> 24, fy = __byte_perm(ex, 0u, 0x4442);
     const uint32_t wx = fx * 65535u + 32u;                 // (32-fx) | fx << 16
     const uint32_t wb = wx * fy, wt = wx * 32u - wb;       // {(32-fx) fy, fx fy}, {(32-fx)(32-fy), fx (32-fy)} as 16-bit pairs
@@ -206,35 +221,54 @@ __device__ __forceinline__ void fused_pair(uint32_t ex, uint32_t ew, uint32_t st
     float rf = __fmaf_rd(__uint2float_rn(r), 0.0009765625f, MAGIC_RD);
     float gf = __fmaf_rd(__uint2float_rn(g), 0.0009765625f, MAGIC_RD);
     float bf = __fmaf_rd(__uint2float_rn(b), 0.0009765625f, MAGIC_RD);
-    if (GAIN) {
-        if (lut == nullptr) {
-            rf = gain_apply_biased(rf, g32, gbias); gf = gain_apply_biased(gf, g32, gbias); bf = gain_apply_biased(bf, g32, gbias);
-        } else {
-            rf = (float)__ldg(lut + (__float_as_uint(rf) & 255u)); gf = (float)__ldg(lut + (__float_as_uint(gf) & 255u));
-            bf = (float)__ldg(lut + (__float_as_uint(bf) & 255u));
-        }
+    if (GAIN && !LUT) {
+        rf = gain_apply_biased(rf, g32, gbias); gf = gain_apply_biased(gf, g32, gbias); bf = gain_apply_biased(bf, g32, gbias);
+    } else if (GAIN) {
+        rf = (float)__ldg(lut + (__float_as_uint(rf) & 255u)); gf = (float)__ldg(lut + (__float_as_uint(gf) & 255u));
+        bf = (float)__ldg(lut + (__float_as_uint(bf) & 255u));
     } else {
         rf = __fadd_rn(rf, -MAGIC_RD); gf = __fadd_rn(gf, -MAGIC_RD); bf = __fadd_rn(bf, -MAGIC_RD);
     }
-    // (short)(v * W): f32 product, truncated (v*W >= 0 so floor == trunc); 2^23 bias removed in the same add.
+    // (short)(v * W): f32 product, truncated (v*W >= 0 so floor == trunc)
     const float w = __uint_as_float(ew);
-    ar += __float_as_uint(__fadd_rd(__fmul_rn(rf, w), MAGIC_RD)) - 0x4B000000u;
-    ag += __float_as_uint(__fadd_rd(__fmul_rn(gf, w), MAGIC_RD)) - 0x4B000000u;
-    ab += __float_as_uint(__fadd_rd(__fmul_rn(bf, w), MAGIC_RD)) - 0x4B000000u;
+    arg += __float_as_uint(__fadd_rd(__fmul_rn(rf, w), MAGIC_RD)) - 0x4B000000u;
+    arg = __float_as_uint(__fadd_rd(__fmul_rn(gf, w), MAGIC_RD)) * 65536u + arg;
+    if (BHI) ab = __float_as_uint(__fadd_rd(__fmul_rn(bf, w), MAGIC_RD)) * 65536u + ab;
+    else ab += __float_as_uint(__fadd_rd(__fmul_rn(bf, w), MAGIC_RD)) - 0x4B000000u;
+}
+
+template <int GAIN, bool LUT>
+__device__ __forceinline__ void gather_job(const uint4 e0, const uint4 e1, const uint8_t* s0, const uint8_t* s1, float g32, float gb,
+                                           const uint8_t* lut, uint32_t (&arg)[FT_PPT], uint32_t (&ab)[FT_PPT / 2])
+{
+    fused_pair<GAIN, LUT, false>(e0.x, e0.y, s0, s1, g32, gb, lut, arg[0], ab[0]);
+    fused_pair<GAIN, LUT, true>(e0.z, e0.w, s0, s1, g32, gb, lut, arg[1], ab[0]);
+    fused_pair<GAIN, LUT, false>(e1.x, e1.y, s0, s1, g32, gb, lut, arg[2], ab[1]);
+    fused_pair<GAIN, LUT, true>(e1.z, e1.w, s0, s1, g32, gb, lut, arg[3], ab[1]);
+}
+
+// dst_16s.convertTo(CV_8UC3, 1.0/N): sat_u8(rint((float)acc * (float)(1/N))) without F2I: the product is rounded to
+// f32 first (as the reference does), the magic add rounds it to the nearest-even integer in the mantissa
+__device__ __forceinline__ int normalise_ch(uint32_t acc, float inv_n)
+{
+    const uint32_t bits = __float_as_uint(__fadd_rn(__fmul_rn(__uint2float_rn(acc), inv_n), MAGIC_RN));
+    return (int)(min(bits, 0x4B4000FFu) & 255u);
 }
 
 template <int GAIN>
-__global__ void __launch_bounds__(FT_THREADS, 3) k_stitch_fused(const __grid_constant__ FusedParams p)
+__global__ void __launch_bounds__(FT_THREADS, 4) k_stitch_fused(const __grid_constant__ FusedParams p)
 {
     extern __shared__ __align__(128) uint8_t smem[];
     uint32_t* s_rgbx = reinterpret_cast<uint32_t*>(smem + FS_RGBX);
     uint8_t* s_y = smem + FS_Y; uint8_t* s_u = smem + FS_U; uint8_t* s_v = smem + FS_V;
     float4* s_gain = reinterpret_cast<float4*>(smem + FS_GAIN);
-    const uint32_t stage = smem_u32(s_rgbx), ent_base = smem_u32(smem + FS_ENT), mbar_base = smem_u32(smem + FS_MBAR);
+    const uint32_t ent_base = smem_u32(smem + FS_ENT), mbar_base = smem_u32(smem + FS_MBAR);
+    const uint32_t yst = smem_u32(smem + FS_YST), uvst = smem_u32(smem + FS_UVST);
     const int tid = threadIdx.x, lx = tid & 31, ly = tid >> 5;
 
-    int ti = __ldg(p.bin_start + blockIdx.x);
-    const int tend = __ldg(p.bin_start + blockIdx.x + 1);
+    const FBin bin = *reinterpret_cast<const FBin*>(p.bins + blockIdx.x);
+    int ti = bin.start;
+    const int tend = bin.end;
     if (ti >= tend) return;
 
     // ---- prologue: metadata of the first two tiles, gain constants, barriers ----
@@ -253,75 +287,85 @@ __global__ void __launch_bounds__(FT_THREADS, 3) k_stitch_fused(const __grid_con
     }
     __syncthreads();
 
-    ItemRegs it0, it1;
-    uint32_t imask = 0u;                                    // bits 0-15 item 0, bits 16-31 item 1
-    auto prefetch_job = [&](const FJob& N, int j, int buf) {
-        if (tid == 0) {
-            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-            f_mbar_expect_tx(mbar_base + 8 * buf, FT_PX * 8);
-            bulk_g2s(ent_base + buf * (FT_PX * 8), p.entries + (size_t)j * FT_PX, FT_PX * 8, mbar_base + 8 * buf);
-        }
-        const CamSrc& c = p.cam[N.cam];
-        uint32_t m0 = 0u, m1 = 0u;
-        if (tid < N.nitems) load_item(c, N, tid, it0, m0);
-        if (tid + FT_THREADS < N.nitems) load_item(c, N, tid + FT_THREADS, it1, m1);
-        imask = m0 | (m1 << 16);
+    // Record k of the CTA's job sequence lives in buffer k & 1: entries of job k, then the item list of job k + 1.
+    uint32_t phase0 = 0u, phase1 = 0u;
+    auto request = [&](int buf, uint32_t rec16, uint32_t bytes, int dst_off) {        // one thread: TMA bulk copy of a record
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        f_mbar_expect_tx(mbar_base + 8 * buf, bytes);
+        bulk_g2s(ent_base + buf * FS_REC_STRIDE + dst_off, p.stream + rec16, bytes, mbar_base + 8 * buf);
     };
-    {
+    auto wait_rec = [&](int buf) {
+        if (buf == 0) { f_mbar_wait(mbar_base, phase0); phase0 ^= 1u; } else { f_mbar_wait(mbar_base + 8, phase1); phase1 ^= 1u; }
+    };
+    // input bytes of job N (item list in buffer `ibuf`) -> Y / chroma stages, by per-thread asynchronous copies
+    auto fetch_job = [&](const FJob& N, int ibuf) {
+        const CamSrc& c = p.cam[N.cam];
+        const uint16_t* items = reinterpret_cast<const uint16_t*>(smem + FS_ENT + ibuf * FS_REC_STRIDE + FT_PX * 8);
+        if (c.aligned4) {
+            if (tid < N.nitems) fetch_item(c, N, items[tid], yst, uvst);
+            if (tid + FT_THREADS < N.nitems) fetch_item(c, N, items[tid + FT_THREADS], yst, uvst);
+        }
+        cp_async_commit();
+    };
+    {   // the first job's item list travels alone (buffer 1); then its record (buffer 0) is requested
         const FTileBlock* B = reinterpret_cast<const FTileBlock*>(meta_slot(ti));
-        prefetch_job(B->job[0], B->tile.j0, 0);
+        if (tid == 0) {
+            if (bin.head_bytes) request(1, bin.head16, bin.head_bytes, FT_PX * 8);
+            request(0, B->job[0].rec16, B->job[0].rec_bytes, 0);
+        }
+        if (bin.head_bytes) wait_rec(1);
+        fetch_job(B->job[0], 1);
+        cp_async_wait_all();
+        __syncthreads();
     }
 
-    uint32_t phase0 = 0u, phase1 = 0u;
     int buf = 0;
     for (; ti < tend; ti++) {
         const FTileBlock* B = reinterpret_cast<const FTileBlock*>(meta_slot(ti));
         const FTile T = B->tile;
-        uint32_t acc[FT_PPT][3];
+        uint32_t arg[FT_PPT], ab[FT_PPT / 2];
         #pragma unroll
-        for (int q = 0; q < FT_PPT; q++) acc[q][0] = acc[q][1] = acc[q][2] = 0u;
+        for (int q = 0; q < FT_PPT; q++) arg[q] = 0u;
+        #pragma unroll
+        for (int q = 0; q < FT_PPT / 2; q++) ab[q] = 0u;
         uint4 meta_next = make_uint4(0u, 0u, 0u, 0u);
 
         #pragma unroll 1
         for (int k = 0; k < T.nj; k++) {
             const FJob J = B->job[k];
-            // ---- (1) convert this job's source box (input bytes were prefetched during the previous job) ----
+            // ---- (1) convert this job's items (input bytes were copied into the stages during the previous job) ----
             {
                 const CamSrc& c = p.cam[J.cam];
-                if (tid < J.nitems) convert_item(c, J, tid, it0, imask & 0xFFFFu, s_rgbx);
-                if (tid + FT_THREADS < J.nitems) convert_item(c, J, tid + FT_THREADS, it1, imask >> 16, s_rgbx);
+                const uint16_t* items = reinterpret_cast<const uint16_t*>(smem + FS_ENT + (buf ^ 1) * FS_REC_STRIDE + FT_PX * 8);
+                if (tid < J.nitems) convert_item(c, J, items[tid], smem + FS_YST, smem + FS_UVST, s_rgbx);
+                if (tid + FT_THREADS < J.nitems) convert_item(c, J, items[tid + FT_THREADS], smem + FS_YST, smem + FS_UVST, s_rgbx);
             }
             __syncthreads();
-            // ---- (2) prefetch the next job (entries by TMA bulk copy, input bytes into registers) ----
-            if (k + 1 < T.nj) prefetch_job(B->job[k + 1], T.j0 + k + 1, buf ^ 1);
-            else if (ti + 1 < tend) {
-                const FTileBlock* Bn = reinterpret_cast<const FTileBlock*>(meta_slot(ti + 1));
-                prefetch_job(Bn->job[0], Bn->tile.j0, buf ^ 1);
-            }
+            // ---- (2) request the next record, wait for this one, start the input copies of the next job ----
+            const FJob* N = nullptr;
+            if (k + 1 < T.nj) N = &B->job[k + 1];
+            else if (ti + 1 < tend) N = &reinterpret_cast<const FTileBlock*>(meta_slot(ti + 1))->job[0];
+            if (N && tid == 0) request(buf ^ 1, N->rec16, N->rec_bytes, 0);
             if (k == 0 && ti + 2 < tend && tid < 65) meta_next = __ldg(reinterpret_cast<const uint4*>(p.blocks + ti + 2) + tid);
+            wait_rec(buf);
+            if (N) fetch_job(*N, buf);
             // ---- (3) gather ----
-            if (buf == 0) { f_mbar_wait(mbar_base, phase0); phase0 ^= 1u; } else { f_mbar_wait(mbar_base + 8, phase1); phase1 ^= 1u; }
             {
-                const uint32_t eaddr = ent_base + buf * (FT_PX * 8) + tid * 32;
-                uint4 e0, e1;
-                asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(e0.x), "=r"(e0.y), "=r"(e0.z), "=r"(e0.w) : "r"(eaddr));
-                asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(e1.x), "=r"(e1.y), "=r"(e1.z), "=r"(e1.w) : "r"(eaddr + 16));
-                const uint32_t bw4 = (uint32_t)J.bw * 4u;
-                float g32 = 0.f, gb = 0.f;
-                const uint8_t* lut = nullptr;
+                const uint4* ep = reinterpret_cast<const uint4*>(smem + FS_ENT + buf * FS_REC_STRIDE) + tid * 2;
+                const uint4 e0 = ep[0], e1 = ep[1];
+                const uint8_t* s0 = smem + FS_RGBX;
+                const uint8_t* s1 = s0 + J.bw * 4;
                 if (GAIN) {
                     const float4 gc = s_gain[J.cam];
-                    g32 = gc.x; gb = gc.y;
-                    if (__float_as_int(gc.z) != 0) lut = p.gain_lut + J.cam * 256;
-                }
-                fused_pair<GAIN>(e0.x, e0.y, stage, bw4, g32, gb, lut, acc[0][0], acc[0][1], acc[0][2]);
-                fused_pair<GAIN>(e0.z, e0.w, stage, bw4, g32, gb, lut, acc[1][0], acc[1][1], acc[1][2]);
-                fused_pair<GAIN>(e1.x, e1.y, stage, bw4, g32, gb, lut, acc[2][0], acc[2][1], acc[2][2]);
-                fused_pair<GAIN>(e1.z, e1.w, stage, bw4, g32, gb, lut, acc[3][0], acc[3][1], acc[3][2]);
+                    if (__float_as_int(gc.z) == 0) gather_job<GAIN, false>(e0, e1, s0, s1, gc.x, gc.y, nullptr, arg, ab);
+                    else gather_job<GAIN, true>(e0, e1, s0, s1, gc.x, gc.y, p.gain_lut + J.cam * 256, arg, ab);
+                } else
+                    gather_job<0, false>(e0, e1, s0, s1, 0.f, 0.f, nullptr, arg, ab);
             }
             if (k == 0 && ti + 2 < tend && tid < 65) reinterpret_cast<uint4*>(meta_slot(ti + 2))[tid] = meta_next;
             buf ^= 1;
-            __syncthreads();                                // stage and entry buffer are free again
+            cp_async_wait_all();
+            __syncthreads();                                // RGBX stage and record buffer are free, the next job's bytes have landed
         }
 
         // ---- tile epilogue: normalise, RGB -> YUV 4:2:0 into shared memory, then 128-bit row stores ----
@@ -329,8 +373,8 @@ __global__ void __launch_bounds__(FT_THREADS, 3) k_stitch_fused(const __grid_con
         #pragma unroll
         for (int q = 0; q < FT_PPT; q++) {
             const int row = ly + 8 * q;
-            const uint32_t px = normalise_px(acc[q][0], acc[q][1], acc[q][2], p.inv_n);
-            const int R = px & 255u, G = (px >> 8) & 255u, Bc = (px >> 16) & 255u;
+            const int R = normalise_ch(arg[q] & 0xFFFFu, p.inv_n), G = normalise_ch(arg[q] >> 16, p.inv_n);
+            const int Bc = normalise_ch((q & 1) ? ab[q >> 1] >> 16 : ab[q >> 1] & 0xFFFFu, p.inv_n);
             s_y[row * FT_W + lx] = (uint8_t)rgb_luma(R, G, Bc);
             if (((lx | ly) & 1) == 0) {                      // top-left pixel of a 2x2 block carries the chroma (color.cpp:6456-6481)
                 s_u[(row >> 1) * (FT_W / 2) + (lx >> 1)] = (uint8_t)rgb_cb(R, G, Bc);
