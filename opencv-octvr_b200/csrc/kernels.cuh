@@ -98,37 +98,38 @@ void launch_blend_staged(const StagedParams& p, cudaStream_t s);
 
 // ---- K_stitch_fused: the whole feather / no-blend frame in ONE kernel, no intermediate image in HBM ----
 //      Persistent CTAs (4 per SM) walk a host-balanced list of 32x32 output tiles.  For every (tile, camera) job the
-//      CTA (1) converts the job's SOURCE BOX of the 4:2:0 input planes (L2-resident, 37 MB for the 6 x 2.7K rig)
-//      straight into an RGBX stage in shared memory (same integer BT.601 arithmetic as K_convert), (2) gathers the
-//      four bilinear taps per output pixel from that stage with LDS, interpolates (IDP.2A), applies gain and weight
-//      and accumulates in registers; the tile is then normalised, converted to YUV 4:2:0 and stored with 128-bit
-//      stores.  The 8 B/pair table entries of job k+1 arrive by a TMA bulk copy (cp.async.bulk + mbarrier) while
-//      job k is processed; the input bytes of job k+1 are prefetched into registers.
-constexpr int FT_W = 32, FT_H = 32, FT_PX = FT_W * FT_H, FT_THREADS = 256, FT_PPT = FT_PX / FT_THREADS;
+//      CTA (1) converts the job's source blocks of the 4:2:0 input planes (L2-resident: 37 MB for the 6 x 2.7K rig)
+//      into an RGBX stage in shared memory (same integer BT.601 arithmetic as K_convert), (2) gathers the four
+//      bilinear taps per output pixel from that stage with LDS, interpolates (IDP.2A), applies gain and weight and
+//      accumulates in registers; a finished tile is normalised, converted to YUV 4:2:0 and stored with 128-bit stores.
+//      Everything a job needs is in flight one or two jobs ahead: its 8 B/pair table entries by a TMA bulk copy
+//      (cp.async.bulk + mbarrier transaction count), its input bytes by per-thread cp.async into thread-private
+//      slots, its job record and item descriptors by plain loads into registers.
+constexpr int FT_W = 32, FT_H = 32, FT_PX = FT_W * FT_H, FT_PPT = 4;
+constexpr int FT_THREADS = FT_PX / FT_PPT;
 constexpr int FUSED_CAP = 6144;          // RGBX stage capacity in pixels (24 KB); a job whose box is larger is split by rows
-constexpr int FUSED_MAXJ = 32;           // jobs per tile (cameras x row splits)
 constexpr int FUSED_MAXITEMS = 2 * FT_THREADS;   // conversion items (8 px x 2 rows of the source box) per job
 // conversion item descriptor (u16): row pair (7 bits) | 8-px group << 7 (7 bits) | class << 14
 enum { FITEM_ZERO = 0, FITEM_FAST = 1, FITEM_SLOW = 2 };     // outside the source (-> 0), inside, straddles the border
-struct FJob {                            // 32 B
-    int cam;
+constexpr int FJOB_LAST = (int)0x80000000u;                  // cam field: last job of its output tile
+struct FJob {                            // 32 B, one per (tile, camera[, row range]), in the order the CTA consumes them
+    int cam;                             // | FJOB_LAST
     int bx0, by0;                        // top-left of the source box (bx0 % 8 == 0, by0 % 2 == 0, may be negative)
     int bw;                              // box width in px (bw % 8 == 0); box area <= FUSED_CAP
-    int nitems;                          // conversion items of this job: only the 8x2 blocks some bilinear tap touches
-    uint32_t rec16;                      // this job's record in the table stream (16-byte units): FT_PX entries of 8 B
-    uint32_t rec_bytes;                  //   followed by the item list of the NEXT job of the CTA's schedule
+    int nitems;                          // conversion items: only the 8x2 blocks some bilinear tap touches
+    uint32_t items_off;                  // (unused) descriptors of job j are at FusedParams::items[j * FUSED_MAXITEMS ...]; item i -> thread i % FT_THREADS
+    uint32_t tile_xy;                    // output tile: x | y << 16 (tile units)
     int pad;
 };
-struct FTile { int tx, ty, nj, pad; };   // tile position (tile units), jobs
-struct FTileBlock { FJob job[FUSED_MAXJ]; FTile tile; };     // one self-contained record per tile, in schedule order
-static_assert(sizeof(FJob) == 32 && sizeof(FTileBlock) == 32 * FUSED_MAXJ + 16, "FTileBlock is read as uint4s");
-struct FBin { int start, end; uint32_t head16, head_bytes; };   // a CTA's tiles [start, end) and the item list of its first job
+static_assert(sizeof(FJob) == 32, "FJob is read as two uint4");
+struct FBin { int start, end; };         // a CTA's jobs [start, end)
 struct FusedParams {
     CamSrc cam[MAX_CAMS];
     int n;
-    const FTileBlock* blocks;            // [tiles], grouped by CTA
+    const FJob* jobs;                    // [jobs] in schedule order, grouped by CTA
     const FBin* bins;                    // [grid]
-    const uint4* stream;                 // job records in schedule order; entry = {byte offset in the stage | fy << 16 | fx << 24, f32 weight}
+    const uint16_t* items;
+    const uint2* entries;                // [jobs * FT_PX]: {byte offset in the stage | fy << 16 | fx << 24, f32 weight}
     int out_w, out_h;
     uint8_t* oy; uint8_t* ou; uint8_t* ov;
     uint32_t oy_pitch, ou_pitch, ov_pitch;

@@ -77,7 +77,7 @@ octvr_mapper::~octvr_mapper()
     cudaSetDevice(device);
     for (auto p : d_rgbx) cudaFree(p);
     for (auto p : d_vig) cudaFree(p);
-    cudaFree(d_tile_job_start); cudaFree(d_job_cam); cudaFree(d_coords); cudaFree(d_weights); cudaFree(d_jobs); cudaFree(d_entries); cudaFree(d_tmaps); cudaFree(d_fblocks); cudaFree(d_fbins); cudaFree(d_fstream);
+    cudaFree(d_tile_job_start); cudaFree(d_job_cam); cudaFree(d_coords); cudaFree(d_weights); cudaFree(d_jobs); cudaFree(d_entries); cudaFree(d_tmaps); cudaFree(d_fjobs); cudaFree(d_fbins); cudaFree(d_fitems);
     cudaFree(d_smask); cudaFree(d_gcoord); cudaFree(d_partial); cudaFree(d_ticket);
     cudaFree(d_gains); cudaFree(d_gain_f32); cudaFree(d_gain_flag); cudaFree(d_gain_lut); cudaFree(d_rgb); cudaFree(d_dbg);
     if (h_gains) cudaFreeHost(h_gains);
@@ -164,7 +164,6 @@ static bool build_fused(octvr_mapper& m, const octvr_template& t, const std::vec
     };
     for (int tl = 0; tl < ntiles && ok; tl++) {
         for (int i = 0; i < n; i++) add_jobs(tl, i, 0, FT_H);
-        if ((int)tile_jobs[tl].size() > FUSED_MAXJ) ok = false;
         if (tile_jobs[tl].empty()) {                       // nobody covers this tile: one job with no items and zero weights
             Job jb; memset(&jb.rec, 0, sizeof(jb.rec));
             jb.cam = -1; jb.r0 = jb.r1 = 0; jb.rec.bw = 8;
@@ -181,8 +180,9 @@ static bool build_fused(octvr_mapper& m, const octvr_template& t, const std::vec
     const int grid = std::max(1, std::min(ntiles, sms * per_sm));
     std::vector<int64_t> cost(ntiles);
     for (int tl = 0; tl < ntiles; tl++) {
-        int64_t c = 6000;                                  // epilogue + stores
-        for (const Job& jb : tile_jobs[tl]) c += (int64_t)FT_PX * 50 + (int64_t)jb.items.size() * 16 * 13 + 4000;
+        // per-thread instruction estimates: ~190 for a job's four pixels, ~280 per conversion round, ~110 for the epilogue
+        int64_t c = 110;
+        for (const Job& jb : tile_jobs[tl]) c += 190 + 280 * (int64_t)((jb.items.size() + FT_THREADS - 1) / FT_THREADS) + 60;
         cost[tl] = c;
     }
     std::vector<int> order(ntiles);
@@ -200,63 +200,52 @@ static bool build_fused(octvr_mapper& m, const octvr_template& t, const std::vec
         }
     }
 
-    // ---- table stream in consumption order ----
-    std::vector<uint4> stream;
-    std::vector<FTileBlock> blocks;
-    blocks.reserve(ntiles);
+    // ---- tables in consumption order ----
+    std::vector<FJob> jobs;
     std::vector<FBin> bins(grid);
+    std::vector<uint16_t> items;
     size_t njobs = 0;
-    auto append_items = [&](const std::vector<uint16_t>& items) {      // padded to 16 bytes; returns the byte count
-        const size_t n16 = (items.size() * 2 + 15) / 16, at = stream.size();
-        stream.resize(at + n16, make_uint4(0u, 0u, 0u, 0u));
-        if (!items.empty()) memcpy(&stream[at], items.data(), items.size() * 2);
-        return (uint32_t)(n16 * 16);
-    };
+    for (auto& v : tile_jobs) njobs += v.size();
+    OB_CHECK(njobs * FT_PX < ((size_t)1 << 31), "table too large");
+    std::vector<uint2> entries(njobs * FT_PX, make_uint2(0u, 0u));
+    jobs.reserve(njobs);
     for (int b = 0; b < grid; b++) {
-        std::vector<Job*> seq;
-        for (int tl : bin_tiles[b]) for (Job& jb : tile_jobs[tl]) seq.push_back(&jb);
-        bins[b].start = (int)blocks.size();
-        bins[b].head16 = (uint32_t)stream.size();
-        bins[b].head_bytes = seq.empty() ? 0u : append_items(seq[0]->items);
-        for (size_t q = 0; q < seq.size(); q++) {
-            Job& jb = *seq[q];
-            OB_CHECK(stream.size() < ((size_t)1 << 32), "table too large");
-            jb.rec.rec16 = (uint32_t)stream.size();
-            stream.resize(stream.size() + FT_PX * 8 / 16, make_uint4(0u, 0u, 0u, 0u));       // entries: filled per tile below
-            jb.rec.rec_bytes = FT_PX * 8 + (q + 1 < seq.size() ? append_items(seq[q + 1]->items) : 0u);
-            njobs++;
-        }
-        for (int tl : bin_tiles[b]) {
-            FTileBlock B;
-            memset(&B, 0, sizeof(B));
-            B.tile.tx = tl % tiles_x; B.tile.ty = tl / tiles_x; B.tile.nj = (int)tile_jobs[tl].size();
+        bins[b].start = (int)jobs.size();
+        for (int tl : bin_tiles[b])
             for (size_t k = 0; k < tile_jobs[tl].size(); k++) {
                 const Job& jb = tile_jobs[tl][k];
-                B.job[k] = jb.rec;
-                if (jb.cam < 0) { B.job[k].cam = 0; continue; }
-                uint2* ent = reinterpret_cast<uint2*>(&stream[jb.rec.rec16]);
-                for (int tid = 0; tid < FT_THREADS; tid++)
-                    for (int q = 0; q < FT_PPT; q++) {
-                        const int px = tid & 31, py = (tid >> 5) + 8 * q;
-                        if (py < jb.r0 || py >= jb.r1) continue;
-                        int ix, iy; int32_t fsx, fsy; float w;
-                        if (!sample(tl, px, py, jb.cam, ix, iy, fsx, fsy, w)) continue;
-                        const uint32_t off = (uint32_t)(((iy - jb.rec.by0) * jb.rec.bw + (ix - jb.rec.bx0)) * 4);
-                        uint32_t wbits; memcpy(&wbits, &w, 4);
-                        ent[tid * FT_PPT + q] = make_uint2(off | ((uint32_t)(fsy & 31) << 16) | ((uint32_t)(fsx & 31) << 24), wbits);
-                    }
+                FJob r = jb.rec;
+                r.cam = std::max(jb.cam, 0) | (k + 1 == tile_jobs[tl].size() ? FJOB_LAST : 0);
+                r.tile_xy = (uint32_t)(tl % tiles_x) | ((uint32_t)(tl / tiles_x) << 16);
+                // descriptors at a fixed stride per job, so their address does not depend on the job record
+                r.items_off = (uint32_t)items.size();
+                items.insert(items.end(), jb.items.begin(), jb.items.end());
+                items.resize(r.items_off + FUSED_MAXITEMS, (uint16_t)0);
+                if (jb.cam >= 0) {
+                    uint2* ent = entries.data() + jobs.size() * FT_PX;
+                    for (int tid = 0; tid < FT_THREADS; tid++)
+                        for (int q = 0; q < FT_PPT; q++) {
+                            const int px = tid & 31, py = (tid >> 5) + 8 * q;
+                            if (py < jb.r0 || py >= jb.r1) continue;
+                            int ix, iy; int32_t fsx, fsy; float w;
+                            if (!sample(tl, px, py, jb.cam, ix, iy, fsx, fsy, w)) continue;
+                            const uint32_t off = (uint32_t)(((iy - r.by0) * r.bw + (ix - r.bx0)) * 4);
+                            uint32_t wbits; memcpy(&wbits, &w, 4);
+                            ent[tid * FT_PPT + q] = make_uint2(off | ((uint32_t)(fsy & 31) << 16) | ((uint32_t)(fsx & 31) << 24), wbits);
+                        }
+                }
+                jobs.push_back(r);
             }
-            blocks.push_back(B);
-        }
-        bins[b].end = (int)blocks.size();
+        bins[b].end = (int)jobs.size();
     }
     m.fused = true;
     m.fused_grid = grid;
     m.njobs = njobs;
-    m.d_fblocks = dev_upload(blocks.data(), blocks.size());
+    m.d_fjobs = dev_upload(jobs.data(), jobs.size());
     m.d_fbins = dev_upload(bins.data(), bins.size());
-    m.d_fstream = dev_upload(stream.data(), stream.size());
-    m.table_bytes = (int64_t)(stream.size() * sizeof(uint4) + blocks.size() * sizeof(FTileBlock));
+    m.d_fitems = dev_upload(items.data(), items.size());
+    m.d_entries = dev_upload(entries.data(), entries.size());
+    m.table_bytes = (int64_t)(entries.size() * sizeof(uint2) + jobs.size() * sizeof(FJob) + items.size() * 2);
     return true;
 }
 
@@ -610,7 +599,7 @@ void ob::mapper_stitch_internal(octvr_mapper& m, const octvr_frame* in, int n_in
         memset(&fp, 0, sizeof(fp));
         for (int i = 0; i < m.n; i++) fp.cam[i] = cp.cam[i];
         fp.n = m.n;
-        fp.blocks = m.d_fblocks; fp.bins = m.d_fbins; fp.stream = m.d_fstream;
+        fp.jobs = m.d_fjobs; fp.bins = m.d_fbins; fp.items = m.d_fitems; fp.entries = m.d_entries;
         fp.out_w = m.out_w; fp.out_h = m.out_h;
         if (out) {
             fp.oy = out->y; fp.ou = out->u; fp.ov = out->v;

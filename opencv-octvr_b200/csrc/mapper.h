@@ -31,9 +31,9 @@ struct octvr_mapper {
     // fused layout (K_stitch_fused)
     bool fused = false;
     int fused_grid = 0;
-    ob::FTileBlock* d_fblocks = nullptr;
+    ob::FJob* d_fjobs = nullptr;
     ob::FBin* d_fbins = nullptr;
-    uint4* d_fstream = nullptr;
+    uint16_t* d_fitems = nullptr;
     // gain compensation
     ob::GainParams gp;
     uint8_t* d_smask = nullptr; uint2* d_gcoord = nullptr; double* d_partial = nullptr;

@@ -18,21 +18,17 @@ namespace ob {
 
 // ---- shared-memory map of a CTA (dynamic) ----
 constexpr int FS_RGBX = 0;                                   // FUSED_CAP u32: the converted source box of the current job
-constexpr int FS_YST = FS_RGBX + FUSED_CAP * 4;              // FUSED_CAP bytes: luma of the NEXT job's box (cp.async destination)
-constexpr int FS_UVST = FS_YST + FUSED_CAP;                  // FUSED_CAP / 2 bytes: its chroma (U plane | V plane, or interleaved rows)
-constexpr int FS_REC_STRIDE = FT_PX * 8 + FUSED_MAXITEMS * 2;  // a job record: 8 B entries, then the item list of the next job
-constexpr int FS_ENT = FS_UVST + FUSED_CAP / 2;              // 2 x job record (TMA bulk destination)
-constexpr int FS_META = FS_ENT + 2 * FS_REC_STRIDE;          // 3 x FTileBlock (padded to 1056 B)
-constexpr int FS_META_STRIDE = 1056;
-constexpr int FS_Y = FS_META + 3 * FS_META_STRIDE;           // 32 x 32 luma bytes of the finished tile
-constexpr int FS_U = FS_Y + FT_PX;                           // 16 x 16
-constexpr int FS_V = FS_U + FT_PX / 4;
-constexpr int FS_GAIN = FS_V + FT_PX / 4;                    // MAX_CAMS x {g32, bias, flag, pad}
-constexpr int FS_MBAR = FS_GAIN + MAX_CAMS * 16;             // 2 x u64
+constexpr int FS_Y0 = FS_RGBX + FUSED_CAP * 4;               // thread-private slots for the input bytes of the NEXT job's items
+constexpr int FS_Y1 = FS_Y0 + 2 * FT_THREADS * 8;            //   (cp.async destinations; slot s of thread t at [s][t]):
+constexpr int FS_UV = FS_Y1 + 2 * FT_THREADS * 8;            //   luma rows 0 / 1 (8 B each), chroma (U 4 B | V 4 B, or NV12 UVUVUVUV)
+constexpr int FS_ENT = FS_UV + 2 * FT_THREADS * 8;           // 2 x FT_PX x 8 B table entries (TMA bulk destinations)
+constexpr int FS_OUT = FS_ENT + 2 * FT_PX * 8;               // 2 x {32 x 32 luma, 16 x 16 U, 16 x 16 V} of finished tiles
+constexpr int FS_OUT_STRIDE = FT_PX + FT_PX / 2;
+constexpr int FS_GAIN = FS_OUT + 2 * FS_OUT_STRIDE;          // MAX_CAMS x {g32, bias, flag, pad}
+constexpr int FS_MBAR = FS_GAIN + MAX_CAMS * 16;             // ent[2]
 constexpr int FS_TOTAL = FS_MBAR + 16;
-static_assert(FS_YST % 16 == 0 && FS_UVST % 16 == 0 && FS_ENT % 128 == 0 && FS_REC_STRIDE % 16 == 0 && FS_META % 16 == 0 && FS_Y % 16 == 0 && FS_MBAR % 8 == 0, "alignment");
+static_assert(FS_Y0 % 16 == 0 && FS_ENT % 128 == 0 && FS_OUT % 16 == 0 && FS_OUT_STRIDE % 16 == 0 && FS_MBAR % 8 == 0, "alignment");
 static_assert(4 * (FS_TOTAL + 1024) <= 228 * 1024, "four CTAs per SM");
-static_assert(FUSED_MAXITEMS == 2 * FT_THREADS, "at most two conversion items per thread");
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void f_mbar_init(uint32_t mbar, int count)
@@ -73,22 +69,21 @@ __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commi
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
 
 // ---- conversion items: 8 px x 2 rows of the job's source box (four chroma samples), listed by the host ----
-// issue the asynchronous copies of one item's input bytes into the Y / chroma stages
-__device__ __forceinline__ void fetch_item(const CamSrc& c, const FJob& J, uint32_t desc, uint32_t yst, uint32_t uvst)
+// what a thread keeps of a job record
+struct JobRegs { int cam, bx0, by0, bw, nitems; uint32_t tile_xy; };
+// issue the asynchronous copies of one item's input bytes (class FAST on 8/4-byte aligned planes) into the thread's slot
+__device__ __forceinline__ void fetch_item(const CamSrc& c, const JobRegs& J, uint32_t desc, uint32_t slot_y0)
 {
-    if ((desc >> 14) != FITEM_FAST) return;
     const int rp = desc & 127u, gx = (desc >> 7) & 127u;
     const int x0 = J.bx0 + (gx << 3), y0 = J.by0 + (rp << 1);
     const uint8_t* yp = c.y + (size_t)y0 * c.y_pitch + x0;
-    const uint32_t yd = yst + (uint32_t)((rp << 1) * J.bw + (gx << 3));
-    cp_async8(yd, yp);
-    cp_async8(yd + J.bw, yp + c.y_pitch);
+    cp_async8(slot_y0, yp);
+    cp_async8(slot_y0 + (FS_Y1 - FS_Y0), yp + c.y_pitch);
     if (c.uv_step == 1) {
-        const uint32_t cd = uvst + (uint32_t)(rp * (J.bw >> 1) + (gx << 2));
-        cp_async4(cd, c.u + (size_t)(y0 >> 1) * c.u_pitch + (x0 >> 1));
-        cp_async4(cd + FUSED_CAP / 4, c.v + (size_t)(y0 >> 1) * c.v_pitch + (x0 >> 1));
+        cp_async4(slot_y0 + (FS_UV - FS_Y0), c.u + (size_t)(y0 >> 1) * c.u_pitch + (x0 >> 1));
+        cp_async4(slot_y0 + (FS_UV - FS_Y0) + 4, c.v + (size_t)(y0 >> 1) * c.v_pitch + (x0 >> 1));
     } else                                                   // NV12: U0 V0 U1 V1 U2 V2 U3 V3
-        cp_async8(uvst + (uint32_t)(rp * J.bw + (gx << 3)), c.u + (size_t)(y0 >> 1) * c.u_pitch + x0);
+        cp_async8(slot_y0 + (FS_UV - FS_Y0), c.u + (size_t)(y0 >> 1) * c.u_pitch + x0);
 }
 
 // BT.601 limited-range integer conversion (imgproc/src/color.cpp:6087-6169):
@@ -145,41 +140,32 @@ __device__ __noinline__ void convert_item_slow(const CamSrc& c, int x0, int y0, 
     }
 }
 
-// convert one item from the Y / chroma stages and store its 2 x 8 RGBX pixels into the RGBX stage
-__device__ __forceinline__ void convert_item(const CamSrc& c, const FJob& J, uint32_t desc, const uint8_t* s_yst, const uint8_t* s_uvst, uint32_t* s_rgbx)
+// convert one item (input bytes in the thread's slot) and store its 2 x 8 RGBX pixels into the RGBX stage
+__device__ __forceinline__ void convert_item(const CamSrc& c, const JobRegs& J, uint32_t desc, bool fast, const uint8_t* slot_y0, uint32_t* s_rgbx)
 {
     const int rp = desc & 127u, gx = (desc >> 7) & 127u;
-    const uint32_t cls = desc >> 14;
     const int o0 = (rp << 1) * J.bw + (gx << 3);
     uint4* d0 = reinterpret_cast<uint4*>(s_rgbx + o0);
     uint4* d1 = reinterpret_cast<uint4*>(s_rgbx + o0 + J.bw);
-    if (cls == FITEM_ZERO) {                                 // BORDER_CONSTANT
-        const uint4 z = make_uint4(0u, 0u, 0u, 0u);
-        d0[0] = z; d0[1] = z; d1[0] = z; d1[1] = z;
+    if (!fast) {
+        if ((desc >> 14) == FITEM_ZERO) {                    // BORDER_CONSTANT
+            const uint4 z = make_uint4(0u, 0u, 0u, 0u);
+            d0[0] = z; d0[1] = z; d1[0] = z; d1[1] = z;
+        } else
+            convert_item_slow(c, J.bx0 + (gx << 3), J.by0 + (rp << 1), reinterpret_cast<uint32_t*>(d0), reinterpret_cast<uint32_t*>(d1));
         return;
     }
-    if (cls == FITEM_SLOW || !c.aligned4) {
-        convert_item_slow(c, J.bx0 + (gx << 3), J.by0 + (rp << 1), reinterpret_cast<uint32_t*>(d0), reinterpret_cast<uint32_t*>(d1));
-        return;
-    }
-    const uint2 ya = *reinterpret_cast<const uint2*>(s_yst + o0);
-    const uint2 yb = *reinterpret_cast<const uint2*>(s_yst + o0 + J.bw);
-    uint32_t ub, vb;
-    if (c.uv_step == 1) {
-        ub = *reinterpret_cast<const uint32_t*>(s_uvst + rp * (J.bw >> 1) + (gx << 2));
-        vb = *reinterpret_cast<const uint32_t*>(s_uvst + FUSED_CAP / 4 + rp * (J.bw >> 1) + (gx << 2));
-    } else {
-        const uint2 uv = *reinterpret_cast<const uint2*>(s_uvst + rp * J.bw + (gx << 3));
-        ub = __byte_perm(uv.x, uv.y, 0x6420);
-        vb = __byte_perm(uv.x, uv.y, 0x7531);
-    }
+    const uint2 ya = *reinterpret_cast<const uint2*>(slot_y0);
+    const uint2 yb = *reinterpret_cast<const uint2*>(slot_y0 + (FS_Y1 - FS_Y0));
+    uint2 uv = *reinterpret_cast<const uint2*>(slot_y0 + (FS_UV - FS_Y0));
+    if (c.uv_step != 1) uv = make_uint2(__byte_perm(uv.x, uv.y, 0x6420), __byte_perm(uv.x, uv.y, 0x7531));
     const bool vig = c.vignette != nullptr;
     const float* vg = vig ? c.vignette + (size_t)(J.by0 + (rp << 1)) * c.w + J.bx0 + (gx << 3) : nullptr;
     #pragma unroll
     for (int h = 0; h < 2; h++) {                            // four pixels of both rows at a time
         const uint32_t wa = h ? ya.y : ya.x, wb = h ? yb.y : yb.x;
-        const Chroma c0 = chroma_terms(__byte_perm(ub, 0u, 0x4404 + (2 * h << 4)), __byte_perm(vb, 0u, 0x4404 + (2 * h << 4)));
-        const Chroma c1 = chroma_terms(__byte_perm(ub, 0u, 0x4414 + (2 * h << 4)), __byte_perm(vb, 0u, 0x4414 + (2 * h << 4)));
+        const Chroma c0 = chroma_terms(__byte_perm(uv.x, 0u, 0x4404 + (2 * h << 4)), __byte_perm(uv.y, 0u, 0x4404 + (2 * h << 4)));
+        const Chroma c1 = chroma_terms(__byte_perm(uv.x, 0u, 0x4414 + (2 * h << 4)), __byte_perm(uv.y, 0u, 0x4414 + (2 * h << 4)));
         uint4 a, b;
         a.x = yuv_px(__byte_perm(wa, 0u, 0x4404), c0); a.y = yuv_px(__byte_perm(wa, 0u, 0x4414), c0);
         a.z = yuv_px(__byte_perm(wa, 0u, 0x4424), c1); a.w = yuv_px(__byte_perm(wa, 0u, 0x4434), c1);
@@ -260,136 +246,146 @@ __global__ void __launch_bounds__(FT_THREADS, 4) k_stitch_fused(const __grid_con
 {
     extern __shared__ __align__(128) uint8_t smem[];
     uint32_t* s_rgbx = reinterpret_cast<uint32_t*>(smem + FS_RGBX);
-    uint8_t* s_y = smem + FS_Y; uint8_t* s_u = smem + FS_U; uint8_t* s_v = smem + FS_V;
     float4* s_gain = reinterpret_cast<float4*>(smem + FS_GAIN);
-    const uint32_t ent_base = smem_u32(smem + FS_ENT), mbar_base = smem_u32(smem + FS_MBAR);
-    const uint32_t yst = smem_u32(smem + FS_YST), uvst = smem_u32(smem + FS_UVST);
+    const uint32_t ent_base = smem_u32(smem + FS_ENT), mbar = smem_u32(smem + FS_MBAR);
     const int tid = threadIdx.x, lx = tid & 31, ly = tid >> 5;
+    const uint8_t* slot0 = smem + FS_Y0 + tid * 8;            // the thread's two item slots
+    const uint8_t* slot1 = slot0 + FT_THREADS * 8;
+    const uint32_t slot0_a = smem_u32(slot0), slot1_a = slot0_a + FT_THREADS * 8;
 
-    const FBin bin = *reinterpret_cast<const FBin*>(p.bins + blockIdx.x);
-    int ti = bin.start;
-    const int tend = bin.end;
-    if (ti >= tend) return;
-
-    // ---- prologue: metadata of the first two tiles, gain constants, barriers ----
-    auto meta_slot = [&](int seq) { return smem + FS_META + (seq % 3) * FS_META_STRIDE; };
-    if (tid < 65) {
-        reinterpret_cast<uint4*>(meta_slot(ti))[tid] = __ldg(reinterpret_cast<const uint4*>(p.blocks + ti) + tid);
-        if (ti + 1 < tend) reinterpret_cast<uint4*>(meta_slot(ti + 1))[tid] = __ldg(reinterpret_cast<const uint4*>(p.blocks + ti + 1) + tid);
-    }
+    const FBin bin = p.bins[blockIdx.x];
+    const int js = bin.start, je = bin.end;
+    if (js >= je) return;
     if (GAIN && tid < p.n) {
         const float g32 = __ldcg(p.gain_f32 + tid);
         s_gain[tid] = make_float4(g32, gain_bias_f32(g32), __int_as_float(__ldcg(p.gain_flag + tid)), 0.f);
     }
     if (tid == 0) {
-        f_mbar_init(mbar_base, 1); f_mbar_init(mbar_base + 8, 1);
+        f_mbar_init(mbar, 1); f_mbar_init(mbar + 8, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncthreads();
 
-    // Record k of the CTA's job sequence lives in buffer k & 1: entries of job k, then the item list of job k + 1.
-    uint32_t phase0 = 0u, phase1 = 0u;
-    auto request = [&](int buf, uint32_t rec16, uint32_t bytes, int dst_off) {        // one thread: TMA bulk copy of a record
-        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-        f_mbar_expect_tx(mbar_base + 8 * buf, bytes);
-        bulk_g2s(ent_base + buf * FS_REC_STRIDE + dst_off, p.stream + rec16, bytes, mbar_base + 8 * buf);
+    const CamSrc* cams = p.cam;
+    const uint16_t* items = p.items + tid;                  // job j's descriptors at items[j * FUSED_MAXITEMS + slot * FT_THREADS + thread]
+    auto load_job = [&](int j) {
+        const uint4* q = reinterpret_cast<const uint4*>(p.jobs + j);
+        const uint4 a = __ldg(q), b = __ldg(q + 1);
+        JobRegs J;
+        J.cam = (int)a.x; J.bx0 = (int)a.y; J.by0 = (int)a.z; J.bw = (int)a.w; J.nitems = (int)b.x; J.tile_xy = b.z;
+        return J;
     };
-    auto wait_rec = [&](int buf) {
-        if (buf == 0) { f_mbar_wait(mbar_base, phase0); phase0 ^= 1u; } else { f_mbar_wait(mbar_base + 8, phase1); phase1 ^= 1u; }
+    auto is_fast = [&](const JobRegs& Q, uint32_t d, int item) {
+        return item < Q.nitems && (d >> 14) == FITEM_FAST && cams[Q.cam & 0xFF].aligned4;
     };
-    // input bytes of job N (item list in buffer `ibuf`) -> Y / chroma stages, by per-thread asynchronous copies
-    auto fetch_job = [&](const FJob& N, int ibuf) {
-        const CamSrc& c = p.cam[N.cam];
-        const uint16_t* items = reinterpret_cast<const uint16_t*>(smem + FS_ENT + ibuf * FS_REC_STRIDE + FT_PX * 8);
-        if (c.aligned4) {
-            if (tid < N.nitems) fetch_item(c, N, items[tid], yst, uvst);
-            if (tid + FT_THREADS < N.nitems) fetch_item(c, N, items[tid + FT_THREADS], yst, uvst);
-        }
+    // input bytes of the thread's items of job Q -> its slots (asynchronous; consumed after the next job boundary)
+    auto fetch_job = [&](const JobRegs& Q, uint32_t da, uint32_t db) {
+        const CamSrc& c = cams[Q.cam & 0xFF];
+        if (is_fast(Q, da, tid)) fetch_item(c, Q, da, slot0_a);
+        if (is_fast(Q, db, tid + FT_THREADS)) fetch_item(c, Q, db, slot1_a);
         cp_async_commit();
     };
-    {   // the first job's item list travels alone (buffer 1); then its record (buffer 0) is requested
-        const FTileBlock* B = reinterpret_cast<const FTileBlock*>(meta_slot(ti));
-        if (tid == 0) {
-            if (bin.head_bytes) request(1, bin.head16, bin.head_bytes, FT_PX * 8);
-            request(0, B->job[0].rec16, B->job[0].rec_bytes, 0);
-        }
-        if (bin.head_bytes) wait_rec(1);
-        fetch_job(B->job[0], 1);
-        cp_async_wait_all();
-        __syncthreads();
+    auto request_entries = [&](int j, int buf) {             // one thread: TMA bulk copy of a job's 8 KB of table entries
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        f_mbar_expect_tx(mbar + 8 * buf, FT_PX * 8);
+        bulk_g2s(ent_base + buf * (FT_PX * 8), p.entries + (size_t)j * FT_PX, FT_PX * 8, mbar + 8 * buf);
+    };
+
+    // ---- prologue: job js fully fetched, job js + 1's record and descriptors in registers ----
+    JobRegs J = load_job(js), N = J;
+    uint32_t d0 = __ldg(items + (size_t)js * FUSED_MAXITEMS), d1 = __ldg(items + (size_t)js * FUSED_MAXITEMS + FT_THREADS);
+    uint32_t e0 = 0u, e1 = 0u;
+    if (tid == 0) request_entries(js, 0);
+    fetch_job(J, d0, d1);
+    if (js + 1 < je) {
+        N = load_job(js + 1);
+        e0 = __ldg(items + (size_t)(js + 1) * FUSED_MAXITEMS); e1 = __ldg(items + (size_t)(js + 1) * FUSED_MAXITEMS + FT_THREADS);
     }
 
+    uint32_t arg[FT_PPT], ab[FT_PPT / 2];
+    #pragma unroll
+    for (int q = 0; q < FT_PPT; q++) arg[q] = 0u;
+    #pragma unroll
+    for (int q = 0; q < FT_PPT / 2; q++) ab[q] = 0u;
+    uint32_t phase = 0u, tiles_done = 0u;
     int buf = 0;
-    for (; ti < tend; ti++) {
-        const FTileBlock* B = reinterpret_cast<const FTileBlock*>(meta_slot(ti));
-        const FTile T = B->tile;
-        uint32_t arg[FT_PPT], ab[FT_PPT / 2];
-        #pragma unroll
-        for (int q = 0; q < FT_PPT; q++) arg[q] = 0u;
-        #pragma unroll
-        for (int q = 0; q < FT_PPT / 2; q++) ab[q] = 0u;
-        uint4 meta_next = make_uint4(0u, 0u, 0u, 0u);
-
-        #pragma unroll 1
-        for (int k = 0; k < T.nj; k++) {
-            const FJob J = B->job[k];
-            // ---- (1) convert this job's items (input bytes were copied into the stages during the previous job) ----
-            {
-                const CamSrc& c = p.cam[J.cam];
-                const uint16_t* items = reinterpret_cast<const uint16_t*>(smem + FS_ENT + (buf ^ 1) * FS_REC_STRIDE + FT_PX * 8);
-                if (tid < J.nitems) convert_item(c, J, items[tid], smem + FS_YST, smem + FS_UVST, s_rgbx);
-                if (tid + FT_THREADS < J.nitems) convert_item(c, J, items[tid + FT_THREADS], smem + FS_YST, smem + FS_UVST, s_rgbx);
-            }
-            __syncthreads();
-            // ---- (2) request the next record, wait for this one, start the input copies of the next job ----
-            const FJob* N = nullptr;
-            if (k + 1 < T.nj) N = &B->job[k + 1];
-            else if (ti + 1 < tend) N = &reinterpret_cast<const FTileBlock*>(meta_slot(ti + 1))->job[0];
-            if (N && tid == 0) request(buf ^ 1, N->rec16, N->rec_bytes, 0);
-            if (k == 0 && ti + 2 < tend && tid < 65) meta_next = __ldg(reinterpret_cast<const uint4*>(p.blocks + ti + 2) + tid);
-            wait_rec(buf);
-            if (N) fetch_job(*N, buf);
-            // ---- (3) gather ----
-            {
-                const uint4* ep = reinterpret_cast<const uint4*>(smem + FS_ENT + buf * FS_REC_STRIDE) + tid * 2;
-                const uint4 e0 = ep[0], e1 = ep[1];
-                const uint8_t* s0 = smem + FS_RGBX;
-                const uint8_t* s1 = s0 + J.bw * 4;
-                if (GAIN) {
-                    const float4 gc = s_gain[J.cam];
-                    if (__float_as_int(gc.z) == 0) gather_job<GAIN, false>(e0, e1, s0, s1, gc.x, gc.y, nullptr, arg, ab);
-                    else gather_job<GAIN, true>(e0, e1, s0, s1, gc.x, gc.y, p.gain_lut + J.cam * 256, arg, ab);
-                } else
-                    gather_job<0, false>(e0, e1, s0, s1, 0.f, 0.f, nullptr, arg, ab);
-            }
-            if (k == 0 && ti + 2 < tend && tid < 65) reinterpret_cast<uint4*>(meta_slot(ti + 2))[tid] = meta_next;
-            buf ^= 1;
-            cp_async_wait_all();
-            __syncthreads();                                // RGBX stage and record buffer are free, the next job's bytes have landed
-        }
-
-        // ---- tile epilogue: normalise, RGB -> YUV 4:2:0 into shared memory, then 128-bit row stores ----
-        const int tx0 = T.tx * FT_W, ty0 = T.ty * FT_H;
-        #pragma unroll
-        for (int q = 0; q < FT_PPT; q++) {
-            const int row = ly + 8 * q;
-            const int R = normalise_ch(arg[q] & 0xFFFFu, p.inv_n), G = normalise_ch(arg[q] >> 16, p.inv_n);
-            const int Bc = normalise_ch((q & 1) ? ab[q >> 1] >> 16 : ab[q >> 1] & 0xFFFFu, p.inv_n);
-            s_y[row * FT_W + lx] = (uint8_t)rgb_luma(R, G, Bc);
-            if (((lx | ly) & 1) == 0) {                      // top-left pixel of a 2x2 block carries the chroma (color.cpp:6456-6481)
-                s_u[(row >> 1) * (FT_W / 2) + (lx >> 1)] = (uint8_t)rgb_cb(R, G, Bc);
-                s_v[(row >> 1) * (FT_W / 2) + (lx >> 1)] = (uint8_t)rgb_cr(R, G, Bc);
-            }
-            if (p.rgb_out) {
-                const int x = tx0 + lx, y = ty0 + row;
-                if (x < p.out_w && y < p.out_h) {
-                    uint8_t* o = p.rgb_out + (size_t)y * p.rgb_pitch + 3 * x;
-                    o[0] = (uint8_t)R; o[1] = (uint8_t)G; o[2] = (uint8_t)Bc;
-                }
-            }
+    #pragma unroll 1
+    for (int j = js; j < je; j++) {
+        // ---- (1) convert this job's items: the thread's own bytes have landed once its copy group completes ----
+        cp_async_wait_all();
+        {
+            const CamSrc& c = cams[J.cam & 0xFF];
+            if (tid < J.nitems) convert_item(c, J, d0, is_fast(J, d0, tid), slot0, s_rgbx);
+            if (tid + FT_THREADS < J.nitems) convert_item(c, J, d1, is_fast(J, d1, tid + FT_THREADS), slot1, s_rgbx);
         }
         __syncthreads();
-        if (p.oy) {
+        // ---- (2) put the next jobs in flight: entries of j + 1, input bytes of j + 1, record and descriptors of j + 2 ----
+        const bool has_next = j + 1 < je;
+        if (has_next) {
+            if (tid == 0) request_entries(j + 1, buf ^ 1);
+            fetch_job(N, e0, e1);
+        }
+        JobRegs NN = N;
+        uint32_t g0 = 0u, g1 = 0u;
+        if (j + 2 < je) {
+            NN = load_job(j + 2);
+            g0 = __ldg(items + (size_t)(j + 2) * FUSED_MAXITEMS); g1 = __ldg(items + (size_t)(j + 2) * FUSED_MAXITEMS + FT_THREADS);
+        }
+        // ---- (3) gather ----
+        f_mbar_wait(mbar + 8 * buf, (phase >> buf) & 1u);
+        phase ^= 1u << buf;
+        {
+            const uint4* ep = reinterpret_cast<const uint4*>(smem + FS_ENT + buf * (FT_PX * 8)) + tid * 2;
+            const uint4 en0 = ep[0], en1 = ep[1];
+            const uint8_t* s0 = smem + FS_RGBX;
+            const uint8_t* s1 = s0 + J.bw * 4;
+            const int cam = J.cam & 0xFF;
+            if (GAIN) {
+                const float4 gc = s_gain[cam];
+                if (__float_as_int(gc.z) == 0) gather_job<GAIN, false>(en0, en1, s0, s1, gc.x, gc.y, nullptr, arg, ab);
+                else gather_job<GAIN, true>(en0, en1, s0, s1, gc.x, gc.y, p.gain_lut + cam * 256, arg, ab);
+            } else
+                gather_job<0, false>(en0, en1, s0, s1, 0.f, 0.f, nullptr, arg, ab);
+        }
+        buf ^= 1;
+        const bool last = J.cam < 0;
+        const uint32_t tile_xy = J.tile_xy;
+        J = N; d0 = e0; d1 = e1;
+        N = NN; e0 = g0; e1 = g1;
+        if (last) {
+            // ---- tile epilogue: normalise, RGB -> YUV 4:2:0 into shared memory, then 128-bit row stores ----
+            uint8_t* s_y = smem + FS_OUT + (tiles_done & 1u) * FS_OUT_STRIDE;
+            uint8_t* s_u = s_y + FT_PX; uint8_t* s_v = s_u + FT_PX / 4;
+            tiles_done++;
+            const int tx0 = (int)(tile_xy & 0xFFFFu) * FT_W, ty0 = (int)(tile_xy >> 16) * FT_H;
+            #pragma unroll
+            for (int q = 0; q < FT_PPT; q++) {
+                const int row = ly + 8 * q;
+                const int R = normalise_ch(arg[q] & 0xFFFFu, p.inv_n), G = normalise_ch(arg[q] >> 16, p.inv_n);
+                const int Bc = normalise_ch((q & 1) ? ab[q >> 1] >> 16 : ab[q >> 1] & 0xFFFFu, p.inv_n);
+                s_y[row * FT_W + lx] = (uint8_t)rgb_luma(R, G, Bc);
+                if (((lx | ly) & 1) == 0) {                  // top-left pixel of a 2x2 block carries the chroma (color.cpp:6456-6481)
+                    s_u[(row >> 1) * (FT_W / 2) + (lx >> 1)] = (uint8_t)rgb_cb(R, G, Bc);
+                    s_v[(row >> 1) * (FT_W / 2) + (lx >> 1)] = (uint8_t)rgb_cr(R, G, Bc);
+                }
+                if (p.rgb_out) {
+                    const int x = tx0 + lx, y = ty0 + row;
+                    if (x < p.out_w && y < p.out_h) {
+                        uint8_t* o = p.rgb_out + (size_t)y * p.rgb_pitch + 3 * x;
+                        o[0] = (uint8_t)R; o[1] = (uint8_t)G; o[2] = (uint8_t)Bc;
+                    }
+                }
+            }
+            #pragma unroll
+            for (int q = 0; q < FT_PPT; q++) arg[q] = 0u;
+            #pragma unroll
+            for (int q = 0; q < FT_PPT / 2; q++) ab[q] = 0u;
+        }
+        __syncthreads();                                    // the RGBX stage and the entry buffer are free; the tile bytes are in place
+        if (last && p.oy) {                                 // (the two output buffers alternate, so the stores need no further barrier)
+            const uint8_t* s_y = smem + FS_OUT + ((tiles_done - 1u) & 1u) * FS_OUT_STRIDE;
+            const uint8_t* s_u = s_y + FT_PX; const uint8_t* s_v = s_u + FT_PX / 4;
+            const int tx0 = (int)(tile_xy & 0xFFFFu) * FT_W, ty0 = (int)(tile_xy >> 16) * FT_H;
             if (tid < 64) {                                 // luma: 32 rows x 2 halves of 16 px
                 const int row = tid >> 1, hx = (tid & 1) << 4;
                 const int x = tx0 + hx, y = ty0 + row;
@@ -421,7 +417,6 @@ __global__ void __launch_bounds__(FT_THREADS, 4) k_stitch_fused(const __grid_con
                 }
             }
         }
-        // the next epilogue writes s_y/s_u/s_v only after at least two more CTA barriers (one job), so no barrier here
     }
 }
 
