@@ -206,22 +206,21 @@ __device__ void gain_solve_warp(int n, const double* Nm, const double* Im, doubl
         }
         return;
     }
-    for (int i = 0; i < n; i++) {
-        int k = i;
-        for (int j = i + 1; j < n; j++) if (fabs(S(j, i)) > fabs(S(k, i))) k = j;     // uniform: every lane reads the same
-        if (k != i && lane <= n) { const double t = S(i, lane); S(i, lane) = S(k, lane); S(k, lane) = t; }
-        __syncwarp();
-        const double d = -1 / S(i, i);
-        for (int j = i + 1; j < n; j++) {
-            const double al = MUL(S(j, i), d);
-            __syncwarp();
-            if (lane > i && lane <= n) S(j, lane) = ADD(S(j, lane), MUL(al, S(i, lane)));
-        }
-        __syncwarp();
-        if (lane == 0) S(i, i) = -d;
-        __syncwarp();
-    }
+    // LU with partial pivoting by ONE thread: every element sees the operations of matrix_decomp.cpp:52-109 in the same
+    // order (row updates are independent across columns), and the matrix is small enough that the dependent chain of
+    // f64 operations, not parallelism, sets the time -- no warp barriers or shared-memory round trips between steps
     if (lane == 0) {
+        for (int i = 0; i < n; i++) {
+            int k = i;
+            for (int j = i + 1; j < n; j++) if (fabs(S(j, i)) > fabs(S(k, i))) k = j;
+            if (k != i) for (int c = i; c <= n; c++) { const double t = S(i, c); S(i, c) = S(k, c); S(k, c) = t; }
+            const double d = -1 / S(i, i);
+            for (int j = i + 1; j < n; j++) {
+                const double al = MUL(S(j, i), d);
+                for (int c = i + 1; c <= n; c++) S(j, c) = ADD(S(j, c), MUL(al, S(i, c)));
+            }
+            S(i, i) = -d;
+        }
         for (int i = n - 1; i >= 0; i--) {
             double sacc = Bv(i);
             for (int k = i + 1; k < n; k++) sacc = SUB(sacc, MUL(S(i, k), Bv(k)));

@@ -108,18 +108,20 @@ void launch_blend_staged(const StagedParams& p, cudaStream_t s);
 constexpr int FT_W = 32, FT_H = 32, FT_PX = FT_W * FT_H, FT_PPT = 4;
 constexpr int FT_THREADS = FT_PX / FT_PPT;
 constexpr int FUSED_CAP = 6144;          // RGBX stage capacity in pixels (24 KB); a job whose box is larger is split by rows
-constexpr int FUSED_MAXITEMS = 2 * FT_THREADS;   // conversion items (8 px x 2 rows of the source box) per job
-// conversion item descriptor (u16): row pair (7 bits) | 8-px group << 7 (7 bits) | class << 14
+constexpr int FUSED_MAXITEMS = 2 * FT_THREADS;   // conversion items (4 px x 2 rows of the source box) per job
+// conversion item descriptor (u16): row pair (7 bits) | 4-px group << 7 (7 bits) | class << 14
 enum { FITEM_ZERO = 0, FITEM_FAST = 1, FITEM_SLOW = 2 };     // outside the source (-> 0), inside, straddles the border
 constexpr int FJOB_LAST = (int)0x80000000u;                  // cam field: last job of its output tile
+constexpr int FJOB_SYNC = 0x40000000;                        // cam field: this job's box overlaps the previous job's box in the stage:
+                                                             //   a CTA barrier must separate the previous gather from this conversion
 struct FJob {                            // 32 B, one per (tile, camera[, row range]), in the order the CTA consumes them
     int cam;                             // | FJOB_LAST
     int bx0, by0;                        // top-left of the source box (bx0 % 8 == 0, by0 % 2 == 0, may be negative)
     int bw;                              // box width in px (bw % 8 == 0); box area <= FUSED_CAP
-    int nitems;                          // conversion items: only the 8x2 blocks some bilinear tap touches
+    int nitems;                          // conversion items: only the 4x2 blocks some bilinear tap touches
     uint32_t items_off;                  // (unused) descriptors of job j are at FusedParams::items[j * FUSED_MAXITEMS ...]; item i -> thread i % FT_THREADS
     uint32_t tile_xy;                    // output tile: x | y << 16 (tile units)
-    int pad;
+    int stage_off;                       // where the box lives in the RGBX stage (px, multiple of 8); consecutive jobs alternate
 };
 static_assert(sizeof(FJob) == 32, "FJob is read as two uint4");
 struct FBin { int start, end; };         // a CTA's jobs [start, end)

@@ -96,7 +96,7 @@ static bool build_fused(octvr_mapper& m, const octvr_template& t, const std::vec
 {
     const int n = m.n;
     const int tiles_x = (t.out_w + FT_W - 1) / FT_W, tiles_y = (t.out_h + FT_H - 1) / FT_H, ntiles = tiles_x * tiles_y;
-    struct Job { int cam, r0, r1; FJob rec; std::vector<uint16_t> items; };
+    struct Job { int cam, r0, r1, bh; FJob rec; std::vector<uint16_t> items; };
     std::vector<std::vector<Job>> tile_jobs(ntiles);
     // pixel of a tile -> (valid, tap position, weight) for camera i
     auto sample = [&](int tl, int px, int py, int i, int& ix, int& iy, int32_t& fsx, int32_t& fsy, float& w) {
@@ -127,7 +127,7 @@ static bool build_fused(octvr_mapper& m, const octvr_template& t, const std::vec
         r.cam = i;
         r.bx0 = floor_div(xmin, 8) * 8; r.by0 = floor_div(ymin, 2) * 2;
         r.bw = (xmax - r.bx0 + 8) / 8 * 8;
-        const int bh = (ymax - r.by0 + 2) / 2 * 2, groups = r.bw / 8, rps = bh / 2;
+        const int bh = (ymax - r.by0 + 2) / 2 * 2, groups = r.bw / 4, rps = bh / 2;
         if ((int64_t)r.bw * bh > FUSED_CAP || groups > 128 || rps > 128) return -1;
         std::vector<uint8_t> touched((size_t)groups * rps, 0);
         for (int py = r0; py < r1; py++)
@@ -135,21 +135,21 @@ static bool build_fused(octvr_mapper& m, const octvr_template& t, const std::vec
                 int ix, iy; int32_t fsx, fsy; float w;
                 if (!sample(tl, px, py, i, ix, iy, fsx, fsy, w)) continue;
                 for (int dy = 0; dy < 2; dy++)
-                    for (int dx = 0; dx < 2; dx++) touched[(size_t)((iy + dy - r.by0) >> 1) * groups + ((ix + dx - r.bx0) >> 3)] = 1;
+                    for (int dx = 0; dx < 2; dx++) touched[(size_t)((iy + dy - r.by0) >> 1) * groups + ((ix + dx - r.bx0) >> 2)] = 1;
             }
         jb.items.clear();
         for (int rp = 0; rp < rps; rp++)
             for (int g = 0; g < groups; g++) {
                 if (!touched[(size_t)rp * groups + g]) continue;
-                const int x0 = r.bx0 + 8 * g, y0 = r.by0 + 2 * rp;
+                const int x0 = r.bx0 + 4 * g, y0 = r.by0 + 2 * rp;
                 int cls = FITEM_SLOW;
-                if (x0 + 8 <= 0 || x0 >= m.in_w[i] || y0 + 2 <= 0 || y0 >= m.in_h[i]) cls = FITEM_ZERO;
-                else if (x0 >= 0 && x0 + 8 <= m.in_w[i] && y0 >= 0 && y0 + 2 <= m.in_h[i]) cls = FITEM_FAST;
+                if (x0 + 4 <= 0 || x0 >= m.in_w[i] || y0 + 2 <= 0 || y0 >= m.in_h[i]) cls = FITEM_ZERO;
+                else if (x0 >= 0 && x0 + 4 <= m.in_w[i] && y0 >= 0 && y0 + 2 <= m.in_h[i]) cls = FITEM_FAST;
                 jb.items.push_back((uint16_t)(rp | (g << 7) | (cls << 14)));
             }
         if ((int)jb.items.size() > FUSED_MAXITEMS) return -1;
         r.nitems = (int)jb.items.size();
-        jb.cam = i; jb.r0 = r0; jb.r1 = r1;
+        jb.cam = i; jb.r0 = r0; jb.r1 = r1; jb.bh = bh;
         return 1;
     };
     bool ok = true;
@@ -166,7 +166,7 @@ static bool build_fused(octvr_mapper& m, const octvr_template& t, const std::vec
         for (int i = 0; i < n; i++) add_jobs(tl, i, 0, FT_H);
         if (tile_jobs[tl].empty()) {                       // nobody covers this tile: one job with no items and zero weights
             Job jb; memset(&jb.rec, 0, sizeof(jb.rec));
-            jb.cam = -1; jb.r0 = jb.r1 = 0; jb.rec.bw = 8;
+            jb.cam = -1; jb.r0 = jb.r1 = 0; jb.bh = 2; jb.rec.bw = 8;
             tile_jobs[tl].push_back(jb);
         }
     }
@@ -180,9 +180,9 @@ static bool build_fused(octvr_mapper& m, const octvr_template& t, const std::vec
     const int grid = std::max(1, std::min(ntiles, sms * per_sm));
     std::vector<int64_t> cost(ntiles);
     for (int tl = 0; tl < ntiles; tl++) {
-        // per-thread instruction estimates: ~190 for a job's four pixels, ~280 per conversion round, ~110 for the epilogue
+        // per-thread instruction estimates: ~190 for a job's four pixels, ~150 per conversion round, ~110 for the epilogue
         int64_t c = 110;
-        for (const Job& jb : tile_jobs[tl]) c += 190 + 280 * (int64_t)((jb.items.size() + FT_THREADS - 1) / FT_THREADS) + 60;
+        for (const Job& jb : tile_jobs[tl]) c += 190 + 150 * (int64_t)((jb.items.size() + FT_THREADS - 1) / FT_THREADS) + 60;
         cost[tl] = c;
     }
     std::vector<int> order(ntiles);
@@ -211,11 +211,19 @@ static bool build_fused(octvr_mapper& m, const octvr_template& t, const std::vec
     jobs.reserve(njobs);
     for (int b = 0; b < grid; b++) {
         bins[b].start = (int)jobs.size();
+        int prev_off = 0, prev_area = 0;                    // stage region of the CTA's previous job
         for (int tl : bin_tiles[b])
             for (size_t k = 0; k < tile_jobs[tl].size(); k++) {
                 const Job& jb = tile_jobs[tl][k];
                 FJob r = jb.rec;
                 r.cam = std::max(jb.cam, 0) | (k + 1 == tile_jobs[tl].size() ? FJOB_LAST : 0);
+                // place the box where the previous job's box is not (its gather may still be running when this job is
+                // converted); if both do not fit side by side the kernel separates them with a barrier
+                const int area = (jb.bh * r.bw + 7) / 8 * 8;
+                if (prev_off + prev_area + area <= FUSED_CAP) r.stage_off = prev_off + prev_area;
+                else if (area <= prev_off) r.stage_off = 0;
+                else { r.stage_off = 0; if ((int)jobs.size() > bins[b].start) r.cam |= FJOB_SYNC; }
+                prev_off = r.stage_off; prev_area = area;
                 r.tile_xy = (uint32_t)(tl % tiles_x) | ((uint32_t)(tl / tiles_x) << 16);
                 // descriptors at a fixed stride per job, so their address does not depend on the job record
                 r.items_off = (uint32_t)items.size();
@@ -229,7 +237,7 @@ static bool build_fused(octvr_mapper& m, const octvr_template& t, const std::vec
                             if (py < jb.r0 || py >= jb.r1) continue;
                             int ix, iy; int32_t fsx, fsy; float w;
                             if (!sample(tl, px, py, jb.cam, ix, iy, fsx, fsy, w)) continue;
-                            const uint32_t off = (uint32_t)(((iy - r.by0) * r.bw + (ix - r.bx0)) * 4);
+                            const uint32_t off = (uint32_t)((r.stage_off + (iy - r.by0) * r.bw + (ix - r.bx0)) * 4);
                             uint32_t wbits; memcpy(&wbits, &w, 4);
                             ent[tid * FT_PPT + q] = make_uint2(off | ((uint32_t)(fsy & 31) << 16) | ((uint32_t)(fsx & 31) << 24), wbits);
                         }
@@ -291,10 +299,11 @@ static void build_mapper(octvr_mapper& m, const octvr_template& t, const int* in
     if (blend <= 0) {
         W = blend < 0 ? feather_weights(t.inputs, -blend) : overwrite_weights(t.inputs);
         m.inv_n = blend < 0 ? (float)(1.0 / n) : 1.f;
-        // fused single-kernel path (default); OCTVR_BLEND=staged|direct selects the two-kernel paths, which are also
-        // the fallback when a job does not fit the fused kernel's shared-memory stage
+        // OCTVR_BLEND=fused selects the single-kernel path (K_stitch_fused: no RGBX image in HBM, half the DRAM traffic, but
+        // measured slower per frame than convert + staged blend because the conversion no longer hides the latency of the
+        // gain launch -- DESIGN.md section 4); default: K_convert(+gain) then K_blend_staged, or K_blend (OCTVR_BLEND=direct)
         const char* mode = getenv("OCTVR_BLEND");
-        if (!mode || std::string(mode) == "fused") build_fused(m, t, sx, sy, W);
+        if (mode && std::string(mode) == "fused") build_fused(m, t, sx, sy, W);
     }
     // RGBX planes written by K_convert: only the two-kernel and multiband paths need them
     if (!m.fused)

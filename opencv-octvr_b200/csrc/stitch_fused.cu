@@ -18,16 +18,16 @@ namespace ob {
 
 // ---- shared-memory map of a CTA (dynamic) ----
 constexpr int FS_RGBX = 0;                                   // FUSED_CAP u32: the converted source box of the current job
-constexpr int FS_Y0 = FS_RGBX + FUSED_CAP * 4;               // thread-private slots for the input bytes of the NEXT job's items
-constexpr int FS_Y1 = FS_Y0 + 2 * FT_THREADS * 8;            //   (cp.async destinations; slot s of thread t at [s][t]):
-constexpr int FS_UV = FS_Y1 + 2 * FT_THREADS * 8;            //   luma rows 0 / 1 (8 B each), chroma (U 4 B | V 4 B, or NV12 UVUVUVUV)
-constexpr int FS_ENT = FS_UV + 2 * FT_THREADS * 8;           // 2 x FT_PX x 8 B table entries (TMA bulk destinations)
+constexpr int FS_SLOT = FS_RGBX + FUSED_CAP * 4;             // thread-private 16-byte slots for the input bytes of the NEXT job's items
+                                                             //   (cp.async destinations; slot s of thread t at [s][t]): luma row 0,
+                                                             //   luma row 1 (4 px each), U chunk, V chunk (or NV12 UVUV, unused)
+constexpr int FS_ENT = FS_SLOT + 2 * FT_THREADS * 16;        // 2 x FT_PX x 8 B table entries (TMA bulk destinations)
 constexpr int FS_OUT = FS_ENT + 2 * FT_PX * 8;               // 2 x {32 x 32 luma, 16 x 16 U, 16 x 16 V} of finished tiles
 constexpr int FS_OUT_STRIDE = FT_PX + FT_PX / 2;
 constexpr int FS_GAIN = FS_OUT + 2 * FS_OUT_STRIDE;          // MAX_CAMS x {g32, bias, flag, pad}
 constexpr int FS_MBAR = FS_GAIN + MAX_CAMS * 16;             // ent[2]
 constexpr int FS_TOTAL = FS_MBAR + 16;
-static_assert(FS_Y0 % 16 == 0 && FS_ENT % 128 == 0 && FS_OUT % 16 == 0 && FS_OUT_STRIDE % 16 == 0 && FS_MBAR % 8 == 0, "alignment");
+static_assert(FS_SLOT % 16 == 0 && FS_ENT % 128 == 0 && FS_OUT % 16 == 0 && FS_OUT_STRIDE % 16 == 0 && FS_MBAR % 8 == 0, "alignment");
 static_assert(4 * (FS_TOTAL + 1024) <= 228 * 1024, "four CTAs per SM");
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -70,20 +70,22 @@ __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wai
 
 // ---- conversion items: 8 px x 2 rows of the job's source box (four chroma samples), listed by the host ----
 // what a thread keeps of a job record
-struct JobRegs { int cam, bx0, by0, bw, nitems; uint32_t tile_xy; };
-// issue the asynchronous copies of one item's input bytes (class FAST on 8/4-byte aligned planes) into the thread's slot
-__device__ __forceinline__ void fetch_item(const CamSrc& c, const JobRegs& J, uint32_t desc, uint32_t slot_y0)
+struct JobRegs { int cam, bx0, by0, bw, nitems, stage_off; uint32_t tile_xy; };
+// issue the asynchronous copies of one item's input bytes (class FAST on 4-byte aligned planes) into the thread's slot.
+// Planar chroma is copied as the aligned 4-sample chunk that holds the item's two samples.
+__device__ __forceinline__ void fetch_item(const CamSrc& c, const JobRegs& J, uint32_t desc, uint32_t slot)
 {
     const int rp = desc & 127u, gx = (desc >> 7) & 127u;
-    const int x0 = J.bx0 + (gx << 3), y0 = J.by0 + (rp << 1);
+    const int x0 = J.bx0 + (gx << 2), y0 = J.by0 + (rp << 1);
     const uint8_t* yp = c.y + (size_t)y0 * c.y_pitch + x0;
-    cp_async8(slot_y0, yp);
-    cp_async8(slot_y0 + (FS_Y1 - FS_Y0), yp + c.y_pitch);
+    cp_async4(slot, yp);
+    cp_async4(slot + 4, yp + c.y_pitch);
     if (c.uv_step == 1) {
-        cp_async4(slot_y0 + (FS_UV - FS_Y0), c.u + (size_t)(y0 >> 1) * c.u_pitch + (x0 >> 1));
-        cp_async4(slot_y0 + (FS_UV - FS_Y0) + 4, c.v + (size_t)(y0 >> 1) * c.v_pitch + (x0 >> 1));
-    } else                                                   // NV12: U0 V0 U1 V1 U2 V2 U3 V3
-        cp_async8(slot_y0 + (FS_UV - FS_Y0), c.u + (size_t)(y0 >> 1) * c.u_pitch + x0);
+        const size_t co = (size_t)((x0 >> 1) & ~3);
+        cp_async4(slot + 8, c.u + (size_t)(y0 >> 1) * c.u_pitch + co);
+        cp_async4(slot + 12, c.v + (size_t)(y0 >> 1) * c.v_pitch + co);
+    } else                                                   // NV12: U0 V0 U1 V1
+        cp_async4(slot + 8, c.u + (size_t)(y0 >> 1) * c.u_pitch + x0);
 }
 
 // BT.601 limited-range integer conversion (imgproc/src/color.cpp:6087-6169):
@@ -123,7 +125,7 @@ __device__ __forceinline__ uint32_t vignette_px(uint32_t p, float k)
 // border / unaligned item: byte loads from global memory, one pixel at a time (rare)
 __device__ __noinline__ void convert_item_slow(const CamSrc& c, int x0, int y0, uint32_t* d0, uint32_t* d1)
 {
-    for (int k = 0; k < 8; k++) {
+    for (int k = 0; k < 4; k++) {
         const int x = x0 + k;
         uint32_t a = 0u, b = 0u;
         if (x >= 0 && x < c.w && y0 >= 0 && y0 < c.h) {
@@ -140,45 +142,40 @@ __device__ __noinline__ void convert_item_slow(const CamSrc& c, int x0, int y0, 
     }
 }
 
-// convert one item (input bytes in the thread's slot) and store its 2 x 8 RGBX pixels into the RGBX stage
-__device__ __forceinline__ void convert_item(const CamSrc& c, const JobRegs& J, uint32_t desc, bool fast, const uint8_t* slot_y0, uint32_t* s_rgbx)
+// convert one item (input bytes in the thread's slot) and store its 2 x 4 RGBX pixels into the RGBX stage
+__device__ __forceinline__ void convert_item(const CamSrc& c, const JobRegs& J, uint32_t desc, bool fast, const uint8_t* slot, uint32_t* s_rgbx)
 {
     const int rp = desc & 127u, gx = (desc >> 7) & 127u;
-    const int o0 = (rp << 1) * J.bw + (gx << 3);
+    const int o0 = J.stage_off + (rp << 1) * J.bw + (gx << 2);
     uint4* d0 = reinterpret_cast<uint4*>(s_rgbx + o0);
     uint4* d1 = reinterpret_cast<uint4*>(s_rgbx + o0 + J.bw);
     if (!fast) {
         if ((desc >> 14) == FITEM_ZERO) {                    // BORDER_CONSTANT
             const uint4 z = make_uint4(0u, 0u, 0u, 0u);
-            d0[0] = z; d0[1] = z; d1[0] = z; d1[1] = z;
+            *d0 = z; *d1 = z;
         } else
-            convert_item_slow(c, J.bx0 + (gx << 3), J.by0 + (rp << 1), reinterpret_cast<uint32_t*>(d0), reinterpret_cast<uint32_t*>(d1));
+            convert_item_slow(c, J.bx0 + (gx << 2), J.by0 + (rp << 1), reinterpret_cast<uint32_t*>(d0), reinterpret_cast<uint32_t*>(d1));
         return;
     }
-    const uint2 ya = *reinterpret_cast<const uint2*>(slot_y0);
-    const uint2 yb = *reinterpret_cast<const uint2*>(slot_y0 + (FS_Y1 - FS_Y0));
-    uint2 uv = *reinterpret_cast<const uint2*>(slot_y0 + (FS_UV - FS_Y0));
-    if (c.uv_step != 1) uv = make_uint2(__byte_perm(uv.x, uv.y, 0x6420), __byte_perm(uv.x, uv.y, 0x7531));
-    const bool vig = c.vignette != nullptr;
-    const float* vg = vig ? c.vignette + (size_t)(J.by0 + (rp << 1)) * c.w + J.bx0 + (gx << 3) : nullptr;
-    #pragma unroll
-    for (int h = 0; h < 2; h++) {                            // four pixels of both rows at a time
-        const uint32_t wa = h ? ya.y : ya.x, wb = h ? yb.y : yb.x;
-        const Chroma c0 = chroma_terms(__byte_perm(uv.x, 0u, 0x4404 + (2 * h << 4)), __byte_perm(uv.y, 0u, 0x4404 + (2 * h << 4)));
-        const Chroma c1 = chroma_terms(__byte_perm(uv.x, 0u, 0x4414 + (2 * h << 4)), __byte_perm(uv.y, 0u, 0x4414 + (2 * h << 4)));
-        uint4 a, b;
-        a.x = yuv_px(__byte_perm(wa, 0u, 0x4404), c0); a.y = yuv_px(__byte_perm(wa, 0u, 0x4414), c0);
-        a.z = yuv_px(__byte_perm(wa, 0u, 0x4424), c1); a.w = yuv_px(__byte_perm(wa, 0u, 0x4434), c1);
-        b.x = yuv_px(__byte_perm(wb, 0u, 0x4404), c0); b.y = yuv_px(__byte_perm(wb, 0u, 0x4414), c0);
-        b.z = yuv_px(__byte_perm(wb, 0u, 0x4424), c1); b.w = yuv_px(__byte_perm(wb, 0u, 0x4434), c1);
-        if (vig) {
-            a.x = vignette_px(a.x, __ldg(vg + 4 * h)); a.y = vignette_px(a.y, __ldg(vg + 4 * h + 1));
-            a.z = vignette_px(a.z, __ldg(vg + 4 * h + 2)); a.w = vignette_px(a.w, __ldg(vg + 4 * h + 3));
-            b.x = vignette_px(b.x, __ldg(vg + c.w + 4 * h)); b.y = vignette_px(b.y, __ldg(vg + c.w + 4 * h + 1));
-            b.z = vignette_px(b.z, __ldg(vg + c.w + 4 * h + 2)); b.w = vignette_px(b.w, __ldg(vg + c.w + 4 * h + 3));
-        }
-        d0[h] = a; d1[h] = b;
+    const uint4 in = *reinterpret_cast<const uint4*>(slot);  // luma row 0, luma row 1, chroma
+    uint32_t ub, vb;                                         // the item's two U and two V samples in bytes 0, 1
+    if (c.uv_step == 1) { const int sh = (gx & 1) << 4; ub = in.z >> sh; vb = in.w >> sh; }
+    else { ub = __byte_perm(in.z, 0u, 0x4420); vb = __byte_perm(in.z, 0u, 0x4431); }
+    const Chroma c0 = chroma_terms(__byte_perm(ub, 0u, 0x4404), __byte_perm(vb, 0u, 0x4404));
+    const Chroma c1 = chroma_terms(__byte_perm(ub, 0u, 0x4414), __byte_perm(vb, 0u, 0x4414));
+    uint4 a, b;
+    a.x = yuv_px(__byte_perm(in.x, 0u, 0x4404), c0); a.y = yuv_px(__byte_perm(in.x, 0u, 0x4414), c0);
+    a.z = yuv_px(__byte_perm(in.x, 0u, 0x4424), c1); a.w = yuv_px(__byte_perm(in.x, 0u, 0x4434), c1);
+    b.x = yuv_px(__byte_perm(in.y, 0u, 0x4404), c0); b.y = yuv_px(__byte_perm(in.y, 0u, 0x4414), c0);
+    b.z = yuv_px(__byte_perm(in.y, 0u, 0x4424), c1); b.w = yuv_px(__byte_perm(in.y, 0u, 0x4434), c1);
+    if (c.vignette) {
+        const float* vg = c.vignette + (size_t)(J.by0 + (rp << 1)) * c.w + J.bx0 + (gx << 2);
+        a.x = vignette_px(a.x, __ldg(vg)); a.y = vignette_px(a.y, __ldg(vg + 1));
+        a.z = vignette_px(a.z, __ldg(vg + 2)); a.w = vignette_px(a.w, __ldg(vg + 3));
+        b.x = vignette_px(b.x, __ldg(vg + c.w)); b.y = vignette_px(b.y, __ldg(vg + c.w + 1));
+        b.z = vignette_px(b.z, __ldg(vg + c.w + 2)); b.w = vignette_px(b.w, __ldg(vg + c.w + 3));
     }
+    *d0 = a; *d1 = b;
 }
 
 // one table entry: four taps from the stage, 1/32-px bilinear, gain, weight, accumulate.
@@ -249,9 +246,9 @@ __global__ void __launch_bounds__(FT_THREADS, 4) k_stitch_fused(const __grid_con
     float4* s_gain = reinterpret_cast<float4*>(smem + FS_GAIN);
     const uint32_t ent_base = smem_u32(smem + FS_ENT), mbar = smem_u32(smem + FS_MBAR);
     const int tid = threadIdx.x, lx = tid & 31, ly = tid >> 5;
-    const uint8_t* slot0 = smem + FS_Y0 + tid * 8;            // the thread's two item slots
-    const uint8_t* slot1 = slot0 + FT_THREADS * 8;
-    const uint32_t slot0_a = smem_u32(slot0), slot1_a = slot0_a + FT_THREADS * 8;
+    const uint8_t* slot0 = smem + FS_SLOT + tid * 16;         // the thread's two item slots
+    const uint8_t* slot1 = slot0 + FT_THREADS * 16;
+    const uint32_t slot0_a = smem_u32(slot0), slot1_a = slot0_a + FT_THREADS * 16;
 
     const FBin bin = p.bins[blockIdx.x];
     const int js = bin.start, je = bin.end;
@@ -272,7 +269,7 @@ __global__ void __launch_bounds__(FT_THREADS, 4) k_stitch_fused(const __grid_con
         const uint4* q = reinterpret_cast<const uint4*>(p.jobs + j);
         const uint4 a = __ldg(q), b = __ldg(q + 1);
         JobRegs J;
-        J.cam = (int)a.x; J.bx0 = (int)a.y; J.by0 = (int)a.z; J.bw = (int)a.w; J.nitems = (int)b.x; J.tile_xy = b.z;
+        J.cam = (int)a.x; J.bx0 = (int)a.y; J.by0 = (int)a.z; J.bw = (int)a.w; J.nitems = (int)b.x; J.tile_xy = b.z; J.stage_off = (int)b.w;
         return J;
     };
     auto is_fast = [&](const JobRegs& Q, uint32_t d, int item) {
@@ -307,8 +304,44 @@ __global__ void __launch_bounds__(FT_THREADS, 4) k_stitch_fused(const __grid_con
     for (int q = 0; q < FT_PPT; q++) arg[q] = 0u;
     #pragma unroll
     for (int q = 0; q < FT_PPT / 2; q++) ab[q] = 0u;
-    uint32_t phase = 0u, tiles_done = 0u;
+    uint32_t phase = 0u, tiles_done = 0u, pending_xy = 0xFFFFFFFFu;
     int buf = 0;
+    // 128-bit row stores of a finished tile from its shared-memory buffer (threads 0..95)
+    auto store_tile = [&](uint32_t tile_xy, uint32_t which) {
+        const uint8_t* s_y = smem + FS_OUT + (which & 1u) * FS_OUT_STRIDE;
+        const uint8_t* s_u = s_y + FT_PX; const uint8_t* s_v = s_u + FT_PX / 4;
+        const int tx0 = (int)(tile_xy & 0xFFFFu) * FT_W, ty0 = (int)(tile_xy >> 16) * FT_H;
+        if (tid < 64) {                                     // luma: 32 rows x 2 halves of 16 px
+            const int row = tid >> 1, hx = (tid & 1) << 4;
+            const int x = tx0 + hx, y = ty0 + row;
+            if (y < p.out_h && x < p.out_w) {
+                const uint4 v = *reinterpret_cast<const uint4*>(s_y + row * FT_W + hx);
+                uint8_t* o = p.oy + (size_t)y * p.oy_pitch + x;
+                if (x + 16 <= p.out_w && (((uintptr_t)o) & 15) == 0) *reinterpret_cast<uint4*>(o) = v;
+                else { const uint8_t* sv = s_y + row * FT_W + hx; for (int k = 0; k < 16 && x + k < p.out_w; k++) o[k] = sv[k]; }
+            }
+        } else if (tid < 96) {                              // chroma: 16 rows x 16 samples per plane
+            const int t = tid - 64;
+            if (p.uv_step == 1) {
+                const int row = t & 15;
+                const uint8_t* sv = (t < 16 ? s_u : s_v) + row * (FT_W / 2);
+                const int x = tx0 >> 1, y = (ty0 >> 1) + row;
+                if (y < (p.out_h >> 1) && x < (p.out_w >> 1)) {
+                    uint8_t* o = (t < 16 ? p.ou + (size_t)y * p.ou_pitch : p.ov + (size_t)y * p.ov_pitch) + x;
+                    if (x + 16 <= (p.out_w >> 1) && (((uintptr_t)o) & 15) == 0) *reinterpret_cast<uint4*>(o) = *reinterpret_cast<const uint4*>(sv);
+                    else for (int k = 0; k < 16 && x + k < (p.out_w >> 1); k++) o[k] = sv[k];
+                }
+            } else {                                        // interleaved (NV12-style) chroma: 8 samples of each plane per thread
+                const int row = t >> 1, hx = (t & 1) << 3;
+                const int x = (tx0 >> 1) + hx, y = (ty0 >> 1) + row;
+                if (y < (p.out_h >> 1))
+                    for (int k = 0; k < 8 && x + k < (p.out_w >> 1); k++) {
+                        p.ou[(size_t)y * p.ou_pitch + (size_t)(x + k) * p.uv_step] = s_u[row * (FT_W / 2) + hx + k];
+                        p.ov[(size_t)y * p.ov_pitch + (size_t)(x + k) * p.uv_step] = s_v[row * (FT_W / 2) + hx + k];
+                    }
+            }
+        }
+    };
     #pragma unroll 1
     for (int j = js; j < je; j++) {
         // ---- (1) convert this job's items: the thread's own bytes have landed once its copy group completes ----
@@ -318,10 +351,13 @@ __global__ void __launch_bounds__(FT_THREADS, 4) k_stitch_fused(const __grid_con
             if (tid < J.nitems) convert_item(c, J, d0, is_fast(J, d0, tid), slot0, s_rgbx);
             if (tid + FT_THREADS < J.nitems) convert_item(c, J, d1, is_fast(J, d1, tid + FT_THREADS), slot1, s_rgbx);
         }
-        __syncthreads();
+        __syncthreads();       // the ONE barrier of a job: conversion done; every thread has also left the previous gather / epilogue
+        if (pending_xy != 0xFFFFFFFFu) {                    // the tile finished by the previous job: its bytes are in place now
+            if (p.oy) store_tile(pending_xy, tiles_done - 1u);
+            pending_xy = 0xFFFFFFFFu;
+        }
         // ---- (2) put the next jobs in flight: entries of j + 1, input bytes of j + 1, record and descriptors of j + 2 ----
-        const bool has_next = j + 1 < je;
-        if (has_next) {
+        if (j + 1 < je) {
             if (tid == 0) request_entries(j + 1, buf ^ 1);
             fetch_job(N, e0, e1);
         }
@@ -348,16 +384,13 @@ __global__ void __launch_bounds__(FT_THREADS, 4) k_stitch_fused(const __grid_con
                 gather_job<0, false>(en0, en1, s0, s1, 0.f, 0.f, nullptr, arg, ab);
         }
         buf ^= 1;
-        const bool last = J.cam < 0;
-        const uint32_t tile_xy = J.tile_xy;
-        J = N; d0 = e0; d1 = e1;
-        N = NN; e0 = g0; e1 = g1;
-        if (last) {
-            // ---- tile epilogue: normalise, RGB -> YUV 4:2:0 into shared memory, then 128-bit row stores ----
+        if (J.cam < 0) {
+            // ---- tile epilogue: normalise, RGB -> YUV 4:2:0 into the tile's shared-memory buffer (stored after the next barrier) ----
             uint8_t* s_y = smem + FS_OUT + (tiles_done & 1u) * FS_OUT_STRIDE;
             uint8_t* s_u = s_y + FT_PX; uint8_t* s_v = s_u + FT_PX / 4;
             tiles_done++;
-            const int tx0 = (int)(tile_xy & 0xFFFFu) * FT_W, ty0 = (int)(tile_xy >> 16) * FT_H;
+            pending_xy = J.tile_xy;
+            const int tx0 = (int)(J.tile_xy & 0xFFFFu) * FT_W, ty0 = (int)(J.tile_xy >> 16) * FT_H;
             #pragma unroll
             for (int q = 0; q < FT_PPT; q++) {
                 const int row = ly + 8 * q;
@@ -381,43 +414,14 @@ __global__ void __launch_bounds__(FT_THREADS, 4) k_stitch_fused(const __grid_con
             #pragma unroll
             for (int q = 0; q < FT_PPT / 2; q++) ab[q] = 0u;
         }
-        __syncthreads();                                    // the RGBX stage and the entry buffer are free; the tile bytes are in place
-        if (last && p.oy) {                                 // (the two output buffers alternate, so the stores need no further barrier)
-            const uint8_t* s_y = smem + FS_OUT + ((tiles_done - 1u) & 1u) * FS_OUT_STRIDE;
-            const uint8_t* s_u = s_y + FT_PX; const uint8_t* s_v = s_u + FT_PX / 4;
-            const int tx0 = (int)(tile_xy & 0xFFFFu) * FT_W, ty0 = (int)(tile_xy >> 16) * FT_H;
-            if (tid < 64) {                                 // luma: 32 rows x 2 halves of 16 px
-                const int row = tid >> 1, hx = (tid & 1) << 4;
-                const int x = tx0 + hx, y = ty0 + row;
-                if (y < p.out_h && x < p.out_w) {
-                    const uint4 v = *reinterpret_cast<const uint4*>(s_y + row * FT_W + hx);
-                    uint8_t* o = p.oy + (size_t)y * p.oy_pitch + x;
-                    if (x + 16 <= p.out_w && (((uintptr_t)o) & 15) == 0) *reinterpret_cast<uint4*>(o) = v;
-                    else { const uint8_t* sv = s_y + row * FT_W + hx; for (int k = 0; k < 16 && x + k < p.out_w; k++) o[k] = sv[k]; }
-                }
-            } else if (tid < 96) {                          // chroma: 16 rows x 16 samples per plane
-                const int t = tid - 64;
-                if (p.uv_step == 1) {
-                    const int row = t & 15;
-                    const uint8_t* sv = (t < 16 ? s_u : s_v) + row * (FT_W / 2);
-                    const int x = tx0 >> 1, y = (ty0 >> 1) + row;
-                    if (y < (p.out_h >> 1) && x < (p.out_w >> 1)) {
-                        uint8_t* o = (t < 16 ? p.ou + (size_t)y * p.ou_pitch : p.ov + (size_t)y * p.ov_pitch) + x;
-                        if (x + 16 <= (p.out_w >> 1) && (((uintptr_t)o) & 15) == 0) *reinterpret_cast<uint4*>(o) = *reinterpret_cast<const uint4*>(sv);
-                        else for (int k = 0; k < 16 && x + k < (p.out_w >> 1); k++) o[k] = sv[k];
-                    }
-                } else {                                    // interleaved (NV12-style) chroma: 8 samples of each plane per thread
-                    const int row = t >> 1, hx = (t & 1) << 3;
-                    const int x = (tx0 >> 1) + hx, y = (ty0 >> 1) + row;
-                    if (y < (p.out_h >> 1))
-                        for (int k = 0; k < 8 && x + k < (p.out_w >> 1); k++) {
-                            p.ou[(size_t)y * p.ou_pitch + (size_t)(x + k) * p.uv_step] = s_u[row * (FT_W / 2) + hx + k];
-                            p.ov[(size_t)y * p.ov_pitch + (size_t)(x + k) * p.uv_step] = s_v[row * (FT_W / 2) + hx + k];
-                        }
-                }
-            }
-        }
+        J = N; d0 = e0; d1 = e1;
+        N = NN; e0 = g0; e1 = g1;
+        // consecutive boxes normally sit side by side in the stage, so the next conversion may start while other warps
+        // still gather; only when the host could not place them apart (FJOB_SYNC) a second barrier is needed
+        if (j + 1 < je && (J.cam & FJOB_SYNC)) __syncthreads();
     }
+    __syncthreads();
+    if (pending_xy != 0xFFFFFFFFu && p.oy) store_tile(pending_xy, tiles_done - 1u);
 }
 
 int fused_ctas_per_sm()
