@@ -42,39 +42,61 @@ def peaks():
 
 
 class ClockSampler:
-    """nvidia-smi clocks/throttle reasons sampled during the timed region (B200_PROFILING.md)."""
+    """SM clock and throttle reasons sampled DURING the timed region (B200_PROFILING.md).  The timed region of this
+    bench is tens of milliseconds, too short for `nvidia-smi -lms`, so NVML is polled directly (every ~1 ms) from a
+    thread; nvidia-smi is the fallback."""
+
+    REASONS = {0x8: "hw_slowdown", 0x40: "hw_thermal_slowdown", 0x20: "sw_thermal_slowdown", 0x4: "sw_power_cap"}
 
     def __init__(self, index):
-        self.rows = []
-        self.proc = None
+        self.sm, self.mask, self.max_mhz, self.err = [], 0, None, None
+        self._stop = threading.Event()
+        self.t = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = float(pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM))
+            self.t = threading.Thread(target=self._poll, daemon=True)
+            self.t.start()
+        except Exception as ex:          # noqa: BLE001
+            self.err = "nvml: %s" % ex
+
+    def _poll(self):
+        nv = self.nv
+        while not self._stop.is_set():
+            try:
+                self.sm.append(float(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM)))
+                try:
+                    self.mask |= int(nv.nvmlDeviceGetCurrentClocksEventReasons(self.h))
+                except Exception:        # noqa: BLE001  (older bindings)
+                    self.mask |= int(nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h))
+            except Exception as ex:      # noqa: BLE001
+                self.err = "nvml: %s" % ex
+                return
+            time.sleep(0.001)
+
+    def stop(self):
+        self._stop.set()
+        if self.t:
+            self.t.join(timeout=2)
+        if not self.sm:
+            return self._smi_once()
+        return {"sm_mhz": statistics.median(self.sm), "sm_max_mhz": self.max_mhz,
+                "reasons": sorted(n for bit, n in self.REASONS.items() if self.mask & bit), "samples": len(self.sm), "source": "nvml"}
+
+    def _smi_once(self):
         q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(index), "--query-gpu=" + q, "--format=csv,noheader,nounits", "-lms", "100"],
-                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
-            self.t = threading.Thread(target=self._read, daemon=True)
-            self.t.start()
-        except Exception:
-            self.proc = None
-
-    def _read(self):
-        for line in self.proc.stdout:
-            self.rows.append([c.strip() for c in line.split(",")])
-
-    def stop(self):
-        if not self.proc:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        self.proc.terminate()
-        try:
-            self.proc.wait(timeout=2)
-        except Exception:
-            self.proc.kill()
-        sm = [float(r[0]) for r in self.rows if len(r) >= 6 and r[0].replace(".", "").isdigit()]
-        mx = [float(r[1]) for r in self.rows if len(r) >= 6 and r[1].replace(".", "").isdigit()]
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        reasons = sorted({names[k] for r in self.rows if len(r) >= 6 for k in range(4) if r[2 + k].lower().startswith("active")})
-        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": reasons,
-                "samples": len(sm)}
+            out = subprocess.run(["nvidia-smi", "--query-gpu=" + q, "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=10).stdout
+            r = [c.strip() for c in out.splitlines()[0].split(",")]
+            names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+            return {"sm_mhz": float(r[0]), "sm_max_mhz": float(r[1]), "reasons": [names[k] for k in range(4) if r[2 + k].lower().startswith("active")],
+                    "samples": 1, "source": "nvidia-smi after the timed region (%s)" % self.err}
+        except Exception as ex:          # noqa: BLE001
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["unavailable: %s / %s" % (self.err, ex)], "samples": 0}
 
 
 def alg_bytes(in_sizes, out_size, pairs, roi_area, blend):
@@ -85,6 +107,20 @@ def alg_bytes(in_sizes, out_size, pairs, roi_area, blend):
         M = 2 * (4 / 3) * roi_area * 4 + 2 * (4 / 3) * out_size[0] * out_size[1] * 6 + (4 / 3) * roi_area * 4
         return I + 8 * pairs + O_ + M
     return I + 12 * pairs + O_
+
+
+def blend_kernel_name():
+    return {"fused": "k_stitch_fused", "direct": "k_blend"}.get(os.environ.get("OCTVR_BLEND", ""), "k_blend_staged")
+
+
+def ncu_traffic(workload, blend):
+    """dram__bytes_read.sum + dram__bytes_write.sum of the dominant kernel, per launch, from the committed ncu --set full
+    capture of this workload (profiles/r01_traffic.json, written by tools/ncu_summary.py from the .ncu-rep)."""
+    try:
+        t = json.load(open(os.path.join(ROOT, "profiles", "r01_traffic.json")))
+        return t.get("%s:%s" % (workload, blend_kernel_name() if blend <= 0 else "multiband"))
+    except Exception:                    # noqa: BLE001
+        return None
 
 
 def make_template(vr, cfg, width, device):
@@ -196,8 +232,8 @@ def run_ours(args):
         "frac_of_hbm_roofline": {"whole_step_vs_measured_%.0f" % peak: round(B / (ms_per_step * 1e-3) / 1e9 / peak, 4),
                                  "whole_step_vs_8000": round(B / (ms_per_step * 1e-3) / 1e9 / 8000.0, 4)},
         "stage_ms": {k: round(statistics.median(v), 5) for k, v in stage.items()},
-        "roofline": {"bound": "hbm", "kernel": "k_blend" if blend <= 0 else "multiband stage (k_mb_warp+k_mb_down+k_mb_band+k_mb_collapse+k_mb_final)", "achieved": round(ach, 1), "peak": peak, "peak_source": how, "unit": "GB/s",
-                     "frac": round(ach / peak, 4), "traffic": None,
+        "roofline": {"bound": "hbm", "kernel": blend_kernel_name() if blend <= 0 else "multiband stage (k_mb_warp+k_mb_down+k_mb_band+k_mb_collapse+k_mb_final)", "achieved": round(ach, 1), "peak": peak, "peak_source": how, "unit": "GB/s",
+                     "frac": round(ach / peak, 4), "traffic": ncu_traffic(args.workload, blend),
                      "alg_bytes_per_launch": int(blend_bytes), "ms_per_launch": round(blend_ms, 5)},
         "gpu_launches": st["launches_per_stitch"] * args.steps,
         "clocks": clocks, "e2e": e2e,
@@ -205,6 +241,61 @@ def run_ours(args):
     if not args.no_cpu:
         line["cpu_baseline"] = cpu_baseline(args.workload, budget_s=20.0)
     print(json.dumps(line))
+
+
+def run_rowband(args):
+    """One stream over all ranks: rank 0 ingests the frames, NCCL broadcasts them, rank r stitches output rows
+    row_bands(H, world, 32)[r], the bands are collected on rank 0.  Everything is inside the timed region."""
+    import torch
+    import torch.distributed as dist
+    import octvr_b200 as vr
+    import util
+    world, rank, local = int(os.environ["WORLD_SIZE"]), int(os.environ["RANK"]), int(os.environ.get("LOCAL_RANK", "0"))
+    dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    torch.cuda.set_device(local)
+    rig, blend, gain, desc = WORKLOADS[args.workload]
+    cfg, width, in_size = util.named_rig(rig)
+    n = len(cfg["inputs"])
+    iw, ih = in_size
+    tmpl = make_template(vr, cfg, width, local)
+    W, H = tmpl.out_size
+    rb = vr.sharding.RowBandStitcher(vr, tmpl, [in_size] * n, blend, gain, local)
+    RING = 4
+    ring = []
+    for k in range(RING):
+        fr = []
+        for c in range(n):
+            y, u, v = util.i420_planes(util.noise_frame(c, iw, ih, seed=1234 + 7919 * k), iw, ih)
+            host = np.concatenate([y, np.concatenate([u, v], 1)], 0)
+            fr.append(torch.from_numpy(host).cuda() if rank == 0 else torch.zeros(host.shape, dtype=torch.uint8, device="cuda"))
+        ring.append(fr)
+    out = torch.zeros((H * 3 // 2, W), dtype=torch.uint8, device="cuda")
+
+    def step(k):
+        out.zero_()
+        rb.stitch(ring[k % RING], out, src=0, collect=True)
+
+    for k in range(args.warmup):
+        step(k)
+    dist.barrier()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for k in range(args.steps):
+        step(k)
+    e1.record()
+    torch.cuda.synchronize()
+    ms = vr.sharding.max_over_ranks(e0.elapsed_time(e1), device="cuda")
+    dist.barrier()
+    dist.destroy_process_group()
+    if rank != 0:
+        return
+    print(json.dumps({
+        "metric": "equirect output Mpix/s", "value": round(W * H * args.steps / (ms * 1e-3) / 1e6, 1), "unit": "Mpix/s", "n_gpus": world,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(ms / args.steps, 5), "higher_is_better": True,
+        "scaling": "strong", "vs_baseline": None, "dtype": "u8", "data": "synthetic", "frames_per_s": round(args.steps / (ms * 1e-3), 1),
+        "config": {"workload": desc, "sharding": "row bands of one stream: NCCL broadcast of %d input frames (%.1f MB) + band stitch + "
+                   "collection of the bands on rank 0 per step" % (n, n * iw * ih * 1.5 / 1e6), "bands": rb.bands}}))
 
 
 def run_e2e(vr, util, tmpl, cfg, in_size, blend, gain, device, steps, world):
@@ -302,9 +393,13 @@ def main():
     ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS))
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--rowband", action="store_true", help="N > 1: all ranks stitch ONE stream, split by output row bands "
+                    "(NCCL broadcast of the inputs + band collection inside the timed region; strong scaling)")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)
+    elif args.rowband and int(os.environ.get("WORLD_SIZE", "1")) > 1:
+        run_rowband(args)
     else:
         run_ours(args)
 

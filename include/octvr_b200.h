@@ -95,6 +95,13 @@ typedef struct octvr_mapper octvr_mapper;
 octvr_status octvr_mapper_create(const octvr_template* t, const int* in_sizes_wh, int n_in,
                                  int blend, int enable_gain, int scale_w, int scale_h,
                                  int device, octvr_mapper** out);
+/* Row-band mapper for the multi-GPU partition of ONE large frame (no counterpart in the reference, which
+ * runs a frame on one GPU): like octvr_mapper_create, but the mapper only holds the tables of, and only writes, output
+ * rows [band_y0, band_y1) (multiples of 32, or the frame height).  The frames passed to stitch are still full size; every
+ * rank reads all inputs (an NCCL broadcast in sharding.py) and computes the same gains.  Feather / no-blend only. */
+octvr_status octvr_mapper_create_band(const octvr_template* t, const int* in_sizes_wh, int n_in,
+                                      int blend, int enable_gain, int band_y0, int band_y1,
+                                      int device, octvr_mapper** out);
 /* void Mapper::stitch(std::vector<GpuMat>& inputs, GpuMat& output, GpuMat& preview, std::vector<double> gains)
  * mapper.cpp:193-323.  DEVICE pointers; asynchronous on `stream` (a cudaStream_t, NULL = default).
  * gains = NULL computes gains from this frame (when enabled); otherwise n_gains predefined gains

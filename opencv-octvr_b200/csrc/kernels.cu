@@ -483,7 +483,7 @@ __global__ void __launch_bounds__(256) k_blend(const BlendParams p)
     __shared__ JobInfo s_job[MAX_CAMS];
     __shared__ uint32_t s_px[TILE_H][TILE_W + 1];
     const int tid = threadIdx.x, lx = tid & 31, ly = tid >> 5;
-    const int tile = blockIdx.y * p.tiles_x + blockIdx.x;
+    const int tile = (blockIdx.y + p.tile_y0) * p.tiles_x + blockIdx.x;
     const uint32_t j0 = __ldg(p.tile_job_start + tile);
     const int nj = (int)(__ldg(p.tile_job_start + tile + 1) - j0);
     if (tid < nj) {
@@ -530,7 +530,7 @@ __global__ void __launch_bounds__(256) k_blend(const BlendParams p)
     __syncthreads();
 
     // ---- store phase: threads re-mapped so each writes packed, coalesced words ----
-    const int tx0 = blockIdx.x * TILE_W, ty0 = blockIdx.y * TILE_H;
+    const int tx0 = blockIdx.x * TILE_W, ty0 = (blockIdx.y + p.tile_y0) * TILE_H;
     if (p.oy) {
         if (tid < 128) {                         // luma: 16 rows x 8 groups of 4 px -> one 32-bit store each
             const int row = tid >> 3, gx = (tid & 7) << 2;
@@ -604,7 +604,7 @@ __global__ void __launch_bounds__(256, 7) k_blend_staged(const __grid_constant__
     __shared__ uint32_t s_gain[MAX_CAMS];
     __shared__ uint32_t s_px[TILE_H][TILE_W + 1];
     const int tid = threadIdx.x, lx = tid & 31, ly = tid >> 5;
-    const int tile = blockIdx.y * p.tiles_x + blockIdx.x;
+    const int tile = (blockIdx.y + p.tile_y0) * p.tiles_x + blockIdx.x;
     const JobMeta* rec = p.jobs + (size_t)tile * MAX_CAMS;
     const int nj = __ldg(&rec->grp_nj) & 0xFF;
     const uint32_t j0 = (uint32_t)__ldg(&rec->j0);
@@ -675,7 +675,7 @@ __global__ void __launch_bounds__(256, 7) k_blend_staged(const __grid_constant__
     s_px[ly + 8][lx] = px1;
     __syncthreads();
 
-    const int tx0 = blockIdx.x * TILE_W, ty0 = blockIdx.y * TILE_H;
+    const int tx0 = blockIdx.x * TILE_W, ty0 = (blockIdx.y + p.tile_y0) * TILE_H;
     if (p.oy) {
         if (tid < 128) {
             const int row = tid >> 3, gx = (tid & 7) << 2;
@@ -713,13 +713,13 @@ __global__ void __launch_bounds__(256, 7) k_blend_staged(const __grid_constant__
 
 void launch_blend_staged(const StagedParams& p, cudaStream_t s)
 {
-    if (p.use_gain) k_blend_staged<1><<<dim3(p.tiles_x, p.tiles_y), 256, 0, s>>>(p);
-    else k_blend_staged<0><<<dim3(p.tiles_x, p.tiles_y), 256, 0, s>>>(p);
+    if (p.use_gain) k_blend_staged<1><<<dim3(p.tiles_x, p.tiles_y_run), 256, 0, s>>>(p);
+    else k_blend_staged<0><<<dim3(p.tiles_x, p.tiles_y_run), 256, 0, s>>>(p);
 }
 
 void launch_blend(const BlendParams& p, cudaStream_t s)
 {
-    k_blend<<<dim3(p.tiles_x, p.tiles_y), 256, 0, s>>>(p);
+    k_blend<<<dim3(p.tiles_x, p.tiles_y_run), 256, 0, s>>>(p);
 }
 
 }  // namespace ob

@@ -58,6 +58,7 @@ struct BlendParams {
     const uint2* coords;              // [jobs*TILE_PX]
     const float* weights;             // [jobs*TILE_PX]
     int tiles_x, tiles_y, out_w, out_h;
+    int tile_y0, tiles_y_run;                 // row band of this mapper (tile rows [tile_y0, tile_y0 + tiles_y_run)); default: all
     uint8_t* oy; uint8_t* ou; uint8_t* ov;
     uint32_t oy_pitch, ou_pitch, ov_pitch;
     int uv_step;
@@ -86,6 +87,7 @@ struct StagedParams {
     const void* tmaps;                // CUtensorMap[...]: one per (camera, box size) in use, 128 B each
     const uint2* entries;             // [jobs*TILE_PX]
     int tiles_x, tiles_y, out_w, out_h;
+    int tile_y0, tiles_y_run;         // row band (see BlendParams)
     uint8_t* oy; uint8_t* ou; uint8_t* ov;
     uint32_t oy_pitch, ou_pitch, ov_pitch;
     int uv_step;

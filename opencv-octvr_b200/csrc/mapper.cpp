@@ -162,7 +162,9 @@ static bool build_fused(octvr_mapper& m, const octvr_template& t, const std::vec
         const int mid = (r0 + r1) / 2;
         add_jobs(tl, i, r0, mid); add_jobs(tl, i, mid, r1);
     };
+    auto in_band = [&](int tl) { const int y = (tl / tiles_x) * FT_H; return y >= m.band_y0 && y < m.band_y1; };
     for (int tl = 0; tl < ntiles && ok; tl++) {
+        if (!in_band(tl)) continue;                        // another rank's rows (row-band mode)
         for (int i = 0; i < n; i++) add_jobs(tl, i, 0, FT_H);
         if (tile_jobs[tl].empty()) {                       // nobody covers this tile: one job with no items and zero weights
             Job jb; memset(&jb.rec, 0, sizeof(jb.rec));
@@ -177,7 +179,9 @@ static bool build_fused(octvr_mapper& m, const octvr_template& t, const std::vec
     OB_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, m.device));
     const int per_sm = fused_ctas_per_sm();
     if (per_sm <= 0) fail(OCTVR_ERR_CUDA, "k_stitch_fused cannot be resident on this device");
-    const int grid = std::max(1, std::min(ntiles, sms * per_sm));
+    int band_tiles = 0;
+    for (int i = 0; i < ntiles; i++) band_tiles += in_band(i);
+    const int grid = std::max(1, std::min(band_tiles, sms * per_sm));
     std::vector<int64_t> cost(ntiles);
     for (int tl = 0; tl < ntiles; tl++) {
         // per-thread instruction estimates: ~190 for a job's four pixels, ~150 per conversion round, ~110 for the epilogue
@@ -185,8 +189,8 @@ static bool build_fused(octvr_mapper& m, const octvr_template& t, const std::vec
         for (const Job& jb : tile_jobs[tl]) c += 190 + 150 * (int64_t)((jb.items.size() + FT_THREADS - 1) / FT_THREADS) + 60;
         cost[tl] = c;
     }
-    std::vector<int> order(ntiles);
-    for (int i = 0; i < ntiles; i++) order[i] = i;
+    std::vector<int> order;
+    for (int i = 0; i < ntiles; i++) if (in_band(i)) order.push_back(i);
     std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return cost[a] > cost[b]; });
     std::vector<std::vector<int>> bin_tiles(grid);
     {
@@ -258,7 +262,7 @@ static bool build_fused(octvr_mapper& m, const octvr_template& t, const std::vec
 }
 
 static void build_mapper(octvr_mapper& m, const octvr_template& t, const int* in_sizes, int n_in,
-                         int blend, bool enable_gain, int scale_w, int scale_h)
+                         int blend, bool enable_gain, int scale_w, int scale_h, int band_y0, int band_y1)
 {
     const int n = (int)t.inputs.size();
     OB_CHECK(n >= 1 && n <= MAX_CAMS, "1..16 inputs supported");
@@ -268,6 +272,12 @@ static void build_mapper(octvr_mapper& m, const octvr_template& t, const int* in
         fail(OCTVR_ERR_UNSUPPORTED, "scale_output != template size is not implemented yet");
     if (n == 1) { enable_gain = false; blend = 0; }        // mapper.cpp:78-82
     m.n = n; m.out_w = t.out_w; m.out_h = t.out_h; m.blend = blend; m.gain = enable_gain;
+    if (band_y0 == 0 && band_y1 == 0) band_y1 = t.out_h;
+    OB_CHECK(band_y0 >= 0 && band_y0 < band_y1 && band_y1 <= t.out_h, "row band must lie inside the output");
+    OB_CHECK(band_y0 % 32 == 0 && (band_y1 % 32 == 0 || band_y1 == t.out_h), "row bands must be aligned to 32 output rows");
+    if ((band_y0 != 0 || band_y1 != t.out_h) && blend > 0)
+        fail(OCTVR_ERR_UNSUPPORTED, "row bands are implemented for feather / no-blend mappers only (multiband needs halo rows)");
+    m.band_y0 = band_y0; m.band_y1 = band_y1;
     OB_CHECK(t.out_w % 2 == 0 && t.out_h % 2 == 0, "output size must be even (4:2:0)");
     for (int i = 0; i < n; i++) {
         int w = in_sizes[2 * i], h = in_sizes[2 * i + 1];
@@ -323,6 +333,7 @@ static void build_mapper(octvr_mapper& m, const octvr_template& t, const int* in
             for (int y = 0; y < in.roi.h; y++) {
                 const uint8_t* mk = in.mask.row(y);
                 const float* wr = W[i].row(y);
+                if (in.roi.y + y < m.band_y0 || in.roi.y + y >= m.band_y1) continue;      // another rank's rows
                 const int ty = (in.roi.y + y) / TILE_H;
                 for (int x = 0; x < in.roi.w; x++)
                     if (mk[x] && wr[x] != 0.f) used[((size_t)ty * tiles_x + (in.roi.x + x) / TILE_W) * n + i] = 1;
@@ -626,6 +637,7 @@ void ob::mapper_stitch_internal(octvr_mapper& m, const octvr_frame* in, int n_in
         for (int i = 0; i < m.n; i++) { sp.rgbx[i] = m.d_rgbx[i]; sp.src_w[i] = m.in_w[i]; sp.src_h[i] = m.in_h[i]; }
         sp.jobs = m.d_jobs; sp.entries = m.d_entries; sp.tmaps = m.d_tmaps;
         sp.tiles_x = m.tiles_x; sp.tiles_y = m.tiles_y; sp.out_w = m.out_w; sp.out_h = m.out_h;
+        sp.tile_y0 = m.band_y0 / TILE_H; sp.tiles_y_run = (m.band_y1 + TILE_H - 1) / TILE_H - sp.tile_y0;
         if (out) {
             sp.oy = out->y; sp.ou = out->u; sp.ov = out->v;
             sp.oy_pitch = (uint32_t)out->y_pitch; sp.ou_pitch = (uint32_t)out->u_pitch; sp.ov_pitch = (uint32_t)out->v_pitch;
@@ -642,6 +654,7 @@ void ob::mapper_stitch_internal(octvr_mapper& m, const octvr_frame* in, int n_in
         for (int i = 0; i < m.n; i++) { bp.rgbx[i] = m.d_rgbx[i]; bp.src_pitch[i] = m.in_w[i]; }
         bp.tile_job_start = m.d_tile_job_start; bp.job_cam = m.d_job_cam; bp.coords = m.d_coords; bp.weights = m.d_weights;
         bp.tiles_x = m.tiles_x; bp.tiles_y = m.tiles_y; bp.out_w = m.out_w; bp.out_h = m.out_h;
+        bp.tile_y0 = m.band_y0 / TILE_H; bp.tiles_y_run = (m.band_y1 + TILE_H - 1) / TILE_H - bp.tile_y0;
         if (out) {
             bp.oy = out->y; bp.ou = out->u; bp.ov = out->v;
             bp.oy_pitch = (uint32_t)out->y_pitch; bp.ou_pitch = (uint32_t)out->u_pitch; bp.ov_pitch = (uint32_t)out->v_pitch;
@@ -672,7 +685,24 @@ octvr_status octvr_mapper_create(const octvr_template* t, const int* in_sizes_wh
         OB_CUDA(cudaSetDevice(device));
         std::unique_ptr<octvr_mapper> m(new octvr_mapper);
         m->device = device;
-        build_mapper(*m, *t, in_sizes_wh, n_in, blend, enable_gain != 0, scale_w, scale_h);
+        build_mapper(*m, *t, in_sizes_wh, n_in, blend, enable_gain != 0, scale_w, scale_h, 0, 0);
+        *out = m.release();
+    });
+}
+
+octvr_status octvr_mapper_create_band(const octvr_template* t, const int* in_sizes_wh, int n_in, int blend,
+                                      int enable_gain, int band_y0, int band_y1, int device, octvr_mapper** out)
+{
+    return guard([&] {
+        OB_CHECK(t && in_sizes_wh && out, "null argument");
+        int count = 0;
+        cudaError_t e = cudaGetDeviceCount(&count);
+        if (e != cudaSuccess || count <= 0 || device < 0 || device >= count)
+            fail(OCTVR_ERR_CUDA, "no usable CUDA device (the stitch path has no CPU fallback)");
+        OB_CUDA(cudaSetDevice(device));
+        std::unique_ptr<octvr_mapper> m(new octvr_mapper);
+        m->device = device;
+        build_mapper(*m, *t, in_sizes_wh, n_in, blend, enable_gain != 0, 0, 0, band_y0, band_y1);
         *out = m.release();
     });
 }

@@ -17,6 +17,7 @@ struct octvr_mapper {
     std::vector<float*> d_vig;
     // tile-compacted tables (feather / no-blend)
     int tiles_x = 0, tiles_y = 0;
+    int band_y0 = 0, band_y1 = 0;       // output rows this mapper produces (multi-GPU row-band mode); default: all rows
     size_t njobs = 0;
     uint32_t* d_tile_job_start = nullptr;
     uint8_t* d_job_cam = nullptr;

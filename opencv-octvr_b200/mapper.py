@@ -139,17 +139,25 @@ def split_packed(t, w, h):
 class Mapper:
     """vr::Mapper (mapper.hpp:29-95).  blend > 0 multiband, < 0 feather border, 0 none."""
 
-    def __init__(self, tmpl, in_sizes, blend=128, enable_gain_compensator=True, scale_output=(0, 0), device=0):
+    def __init__(self, tmpl, in_sizes, blend=128, enable_gain_compensator=True, scale_output=(0, 0), device=0, band=None):
+        """band=(y0, y1): row-band mapper (multi-GPU partition of one frame, sharding.RowBandStitcher): only output rows
+        [y0, y1) are produced; frames passed to stitch() stay full size."""
         import torch
         self._torch = torch
         self.tmpl = tmpl
         self.device = device
+        self.band = band
         self.in_sizes = [tuple(s) for s in in_sizes]
         sz = np.ascontiguousarray(np.array(self.in_sizes, np.int32).reshape(-1, 2))
         h = C.c_void_p()
-        check(lib().octvr_mapper_create(tmpl._h, sz.ctypes.data_as(C.c_void_p), len(self.in_sizes), int(blend),
-                                        int(bool(enable_gain_compensator)), int(scale_output[0]), int(scale_output[1]),
-                                        int(device), C.byref(h)))
+        if band is None:
+            check(lib().octvr_mapper_create(tmpl._h, sz.ctypes.data_as(C.c_void_p), len(self.in_sizes), int(blend),
+                                            int(bool(enable_gain_compensator)), int(scale_output[0]), int(scale_output[1]),
+                                            int(device), C.byref(h)))
+        else:
+            check(lib().octvr_mapper_create_band(tmpl._h, sz.ctypes.data_as(C.c_void_p), len(self.in_sizes), int(blend),
+                                                 int(bool(enable_gain_compensator)), int(band[0]), int(band[1]),
+                                                 int(device), C.byref(h)))
         self._h = h
         self.out_size = tmpl.out_size
 

@@ -18,7 +18,16 @@ WORKER = textwrap.dedent("""
     t = vr.sharding.max_over_ranks(1.0 + r)
     counts = vr.sharding.gather_frame_counts(100 * len(mine))
     bands = vr.sharding.row_bands(1920, w, 32)
-    print(json.dumps({"rank": r, "mine": mine, "t": t, "counts": counts, "bands": bands}))
+    # row-band mode plumbing on CPU tensors: inputs broadcast from rank 0, each rank fills only its band, bands collected on rank 0
+    import torch
+    frames = [torch.full((6, 8), 10 * (k + 1) if r == 0 else 0, dtype=torch.uint8) for k in range(3)]
+    vr.sharding.broadcast_frames(frames, src=0)
+    got = [int(f[0, 0]) for f in frames]
+    out = torch.zeros((64, 4), dtype=torch.uint8)
+    y0, y1 = vr.sharding.row_bands(64, w, 32)[r]
+    out[y0:y1] = r + 1
+    vr.sharding.collect_bands(out, dst=0)
+    print(json.dumps({"rank": r, "mine": mine, "t": t, "counts": counts, "bands": bands, "bcast": got, "rows": out[:, 0].tolist()}))
     dist.destroy_process_group()
 """) % ROOT
 
@@ -39,6 +48,8 @@ def test_two_rank_gloo_sharding(tmp_path):
     assert rows[0]["t"] == rows[1]["t"] == 2.0                                   # max over ranks
     assert rows[0]["counts"] == rows[1]["counts"] == [800, 800]
     assert rows[0]["bands"] == [[0, 960], [960, 1920]]
+    assert rows[0]["bcast"] == rows[1]["bcast"] == [10, 20, 30]                   # every rank sees the ingest rank's frames
+    assert rows[0]["rows"] == [1] * 32 + [2] * 32                                 # the bands assembled on rank 0
 
 
 def test_row_bands_alignment():
