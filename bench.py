@@ -348,6 +348,10 @@ def cpu_baseline(workload, budget_s=20.0, steps=None, warmup=1):
     cfg, width, in_size = util.named_rig(rig)
     n = len(cfg["inputs"])
     iw, ih = in_size
+    try:                                  # torchrun exports OMP_NUM_THREADS=1: the CPU arm is meant to use every host core
+        O.set_num_threads(len(os.sched_getaffinity(0)))
+    except Exception:                     # noqa: BLE001
+        pass
     ot = O.build_template(cfg, width)
     so = O.StitchOracle(ot, [in_size] * n, blend=blend, enable_gain=gain)
     frames = [util.i420_planes(util.noise_frame(c, iw, ih), iw, ih) for c in range(n)]
