@@ -31,6 +31,7 @@ WORKLOADS = {
     "c1": ("rig2", -1, True, "C1 2x1920x1080 fisheye -> 2048x1024 equirect, gain + feather(1)"),
     "c2": ("rig6", -1, True, "C2 6x2704x1520 -> 4096x2048 equirect, gain + feather(1)"),
     "c3": ("rig6", 64, True, "C3 6x2704x1520 -> 4096x2048 equirect, gain + 5-band multiband"),
+    "c2ng": ("rig6", -1, False, "C2 rig without gain compensation: 6x2704x1520 -> 4096x2048 equirect, feather(1) (diagnostic)"),
 }
 
 

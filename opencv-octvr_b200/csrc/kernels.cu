@@ -251,13 +251,21 @@ __device__ void gain_tables(const GainParams& p)
         unsigned int ok = 0u;
         if (g > 0. && g < 4096.) {
             const float g0 = (float)g;
-            #pragma unroll
-            for (int k = 0; k < 5; k++) {                   // candidate k: (float)g + {0,+1,-1,+2,-2} ulp
+            // candidate k: (float)g + {0,+1,-1,+2,-2} ulp.  Candidate 0 almost always reproduces the f64 rule for all 256
+            // inputs, so the others are only evaluated (by the whole CTA, uniformly) when some input rejects it
+            auto good = [&](int k) {
                 const int step = (k == 0) ? 0 : (k & 1) ? (k + 1) / 2 : -(k / 2);
                 const float gc = __int_as_float(__float_as_int(g0) + step);
-                if ((int)gain_apply_f32((float)v, gc) == exact && (int)gain_apply_biased(MAGIC_RD + (float)v, gc, gain_bias_f32(gc)) == exact) ok |= 1u << k;
+                return (int)gain_apply_f32((float)v, gc) == exact && (int)gain_apply_biased(MAGIC_RD + (float)v, gc, gain_bias_f32(gc)) == exact;
+            };
+            ok = good(0) ? 0x1Fu : 0u;
+            if (__syncthreads_or(ok == 0u)) {
+                ok = 0u;
+                #pragma unroll 1
+                for (int k = 0; k < 5; k++) if (good(k)) ok |= 1u << k;
             }
-        }
+        } else
+            __syncthreads_or(0);
         if (ok != 0x1Fu) atomicAnd(&s_ok[c], ok);
     }
     asm volatile("bar.sync 1, 256;");
@@ -270,86 +278,76 @@ __device__ void gain_tables(const GainParams& p)
     }
 }
 
-// Working-scale statistics (mapper.cpp:94-99: a ~0.1 Mpix canvas) + gain solve in ONE launch.
-// A CTA takes 256-pixel chunks of the canvas.  Phase A: thread = canvas pixel; for every camera whose
-// working-scale mask is 255 there (CPU compensator's intersect rule, exposure_compensate.cpp:71-78,112) it remaps
-// that one pixel (nearest-resized position, mapper.cpp:235-237) and stores ||rgb||_2 (f64) in shared memory;
-// cameras are processed four at a time so each dependent load step has four requests in flight.
-// Phase B: warp = camera pair; lanes stride the chunk, one shuffle reduction per pair.  The last CTA to
-// finish (ticket) adds the CTA partials in a fixed order, solves for the gains (one warp) and builds the gain
-// tables.  Deterministic; no host round trip.
+// Working-scale statistics (mapper.cpp:94-99: a ~0.1 Mpix canvas) + gain solve in ONE launch, written for latency.
+// A CTA takes one chunk of the canvas: up to 128 pixels and the (at most 256) samples (pixel, camera) whose
+// working-scale mask is 255 there (CPU compensator's intersect rule, exposure_compensate.cpp:71-78,112), listed by the
+// host.  Phase A: thread = sample; it remaps that one pixel (nearest-resized position, mapper.cpp:235-237) straight
+// from the input planes and stores ||rgb||_2 (f64) in shared memory -- every table and tap load of the chunk is in
+// flight at once.  Phase B: warp = camera pair, lanes = pixels.  The sums are accumulated EXACTLY: a norm is sqrt of
+// an integer >= 1 (or 0), i.e. an integer multiple of 2^-52 below 2^9, so its 61-bit fixed-point image is split into
+// two 64-bit integer accumulators (high / low 32 bits) that cannot overflow over 2^17 samples.  Integer addition is
+// associative: atomics in any order give the same totals, no per-CTA partial rows, no reduction pass, and the totals
+// are the exact sums rounded to f64 once (the reference's sequential f64 sum differs from that by its own rounding).
+// The last CTA to finish (ticket) solves for the gains (one warp) and builds the gain tables.  Deterministic.
 constexpr int MAX_PAIRS = MAX_CAMS * (MAX_CAMS + 1) / 2;
 __device__ __forceinline__ unsigned long long gtime() { unsigned long long t; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t)); return t; }
-constexpr int GAIN_BLK = 256;                              // canvas pixels per chunk = CTA size of the fused kernel
-constexpr int GAIN_BATCH = 8;
-__device__ __forceinline__ void gain_body(const GainParams& p, double* s_nrm, const unsigned gain_blocks)   // s_nrm: [n][GAIN_BLK]
+constexpr int GAIN_BLK = 256;                              // CTA size of the fused kernel = samples per chunk
+constexpr int GAIN_PX = 128;                               // canvas pixels per chunk
+__device__ __forceinline__ void gain_body(const GainParams& p, double* s_nrm, const unsigned gain_blocks, const unsigned chunk)   // s_nrm: [n][GAIN_PX]
 {
     __shared__ double s_part[3 * MAX_PAIRS];
     __shared__ double Nm[MAX_CAMS * MAX_CAMS], Im[MAX_CAMS * MAX_CAMS], Aug[MAX_CAMS * (MAX_CAMS + 1)];
     __shared__ uint8_t s_pi[MAX_PAIRS], s_pj[MAX_PAIRS];
     __shared__ bool is_last;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int n = p.n, np = p.n_pairs, nq = 3 * np;
+    const int n = p.n, np = p.n_pairs;
     const unsigned long long T0 = gtime();
-    for (int q = tid; q < nq; q += GAIN_BLK) s_part[q] = 0;
+    if (chunk == 0 && tid == 0 && p.dbg) p.dbg[5] = T0;      // diagnostics: when the first gain CTA started
+    for (int q = tid; q < n * GAIN_PX; q += GAIN_BLK) s_nrm[q] = -1.0;
     if (tid == 0) { int q = 0; for (int i = 0; i < n; i++) for (int j = i; j < n; j++, q++) { s_pi[q] = (uint8_t)i; s_pj[q] = (uint8_t)j; } }
-    const int area = p.cw * p.ch, nchunks = (area + GAIN_BLK - 1) / GAIN_BLK;
-    for (int chunk = blockIdx.x; chunk < nchunks; chunk += gain_blocks) {
-        __syncthreads();
-        const int pix = chunk * GAIN_BLK + tid;
-        const int X = p.cx0 + pix % p.cw, Y = pix < area ? p.cy0 + pix / p.cw : -0x40000000;
-        #pragma unroll 1
-        for (int c0 = 0; c0 < n; c0 += GAIN_BATCH) {        // GAIN_BATCH cameras at a time: every dependent load step has
-            uint32_t t[GAIN_BATCH]; bool in[GAIN_BATCH]; uint2 cc[GAIN_BATCH]; uint32_t tap[GAIN_BATCH][4];   // that many requests in flight
-            #pragma unroll
-            for (int u = 0; u < GAIN_BATCH; u++) {
-                const GainCam gc = p.cam[min(c0 + u, n - 1)];
-                const int lx = X - gc.sx, ly = Y - gc.sy;
-                in[u] = c0 + u < n && lx >= 0 && ly >= 0 && lx < gc.sw && ly < gc.sh;
-                t[u] = gc.off + ly * gc.sw + lx;
+    __syncthreads();
+    {
+        const uint4 sm = __ldg(p.samples + (size_t)chunk * GAIN_BLK + tid);      // entry.x, entry.y, camera | local pixel << 8 (all ones: empty slot)
+        if (sm.z != 0xFFFFFFFFu) {
+            const int c = (int)(sm.z & 255u), lp = (int)(sm.z >> 8);
+            uint32_t t00 = 0u, t01 = 0u, t10 = 0u, t11 = 0u;
+            if (sm.y & C_VALID) {
+                const CamSrc& sc = p.src[c];
+                const int ix = (int)(sm.x & 0xFFFFu) - 1, iy = (int)(sm.x >> 16) - 1;
+                const uint32_t bits = (sm.y & C_BORDER) ? (sm.y >> C_TAP_SHIFT) : 15u;
+                if (bits & 1u) t00 = source_px(sc, ix, iy);
+                if (bits & 2u) t01 = source_px(sc, ix + 1, iy);
+                if (bits & 4u) t10 = source_px(sc, ix, iy + 1);
+                if (bits & 8u) t11 = source_px(sc, ix + 1, iy + 1);
             }
-            #pragma unroll
-            for (int u = 0; u < GAIN_BATCH; u++) cc[u] = in[u] ? __ldg(p.gcoord + t[u]) : make_uint2(0xFFFFFFFFu, 0u);
-            #pragma unroll
-            for (int u = 0; u < GAIN_BATCH; u++) in[u] = cc[u].x != 0xFFFFFFFFu;      // marker: working-scale mask != 255 there
-            #pragma unroll
-            for (int u = 0; u < GAIN_BATCH; u++) {
-                tap[u][0] = tap[u][1] = tap[u][2] = tap[u][3] = 0u;
-                if (cc[u].y & C_VALID) {
-                    const CamSrc& sc = p.src[min(c0 + u, n - 1)];
-                    const int ix = (int)(cc[u].x & 0xFFFFu) - 1, iy = (int)(cc[u].x >> 16) - 1;
-                    const uint32_t bits = (cc[u].y & C_BORDER) ? (cc[u].y >> C_TAP_SHIFT) : 15u;
-                    if (bits & 1u) tap[u][0] = source_px(sc, ix, iy);
-                    if (bits & 2u) tap[u][1] = source_px(sc, ix + 1, iy);
-                    if (bits & 4u) tap[u][2] = source_px(sc, ix, iy + 1);
-                    if (bits & 8u) tap[u][3] = source_px(sc, ix + 1, iy + 1);
-                }
-            }
-            #pragma unroll
-            for (int u = 0; u < GAIN_BATCH; u++) {
-                int r, g, b;
-                bilerp_rgbx(tap[u][0], tap[u][1], tap[u][2], tap[u][3], cc[u].y & 31u, (cc[u].y >> 5) & 31u, r, g, b);
-                if (c0 + u < n) s_nrm[(c0 + u) * GAIN_BLK + tid] = in[u] ? sqrt((double)(r * r + g * g + b * b)) : -1.0;
-            }
-        }
-        __syncthreads();
-        for (int q = warp; q < np; q += GAIN_BLK / 32) {
-            const double* na = s_nrm + s_pi[q] * GAIN_BLK, *nb = s_nrm + s_pj[q] * GAIN_BLK;
-            int cnt = 0; double s1 = 0, s2 = 0;
-            #pragma unroll 8
-            for (int l = lane; l < GAIN_BLK; l += 32) {
-                const double a = na[l], b = nb[l];
-                if (a >= 0 && b >= 0) { cnt++; s1 += a; s2 += b; }
-            }
-            cnt = __reduce_add_sync(0xffffffffu, cnt);
-            if (cnt) {                                      // uniform
-                s1 = warp_sum(s1); s2 = warp_sum(s2);
-                if (lane == 0) { s_part[3 * q] += (double)cnt; s_part[3 * q + 1] += s1; s_part[3 * q + 2] += s2; }
-            }
+            int r, g, b;
+            bilerp_rgbx(t00, t01, t10, t11, sm.y & 31u, (sm.y >> 5) & 31u, r, g, b);
+            s_nrm[c * GAIN_PX + lp] = sqrt((double)(r * r + g * g + b * b));
         }
     }
     __syncthreads();
-    for (int q = tid; q < nq; q += GAIN_BLK) __stcg(p.partial + (size_t)blockIdx.x * nq + q, s_part[q]);
+    #pragma unroll 1
+    for (int q = warp; q < np; q += GAIN_BLK / 32) {
+        const double* na = s_nrm + s_pi[q] * GAIN_PX, *nb = s_nrm + s_pj[q] * GAIN_PX;
+        unsigned long long cnt = 0, ha = 0, la = 0, hb = 0, lb = 0;
+        #pragma unroll 1
+        for (int l = lane; l < GAIN_PX; l += 32) {
+            const double a = na[l], b = nb[l];
+            if (a >= 0 && b >= 0) {
+                const unsigned long long qa = __double2ull_rz(a * 4503599627370496.0), qb = __double2ull_rz(b * 4503599627370496.0);   // x 2^52: exact
+                cnt++; ha += qa >> 32; la += qa & 0xFFFFFFFFull; hb += qb >> 32; lb += qb & 0xFFFFFFFFull;
+            }
+        }
+        #pragma unroll 1
+        for (int o = 16; o > 0; o >>= 1) {                  // integer sums: any order gives the same result
+            cnt += __shfl_down_sync(0xffffffffu, cnt, o); ha += __shfl_down_sync(0xffffffffu, ha, o); la += __shfl_down_sync(0xffffffffu, la, o);
+            hb += __shfl_down_sync(0xffffffffu, hb, o); lb += __shfl_down_sync(0xffffffffu, lb, o);
+        }
+        if (lane == 0 && cnt) {
+            unsigned long long* o = p.totals + 5 * q;
+            atomicAdd(o, cnt); atomicAdd(o + 1, ha); atomicAdd(o + 2, la); atomicAdd(o + 3, hb); atomicAdd(o + 4, lb);
+        }
+    }
     __threadfence();
     __syncthreads();
     if (tid == 0) {
@@ -361,22 +359,14 @@ __device__ __forceinline__ void gain_body(const GainParams& p, double* s_nrm, co
     const unsigned long long T1 = gtime();
     __threadfence();
     for (int k = tid; k < n * n; k += GAIN_BLK) { Nm[k] = 0; Im[k] = 0; }
-    // CTA partials -> totals in a fixed order: thread = (value q, slice of the CTAs); 8 independent loads in flight
-    {
-        __shared__ double s_slice[4][3 * MAX_PAIRS];
-        for (int q = tid & 63; q < nq; q += 64) {
-            const int slice = tid >> 6;
-            double acc = 0;
-            for (unsigned k0 = slice; k0 < gain_blocks; k0 += 32) {
-                double t[8];
-                #pragma unroll
-                for (int u = 0; u < 8; u++) { const unsigned k = k0 + 4 * u; t[u] = k < gain_blocks ? __ldcg(p.partial + (size_t)k * nq + q) : 0.0; }
-                acc += ((t[0] + t[1]) + (t[2] + t[3])) + ((t[4] + t[5]) + (t[6] + t[7]));
-            }
-            s_slice[slice][q] = acc;
-        }
-        __syncthreads();
-        for (int q = tid; q < nq; q += 256) s_part[q] = (s_slice[0][q] + s_slice[1][q]) + (s_slice[2][q] + s_slice[3][q]);
+    // totals -> f64 (one rounding each), and reset for the next frame
+    for (int q = tid; q < np; q += GAIN_BLK) {
+        unsigned long long v[5];
+        #pragma unroll
+        for (int u = 0; u < 5; u++) { v[u] = __ldcg(p.totals + 5 * q + u); __stcg(p.totals + 5 * q + u, 0ull); }
+        s_part[3 * q] = (double)v[0];
+        s_part[3 * q + 1] = fma((double)v[1], 4294967296.0, (double)v[2]) * 2.220446049250313e-16;     // (hi 2^32 + lo) 2^-52
+        s_part[3 * q + 2] = fma((double)v[3], 4294967296.0, (double)v[4]) * 2.220446049250313e-16;
     }
     __syncthreads();
     if (tid < np) {
@@ -403,22 +393,32 @@ __device__ __forceinline__ void gain_body(const GainParams& p, double* s_nrm, co
 
 __global__ void __launch_bounds__(256) k_gain_finalize(const GainParams p) { gain_tables(p); }
 
-// Horizontally fused front end of a frame: the first `gain_blocks` CTAs compute the gain statistics and solve (they
-// read the input planes directly, so they do not depend on the conversion), all other CTAs convert the inputs to
-// RGBX.  One launch, both parts run concurrently, no cross-stream synchronisation.
-__global__ void __launch_bounds__(256, 4) k_convert_gain(const __grid_constant__ ConvertParams cp, const __grid_constant__ GainParams gp, const unsigned gain_blocks)
+// Horizontally fused front end of a frame: `gain_blocks` CTAs compute the gain statistics and solve (they read the
+// input planes directly, so they do not depend on the conversion), all other CTAs convert the inputs to RGBX.  One
+// launch, both parts run concurrently, no cross-stream synchronisation.  The gain CTAs are latency-bound and light, the
+// conversion CTAs DRAM-bound: at the head of the grid they are interleaved 1 : 2, so the whole gain chain starts within
+// the first third of the conversion without ever holding more than a fraction of the resident CTA slots.
+__global__ void __launch_bounds__(256, 6) k_convert_gain(const __grid_constant__ ConvertParams cp, const __grid_constant__ GainParams gp, const unsigned gain_blocks,
+                                                         const unsigned interleave)
 {
     extern __shared__ double s_dyn_nrm[];
-    if (blockIdx.x < gain_blocks) gain_body(gp, s_dyn_nrm, gain_blocks);
-    else convert_body(cp, (int)(blockIdx.x - gain_blocks));
+    const unsigned b = blockIdx.x;
+    if (interleave) {
+        if (b < 3u * gain_blocks) {
+            if (b % 3u == 0u) gain_body(gp, s_dyn_nrm, gain_blocks, b / 3u);
+            else convert_body(cp, (int)(b - (b / 3u + 1u)));
+        } else
+            convert_body(cp, (int)(b - gain_blocks));
+    } else if (b < gain_blocks) gain_body(gp, s_dyn_nrm, gain_blocks, b);
+    else convert_body(cp, (int)(b - gain_blocks));
 }
 
 void launch_convert_gain(const ConvertParams& cp, const GainParams* gp, cudaStream_t s)
 {
     static const GainParams none = {};
-    const unsigned gb = gp ? (unsigned)gp->grid : 0u;
-    const size_t smem = gp ? (size_t)gp->n * GAIN_BLK * sizeof(double) : 0;
-    k_convert_gain<<<gb + (unsigned)(cp.grid_x * cp.grid_y * cp.n), 256, smem, s>>>(cp, gp ? *gp : none, gb);
+    const unsigned gb = gp ? (unsigned)gp->grid : 0u, cb = (unsigned)(cp.grid_x * cp.grid_y * cp.n);
+    const size_t smem = gp ? (size_t)gp->n * GAIN_PX * sizeof(double) : 0;
+    k_convert_gain<<<gb + cb, 256, smem, s>>>(cp, gp ? *gp : none, gb, (gb > 0 && cb >= 2u * gb) ? 1u : 0u);
 }
 void launch_gain_finalize(const GainParams& p, cudaStream_t s) { k_gain_finalize<<<1, 256, 0, s>>>(p); }
 

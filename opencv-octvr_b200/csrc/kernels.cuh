@@ -34,6 +34,9 @@ struct GainParams {
     uint32_t total;            // sum of sw*sh
     const uint8_t* smask;      // linearly resized masks (mapper.cpp:113-114)
     const uint2* gcoord;       // NEAREST-resized sample (mapper.cpp:235-237): x = (ix+1) | (iy+1)<<16 of the top-left tap, y = fx|fy<<5|flags
+    const uint4* samples;      // the same entries regrouped per canvas chunk: {entry.x, entry.y, camera | local pixel << 8, 0}
+    const int2* chunks;        // [grid]: {first sample, samples (<= 256)} of up to 128 consecutive canvas pixels
+    unsigned long long* totals;   // [n_pairs][5] exact integer sums (count, hi/lo of sum_i, hi/lo of sum_j); zeroed by the last CTA
     int cx0, cy0, cw, ch;      // working-scale canvas = union of the scaled ROIs
     int n_pairs, grid;         // pairs (i<=j); CTAs launched
     double* partial;           // [grid][n_pairs][3] : count, sum_i, sum_j

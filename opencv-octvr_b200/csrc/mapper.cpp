@@ -78,7 +78,7 @@ octvr_mapper::~octvr_mapper()
     for (auto p : d_rgbx) cudaFree(p);
     for (auto p : d_vig) cudaFree(p);
     cudaFree(d_tile_job_start); cudaFree(d_job_cam); cudaFree(d_coords); cudaFree(d_weights); cudaFree(d_jobs); cudaFree(d_entries); cudaFree(d_tmaps); cudaFree(d_fjobs); cudaFree(d_fbins); cudaFree(d_fitems);
-    cudaFree(d_smask); cudaFree(d_gcoord); cudaFree(d_partial); cudaFree(d_ticket);
+    cudaFree(d_smask); cudaFree(d_gcoord); cudaFree(d_partial); cudaFree(d_ticket); cudaFree(d_gsamples); cudaFree(d_gchunks); cudaFree(d_gtotals);
     cudaFree(d_gains); cudaFree(d_gain_f32); cudaFree(d_gain_flag); cudaFree(d_gain_lut); cudaFree(d_rgb); cudaFree(d_dbg);
     if (h_gains) cudaFreeHost(h_gains);
     for (auto& e : ev) if (e) cudaEventDestroy(e);
@@ -519,10 +519,42 @@ static void build_mapper(octvr_mapper& m, const octvr_template& t, const int* in
             x1 = std::max(x1, g.cam[i].sx + g.cam[i].sw); y1 = std::max(y1, g.cam[i].sy + g.cam[i].sh);
         }
         g.cx0 = x0; g.cy0 = y0; g.cw = x1 - x0; g.ch = y1 - y0;
-        g.grid = std::max(1, std::min(256, (g.cw * g.ch + 255) / 256));
+        // samples regrouped per canvas chunk (<= 128 pixels, <= 256 samples): one CTA per chunk, one thread per sample;
+        // every chunk owns 256 sample slots (empty ones all ones), so a thread finds its sample without a chunk table
+        std::vector<uint4> samples;
+        {
+            const uint4 empty = make_uint4(0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu);
+            size_t first = 0; int npx = 0, cnt = 0;
+            auto close = [&]() { if (cnt) { samples.resize(first + 256, empty); first = samples.size(); } npx = 0; cnt = 0; };
+            std::vector<uint4> here;
+            for (int pix = 0; pix < g.cw * g.ch; pix++) {
+                const int X = g.cx0 + pix % g.cw, Y = g.cy0 + pix / g.cw;
+                here.clear();
+                for (int i = 0; i < n; i++) {
+                    const GainCam& c = g.cam[i];
+                    const int lx = X - c.sx, ly = Y - c.sy;
+                    if (lx < 0 || ly < 0 || lx >= c.sw || ly >= c.sh) continue;
+                    const uint2 e = gcoord[c.off + (size_t)ly * c.sw + lx];
+                    if (e.x == 0xFFFFFFFFu) continue;            // working-scale mask != 255: not in any intersection
+                    here.push_back(make_uint4(e.x, e.y, (uint32_t)i, 0u));
+                }
+                if (here.empty()) continue;
+                if (npx == 128 || cnt + (int)here.size() > 256) close();
+                for (uint4 s : here) { s.z |= (uint32_t)npx << 8; samples.push_back(s); cnt++; }
+                npx++;
+            }
+            close();
+            if (samples.empty()) samples.resize(256, empty);
+        }
+        std::vector<int2> chunks(samples.size() / 256, make_int2(0, 0));
+        g.grid = (int)chunks.size();
         m.d_smask = dev_upload(smask.data(), smask.size());
         m.d_gcoord = dev_upload(gcoord.data(), gcoord.size());
-        m.d_partial = dev_alloc<double>((size_t)g.n_pairs * g.grid * 3, true);
+        m.d_gsamples = dev_upload(samples.data(), samples.size());
+        m.d_gchunks = dev_upload(chunks.data(), chunks.size());
+        m.d_gtotals = dev_alloc<unsigned long long>((size_t)g.n_pairs * 5, true);
+        g.samples = m.d_gsamples; g.chunks = m.d_gchunks; g.totals = m.d_gtotals;
+        m.d_partial = dev_alloc<double>((size_t)g.n_pairs * 3, true);
         m.d_ticket = dev_alloc<unsigned int>(1, true);
         m.d_gains = dev_alloc<double>(MAX_CAMS, true);
         m.d_gain_f32 = dev_alloc<float>(MAX_CAMS, true);
@@ -532,7 +564,7 @@ static void build_mapper(octvr_mapper& m, const octvr_template& t, const int* in
         g.smask = m.d_smask; g.gcoord = m.d_gcoord; g.partial = m.d_partial; g.ticket = m.d_ticket;
         m.d_dbg = dev_alloc<unsigned long long>(8, true); g.dbg = m.d_dbg;
         g.gains = m.d_gains; g.gain_f32 = m.d_gain_f32; g.gain_flag = m.d_gain_flag; g.gain_lut = m.d_gain_lut;
-        m.table_bytes += (int64_t)(smask.size() + gcoord.size() * sizeof(uint2));
+        m.table_bytes += (int64_t)(samples.size() * sizeof(uint4) + chunks.size() * sizeof(int2));
     }
     for (auto& e : m.ev) OB_CUDA(cudaEventCreate(&e));
 
@@ -802,7 +834,7 @@ octvr_status octvr_mapper_debug_gain_ns(octvr_mapper* m, unsigned long long* out
     return guard([&] {
         OB_CHECK(m && out5 && m->d_dbg, "no gain stage");
         OB_CUDA(cudaDeviceSynchronize());
-        OB_CUDA(cudaMemcpy(out5, m->d_dbg, 5 * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
+        OB_CUDA(cudaMemcpy(out5, m->d_dbg, 6 * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
     });
 }
 

@@ -38,6 +38,7 @@ struct octvr_mapper {
     // gain compensation
     ob::GainParams gp;
     uint8_t* d_smask = nullptr; uint2* d_gcoord = nullptr; double* d_partial = nullptr;
+    uint4* d_gsamples = nullptr; int2* d_gchunks = nullptr; unsigned long long* d_gtotals = nullptr;
     unsigned int* d_ticket = nullptr; double* d_gains = nullptr; float* d_gain_f32 = nullptr;
     unsigned long long* d_dbg = nullptr;
     int* d_gain_flag = nullptr; uint8_t* d_gain_lut = nullptr; double* h_gains = nullptr;

@@ -221,7 +221,7 @@ class Mapper:
 
     def debug_gain_ns(self):
         """%globaltimer stamps of the gain kernel's last CTA (diagnostics)."""
-        a = (C.c_ulonglong * 5)()
+        a = (C.c_ulonglong * 6)()
         check(lib().octvr_mapper_debug_gain_ns(self._h, a))
         return list(a)
 

@@ -48,6 +48,7 @@ for k in range(3):
     print({s: round(m.stage_ms(s), 4) for s in ("convert", "gain", "blend", "total")})
 try:
     d = m.debug_gain_ns()
-    print("gain kernel last-CTA stamps (ns): stats %d, reduce %d, solve %d, tables %d" % (d[1] - d[0], d[2] - d[1], d[3] - d[2], d[4] - d[3]))
+    print("gain kernel last-CTA stamps (ns): stats %d, reduce %d, solve %d, tables %d; last CTA started %d ns after the first, chain ended %d ns after the first CTA started"
+          % (d[1] - d[0], d[2] - d[1], d[3] - d[2], d[4] - d[3], d[0] - d[5], d[4] - d[5]))
 except Exception as ex:
     print("no gain stamps:", ex)
