@@ -235,6 +235,76 @@ __device__ void gain_solve_warp(int n, const double* Nm, const double* Im, doubl
     #undef ADD
 }
 
+// The same solve by the whole CTA for n > 3: one thread per element of the augmented matrix [A | b].  Every element
+// sees exactly the operations of matrix_decomp.cpp:52-109 in the same order (alpha = A[j][i] * d, A[j][k] += alpha *
+// A[i][k]; no FMA contraction), but a pivot step costs one division plus one multiply-add instead of a serial sweep.
+__device__ void gain_solve_cta(int n, const double* Nm, const double* Im, double* Aug, double* g)
+{
+    const int tid = threadIdx.x, nt = blockDim.x, ld = n + 1, ne = n * ld;
+    const double alpha = 0.01, beta = 100;
+    if (tid < n) {                                          // normal equations: thread = row (exposure_compensate.cpp:138-153)
+        const int i = tid;
+        double bi = 0, aii = 0;
+        #pragma unroll 1
+        for (int j = 0; j < n; j++) {
+            const double nij = Nm[i * n + j];
+            bi = __dadd_rn(bi, __dmul_rn(beta, nij));
+            aii = __dadd_rn(aii, __dmul_rn(beta, nij));
+            if (j != i) {
+                const double iij = Im[i * n + j], iji = Im[j * n + i];
+                aii = __dadd_rn(aii, __dmul_rn(__dmul_rn(__dmul_rn(2 * alpha, iij), iij), nij));
+                Aug[i * ld + j] = -__dmul_rn(__dmul_rn(__dmul_rn(2 * alpha, iij), iji), nij);
+            }
+        }
+        Aug[i * ld + i] = aii; Aug[i * ld + n] = bi;
+    }
+    __syncthreads();
+    #pragma unroll 1
+    for (int i = 0; i < n; i++) {
+        int k = i;                                          // pivot: every thread scans the column (uniform result)
+        #pragma unroll 1
+        for (int j = i + 1; j < n; j++) if (fabs(Aug[j * ld + i]) > fabs(Aug[k * ld + i])) k = j;
+        if (k != i) {                                       // swap rows i and k from column i on (and b)
+            double t0 = 0, t1 = 0;
+            const int c = i + tid;
+            if (c <= n) { t0 = Aug[i * ld + c]; t1 = Aug[k * ld + c]; }
+            __syncthreads();
+            if (c <= n) { Aug[i * ld + c] = t1; Aug[k * ld + c] = t0; }
+            __syncthreads();
+        }
+        const double d = -1 / Aug[i * ld + i];
+        double upd[2]; int at[2] = { -1, -1 };
+        #pragma unroll
+        for (int u = 0; u < 2; u++) {                       // up to two elements per thread (n = 16: 272 elements)
+            const int e = tid + u * nt;
+            if (e < ne) {
+                const int r = e / ld, c = e - r * ld;
+                if (r > i && c > i) {
+                    const double al = __dmul_rn(Aug[r * ld + i], d);
+                    upd[u] = __dadd_rn(Aug[e], __dmul_rn(al, Aug[i * ld + c]));
+                    at[u] = e;
+                }
+            }
+        }
+        __syncthreads();
+        #pragma unroll
+        for (int u = 0; u < 2; u++) if (at[u] >= 0) Aug[at[u]] = upd[u];
+        if (tid == 0) Aug[i * ld + i] = -d;
+        __syncthreads();
+    }
+    if (tid == 0) {                                         // back substitution: a serial chain by definition
+        #pragma unroll 1
+        for (int i = n - 1; i >= 0; i--) {
+            double sacc = Aug[i * ld + n];
+            #pragma unroll 1
+            for (int k = i + 1; k < n; k++) sacc = __dadd_rn(sacc, -__dmul_rn(Aug[i * ld + k], Aug[k * ld + n]));
+            Aug[i * ld + n] = __dmul_rn(sacc, Aug[i * ld + i]);
+        }
+        #pragma unroll 1
+        for (int i = 0; i < n; i++) g[i] = Aug[i * ld + n];
+    }
+}
+
 // Per camera: the exact u8 gain LUT in f64, and an f32 multiplier for which the single-FMA formula of
 // gain_apply_f32() reproduces that LUT for all 256 inputs (searched within +-2 ulp of (float)g).
 // If none exists the camera is flagged and the blend kernel reads the LUT instead.  256 threads = 256 inputs.
@@ -384,7 +454,9 @@ __device__ __forceinline__ void gain_body(const GainParams& p, double* s_nrm, co
     }
     __syncthreads();
     const unsigned long long T2 = gtime();
-    if (warp == 0) { gain_solve_warp(n, Nm, Im, Aug, p.gains); __threadfence(); }
+    if (n > 3) gain_solve_cta(n, Nm, Im, Aug, p.gains);        // uniform
+    else if (warp == 0) gain_solve_warp(n, Nm, Im, Aug, p.gains);
+    __threadfence();
     __syncthreads();
     const unsigned long long T3 = gtime();
     gain_tables(p);                         // 256 threads = the 256 input values
