@@ -37,6 +37,9 @@ struct MbParams {
     int lw[MB_MAX_LEVELS], lh[MB_MAX_LEVELS];
     unsigned long long off_d[MB_MAX_LEVELS];   // offsets of dst level l (short4 units) and dstw (floats)
     const uint2* coords;              // per camera bordered level-0 pixel: table entry (reflection already applied)
+    const uint2* warp_chunks;         // {camera, 256-pixel chunk} of every chunk with at least one valid entry (the others stay 0)
+    const uint16_t* tile_cams;        // per level and 32 x 8 tile of dst: bit c set if camera c has a non-zero weight in the tile
+    unsigned long long off_t[MB_MAX_LEVELS];   // first tile of level l in tile_cams
     uint32_t* g0;                     // level 0 images, RGBX8888
     short4* g;                        // levels >= 1, 16S x 3 (+pad)
     const float* w;                   // weight pyramids
@@ -54,6 +57,7 @@ struct MbParams {
 
 struct Multiband {
     MbParams p;
+    uint2* d_chunks = nullptr; uint16_t* d_tile_cams = nullptr; unsigned n_chunks = 0;
     uint2* d_coords = nullptr; uint32_t* d_g0 = nullptr; short4* d_g = nullptr; float* d_w = nullptr;
     short4* d_dst = nullptr; float* d_dstw = nullptr;
     int max_bw = 0, max_bh = 0;
@@ -97,12 +101,13 @@ template <class T> __device__ int3 pyrup_at(const T* s, int sw, int sh, int x, i
     return make_int3(sat16((v.x + 32) >> 6), sat16((v.y + 32) >> 6), sat16((v.z + 32) >> 6));
 }
 
-// ---- k_mb_warp: grid (ceil(max_area/256), cameras) ----
+// ---- k_mb_warp: one CTA per 256-pixel chunk of a camera's bordered level-0 image that has a valid entry ----
 __global__ void __launch_bounds__(256) k_mb_warp(const __grid_constant__ MbParams p)
 {
-    const int c = blockIdx.y;
+    const uint2 wc = __ldg(p.warp_chunks + blockIdx.x);     // chunks without any valid entry are never launched: they stay 0
+    const int c = (int)wc.x;
     const MbCam& cam = p.cam[c];
-    const unsigned t = blockIdx.x * 256 + threadIdx.x;
+    const unsigned t = wc.y * 256 + threadIdx.x;
     if (t >= (unsigned)(cam.bw * cam.bh)) return;
     const uint2 cc = __ldg(p.coords + cam.off_g[0] + t);
     uint32_t px = 0;
@@ -143,14 +148,54 @@ template <class T> __device__ __forceinline__ int3 pyrdown_at(const T* s, int sw
     return make_int3(sat16((acc.x + 128) >> 8), sat16((acc.y + 128) >> 8), sat16((acc.z + 128) >> 8));
 }
 
+// Tiled, separable version: a CTA produces a 32 x 8 tile of level l+1 from the 67 x 19 source tile it stages in shared
+// memory (REFLECT_101 applied while loading), first the five-tap horizontal sums of all 19 rows, then the vertical sums.
+// Integer arithmetic, so the separable order gives the same numbers as the 5 x 5 form of pyrdown_at (pyramids.cpp:849-964).
+constexpr int DN_W = 32, DN_H = 8, DN_SW = 2 * DN_W + 3, DN_SH = 2 * DN_H + 3;
+template <class T> __device__ __forceinline__ void mb_down_tile(const T* __restrict__ src, short4* __restrict__ dst, int sw, int sh, int dw, int dh,
+                                                                int (&s_in)[3][DN_SH][DN_SW + 1], int (&s_h)[3][DN_SH][DN_W])
+{
+    const int tx = threadIdx.x, ty = threadIdx.y, tid = ty * DN_W + tx;
+    const int ox = blockIdx.x * DN_W, oy = blockIdx.y * DN_H;
+    const int ix0 = 2 * ox - 2, iy0 = 2 * oy - 2;
+    const bool interior = ix0 >= 0 && iy0 >= 0 && ix0 + DN_SW <= sw && iy0 + DN_SH <= sh;
+    for (int e = tid; e < DN_SW * DN_SH; e += DN_W * DN_H) {
+        const int r = e / DN_SW, c = e - r * DN_SW;
+        int gx = ix0 + c, gy = iy0 + r;
+        if (!interior) { gx = refl101(gx, sw); gy = refl101(gy, sh); }
+        const int3 v = ld3(src, gy * sw + gx);
+        s_in[0][r][c] = v.x; s_in[1][r][c] = v.y; s_in[2][r][c] = v.z;
+    }
+    __syncthreads();
+    #pragma unroll
+    for (int r = ty; r < DN_SH; r += DN_H) {
+        #pragma unroll
+        for (int ch = 0; ch < 3; ch++) {
+            const int* q = &s_in[ch][r][2 * tx];
+            s_h[ch][r][tx] = q[0] + 4 * q[1] + 6 * q[2] + 4 * q[3] + q[4];
+        }
+    }
+    __syncthreads();
+    const int x = ox + tx, y = oy + ty;
+    if (x >= dw || y >= dh) return;
+    int o[3];
+    #pragma unroll
+    for (int ch = 0; ch < 3; ch++) {
+        const int acc = s_h[ch][2 * ty][tx] + 4 * s_h[ch][2 * ty + 1][tx] + 6 * s_h[ch][2 * ty + 2][tx] + 4 * s_h[ch][2 * ty + 3][tx] + s_h[ch][2 * ty + 4][tx];
+        o[ch] = sat16((acc + 128) >> 8);
+    }
+    dst[(size_t)y * dw + x] = make_short4((short)o[0], (short)o[1], (short)o[2], 0);
+}
+
 __global__ void __launch_bounds__(256) k_mb_down(const __grid_constant__ MbParams p, int l)
 {
     const MbCam& cam = p.cam[blockIdx.z];
     const int sw = cam.bw >> l, sh = cam.bh >> l, dw = sw >> 1, dh = sh >> 1;
-    const int x = blockIdx.x * 32 + threadIdx.x, y = blockIdx.y * 8 + threadIdx.y;
-    if (x >= dw || y >= dh) return;
-    const int3 v = l == 0 ? pyrdown_at(p.g0 + cam.off_g[0], sw, sh, x, y) : pyrdown_at(p.g + cam.off_g[l], sw, sh, x, y);
-    p.g[cam.off_g[l + 1] + (size_t)y * dw + x] = make_short4((short)v.x, (short)v.y, (short)v.z, 0);
+    if ((int)(blockIdx.x * DN_W) >= dw || (int)(blockIdx.y * DN_H) >= dh) return;       // CTA outside this (smaller) camera
+    __shared__ int s_in[3][DN_SH][DN_SW + 1];
+    __shared__ int s_h[3][DN_SH][DN_W];
+    if (l == 0) mb_down_tile(p.g0 + cam.off_g[0], p.g + cam.off_g[1], sw, sh, dw, dh, s_in, s_h);
+    else mb_down_tile(p.g + cam.off_g[l], p.g + cam.off_g[l + 1], sw, sh, dw, dh, s_in, s_h);
 }
 
 // ---- k_mb_band: one thread per pixel of destination level l ----
@@ -160,7 +205,11 @@ __global__ void __launch_bounds__(256) k_mb_band(const __grid_constant__ MbParam
     const int lw = p.lw[l], lh = p.lh[l];
     if (X >= lw || Y >= lh) return;
     int ar = 0, ag = 0, ab = 0;
-    for (int c = 0; c < p.n; c++) {
+    // only the cameras that have a non-zero weight somewhere in this 32 x 8 tile (at level 0 the weights are the hard seam
+    // masks: usually one camera); uniform over the CTA
+    unsigned cams = __ldg(p.tile_cams + p.off_t[l] + (size_t)blockIdx.y * gridDim.x + blockIdx.x);
+    for (; cams; cams &= cams - 1) {
+        const int c = __ffs(cams) - 1;
         const MbCam& cam = p.cam[c];
         const int x = X - (cam.x0 >> l), y = Y - (cam.y0 >> l);
         const int w_l = cam.bw >> l, h_l = cam.bh >> l;
@@ -290,6 +339,13 @@ Multiband* multiband_create(octvr_mapper& m, const octvr_template& t,
         p.off_d[l] = doff; doff += (size_t)p.lw[l] * p.lh[l];
     }
     std::vector<float> dstw(doff, 0.f);
+    std::vector<uint2> chunks;                              // k_mb_warp work list
+    std::vector<uint16_t> tile_cams;                        // k_mb_band camera masks
+    {
+        size_t toff = 0;
+        for (int l = 0; l <= nb; l++) { p.off_t[l] = toff; toff += (size_t)((p.lw[l] + 31) / 32) * ((p.lh[l] + 7) / 8); }
+        tile_cams.assign(toff, 0);
+    }
     std::vector<uint2> coords;
     std::vector<float> wts;
     size_t g0_total = 0, g_total = 0;
@@ -325,6 +381,11 @@ Multiband* multiband_create(octvr_mapper& m, const octvr_template& t,
                 if (in_y && x - left >= 0 && x - left < in.roi.w) wmap.row(y)[x] = seams[i].row(y - top)[x - left] * inv255 + 0.f;
             }
         }
+        for (size_t k = 0; k < ((size_t)width * height + 255) / 256; k++) {
+            bool any = false;
+            for (size_t e = k * 256; e < std::min((k + 1) * 256, (size_t)width * height) && !any; e++) any = (ce[e].y & C_VALID) != 0;
+            if (any) chunks.push_back(make_uint2((uint32_t)i, (uint32_t)k));
+        }
         Img<float> wl = std::move(wmap);
         int xt = c.x0, yt = c.y0;
         for (int l = 0; l <= nb; l++) {
@@ -333,7 +394,10 @@ Multiband* multiband_create(octvr_mapper& m, const octvr_template& t,
             for (int y = 0; y < wl.h; y++) {                        // dst_band_weights_[l](rc) += weight (blenders.cpp:421)
                 float* dr = dstw.data() + p.off_d[l] + (size_t)(yt + y) * p.lw[l] + xt;
                 const float* wr = wl.row(y);
-                for (int x = 0; x < wl.w; x++) dr[x] += wr[x];
+                for (int x = 0; x < wl.w; x++) {
+                    dr[x] += wr[x];
+                    if (wr[x] != 0.f) tile_cams[p.off_t[l] + (size_t)((yt + y) / 8) * ((p.lw[l] + 31) / 32) + (xt + x) / 32] |= (uint16_t)(1u << i);
+                }
             }
             if (l < nb) wl = pyrdown_f32(wl);
             xt /= 2; yt /= 2;
@@ -342,7 +406,11 @@ Multiband* multiband_create(octvr_mapper& m, const octvr_template& t,
     mb->d_coords = upload(coords);
     mb->d_w = upload(wts);
     mb->d_dstw = upload(dstw);
+    mb->d_chunks = upload(chunks); mb->n_chunks = (unsigned)chunks.size();
+    mb->d_tile_cams = upload(tile_cams);
+    p.warp_chunks = mb->d_chunks; p.tile_cams = mb->d_tile_cams;
     OB_CUDA(cudaMalloc(&mb->d_g0, std::max<size_t>(g0_total, 1) * sizeof(uint32_t)));
+    OB_CUDA(cudaMemset(mb->d_g0, 0, std::max<size_t>(g0_total, 1) * sizeof(uint32_t)));       // chunks without valid entries stay 0
     OB_CUDA(cudaMalloc(&mb->d_g, std::max<size_t>(g_total, 1) * sizeof(short4)));
     OB_CUDA(cudaMalloc(&mb->d_dst, std::max<size_t>(doff, 1) * sizeof(short4)));
     p.coords = mb->d_coords; p.g0 = mb->d_g0; p.g = mb->d_g; p.w = mb->d_w; p.dst = mb->d_dst; p.dstw = mb->d_dstw;
@@ -364,7 +432,7 @@ void multiband_stitch(octvr_mapper& m, const octvr_frame* out, cudaStream_t s)
     }
     p.rgb_out = m.keep_rgb ? m.d_rgb : nullptr; p.rgb_pitch = (uint32_t)m.out_w * 3;
     const int nb = p.nb, n = p.n;
-    k_mb_warp<<<dim3(((size_t)mb.max_bw * mb.max_bh + 255) / 256, n), 256, 0, s>>>(p);
+    if (mb.n_chunks) k_mb_warp<<<mb.n_chunks, 256, 0, s>>>(p);
     for (int l = 0; l < nb; l++)
         k_mb_down<<<dim3(((mb.max_bw >> (l + 1)) + 31) / 32, ((mb.max_bh >> (l + 1)) + 7) / 8, n), dim3(32, 8), 0, s>>>(p, l);
     for (int l = nb; l >= 0; l--)
@@ -379,7 +447,7 @@ int multiband_launches(const octvr_mapper& m) { return m.mb ? m.mb->launches : 0
 void multiband_destroy(Multiband* mb)
 {
     if (!mb) return;
-    cudaFree(mb->d_coords); cudaFree(mb->d_g0); cudaFree(mb->d_g); cudaFree(mb->d_w); cudaFree(mb->d_dst); cudaFree(mb->d_dstw);
+    cudaFree(mb->d_chunks); cudaFree(mb->d_tile_cams); cudaFree(mb->d_coords); cudaFree(mb->d_g0); cudaFree(mb->d_g); cudaFree(mb->d_w); cudaFree(mb->d_dst); cudaFree(mb->d_dstw);
     delete mb;
 }
 
