@@ -101,6 +101,44 @@ template <class T> __device__ int3 pyrup_at(const T* s, int sw, int sh, int x, i
     return make_int3(sat16((v.x + 32) >> 6), sat16((v.y + 32) >> 6), sat16((v.z + 32) >> 6));
 }
 
+// ---- pyrUp of FOUR horizontally adjacent pixels by one thread ----
+// pyrUp_ (pyramids.cpp:967-1060) is a separable [1 6 1 | 4 4] filter whose border cases are index extensions: -1 maps to
+// 1 (0 for a single sample) and len maps to len - 1 -- exactly the special cases of pyrup_at above.  Four neighbours share
+// their source samples: 12 loads and a third of the arithmetic instead of 4 x 9 loads.  x0 may be even or odd.
+__device__ __forceinline__ int up_idx(int k, int len) { return k < 0 ? (len > 1 ? 1 : 0) : (k >= len ? len - 1 : k); }
+__device__ __forceinline__ int3 add3(int3 a, int3 b) { return make_int3(a.x + b.x, a.y + b.y, a.z + b.z); }
+__device__ __forceinline__ int3 mul3(int3 a, int k) { return make_int3(a.x * k, a.y * k, a.z * k); }
+template <class T> __device__ __forceinline__ void pyrup_row4(const T* __restrict__ s, int sw, int r, int x0, int3 (&h)[4])
+{
+    const T* row = s + (size_t)r * sw;
+    const int k = x0 >> 1;
+    if ((x0 & 1) == 0) {
+        const int3 a = ld3(row, up_idx(k - 1, sw)), b = ld3(row, up_idx(k, sw)), c = ld3(row, up_idx(k + 1, sw)), d = ld3(row, up_idx(k + 2, sw));
+        h[0] = add3(add3(a, mul3(b, 6)), c); h[1] = mul3(add3(b, c), 4); h[2] = add3(add3(b, mul3(c, 6)), d); h[3] = mul3(add3(c, d), 4);
+    } else {
+        const int3 a = ld3(row, up_idx(k, sw)), b = ld3(row, up_idx(k + 1, sw)), c = ld3(row, up_idx(k + 2, sw)), d = ld3(row, up_idx(k + 3, sw));
+        h[0] = mul3(add3(a, b), 4); h[1] = add3(add3(a, mul3(b, 6)), c); h[2] = mul3(add3(b, c), 4); h[3] = add3(add3(b, mul3(c, 6)), d);
+    }
+}
+template <class T> __device__ __forceinline__ void pyrup4(const T* __restrict__ s, int sw, int sh, int x0, int y, int3 (&out)[4])
+{
+    const int ky = y >> 1;
+    int3 h1[4], h2[4];
+    pyrup_row4(s, sw, up_idx(ky, sh), x0, h1);
+    pyrup_row4(s, sw, up_idx(ky + 1, sh), x0, h2);
+    if ((y & 1) == 0) {
+        int3 h0[4];
+        pyrup_row4(s, sw, up_idx(ky - 1, sh), x0, h0);
+        #pragma unroll
+        for (int q = 0; q < 4; q++) out[q] = add3(add3(h0[q], mul3(h1[q], 6)), h2[q]);
+    } else {
+        #pragma unroll
+        for (int q = 0; q < 4; q++) out[q] = mul3(add3(h1[q], h2[q]), 4);
+    }
+    #pragma unroll
+    for (int q = 0; q < 4; q++) out[q] = make_int3(sat16((out[q].x + 32) >> 6), sat16((out[q].y + 32) >> 6), sat16((out[q].z + 32) >> 6));
+}
+
 // ---- k_mb_warp: one CTA per 256-pixel chunk of a camera's bordered level-0 image that has a valid entry ----
 __global__ void __launch_bounds__(256) k_mb_warp(const __grid_constant__ MbParams p)
 {
@@ -198,85 +236,135 @@ __global__ void __launch_bounds__(256) k_mb_down(const __grid_constant__ MbParam
     else mb_down_tile(p.g + cam.off_g[l], p.g + cam.off_g[l + 1], sw, sh, dw, dh, s_in, s_h);
 }
 
-// ---- k_mb_band: one thread per pixel of destination level l ----
+// ---- k_mb_band: one thread per FOUR horizontally adjacent pixels of destination level l (CTA = 128 x 8 pixels) ----
 __global__ void __launch_bounds__(256) k_mb_band(const __grid_constant__ MbParams p, int l)
 {
-    const int X = blockIdx.x * 32 + threadIdx.x, Y = blockIdx.y * 8 + threadIdx.y;
+    const int X0 = (blockIdx.x * 32 + threadIdx.x) * 4, Y = blockIdx.y * 8 + threadIdx.y;
     const int lw = p.lw[l], lh = p.lh[l];
-    if (X >= lw || Y >= lh) return;
-    int ar = 0, ag = 0, ab = 0;
-    // only the cameras that have a non-zero weight somewhere in this 32 x 8 tile (at level 0 the weights are the hard seam
-    // masks: usually one camera); uniform over the CTA
-    unsigned cams = __ldg(p.tile_cams + p.off_t[l] + (size_t)blockIdx.y * gridDim.x + blockIdx.x);
+    // only the cameras that have a non-zero weight somewhere in the CTA's four 32 x 8 tiles (at level 0 the weights are the
+    // hard seam masks: usually one camera); uniform over the CTA
+    unsigned cams = 0;
+    {
+        const int tiles_x = (lw + 31) / 32;
+        const uint16_t* tm = p.tile_cams + p.off_t[l] + (size_t)blockIdx.y * tiles_x;
+        #pragma unroll
+        for (int k = 0; k < 4; k++) if ((int)blockIdx.x * 4 + k < tiles_x) cams |= __ldg(tm + blockIdx.x * 4 + k);
+    }
+    if (X0 >= lw || Y >= lh) return;
+    int acc[4][3];
+    #pragma unroll
+    for (int q = 0; q < 4; q++) acc[q][0] = acc[q][1] = acc[q][2] = 0;
     for (; cams; cams &= cams - 1) {
         const int c = __ffs(cams) - 1;
         const MbCam& cam = p.cam[c];
-        const int x = X - (cam.x0 >> l), y = Y - (cam.y0 >> l);
+        const int x0 = X0 - (cam.x0 >> l), y = Y - (cam.y0 >> l);
         const int w_l = cam.bw >> l, h_l = cam.bh >> l;
-        if (x < 0 || y < 0 || x >= w_l || y >= h_l) continue;
-        const float w = __ldg(p.w + cam.off_w[l] + (size_t)y * w_l + x);
-        if (w == 0.f) continue;                                       // (short)(lap * 0) == 0
-        int3 gl = l == 0 ? ld3(p.g0 + cam.off_g[0], y * w_l + x) : ld3(p.g + cam.off_g[l], y * w_l + x);
-        if (l < p.nb) {                                               // createLaplacePyr: pyr[l] -= pyrUp(pyr[l+1]), saturating 16S
-            const int3 up = pyrup_at(p.g + cam.off_g[l + 1], w_l >> 1, h_l >> 1, x, y);
-            gl = make_int3(sat16(gl.x - up.x), sat16(gl.y - up.y), sat16(gl.z - up.z));
+        if (y < 0 || y >= h_l || x0 + 3 < 0 || x0 >= w_l) continue;
+        float w[4];
+        bool any = false;
+        #pragma unroll
+        for (int q = 0; q < 4; q++) {
+            const int x = x0 + q;
+            w[q] = (x >= 0 && x < w_l) ? __ldg(p.w + cam.off_w[l] + (size_t)y * w_l + x) : 0.f;
+            any = any || w[q] != 0.f;                                 // (short)(lap * 0) == 0
         }
-        // dst += static_cast<short>(lap * weight): f32 product truncated toward zero (blenders.cpp:418-420)
-        ar += __float2int_rz(__fmul_rn((float)gl.x, w));
-        ag += __float2int_rz(__fmul_rn((float)gl.y, w));
-        ab += __float2int_rz(__fmul_rn((float)gl.z, w));
+        if (!any) continue;
+        int3 up[4];
+        if (l < p.nb) pyrup4(p.g + cam.off_g[l + 1], w_l >> 1, h_l >> 1, x0, y, up);     // x0 is even here: camera rects are 2^bands aligned
+        #pragma unroll
+        for (int q = 0; q < 4; q++) {
+            if (w[q] == 0.f) continue;
+            const int x = x0 + q;
+            int3 gl = l == 0 ? ld3(p.g0 + cam.off_g[0], y * w_l + x) : ld3(p.g + cam.off_g[l], y * w_l + x);
+            if (l < p.nb)                                             // createLaplacePyr: pyr[l] -= pyrUp(pyr[l+1]), saturating 16S
+                gl = make_int3(sat16(gl.x - up[q].x), sat16(gl.y - up[q].y), sat16(gl.z - up[q].z));
+            // dst += static_cast<short>(lap * weight): f32 product truncated toward zero (blenders.cpp:418-420)
+            acc[q][0] += __float2int_rz(__fmul_rn((float)gl.x, w[q]));
+            acc[q][1] += __float2int_rz(__fmul_rn((float)gl.y, w[q]));
+            acc[q][2] += __float2int_rz(__fmul_rn((float)gl.z, w[q]));
+        }
     }
-    const size_t di = p.off_d[l] + (size_t)Y * lw + X;
-    // normalizeUsingWeightMap (blenders.cpp:788-797): (short)(v / (w + 1e-5f))
-    const float den = __fadd_rn(__ldg(p.dstw + di), 1e-5f);
-    const short r = (short)__float2int_rz(__fdiv_rn((float)(short)ar, den));
-    const short g = (short)__float2int_rz(__fdiv_rn((float)(short)ag, den));
-    const short b = (short)__float2int_rz(__fdiv_rn((float)(short)ab, den));
-    p.dst[di] = make_short4(r, g, b, 0);
+    #pragma unroll
+    for (int q = 0; q < 4; q++) {
+        if (X0 + q >= lw) break;
+        const size_t di = p.off_d[l] + (size_t)Y * lw + X0 + q;
+        // normalizeUsingWeightMap (blenders.cpp:788-797): (short)(v / (w + 1e-5f))
+        const float den = __fadd_rn(__ldg(p.dstw + di), 1e-5f);
+        const short r = (short)__float2int_rz(__fdiv_rn((float)(short)acc[q][0], den));
+        const short g = (short)__float2int_rz(__fdiv_rn((float)(short)acc[q][1], den));
+        const short b = (short)__float2int_rz(__fdiv_rn((float)(short)acc[q][2], den));
+        p.dst[di] = make_short4(r, g, b, 0);
+    }
 }
 
-// ---- k_mb_collapse: dst_{l-1} = sat(pyrUp(dst_l) + dst_{l-1}), l >= 2 ----
+// ---- k_mb_collapse: dst_{l-1} = sat(pyrUp(dst_l) + dst_{l-1}), l >= 2; four pixels per thread ----
 __global__ void __launch_bounds__(256) k_mb_collapse(const __grid_constant__ MbParams p, int l)
 {
-    const int X = blockIdx.x * 32 + threadIdx.x, Y = blockIdx.y * 8 + threadIdx.y;
+    const int X0 = (blockIdx.x * 32 + threadIdx.x) * 4, Y = blockIdx.y * 8 + threadIdx.y;
     const int w = p.lw[l - 1], h = p.lh[l - 1];
-    if (X >= w || Y >= h) return;
-    const int3 up = pyrup_at(p.dst + p.off_d[l], p.lw[l], p.lh[l], X, Y);
-    const size_t di = p.off_d[l - 1] + (size_t)Y * w + X;
-    const short4 cur = p.dst[di];
-    p.dst[di] = make_short4((short)sat16(up.x + cur.x), (short)sat16(up.y + cur.y), (short)sat16(up.z + cur.z), 0);
+    if (X0 >= w || Y >= h) return;
+    int3 up[4];
+    pyrup4(p.dst + p.off_d[l], p.lw[l], p.lh[l], X0, Y, up);
+    #pragma unroll
+    for (int q = 0; q < 4; q++) {
+        if (X0 + q >= w) break;
+        const size_t di = p.off_d[l - 1] + (size_t)Y * w + X0 + q;
+        const short4 cur = p.dst[di];
+        p.dst[di] = make_short4((short)sat16(up[q].x + cur.x), (short)sat16(up[q].y + cur.y), (short)sat16(up[q].z + cur.z), 0);
+    }
 }
 
-// ---- k_mb_final: level 1 -> 0 collapse fused with mask, 8-bit narrowing and the output store; one thread per
-//      OUTPUT-FRAME pixel (pixels outside the result roi are black) ----
+// ---- k_mb_final: level 1 -> 0 collapse fused with mask, 8-bit narrowing and the output store; one thread per FOUR
+//      OUTPUT-FRAME pixels (pixels outside the result roi are black) ----
 __global__ void __launch_bounds__(256) k_mb_final(const __grid_constant__ MbParams p)
 {
-    const int X = blockIdx.x * 32 + threadIdx.x, Y = blockIdx.y * 8 + threadIdx.y;
-    if (X >= p.out_w || Y >= p.out_h) return;
-    int R = 0, G = 0, B = 0;
-    const int x = X - p.rx, y = Y - p.ry;
-    if (x >= 0 && y >= 0 && x < p.rw && y < p.rh) {
-        const size_t di = p.off_d[0] + (size_t)y * p.lw[0] + x;
-        if (__ldg(p.dstw + di) > 1e-5f) {                              // dst_mask = dst_band_weights_[0] > WEIGHT_EPS (blenders.cpp:472)
-            short4 cur = p.dst[di];
-            int3 v = make_int3(cur.x, cur.y, cur.z);
-            if (p.nb > 0) {
-                const int3 up = pyrup_at(p.dst + p.off_d[1], p.lw[1], p.lh[1], x, y);
-                v = make_int3(sat16(up.x + v.x), sat16(up.y + v.y), sat16(up.z + v.z));
+    const int X0 = (blockIdx.x * 32 + threadIdx.x) * 4, Y = blockIdx.y * 8 + threadIdx.y;
+    if (X0 >= p.out_w || Y >= p.out_h) return;
+    int R[4], G[4], B[4];
+    #pragma unroll
+    for (int q = 0; q < 4; q++) R[q] = G[q] = B[q] = 0;
+    const int x0 = X0 - p.rx, y = Y - p.ry;
+    if (y >= 0 && y < p.rh && x0 + 3 >= 0 && x0 < p.rw) {
+        float dw[4];
+        bool any = false;
+        #pragma unroll
+        for (int q = 0; q < 4; q++) {
+            const int x = x0 + q;
+            dw[q] = (x >= 0 && x < p.rw) ? __ldg(p.dstw + p.off_d[0] + (size_t)y * p.lw[0] + x) : 0.f;
+            any = any || dw[q] > 1e-5f;                                // dst_mask = dst_band_weights_[0] > WEIGHT_EPS (blenders.cpp:472)
+        }
+        if (any) {
+            int3 up[4];
+            if (p.nb > 0) pyrup4(p.dst + p.off_d[1], p.lw[1], p.lh[1], x0, y, up);
+            #pragma unroll
+            for (int q = 0; q < 4; q++) {
+                if (!(dw[q] > 1e-5f)) continue;
+                const short4 cur = p.dst[p.off_d[0] + (size_t)y * p.lw[0] + x0 + q];
+                int3 v = make_int3(cur.x, cur.y, cur.z);
+                if (p.nb > 0) v = make_int3(sat16(up[q].x + v.x), sat16(up[q].y + v.y), sat16(up[q].z + v.z));
+                R[q] = clamp255(v.x); G[q] = clamp255(v.y); B[q] = clamp255(v.z);   // convertTo(CV_8U)
             }
-            R = clamp255(v.x); G = clamp255(v.y); B = clamp255(v.z);   // convertTo(CV_8U)
         }
     }
+    const bool full = X0 + 3 < p.out_w;
     if (p.rgb_out) {
-        uint8_t* o = p.rgb_out + (size_t)Y * p.rgb_pitch + 3 * X;
-        o[0] = (uint8_t)R; o[1] = (uint8_t)G; o[2] = (uint8_t)B;
+        uint8_t* o = p.rgb_out + (size_t)Y * p.rgb_pitch + 3 * X0;
+        #pragma unroll
+        for (int q = 0; q < 4; q++) if (X0 + q < p.out_w) { o[3 * q] = (uint8_t)R[q]; o[3 * q + 1] = (uint8_t)G[q]; o[3 * q + 2] = (uint8_t)B[q]; }
     }
     if (p.oy) {
-        p.oy[(size_t)Y * p.oy_pitch + X] = (uint8_t)rgb_luma(R, G, B);
-        if (((X | Y) & 1) == 0) {
-            const size_t co = (size_t)(X >> 1) * p.uv_step;
-            p.ou[(size_t)(Y >> 1) * p.ou_pitch + co] = (uint8_t)rgb_cb(R, G, B);
-            p.ov[(size_t)(Y >> 1) * p.ov_pitch + co] = (uint8_t)rgb_cr(R, G, B);
+        uint8_t* oyp = p.oy + (size_t)Y * p.oy_pitch + X0;
+        const uint32_t l4 = rgb_luma(R[0], G[0], B[0]) | (rgb_luma(R[1], G[1], B[1]) << 8) | (rgb_luma(R[2], G[2], B[2]) << 16) | (rgb_luma(R[3], G[3], B[3]) << 24);
+        if (full && (((uintptr_t)oyp) & 3) == 0) *reinterpret_cast<uint32_t*>(oyp) = l4;
+        else for (int q = 0; q < 4 && X0 + q < p.out_w; q++) oyp[q] = (uint8_t)(l4 >> (8 * q));
+        if ((Y & 1) == 0) {                                            // X0 is even: chroma from pixels 0 and 2 of the group
+            #pragma unroll
+            for (int q = 0; q < 4; q += 2) {
+                if (X0 + q >= p.out_w) break;
+                const size_t co = (size_t)((X0 + q) >> 1) * p.uv_step;
+                p.ou[(size_t)(Y >> 1) * p.ou_pitch + co] = (uint8_t)rgb_cb(R[q], G[q], B[q]);
+                p.ov[(size_t)(Y >> 1) * p.ov_pitch + co] = (uint8_t)rgb_cr(R[q], G[q], B[q]);
+            }
         }
     }
 }
@@ -436,10 +524,10 @@ void multiband_stitch(octvr_mapper& m, const octvr_frame* out, cudaStream_t s)
     for (int l = 0; l < nb; l++)
         k_mb_down<<<dim3(((mb.max_bw >> (l + 1)) + 31) / 32, ((mb.max_bh >> (l + 1)) + 7) / 8, n), dim3(32, 8), 0, s>>>(p, l);
     for (int l = nb; l >= 0; l--)
-        k_mb_band<<<dim3((p.lw[l] + 31) / 32, (p.lh[l] + 7) / 8), dim3(32, 8), 0, s>>>(p, l);
+        k_mb_band<<<dim3((p.lw[l] + 127) / 128, (p.lh[l] + 7) / 8), dim3(32, 8), 0, s>>>(p, l);
     for (int l = nb; l >= 2; l--)
-        k_mb_collapse<<<dim3((p.lw[l - 1] + 31) / 32, (p.lh[l - 1] + 7) / 8), dim3(32, 8), 0, s>>>(p, l);
-    k_mb_final<<<dim3((p.out_w + 31) / 32, (p.out_h + 7) / 8), dim3(32, 8), 0, s>>>(p);
+        k_mb_collapse<<<dim3((p.lw[l - 1] + 127) / 128, (p.lh[l - 1] + 7) / 8), dim3(32, 8), 0, s>>>(p, l);
+    k_mb_final<<<dim3((p.out_w + 127) / 128, (p.out_h + 7) / 8), dim3(32, 8), 0, s>>>(p);
 }
 
 int multiband_launches(const octvr_mapper& m) { return m.mb ? m.mb->launches : 0; }
