@@ -186,54 +186,47 @@ template <class T> __device__ __forceinline__ int3 pyrdown_at(const T* s, int sw
     return make_int3(sat16((acc.x + 128) >> 8), sat16((acc.y + 128) >> 8), sat16((acc.z + 128) >> 8));
 }
 
-// Tiled, separable version: a CTA produces a 32 x 8 tile of level l+1 from the 67 x 19 source tile it stages in shared
-// memory (REFLECT_101 applied while loading), first the five-tap horizontal sums of all 19 rows, then the vertical sums.
-// Integer arithmetic, so the separable order gives the same numbers as the 5 x 5 form of pyrdown_at (pyramids.cpp:849-964).
-constexpr int DN_W = 32, DN_H = 8, DN_SW = 2 * DN_W + 3, DN_SH = 2 * DN_H + 3;
-template <class T> __device__ __forceinline__ void mb_down_tile(const T* __restrict__ src, short4* __restrict__ dst, int sw, int sh, int dw, int dh,
-                                                                int (&s_in)[3][DN_SH][DN_SW + 1], int (&s_h)[3][DN_SH][DN_W])
+// Column-strip version: a thread produces FOUR vertically adjacent pixels of level l+1.  It walks the 11 source rows they
+// depend on, forms the five-tap horizontal sum of each row once and scatters it (x 1, 4, 6, 4, 1) into the outputs that use
+// the row -- 55 loads for four outputs instead of 100, no shared memory, no barrier.  Integer arithmetic, so the separable
+// order gives the same numbers as the 5 x 5 form of pyrdown_at (pyramids.cpp:849-964).  Threads of a warp walk adjacent
+// columns, so every load instruction is a contiguous (stride-2) row segment.
+template <class T> __device__ __forceinline__ void mb_down_strip(const T* __restrict__ src, short4* __restrict__ dst, int sw, int sh, int dw, int dh, int x, int y0)
 {
-    const int tx = threadIdx.x, ty = threadIdx.y, tid = ty * DN_W + tx;
-    const int ox = blockIdx.x * DN_W, oy = blockIdx.y * DN_H;
-    const int ix0 = 2 * ox - 2, iy0 = 2 * oy - 2;
-    const bool interior = ix0 >= 0 && iy0 >= 0 && ix0 + DN_SW <= sw && iy0 + DN_SH <= sh;
-    for (int e = tid; e < DN_SW * DN_SH; e += DN_W * DN_H) {
-        const int r = e / DN_SW, c = e - r * DN_SW;
-        int gx = ix0 + c, gy = iy0 + r;
-        if (!interior) { gx = refl101(gx, sw); gy = refl101(gy, sh); }
-        const int3 v = ld3(src, gy * sw + gx);
-        s_in[0][r][c] = v.x; s_in[1][r][c] = v.y; s_in[2][r][c] = v.z;
-    }
-    __syncthreads();
+    int xi[5];
     #pragma unroll
-    for (int r = ty; r < DN_SH; r += DN_H) {
+    for (int k = 0; k < 5; k++) xi[k] = refl101(2 * x + k - 2, sw);
+    int acc[4][3];
+    #pragma unroll
+    for (int j = 0; j < 4; j++) acc[j][0] = acc[j][1] = acc[j][2] = 0;
+    #pragma unroll
+    for (int r = 0; r < 11; r++) {
+        if (r >= 5 && y0 + (r - 3) / 2 >= dh) break;                  // rows only the missing outputs of a ragged strip would use
+        const T* row = src + (size_t)refl101(2 * y0 - 2 + r, sh) * sw;
+        const int3 a = ld3(row, xi[0]), b = ld3(row, xi[1]), c = ld3(row, xi[2]), d = ld3(row, xi[3]), e = ld3(row, xi[4]);
+        const int hx = a.x + e.x + 4 * (b.x + d.x) + 6 * c.x, hy = a.y + e.y + 4 * (b.y + d.y) + 6 * c.y, hz = a.z + e.z + 4 * (b.z + d.z) + 6 * c.z;
         #pragma unroll
-        for (int ch = 0; ch < 3; ch++) {
-            const int* q = &s_in[ch][r][2 * tx];
-            s_h[ch][r][tx] = q[0] + 4 * q[1] + 6 * q[2] + 4 * q[3] + q[4];
+        for (int j = 0; j < 4; j++) {
+            const int t = r - 2 * j;                                  // tap of output j that reads this row
+            if (t < 0 || t > 4) continue;
+            const int kw = t == 2 ? 6 : (t == 1 || t == 3) ? 4 : 1;
+            acc[j][0] += kw * hx; acc[j][1] += kw * hy; acc[j][2] += kw * hz;
         }
     }
-    __syncthreads();
-    const int x = ox + tx, y = oy + ty;
-    if (x >= dw || y >= dh) return;
-    int o[3];
     #pragma unroll
-    for (int ch = 0; ch < 3; ch++) {
-        const int acc = s_h[ch][2 * ty][tx] + 4 * s_h[ch][2 * ty + 1][tx] + 6 * s_h[ch][2 * ty + 2][tx] + 4 * s_h[ch][2 * ty + 3][tx] + s_h[ch][2 * ty + 4][tx];
-        o[ch] = sat16((acc + 128) >> 8);
-    }
-    dst[(size_t)y * dw + x] = make_short4((short)o[0], (short)o[1], (short)o[2], 0);
+    for (int j = 0; j < 4; j++)
+        if (y0 + j < dh)
+            dst[(size_t)(y0 + j) * dw + x] = make_short4((short)sat16((acc[j][0] + 128) >> 8), (short)sat16((acc[j][1] + 128) >> 8), (short)sat16((acc[j][2] + 128) >> 8), 0);
 }
 
 __global__ void __launch_bounds__(256) k_mb_down(const __grid_constant__ MbParams p, int l)
 {
     const MbCam& cam = p.cam[blockIdx.z];
     const int sw = cam.bw >> l, sh = cam.bh >> l, dw = sw >> 1, dh = sh >> 1;
-    if ((int)(blockIdx.x * DN_W) >= dw || (int)(blockIdx.y * DN_H) >= dh) return;       // CTA outside this (smaller) camera
-    __shared__ int s_in[3][DN_SH][DN_SW + 1];
-    __shared__ int s_h[3][DN_SH][DN_W];
-    if (l == 0) mb_down_tile(p.g0 + cam.off_g[0], p.g + cam.off_g[1], sw, sh, dw, dh, s_in, s_h);
-    else mb_down_tile(p.g + cam.off_g[l], p.g + cam.off_g[l + 1], sw, sh, dw, dh, s_in, s_h);
+    const int x = blockIdx.x * 32 + threadIdx.x, y0 = (blockIdx.y * 8 + threadIdx.y) * 4;
+    if (x >= dw || y0 >= dh) return;
+    if (l == 0) mb_down_strip(p.g0 + cam.off_g[0], p.g + cam.off_g[1], sw, sh, dw, dh, x, y0);
+    else mb_down_strip(p.g + cam.off_g[l], p.g + cam.off_g[l + 1], sw, sh, dw, dh, x, y0);
 }
 
 // ---- k_mb_band: one thread per FOUR horizontally adjacent pixels of destination level l (CTA = 128 x 8 pixels) ----
@@ -522,7 +515,7 @@ void multiband_stitch(octvr_mapper& m, const octvr_frame* out, cudaStream_t s)
     const int nb = p.nb, n = p.n;
     if (mb.n_chunks) k_mb_warp<<<mb.n_chunks, 256, 0, s>>>(p);
     for (int l = 0; l < nb; l++)
-        k_mb_down<<<dim3(((mb.max_bw >> (l + 1)) + 31) / 32, ((mb.max_bh >> (l + 1)) + 7) / 8, n), dim3(32, 8), 0, s>>>(p, l);
+        k_mb_down<<<dim3(((mb.max_bw >> (l + 1)) + 31) / 32, ((mb.max_bh >> (l + 1)) + 31) / 32, n), dim3(32, 8), 0, s>>>(p, l);
     for (int l = nb; l >= 0; l--)
         k_mb_band<<<dim3((p.lw[l] + 127) / 128, (p.lh[l] + 7) / 8), dim3(32, 8), 0, s>>>(p, l);
     for (int l = nb; l >= 2; l--)
