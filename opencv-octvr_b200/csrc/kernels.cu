@@ -690,7 +690,8 @@ __global__ void __launch_bounds__(256, 7) k_blend_staged(const __grid_constant__
     if (tid == 0) { mbar_init(&s_mbar, 1); asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
     __syncthreads();
 
-    uint32_t ar0 = 0, ag0 = 0, ab0 = 0, ar1 = 0, ag1 = 0, ab1 = 0;
+    // sums of floor(v * W) <= 255 * MAX_CAMS < 2^16: R and G of a pixel share one accumulator, the two blue sums another
+    uint32_t arg0 = 0, arg1 = 0, abb = 0;
     const uint2* ep = p.entries + (size_t)j0 * TILE_PX + tid;
     uint2 e0 = make_uint2(0, 0), e1 = make_uint2(0, 0);
     if (nj > 0) { e0 = __ldcs(ep); e1 = __ldcs(ep + 256); }
@@ -713,36 +714,26 @@ __global__ void __launch_bounds__(256, 7) k_blend_staged(const __grid_constant__
         for (; k < kend; k++) {
             const uint2 a0 = e0, a1 = e1;
             if (k + 1 < nj) { ep += TILE_PX; e0 = __ldcs(ep); e1 = __ldcs(ep + 256); }
-            const int bw = s_job[k].bw;
+            const uint8_t* s0 = reinterpret_cast<const uint8_t*>(s_buf);
+            const uint8_t* s1 = s0 + s_job[k].bw * 4;
             const uint32_t g = s_gain[k];
-            const uint32_t o0 = a0.x & 0xFFFFu, o1 = a1.x & 0xFFFFu;
-            const uint32_t t00 = s_buf[o0], t01 = s_buf[o0 + 1], t10 = s_buf[o0 + bw], t11 = s_buf[o0 + bw + 1];
-            const uint32_t u00 = s_buf[o1], u01 = s_buf[o1 + 1], u10 = s_buf[o1 + bw], u11 = s_buf[o1 + bw + 1];
-            int r, gg, bb;
-            float rf, gf, bf;
-            const float w0 = __int_as_float((int)a0.y), w1 = __int_as_float((int)a1.y);
-            bilerp_rgbx(t00, t01, t10, t11, (a0.x >> 16) & 31u, (a0.x >> 21) & 31u, r, gg, bb);
-            rf = (float)r; gf = (float)gg; bf = (float)bb;
-            if (GAIN) {
-                if (g != 0xFFFFFFFFu) { const float g32 = __int_as_float((int)g); rf = gain_apply_f32(rf, g32); gf = gain_apply_f32(gf, g32); bf = gain_apply_f32(bf, g32); }
-                else { const uint8_t* lut = p.gain_lut + s_job[k].cam * 256; rf = (float)__ldg(lut + r); gf = (float)__ldg(lut + gg); bf = (float)__ldg(lut + bb); }
+            // the gather of device_common.cuh (fused_pair): floor / rint by magic-number adds on the FP32 pipe, IDP.2A bilinear
+            if (!GAIN) {
+                fused_pair<0, false, false>(a0.x, a0.y, s0, s1, 0.f, 0.f, nullptr, arg0, abb);
+                fused_pair<0, false, true>(a1.x, a1.y, s0, s1, 0.f, 0.f, nullptr, arg1, abb);
+            } else if (g != 0xFFFFFFFFu) {
+                const float g32 = __int_as_float((int)g), gb = gain_bias_f32(g32);
+                fused_pair<1, false, false>(a0.x, a0.y, s0, s1, g32, gb, nullptr, arg0, abb);
+                fused_pair<1, false, true>(a1.x, a1.y, s0, s1, g32, gb, nullptr, arg1, abb);
+            } else {
+                const uint8_t* lut = p.gain_lut + s_job[k].cam * 256;
+                fused_pair<1, true, false>(a0.x, a0.y, s0, s1, 0.f, 0.f, lut, arg0, abb);
+                fused_pair<1, true, true>(a1.x, a1.y, s0, s1, 0.f, 0.f, lut, arg1, abb);
             }
-            ar0 += (uint32_t)__float_as_int(__fadd_rd(__fmul_rn(rf, w0), MAGIC_RD)) - 0x4B000000u;
-            ag0 += (uint32_t)__float_as_int(__fadd_rd(__fmul_rn(gf, w0), MAGIC_RD)) - 0x4B000000u;
-            ab0 += (uint32_t)__float_as_int(__fadd_rd(__fmul_rn(bf, w0), MAGIC_RD)) - 0x4B000000u;
-            bilerp_rgbx(u00, u01, u10, u11, (a1.x >> 16) & 31u, (a1.x >> 21) & 31u, r, gg, bb);
-            rf = (float)r; gf = (float)gg; bf = (float)bb;
-            if (GAIN) {
-                if (g != 0xFFFFFFFFu) { const float g32 = __int_as_float((int)g); rf = gain_apply_f32(rf, g32); gf = gain_apply_f32(gf, g32); bf = gain_apply_f32(bf, g32); }
-                else { const uint8_t* lut = p.gain_lut + s_job[k].cam * 256; rf = (float)__ldg(lut + r); gf = (float)__ldg(lut + gg); bf = (float)__ldg(lut + bb); }
-            }
-            ar1 += (uint32_t)__float_as_int(__fadd_rd(__fmul_rn(rf, w1), MAGIC_RD)) - 0x4B000000u;
-            ag1 += (uint32_t)__float_as_int(__fadd_rd(__fmul_rn(gf, w1), MAGIC_RD)) - 0x4B000000u;
-            ab1 += (uint32_t)__float_as_int(__fadd_rd(__fmul_rn(bf, w1), MAGIC_RD)) - 0x4B000000u;
         }
         if (k < nj) { __syncthreads(); fence_proxy_async(); }   // the stage is refilled (async proxy) by the next group
     }
-    const uint32_t px0 = normalise_px(ar0, ag0, ab0, p.inv_n), px1 = normalise_px(ar1, ag1, ab1, p.inv_n);
+    const uint32_t px0 = normalise_px(arg0 & 0xFFFFu, arg0 >> 16, abb & 0xFFFFu, p.inv_n), px1 = normalise_px(arg1 & 0xFFFFu, arg1 >> 16, abb >> 16, p.inv_n);
     s_px[ly][lx] = px0;
     s_px[ly + 8][lx] = px1;
     __syncthreads();

@@ -425,7 +425,7 @@ static void build_mapper(octvr_mapper& m, const octvr_template& t, const int* in
                         const int ix = std::min(32767, std::max(-32768, fsx >> 5)), iy = std::min(32767, std::max(-32768, fsy >> 5));
                         const uint32_t off = (uint32_t)(jm.soff + (iy - jm.by0) * jm.bw + (ix - jm.bx0));
                         uint32_t wbits; memcpy(&wbits, &w, 4);
-                        entries[(size_t)j * TILE_PX + p] = make_uint2(off | ((uint32_t)(fsx & 31) << 16) | ((uint32_t)(fsy & 31) << 21), wbits);
+                        entries[(size_t)j * TILE_PX + p] = make_uint2((off << 2) | ((uint32_t)(fsy & 31) << 16) | ((uint32_t)(fsx & 31) << 24), wbits);   // byte offset | fy | fx
                     }
                 }
             // tensor maps over the mapper-owned RGBX planes (static addresses): u32 elements, no swizzle, zero OOB fill

@@ -178,48 +178,6 @@ __device__ __forceinline__ void convert_item(const CamSrc& c, const JobRegs& J, 
     *d0 = a; *d1 = b;
 }
 
-// one table entry: four taps from the stage, 1/32-px bilinear, gain, weight, accumulate.
-// ex = byte offset of the top-left tap in the stage | fy << 16 | fx << 24 ; ew = f32 weight bits.
-// The sums of floor(v * W) are at most 255 * MAX_CAMS < 2^16: R and G share one accumulator (G in the high half), the
-// blue sums of two pixels share another.  bits(2^23 + k) * 65536 = k << 16 mod 2^32, so the high halves need no bias
-// removal and take their add on the IMAD pipe.
-template <int GAIN, bool LUT, bool BHI>
-__device__ __forceinline__ void fused_pair(uint32_t ex, uint32_t ew, const uint8_t* __restrict__ s0, const uint8_t* __restrict__ s1,
-                                           float g32, float gbias, const uint8_t* __restrict__ lut, uint32_t& arg, uint32_t& ab)
-{
-    const uint32_t off = ex & 0xFFFFu;
-    const uint32_t t00 = *reinterpret_cast<const uint32_t*>(s0 + off), t01 = *reinterpret_cast<const uint32_t*>(s0 + off + 4);
-    const uint32_t t10 = *reinterpret_cast<const uint32_t*>(s1 + off), t11 = *reinterpret_cast<const uint32_t*>(s1 + off + 4);
-    const uint32_t fx = ex >> 24, fy = __byte_perm(ex, 0u, 0x4442);
-    const uint32_t wx = fx * 65535u + 32u;                 // (32-fx) | fx << 16
-    const uint32_t wb = wx * fy, wt = wx * 32u - wb;       // {(32-fx) fy, fx fy}, {(32-fx)(32-fy), fx (32-fy)} as 16-bit pairs
-    const uint32_t rg0 = __byte_perm(t00, t01, 0x5140);    // R00 R01 G00 G01
-    const uint32_t bb0 = __byte_perm(t00, t01, 0x6262);    // B00 B01 .. ..
-    const uint32_t rg1 = __byte_perm(t10, t11, 0x5140);
-    const uint32_t bb1 = __byte_perm(t10, t11, 0x6262);
-    const uint32_t r = __dp2a_lo(wb, rg1, __dp2a_lo(wt, rg0, 512u));     // sum + 512 (< 2^18): exact in f32
-    const uint32_t g = __dp2a_hi(wb, rg1, __dp2a_hi(wt, rg0, 512u));
-    const uint32_t b = __dp2a_lo(wb, bb1, __dp2a_lo(wt, bb0, 512u));
-    // floor(x / 1024) + 2^23 by a round-down fma: the integer lands in the mantissa (no shift, no F2I)
-    float rf = __fmaf_rd(__uint2float_rn(r), 0.0009765625f, MAGIC_RD);
-    float gf = __fmaf_rd(__uint2float_rn(g), 0.0009765625f, MAGIC_RD);
-    float bf = __fmaf_rd(__uint2float_rn(b), 0.0009765625f, MAGIC_RD);
-    if (GAIN && !LUT) {
-        rf = gain_apply_biased(rf, g32, gbias); gf = gain_apply_biased(gf, g32, gbias); bf = gain_apply_biased(bf, g32, gbias);
-    } else if (GAIN) {
-        rf = (float)__ldg(lut + (__float_as_uint(rf) & 255u)); gf = (float)__ldg(lut + (__float_as_uint(gf) & 255u));
-        bf = (float)__ldg(lut + (__float_as_uint(bf) & 255u));
-    } else {
-        rf = __fadd_rn(rf, -MAGIC_RD); gf = __fadd_rn(gf, -MAGIC_RD); bf = __fadd_rn(bf, -MAGIC_RD);
-    }
-    // (short)(v * W): f32 product, truncated (v*W >= 0 so floor == trunc)
-    const float w = __uint_as_float(ew);
-    arg += __float_as_uint(__fadd_rd(__fmul_rn(rf, w), MAGIC_RD)) - 0x4B000000u;
-    arg = __float_as_uint(__fadd_rd(__fmul_rn(gf, w), MAGIC_RD)) * 65536u + arg;
-    if (BHI) ab = __float_as_uint(__fadd_rd(__fmul_rn(bf, w), MAGIC_RD)) * 65536u + ab;
-    else ab += __float_as_uint(__fadd_rd(__fmul_rn(bf, w), MAGIC_RD)) - 0x4B000000u;
-}
-
 template <int GAIN, bool LUT>
 __device__ __forceinline__ void gather_job(const uint4 e0, const uint4 e1, const uint8_t* s0, const uint8_t* s1, float g32, float gb,
                                            const uint8_t* lut, uint32_t (&arg)[FT_PPT], uint32_t (&ab)[FT_PPT / 2])
