@@ -31,6 +31,7 @@ WORKLOADS = {
     "c1": ("rig2", -1, True, "C1 2x1920x1080 fisheye -> 2048x1024 equirect, gain + feather(1)"),
     "c2": ("rig6", -1, True, "C2 6x2704x1520 -> 4096x2048 equirect, gain + feather(1)"),
     "c3": ("rig6", 64, True, "C3 6x2704x1520 -> 4096x2048 equirect, gain + 5-band multiband"),
+    "c4": (("rig8L", "rig8R"), 64, True, "C4 8x3840x2160 fisheye -> 7680x3840 stereo top-bottom, gain + 5-band multiband"),
     "c2ng": ("rig6", -1, False, "C2 rig without gain compensation: 6x2704x1520 -> 4096x2048 equirect, feather(1) (diagnostic)"),
 }
 
@@ -299,6 +300,125 @@ def run_rowband(args):
                    "collection of the bands on rank 0 per step" % (n, n * iw * ih * 1.5 / 1e6), "bands": rb.bands}}))
 
 
+def run_stereo(args):
+    """BASELINE config C4: 8 x 3840x2160 fisheye -> 7680x3840 stereo top-bottom (two 7680x1920 eye templates, 5-band multiband),
+    ONE stream over all ranks split by (eye, row band) -- sharding.StereoRowBandStitcher.  N > 1: rank 0 ingests, NCCL
+    broadcasts the inputs, the bands are collected on rank 0; everything inside the timed region (strong scaling)."""
+    import torch
+    import torch.distributed as dist
+    import octvr_b200 as vr
+    import util
+    world, rank, local = int(os.environ.get("WORLD_SIZE", "1")), int(os.environ.get("RANK", "0")), int(os.environ.get("LOCAL_RANK", "0"))
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    torch.cuda.set_device(local)
+    rigs, blend, gain, desc = WORKLOADS[args.workload]
+    eye_h = 1920
+    tmpls, in_size = [], None
+    t0 = time.time()
+    todo = sorted({e for e, _, _ in vr.sharding.stereo_assignment(world)[rank]})
+    for e, rig in enumerate(rigs):
+        cfg, width, in_size = util.named_rig(rig)
+        n = len(cfg["inputs"])
+        # only the eye(s) this rank stitches need tables; the other slot reuses the same template object (never stitched)
+        tmpls.append(vr.MapperTemplate.from_json(cfg, width, eye_h, use_roi=True, with_seam_masks=True, device=local) if e in todo else None)
+    for e in range(2):
+        if tmpls[e] is None:
+            tmpls[e] = tmpls[todo[0]]
+    t_tmpl = time.time() - t0
+    iw, ih = in_size
+    t0 = time.time()
+    st = vr.sharding.StereoRowBandStitcher(vr, tmpls, [in_size] * n, blend, gain, local)
+    t_map = time.time() - t0
+    W, He = st.eye_w, st.eye_h
+    H = 2 * He
+    RING = 4
+    ring = []
+    for k in range(RING):
+        fr = []
+        for c in range(n):
+            if rank == 0:
+                y, u, v = util.i420_planes(util.noise_frame(c, iw, ih, seed=1234 + 7919 * k), iw, ih)
+                fr.append(torch.from_numpy(np.concatenate([y, np.concatenate([u, v], 1)], 0)).cuda())
+            else:
+                fr.append(torch.zeros((ih * 3 // 2, iw), dtype=torch.uint8, device="cuda"))
+        ring.append(fr)
+    out = torch.zeros((H * 3 // 2, W), dtype=torch.uint8, device="cuda")
+
+    def step(k):
+        if world > 1:
+            out.zero_()
+            st.stitch(ring[k % RING], out, src=0, collect=True)
+        else:
+            st.stitch_local(ring[k % RING], out)
+
+    for k in range(args.warmup):
+        step(k)
+    torch.cuda.synchronize()
+    # per-stage split and stitch-only time of this rank (separate, untimed pass)
+    stage = {"convert": [], "gain": [], "blend": [], "total": []}
+    for _, _, m in st.jobs:
+        m.set_profiling(True)
+    for k in range(5):
+        st.stitch_local(ring[k % RING], out)
+        for s_ in stage:
+            stage[s_].append(sum(m.stage_ms(s_) for _, _, m in st.jobs))
+    for _, _, m in st.jobs:
+        m.set_profiling(False)
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    sampler = ClockSampler(local) if rank == 0 else None
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for k in range(args.steps):
+        step(k)
+    e1.record()
+    torch.cuda.synchronize()
+    clocks = sampler.stop() if sampler else None
+    ms = vr.sharding.max_over_ranks(e0.elapsed_time(e1), device="cuda")
+    local_ms = vr.sharding.max_over_ranks(statistics.median(stage["total"]), device="cuda")
+    stats = [m.stats() for _, _, m in st.jobs]
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+    if rank != 0:
+        return
+    peak, how = peaks()
+    I = n * iw * ih * 3 // 2
+    # both eyes are the same rig mirrored: P and roi area of eye 0 stand for both (SURVEY.md 8d, C4)
+    B = 2 * alg_bytes([in_size] * n, (W, He), stats[0]["pairs"], stats[0]["roi_area"], blend) - I
+    ms_per_step = ms / args.steps
+    blend_ms = statistics.median(stage["blend"])
+    line = {
+        "metric": "equirect output Mpix/s", "value": round(W * H * args.steps / (ms * 1e-3) / 1e6, 1), "unit": "Mpix/s", "n_gpus": world,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(ms_per_step, 5), "higher_is_better": True,
+        "scaling": "strong" if world > 1 else "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
+        "frames_per_s": round(args.steps / (ms * 1e-3), 2),
+        "config": {"workload": desc, "inputs": "%dx%dx%d I420 (octvr packed layout), ring of %d noise frames resident on rank 0" % (n, iw, ih, RING),
+                   "output": "%dx%d 4:2:0 top-bottom (two %dx%d eyes)" % (W, H, W, He),
+                   "l2": "working set per step exceeds the 126 MB L2; no flush",
+                   "sharding": ("row bands of one stream: per step NCCL broadcast of %d input frames (%.1f MB) from rank 0, (eye, band) stitch, "
+                                "bands collected on rank 0 (NCCL reduce of the %.1f MB frame)" % (n, I / 1e6, W * H * 1.5 / 1e6)) if world > 1 else "single GPU, both eyes",
+                   "assignment_rank0": [(j[0], list(j[1])) for j in st.jobs],
+                   "pairs_P_per_eye": stats[0]["pairs"], "roi_area_per_eye": stats[0]["roi_area"],
+                   "template_build_s": round(t_tmpl, 2), "mapper_build_s": round(t_map, 2)},
+        "alg_bytes_per_frame": int(B),
+        "frac_of_hbm_roofline": {"whole_step_vs_measured_%.0f_x%d" % (peak, world): round(B / (ms_per_step * 1e-3) / 1e9 / (peak * world), 4)},
+        "stage_ms_rank0": {k: round(statistics.median(v), 5) for k, v in stage.items()},
+        "stitch_only_ms_max_over_ranks": round(local_ms, 5),
+        "gpu_launches": sum(s_["launches_per_stitch"] for s_ in stats) * args.steps,
+        "clocks": clocks,
+    }
+    if world == 1:
+        ach = (B - I) / (blend_ms * 1e-3) / 1e9
+        line["roofline"] = {"bound": "hbm", "kernel": "multiband stage, both eyes (k_mb_warp+k_mb_down+k_mb_band+k_mb_collapse+k_mb_final)",
+                            "achieved": round(ach, 1), "peak": peak, "peak_source": how, "unit": "GB/s", "frac": round(ach / peak, 4),
+                            "traffic": None, "alg_bytes_per_launch": int(B - I), "ms_per_launch": round(blend_ms, 5)}
+    print(json.dumps(line))
+
+
 def run_e2e(vr, util, tmpl, cfg, in_size, blend, gain, device, steps, world):
     """Same metric through AsyncMultiMapper.push/pop with HOST frames: H2D + stitch + D2H every step."""
     import torch
@@ -346,6 +466,8 @@ def cpu_baseline(workload, budget_s=20.0, steps=None, warmup=1):
     import oracle as O
     import util
     rig, blend, gain, desc = WORKLOADS[workload]
+    if not isinstance(rig, str):
+        raise SystemExit("the CPU arm runs the single-template workloads (c1, c2, c3); c4 is a GPU-only bench line")
     cfg, width, in_size = util.named_rig(rig)
     n = len(cfg["inputs"])
     iw, ih = in_size
@@ -403,6 +525,8 @@ def main():
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)
+    elif args.workload == "c4":
+        run_stereo(args)
     elif args.rowband and int(os.environ.get("WORLD_SIZE", "1")) > 1:
         run_rowband(args)
     else:

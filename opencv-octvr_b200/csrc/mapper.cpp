@@ -275,8 +275,6 @@ static void build_mapper(octvr_mapper& m, const octvr_template& t, const int* in
     if (band_y0 == 0 && band_y1 == 0) band_y1 = t.out_h;
     OB_CHECK(band_y0 >= 0 && band_y0 < band_y1 && band_y1 <= t.out_h, "row band must lie inside the output");
     OB_CHECK(band_y0 % 32 == 0 && (band_y1 % 32 == 0 || band_y1 == t.out_h), "row bands must be aligned to 32 output rows");
-    if ((band_y0 != 0 || band_y1 != t.out_h) && blend > 0)
-        fail(OCTVR_ERR_UNSUPPORTED, "row bands are implemented for feather / no-blend mappers only (multiband needs halo rows)");
     m.band_y0 = band_y0; m.band_y1 = band_y1;
     OB_CHECK(t.out_w % 2 == 0 && t.out_h % 2 == 0, "output size must be even (4:2:0)");
     for (int i = 0; i < n; i++) {

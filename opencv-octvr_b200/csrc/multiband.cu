@@ -49,8 +49,9 @@ struct MbParams {
     const uint32_t* rgbx[MAX_CAMS]; int src_pitch[MAX_CAMS];
     const float* gain_f32; const int* gain_flag; const uint8_t* gain_lut; int use_gain;
     // output
-    int rx, ry, rw, rh;               // final result roi in the output frame (dst_roi_final_)
+    int rx, ry, rw, rh;               // final result roi in the output frame (dst_roi_final_); row-band mappers: the part inside the row window
     int out_w, out_h;
+    int oy0, oy1;                     // output rows this mapper writes (row-band mode; default 0 .. out_h)
     uint8_t* oy; uint8_t* ou; uint8_t* ov; uint32_t oy_pitch, ou_pitch, ov_pitch; int uv_step;
     uint8_t* rgb_out; uint32_t rgb_pitch;
 };
@@ -311,8 +312,8 @@ __global__ void __launch_bounds__(256) k_mb_collapse(const __grid_constant__ MbP
 //      OUTPUT-FRAME pixels (pixels outside the result roi are black) ----
 __global__ void __launch_bounds__(256) k_mb_final(const __grid_constant__ MbParams p)
 {
-    const int X0 = (blockIdx.x * 32 + threadIdx.x) * 4, Y = blockIdx.y * 8 + threadIdx.y;
-    if (X0 >= p.out_w || Y >= p.out_h) return;
+    const int X0 = (blockIdx.x * 32 + threadIdx.x) * 4, Y = p.oy0 + blockIdx.y * 8 + threadIdx.y;
+    if (X0 >= p.out_w || Y >= p.oy1) return;
     int R[4], G[4], B[4];
     #pragma unroll
     for (int q = 0; q < 4; q++) R[q] = G[q] = B[q] = 0;
@@ -413,10 +414,26 @@ Multiband* multiband_create(octvr_mapper& m, const octvr_template& t,
     const int al = 1 << nb;
     const int PW = Rf.w + (al - Rf.w % al) % al, PH = Rf.h + (al - Rf.h % al) % al;   // blenders.cpp:246-247
     p.n = n; p.nb = nb;
-    p.rx = Rf.x; p.ry = Rf.y; p.rw = Rf.w; p.rh = Rf.h; p.out_w = t.out_w; p.out_h = t.out_h;
+    // Row window [E0, E1) of the padded dst roi this mapper computes.  A row-band mapper (multi-GPU partition of one frame,
+    // SURVEY.md 8e) keeps its band plus a halo and crops every camera rectangle, weight pyramid and dst level to it.  Cutting
+    // the pyramids at a window edge corrupts, per level, at most 2 rows of the Gaussian levels next to the cut, 6 rows of the
+    // Laplacian levels (pyrUp reads one coarser row either side) and r_l = 2 r_{l+1} + 2 rows of the collapsed levels, i.e.
+    // 2^(bands+2) - 2 rows at level 0; a halo of 4 * 2^bands rows therefore leaves the band itself bit-identical to the
+    // full-frame result.  Weights are computed on the full rectangles and cropped, so they are exact everywhere.
+    int E0 = 0, E1 = PH;
+    if (m.band_y0 != 0 || m.band_y1 != t.out_h) {
+        const int halo = 4 * al;
+        auto fl = [&](int v) { return v >= 0 ? v / al * al : -((-v + al - 1) / al * al); };
+        E0 = std::min(PH, std::max(0, fl(m.band_y0 - Rf.y - halo)));
+        E1 = std::min(PH, std::max(0, fl(m.band_y1 - Rf.y + halo + al - 1)));
+        if (E1 <= E0) E0 = E1 = 0;
+    }
+    const int WH = E1 - E0;
+    p.rx = Rf.x; p.ry = Rf.y + E0; p.rw = Rf.w; p.rh = std::min(Rf.h, E1) - E0; p.out_w = t.out_w; p.out_h = t.out_h;
+    p.oy0 = m.band_y0; p.oy1 = m.band_y1;
     size_t doff = 0;
     for (int l = 0; l <= nb; l++) {
-        p.lw[l] = l == 0 ? PW : (p.lw[l - 1] + 1) / 2; p.lh[l] = l == 0 ? PH : (p.lh[l - 1] + 1) / 2;
+        p.lw[l] = l == 0 ? PW : (p.lw[l - 1] + 1) / 2; p.lh[l] = l == 0 ? WH : (p.lh[l - 1] + 1) / 2;
         p.off_d[l] = doff; doff += (size_t)p.lw[l] * p.lh[l];
     }
     std::vector<float> dstw(doff, 0.f);
@@ -444,37 +461,44 @@ Multiband* multiband_create(octvr_mapper& m, const octvr_template& t,
         const int dy = std::max(bny - (Rf.y + PH), 0), dx = std::max(bnx - (Rf.x + PW), 0);
         tnx -= dx; bnx -= dx; tny -= dy; bny -= dy;
         const int top = in.roi.y - tny, left = in.roi.x - tnx;
-        c.x0 = tnx - Rf.x; c.y0 = tny - Rf.y; c.bw = width; c.bh = height;
-        mb->max_bw = std::max(mb->max_bw, width); mb->max_bh = std::max(mb->max_bh, height);
-        c.off_g[0] = g0_total; g0_total += (size_t)width * height;
-        for (int l = 1; l <= nb; l++) { c.off_g[l] = g_total; g_total += (size_t)(width >> l) * (height >> l); }
+        // rows [ys, ye) of the full rectangle fall inside the row window (all of it without row bands)
+        const int fy0 = tny - Rf.y;
+        const int ys = std::min(height, std::max(0, E0 - fy0)), ye = std::max(ys, std::min(height, E1 - fy0));
+        const int ch = ye - ys;
+        c.x0 = tnx - Rf.x; c.y0 = fy0 + ys - E0; c.bw = width; c.bh = ch;
+        if (ch > 0) { mb->max_bw = std::max(mb->max_bw, width); mb->max_bh = std::max(mb->max_bh, ch); }
+        c.off_g[0] = g0_total; g0_total += (size_t)width * ch;
+        for (int l = 1; l <= nb; l++) { c.off_g[l] = g_total; g_total += (size_t)(width >> l) * (ch >> l); }
         // level-0 remap table with BORDER_REFLECT baked in, and the f32 weight map (BORDER_CONSTANT 0)
         Img<float> wmap(width, height, 0.f);
         const float inv255 = (float)(1. / 255.);
-        coords.resize(coords.size() + (size_t)width * height);
+        coords.resize(coords.size() + (size_t)width * ch);
         uint2* ce = coords.data() + c.off_g[0];
         for (int y = 0; y < height; y++) {
             const int ly = mirror(y - top, in.roi.h);
             const bool in_y = y - top >= 0 && y - top < in.roi.h;
+            const bool in_win = y >= ys && y < ye;
+            if (!in_win && !in_y) continue;
             for (int x = 0; x < width; x++) {
                 const int lx = mirror(x - left, in.roi.w);
-                ce[(size_t)y * width + x] = mk_entry(sx[i].row(ly)[lx], sy[i].row(ly)[lx], m.in_w[i], m.in_h[i], in.mask.row(ly)[lx] != 0);
+                if (in_win) ce[(size_t)(y - ys) * width + x] = mk_entry(sx[i].row(ly)[lx], sy[i].row(ly)[lx], m.in_w[i], m.in_h[i], in.mask.row(ly)[lx] != 0);
                 if (in_y && x - left >= 0 && x - left < in.roi.w) wmap.row(y)[x] = seams[i].row(y - top)[x - left] * inv255 + 0.f;
             }
         }
-        for (size_t k = 0; k < ((size_t)width * height + 255) / 256; k++) {
+        for (size_t k = 0; k < ((size_t)width * ch + 255) / 256; k++) {
             bool any = false;
-            for (size_t e = k * 256; e < std::min((k + 1) * 256, (size_t)width * height) && !any; e++) any = (ce[e].y & C_VALID) != 0;
+            for (size_t e = k * 256; e < std::min((k + 1) * 256, (size_t)width * ch) && !any; e++) any = (ce[e].y & C_VALID) != 0;
             if (any) chunks.push_back(make_uint2((uint32_t)i, (uint32_t)k));
         }
         Img<float> wl = std::move(wmap);
         int xt = c.x0, yt = c.y0;
         for (int l = 0; l <= nb; l++) {
             c.off_w[l] = wts.size();
-            wts.insert(wts.end(), wl.d.begin(), wl.d.end());
-            for (int y = 0; y < wl.h; y++) {                        // dst_band_weights_[l](rc) += weight (blenders.cpp:421)
+            const int r0 = ys >> l, r1 = ye >> l;                   // the window's rows of the full level-l weight map
+            wts.insert(wts.end(), wl.d.begin() + (size_t)r0 * wl.w, wl.d.begin() + (size_t)r1 * wl.w);
+            for (int y = 0; y < r1 - r0; y++) {                     // dst_band_weights_[l](rc) += weight (blenders.cpp:421)
                 float* dr = dstw.data() + p.off_d[l] + (size_t)(yt + y) * p.lw[l] + xt;
-                const float* wr = wl.row(y);
+                const float* wr = wl.row(r0 + y);
                 for (int x = 0; x < wl.w; x++) {
                     dr[x] += wr[x];
                     if (wr[x] != 0.f) tile_cams[p.off_t[l] + (size_t)((yt + y) / 8) * ((p.lw[l] + 31) / 32) + (xt + x) / 32] |= (uint16_t)(1u << i);
@@ -514,13 +538,15 @@ void multiband_stitch(octvr_mapper& m, const octvr_frame* out, cudaStream_t s)
     p.rgb_out = m.keep_rgb ? m.d_rgb : nullptr; p.rgb_pitch = (uint32_t)m.out_w * 3;
     const int nb = p.nb, n = p.n;
     if (mb.n_chunks) k_mb_warp<<<mb.n_chunks, 256, 0, s>>>(p);
-    for (int l = 0; l < nb; l++)
-        k_mb_down<<<dim3(((mb.max_bw >> (l + 1)) + 31) / 32, ((mb.max_bh >> (l + 1)) + 31) / 32, n), dim3(32, 8), 0, s>>>(p, l);
-    for (int l = nb; l >= 0; l--)
-        k_mb_band<<<dim3((p.lw[l] + 127) / 128, (p.lh[l] + 7) / 8), dim3(32, 8), 0, s>>>(p, l);
-    for (int l = nb; l >= 2; l--)
-        k_mb_collapse<<<dim3((p.lw[l - 1] + 127) / 128, (p.lh[l - 1] + 7) / 8), dim3(32, 8), 0, s>>>(p, l);
-    k_mb_final<<<dim3((p.out_w + 127) / 128, (p.out_h + 7) / 8), dim3(32, 8), 0, s>>>(p);
+    if (p.lh[0] > 0 && mb.max_bh > 0) {                    // an empty row window (a band outside the result roi) only writes black
+        for (int l = 0; l < nb; l++)
+            k_mb_down<<<dim3(((mb.max_bw >> (l + 1)) + 31) / 32, ((mb.max_bh >> (l + 1)) + 31) / 32, n), dim3(32, 8), 0, s>>>(p, l);
+        for (int l = nb; l >= 0; l--)
+            k_mb_band<<<dim3((p.lw[l] + 127) / 128, (p.lh[l] + 7) / 8), dim3(32, 8), 0, s>>>(p, l);
+        for (int l = nb; l >= 2; l--)
+            k_mb_collapse<<<dim3((p.lw[l - 1] + 127) / 128, (p.lh[l - 1] + 7) / 8), dim3(32, 8), 0, s>>>(p, l);
+    }
+    k_mb_final<<<dim3((p.out_w + 127) / 128, (p.oy1 - p.oy0 + 7) / 8), dim3(32, 8), 0, s>>>(p);
 }
 
 int multiband_launches(const octvr_mapper& m) { return m.mb ? m.mb->launches : 0; }
