@@ -123,6 +123,17 @@ public:
         const octvr_frame fo = to_frame(output);
         check(octvr_mapper_stitch(h_, fin.data(), (int)fin.size(), &fo, nullptr, 0, 0, 0, gains.empty() ? nullptr : gains.data(), (int)gains.size(), stream));
     }
+    // the same with the preview_output argument of Mapper::stitch (mapper.cpp:308-312): the result resized (INTER_LINEAR)
+    // into a DEVICE RGB888 buffer of preview_size; inputs = blended inputs followed by the template's overlay inputs
+    void stitch(const std::vector<YUV>& inputs, const YUV& output, uint8_t* preview_rgb, size_t preview_step, Size preview_size,
+                std::vector<double> gains = std::vector<double>(), void* stream = nullptr)
+    {
+        std::vector<octvr_frame> fin;
+        for (auto& f : inputs) fin.push_back(to_frame(f));
+        const octvr_frame fo = to_frame(output);
+        check(octvr_mapper_stitch(h_, fin.data(), (int)fin.size(), &fo, preview_rgb, preview_step, preview_size.width, preview_size.height,
+                                  gains.empty() ? nullptr : gains.data(), (int)gains.size(), stream));
+    }
     // void stitch(std::vector<GpuMat>& inputs, GpuMat& output, GpuMat& preview, std::vector<double> gains) with the
     // W x 1.5H single-plane layout of mapper.hpp:75-83
     void stitch_packed(const std::vector<const uint8_t*>& inputs, const std::vector<size_t>& steps, uint8_t* output, size_t out_step,
@@ -176,6 +187,16 @@ public:
     }
     virtual void pop() { check(octvr_async_pop(h_)); }
     double fps() const { double v = 0; check(octvr_async_fps(h_, &v)); return v; }
+    // preview frame (preview_size, RGB888, host) of the frame popped last; the reference publishes it through Qt shared
+    // memory (async.cpp:119-137), here the caller reads it
+    const uint8_t* preview(size_t* step = nullptr, Size* size = nullptr) const
+    {
+        const uint8_t* p = nullptr; size_t st = 0; int w = 0, h = 0;
+        check(octvr_async_preview(h_, &p, &st, &w, &h));
+        if (step) *step = st;
+        if (size) { size->width = w; size->height = h; }
+        return p;
+    }
     virtual ~AsyncMultiMapper() { octvr_async_destroy(h_); }      // joins cleanly (the reference's destructor terminates, App. F)
 #ifdef OCTVR_WITH_OPENCV
     static Plane plane(const cv::Mat& m) { return Plane{ m.data, m.step, 1 }; }

@@ -61,6 +61,10 @@ octvr_status octvr_template_from_arrays(int out_w, int out_h, int n_inputs, cons
                                         const uint8_t* const* mask, const uint8_t* const* seam_mask,
                                         const float* const* vignette, int vig_w, int vig_h,
                                         octvr_template** out);
+/* Append one entry of MapperTemplate::overlay_inputs (octvr.hpp:63, filled by add_input(..., overlay = true),
+ * template.cpp:46-153) to a template made by octvr_template_from_arrays.  Same array conventions; copied. */
+octvr_status octvr_template_add_overlay(octvr_template* t, const int* roi_xywh, const float* map1, const float* map2,
+                                        const uint8_t* mask, const float* vignette, int vig_w, int vig_h);
 /* MapperTemplate::create_masks() with no images (DistanceSeamFinder), template.cpp:155-204 */
 octvr_status octvr_template_create_masks(octvr_template* t);
 
@@ -147,6 +151,10 @@ octvr_status octvr_async_push(octvr_async* a, const octvr_frame* h_inputs, int n
 /* pop(): blocks until the oldest pushed frame is complete (async.cpp:191-193). */
 octvr_status octvr_async_pop(octvr_async* a);
 octvr_status octvr_async_fps(octvr_async* a, double* fps);
+/* The preview frame (preview_size, RGB888; every output region resized into its share of it, async.cpp:76-84,
+ * mapper.cpp:308-312) of the frame popped last.  The reference hands this buffer to its GUI through Qt shared memory
+ * (async.cpp:119-137, out of scope); here the caller reads it.  Valid until the next-but-two pop(). */
+octvr_status octvr_async_preview(octvr_async* a, const uint8_t** h_rgb, size_t* pitch, int* w, int* h);
 void         octvr_async_destroy(octvr_async* a);
 
 #ifdef __cplusplus

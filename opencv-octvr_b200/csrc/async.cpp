@@ -8,6 +8,7 @@
 // for the oldest frame's last event and finishes the copy-out.  No stage ever blocks the GPU on the host.
 #include "mapper.h"
 #include <chrono>
+#include <cmath>
 #include <cstring>
 #include <deque>
 #include <memory>
@@ -17,7 +18,8 @@
 using namespace ob;
 
 namespace ob { void mapper_stitch_internal(octvr_mapper& m, const octvr_frame* in, int n_in, const octvr_frame* out,
-                                          const double* gains, int n_gains, const double* d_gains_src, cudaStream_t s); }
+                                          const double* gains, int n_gains, const double* d_gains_src, cudaStream_t s,
+                                          uint8_t* d_preview, size_t preview_pitch, int preview_w, int preview_h); }
 
 namespace {
 
@@ -26,6 +28,8 @@ struct Slot {
     std::vector<uint8_t*> h_in;       // pinned staging, same layout
     uint8_t* d_out = nullptr;         // whole output frame, contiguous I420
     uint8_t* h_out = nullptr;         // pinned staging
+    uint8_t* d_preview = nullptr;     // preview frame, RGB888 (async.cpp:299-304), when a preview size was given
+    uint8_t* h_preview = nullptr;     // pinned copy of it, valid after pop()
     cudaEvent_t uploaded = nullptr, stitched = nullptr, done = nullptr;
     bool busy = false;
     octvr_frame user_out{};           // caller's output planes (filled by pop when staged)
@@ -66,6 +70,9 @@ struct octvr_async {
     std::vector<std::unique_ptr<octvr_mapper>> mappers;
     std::vector<int> gain_modes;
     std::vector<Rect> regions;                 // pixel rectangles of the output frame
+    std::vector<Rect> preview_regions;         // the same fractions of the preview frame
+    int preview_w = 0, preview_h = 0;
+    const uint8_t* last_preview = nullptr;     // h_preview of the frame popped last
     static constexpr int BUF = 3;              // async.cpp:261
     Slot slots[BUF];
     uint64_t pushed = 0, popped = 0;
@@ -82,6 +89,7 @@ struct octvr_async {
         if (s_run) cudaStreamSynchronize(s_run);
         if (s_down) cudaStreamSynchronize(s_down);
         for (auto& s : slots) {
+            cudaFree(s.d_preview); cudaFreeHost(s.h_preview);
             for (auto p : s.d_in) cudaFree(p);
             for (auto p : s.h_in) cudaFreeHost(p);
             cudaFree(s.d_out);
@@ -127,19 +135,32 @@ octvr_status octvr_async_create(const octvr_template* const* tmpls, int n_out, c
         OB_CHECK(tmpls && in_sizes_wh && blend_modes && gain_modes && regions_xywh && out, "null argument");
         OB_CHECK(n_out >= 1 && n_in >= 1, "need at least one template and one input");
         OB_CHECK(out_w > 0 && out_h > 0 && out_w % 2 == 0 && out_h % 2 == 0, "output size must be even (async.cpp:266-267)");
-        if (preview_w > 0 || preview_h > 0) fail(OCTVR_ERR_UNSUPPORTED, "preview output is not implemented yet");
+        OB_CHECK(preview_w >= 0 && preview_h >= 0, "negative preview size");
         int count = 0;
         if (cudaGetDeviceCount(&count) != cudaSuccess || count <= 0 || device < 0 || device >= count)
             fail(OCTVR_ERR_CUDA, "no usable CUDA device (the stitch path has no CPU fallback)");
         OB_CUDA(cudaSetDevice(device));
         std::unique_ptr<octvr_async> a(new octvr_async);
         a->device = device; a->n_in = n_in; a->n_out = n_out; a->out_w = out_w; a->out_h = out_h;
+        if (preview_w > 0 && preview_h > 0) { a->preview_w = preview_w; a->preview_h = preview_h; }    // preview_size.area() > 0
+        // _rect_mul_size (async.cpp:20-30): rounded corner and size, clipped to the frame
+        auto rect_mul = [](const double* r, int W, int H) {
+            int x = (int)std::round(r[0] * W), y = (int)std::round(r[1] * H), w = (int)std::round(r[2] * W), h = (int)std::round(r[3] * H);
+            if (x + w >= W) w = W - x;
+            if (y + h >= H) h = H - y;
+            return Rect{ x, y, w, h };
+        };
         for (int i = 0; i < n_in; i++) { a->in_w.push_back(in_sizes_wh[2 * i]); a->in_h.push_back(in_sizes_wh[2 * i + 1]); }
         for (int i = 0; i < n_out; i++) {
             OB_CHECK(tmpls[i], "null template");
             // output_regions are fractions of the output frame (async.cpp:181-185, 247-259)
             const double* r = regions_xywh + 4 * i;
-            Rect px{ (int)(r[0] * out_w), (int)(r[1] * out_h), (int)(r[2] * out_w), (int)(r[3] * out_h) };
+            const Rect px = rect_mul(r, out_w, out_h);
+            if (a->preview_w) {
+                const Rect pv = rect_mul(r, a->preview_w, a->preview_h);
+                OB_CHECK(pv.w > 0 && pv.h > 0 && pv.x >= 0 && pv.y >= 0, "output region leaves no room in the preview frame");
+                a->preview_regions.push_back(pv);
+            }
             OB_CHECK(px.w > 0 && px.h > 0 && px.x >= 0 && px.y >= 0 && px.x + px.w <= out_w && px.y + px.h <= out_h, "output region outside the frame");
             OB_CHECK(px.x % 2 == 0 && px.y % 2 == 0 && px.w % 2 == 0 && px.h % 2 == 0, "output regions must be even (4:2:0)");
             a->regions.push_back(px);
@@ -167,6 +188,13 @@ octvr_status octvr_async_create(const octvr_template* const* tmpls, int n_out, c
             // output pre-filled with black in YUV (async.cpp:283-310): regions need not tile the frame
             OB_CUDA(cudaMemset(s.d_out, 16, (size_t)out_w * out_h));
             OB_CUDA(cudaMemset(s.d_out + (size_t)out_w * out_h, 128, (size_t)out_w * out_h / 2));
+            if (a->preview_w) {
+                const size_t pb = (size_t)a->preview_w * a->preview_h * 3;
+                OB_CUDA(cudaMalloc(&s.d_preview, pb));
+                OB_CUDA(cudaMemset(s.d_preview, 0, pb));                    // preview_mat.setTo(0)
+                OB_CUDA(cudaMallocHost(&s.h_preview, pb));
+                memset(s.h_preview, 0, pb);
+            }
             OB_CUDA(cudaEventCreateWithFlags(&s.uploaded, cudaEventDisableTiming));
             OB_CUDA(cudaEventCreateWithFlags(&s.stitched, cudaEventDisableTiming));
             OB_CUDA(cudaEventCreateWithFlags(&s.done, cudaEventDisableTiming));
@@ -214,7 +242,13 @@ octvr_status octvr_async_push(octvr_async* a, const octvr_frame* in, int n_input
             o.v += (size_t)(px.y / 2) * whole.v_pitch + px.x / 2;
             const int gm = a->gain_modes[r];
             const double* shared = (gm >= 0 && gm != r) ? a->mappers[gm]->d_gains : nullptr;   // gains of an earlier output
-            mapper_stitch_internal(*a->mappers[r], fin.data(), a->n_in, &o, nullptr, 0, shared, a->s_run);
+            uint8_t* pv = nullptr;                                          // this output's part of the preview frame (async.cpp:78-79)
+            int pvw = 0, pvh = 0;
+            if (a->preview_w) {
+                const Rect& pr = a->preview_regions[r];
+                pv = s.d_preview + ((size_t)pr.y * a->preview_w + pr.x) * 3; pvw = pr.w; pvh = pr.h;
+            }
+            mapper_stitch_internal(*a->mappers[r], fin.data(), a->n_in, &o, nullptr, 0, shared, a->s_run, pv, (size_t)a->preview_w * 3, pvw, pvh);
         }
         OB_CUDA(cudaEventRecord(s.stitched, a->s_run));
         // T4: device -> host on the download stream; straight into the caller's planes when they are pinned
@@ -237,6 +271,8 @@ octvr_status octvr_async_push(octvr_async* a, const octvr_frame* in, int n_input
         } else {
             OB_CUDA(cudaMemcpyAsync(s.h_out, s.d_out, (size_t)W * H * 3 / 2, cudaMemcpyDeviceToHost, a->s_down));
         }
+        if (a->preview_w)
+            OB_CUDA(cudaMemcpyAsync(s.h_preview, s.d_preview, (size_t)a->preview_w * a->preview_h * 3, cudaMemcpyDeviceToHost, a->s_down));
         OB_CUDA(cudaEventRecord(s.done, a->s_down));
         // the next frame's upload into this slot's device buffers must not start before this stitch has read them;
         // slots are reused only after pop(), which waits for `done` (ordered after `stitched`)
@@ -271,6 +307,7 @@ octvr_status octvr_async_pop(octvr_async* a)
         }
         std::lock_guard<std::mutex> lk(a->mtx);
         s.busy = false;
+        a->last_preview = s.h_preview;
         a->popped++;
         auto now = std::chrono::steady_clock::now();
         a->stamps.push_back(now);
@@ -283,6 +320,20 @@ octvr_status octvr_async_pop(octvr_async* a)
 octvr_status octvr_async_fps(octvr_async* a, double* fps)
 {
     return guard([&] { OB_CHECK(a && fps, "null argument"); std::lock_guard<std::mutex> lk(a->mtx); *fps = a->fps; });
+}
+
+octvr_status octvr_async_preview(octvr_async* a, const uint8_t** rgb, size_t* pitch, int* w, int* h)
+{
+    return guard([&] {
+        OB_CHECK(a && rgb, "null argument");
+        std::lock_guard<std::mutex> lk(a->mtx);
+        OB_CHECK(a->preview_w > 0, "no preview size was given to octvr_async_create");
+        OB_CHECK(a->last_preview, "no frame popped yet");
+        *rgb = a->last_preview;
+        if (pitch) *pitch = (size_t)a->preview_w * 3;
+        if (w) *w = a->preview_w;
+        if (h) *h = a->preview_h;
+    });
 }
 
 void octvr_async_destroy(octvr_async* a) { delete a; }

@@ -77,6 +77,8 @@ octvr_mapper::~octvr_mapper()
     cudaSetDevice(device);
     for (auto p : d_rgbx) cudaFree(p);
     for (auto p : d_vig) cudaFree(p);
+    for (auto p : d_ov_coords) cudaFree(p);
+    cudaFree(d_rgb_scaled); delete scale_plan; delete preview_plan;
     cudaFree(d_tile_job_start); cudaFree(d_job_cam); cudaFree(d_coords); cudaFree(d_weights); cudaFree(d_jobs); cudaFree(d_entries); cudaFree(d_tmaps); cudaFree(d_fjobs); cudaFree(d_fbins); cudaFree(d_fitems);
     cudaFree(d_smask); cudaFree(d_gcoord); cudaFree(d_partial); cudaFree(d_ticket); cudaFree(d_gsamples); cudaFree(d_gchunks); cudaFree(d_gtotals);
     cudaFree(d_gains); cudaFree(d_gain_f32); cudaFree(d_gain_flag); cudaFree(d_gain_lut); cudaFree(d_rgb); cudaFree(d_dbg);
@@ -265,19 +267,23 @@ static void build_mapper(octvr_mapper& m, const octvr_template& t, const int* in
                          int blend, bool enable_gain, int scale_w, int scale_h, int band_y0, int band_y1)
 {
     const int n = (int)t.inputs.size();
-    OB_CHECK(n >= 1 && n <= MAX_CAMS, "1..16 inputs supported");
-    OB_CHECK(n_in == n + (int)t.overlays.size(), "in_sizes must list every input and overlay");
-    if (!t.overlays.empty()) fail(OCTVR_ERR_UNSUPPORTED, "overlay inputs are not implemented yet");
-    if ((scale_w || scale_h) && (scale_w != t.out_w || scale_h != t.out_h))
-        fail(OCTVR_ERR_UNSUPPORTED, "scale_output != template size is not implemented yet");
+    const int n_ov = (int)t.overlays.size();
+    OB_CHECK(n >= 1 && n + n_ov <= MAX_CAMS, "1..16 inputs (including overlays) supported");
+    OB_CHECK(n_in == n + n_ov, "in_sizes must list every input and overlay");
     if (n == 1) { enable_gain = false; blend = 0; }        // mapper.cpp:78-82
-    m.n = n; m.out_w = t.out_w; m.out_h = t.out_h; m.blend = blend; m.gain = enable_gain;
+    m.n = n; m.n_ov = n_ov; m.out_w = t.out_w; m.out_h = t.out_h; m.blend = blend; m.gain = enable_gain;
+    // scaled_output_size = scale_output.area() == 0 ? mt.out_size : scale_output (mapper.cpp:68)
+    const bool scaled = scale_w > 0 && scale_h > 0 && (scale_w != t.out_w || scale_h != t.out_h);
+    m.scaled_w = scaled ? scale_w : t.out_w; m.scaled_h = scaled ? scale_h : t.out_h;
+    OB_CHECK(m.scaled_w % 2 == 0 && m.scaled_h % 2 == 0, "scale_output must be even (4:2:0)");
     if (band_y0 == 0 && band_y1 == 0) band_y1 = t.out_h;
+    if ((band_y0 != 0 || band_y1 != t.out_h) && (n_ov > 0 || scaled))
+        fail(OCTVR_ERR_UNSUPPORTED, "row-band mappers do not take overlays or scale_output");
     OB_CHECK(band_y0 >= 0 && band_y0 < band_y1 && band_y1 <= t.out_h, "row band must lie inside the output");
     OB_CHECK(band_y0 % 32 == 0 && (band_y1 % 32 == 0 || band_y1 == t.out_h), "row bands must be aligned to 32 output rows");
     m.band_y0 = band_y0; m.band_y1 = band_y1;
     OB_CHECK(t.out_w % 2 == 0 && t.out_h % 2 == 0, "output size must be even (4:2:0)");
-    for (int i = 0; i < n; i++) {
+    for (int i = 0; i < n + n_ov; i++) {
         int w = in_sizes[2 * i], h = in_sizes[2 * i + 1];
         OB_CHECK(w > 0 && h > 0 && w % 2 == 0 && h % 2 == 0, "input sizes must be positive and even (async.cpp:44-46)");
         OB_CHECK((int64_t)w * h < (int64_t)1 << 30, "input too large");
@@ -285,10 +291,11 @@ static void build_mapper(octvr_mapper& m, const octvr_template& t, const int* in
     }
 
     // ---- per-camera source planes ----
-    for (int i = 0; i < n; i++) {
+    for (int i = 0; i < n + n_ov; i++) {
         float* dv = nullptr;
-        if (!t.inputs[i].vignette.empty()) {               // mapper.cpp:108-112
-            Img<float> v = resize_linear(t.inputs[i].vignette, m.in_w[i], m.in_h[i]);
+        const TInput& ti = i < n ? t.inputs[i] : t.overlays[i - n];
+        if (!ti.vignette.empty()) {                        // mapper.cpp:108-112, 121-126
+            Img<float> v = resize_linear(ti.vignette, m.in_w[i], m.in_h[i]);
             dv = dev_upload(v.d.data(), v.d.size());
         }
         m.d_vig.push_back(dv);
@@ -311,11 +318,27 @@ static void build_mapper(octvr_mapper& m, const octvr_template& t, const int* in
         // measured slower per frame than convert + staged blend because the conversion no longer hides the latency of the
         // gain launch -- DESIGN.md section 4); default: K_convert(+gain) then K_blend_staged, or K_blend (OCTVR_BLEND=direct)
         const char* mode = getenv("OCTVR_BLEND");
-        if (mode && std::string(mode) == "fused") build_fused(m, t, sx, sy, W);
+        if (mode && std::string(mode) == "fused" && n_ov == 0) build_fused(m, t, sx, sy, W);   // overlays need the RGBX planes
     }
     // RGBX planes written by K_convert: only the two-kernel and multiband paths need them
     if (!m.fused)
-        for (int i = 0; i < n; i++) m.d_rgbx.push_back(dev_alloc<uint32_t>((size_t)m.in_w[i] * m.in_h[i] + 4));
+        for (int i = 0; i < n + n_ov; i++) m.d_rgbx.push_back(dev_alloc<uint32_t>((size_t)m.in_w[i] * m.in_h[i] + 4));
+    // overlay inputs: one table entry per roi pixel (cv::remap fixed point; valid <=> mask), mapper.cpp:116-127
+    for (int k = 0; k < n_ov; k++) {
+        const TInput& in = t.overlays[k];
+        Img<int32_t> ox, oy;
+        quantise_map(in.map1, in.map2, m.in_w[n + k], m.in_h[n + k], ox, oy);
+        std::vector<uint2> ce((size_t)in.roi.w * in.roi.h);
+        for (int y = 0; y < in.roi.h; y++)
+            for (int x = 0; x < in.roi.w; x++)
+                ce[(size_t)y * in.roi.w + x] = make_entry(ox.row(y)[x], oy.row(y)[x], m.in_w[n + k], m.in_h[n + k], in.mask.row(y)[x] != 0);
+        m.d_ov_coords.push_back(dev_upload(ce.data(), ce.size()));
+        m.ov_roi.push_back(in.roi);
+    }
+    if (scaled) {
+        m.scale_plan = ob::resize_plan_create(t.out_w, t.out_h, m.scaled_w, m.scaled_h);
+        m.d_rgb_scaled = dev_alloc<uint8_t>((size_t)m.scaled_w * m.scaled_h * 3, true);
+    }
 
     if (blend > 0) {
         m.mb = ob::multiband_create(m, t, sx, sy);
@@ -578,30 +601,41 @@ static void check_frame(const octvr_frame& f, int w, int h, const char* what)
 
 namespace ob {
 void mapper_stitch_internal(octvr_mapper& m, const octvr_frame* in, int n_in, const octvr_frame* out,
-                            const double* gains, int n_gains, const double* d_gains_src, cudaStream_t s);
+                            const double* gains, int n_gains, const double* d_gains_src, cudaStream_t s,
+                            uint8_t* d_preview, size_t preview_pitch, int preview_w, int preview_h);
 }
 static void do_stitch(octvr_mapper& m, const octvr_frame* in, int n_in, const octvr_frame* out,
-                      const double* gains, int n_gains, cudaStream_t s)
+                      const double* gains, int n_gains, cudaStream_t s,
+                      uint8_t* d_preview = nullptr, size_t preview_pitch = 0, int preview_w = 0, int preview_h = 0)
 {
-    ob::mapper_stitch_internal(m, in, n_in, out, gains, n_gains, nullptr, s);
+    ob::mapper_stitch_internal(m, in, n_in, out, gains, n_gains, nullptr, s, d_preview, preview_pitch, preview_w, preview_h);
 }
 
 // gains: host array of predefined gains, or d_gains_src: another mapper's device gains (gain sharing between
 // output regions, async.cpp:75-86), or neither: computed from this frame.
-void ob::mapper_stitch_internal(octvr_mapper& m, const octvr_frame* in, int n_in, const octvr_frame* out,
-                                const double* gains, int n_gains, const double* d_gains_src, cudaStream_t s)
+void ob::mapper_stitch_internal(octvr_mapper& m, const octvr_frame* in, int n_in, const octvr_frame* user_out,
+                                const double* gains, int n_gains, const double* d_gains_src, cudaStream_t s,
+                                uint8_t* d_preview, size_t preview_pitch, int preview_w, int preview_h)
 {
-    OB_CHECK(n_in == m.n, "wrong number of input frames");           // mapper.cpp:208
+    const int n_all = m.n + m.n_ov;
+    OB_CHECK(n_in == n_all, "wrong number of input frames");         // mapper.cpp:208
     OB_CUDA(cudaSetDevice(m.device));
-    for (int i = 0; i < m.n; i++) check_frame(in[i], m.in_w[i], m.in_h[i], "bad input frame");
-    if (out) check_frame(*out, m.out_w, m.out_h, "bad output frame");
-    OB_CHECK(out || m.keep_rgb, "no output requested");
+    for (int i = 0; i < n_all; i++) check_frame(in[i], m.in_w[i], m.in_h[i], "bad input frame");
+    if (user_out) check_frame(*user_out, m.scaled_w, m.scaled_h, "bad output frame");
+    OB_CHECK(user_out || m.keep_rgb || d_preview, "no output requested");
+    if (d_preview) OB_CHECK(preview_w > 0 && preview_h > 0 && preview_pitch >= (size_t)preview_w * 3, "bad preview buffer");
+    // The blend kernels write the 4:2:0 output themselves unless something still has to happen to the RGB result
+    // (overlays copied over it, resize to scale_output: mapper.cpp:279-306); those go through post.cu.
+    const bool scaled = m.scale_plan != nullptr;
+    const bool post_yuv = m.n_ov > 0 || scaled;
+    const octvr_frame* out = post_yuv ? nullptr : user_out;
+    m.rgb_this_frame = m.keep_rgb || post_yuv || d_preview != nullptr;
     if (m.profiling) OB_CUDA(cudaEventRecord(m.ev[0], s));
 
     ConvertParams cp;                 // also describes the input planes for the fused kernel
     memset(&cp, 0, sizeof(cp));
-    cp.n = m.n;
-    for (int i = 0; i < m.n; i++) {
+    cp.n = n_all;
+    for (int i = 0; i < n_all; i++) {
         CamSrc& c = cp.cam[i];
         c.y = in[i].y; c.u = in[i].u; c.v = in[i].v;
         c.y_pitch = (uint32_t)in[i].y_pitch; c.u_pitch = (uint32_t)in[i].u_pitch; c.v_pitch = (uint32_t)in[i].v_pitch;
@@ -641,7 +675,7 @@ void ob::mapper_stitch_internal(octvr_mapper& m, const octvr_frame* in, int n_in
     }
     if (m.profiling) OB_CUDA(cudaEventRecord(m.ev[2], s));
 
-    if (m.keep_rgb && !m.d_rgb) m.d_rgb = dev_alloc<uint8_t>((size_t)m.out_w * m.out_h * 3, true);
+    if (m.rgb_this_frame && !m.d_rgb) m.d_rgb = dev_alloc<uint8_t>((size_t)m.out_w * m.out_h * 3, true);
     if (m.mb) {
         ob::multiband_stitch(m, out, s);
     } else if (m.fused) {
@@ -656,7 +690,7 @@ void ob::mapper_stitch_internal(octvr_mapper& m, const octvr_frame* in, int n_in
             fp.oy_pitch = (uint32_t)out->y_pitch; fp.ou_pitch = (uint32_t)out->u_pitch; fp.ov_pitch = (uint32_t)out->v_pitch;
             fp.uv_step = out->uv_pixel_stride;
         }
-        fp.rgb_out = m.keep_rgb ? m.d_rgb : nullptr; fp.rgb_pitch = (uint32_t)m.out_w * 3;
+        fp.rgb_out = m.rgb_this_frame ? m.d_rgb : nullptr; fp.rgb_pitch = (uint32_t)m.out_w * 3;
         fp.gain_f32 = m.d_gain_f32; fp.gain_flag = m.d_gain_flag; fp.gain_lut = m.d_gain_lut;
         fp.use_gain = m.gain ? 1 : 0;
         fp.inv_n = m.inv_n;
@@ -673,7 +707,7 @@ void ob::mapper_stitch_internal(octvr_mapper& m, const octvr_frame* in, int n_in
             sp.oy_pitch = (uint32_t)out->y_pitch; sp.ou_pitch = (uint32_t)out->u_pitch; sp.ov_pitch = (uint32_t)out->v_pitch;
             sp.uv_step = out->uv_pixel_stride;
         }
-        sp.rgb_out = m.keep_rgb ? m.d_rgb : nullptr; sp.rgb_pitch = (uint32_t)m.out_w * 3;
+        sp.rgb_out = m.rgb_this_frame ? m.d_rgb : nullptr; sp.rgb_pitch = (uint32_t)m.out_w * 3;
         sp.gain_f32 = m.d_gain_f32; sp.gain_flag = m.d_gain_flag; sp.gain_lut = m.d_gain_lut;
         sp.use_gain = m.gain ? 1 : 0;
         sp.inv_n = m.inv_n;
@@ -690,11 +724,27 @@ void ob::mapper_stitch_internal(octvr_mapper& m, const octvr_frame* in, int n_in
             bp.oy_pitch = (uint32_t)out->y_pitch; bp.ou_pitch = (uint32_t)out->u_pitch; bp.ov_pitch = (uint32_t)out->v_pitch;
             bp.uv_step = out->uv_pixel_stride;
         }
-        bp.rgb_out = m.keep_rgb ? m.d_rgb : nullptr; bp.rgb_pitch = (uint32_t)m.out_w * 3;
+        bp.rgb_out = m.rgb_this_frame ? m.d_rgb : nullptr; bp.rgb_pitch = (uint32_t)m.out_w * 3;
         bp.gain_f32 = m.d_gain_f32; bp.gain_flag = m.d_gain_flag; bp.gain_lut = m.d_gain_lut;
         bp.use_gain = m.gain ? 1 : 0;
         bp.inv_n = m.inv_n;
         launch_blend(bp, s);
+    }
+    // ---- after the blender: overlays, scale_output, preview (mapper.cpp:279-312) ----
+    for (int k = 0; k < m.n_ov; k++)
+        launch_overlay(m.d_rgbx[m.n + k], m.in_w[m.n + k], m.d_ov_coords[k], m.ov_roi[k], m.d_rgb, (size_t)m.out_w * 3, s);
+    if (post_yuv && user_out) {
+        const uint8_t* src = m.d_rgb;
+        if (scaled) { launch_resize_rgb(*m.scale_plan, m.d_rgb, (size_t)m.out_w * 3, m.d_rgb_scaled, (size_t)m.scaled_w * 3, s); src = m.d_rgb_scaled; }
+        launch_rgb_to_yuv420(src, (size_t)m.scaled_w * 3, m.scaled_w, m.scaled_h, *user_out, s);
+    }
+    if (d_preview) {                  // cv::cuda::resize(result, preview_output, preview_output.size(), INTER_LINEAR), mapper.cpp:308-312
+        if (!m.preview_plan || m.preview_plan->dw != preview_w || m.preview_plan->dh != preview_h) {
+            if (m.preview_plan && m.last_stream_valid) OB_CUDA(cudaStreamSynchronize(m.last_stream));   // tables may still be in use
+            delete m.preview_plan; m.preview_plan = nullptr;
+            m.preview_plan = ob::resize_plan_create(m.out_w, m.out_h, preview_w, preview_h);
+        }
+        launch_resize_rgb(*m.preview_plan, m.d_rgb, (size_t)m.out_w * 3, d_preview, preview_pitch, s);
     }
     if (m.profiling) OB_CUDA(cudaEventRecord(m.ev[3], s));
     OB_CUDA(cudaGetLastError());
@@ -743,9 +793,7 @@ octvr_status octvr_mapper_stitch(octvr_mapper* m, const octvr_frame* d_inputs, i
 {
     return guard([&] {
         OB_CHECK(m && d_inputs, "null argument");
-        (void)preview_pitch; (void)preview_w; (void)preview_h;
-        if (d_preview_rgb) fail(OCTVR_ERR_UNSUPPORTED, "preview output is not implemented yet");
-        do_stitch(*m, d_inputs, n_inputs, d_output, gains, n_gains, (cudaStream_t)stream);
+        do_stitch(*m, d_inputs, n_inputs, d_output, gains, n_gains, (cudaStream_t)stream, d_preview_rgb, preview_pitch, preview_w, preview_h);
     });
 }
 
@@ -754,7 +802,7 @@ octvr_status octvr_mapper_stitch_packed(octvr_mapper* m, const uint8_t* const* d
 {
     return guard([&] {
         OB_CHECK(m && d_inputs && in_pitch && d_output, "null argument");
-        OB_CHECK(n_inputs == m->n, "wrong number of input frames");
+        OB_CHECK(n_inputs == m->n + m->n_ov, "wrong number of input frames");
         std::vector<octvr_frame> f(n_inputs);
         for (int i = 0; i < n_inputs; i++) {              // mapper.cpp:222-226
             uint8_t* b = const_cast<uint8_t*>(d_inputs[i]);
@@ -762,7 +810,7 @@ octvr_status octvr_mapper_stitch_packed(octvr_mapper* m, const uint8_t* const* d
             f[i].y_pitch = f[i].u_pitch = f[i].v_pitch = in_pitch[i]; f[i].uv_pixel_stride = 1;
         }
         octvr_frame o;                                     // mapper.cpp:296-302
-        o.y = d_output; o.u = d_output + (size_t)m->out_h * out_pitch; o.v = o.u + m->out_w / 2;
+        o.y = d_output; o.u = d_output + (size_t)m->scaled_h * out_pitch; o.v = o.u + m->scaled_w / 2;
         o.y_pitch = o.u_pitch = o.v_pitch = out_pitch; o.uv_pixel_stride = 1;
         do_stitch(*m, f.data(), n_inputs, &o, gains, n_gains, (cudaStream_t)stream);
     });

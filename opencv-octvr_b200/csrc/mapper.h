@@ -3,6 +3,7 @@
 #include "common.h"
 #include "kernels.cuh"
 #include "template.h"
+#include "post.h"
 
 namespace ob { struct Multiband; }
 
@@ -44,7 +45,16 @@ struct octvr_mapper {
     int* d_gain_flag = nullptr; uint8_t* d_gain_lut = nullptr; double* h_gains = nullptr;
     // optional RGB result (Mapper::result)
     bool keep_rgb = false;
+    bool rgb_this_frame = false;        // keep_rgb, or the after-blend stages below need the RGB888 result of this stitch
     uint8_t* d_rgb = nullptr;
+    // after-blend stages (post.cu; mapper.cpp:279-312): overlay inputs, scale_output, preview
+    int n_ov = 0;                       // overlay inputs follow the n blended inputs in every per-input array
+    std::vector<uint2*> d_ov_coords;
+    std::vector<ob::Rect> ov_roi;
+    int scaled_w = 0, scaled_h = 0;     // size of the 4:2:0 output (== out_w x out_h unless scale_output differs)
+    uint8_t* d_rgb_scaled = nullptr;
+    ob::ResizePlan* scale_plan = nullptr;
+    ob::ResizePlan* preview_plan = nullptr;
     // multiband state (blend > 0)
     ob::Multiband* mb = nullptr;
     // bookkeeping

@@ -10,8 +10,8 @@
 //   k_mb_down      Gaussian pyramid level l -> l+1 per camera ([1 4 6 4 1]^2, (v+128)>>8, REFLECT_101), 16S
 //   k_mb_band      per destination level: sum over cameras of (short)((G_l - pyrUp(G_{l+1})) * W_l), then
 //                  (short)(sum / (sumW + 1e-5))  -- Laplacian, weighting, accumulation and normalisation fused
-//   k_mb_collapse  dst_{l-1} += pyrUp(dst_l) (saturating); the last level also masks, narrows to 8 bit and writes
-//                  RGB / YUV 4:2:0
+//   k_mb_collapse  dst_{l-1} += pyrUp(dst_l) (saturating), levels >= 1
+//   k_mb_final     level-0 band computed in registers + pyrUp(dst_1), mask, 8-bit narrowing, RGB / YUV 4:2:0 store
 #include "mapper.h"
 #include "prep.h"
 #include "device_common.cuh"
@@ -308,11 +308,24 @@ __global__ void __launch_bounds__(256) k_mb_collapse(const __grid_constant__ MbP
     }
 }
 
-// ---- k_mb_final: level 1 -> 0 collapse fused with mask, 8-bit narrowing and the output store; one thread per FOUR
-//      OUTPUT-FRAME pixels (pixels outside the result roi are black) ----
+// ---- k_mb_final: destination level 0 never exists in memory.  One thread per FOUR OUTPUT-FRAME pixels computes the level-0
+//      band (k_mb_band with l = 0: Laplacian, weighting, accumulation over the cameras, normalisation), adds pyrUp(dst_1)
+//      (the last collapse step), masks, narrows to 8 bit and stores RGB / YUV 4:2:0.  Pixels outside the result roi are
+//      black.  Saves the 8 B/px write + read of dst_0 and one launch. ----
 __global__ void __launch_bounds__(256) k_mb_final(const __grid_constant__ MbParams p)
 {
     const int X0 = (blockIdx.x * 32 + threadIdx.x) * 4, Y = p.oy0 + blockIdx.y * 8 + threadIdx.y;
+    // cameras with a non-zero level-0 weight somewhere under this CTA (128 x 8 output pixels = up to 5 x 2 weight tiles)
+    unsigned cams = 0;
+    {
+        const int tiles_x = (p.lw[0] + 31) / 32, tiles_y = (p.lh[0] + 7) / 8;
+        const int xs = (int)blockIdx.x * 128 - p.rx, ys = p.oy0 + (int)blockIdx.y * 8 - p.ry;
+        const int tx0 = max(xs, 0) >> 5, tx1 = min((xs + 127) >> 5, tiles_x - 1);
+        const int ty0 = max(ys, 0) >> 3, ty1 = min((ys + 7) >> 3, tiles_y - 1);
+        if (xs + 127 >= 0 && ys + 7 >= 0)
+            for (int ty = ty0; ty <= ty1; ty++)
+                for (int tx = tx0; tx <= tx1; tx++) cams |= __ldg(p.tile_cams + p.off_t[0] + (size_t)ty * tiles_x + tx);
+    }
     if (X0 >= p.out_w || Y >= p.oy1) return;
     int R[4], G[4], B[4];
     #pragma unroll
@@ -328,13 +341,44 @@ __global__ void __launch_bounds__(256) k_mb_final(const __grid_constant__ MbPara
             any = any || dw[q] > 1e-5f;                                // dst_mask = dst_band_weights_[0] > WEIGHT_EPS (blenders.cpp:472)
         }
         if (any) {
+            int acc[4][3];
+            #pragma unroll
+            for (int q = 0; q < 4; q++) acc[q][0] = acc[q][1] = acc[q][2] = 0;
+            for (; cams; cams &= cams - 1) {
+                const int c = __ffs(cams) - 1;
+                const MbCam& cam = p.cam[c];
+                const int cx0 = x0 - cam.x0, cy = y - cam.y0;
+                if (cy < 0 || cy >= cam.bh || cx0 + 3 < 0 || cx0 >= cam.bw) continue;
+                float w[4];
+                bool anyw = false;
+                #pragma unroll
+                for (int q = 0; q < 4; q++) {
+                    const int x = cx0 + q;
+                    w[q] = (x >= 0 && x < cam.bw && dw[q] > 1e-5f) ? __ldg(p.w + cam.off_w[0] + (size_t)cy * cam.bw + x) : 0.f;
+                    anyw = anyw || w[q] != 0.f;
+                }
+                if (!anyw) continue;
+                int3 up[4];
+                if (p.nb > 0) pyrup4(p.g + cam.off_g[1], cam.bw >> 1, cam.bh >> 1, cx0, cy, up);
+                #pragma unroll
+                for (int q = 0; q < 4; q++) {
+                    if (w[q] == 0.f) continue;
+                    int3 gl = ld3(p.g0 + cam.off_g[0], cy * cam.bw + cx0 + q);
+                    if (p.nb > 0) gl = make_int3(sat16(gl.x - up[q].x), sat16(gl.y - up[q].y), sat16(gl.z - up[q].z));
+                    acc[q][0] += __float2int_rz(__fmul_rn((float)gl.x, w[q]));
+                    acc[q][1] += __float2int_rz(__fmul_rn((float)gl.y, w[q]));
+                    acc[q][2] += __float2int_rz(__fmul_rn((float)gl.z, w[q]));
+                }
+            }
             int3 up[4];
             if (p.nb > 0) pyrup4(p.dst + p.off_d[1], p.lw[1], p.lh[1], x0, y, up);
             #pragma unroll
             for (int q = 0; q < 4; q++) {
                 if (!(dw[q] > 1e-5f)) continue;
-                const short4 cur = p.dst[p.off_d[0] + (size_t)y * p.lw[0] + x0 + q];
-                int3 v = make_int3(cur.x, cur.y, cur.z);
+                const float den = __fadd_rn(dw[q], 1e-5f);            // normalizeUsingWeightMap (blenders.cpp:788-797)
+                int3 v = make_int3((short)__float2int_rz(__fdiv_rn((float)(short)acc[q][0], den)),
+                                   (short)__float2int_rz(__fdiv_rn((float)(short)acc[q][1], den)),
+                                   (short)__float2int_rz(__fdiv_rn((float)(short)acc[q][2], den)));
                 if (p.nb > 0) v = make_int3(sat16(up[q].x + v.x), sat16(up[q].y + v.y), sat16(up[q].z + v.z));
                 R[q] = clamp255(v.x); G[q] = clamp255(v.y); B[q] = clamp255(v.z);   // convertTo(CV_8U)
             }
@@ -521,7 +565,7 @@ Multiband* multiband_create(octvr_mapper& m, const octvr_template& t,
     p.coords = mb->d_coords; p.g0 = mb->d_g0; p.g = mb->d_g; p.w = mb->d_w; p.dst = mb->d_dst; p.dstw = mb->d_dstw;
     for (int i = 0; i < n; i++) { p.rgbx[i] = m.d_rgbx[i]; p.src_pitch[i] = m.in_w[i]; }
     m.table_bytes = (int64_t)(coords.size() * sizeof(uint2) + wts.size() * 4 + dstw.size() * 4);
-    mb->launches = 1 + nb + (nb + 1) + std::max(0, nb - 1) + 1;
+    mb->launches = 1 + nb + nb + std::max(0, nb - 1) + 1;
     return mb.release();
 }
 
@@ -535,13 +579,13 @@ void multiband_stitch(octvr_mapper& m, const octvr_frame* out, cudaStream_t s)
         p.oy_pitch = (uint32_t)out->y_pitch; p.ou_pitch = (uint32_t)out->u_pitch; p.ov_pitch = (uint32_t)out->v_pitch;
         p.uv_step = out->uv_pixel_stride;
     }
-    p.rgb_out = m.keep_rgb ? m.d_rgb : nullptr; p.rgb_pitch = (uint32_t)m.out_w * 3;
+    p.rgb_out = m.rgb_this_frame ? m.d_rgb : nullptr; p.rgb_pitch = (uint32_t)m.out_w * 3;
     const int nb = p.nb, n = p.n;
     if (mb.n_chunks) k_mb_warp<<<mb.n_chunks, 256, 0, s>>>(p);
     if (p.lh[0] > 0 && mb.max_bh > 0) {                    // an empty row window (a band outside the result roi) only writes black
         for (int l = 0; l < nb; l++)
             k_mb_down<<<dim3(((mb.max_bw >> (l + 1)) + 31) / 32, ((mb.max_bh >> (l + 1)) + 31) / 32, n), dim3(32, 8), 0, s>>>(p, l);
-        for (int l = nb; l >= 0; l--)
+        for (int l = nb; l >= 1; l--)                       // level 0 is computed inside k_mb_final
             k_mb_band<<<dim3((p.lw[l] + 127) / 128, (p.lh[l] + 7) / 8), dim3(32, 8), 0, s>>>(p, l);
         for (int l = nb; l >= 2; l--)
             k_mb_collapse<<<dim3((p.lw[l - 1] + 127) / 128, (p.lh[l - 1] + 7) / 8), dim3(32, 8), 0, s>>>(p, l);

@@ -113,6 +113,17 @@ Img<uint8_t> resize_linear(const Img<uint8_t>& src, int dw, int dh)
     return dst;
 }
 
+void resize_linear_tables(int src, int dst, bool clamp_ofs, std::vector<int>& ofs, std::vector<short>& coef)
+{
+    Axis a = linear_axis(src, dst, clamp_ofs);
+    ofs = a.ofs;
+    coef.resize(2 * (size_t)dst);
+    for (int d = 0; d < dst; d++) {
+        coef[2 * d] = to_short(round_he((1.f - a.frac[d]) * 2048));
+        coef[2 * d + 1] = to_short(round_he(a.frac[d] * 2048));
+    }
+}
+
 Img<float> resize_linear(const Img<float>& src, int dw, int dh)
 {
     OB_CHECK(!src.empty() && dw > 0 && dh > 0, "resize: empty");

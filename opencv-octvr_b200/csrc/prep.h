@@ -11,6 +11,9 @@ Img<float> chamfer_l2(const Img<uint8_t>& mask);
 // cv::resize(..., INTER_LINEAR) for 8UC1 (imgwarp.cpp:3224-3500,1387-1500) and 32FC1.
 Img<uint8_t> resize_linear(const Img<uint8_t>& src, int dw, int dh);
 Img<float> resize_linear(const Img<float>& src, int dw, int dh);
+// per destination index: source offset (x: clamped to [0, src-1]; y: unclamped, imgwarp.cpp:3404-3447) and the two
+// 11-bit coefficients {round((1-f)*2048), round(f*2048)} of the 8-bit INTER_LINEAR path
+void resize_linear_tables(int src, int dst, bool clamp_ofs, std::vector<int>& ofs, std::vector<short>& coef);
 // cv::pyrDown for 32FC1 (pyramids.cpp:849-964 incl. the SSE association of :143-185)
 Img<float> pyrdown_f32(const Img<float>& src);
 

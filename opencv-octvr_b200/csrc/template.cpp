@@ -179,6 +179,27 @@ octvr_status octvr_template_from_arrays(int out_w, int out_h, int n, const int* 
     });
 }
 
+octvr_status octvr_template_add_overlay(octvr_template* t, const int* roi, const float* map1, const float* map2,
+                                        const uint8_t* mask, const float* vignette, int vig_w, int vig_h)
+{
+    return guard([&] {
+        OB_CHECK(t && roi && map1 && map2 && mask, "null argument");
+        TInput in;
+        in.roi = Rect{ roi[0], roi[1], roi[2], roi[3] };
+        OB_CHECK(in.roi.w > 0 && in.roi.h > 0, "empty ROI");
+        const size_t area = (size_t)in.roi.w * in.roi.h;
+        in.map1 = Img<float>(in.roi.w, in.roi.h); memcpy(in.map1.d.data(), map1, area * 4);
+        in.map2 = Img<float>(in.roi.w, in.roi.h); memcpy(in.map2.d.data(), map2, area * 4);
+        in.mask = Img<uint8_t>(in.roi.w, in.roi.h); memcpy(in.mask.d.data(), mask, area);
+        if (vignette) {
+            OB_CHECK(vig_w > 0 && vig_h > 0, "vignette size");
+            in.vignette = Img<float>(vig_w, vig_h); memcpy(in.vignette.d.data(), vignette, (size_t)vig_w * vig_h * 4);
+        }
+        check_input(in, t->out_w, t->out_h);
+        t->overlays.push_back(std::move(in));
+    });
+}
+
 octvr_status octvr_template_create_masks(octvr_template* t)
 {
     return guard([&] { OB_CHECK(t, "null argument"); t->seam_masks = distance_seam_masks(t->inputs, t->out_w); });

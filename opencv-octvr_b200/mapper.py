@@ -48,8 +48,9 @@ class MapperTemplate:
         return cls(h)
 
     @classmethod
-    def from_arrays(cls, out_size, inputs, seam_masks=None):
-        """inputs: dicts with roi (x,y,w,h), map1, map2, mask[, vignette] -- the fields of MapperTemplate::Input."""
+    def from_arrays(cls, out_size, inputs, seam_masks=None, overlays=()):
+        """inputs / overlays: dicts with roi (x,y,w,h), map1, map2, mask[, vignette] -- the fields of MapperTemplate::Input
+        (octvr.hpp:55-63: `inputs` and `overlay_inputs`)."""
         n = len(inputs)
         rois = np.ascontiguousarray(np.array([d["roi"] for d in inputs], np.int32).reshape(n, 4))
         m1 = [np.ascontiguousarray(d["map1"], np.float32) for d in inputs]
@@ -67,7 +68,16 @@ class MapperTemplate:
                                                _np_ptr_array(sm) if sm else None,
                                                _np_ptr_array(vg) if any(v is not None for v in vg) else None,
                                                vw, vh, C.byref(h)))
-        return cls(h)
+        t = cls(h)
+        for d in overlays:
+            roi = (C.c_int * 4)(*[int(v) for v in d["roi"]])
+            a1, a2, ak = (np.ascontiguousarray(d["map1"], np.float32), np.ascontiguousarray(d["map2"], np.float32),
+                          np.ascontiguousarray(d["mask"], np.uint8))
+            v = np.ascontiguousarray(d["vignette"], np.float32) if d.get("vignette") is not None else None
+            check(lib().octvr_template_add_overlay(t._h, roi, a1.ctypes.data_as(C.c_void_p), a2.ctypes.data_as(C.c_void_p),
+                                                   ak.ctypes.data_as(C.c_void_p), v.ctypes.data_as(C.c_void_p) if v is not None else None,
+                                                   v.shape[1] if v is not None else 0, v.shape[0] if v is not None else 0))
+        return t
 
     # -- accessors -------------------------------------------------------------------------------
     @property
@@ -79,6 +89,10 @@ class MapperTemplate:
     @property
     def num_inputs(self):
         return lib().octvr_template_num_inputs(self._h)
+
+    @property
+    def num_overlays(self):
+        return lib().octvr_template_num_overlays(self._h)
 
     def input(self, i):
         roi = (C.c_int * 4)()
@@ -159,10 +173,13 @@ class Mapper:
                                                  int(bool(enable_gain_compensator)), int(band[0]), int(band[1]),
                                                  int(device), C.byref(h)))
         self._h = h
-        self.out_size = tmpl.out_size
+        so = tuple(int(v) for v in scale_output)
+        self.out_size = so if so[0] > 0 and so[1] > 0 else tmpl.out_size      # scaled_output_size, mapper.cpp:68
+        self.stitch_size = tmpl.out_size
 
-    def stitch(self, inputs, output, gains=None, stream=None):
-        """inputs: list of (y,u,v) CUDA u8 tensors; output: (y,u,v) CUDA u8 tensors (written in place).
+    def stitch(self, inputs, output, gains=None, stream=None, preview=None):
+        """inputs: list of (y,u,v) CUDA u8 tensors (blended inputs, then overlays); output: (y,u,v) CUDA u8 tensors (written
+        in place); preview: optional (ph, pw, 3) CUDA u8 tensor, the result resized into it (mapper.cpp:308-312).
         Asynchronous on `stream` (default: torch's current stream)."""
         torch = self._torch
         s = stream if stream is not None else torch.cuda.current_stream(self.device)
@@ -173,7 +190,11 @@ class Mapper:
         if gains is not None:
             ng = len(gains)
             g = (C.c_double * ng)(*[float(v) for v in gains])
-        check(lib().octvr_mapper_stitch(self._h, fin, len(inputs), C.byref(fout) if fout is not None else None, None, 0, 0, 0,
+        pv, pp, pw, ph = None, 0, 0, 0
+        if preview is not None:
+            assert preview.dim() == 3 and preview.shape[2] == 3 and preview.stride(2) == 1 and preview.stride(1) == 3
+            pv, pp, pw, ph = C.c_void_p(preview.data_ptr()), preview.stride(0), preview.shape[1], preview.shape[0]
+        check(lib().octvr_mapper_stitch(self._h, fin, len(inputs), C.byref(fout) if fout is not None else None, pv, C.c_size_t(pp), pw, ph,
                                         g, ng, C.c_void_p(s.cuda_stream)))
 
     def stitch_packed(self, inputs, output, gains=None, stream=None):
@@ -194,7 +215,7 @@ class Mapper:
         check(lib().octvr_mapper_set_keep_rgb(self._h, int(on)))
 
     def result_rgb(self):
-        w, h = self.out_size
+        w, h = self.stitch_size
         out = np.empty((h, w, 3), np.uint8)
         check(lib().octvr_mapper_result_rgb(self._h, out.ctypes.data_as(C.c_void_p), C.c_size_t(w * 3)))
         return out
@@ -271,6 +292,13 @@ class AsyncMultiMapper:
         v = C.c_double()
         check(lib().octvr_async_fps(self._h, C.byref(v)))
         return v.value
+
+    def preview(self):
+        """(ph, pw, 3) RGB preview of the frame popped last (copy)."""
+        p = C.POINTER(C.c_uint8)()
+        pitch, w, h = C.c_size_t(), C.c_int(), C.c_int()
+        check(lib().octvr_async_preview(self._h, C.byref(p), C.byref(pitch), C.byref(w), C.byref(h)))
+        return np.ctypeslib.as_array(p, shape=(h.value, pitch.value))[:, :w.value * 3].reshape(h.value, w.value, 3).copy()
 
     def close(self):
         if self._h:

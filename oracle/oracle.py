@@ -128,6 +128,20 @@ def resize_linear(src, dw, dh):
     return dst
 
 
+def resize_rgb(src, dw, dh):
+    """cv::resize(src, dsize, 0, 0, INTER_LINEAR) for 8-bit images as Mapper::stitch calls it (mapper.cpp:290-294,308-312):
+    equal sizes copy (imgwarp.cpp:3261-3265), exact 2x reductions take the INTER_AREA fast path (imgwarp.cpp:3299-3303,
+    ResizeAreaFastVec :2349-2390: (a + b + c + d + 2) >> 2), everything else the 11-bit fixed-point bilinear."""
+    src = np.ascontiguousarray(src)
+    sh, sw = src.shape[:2]
+    if (sw, sh) == (dw, dh):
+        return src.copy()
+    if sw == 2 * dw and sh == 2 * dh:
+        s = src.astype(np.int32)
+        return ((s[0::2, 0::2] + s[0::2, 1::2] + s[1::2, 0::2] + s[1::2, 1::2] + 2) >> 2).astype(np.uint8)
+    return resize_linear(src, dw, dh)
+
+
 def dist_l2_3x3(mask):
     mask = np.ascontiguousarray(mask, np.uint8)
     h, w = mask.shape
@@ -495,10 +509,20 @@ def split_packed(frame, w, h):
 class StitchOracle:
     """CPU contract for Mapper::Mapper + Mapper::stitch (mapper.cpp:47-323), stage by stage per SURVEY 8(c)."""
 
-    def __init__(self, tmpl, in_sizes, blend=128, enable_gain=True):
+    def __init__(self, tmpl, in_sizes, blend=128, enable_gain=True, scale_output=(0, 0)):
+        """in_sizes: blended inputs, then overlay inputs (mapper.cpp:84-127); scale_output: (0, 0) keeps the template size."""
         self.t = tmpl
         self.in_sizes = [tuple(s) for s in in_sizes]
         n = len(tmpl.inputs)
+        self.overlays = list(getattr(tmpl, "overlay_inputs", []))
+        assert len(self.in_sizes) == n + len(self.overlays)
+        ov_sizes = self.in_sizes[n:]
+        self.ov_mapx = [scale_map(d["map1"], s[0]) for d, s in zip(self.overlays, ov_sizes)]
+        self.ov_mapy = [scale_map(d["map2"], s[1]) for d, s in zip(self.overlays, ov_sizes)]
+        self.ov_vig = [resize_linear(d["vignette"], s[0], s[1]) if d.get("vignette") is not None else None
+                       for d, s in zip(self.overlays, ov_sizes)]
+        self.scale_output = tuple(scale_output) if scale_output[0] > 0 and scale_output[1] > 0 else tuple(tmpl.out_size)
+        self.last_preview = None
         if n == 1:
             enable_gain, blend = False, 0
         self.blend, self.enable_gain, self.n = blend, enable_gain, n
@@ -552,14 +576,32 @@ class StitchOracle:
         return result
 
     def stitch_rgb(self, frames_rgb, gains=None):
-        warped = self.warp(frames_rgb)
+        """Mapper::result: blended inputs, then the overlays copied over it through their masks (mapper.cpp:279-282; the
+        evident intent -- the reference copies from a buffer it never fills)."""
+        warped = self.warp(frames_rgb[:self.n])
         if self.enable_gain:
             g = self.gains_from(warped) if gains is None else np.asarray(gains, np.float64)
             self.last_gains = g
             warped = [mul_scalar(w, float(gi)) for w, gi in zip(warped, g)]
-        return self.blend_rgb(warped)
+        result = self.blend_rgb(warped)
+        for k, d in enumerate(self.overlays):
+            src = frames_rgb[self.n + k]
+            if self.ov_vig[k] is not None:
+                src = np.clip(np.rint(src.astype(np.float32) * self.ov_vig[k][:, :, None]), 0, 255).astype(np.uint8)
+            w = remap(src, self.ov_mapx[k], self.ov_mapy[k], True)
+            x, y, rw, rh = d["roi"]
+            m = d["mask"] != 0
+            result[y:y + rh, x:x + rw][m] = w[m]
+        return result
 
-    def stitch(self, frames_yuv, gains=None):
-        """frames_yuv: list of (y,u,v) plane triples.  Returns (y,u,v) of the stitched frame."""
+    def stitch(self, frames_yuv, gains=None, preview_size=None):
+        """frames_yuv: list of (y,u,v) plane triples.  Returns (y,u,v) of the stitched frame at scale_output size
+        (mapper.cpp:290-306); preview_size=(w, h) also leaves the preview (mapper.cpp:308-312) in self.last_preview."""
         rgb = [yuv420_to_rgb(*f) for f in frames_yuv]
-        return rgb_to_yuv420(self.stitch_rgb(rgb, gains))
+        result = self.stitch_rgb(rgb, gains)
+        self.last_result = result
+        if preview_size is not None:
+            self.last_preview = resize_rgb(result, preview_size[0], preview_size[1])
+        if self.scale_output != tuple(self.t.out_size):
+            result = resize_rgb(result, self.scale_output[0], self.scale_output[1])
+        return rgb_to_yuv420(result)

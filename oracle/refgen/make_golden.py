@@ -58,12 +58,15 @@ def read_container(path):
 
 
 def main():
+    only = sys.argv[1:]            # optional: regenerate only the named rigs / stitch cases (new fixtures without touching the others)
     os.makedirs(TMP, exist_ok=True)
     import oracle as O
     rigs_dir = os.path.join(GOLD, "rigs")
     widths = json.load(open(os.path.join(rigs_dir, "widths.json")))
     dump = os.path.join(B, "bin", "octvr_dump")
     for rig, w in widths.items():
+        if only and rig not in only:
+            continue
         dat = os.path.join(TMP, rig + ".dat")
         subprocess.check_call([dump, "-w", str(w), "-o", dat, os.path.join(rigs_dir, rig + ".json")],
                               stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
@@ -75,13 +78,25 @@ def main():
             if d["vignette"] is not None:
                 arrs["vig%d" % i] = d["vignette"]
             arrs["seam%d" % i] = t.seam_masks[i]
+        arrs["n_ov"] = np.array(len(t.overlay_inputs))
+        for i, d in enumerate(t.overlay_inputs):
+            arrs["ov_roi%d" % i] = np.array(d["roi"], np.int64)
+            arrs["ov_map1_%d" % i], arrs["ov_map2_%d" % i], arrs["ov_mask%d" % i] = d["map1"], d["map2"], d["mask"]
         np.savez_compressed(os.path.join(GOLD, "tmpl_%s.npz" % rig), **arrs)
         print("template", rig, t.out_size, len(t.inputs))
+        # digest of the reference tool's own file: the product's octvr_dump must write the same bytes (tests/test_gpu_cli.py)
+        import hashlib
+        hp = os.path.join(GOLD, "dat_sha256.json")
+        hs = json.load(open(hp)) if os.path.exists(hp) else {}
+        if rig in ("rig3", "rig3ov", "rig2s", "models", "masks"):
+            hs[rig] = {"sha256": hashlib.sha256(open(dat, "rb").read()).hexdigest(), "bytes": os.path.getsize(dat)}
+            json.dump(hs, open(hp, "w"), indent=1)
 
-    gbin = os.path.join(TMP, "golden.bin")
-    subprocess.check_call([compile_tool("ref_golden"), gbin])
-    np.savez_compressed(os.path.join(GOLD, "primitives.npz"), **read_container(gbin))
-    print("primitives ok")
+    if not only or "primitives" in only:
+        gbin = os.path.join(TMP, "golden.bin")
+        subprocess.check_call([compile_tool("ref_golden"), gbin])
+        np.savez_compressed(os.path.join(GOLD, "primitives.npz"), **read_container(gbin))
+        print("primitives ok")
 
     st = compile_tool("ref_stitch")
     cases = [  # name, rig, in_w, in_h, blend, gain, kind
@@ -92,15 +107,21 @@ def main():
         ("rig3_noblend_noise", "rig3", 320, 240, 0, 0, "noise"),
         ("rig2s_feather3_gain_smooth", "rig2s", 192, 108, -3, 1, "smooth"),
         ("masks_feather2_gain_noise", "masks", 320, 240, -2, 1, "noise"),
+        # after-blend stages (mapper.cpp:279-312): overlay input, scale_output (generic and exact 2x), preview
+        ("rig3ov_feather2_gain_noise_scale200x90_prev64x32", "rig3ov", 320, 240, -2, 1, "noise", 200, 90, 64, 32),
+        ("rig3ov_mb8_gain_smooth_scale128x64_prev100x60", "rig3ov", 320, 240, 8, 1, "smooth", 128, 64, 100, 60),
+        ("rig3ov_noblend_noise_prev128x64", "rig3ov", 320, 240, 0, 0, "noise", 0, 0, 128, 64),
     ]
-    for name, rig, iw, ih, blend, gain, kind in cases:
+    for name, rig, iw, ih, blend, gain, kind, *post in cases:
+        if only and name not in only:
+            continue
         out = os.path.join(TMP, name + ".bin")
-        subprocess.check_call([st, os.path.join(TMP, rig + ".dat"), str(iw), str(ih), str(blend), str(gain), kind, out],
+        subprocess.check_call([st, os.path.join(TMP, rig + ".dat"), str(iw), str(ih), str(blend), str(gain), kind, out] + [str(v) for v in post],
                               stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
         c = read_container(out)
         keep = {k: v for k, v in c.items() if not k.startswith("warped") or name.startswith("rig3_feather5")}
-        keep["meta"] = np.array([iw, ih, blend, gain, 1 if kind == "noise" else 0], np.int64)
-        np.savez_compressed(os.path.join(GOLD, "stitch_%s.npz" % name), **keep)
+        keep["meta"] = np.array([iw, ih, blend, gain, 1 if kind == "noise" else 0] + list(post), np.int64)
+        np.savez_compressed(os.path.join(GOLD, ("post_%s.npz" if post else "stitch_%s.npz") % name), **keep)
         print("stitch", name, {k: v.shape for k, v in keep.items() if k.startswith("result") or k == "gains"})
 
 

@@ -8,7 +8,12 @@
 //   cv::detail::GainCompensator -> feather (octvr recipe, blenders.cpp:531-586 + blender.cu:73-98)
 //   or cv::detail::MultiBandBlender(false, bands, CV_32F) fed 16S -> cv::cvtColor(RGB2YUV_I420).
 //
+// After the blender, as Mapper::stitch does (mapper.cpp:279-312; evident intent for overlays):
+//   overlay inputs cvtColor -> remap -> copyTo(result(roi), mask); cv::resize(result, scale_output, INTER_LINEAR) before
+//   the RGB2YUV_I420 conversion; cv::resize(result, preview size, INTER_LINEAR).  Overlay frames are camera n, n+1, ...
+//
 // usage: ref_stitch <tmpl.dat> <in_w> <in_h> <blend> <gain 0|1> <frame kind: noise|smooth> <out.bin>
+//                   [<scale_w> <scale_h> <preview_w> <preview_h>]   (0 0 = none)
 #include <opencv2/core.hpp>
 #include <opencv2/imgproc.hpp>
 #include <opencv2/stitching/detail/blenders.hpp>
@@ -156,10 +161,30 @@ int main(int argc, char** argv)
     } else {
         for (int i = 0; i < n; i++) warped[i].copyTo(result(rois[i]), mt.inputs[i].mask);   // mapper.cpp:269-275
     }
+    for (size_t k = 0; k < mt.overlay_inputs.size(); k++) {                // mapper.cpp:279-282
+        const auto& ov = mt.overlay_inputs[k];
+        cv::Mat f = make_frame(n + (int)k, in_w, in_h, noise, 1234), rgb, w;
+        put("frame" + std::to_string(n + k), f);
+        cv::cvtColor(f, rgb, cv::COLOR_YUV2RGB_I420);
+        cv::remap(rgb, w, ov.map1 * in_w, ov.map2 * in_h, cv::INTER_LINEAR);
+        w.copyTo(result(ov.roi), ov.mask);
+    }
     put("result_rgb", result);
+    const int scale_w = argc > 9 ? atoi(argv[8]) : 0, scale_h = argc > 9 ? atoi(argv[9]) : 0;
+    const int prev_w = argc > 11 ? atoi(argv[10]) : 0, prev_h = argc > 11 ? atoi(argv[11]) : 0;
+    cv::Mat scaled = result;
+    if (scale_w > 0 && scale_h > 0 && cv::Size(scale_w, scale_h) != out) {  // mapper.cpp:290-294
+        cv::resize(result, scaled, cv::Size(scale_w, scale_h), 0, 0, cv::INTER_LINEAR);
+        put("result_scaled_rgb", scaled);
+    }
     cv::Mat yuv;
-    cv::cvtColor(result, yuv, cv::COLOR_RGB2YUV_I420);
+    cv::cvtColor(scaled, yuv, cv::COLOR_RGB2YUV_I420);
     put("result_yuv", yuv);
+    if (prev_w > 0 && prev_h > 0) {                                        // mapper.cpp:308-312
+        cv::Mat pv;
+        cv::resize(result, pv, cv::Size(prev_w, prev_h), 0, 0, cv::INTER_LINEAR);
+        put("preview_rgb", pv);
+    }
     fclose(g_out);
     return 0;
 }

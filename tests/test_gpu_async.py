@@ -103,7 +103,7 @@ def test_async_rejects_bad_arguments():
     with pytest.raises(vr.OctvrError):
         vr.AsyncMultiMapper([t], [(192, 108)] * 2, (128, 64), [-3], [1], [(0, 0, 1, 1)])       # gain mode > own index
     with pytest.raises(vr.OctvrError):
-        vr.AsyncMultiMapper([t], [(192, 108)] * 2, (128, 64), [-3], [0], [(0, 0.5, 1, 1)])     # region outside the frame
+        vr.AsyncMultiMapper([t], [(192, 108)] * 2, (128, 64), [-3], [0], [(1.25, 0, 0.5, 1)])  # region outside the frame (a region that only overhangs is clipped, async.cpp:25-28)
     am = vr.AsyncMultiMapper([t], [(192, 108)] * 2, (128, 64), [-3], [0], [(0, 0, 1, 1)])
     f = util.noise_frame(0, 192, 108)
     out = np.zeros(128 * 64 * 3 // 2, np.uint8)

@@ -209,3 +209,29 @@ def test_stitch_composition_bit_exact(case):
     assert np.array_equal(y, ref[:H])
     assert np.array_equal(u.ravel(), ref[H:H + H // 4].ravel())
     assert np.array_equal(v.ravel(), ref[H + H // 4:].ravel())
+
+
+POST = sorted(os.path.basename(f)[5:-4] for f in glob.glob(os.path.join(GOLD, "post_*.npz")))
+
+
+@pytest.mark.parametrize("case", POST)
+def test_after_blend_stages_bit_exact(case):
+    """Overlay inputs, scale_output and preview (mapper.cpp:279-312) vs the reference's own cv::remap / cv::resize /
+    cv::cvtColor run on the same template and frames (oracle/refgen/ref_stitch.cpp)."""
+    import util
+    g = np.load(os.path.join(GOLD, "post_%s.npz" % case))
+    iw, ih, blend, gain, _, sw, sh, pw, ph = [int(v) for v in g["meta"]]
+    t = util.template_from_gold(O, case.split("_")[0])
+    for d in t.inputs:
+        d["vignette"] = None
+    n = len(t.inputs) + len(t.overlay_inputs)
+    assert len(t.overlay_inputs) == 1
+    so = O.StitchOracle(t, [(iw, ih)] * n, blend=blend, enable_gain=bool(gain), scale_output=(sw, sh))
+    frames = [util.i420_planes(g["frame%d" % i], iw, ih) for i in range(n)]
+    y, u, v = so.stitch(frames, preview_size=(pw, ph) if pw else None)
+    assert np.array_equal(so.last_result, g["result_rgb"])
+    W, H = (sw, sh) if sh else t.out_size
+    ry, ru, rv = util.i420_planes(g["result_yuv"], W, H)
+    assert np.array_equal(y, ry) and np.array_equal(u, ru) and np.array_equal(v, rv)
+    if pw:
+        assert np.array_equal(so.last_preview, g["preview_rgb"])

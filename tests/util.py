@@ -76,6 +76,9 @@ def template_from_gold(O, rig):
         t.inputs.append(dict(roi=tuple(int(v) for v in g["roi%d" % i]), map1=g["map1_%d" % i], map2=g["map2_%d" % i],
                              mask=g["mask%d" % i], vignette=(g["vig%d" % i] if "vig%d" % i in g else None)))
         t.seam_masks.append(g["seam%d" % i])
+    for i in range(int(g["n_ov"]) if "n_ov" in g else 0):
+        t.overlay_inputs.append(dict(roi=tuple(int(v) for v in g["ov_roi%d" % i]), map1=g["ov_map1_%d" % i], map2=g["ov_map2_%d" % i],
+                                     mask=g["ov_mask%d" % i], vignette=None))
     return t
 
 
