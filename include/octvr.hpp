@@ -114,6 +114,7 @@ public:
         std::vector<int> wh;
         for (auto& s : in_sizes) { wh.push_back(s.width); wh.push_back(s.height); }
         check(octvr_mapper_create(mt.handle(), wh.data(), n_, blend, enable_gain_compensator, scale_output.width, scale_output.height, device, &h_));
+        n_ = octvr_template_num_inputs(mt.handle());      // gains() covers the blended inputs, not the overlays
     }
     // inputs / output: DEVICE planes (the reference takes GpuMat in its packed layout; use stitch_packed for that)
     void stitch(const std::vector<YUV>& inputs, const YUV& output, std::vector<double> gains = std::vector<double>(), void* stream = nullptr)

@@ -221,7 +221,7 @@ class Mapper:
         return out
 
     def gains(self):
-        n = len(self.in_sizes)
+        n = self.tmpl.num_inputs             # overlay inputs are not gain-compensated (mapper.cpp:255-265)
         g = (C.c_double * n)()
         check(lib().octvr_mapper_gains(self._h, g, n))
         return np.array(list(g))
