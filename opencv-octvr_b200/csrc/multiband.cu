@@ -140,33 +140,55 @@ template <class T> __device__ __forceinline__ void pyrup4(const T* __restrict__ 
     for (int q = 0; q < 4; q++) out[q] = make_int3(sat16((out[q].x + 32) >> 6), sat16((out[q].y + 32) >> 6), sat16((out[q].z + 32) >> 6));
 }
 
-// ---- k_mb_warp: one CTA per 256-pixel chunk of a camera's bordered level-0 image that has a valid entry ----
-__global__ void __launch_bounds__(256) k_mb_warp(const __grid_constant__ MbParams p)
+// ---- k_mb_warp: one CTA per FOUR 256-pixel chunks (of any cameras' bordered level-0 images) that have a valid entry.
+//      The chain table entry -> four taps is two dependent DRAM round trips; with one pixel per thread the kernel was bound
+//      by that latency (ncu: 26 long-scoreboard stalls per issue at 85 % occupancy).  A thread now loads its four table
+//      entries first, then all sixteen taps, then does the arithmetic: four independent chains in flight per thread. ----
+constexpr int MB_WARP_CHUNKS = 4;
+__global__ void __launch_bounds__(256) k_mb_warp(const __grid_constant__ MbParams p, unsigned n_chunks)
 {
-    const uint2 wc = __ldg(p.warp_chunks + blockIdx.x);     // chunks without any valid entry are never launched: they stay 0
-    const int c = (int)wc.x;
-    const MbCam& cam = p.cam[c];
-    const unsigned t = wc.y * 256 + threadIdx.x;
-    if (t >= (unsigned)(cam.bw * cam.bh)) return;
-    const uint2 cc = __ldg(p.coords + cam.off_g[0] + t);
-    uint32_t px = 0;
-    if (cc.y & C_VALID) {
-        uint32_t t00, t01, t10, t11;
-        fetch_taps(p.rgbx[c], p.src_pitch[c], cc, t00, t01, t10, t11);
-        int r, g, b;
-        bilerp_rgbx(t00, t01, t10, t11, cc.y & 31u, (cc.y >> 5) & 31u, r, g, b);
-        if (p.use_gain) {
-            if (__ldg(p.gain_flag + c) == 0) {
-                const float g32 = __ldg(p.gain_f32 + c);
-                r = (int)gain_apply_f32((float)r, g32); g = (int)gain_apply_f32((float)g, g32); b = (int)gain_apply_f32((float)b, g32);
-            } else {
-                const uint8_t* lut = p.gain_lut + c * 256;
-                r = __ldg(lut + r); g = __ldg(lut + g); b = __ldg(lut + b);
-            }
+    int cam[MB_WARP_CHUNKS];
+    unsigned long long at[MB_WARP_CHUNKS];
+    uint2 cc[MB_WARP_CHUNKS];
+    #pragma unroll
+    for (int j = 0; j < MB_WARP_CHUNKS; j++) {
+        const unsigned e = blockIdx.x * MB_WARP_CHUNKS + j;
+        cam[j] = -1; cc[j] = make_uint2(0u, 0u); at[j] = 0;
+        if (e < n_chunks) {
+            const uint2 wc = __ldg(p.warp_chunks + e);      // chunks without any valid entry are never listed: they stay 0
+            const MbCam& c = p.cam[wc.x];
+            const unsigned t = wc.y * 256 + threadIdx.x;
+            if (t < (unsigned)(c.bw * c.bh)) { cam[j] = (int)wc.x; at[j] = c.off_g[0] + t; }
         }
-        px = (uint32_t)r | ((uint32_t)g << 8) | ((uint32_t)b << 16);
     }
-    p.g0[cam.off_g[0] + t] = px;
+    #pragma unroll
+    for (int j = 0; j < MB_WARP_CHUNKS; j++) if (cam[j] >= 0) cc[j] = __ldcs(p.coords + at[j]);
+    uint32_t tap[MB_WARP_CHUNKS][4];
+    #pragma unroll
+    for (int j = 0; j < MB_WARP_CHUNKS; j++) {
+        tap[j][0] = tap[j][1] = tap[j][2] = tap[j][3] = 0u;
+        if (cc[j].y & C_VALID) fetch_taps(p.rgbx[cam[j]], p.src_pitch[cam[j]], cc[j], tap[j][0], tap[j][1], tap[j][2], tap[j][3]);
+    }
+    #pragma unroll
+    for (int j = 0; j < MB_WARP_CHUNKS; j++) {
+        if (cam[j] < 0) continue;
+        uint32_t px = 0;
+        if (cc[j].y & C_VALID) {
+            int r, g, b;
+            bilerp_rgbx(tap[j][0], tap[j][1], tap[j][2], tap[j][3], cc[j].y & 31u, (cc[j].y >> 5) & 31u, r, g, b);
+            if (p.use_gain) {
+                if (__ldg(p.gain_flag + cam[j]) == 0) {
+                    const float g32 = __ldg(p.gain_f32 + cam[j]);
+                    r = (int)gain_apply_f32((float)r, g32); g = (int)gain_apply_f32((float)g, g32); b = (int)gain_apply_f32((float)b, g32);
+                } else {
+                    const uint8_t* lut = p.gain_lut + cam[j] * 256;
+                    r = __ldg(lut + r); g = __ldg(lut + g); b = __ldg(lut + b);
+                }
+            }
+            px = (uint32_t)r | ((uint32_t)g << 8) | ((uint32_t)b << 16);
+        }
+        p.g0[at[j]] = px;
+    }
 }
 
 // ---- k_mb_down: level l -> l+1 for every camera.  grid (ceil(w/32), ceil(h/8), cameras) at level l+1 ----
@@ -231,10 +253,14 @@ __global__ void __launch_bounds__(256) k_mb_down(const __grid_constant__ MbParam
 }
 
 // ---- k_mb_band: one thread per FOUR horizontally adjacent pixels of destination level l (CTA = 128 x 8 pixels) ----
-__global__ void __launch_bounds__(256) k_mb_band(const __grid_constant__ MbParams p, int l)
+//      Levels do not depend on each other, so one launch covers all of them (blockIdx.z + 1 = level): the small levels,
+//      latency-bound on their own (15 us each for a few thousand pixels), hide under level 1.
+__global__ void __launch_bounds__(256) k_mb_band(const __grid_constant__ MbParams p)
 {
+    const int l = (int)blockIdx.z + 1;
     const int X0 = (blockIdx.x * 32 + threadIdx.x) * 4, Y = blockIdx.y * 8 + threadIdx.y;
     const int lw = p.lw[l], lh = p.lh[l];
+    if ((int)blockIdx.x * 128 >= lw || (int)blockIdx.y * 8 >= lh) return;
     // only the cameras that have a non-zero weight somewhere in the CTA's four 32 x 8 tiles (at level 0 the weights are the
     // hard seam masks: usually one camera); uniform over the CTA
     unsigned cams = 0;
@@ -565,7 +591,7 @@ Multiband* multiband_create(octvr_mapper& m, const octvr_template& t,
     p.coords = mb->d_coords; p.g0 = mb->d_g0; p.g = mb->d_g; p.w = mb->d_w; p.dst = mb->d_dst; p.dstw = mb->d_dstw;
     for (int i = 0; i < n; i++) { p.rgbx[i] = m.d_rgbx[i]; p.src_pitch[i] = m.in_w[i]; }
     m.table_bytes = (int64_t)(coords.size() * sizeof(uint2) + wts.size() * 4 + dstw.size() * 4);
-    mb->launches = 1 + nb + nb + std::max(0, nb - 1) + 1;
+    mb->launches = 1 + nb + (nb >= 1 ? 1 : 0) + std::max(0, nb - 1) + 1;
     return mb.release();
 }
 
@@ -581,12 +607,12 @@ void multiband_stitch(octvr_mapper& m, const octvr_frame* out, cudaStream_t s)
     }
     p.rgb_out = m.rgb_this_frame ? m.d_rgb : nullptr; p.rgb_pitch = (uint32_t)m.out_w * 3;
     const int nb = p.nb, n = p.n;
-    if (mb.n_chunks) k_mb_warp<<<mb.n_chunks, 256, 0, s>>>(p);
+    if (mb.n_chunks) k_mb_warp<<<(mb.n_chunks + MB_WARP_CHUNKS - 1) / MB_WARP_CHUNKS, 256, 0, s>>>(p, mb.n_chunks);
     if (p.lh[0] > 0 && mb.max_bh > 0) {                    // an empty row window (a band outside the result roi) only writes black
         for (int l = 0; l < nb; l++)
             k_mb_down<<<dim3(((mb.max_bw >> (l + 1)) + 31) / 32, ((mb.max_bh >> (l + 1)) + 31) / 32, n), dim3(32, 8), 0, s>>>(p, l);
-        for (int l = nb; l >= 1; l--)                       // level 0 is computed inside k_mb_final
-            k_mb_band<<<dim3((p.lw[l] + 127) / 128, (p.lh[l] + 7) / 8), dim3(32, 8), 0, s>>>(p, l);
+        if (nb >= 1)                                        // levels 1 .. nb in one launch; level 0 is computed inside k_mb_final
+            k_mb_band<<<dim3((p.lw[1] + 127) / 128, (p.lh[1] + 7) / 8, nb), dim3(32, 8), 0, s>>>(p);
         for (int l = nb; l >= 2; l--)
             k_mb_collapse<<<dim3((p.lw[l - 1] + 127) / 128, (p.lh[l - 1] + 7) / 8), dim3(32, 8), 0, s>>>(p, l);
     }
