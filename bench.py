@@ -263,28 +263,29 @@ def run_rowband(args):
     W, H = tmpl.out_size
     rb = vr.sharding.RowBandStitcher(vr, tmpl, [in_size] * n, blend, gain, local)
     RING = 4
-    ring = []
+    ring, flats = [], []
     for k in range(RING):
-        fr = []
-        for c in range(n):
-            y, u, v = util.i420_planes(util.noise_frame(c, iw, ih, seed=1234 + 7919 * k), iw, ih)
-            host = np.concatenate([y, np.concatenate([u, v], 1)], 0)
-            fr.append(torch.from_numpy(host).cuda() if rank == 0 else torch.zeros(host.shape, dtype=torch.uint8, device="cuda"))
-        ring.append(fr)
+        flat, views = vr.sharding.alloc_frame_set([in_size] * n, "cuda")
+        if rank == 0:
+            for c in range(n):
+                y, u, v = util.i420_planes(util.noise_frame(c, iw, ih, seed=1234 + 7919 * k), iw, ih)
+                views[c].copy_(torch.from_numpy(np.concatenate([y, np.concatenate([u, v], 1)], 0)))
+        ring.append(views)
+        flats.append(flat)
     out = torch.zeros((H * 3 // 2, W), dtype=torch.uint8, device="cuda")
+    pipe = vr.sharding.FramePipeline(rb, src=0)
 
-    def step(k):
-        out.zero_()
-        rb.stitch(ring[k % RING], out, src=0, collect=True)
+    def step(k, last=False):
+        pipe.step(flats[k % RING], ring[k % RING], out, next_flat=None if last else flats[(k + 1) % RING])
 
     for k in range(args.warmup):
-        step(k)
+        step(k, last=True)
     dist.barrier()
     torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     for k in range(args.steps):
-        step(k)
+        step(k, last=(k == args.steps - 1))
     e1.record()
     torch.cuda.synchronize()
     ms = vr.sharding.max_over_ranks(e0.elapsed_time(e1), device="cuda")
@@ -296,8 +297,8 @@ def run_rowband(args):
         "metric": "equirect output Mpix/s", "value": round(W * H * args.steps / (ms * 1e-3) / 1e6, 1), "unit": "Mpix/s", "n_gpus": world,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(ms / args.steps, 5), "higher_is_better": True,
         "scaling": "strong", "vs_baseline": None, "dtype": "u8", "data": "synthetic", "frames_per_s": round(args.steps / (ms * 1e-3), 1),
-        "config": {"workload": desc, "sharding": "row bands of one stream: NCCL broadcast of %d input frames (%.1f MB) + band stitch + "
-                   "collection of the bands on rank 0 per step" % (n, n * iw * ih * 1.5 / 1e6), "bands": rb.bands}}))
+        "config": {"workload": desc, "sharding": "row bands of one stream: one NCCL broadcast of the %d input frames (%.1f MB) per step, issued one step ahead, + band "
+                   "stitch + bands sent to rank 0 (NCCL send/recv)" % (n, n * iw * ih * 1.5 / 1e6), "bands": rb.bands}}))
 
 
 def run_stereo(args):
@@ -317,6 +318,8 @@ def run_stereo(args):
     tmpls, in_size = [], None
     t0 = time.time()
     todo = sorted({e for e, _, _ in vr.sharding.stereo_assignment(world)[rank]})
+    if args.verify and rank == 0:
+        todo = [0, 1]
     for e, rig in enumerate(rigs):
         cfg, width, in_size = util.named_rig(rig)
         n = len(cfg["inputs"])
@@ -333,27 +336,26 @@ def run_stereo(args):
     W, He = st.eye_w, st.eye_h
     H = 2 * He
     RING = 4
-    ring = []
-    for k in range(RING):
-        fr = []
-        for c in range(n):
-            if rank == 0:
+    ring, flats = [], []
+    for k in range(RING):      # every time step's frames in one contiguous buffer: a single broadcast per step
+        flat, views = vr.sharding.alloc_frame_set([in_size] * n, "cuda")
+        if rank == 0:
+            for c in range(n):
                 y, u, v = util.i420_planes(util.noise_frame(c, iw, ih, seed=1234 + 7919 * k), iw, ih)
-                fr.append(torch.from_numpy(np.concatenate([y, np.concatenate([u, v], 1)], 0)).cuda())
-            else:
-                fr.append(torch.zeros((ih * 3 // 2, iw), dtype=torch.uint8, device="cuda"))
-        ring.append(fr)
+                views[c].copy_(torch.from_numpy(np.concatenate([y, np.concatenate([u, v], 1)], 0)))
+        ring.append(views)
+        flats.append(flat)
     out = torch.zeros((H * 3 // 2, W), dtype=torch.uint8, device="cuda")
+    pipe = vr.sharding.FramePipeline(st, src=0)
 
-    def step(k):
-        if world > 1:
-            out.zero_()
-            st.stitch(ring[k % RING], out, src=0, collect=True)
+    def step(k, last=False):
+        if world > 1:      # broadcast of step k + 1 runs under the stitch of step k; bands go to rank 0 point to point
+            pipe.step(flats[k % RING], ring[k % RING], out, next_flat=None if last else flats[(k + 1) % RING])
         else:
             st.stitch_local(ring[k % RING], out)
 
     for k in range(args.warmup):
-        step(k)
+        step(k, last=True)
     torch.cuda.synchronize()
     # per-stage split and stitch-only time of this rank (separate, untimed pass)
     stage = {"convert": [], "gain": [], "blend": [], "total": []}
@@ -373,13 +375,20 @@ def run_stereo(args):
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     for k in range(args.steps):
-        step(k)
+        step(k, last=(k == args.steps - 1))
     e1.record()
     torch.cuda.synchronize()
     clocks = sampler.stop() if sampler else None
     ms = vr.sharding.max_over_ranks(e0.elapsed_time(e1), device="cuda")
     local_ms = vr.sharding.max_over_ranks(statistics.median(stage["total"]), device="cuda")
     stats = [m.stats() for _, _, m in st.jobs]
+    verified = None
+    if args.verify and world > 1 and rank == 0:      # the assembled frame of the last step == both eyes stitched whole on this GPU
+        one = vr.sharding.StereoRowBandStitcher(vr, tmpls, [in_size] * n, blend, gain, local, rank=0, world=1)
+        ref = torch.zeros_like(out)
+        one.stitch_local(ring[(args.steps - 1) % RING], ref)
+        torch.cuda.synchronize()
+        verified = bool(torch.equal(ref, out))
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
@@ -399,8 +408,9 @@ def run_stereo(args):
         "config": {"workload": desc, "inputs": "%dx%dx%d I420 (octvr packed layout), ring of %d noise frames resident on rank 0" % (n, iw, ih, RING),
                    "output": "%dx%d 4:2:0 top-bottom (two %dx%d eyes)" % (W, H, W, He),
                    "l2": "working set per step exceeds the 126 MB L2; no flush",
-                   "sharding": ("row bands of one stream: per step NCCL broadcast of %d input frames (%.1f MB) from rank 0, (eye, band) stitch, "
-                                "bands collected on rank 0 (NCCL reduce of the %.1f MB frame)" % (n, I / 1e6, W * H * 1.5 / 1e6)) if world > 1 else "single GPU, both eyes",
+                   "sharding": ("row bands of one stream: per step ONE NCCL broadcast of the %d input frames (%.1f MB) from rank 0 (issued one step "
+                                "ahead, overlapping the previous stitch), (eye, band) stitch, bands sent to rank 0 by NCCL send/recv "
+                                "(%.1f MB frame in total)" % (n, I / 1e6, W * H * 1.5 / 1e6)) if world > 1 else "single GPU, both eyes",
                    "assignment_rank0": [(j[0], list(j[1])) for j in st.jobs],
                    "pairs_P_per_eye": stats[0]["pairs"], "roi_area_per_eye": stats[0]["roi_area"],
                    "template_build_s": round(t_tmpl, 2), "mapper_build_s": round(t_map, 2)},
@@ -411,6 +421,8 @@ def run_stereo(args):
         "gpu_launches": sum(s_["launches_per_stitch"] for s_ in stats) * args.steps,
         "clocks": clocks,
     }
+    if verified is not None:
+        line["assembled_frame_equals_single_gpu_result"] = verified
     if world == 1:
         ach = (B - I) / (blend_ms * 1e-3) / 1e9
         line["roofline"] = {"bound": "hbm", "kernel": "multiband stage, both eyes (k_mb_warp+k_mb_down+k_mb_band+k_mb_collapse+k_mb_final)",
@@ -520,6 +532,7 @@ def main():
     ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS))
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--verify", action="store_true", help="c4, N > 1: rank 0 also stitches the last frame whole and compares")
     ap.add_argument("--rowband", action="store_true", help="N > 1: all ranks stitch ONE stream, split by output row bands "
                     "(NCCL broadcast of the inputs + band collection inside the timed region; strong scaling)")
     args = ap.parse_args()

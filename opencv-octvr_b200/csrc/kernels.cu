@@ -7,6 +7,7 @@
 //   gain     : core/src/arithm.cpp multiply-by-scalar in f64 -> sat_u8(rint(v*g))
 //   feather  : stitching/src/cuda/blender.cu:73-98 (short)(v*W) truncation, blenders.cpp:581 (x 1/N, rint)
 #include "kernels.cuh"
+#include <cstdlib>
 #include "device_common.cuh"
 
 namespace ob {
@@ -490,7 +491,8 @@ void launch_convert_gain(const ConvertParams& cp, const GainParams* gp, cudaStre
     static const GainParams none = {};
     const unsigned gb = gp ? (unsigned)gp->grid : 0u, cb = (unsigned)(cp.grid_x * cp.grid_y * cp.n);
     const size_t smem = gp ? (size_t)gp->n * GAIN_PX * sizeof(double) : 0;
-    k_convert_gain<<<gb + cb, 256, smem, s>>>(cp, gp ? *gp : none, gb, (gb > 0 && cb >= 2u * gb) ? 1u : 0u);
+    static const int mode = [] { const char* e = getenv("OCTVR_GAIN_INTERLEAVE"); return e ? atoi(e) : 1; }();   // diagnostic: 0 = gain CTAs first
+    k_convert_gain<<<gb + cb, 256, smem, s>>>(cp, gp ? *gp : none, gb, (mode && gb > 0 && cb >= 2u * gb) ? 1u : 0u);
 }
 void launch_gain_finalize(const GainParams& p, cudaStream_t s) { k_gain_finalize<<<1, 256, 0, s>>>(p); }
 

@@ -242,13 +242,50 @@ template <class T> __device__ __forceinline__ void mb_down_strip(const T* __rest
             dst[(size_t)(y0 + j) * dw + x] = make_short4((short)sat16((acc[j][0] + 128) >> 8), (short)sat16((acc[j][1] + 128) >> 8), (short)sat16((acc[j][2] + 128) >> 8), 0);
 }
 
+// Level 0 -> 1: the source is RGBX8888 with X = 0, so R and B travel together as two 16-bit lanes of one register
+// (px & 0x00FF00FF) and G alone.  The horizontal sum is at most 16 * 255 and the full 5 x 5 sum at most 256 * 255 = 65280
+// < 2^16: no lane ever carries into its neighbour, and ((sum + 128) >> 8) <= 255 needs no saturation.  Two multiply-adds
+// per tap row instead of three, no per-channel unpacking -- the same integers as mb_down_strip<uint32_t>.
+__device__ __forceinline__ void mb_down_strip_u8(const uint32_t* __restrict__ src, short4* __restrict__ dst, int sw, int sh, int dw, int dh, int x, int y0)
+{
+    int xi[5];
+    #pragma unroll
+    for (int k = 0; k < 5; k++) xi[k] = refl101(2 * x + k - 2, sw);
+    uint32_t arb[4], ag[4];
+    #pragma unroll
+    for (int j = 0; j < 4; j++) arb[j] = ag[j] = 0u;
+    #pragma unroll
+    for (int r = 0; r < 11; r++) {
+        if (r >= 5 && y0 + (r - 3) / 2 >= dh) break;                  // rows only the missing outputs of a ragged strip would use
+        const uint32_t* row = src + (size_t)refl101(2 * y0 - 2 + r, sh) * sw;
+        const uint32_t a = __ldg(row + xi[0]), b = __ldg(row + xi[1]), c = __ldg(row + xi[2]), d = __ldg(row + xi[3]), e = __ldg(row + xi[4]);
+        const uint32_t M = 0x00FF00FFu;
+        const uint32_t hrb = ((a & M) + (e & M)) + 4u * ((b & M) + (d & M)) + 6u * (c & M);
+        const uint32_t hg = (((a >> 8) & 0xFFu) + ((e >> 8) & 0xFFu)) + 4u * (((b >> 8) & 0xFFu) + ((d >> 8) & 0xFFu)) + 6u * ((c >> 8) & 0xFFu);
+        #pragma unroll
+        for (int j = 0; j < 4; j++) {
+            const int t = r - 2 * j;                                  // tap of output j that reads this row
+            if (t < 0 || t > 4) continue;
+            const uint32_t kw = t == 2 ? 6u : (t == 1 || t == 3) ? 4u : 1u;
+            arb[j] += kw * hrb; ag[j] += kw * hg;
+        }
+    }
+    #pragma unroll
+    for (int j = 0; j < 4; j++)
+        if (y0 + j < dh) {
+            const uint32_t rb = ((arb[j] + 0x00800080u) >> 8) & 0x00FF00FFu, g = (ag[j] + 128u) >> 8;
+            // short4 {R, G, B, 0} as two words
+            *reinterpret_cast<uint2*>(dst + (size_t)(y0 + j) * dw + x) = make_uint2((rb & 0xFFFFu) | (g << 16), rb >> 16);
+        }
+}
+
 __global__ void __launch_bounds__(256) k_mb_down(const __grid_constant__ MbParams p, int l)
 {
     const MbCam& cam = p.cam[blockIdx.z];
     const int sw = cam.bw >> l, sh = cam.bh >> l, dw = sw >> 1, dh = sh >> 1;
     const int x = blockIdx.x * 32 + threadIdx.x, y0 = (blockIdx.y * 8 + threadIdx.y) * 4;
     if (x >= dw || y0 >= dh) return;
-    if (l == 0) mb_down_strip(p.g0 + cam.off_g[0], p.g + cam.off_g[1], sw, sh, dw, dh, x, y0);
+    if (l == 0) mb_down_strip_u8(p.g0 + cam.off_g[0], p.g + cam.off_g[1], sw, sh, dw, dh, x, y0);
     else mb_down_strip(p.g + cam.off_g[l], p.g + cam.off_g[l + 1], sw, sh, dw, dh, x, y0);
 }
 

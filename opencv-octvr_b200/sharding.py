@@ -51,17 +51,63 @@ def gather_frame_counts(n_frames, device="cpu"):
     return [int(o.item()) for o in out]
 
 
-def broadcast_frames(frames, src=0):
-    """Row-band mode: every rank needs every input frame.  `frames`: list of equally shaped u8 tensors, valid on `src`."""
-    if dist.is_initialized() and dist.get_world_size() > 1:
-        for f in frames:
-            dist.broadcast(f, src=src)
-    return frames
+def alloc_frame_set(in_sizes, device, torch_mod=None):
+    """All input frames of one time step in ONE contiguous buffer (Mapper's packed layout per camera), so that the
+    row-band exchange is a single broadcast.  Returns (flat u8 tensor, [per-camera (1.5h, w) views])."""
+    torch_mod = torch_mod or torch
+    sizes = [w * h * 3 // 2 for w, h in in_sizes]
+    flat = torch_mod.zeros(sum(sizes), dtype=torch_mod.uint8, device=device)
+    views, o = [], 0
+    for (w, h), n in zip(in_sizes, sizes):
+        views.append(flat[o:o + n].view(h * 3 // 2, w))
+        o += n
+    return flat, views
+
+
+def broadcast_frames(frames, src=0, async_op=False):
+    """Row-band mode: every rank needs every input frame.  `frames`: one flat tensor (alloc_frame_set) or a list of u8
+    tensors, valid on `src`.  async_op=True returns the work handles (wait() before reading the frames)."""
+    if not (dist.is_initialized() and dist.get_world_size() > 1):
+        return []
+    if torch.is_tensor(frames):
+        frames = [frames]
+    works = [dist.broadcast(f, src=src, async_op=async_op) for f in frames]
+    return [w for w in works if w is not None]
+
+
+def band_slices(out, width, height, y0, y1, row0=0):
+    """The two contiguous row ranges of a packed (1.5 H, W) frame that hold output rows [y0, y1) of a region starting at
+    frame row `row0`: luma rows, and the chroma rows below the luma plane (U | V side by side, mapper.hpp:75-83)."""
+    return out[row0 + y0:row0 + y1], out[height + (row0 + y0) // 2:height + (row0 + y1) // 2]
+
+
+def collect_shares(out, shares, dst=0):
+    """Row-band mode: `shares[r]` = list of (row_a, row_b) ranges of `out` (a packed frame tensor, rows are contiguous)
+    that rank r produced.  Every rank sends its ranges to `dst` point to point (batched isend / irecv: NCCL send/recv over
+    NVLink on the GPU box); only the bands move, nothing is summed and `out` needs no zero fill."""
+    if not (dist.is_initialized() and dist.get_world_size() > 1):
+        return out
+    rank = dist.get_rank()
+    ops = []
+    for r, ranges in enumerate(shares):
+        if r == dst:
+            continue
+        for a, b in ranges:
+            if b <= a:
+                continue
+            if rank == r:
+                ops.append(dist.P2POp(dist.isend, out[a:b], dst))
+            elif rank == dst:
+                ops.append(dist.P2POp(dist.irecv, out[a:b], r))
+    if ops:
+        for w in dist.batch_isend_irecv(ops):
+            w.wait()
+    return out
 
 
 def collect_bands(out, dst=0):
-    """Row-band mode: each rank's output buffer is zero outside its own band, so the full frame is the element-wise sum.
-    (u8 sum; bands are disjoint, nothing overflows.)  The result is valid on `dst`."""
+    """Row-band mode, simple form: each rank's output buffer is zero outside its own band, so the full frame is the
+    element-wise sum (u8; bands are disjoint, nothing overflows).  The result is valid on `dst`."""
     if dist.is_initialized() and dist.get_world_size() > 1:
         dist.reduce(out, dst=dst, op=dist.ReduceOp.SUM)
     return out
@@ -78,13 +124,18 @@ class RowBandStitcher:
         self.mapper = vr.Mapper(tmpl, in_sizes, blend=blend, enable_gain_compensator=enable_gain, device=device,
                                 band=self.bands[self.rank])
 
-    def stitch(self, frames_packed, out_packed, src=0, collect=True):
-        """frames_packed: per-camera packed (1.5h, w) CUDA tensors (contents valid on `src`); out_packed: full-size
-        packed output, zero-initialised by the caller; after the call rank `src` holds the whole frame if collect."""
-        broadcast_frames(frames_packed, src)
+    def shares(self):
+        H = self.mapper.out_size[1]
+        return [[(y0, y1), (H + y0 // 2, H + y1 // 2)] for (y0, y1) in self.bands]
+
+    def stitch(self, frames_packed, out_packed, src=0, collect=True, flat=None):
+        """frames_packed: per-camera packed (1.5h, w) CUDA tensors (contents valid on `src`; views of `flat` when the
+        frame set was made by alloc_frame_set: one broadcast instead of one per camera); out_packed: full-size packed
+        output; after the call rank `src` holds the whole frame if collect."""
+        broadcast_frames(flat if flat is not None else frames_packed, src)
         self.mapper.stitch_packed(frames_packed, out_packed)
         if collect:
-            collect_bands(out_packed, src)
+            collect_shares(out_packed, self.shares(), src)
         return out_packed
 
 
@@ -108,6 +159,7 @@ class StereoRowBandStitcher:
         self.rank = rank if rank is not None else (dist.get_rank() if dist.is_initialized() else 0)
         self.world = world if world is not None else (dist.get_world_size() if dist.is_initialized() else 1)
         self.eye_w, self.eye_h = tmpls[0].out_size
+        self.align = align
         self.in_sizes = [tuple(s) for s in in_sizes]
         self.jobs = []
         for eye, b, per in stereo_assignment(self.world)[self.rank]:
@@ -125,9 +177,48 @@ class StereoRowBandStitcher:
             m.stitch(ins, (oy[eye * He:(eye + 1) * He], ou[eye * He // 2:(eye + 1) * He // 2], ov[eye * He // 2:(eye + 1) * He // 2]),
                      stream=stream)
 
-    def stitch(self, frames_packed, out_packed, src=0, collect=True):
-        broadcast_frames(frames_packed, src)
+    def shares(self):
+        """Row ranges of the packed top-bottom frame produced by every rank (for collect_shares)."""
+        He, H = self.eye_h, 2 * self.eye_h
+        out = []
+        for jobs in stereo_assignment(self.world):
+            rr = []
+            for eye, b, per in jobs:
+                y0, y1 = row_bands(He, per, self.align)[b]
+                rr += [(eye * He + y0, eye * He + y1), (H + (eye * He + y0) // 2, H + (eye * He + y1) // 2)]
+            out.append(rr)
+        return out
+
+    def stitch(self, frames_packed, out_packed, src=0, collect=True, flat=None):
+        """Collective: broadcast (one call when `flat`, the buffer behind frames_packed, is given), this rank's share,
+        bands sent to `src`.  FramePipeline overlaps the broadcast of the next time step with the stitch."""
+        broadcast_frames(flat if flat is not None else frames_packed, src)
         self.stitch_local(frames_packed, out_packed)
         if collect:
-            collect_bands(out_packed, src)
+            collect_shares(out_packed, self.shares(), src)
         return out_packed
+
+
+class FramePipeline:
+    """Row-band exchange with the input broadcast of time step k + 1 overlapped with the stitch of step k (SURVEY.md 8e:
+    "overlap with previous frame").  stitcher: RowBandStitcher or StereoRowBandStitcher."""
+
+    def __init__(self, stitcher, src=0):
+        self.st, self.src, self.pending = stitcher, src, {}
+
+    def step(self, flat, frames, out, next_flat=None, collect=True):
+        key = flat.data_ptr()
+        works = self.pending.pop(key, None)
+        if works is None:
+            works = broadcast_frames(flat, self.src, async_op=True)
+        for w in works:
+            w.wait()                                   # the compute stream waits for the broadcast, the host does not
+        if next_flat is not None:
+            self.pending[next_flat.data_ptr()] = broadcast_frames(next_flat, self.src, async_op=True)
+        if hasattr(self.st, "stitch_local"):
+            self.st.stitch_local(frames, out)
+        else:
+            self.st.mapper.stitch_packed(frames, out)
+        if collect:
+            collect_shares(out, self.st.shares(), self.src)
+        return out

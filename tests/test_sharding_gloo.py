@@ -27,7 +27,22 @@ WORKER = textwrap.dedent("""
     y0, y1 = vr.sharding.row_bands(64, w, 32)[r]
     out[y0:y1] = r + 1
     vr.sharding.collect_bands(out, dst=0)
-    print(json.dumps({"rank": r, "mine": mine, "t": t, "counts": counts, "bands": bands, "bcast": got, "rows": out[:, 0].tolist()}))
+    # the same by point-to-point band transfers from one contiguous frame set, with the next step's broadcast in flight
+    flat, views = vr.sharding.alloc_frame_set([(8, 4), (8, 4)], "cpu")
+    flat2, views2 = vr.sharding.alloc_frame_set([(8, 4), (8, 4)], "cpu")
+    if r == 0:
+        flat.fill_(7); flat2.fill_(9)
+    w1 = vr.sharding.broadcast_frames(flat, src=0, async_op=True)
+    w2 = vr.sharding.broadcast_frames(flat2, src=0, async_op=True)
+    for x in w1 + w2:
+        x.wait()
+    out2 = torch.full((96, 4), 99, dtype=torch.uint8)       # packed 64-row frame: 64 luma rows + 32 chroma rows
+    shares = [[(a, b), (64 + a // 2, 64 + b // 2)] for a, b in vr.sharding.row_bands(64, w, 32)]
+    for a, b in shares[r]:
+        out2[a:b] = r + 1
+    vr.sharding.collect_shares(out2, shares, dst=0)
+    print(json.dumps({"rank": r, "mine": mine, "t": t, "counts": counts, "bands": bands, "bcast": got, "rows": out[:, 0].tolist(),
+                      "set": [int(views[1][0, 0]), int(views2[0][5, 7])], "rows2": out2[:, 0].tolist()}))
     dist.destroy_process_group()
 """) % ROOT
 
@@ -50,6 +65,8 @@ def test_two_rank_gloo_sharding(tmp_path):
     assert rows[0]["bands"] == [[0, 960], [960, 1920]]
     assert rows[0]["bcast"] == rows[1]["bcast"] == [10, 20, 30]                   # every rank sees the ingest rank's frames
     assert rows[0]["rows"] == [1] * 32 + [2] * 32                                 # the bands assembled on rank 0
+    assert rows[0]["set"] == rows[1]["set"] == [7, 9]
+    assert rows[0]["rows2"] == [1] * 32 + [2] * 32 + [1] * 16 + [2] * 16          # luma and chroma bands, point to point
 
 
 def test_row_bands_alignment():
