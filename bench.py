@@ -311,7 +311,11 @@ def run_stereo(args):
     import util
     world, rank, local = int(os.environ.get("WORLD_SIZE", "1")), int(os.environ.get("RANK", "0")), int(os.environ.get("LOCAL_RANK", "0"))
     if world > 1:
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+        # the exchange runs on NCCL's own stream next to the stitch kernels: give it priority, or its few CTAs queue behind
+        # the stitch grids and the "overlapped" broadcast only starts when the stitch has drained
+        hp = os.environ.get("OCTVR_NCCL_HP", "1") != "0"
+        opts = dist.ProcessGroupNCCL.Options(is_high_priority_stream=hp)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local), pg_options=opts)
     torch.cuda.set_device(local)
     rigs, blend, gain, desc = WORKLOADS[args.workload]
     eye_h = 1920
@@ -382,6 +386,20 @@ def run_stereo(args):
     ms = vr.sharding.max_over_ranks(e0.elapsed_time(e1), device="cuda")
     local_ms = vr.sharding.max_over_ranks(statistics.median(stage["total"]), device="cuda")
     stats = [m.stats() for _, _, m in st.jobs]
+    exchange = None
+    if args.verify and world > 1:                    # the two exchange steps timed on their own (diagnostic)
+        def timed(fn, reps=10):
+            torch.cuda.synchronize()
+            dist.barrier()
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            for _ in range(reps):
+                fn()
+            b.record()
+            torch.cuda.synchronize()
+            return vr.sharding.max_over_ranks(a.elapsed_time(b) / reps, device="cuda")
+        exchange = {"broadcast_ms": round(timed(lambda: vr.sharding.broadcast_frames(flats[0], 0)), 4),
+                    "collect_ms": round(timed(lambda: vr.sharding.collect_shares(out, st.shares(), 0)), 4)}
     verified = None
     if args.verify and world > 1 and rank == 0:      # the assembled frame of the last step == both eyes stitched whole on this GPU
         one = vr.sharding.StereoRowBandStitcher(vr, tmpls, [in_size] * n, blend, gain, local, rank=0, world=1)
@@ -423,6 +441,8 @@ def run_stereo(args):
     }
     if verified is not None:
         line["assembled_frame_equals_single_gpu_result"] = verified
+    if exchange is not None:
+        line["exchange_alone_ms"] = exchange
     if world == 1:
         ach = (B - I) / (blend_ms * 1e-3) / 1e9
         line["roofline"] = {"bound": "hbm", "kernel": "multiband stage, both eyes (k_mb_warp+k_mb_down+k_mb_band+k_mb_collapse+k_mb_final)",

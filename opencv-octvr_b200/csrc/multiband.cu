@@ -140,6 +140,55 @@ template <class T> __device__ __forceinline__ void pyrup4(const T* __restrict__ 
     for (int q = 0; q < 4; q++) out[q] = make_int3(sat16((out[q].x + 32) >> 6), sat16((out[q].y + 32) >> 6), sat16((out[q].z + 32) >> 6));
 }
 
+// ---- the same for a CAMERA's Gaussian levels, on packed 16-bit lanes ----
+// Gaussian levels of 8-bit images stay within [0, 255] (pyrDown is a rounded convex combination), so a camera's short4
+// {R, G, B, 0} is filtered as two words of two 16-bit lanes: the largest intermediate is 64 * 255 + 32 < 2^16, no lane
+// carries into its neighbour, no unpacking, and (v + 32) >> 6 <= 255 needs no saturation.  Same integers as pyrup4.
+__device__ __forceinline__ uint2 ldp(const short4* __restrict__ s, int idx) { return __ldg(reinterpret_cast<const uint2*>(s) + idx); }
+__device__ __forceinline__ uint2 p_add(uint2 a, uint2 b) { return make_uint2(a.x + b.x, a.y + b.y); }
+__device__ __forceinline__ uint2 p_161(uint2 a, uint2 b, uint2 c) { return make_uint2(a.x + 6u * b.x + c.x, a.y + 6u * b.y + c.y); }
+__device__ __forceinline__ uint2 p_44(uint2 a, uint2 b) { return make_uint2(4u * (a.x + b.x), 4u * (a.y + b.y)); }
+__device__ __forceinline__ void pyrup_row4_packed(const short4* __restrict__ s, int sw, int r, int x0, uint2 (&h)[4])
+{
+    const short4* row = s + (size_t)r * sw;
+    const int k = x0 >> 1;
+    if ((x0 & 1) == 0) {
+        const uint2 a = ldp(row, up_idx(k - 1, sw)), b = ldp(row, up_idx(k, sw)), c = ldp(row, up_idx(k + 1, sw)), d = ldp(row, up_idx(k + 2, sw));
+        h[0] = p_161(a, b, c); h[1] = p_44(b, c); h[2] = p_161(b, c, d); h[3] = p_44(c, d);
+    } else {
+        const uint2 a = ldp(row, up_idx(k, sw)), b = ldp(row, up_idx(k + 1, sw)), c = ldp(row, up_idx(k + 2, sw)), d = ldp(row, up_idx(k + 3, sw));
+        h[0] = p_44(a, b); h[1] = p_161(a, b, c); h[2] = p_44(b, c); h[3] = p_161(b, c, d);
+    }
+}
+// out[q] = {R | G << 16, B} of the up-sampled level at (x0 + q, y)
+__device__ __forceinline__ void pyrup4_packed(const short4* __restrict__ s, int sw, int sh, int x0, int y, uint2 (&out)[4])
+{
+    const int ky = y >> 1;
+    uint2 h1[4], h2[4];
+    pyrup_row4_packed(s, sw, up_idx(ky, sh), x0, h1);
+    pyrup_row4_packed(s, sw, up_idx(ky + 1, sh), x0, h2);
+    if ((y & 1) == 0) {
+        uint2 h0[4];
+        pyrup_row4_packed(s, sw, up_idx(ky - 1, sh), x0, h0);
+        #pragma unroll
+        for (int q = 0; q < 4; q++) out[q] = p_161(h0[q], h1[q], h2[q]);
+    } else {
+        #pragma unroll
+        for (int q = 0; q < 4; q++) out[q] = p_44(h1[q], h2[q]);
+    }
+    #pragma unroll
+    for (int q = 0; q < 4; q++) out[q] = make_uint2(((out[q].x + 0x00200020u) >> 6) & 0x03FF03FFu, (out[q].y + 32u) >> 6);
+}
+// (short)(lap * weight) for the three channels of one pixel, lap = g - up (within [-255, 255]: the saturating 16S
+// subtraction of createLaplacePyr cannot saturate), f32 product truncated toward zero (blenders.cpp:418-420)
+__device__ __forceinline__ void lap_weight_acc(int gr, int gg, int gb, uint2 up, bool lap, float w, int (&acc)[3])
+{
+    if (lap) { gr -= (int)(up.x & 0xFFFFu); gg -= (int)(up.x >> 16); gb -= (int)up.y; }
+    acc[0] += __float2int_rz(__fmul_rn((float)gr, w));
+    acc[1] += __float2int_rz(__fmul_rn((float)gg, w));
+    acc[2] += __float2int_rz(__fmul_rn((float)gb, w));
+}
+
 // ---- k_mb_warp: one CTA per FOUR 256-pixel chunks (of any cameras' bordered level-0 images) that have a valid entry.
 //      The chain table entry -> four taps is two dependent DRAM round trips; with one pixel per thread the kernel was bound
 //      by that latency (ncu: 26 long-scoreboard stalls per issue at 85 % occupancy).  A thread now loads its four table
@@ -242,26 +291,42 @@ template <class T> __device__ __forceinline__ void mb_down_strip(const T* __rest
             dst[(size_t)(y0 + j) * dw + x] = make_short4((short)sat16((acc[j][0] + 128) >> 8), (short)sat16((acc[j][1] + 128) >> 8), (short)sat16((acc[j][2] + 128) >> 8), 0);
 }
 
-// Level 0 -> 1: the source is RGBX8888 with X = 0, so R and B travel together as two 16-bit lanes of one register
-// (px & 0x00FF00FF) and G alone.  The horizontal sum is at most 16 * 255 and the full 5 x 5 sum at most 256 * 255 = 65280
-// < 2^16: no lane ever carries into its neighbour, and ((sum + 128) >> 8) <= 255 needs no saturation.  Two multiply-adds
-// per tap row instead of three, no per-channel unpacking -- the same integers as mb_down_strip<uint32_t>.
+// Level 0 -> 1: the source is RGBX8888 with X = 0.  ncu showed the generic strip ALU-pipe bound (75 % of the LOP3 / SHF /
+// PRMT / IADD3 pipe: byte unpacking and index arithmetic, 107 instructions per source row).  Here the five pixels of a row
+// come from two 8-byte loads and one 4-byte load (interior columns), their bytes are transposed per channel with seven
+// PRMTs, the [1 4 6 4 | 1] row sums are two IDP.4A per channel (IMAD pipe), and R, B then travel as two 16-bit lanes: the
+// full 5 x 5 sum is at most 256 * 255 < 2^16, so no lane carries and ((sum + 128) >> 8) <= 255 needs no saturation.  The
+// same integers as mb_down_strip<uint32_t>.
 __device__ __forceinline__ void mb_down_strip_u8(const uint32_t* __restrict__ src, short4* __restrict__ dst, int sw, int sh, int dw, int dh, int x, int y0)
 {
+    const bool interior = 2 * x - 2 >= 0 && 2 * x + 2 < sw;           // no column reflection, 8-byte aligned pairs (sw is even)
     int xi[5];
     #pragma unroll
     for (int k = 0; k < 5; k++) xi[k] = refl101(2 * x + k - 2, sw);
     uint32_t arb[4], ag[4];
     #pragma unroll
     for (int j = 0; j < 4; j++) arb[j] = ag[j] = 0u;
+    const bool inner_rows = 2 * y0 - 2 >= 0 && 2 * y0 + 8 < sh;       // no row reflection for any of the 11 rows
     #pragma unroll
     for (int r = 0; r < 11; r++) {
         if (r >= 5 && y0 + (r - 3) / 2 >= dh) break;                  // rows only the missing outputs of a ragged strip would use
-        const uint32_t* row = src + (size_t)refl101(2 * y0 - 2 + r, sh) * sw;
-        const uint32_t a = __ldg(row + xi[0]), b = __ldg(row + xi[1]), c = __ldg(row + xi[2]), d = __ldg(row + xi[3]), e = __ldg(row + xi[4]);
-        const uint32_t M = 0x00FF00FFu;
-        const uint32_t hrb = ((a & M) + (e & M)) + 4u * ((b & M) + (d & M)) + 6u * (c & M);
-        const uint32_t hg = (((a >> 8) & 0xFFu) + ((e >> 8) & 0xFFu)) + 4u * (((b >> 8) & 0xFFu) + ((d >> 8) & 0xFFu)) + 6u * ((c >> 8) & 0xFFu);
+        const int sy = inner_rows ? 2 * y0 - 2 + r : refl101(2 * y0 - 2 + r, sh);
+        const uint32_t* row = src + (size_t)sy * sw;
+        uint32_t a, b, c, d, e;
+        if (interior) {
+            const uint2 ab = __ldg(reinterpret_cast<const uint2*>(row + 2 * x - 2)), cd = __ldg(reinterpret_cast<const uint2*>(row + 2 * x));
+            a = ab.x; b = ab.y; c = cd.x; d = cd.y; e = __ldg(row + 2 * x + 2);
+        } else {
+            a = __ldg(row + xi[0]); b = __ldg(row + xi[1]); c = __ldg(row + xi[2]); d = __ldg(row + xi[3]); e = __ldg(row + xi[4]);
+        }
+        const uint32_t rg_ab = __byte_perm(a, b, 0x5140), rg_cd = __byte_perm(c, d, 0x5140);       // Ra Rb Ga Gb | Rc Rd Gc Gd
+        const uint32_t r4 = __byte_perm(rg_ab, rg_cd, 0x5410), g4 = __byte_perm(rg_ab, rg_cd, 0x7632);
+        const uint32_t b4 = __byte_perm(__byte_perm(a, b, 0x4462), __byte_perm(c, d, 0x4462), 0x5410);
+        const uint32_t W = 0x04060401u;                                // weights of a, b, c, d; e has weight 1
+        const uint32_t hr = __dp4a(r4, W, __dp4a(e, 0x00000001u, 0u));
+        const uint32_t hg = __dp4a(g4, W, __dp4a(e, 0x00000100u, 0u));
+        const uint32_t hb = __dp4a(b4, W, __dp4a(e, 0x00010000u, 0u));
+        const uint32_t hrb = hb * 65536u + hr;                         // R | B << 16 (each <= 16 * 255)
         #pragma unroll
         for (int j = 0; j < 4; j++) {
             const int t = r - 2 * j;                                  // tap of output j that reads this row
@@ -326,19 +391,14 @@ __global__ void __launch_bounds__(256) k_mb_band(const __grid_constant__ MbParam
             any = any || w[q] != 0.f;                                 // (short)(lap * 0) == 0
         }
         if (!any) continue;
-        int3 up[4];
-        if (l < p.nb) pyrup4(p.g + cam.off_g[l + 1], w_l >> 1, h_l >> 1, x0, y, up);     // x0 is even here: camera rects are 2^bands aligned
+        uint2 up[4];
+        const bool lap = l < p.nb;                                    // createLaplacePyr: pyr[l] -= pyrUp(pyr[l+1]); the top level stays Gaussian
+        if (lap) pyrup4_packed(p.g + cam.off_g[l + 1], w_l >> 1, h_l >> 1, x0, y, up);
         #pragma unroll
         for (int q = 0; q < 4; q++) {
             if (w[q] == 0.f) continue;
-            const int x = x0 + q;
-            int3 gl = l == 0 ? ld3(p.g0 + cam.off_g[0], y * w_l + x) : ld3(p.g + cam.off_g[l], y * w_l + x);
-            if (l < p.nb)                                             // createLaplacePyr: pyr[l] -= pyrUp(pyr[l+1]), saturating 16S
-                gl = make_int3(sat16(gl.x - up[q].x), sat16(gl.y - up[q].y), sat16(gl.z - up[q].z));
-            // dst += static_cast<short>(lap * weight): f32 product truncated toward zero (blenders.cpp:418-420)
-            acc[q][0] += __float2int_rz(__fmul_rn((float)gl.x, w[q]));
-            acc[q][1] += __float2int_rz(__fmul_rn((float)gl.y, w[q]));
-            acc[q][2] += __float2int_rz(__fmul_rn((float)gl.z, w[q]));
+            const uint2 gl = ldp(p.g + cam.off_g[l], y * w_l + x0 + q);            // levels >= 1 only (level 0 lives in k_mb_final)
+            lap_weight_acc((int)(gl.x & 0xFFFFu), (int)(gl.x >> 16), (int)gl.y, up[q], lap, w[q], acc[q]);
         }
     }
     #pragma unroll
@@ -421,16 +481,13 @@ __global__ void __launch_bounds__(256) k_mb_final(const __grid_constant__ MbPara
                     anyw = anyw || w[q] != 0.f;
                 }
                 if (!anyw) continue;
-                int3 up[4];
-                if (p.nb > 0) pyrup4(p.g + cam.off_g[1], cam.bw >> 1, cam.bh >> 1, cx0, cy, up);
+                uint2 up[4];
+                if (p.nb > 0) pyrup4_packed(p.g + cam.off_g[1], cam.bw >> 1, cam.bh >> 1, cx0, cy, up);
                 #pragma unroll
                 for (int q = 0; q < 4; q++) {
                     if (w[q] == 0.f) continue;
-                    int3 gl = ld3(p.g0 + cam.off_g[0], cy * cam.bw + cx0 + q);
-                    if (p.nb > 0) gl = make_int3(sat16(gl.x - up[q].x), sat16(gl.y - up[q].y), sat16(gl.z - up[q].z));
-                    acc[q][0] += __float2int_rz(__fmul_rn((float)gl.x, w[q]));
-                    acc[q][1] += __float2int_rz(__fmul_rn((float)gl.y, w[q]));
-                    acc[q][2] += __float2int_rz(__fmul_rn((float)gl.z, w[q]));
+                    const uint32_t px = __ldg(p.g0 + cam.off_g[0] + (size_t)cy * cam.bw + cx0 + q);
+                    lap_weight_acc((int)(px & 255u), (int)((px >> 8) & 255u), (int)((px >> 16) & 255u), up[q], p.nb > 0, w[q], acc[q]);
                 }
             }
             int3 up[4];
