@@ -32,6 +32,7 @@ WORKLOADS = {
     "c2": ("rig6", -1, True, "C2 6x2704x1520 -> 4096x2048 equirect, gain + feather(1)"),
     "c3": ("rig6", 64, True, "C3 6x2704x1520 -> 4096x2048 equirect, gain + 5-band multiband"),
     "c4": (("rig8L", "rig8R"), 64, True, "C4 8x3840x2160 fisheye -> 7680x3840 stereo top-bottom, gain + 5-band multiband"),
+    "c5": ("rig6", -1, True, "C5 16 independent streams of the C2 rig (6x2704x1520 -> 4096x2048, gain + feather(1)), frame-sharded"),
     "c2ng": ("rig6", -1, False, "C2 rig without gain compensation: 6x2704x1520 -> 4096x2048 equirect, feather(1) (diagnostic)"),
 }
 
@@ -301,6 +302,120 @@ def run_rowband(args):
                    "stitch + bands sent to rank 0 (NCCL send/recv)" % (n, n * iw * ih * 1.5 / 1e6), "bands": rb.bands}}))
 
 
+def run_streams(args):
+    """BASELINE config C5: 16 independent video streams of the C2 rig, sharded over the ranks (stream s -> rank s mod N, no
+    data-path collective).  A rank serves its streams round-robin on `--concurrency` CUDA streams, one Mapper each (a
+    Mapper's per-frame buffers belong to one frame at a time), so the latency-bound gain chain of one frame runs under the
+    blend of another.  A step = one frame of every stream of the job; value = frames of all ranks / max-over-ranks time."""
+    import torch
+    import torch.distributed as dist
+    import octvr_b200 as vr
+    import util
+    world, rank, local = int(os.environ.get("WORLD_SIZE", "1")), int(os.environ.get("RANK", "0")), int(os.environ.get("LOCAL_RANK", "0"))
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    torch.cuda.set_device(local)
+    rig, blend, gain, desc = WORKLOADS[args.workload]
+    cfg, width, in_size = util.named_rig(rig)
+    n = len(cfg["inputs"])
+    iw, ih = in_size
+    NS = 16
+    mine = vr.sharding.streams_of_rank(NS, rank, world)
+    conc = max(1, min(args.concurrency, len(mine)))
+    tmpl = make_template(vr, cfg, width, local)
+    W, H = tmpl.out_size
+    mappers = [vr.Mapper(tmpl, [in_size] * n, blend=blend, enable_gain_compensator=gain, device=local) for _ in range(conc)]
+    cstreams = [torch.cuda.Stream(device=local) for _ in range(conc)]
+    st = mappers[0].stats()
+    RING = 2
+    frames, outs = {}, {}
+    for s_ in mine:            # every video stream has its own frames and its own output
+        frames[s_] = []
+        for k in range(RING):
+            fr = []
+            for c in range(n):
+                y, u, v = util.i420_planes(util.noise_frame(c, iw, ih, seed=1234 + 7919 * k + 104729 * s_), iw, ih)
+                fr.append(torch.from_numpy(np.concatenate([y, np.concatenate([u, v], 1)], 0)).cuda())
+            frames[s_].append(fr)
+        outs[s_] = torch.zeros((H * 3 // 2, W), dtype=torch.uint8, device="cuda")
+    main = torch.cuda.current_stream()
+
+    def step(k):
+        for i, s_ in enumerate(mine):
+            q = (k * len(mine) + i) % conc
+            mappers[q].stitch_packed(frames[s_][k % RING], outs[s_], stream=cstreams[q])
+
+    def fork():
+        ev = torch.cuda.Event()
+        ev.record(main)
+        for cs in cstreams:
+            cs.wait_event(ev)
+
+    def join():
+        for cs in cstreams:
+            ev = torch.cuda.Event()
+            ev.record(cs)
+            main.wait_event(ev)
+
+    fork()
+    for k in range(args.warmup):
+        step(k)
+    join()
+    torch.cuda.synchronize()
+    # dominant kernel alone (one mapper, serial): duration for the roofline object
+    mappers[0].set_profiling(True)
+    stage = {"convert": [], "gain": [], "blend": []}
+    for k in range(10):
+        mappers[0].stitch_packed(frames[mine[0]][k % RING], outs[mine[0]], stream=main)
+        for s_ in stage:
+            stage[s_].append(mappers[0].stage_ms(s_))
+    mappers[0].set_profiling(False)
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    sampler = ClockSampler(local) if rank == 0 else None
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(main)
+    fork()
+    for k in range(args.steps):
+        step(k)
+    join()
+    e1.record(main)
+    torch.cuda.synchronize()
+    clocks = sampler.stop() if sampler else None
+    ms = vr.sharding.max_over_ranks(e0.elapsed_time(e1), device="cuda")
+    frames_all = sum(vr.sharding.gather_frame_counts(args.steps * len(mine), device="cuda"))
+    e2e = run_e2e(vr, util, tmpl, cfg, in_size, blend, gain, local, min(args.steps * len(mine), 60), world)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+    if rank != 0:
+        return
+    B = alg_bytes([in_size] * n, (W, H), st["pairs"], st["roi_area"], blend)
+    peak, how = peaks()
+    per_frame_ms = ms / (args.steps * len(mine))
+    blend_ms = statistics.median(stage["blend"])
+    blend_bytes = 12 * st["pairs"] + W * H * 3 // 2
+    ach = blend_bytes / (blend_ms * 1e-3) / 1e9
+    print(json.dumps({
+        "metric": "equirect output Mpix/s", "value": round(W * H * frames_all / (ms * 1e-3) / 1e6, 1), "unit": "Mpix/s", "n_gpus": world,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(ms / args.steps, 5), "higher_is_better": True,
+        "scaling": "strong", "vs_baseline": None, "dtype": "u8", "data": "synthetic", "frames_per_s": round(frames_all / (ms * 1e-3), 1),
+        "config": {"workload": desc, "streams": NS, "streams_per_rank": len(mine), "cuda_streams_per_rank": conc,
+                   "inputs": "per stream a ring of %d distinct noise frame sets resident in HBM" % RING,
+                   "l2": "working set per step (tables + %d streams' frames) exceeds the 126 MB L2; no flush" % len(mine),
+                   "sharding": "stream s -> rank s mod N, no data-path collective; a step = one frame of each of the 16 streams",
+                   "pairs_P": st["pairs"], "roi_area": st["roi_area"]},
+        "alg_bytes_per_frame": int(B), "ms_per_frame_per_gpu": round(per_frame_ms, 5),
+        "frac_of_hbm_roofline": {"per_gpu_vs_measured_%.0f" % peak: round(B / (per_frame_ms * 1e-3) / 1e9 / peak, 4)},
+        "stage_ms_serial": {k: round(statistics.median(v), 5) for k, v in stage.items()},
+        "roofline": {"bound": "hbm", "kernel": blend_kernel_name(), "achieved": round(ach, 1), "peak": peak, "peak_source": how, "unit": "GB/s",
+                     "frac": round(ach / peak, 4), "traffic": ncu_traffic("c2", blend), "alg_bytes_per_launch": int(blend_bytes),
+                     "ms_per_launch": round(blend_ms, 5), "note": "kernel timed alone on one CUDA stream"},
+        "gpu_launches": st["launches_per_stitch"] * args.steps * len(mine), "clocks": clocks, "e2e": e2e}))
+
+
 def run_stereo(args):
     """BASELINE config C4: 8 x 3840x2160 fisheye -> 7680x3840 stereo top-bottom (two 7680x1920 eye templates, 5-band multiband),
     ONE stream over all ranks split by (eye, row band) -- sharding.StereoRowBandStitcher.  N > 1: rank 0 ingests, NCCL
@@ -552,6 +667,7 @@ def main():
     ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS))
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--concurrency", type=int, default=2, help="c5: CUDA streams (and Mappers) a rank serves its video streams on")
     ap.add_argument("--verify", action="store_true", help="c4, N > 1: rank 0 also stitches the last frame whole and compares")
     ap.add_argument("--rowband", action="store_true", help="N > 1: all ranks stitch ONE stream, split by output row bands "
                     "(NCCL broadcast of the inputs + band collection inside the timed region; strong scaling)")
@@ -560,6 +676,8 @@ def main():
         run_reference(args)
     elif args.workload == "c4":
         run_stereo(args)
+    elif args.workload == "c5":
+        run_streams(args)
     elif args.rowband and int(os.environ.get("WORLD_SIZE", "1")) > 1:
         run_rowband(args)
     else:

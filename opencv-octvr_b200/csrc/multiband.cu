@@ -16,6 +16,7 @@
 #include "prep.h"
 #include "device_common.cuh"
 #include <algorithm>
+#include <cstdlib>
 #include <cstring>
 #include <cmath>
 #include <memory>
@@ -45,6 +46,9 @@ struct MbParams {
     const float* w;                   // weight pyramids
     short4* dst;                      // blended Laplacian pyramid
     const float* dstw;                // summed band weights
+    int clear_wide;                   // 0 only for the forced-wide diagnostic mode (OCTVR_MB_WIDE=1)
+    int* wide;                        // wide[l] != 0: some value of dst level l lies outside [-512, 511] (written by the kernels that
+                                      // produce the level, cleared by k_mb_warp at the start of a frame); readers then take the 32-bit pyrUp
     // gain
     const uint32_t* rgbx[MAX_CAMS]; int src_pitch[MAX_CAMS];
     const float* gain_f32; const int* gain_flag; const uint8_t* gain_lut; int use_gain;
@@ -60,7 +64,7 @@ struct Multiband {
     MbParams p;
     uint2* d_chunks = nullptr; uint16_t* d_tile_cams = nullptr; unsigned n_chunks = 0;
     uint2* d_coords = nullptr; uint32_t* d_g0 = nullptr; short4* d_g = nullptr; float* d_w = nullptr;
-    short4* d_dst = nullptr; float* d_dstw = nullptr;
+    short4* d_dst = nullptr; float* d_dstw = nullptr; int* d_wide = nullptr; bool force_wide = false;
     int max_bw = 0, max_bh = 0;
     int launches = 0;
 };
@@ -136,8 +140,10 @@ template <class T> __device__ __forceinline__ void pyrup4(const T* __restrict__ 
         #pragma unroll
         for (int q = 0; q < 4; q++) out[q] = mul3(add3(h1[q], h2[q]), 4);
     }
+    // FixPtCast<short, 6>: (v + 32) >> 6.  The taps sum to 64, so |v| <= 64 * 32768 and the result is a short already:
+    // the saturate_cast of pyramids.cpp never clips here.
     #pragma unroll
-    for (int q = 0; q < 4; q++) out[q] = make_int3(sat16((out[q].x + 32) >> 6), sat16((out[q].y + 32) >> 6), sat16((out[q].z + 32) >> 6));
+    for (int q = 0; q < 4; q++) out[q] = make_int3((out[q].x + 32) >> 6, (out[q].y + 32) >> 6, (out[q].z + 32) >> 6);
 }
 
 // ---- the same for a CAMERA's Gaussian levels, on packed 16-bit lanes ----
@@ -189,6 +195,61 @@ __device__ __forceinline__ void lap_weight_acc(int gr, int gg, int gb, uint2 up,
     acc[2] += __float2int_rz(__fmul_rn((float)gb, w));
 }
 
+// ---- and for the BLENDED pyramid (signed 16S) when all its values lie within [-512, 511] ----
+// v + 512 fits 10 bits, 64 * 1023 + 32 < 2^16, and because the taps always sum to 64,
+// (sum w (v + 512) + 32) >> 6 = ((sum w v + 32) >> 6) + 512 exactly: the packed filter on biased lanes gives the same
+// integers as pyrup4<short4>.  v + 512 = (v ^ 0x200) & 0x3FF for a 16-bit two's complement v in range.  Whether a level
+// is in range is recorded by the kernels that write it (MbParams::wide); out-of-range levels (possible in principle:
+// |collapsed value| <= 255 * levels) take the 32-bit path.
+__device__ __forceinline__ uint2 ldp_biased(const short4* __restrict__ s, int idx)
+{
+    const uint2 v = ldp(s, idx);
+    return make_uint2((v.x ^ 0x02000200u) & 0x03FF03FFu, (v.y ^ 0x00000200u) & 0x000003FFu);
+}
+__device__ __forceinline__ void pyrup_row4_biased(const short4* __restrict__ s, int sw, int r, int x0, uint2 (&h)[4])
+{
+    const short4* row = s + (size_t)r * sw;
+    const int k = x0 >> 1;
+    if ((x0 & 1) == 0) {
+        const uint2 a = ldp_biased(row, up_idx(k - 1, sw)), b = ldp_biased(row, up_idx(k, sw)), c = ldp_biased(row, up_idx(k + 1, sw)), d = ldp_biased(row, up_idx(k + 2, sw));
+        h[0] = p_161(a, b, c); h[1] = p_44(b, c); h[2] = p_161(b, c, d); h[3] = p_44(c, d);
+    } else {
+        const uint2 a = ldp_biased(row, up_idx(k, sw)), b = ldp_biased(row, up_idx(k + 1, sw)), c = ldp_biased(row, up_idx(k + 2, sw)), d = ldp_biased(row, up_idx(k + 3, sw));
+        h[0] = p_44(a, b); h[1] = p_161(a, b, c); h[2] = p_44(b, c); h[3] = p_161(b, c, d);
+    }
+}
+__device__ __forceinline__ void pyrup4_narrow(const short4* __restrict__ s, int sw, int sh, int x0, int y, int3 (&out)[4])
+{
+    const int ky = y >> 1;
+    uint2 h1[4], h2[4], o[4];
+    pyrup_row4_biased(s, sw, up_idx(ky, sh), x0, h1);
+    pyrup_row4_biased(s, sw, up_idx(ky + 1, sh), x0, h2);
+    if ((y & 1) == 0) {
+        uint2 h0[4];
+        pyrup_row4_biased(s, sw, up_idx(ky - 1, sh), x0, h0);
+        #pragma unroll
+        for (int q = 0; q < 4; q++) o[q] = p_161(h0[q], h1[q], h2[q]);
+    } else {
+        #pragma unroll
+        for (int q = 0; q < 4; q++) o[q] = p_44(h1[q], h2[q]);
+    }
+    #pragma unroll
+    for (int q = 0; q < 4; q++) {
+        const uint32_t lo = (o[q].x + 0x00200020u) >> 6, hi = (o[q].y + 32u) >> 6;
+        out[q] = make_int3((int)(lo & 0x3FFu) - 512, (int)((lo >> 16) & 0x3FFu) - 512, (int)hi - 512);
+    }
+}
+// pyrUp of a blended level: packed when the level is known to be narrow, 32-bit otherwise (uniform over the grid)
+__device__ __forceinline__ void pyrup4_dst(const MbParams& p, int l, int x0, int y, int3 (&out)[4])
+{
+    if (__ldg(p.wide + l) == 0) pyrup4_narrow(p.dst + p.off_d[l], p.lw[l], p.lh[l], x0, y, out);
+    else pyrup4(p.dst + p.off_d[l], p.lw[l], p.lh[l], x0, y, out);
+}
+__device__ __forceinline__ void note_range(const MbParams& p, int l, int r, int g, int b)
+{
+    if ((unsigned)(r + 512) > 1023u || (unsigned)(g + 512) > 1023u || (unsigned)(b + 512) > 1023u) atomicOr(p.wide + l, 1);
+}
+
 // ---- k_mb_warp: one CTA per FOUR 256-pixel chunks (of any cameras' bordered level-0 images) that have a valid entry.
 //      The chain table entry -> four taps is two dependent DRAM round trips; with one pixel per thread the kernel was bound
 //      by that latency (ncu: 26 long-scoreboard stalls per issue at 85 % occupancy).  A thread now loads its four table
@@ -196,6 +257,7 @@ __device__ __forceinline__ void lap_weight_acc(int gr, int gg, int gb, uint2 up,
 constexpr int MB_WARP_CHUNKS = 4;
 __global__ void __launch_bounds__(256) k_mb_warp(const __grid_constant__ MbParams p, unsigned n_chunks)
 {
+    if (blockIdx.x == 0 && threadIdx.x < MB_MAX_LEVELS && p.clear_wide) p.wide[threadIdx.x] = 0;   // new frame: every level narrow until proven wide
     int cam[MB_WARP_CHUNKS];
     unsigned long long at[MB_WARP_CHUNKS];
     uint2 cc[MB_WARP_CHUNKS];
@@ -271,10 +333,11 @@ template <class T> __device__ __forceinline__ void mb_down_strip(const T* __rest
     int acc[4][3];
     #pragma unroll
     for (int j = 0; j < 4; j++) acc[j][0] = acc[j][1] = acc[j][2] = 0;
+    const bool inner_rows = 2 * y0 - 2 >= 0 && 2 * y0 + 8 < sh;       // no row reflection for any of the 11 rows
     #pragma unroll
     for (int r = 0; r < 11; r++) {
         if (r >= 5 && y0 + (r - 3) / 2 >= dh) break;                  // rows only the missing outputs of a ragged strip would use
-        const T* row = src + (size_t)refl101(2 * y0 - 2 + r, sh) * sw;
+        const T* row = src + (size_t)(inner_rows ? 2 * y0 - 2 + r : refl101(2 * y0 - 2 + r, sh)) * sw;
         const int3 a = ld3(row, xi[0]), b = ld3(row, xi[1]), c = ld3(row, xi[2]), d = ld3(row, xi[3]), e = ld3(row, xi[4]);
         const int hx = a.x + e.x + 4 * (b.x + d.x) + 6 * c.x, hy = a.y + e.y + 4 * (b.y + d.y) + 6 * c.y, hz = a.z + e.z + 4 * (b.z + d.z) + 6 * c.z;
         #pragma unroll
@@ -307,18 +370,30 @@ __device__ __forceinline__ void mb_down_strip_u8(const uint32_t* __restrict__ sr
     #pragma unroll
     for (int j = 0; j < 4; j++) arb[j] = ag[j] = 0u;
     const bool inner_rows = 2 * y0 - 2 >= 0 && 2 * y0 + 8 < sh;       // no row reflection for any of the 11 rows
+    // The kernel is bound by load latency once the arithmetic is this short (ncu: 14 long-scoreboard stalls per issue): no
+    // early exit for ragged strips (rows past the image are reflected like any other and their outputs never stored), so
+    // every load of the strip is independent of control flow and the rows are fetched in groups ahead of their use.
     #pragma unroll
-    for (int r = 0; r < 11; r++) {
-        if (r >= 5 && y0 + (r - 3) / 2 >= dh) break;                  // rows only the missing outputs of a ragged strip would use
+    for (int r0 = 0; r0 < 11; r0 += 4) {
+      uint32_t A[4], B[4], C[4], D[4], E[4];
+      #pragma unroll
+      for (int i = 0; i < 4; i++) {
+        const int r = r0 + i;
+        if (r >= 11) break;
         const int sy = inner_rows ? 2 * y0 - 2 + r : refl101(2 * y0 - 2 + r, sh);
         const uint32_t* row = src + (size_t)sy * sw;
-        uint32_t a, b, c, d, e;
         if (interior) {
             const uint2 ab = __ldg(reinterpret_cast<const uint2*>(row + 2 * x - 2)), cd = __ldg(reinterpret_cast<const uint2*>(row + 2 * x));
-            a = ab.x; b = ab.y; c = cd.x; d = cd.y; e = __ldg(row + 2 * x + 2);
+            A[i] = ab.x; B[i] = ab.y; C[i] = cd.x; D[i] = cd.y; E[i] = __ldg(row + 2 * x + 2);
         } else {
-            a = __ldg(row + xi[0]); b = __ldg(row + xi[1]); c = __ldg(row + xi[2]); d = __ldg(row + xi[3]); e = __ldg(row + xi[4]);
+            A[i] = __ldg(row + xi[0]); B[i] = __ldg(row + xi[1]); C[i] = __ldg(row + xi[2]); D[i] = __ldg(row + xi[3]); E[i] = __ldg(row + xi[4]);
         }
+      }
+      #pragma unroll
+      for (int i = 0; i < 4; i++) {
+        const int r = r0 + i;
+        if (r >= 11) break;
+        const uint32_t a = A[i], b = B[i], c = C[i], d = D[i], e = E[i];
         const uint32_t rg_ab = __byte_perm(a, b, 0x5140), rg_cd = __byte_perm(c, d, 0x5140);       // Ra Rb Ga Gb | Rc Rd Gc Gd
         const uint32_t r4 = __byte_perm(rg_ab, rg_cd, 0x5410), g4 = __byte_perm(rg_ab, rg_cd, 0x7632);
         const uint32_t b4 = __byte_perm(__byte_perm(a, b, 0x4462), __byte_perm(c, d, 0x4462), 0x5410);
@@ -334,6 +409,7 @@ __device__ __forceinline__ void mb_down_strip_u8(const uint32_t* __restrict__ sr
             const uint32_t kw = t == 2 ? 6u : (t == 1 || t == 3) ? 4u : 1u;
             arb[j] += kw * hrb; ag[j] += kw * hg;
         }
+      }
     }
     #pragma unroll
     for (int j = 0; j < 4; j++)
@@ -410,6 +486,7 @@ __global__ void __launch_bounds__(256) k_mb_band(const __grid_constant__ MbParam
         const short r = (short)__float2int_rz(__fdiv_rn((float)(short)acc[q][0], den));
         const short g = (short)__float2int_rz(__fdiv_rn((float)(short)acc[q][1], den));
         const short b = (short)__float2int_rz(__fdiv_rn((float)(short)acc[q][2], den));
+        note_range(p, l, r, g, b);
         p.dst[di] = make_short4(r, g, b, 0);
     }
 }
@@ -421,13 +498,15 @@ __global__ void __launch_bounds__(256) k_mb_collapse(const __grid_constant__ MbP
     const int w = p.lw[l - 1], h = p.lh[l - 1];
     if (X0 >= w || Y >= h) return;
     int3 up[4];
-    pyrup4(p.dst + p.off_d[l], p.lw[l], p.lh[l], X0, Y, up);
+    pyrup4_dst(p, l, X0, Y, up);
     #pragma unroll
     for (int q = 0; q < 4; q++) {
         if (X0 + q >= w) break;
         const size_t di = p.off_d[l - 1] + (size_t)Y * w + X0 + q;
         const short4 cur = p.dst[di];
-        p.dst[di] = make_short4((short)sat16(up[q].x + cur.x), (short)sat16(up[q].y + cur.y), (short)sat16(up[q].z + cur.z), 0);
+        const int r = sat16(up[q].x + cur.x), g = sat16(up[q].y + cur.y), b = sat16(up[q].z + cur.z);
+        note_range(p, l - 1, r, g, b);
+        p.dst[di] = make_short4((short)r, (short)g, (short)b, 0);
     }
 }
 
@@ -491,7 +570,7 @@ __global__ void __launch_bounds__(256) k_mb_final(const __grid_constant__ MbPara
                 }
             }
             int3 up[4];
-            if (p.nb > 0) pyrup4(p.dst + p.off_d[1], p.lw[1], p.lh[1], x0, y, up);
+            if (p.nb > 0) pyrup4_dst(p, 1, x0, y, up);
             #pragma unroll
             for (int q = 0; q < 4; q++) {
                 if (!(dw[q] > 1e-5f)) continue;
@@ -682,6 +761,14 @@ Multiband* multiband_create(octvr_mapper& m, const octvr_template& t,
     OB_CUDA(cudaMemset(mb->d_g0, 0, std::max<size_t>(g0_total, 1) * sizeof(uint32_t)));       // chunks without valid entries stay 0
     OB_CUDA(cudaMalloc(&mb->d_g, std::max<size_t>(g_total, 1) * sizeof(short4)));
     OB_CUDA(cudaMalloc(&mb->d_dst, std::max<size_t>(doff, 1) * sizeof(short4)));
+    OB_CUDA(cudaMalloc(&mb->d_wide, MB_MAX_LEVELS * sizeof(int)));
+    {   // OCTVR_MB_WIDE=1 (diagnostic / tests): every blended level is treated as wide, i.e. the 32-bit pyrUp everywhere
+        const char* e = getenv("OCTVR_MB_WIDE");
+        mb->force_wide = e && atoi(e) != 0;
+        std::vector<int> init(MB_MAX_LEVELS, mb->force_wide ? 1 : 0);
+        OB_CUDA(cudaMemcpy(mb->d_wide, init.data(), init.size() * sizeof(int), cudaMemcpyHostToDevice));
+    }
+    p.wide = mb->d_wide; p.clear_wide = mb->force_wide ? 0 : 1;
     p.coords = mb->d_coords; p.g0 = mb->d_g0; p.g = mb->d_g; p.w = mb->d_w; p.dst = mb->d_dst; p.dstw = mb->d_dstw;
     for (int i = 0; i < n; i++) { p.rgbx[i] = m.d_rgbx[i]; p.src_pitch[i] = m.in_w[i]; }
     m.table_bytes = (int64_t)(coords.size() * sizeof(uint2) + wts.size() * 4 + dstw.size() * 4);
@@ -718,7 +805,7 @@ int multiband_launches(const octvr_mapper& m) { return m.mb ? m.mb->launches : 0
 void multiband_destroy(Multiband* mb)
 {
     if (!mb) return;
-    cudaFree(mb->d_chunks); cudaFree(mb->d_tile_cams); cudaFree(mb->d_coords); cudaFree(mb->d_g0); cudaFree(mb->d_g); cudaFree(mb->d_w); cudaFree(mb->d_dst); cudaFree(mb->d_dstw);
+    cudaFree(mb->d_chunks); cudaFree(mb->d_tile_cams); cudaFree(mb->d_coords); cudaFree(mb->d_g0); cudaFree(mb->d_g); cudaFree(mb->d_w); cudaFree(mb->d_dst); cudaFree(mb->d_dstw); cudaFree(mb->d_wide);
     delete mb;
 }
 
