@@ -354,6 +354,57 @@ template <class T> __device__ __forceinline__ void mb_down_strip(const T* __rest
             dst[(size_t)(y0 + j) * dw + x] = make_short4((short)sat16((acc[j][0] + 128) >> 8), (short)sat16((acc[j][1] + 128) >> 8), (short)sat16((acc[j][2] + 128) >> 8), 0);
 }
 
+// Levels >= 1 of a CAMERA pyramid: values within [0, 255] stored as short4 {R, G, B, 0}, so the words {R | G << 16, B} are
+// filtered as packed 16-bit lanes (5 x 5 sum <= 256 * 255 < 2^16) with 16-byte loads in the interior, rows fetched in
+// groups ahead of their use and no early exit (see mb_down_strip_u8).  The same integers as mb_down_strip<short4>.
+__device__ __forceinline__ void mb_down_strip_p16(const short4* __restrict__ src, short4* __restrict__ dst, int sw, int sh, int dw, int dh, int x, int y0)
+{
+    const bool interior = 2 * x - 2 >= 0 && 2 * x + 2 < sw;
+    int xi[5];
+    #pragma unroll
+    for (int k = 0; k < 5; k++) xi[k] = refl101(2 * x + k - 2, sw);
+    uint32_t alo[4], ahi[4];
+    #pragma unroll
+    for (int j = 0; j < 4; j++) alo[j] = ahi[j] = 0u;
+    const bool inner_rows = 2 * y0 - 2 >= 0 && 2 * y0 + 8 < sh;
+    #pragma unroll
+    for (int r0 = 0; r0 < 11; r0 += 3) {
+        uint2 P[3][5];
+        #pragma unroll
+        for (int i = 0; i < 3; i++) {
+            const int r = r0 + i;
+            if (r >= 11) break;
+            const short4* row = src + (size_t)(inner_rows ? 2 * y0 - 2 + r : refl101(2 * y0 - 2 + r, sh)) * sw;
+            if (interior) {
+                const uint4 ab = __ldg(reinterpret_cast<const uint4*>(row + 2 * x - 2)), cd = __ldg(reinterpret_cast<const uint4*>(row + 2 * x));
+                P[i][0] = make_uint2(ab.x, ab.y); P[i][1] = make_uint2(ab.z, ab.w); P[i][2] = make_uint2(cd.x, cd.y); P[i][3] = make_uint2(cd.z, cd.w);
+                P[i][4] = ldp(row, 2 * x + 2);
+            } else {
+                #pragma unroll
+                for (int k = 0; k < 5; k++) P[i][k] = ldp(row, xi[k]);
+            }
+        }
+        #pragma unroll
+        for (int i = 0; i < 3; i++) {
+            const int r = r0 + i;
+            if (r >= 11) break;
+            const uint32_t hlo = (P[i][0].x + P[i][4].x) + 4u * (P[i][1].x + P[i][3].x) + 6u * P[i][2].x;
+            const uint32_t hhi = (P[i][0].y + P[i][4].y) + 4u * (P[i][1].y + P[i][3].y) + 6u * P[i][2].y;
+            #pragma unroll
+            for (int j = 0; j < 4; j++) {
+                const int t = r - 2 * j;
+                if (t < 0 || t > 4) continue;
+                const uint32_t kw = t == 2 ? 6u : (t == 1 || t == 3) ? 4u : 1u;
+                alo[j] += kw * hlo; ahi[j] += kw * hhi;
+            }
+        }
+    }
+    #pragma unroll
+    for (int j = 0; j < 4; j++)
+        if (y0 + j < dh)
+            *reinterpret_cast<uint2*>(dst + (size_t)(y0 + j) * dw + x) = make_uint2(((alo[j] + 0x00800080u) >> 8) & 0x00FF00FFu, (ahi[j] + 128u) >> 8);
+}
+
 // Level 0 -> 1: the source is RGBX8888 with X = 0.  ncu showed the generic strip ALU-pipe bound (75 % of the LOP3 / SHF /
 // PRMT / IADD3 pipe: byte unpacking and index arithmetic, 107 instructions per source row).  Here the five pixels of a row
 // come from two 8-byte loads and one 4-byte load (interior columns), their bytes are transposed per channel with seven
@@ -420,14 +471,14 @@ __device__ __forceinline__ void mb_down_strip_u8(const uint32_t* __restrict__ sr
         }
 }
 
-__global__ void __launch_bounds__(256) k_mb_down(const __grid_constant__ MbParams p, int l)
+template <bool L0> __global__ void __launch_bounds__(256) k_mb_down(const __grid_constant__ MbParams p, int l)
 {
     const MbCam& cam = p.cam[blockIdx.z];
     const int sw = cam.bw >> l, sh = cam.bh >> l, dw = sw >> 1, dh = sh >> 1;
     const int x = blockIdx.x * 32 + threadIdx.x, y0 = (blockIdx.y * 8 + threadIdx.y) * 4;
     if (x >= dw || y0 >= dh) return;
-    if (l == 0) mb_down_strip_u8(p.g0 + cam.off_g[0], p.g + cam.off_g[1], sw, sh, dw, dh, x, y0);
-    else mb_down_strip(p.g + cam.off_g[l], p.g + cam.off_g[l + 1], sw, sh, dw, dh, x, y0);
+    if (L0) mb_down_strip_u8(p.g0 + cam.off_g[0], p.g + cam.off_g[1], sw, sh, dw, dh, x, y0);
+    else mb_down_strip_p16(p.g + cam.off_g[l], p.g + cam.off_g[l + 1], sw, sh, dw, dh, x, y0);
 }
 
 // ---- k_mb_band: one thread per FOUR horizontally adjacent pixels of destination level l (CTA = 128 x 8 pixels) ----
@@ -711,7 +762,8 @@ Multiband* multiband_create(octvr_mapper& m, const octvr_template& t,
         c.x0 = tnx - Rf.x; c.y0 = fy0 + ys - E0; c.bw = width; c.bh = ch;
         if (ch > 0) { mb->max_bw = std::max(mb->max_bw, width); mb->max_bh = std::max(mb->max_bh, ch); }
         c.off_g[0] = g0_total; g0_total += (size_t)width * ch;
-        for (int l = 1; l <= nb; l++) { c.off_g[l] = g_total; g_total += (size_t)(width >> l) * (ch >> l); }
+        // every level starts at an even element: 16-byte aligned rows for the vector loads of mb_down_strip_p16
+        for (int l = 1; l <= nb; l++) { c.off_g[l] = g_total; g_total += (size_t)(width >> l) * (ch >> l); g_total += g_total & 1; }
         // level-0 remap table with BORDER_REFLECT baked in, and the f32 weight map (BORDER_CONSTANT 0)
         Img<float> wmap(width, height, 0.f);
         const float inv255 = (float)(1. / 255.);
@@ -790,8 +842,11 @@ void multiband_stitch(octvr_mapper& m, const octvr_frame* out, cudaStream_t s)
     const int nb = p.nb, n = p.n;
     if (mb.n_chunks) k_mb_warp<<<(mb.n_chunks + MB_WARP_CHUNKS - 1) / MB_WARP_CHUNKS, 256, 0, s>>>(p, mb.n_chunks);
     if (p.lh[0] > 0 && mb.max_bh > 0) {                    // an empty row window (a band outside the result roi) only writes black
-        for (int l = 0; l < nb; l++)
-            k_mb_down<<<dim3(((mb.max_bw >> (l + 1)) + 31) / 32, ((mb.max_bh >> (l + 1)) + 31) / 32, n), dim3(32, 8), 0, s>>>(p, l);
+        for (int l = 0; l < nb; l++) {
+            const dim3 grid(((mb.max_bw >> (l + 1)) + 31) / 32, ((mb.max_bh >> (l + 1)) + 31) / 32, n);
+            if (l == 0) k_mb_down<true><<<grid, dim3(32, 8), 0, s>>>(p, l);
+            else k_mb_down<false><<<grid, dim3(32, 8), 0, s>>>(p, l);
+        }
         if (nb >= 1)                                        // levels 1 .. nb in one launch; level 0 is computed inside k_mb_final
             k_mb_band<<<dim3((p.lw[1] + 127) / 128, (p.lh[1] + 7) / 8, nb), dim3(32, 8), 0, s>>>(p);
         for (int l = nb; l >= 2; l--)
