@@ -255,50 +255,51 @@ __device__ __forceinline__ void note_range(const MbParams& p, int l, int r, int 
 //      by that latency (ncu: 26 long-scoreboard stalls per issue at 85 % occupancy).  A thread now loads its four table
 //      entries first, then all sixteen taps, then does the arithmetic: four independent chains in flight per thread. ----
 constexpr int MB_WARP_CHUNKS = 4;
-__global__ void __launch_bounds__(256) k_mb_warp(const __grid_constant__ MbParams p, unsigned n_chunks)
+// The four chunks of a CTA belong to ONE camera (the host pads every camera's part of the list to a multiple of four with
+// chunk index 0xFFFFFFFF), so the source plane, pitch and gain are CTA-uniform and stay out of the per-pixel code.
+__global__ void __launch_bounds__(256) k_mb_warp(const __grid_constant__ MbParams p)
 {
     if (blockIdx.x == 0 && threadIdx.x < MB_MAX_LEVELS && p.clear_wide) p.wide[threadIdx.x] = 0;   // new frame: every level narrow until proven wide
-    int cam[MB_WARP_CHUNKS];
-    unsigned long long at[MB_WARP_CHUNKS];
+    const uint2* list = p.warp_chunks + (size_t)blockIdx.x * MB_WARP_CHUNKS;
+    const int c = (int)__ldg(&list[0].x);
+    const MbCam& cam = p.cam[c];
+    const unsigned npx = (unsigned)(cam.bw * cam.bh);
+    const uint2* __restrict__ coords = p.coords + cam.off_g[0];
+    uint32_t* __restrict__ g0 = p.g0 + cam.off_g[0];
+    const uint32_t* __restrict__ src = p.rgbx[c];
+    const int pitch = p.src_pitch[c];
+    unsigned t[MB_WARP_CHUNKS];
     uint2 cc[MB_WARP_CHUNKS];
     #pragma unroll
     for (int j = 0; j < MB_WARP_CHUNKS; j++) {
-        const unsigned e = blockIdx.x * MB_WARP_CHUNKS + j;
-        cam[j] = -1; cc[j] = make_uint2(0u, 0u); at[j] = 0;
-        if (e < n_chunks) {
-            const uint2 wc = __ldg(p.warp_chunks + e);      // chunks without any valid entry are never listed: they stay 0
-            const MbCam& c = p.cam[wc.x];
-            const unsigned t = wc.y * 256 + threadIdx.x;
-            if (t < (unsigned)(c.bw * c.bh)) { cam[j] = (int)wc.x; at[j] = c.off_g[0] + t; }
-        }
+        const unsigned k = __ldg(&list[j].y);
+        t[j] = k == 0xFFFFFFFFu ? 0xFFFFFFFFu : k * 256u + threadIdx.x;
+        if (t[j] >= npx) t[j] = 0xFFFFFFFFu;
     }
     #pragma unroll
-    for (int j = 0; j < MB_WARP_CHUNKS; j++) if (cam[j] >= 0) cc[j] = __ldcs(p.coords + at[j]);
+    for (int j = 0; j < MB_WARP_CHUNKS; j++) cc[j] = t[j] != 0xFFFFFFFFu ? __ldcs(coords + t[j]) : make_uint2(0u, 0u);
     uint32_t tap[MB_WARP_CHUNKS][4];
     #pragma unroll
     for (int j = 0; j < MB_WARP_CHUNKS; j++) {
         tap[j][0] = tap[j][1] = tap[j][2] = tap[j][3] = 0u;
-        if (cc[j].y & C_VALID) fetch_taps(p.rgbx[cam[j]], p.src_pitch[cam[j]], cc[j], tap[j][0], tap[j][1], tap[j][2], tap[j][3]);
+        if (cc[j].y & C_VALID) fetch_taps(src, pitch, cc[j], tap[j][0], tap[j][1], tap[j][2], tap[j][3]);
     }
+    // gain: verified f32 multiplier, or the exact LUT when the camera is flagged (kernels.cu, gain_tables)
+    const bool use_lut = p.use_gain && __ldg(p.gain_flag + c) != 0;
+    const float g32 = p.use_gain ? __ldg(p.gain_f32 + c) : 1.f;
+    const uint8_t* lut = p.gain_lut + c * 256;
     #pragma unroll
     for (int j = 0; j < MB_WARP_CHUNKS; j++) {
-        if (cam[j] < 0) continue;
+        if (t[j] == 0xFFFFFFFFu) continue;
         uint32_t px = 0;
         if (cc[j].y & C_VALID) {
             int r, g, b;
             bilerp_rgbx(tap[j][0], tap[j][1], tap[j][2], tap[j][3], cc[j].y & 31u, (cc[j].y >> 5) & 31u, r, g, b);
-            if (p.use_gain) {
-                if (__ldg(p.gain_flag + cam[j]) == 0) {
-                    const float g32 = __ldg(p.gain_f32 + cam[j]);
-                    r = (int)gain_apply_f32((float)r, g32); g = (int)gain_apply_f32((float)g, g32); b = (int)gain_apply_f32((float)b, g32);
-                } else {
-                    const uint8_t* lut = p.gain_lut + cam[j] * 256;
-                    r = __ldg(lut + r); g = __ldg(lut + g); b = __ldg(lut + b);
-                }
-            }
+            if (use_lut) { r = __ldg(lut + r); g = __ldg(lut + g); b = __ldg(lut + b); }
+            else if (p.use_gain) { r = (int)gain_apply_f32((float)r, g32); g = (int)gain_apply_f32((float)g, g32); b = (int)gain_apply_f32((float)b, g32); }
             px = (uint32_t)r | ((uint32_t)g << 8) | ((uint32_t)b << 16);
         }
-        p.g0[at[j]] = px;
+        g0[t[j]] = px;
     }
 }
 
@@ -548,13 +549,16 @@ __global__ void __launch_bounds__(256) k_mb_collapse(const __grid_constant__ MbP
     const int X0 = (blockIdx.x * 32 + threadIdx.x) * 4, Y = blockIdx.y * 8 + threadIdx.y;
     const int w = p.lw[l - 1], h = p.lh[l - 1];
     if (X0 >= w || Y >= h) return;
+    short4 curv[4];                                                  // fetched before the pyrUp: both load groups in flight together
+    #pragma unroll
+    for (int q = 0; q < 4; q++) curv[q] = X0 + q < w ? p.dst[p.off_d[l - 1] + (size_t)Y * w + X0 + q] : make_short4(0, 0, 0, 0);
     int3 up[4];
     pyrup4_dst(p, l, X0, Y, up);
     #pragma unroll
     for (int q = 0; q < 4; q++) {
         if (X0 + q >= w) break;
         const size_t di = p.off_d[l - 1] + (size_t)Y * w + X0 + q;
-        const short4 cur = p.dst[di];
+        const short4 cur = curv[q];
         const int r = sat16(up[q].x + cur.x), g = sat16(up[q].y + cur.y), b = sat16(up[q].z + cur.z);
         note_range(p, l - 1, r, g, b);
         p.dst[di] = make_short4((short)r, (short)g, (short)b, 0);
@@ -785,6 +789,7 @@ Multiband* multiband_create(octvr_mapper& m, const octvr_template& t,
             for (size_t e = k * 256; e < std::min((k + 1) * 256, (size_t)width * ch) && !any; e++) any = (ce[e].y & C_VALID) != 0;
             if (any) chunks.push_back(make_uint2((uint32_t)i, (uint32_t)k));
         }
+        while (chunks.size() % MB_WARP_CHUNKS) chunks.push_back(make_uint2((uint32_t)i, 0xFFFFFFFFu));   // a CTA's chunks share a camera
         Img<float> wl = std::move(wmap);
         int xt = c.x0, yt = c.y0;
         for (int l = 0; l <= nb; l++) {
@@ -840,7 +845,7 @@ void multiband_stitch(octvr_mapper& m, const octvr_frame* out, cudaStream_t s)
     }
     p.rgb_out = m.rgb_this_frame ? m.d_rgb : nullptr; p.rgb_pitch = (uint32_t)m.out_w * 3;
     const int nb = p.nb, n = p.n;
-    if (mb.n_chunks) k_mb_warp<<<(mb.n_chunks + MB_WARP_CHUNKS - 1) / MB_WARP_CHUNKS, 256, 0, s>>>(p, mb.n_chunks);
+    if (mb.n_chunks) k_mb_warp<<<mb.n_chunks / MB_WARP_CHUNKS, 256, 0, s>>>(p);
     if (p.lh[0] > 0 && mb.max_bh > 0) {                    // an empty row window (a band outside the result roi) only writes black
         for (int l = 0; l < nb; l++) {
             const dim3 grid(((mb.max_bw >> (l + 1)) + 31) / 32, ((mb.max_bh >> (l + 1)) + 31) / 32, n);
