@@ -652,15 +652,17 @@ __device__ __forceinline__ void mbar_expect_tx(uint64_t* mbar, uint32_t bytes)
 {
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"((uint32_t)__cvta_generic_to_shared(mbar)), "r"(bytes) : "memory");
 }
+// try_wait with a suspend-time hint: the waiting warp sleeps in hardware instead of re-issuing the poll (the ncu source
+// page showed the bare try_wait + branch loop at 14 % of all issued instructions of K_blend_staged)
 __device__ __forceinline__ void mbar_wait(uint64_t* mbar, uint32_t phase)
 {
     asm volatile(
         "{\n\t.reg .pred P1;\n\t"
         "WAIT_LOOP:\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1, %2;\n\t"
         "@P1 bra DONE;\n\t"
         "bra WAIT_LOOP;\n\t"
-        "DONE:\n\t}" ::"r"((uint32_t)__cvta_generic_to_shared(mbar)), "r"(phase) : "memory");
+        "DONE:\n\t}" ::"r"((uint32_t)__cvta_generic_to_shared(mbar)), "r"(phase), "r"(0x989680u) : "memory");
 }
 __device__ __forceinline__ void tma_load_2d(void* smem_dst, const void* tmap, int x, int y, uint64_t* mbar)
 {
@@ -669,6 +671,9 @@ __device__ __forceinline__ void tma_load_2d(void* smem_dst, const void* tmap, in
 }
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
+#ifndef OCTVR_STAGED_WAIT_ALL
+#define OCTVR_STAGED_WAIT_ALL 0
+#endif
 template <int GAIN>   // 0: no gain, 1: verified f32 multiplier (LUT fallback per job if flagged)
 __global__ void __launch_bounds__(256, 7) k_blend_staged(const __grid_constant__ StagedParams p)
 {
@@ -710,7 +715,10 @@ __global__ void __launch_bounds__(256, 7) k_blend_staged(const __grid_constant__
             for (int q = k; q < kend; q++)
                 tma_load_2d(s_buf + s_job[q].soff, (const char*)p.tmaps + (size_t)s_job[q].tmap * 128, s_job[q].bx0, s_job[q].by0, &s_mbar);
         }
-        mbar_wait(&s_mbar, phase);
+        // one warp polls the mbarrier, the others park at the CTA barrier (which costs no issue slots); the polling thread's
+        // acquire plus the barrier make the TMA-written stage visible to every thread
+        if (OCTVR_STAGED_WAIT_ALL || tid < 32) mbar_wait(&s_mbar, phase);
+        if (!OCTVR_STAGED_WAIT_ALL) __syncthreads();
         phase ^= 1u;
         #pragma unroll 1
         for (; k < kend; k++) {

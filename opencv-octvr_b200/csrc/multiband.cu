@@ -510,24 +510,26 @@ __global__ void __launch_bounds__(256) k_mb_band(const __grid_constant__ MbParam
         const int x0 = X0 - (cam.x0 >> l), y = Y - (cam.y0 >> l);
         const int w_l = cam.bw >> l, h_l = cam.bh >> l;
         if (y < 0 || y >= h_l || x0 + 3 < 0 || x0 >= w_l) continue;
+        // interior groups: no per-pixel bounds checks or branches (a zero weight adds (short)(lap * 0) = 0); the weight and
+        // the level-l samples are fetched together
+        const float* wrow = p.w + cam.off_w[l] + (size_t)y * w_l + x0;
+        const short4* grow = p.g + cam.off_g[l] + (size_t)y * w_l + x0;
+        const bool in4 = x0 >= 0 && x0 + 3 < w_l;
         float w[4];
-        bool any = false;
+        uint2 gl[4];
         #pragma unroll
         for (int q = 0; q < 4; q++) {
-            const int x = x0 + q;
-            w[q] = (x >= 0 && x < w_l) ? __ldg(p.w + cam.off_w[l] + (size_t)y * w_l + x) : 0.f;
-            any = any || w[q] != 0.f;                                 // (short)(lap * 0) == 0
+            const bool in = in4 || (x0 + q >= 0 && x0 + q < w_l);
+            w[q] = in ? __ldg(wrow + q) : 0.f;
+            gl[q] = in ? ldp(grow, q) : make_uint2(0u, 0u);
         }
-        if (!any) continue;
+        if (w[0] == 0.f && w[1] == 0.f && w[2] == 0.f && w[3] == 0.f) continue;
         uint2 up[4];
         const bool lap = l < p.nb;                                    // createLaplacePyr: pyr[l] -= pyrUp(pyr[l+1]); the top level stays Gaussian
         if (lap) pyrup4_packed(p.g + cam.off_g[l + 1], w_l >> 1, h_l >> 1, x0, y, up);
         #pragma unroll
-        for (int q = 0; q < 4; q++) {
-            if (w[q] == 0.f) continue;
-            const uint2 gl = ldp(p.g + cam.off_g[l], y * w_l + x0 + q);            // levels >= 1 only (level 0 lives in k_mb_final)
-            lap_weight_acc((int)(gl.x & 0xFFFFu), (int)(gl.x >> 16), (int)gl.y, up[q], lap, w[q], acc[q]);
-        }
+        for (int q = 0; q < 4; q++)
+            lap_weight_acc((int)(gl[q].x & 0xFFFFu), (int)(gl[q].x >> 16), (int)gl[q].y, up[q], lap, w[q], acc[q]);
     }
     #pragma unroll
     for (int q = 0; q < 4; q++) {
@@ -589,52 +591,54 @@ __global__ void __launch_bounds__(256) k_mb_final(const __grid_constant__ MbPara
     for (int q = 0; q < 4; q++) R[q] = G[q] = B[q] = 0;
     const int x0 = X0 - p.rx, y = Y - p.ry;
     if (y >= 0 && y < p.rh && x0 + 3 >= 0 && x0 < p.rw) {
+        // Interior groups (all four pixels inside the roi / the camera rectangle: almost all of them) run without per-pixel
+        // bounds checks or branches: a zero weight contributes (short)(lap * 0) = 0 whether or not it is skipped.
+        const float* dwrow = p.dstw + p.off_d[0] + (size_t)y * p.lw[0] + x0;
+        const bool full4 = x0 >= 0 && x0 + 3 < p.rw;
         float dw[4];
-        bool any = false;
         #pragma unroll
-        for (int q = 0; q < 4; q++) {
-            const int x = x0 + q;
-            dw[q] = (x >= 0 && x < p.rw) ? __ldg(p.dstw + p.off_d[0] + (size_t)y * p.lw[0] + x) : 0.f;
-            any = any || dw[q] > 1e-5f;                                // dst_mask = dst_band_weights_[0] > WEIGHT_EPS (blenders.cpp:472)
-        }
-        if (any) {
+        for (int q = 0; q < 4; q++) dw[q] = (full4 || (x0 + q >= 0 && x0 + q < p.rw)) ? __ldg(dwrow + q) : 0.f;
+        bool ok[4];
+        #pragma unroll
+        for (int q = 0; q < 4; q++) ok[q] = dw[q] > 1e-5f;             // dst_mask = dst_band_weights_[0] > WEIGHT_EPS (blenders.cpp:472)
+        if (ok[0] || ok[1] || ok[2] || ok[3]) {
             int acc[4][3];
             #pragma unroll
             for (int q = 0; q < 4; q++) acc[q][0] = acc[q][1] = acc[q][2] = 0;
             for (; cams; cams &= cams - 1) {
                 const int c = __ffs(cams) - 1;
                 const MbCam& cam = p.cam[c];
-                const int cx0 = x0 - cam.x0, cy = y - cam.y0;
-                if (cy < 0 || cy >= cam.bh || cx0 + 3 < 0 || cx0 >= cam.bw) continue;
+                const int bw = cam.bw, cx0 = x0 - cam.x0, cy = y - cam.y0;
+                if (cy < 0 || cy >= cam.bh || cx0 + 3 < 0 || cx0 >= bw) continue;
+                const float* wrow = p.w + cam.off_w[0] + (size_t)cy * bw + cx0;
+                const uint32_t* grow = p.g0 + cam.off_g[0] + (size_t)cy * bw + cx0;
+                const bool in4 = cx0 >= 0 && cx0 + 3 < bw;
                 float w[4];
-                bool anyw = false;
+                uint32_t px[4];
                 #pragma unroll
                 for (int q = 0; q < 4; q++) {
-                    const int x = cx0 + q;
-                    w[q] = (x >= 0 && x < cam.bw && dw[q] > 1e-5f) ? __ldg(p.w + cam.off_w[0] + (size_t)cy * cam.bw + x) : 0.f;
-                    anyw = anyw || w[q] != 0.f;
+                    const bool in = in4 || (cx0 + q >= 0 && cx0 + q < bw);
+                    w[q] = in ? __ldg(wrow + q) : 0.f;
+                    px[q] = in ? __ldg(grow + q) : 0u;
+                    w[q] = ok[q] ? w[q] : 0.f;
                 }
-                if (!anyw) continue;
+                if (w[0] == 0.f && w[1] == 0.f && w[2] == 0.f && w[3] == 0.f) continue;
                 uint2 up[4];
-                if (p.nb > 0) pyrup4_packed(p.g + cam.off_g[1], cam.bw >> 1, cam.bh >> 1, cx0, cy, up);
+                if (p.nb > 0) pyrup4_packed(p.g + cam.off_g[1], bw >> 1, cam.bh >> 1, cx0, cy, up);
                 #pragma unroll
-                for (int q = 0; q < 4; q++) {
-                    if (w[q] == 0.f) continue;
-                    const uint32_t px = __ldg(p.g0 + cam.off_g[0] + (size_t)cy * cam.bw + cx0 + q);
-                    lap_weight_acc((int)(px & 255u), (int)((px >> 8) & 255u), (int)((px >> 16) & 255u), up[q], p.nb > 0, w[q], acc[q]);
-                }
+                for (int q = 0; q < 4; q++)
+                    lap_weight_acc((int)(px[q] & 255u), (int)((px[q] >> 8) & 255u), (int)((px[q] >> 16) & 255u), up[q], p.nb > 0, w[q], acc[q]);
             }
             int3 up[4];
             if (p.nb > 0) pyrup4_dst(p, 1, x0, y, up);
             #pragma unroll
             for (int q = 0; q < 4; q++) {
-                if (!(dw[q] > 1e-5f)) continue;
                 const float den = __fadd_rn(dw[q], 1e-5f);            // normalizeUsingWeightMap (blenders.cpp:788-797)
                 int3 v = make_int3((short)__float2int_rz(__fdiv_rn((float)(short)acc[q][0], den)),
                                    (short)__float2int_rz(__fdiv_rn((float)(short)acc[q][1], den)),
                                    (short)__float2int_rz(__fdiv_rn((float)(short)acc[q][2], den)));
                 if (p.nb > 0) v = make_int3(sat16(up[q].x + v.x), sat16(up[q].y + v.y), sat16(up[q].z + v.z));
-                R[q] = clamp255(v.x); G[q] = clamp255(v.y); B[q] = clamp255(v.z);   // convertTo(CV_8U)
+                R[q] = ok[q] ? clamp255(v.x) : 0; G[q] = ok[q] ? clamp255(v.y) : 0; B[q] = ok[q] ? clamp255(v.z) : 0;   // convertTo(CV_8U), masked
             }
         }
     }
