@@ -50,6 +50,20 @@ static TensorMapEncodeFn tensor_map_encoder()
     return fn;
 }
 
+// one 128-byte CUtensorMap over an RGBX plane (u32 elements, no swizzle, zero fill outside the plane) for w x h boxes
+void encode_rgbx_tensor_map(void* out128, const uint32_t* plane, int plane_w, int plane_h, int box_w, int box_h)
+{
+    static_assert(sizeof(CUtensorMap) == 128, "CUtensorMap is 128 bytes");
+    const cuuint64_t gdim[2] = { (cuuint64_t)plane_w, (cuuint64_t)plane_h };
+    const cuuint64_t gstride[1] = { (cuuint64_t)plane_w * 4 };
+    const cuuint32_t box[2] = { (cuuint32_t)box_w, (cuuint32_t)box_h };
+    const cuuint32_t estr[2] = { 1, 1 };
+    CUresult r = tensor_map_encoder()(reinterpret_cast<CUtensorMap*>(out128), CU_TENSOR_MAP_DATA_TYPE_UINT32, 2, const_cast<uint32_t*>(plane), gdim, gstride,
+                                      box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                                      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) fail(OCTVR_ERR_CUDA, "cuTensorMapEncodeTiled failed (" + std::to_string((int)r) + ")");
+}
+
 // table entry for one ROI pixel: fixed-point source position -> tap offset, fractions, border bits
 // Entries that do not contribute are {offset 0, no flags}: the blend kernel runs them branch-free with
 // weight 0 (reads source pixel 0, adds floor(v*0) = 0); the gain kernel checks C_VALID.

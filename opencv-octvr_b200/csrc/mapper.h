@@ -67,6 +67,8 @@ struct octvr_mapper {
 };
 
 namespace ob {
+// mapper.cpp: CUtensorMap (128 bytes, written to out128) over an RGBX plane for box_w x box_h boxes, zero fill outside
+void encode_rgbx_tensor_map(void* out128, const uint32_t* plane, int plane_w, int plane_h, int box_w, int box_h);
 // multiband.cu
 Multiband* multiband_create(octvr_mapper& m, const octvr_template& t,
                             const std::vector<Img<int32_t>>& sx, const std::vector<Img<int32_t>>& sy);

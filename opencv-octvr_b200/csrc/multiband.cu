@@ -19,7 +19,10 @@
 #include <cstdlib>
 #include <cstring>
 #include <cmath>
+#include <map>
 #include <memory>
+#include <string>
+#include <climits>
 
 namespace ob {
 
@@ -32,12 +35,20 @@ struct MbCam {
     unsigned long long off_w[MB_MAX_LEVELS];   // float offset of the level-l weights
 };
 
+// one job of the staged warp: the taps of the tile's valid pixels lie inside the box (bx0, by0, bw, bh) of camera `cam`'s
+// RGBX plane; the tile is (tx, ty) in units of 32 x 16 pixels of the camera's bordered level-0 rectangle
+struct MbWarpJob { int bx0, by0; uint16_t bw, bh; uint16_t tmap, cam; uint16_t tx, ty; uint32_t pad[3]; };
+constexpr int MB_STAGE = 6144;       // shared-memory stage of the staged warp, pixels (24 KB)
+constexpr uint32_t MBW_VALID = 0x80000000u;   // entry: stage offset (13 bits) | fy << 13 | fx << 18 | valid
+
 struct MbParams {
     int n, nb;
     MbCam cam[MAX_CAMS];
     int lw[MB_MAX_LEVELS], lh[MB_MAX_LEVELS];
     unsigned long long off_d[MB_MAX_LEVELS];   // offsets of dst level l (short4 units) and dstw (floats)
     const uint2* coords;              // per camera bordered level-0 pixel: table entry (reflection already applied)
+    // staged warp (k_mb_warp_staged): per (camera, 32 x 16 tile of its bordered rectangle) a TMA box of the source plane
+    const struct MbWarpJob* wjobs; const uint32_t* wentries; const void* wtmaps;
     const uint2* warp_chunks;         // {camera, 256-pixel chunk} of every chunk with at least one valid entry (the others stay 0)
     const uint16_t* tile_cams;        // per level and 32 x 8 tile of dst: bit c set if camera c has a non-zero weight in the tile
     unsigned long long off_t[MB_MAX_LEVELS];   // first tile of level l in tile_cams
@@ -63,6 +74,7 @@ struct MbParams {
 struct Multiband {
     MbParams p;
     uint2* d_chunks = nullptr; uint16_t* d_tile_cams = nullptr; unsigned n_chunks = 0;
+    MbWarpJob* d_wjobs = nullptr; uint32_t* d_wentries = nullptr; void* d_wtmaps = nullptr; unsigned n_wjobs = 0;   // staged warp (0: direct)
     uint2* d_coords = nullptr; uint32_t* d_g0 = nullptr; short4* d_g = nullptr; float* d_w = nullptr;
     short4* d_dst = nullptr; float* d_dstw = nullptr; int* d_wide = nullptr; bool force_wide = false;
     int max_bw = 0, max_bh = 0;
@@ -303,6 +315,70 @@ __global__ void __launch_bounds__(256) k_mb_warp(const __grid_constant__ MbParam
     }
 }
 
+// ---- k_mb_warp_staged: the same warp with the source footprint of a 32 x 16 tile brought into shared memory by ONE TMA
+//      box copy (UTMALDG, zero fill outside the plane = BORDER_CONSTANT 0) and the four taps read from there.  The direct
+//      kernel's scattered 4-byte gathers made DRAM fetch random sectors (L2 hit rate 38 %); the box copy reads whole rows,
+//      and a 4-byte entry (stage offset | fractions) replaces the 8-byte one.  256 threads, two pixels each. ----
+__device__ __forceinline__ void mbw_mbar_init(uint64_t* mbar)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"((uint32_t)__cvta_generic_to_shared(mbar)) : "memory");
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbw_tma_box(void* smem_dst, const void* tmap, int x, int y, uint32_t bytes, uint64_t* mbar)
+{
+    const uint32_t mb = (uint32_t)__cvta_generic_to_shared(mbar);
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(mb), "r"(bytes) : "memory");
+    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+                 ::"r"((uint32_t)__cvta_generic_to_shared(smem_dst)), "l"((uint64_t)tmap), "r"(mb), "r"(x), "r"(y) : "memory");
+}
+__device__ __forceinline__ void mbw_wait(uint64_t* mbar)
+{
+    asm volatile(
+        "{\n\t.reg .pred P1;\n\t"
+        "MBW_WAIT:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], 0, %1;\n\t"
+        "@P1 bra MBW_DONE;\n\t"
+        "bra MBW_WAIT;\n\t"
+        "MBW_DONE:\n\t}" ::"r"((uint32_t)__cvta_generic_to_shared(mbar)), "r"(0x989680u) : "memory");
+}
+__global__ void __launch_bounds__(256) k_mb_warp_staged(const __grid_constant__ MbParams p)
+{
+    __shared__ __align__(128) uint32_t s_buf[MB_STAGE];
+    __shared__ __align__(8) uint64_t s_mbar;
+    if (blockIdx.x == 0 && threadIdx.x < MB_MAX_LEVELS && p.clear_wide) p.wide[threadIdx.x] = 0;   // new frame: every level narrow until proven wide
+    const int tid = threadIdx.x, lx = tid & 31, ly = tid >> 5;
+    const MbWarpJob job = p.wjobs[blockIdx.x];
+    if (tid == 0) mbw_mbar_init(&s_mbar);
+    __syncthreads();
+    if (tid == 0) mbw_tma_box(s_buf, (const char*)p.wtmaps + (size_t)job.tmap * 128, job.bx0, job.by0, (uint32_t)job.bw * job.bh * 4u, &s_mbar);
+    const uint32_t* ent = p.wentries + (size_t)blockIdx.x * TILE_PX + tid;
+    const uint32_t e0 = __ldcs(ent), e1 = __ldcs(ent + 256);
+    const int c = job.cam;
+    const MbCam& cam = p.cam[c];
+    const bool use_lut = p.use_gain && __ldg(p.gain_flag + c) != 0;
+    const float g32 = p.use_gain ? __ldg(p.gain_f32 + c) : 1.f;
+    const uint8_t* lut = p.gain_lut + c * 256;
+    const int bw = job.bw;
+    if (tid < 32) mbw_wait(&s_mbar);                        // one warp polls, the others park at the barrier
+    __syncthreads();
+    #pragma unroll
+    for (int h = 0; h < 2; h++) {
+        const uint32_t e = h ? e1 : e0;
+        const int x = job.tx * TILE_W + lx, y = job.ty * TILE_H + ly + 8 * h;
+        if (x >= cam.bw || y >= cam.bh) continue;
+        uint32_t px = 0;
+        if (e & MBW_VALID) {
+            const uint32_t off = e & 0x1FFFu;
+            int r, g, b;
+            bilerp_rgbx(s_buf[off], s_buf[off + 1], s_buf[off + bw], s_buf[off + bw + 1], (e >> 18) & 31u, (e >> 13) & 31u, r, g, b);
+            if (use_lut) { r = __ldg(lut + r); g = __ldg(lut + g); b = __ldg(lut + b); }
+            else if (p.use_gain) { r = (int)gain_apply_f32((float)r, g32); g = (int)gain_apply_f32((float)g, g32); b = (int)gain_apply_f32((float)b, g32); }
+            px = (uint32_t)r | ((uint32_t)g << 8) | ((uint32_t)b << 16);
+        }
+        p.g0[cam.off_g[0] + (size_t)y * cam.bw + x] = px;
+    }
+}
+
 // ---- k_mb_down: level l -> l+1 for every camera.  grid (ceil(w/32), ceil(h/8), cameras) at level l+1 ----
 template <class T> __device__ __forceinline__ int3 pyrdown_at(const T* s, int sw, int sh, int x, int y)
 {
@@ -485,7 +561,7 @@ template <bool L0> __global__ void __launch_bounds__(256) k_mb_down(const __grid
 // ---- k_mb_band: one thread per FOUR horizontally adjacent pixels of destination level l (CTA = 128 x 8 pixels) ----
 //      Levels do not depend on each other, so one launch covers all of them (blockIdx.z + 1 = level): the small levels,
 //      latency-bound on their own (15 us each for a few thousand pixels), hide under level 1.
-__global__ void __launch_bounds__(256) k_mb_band(const __grid_constant__ MbParams p)
+template <int MINB> __global__ void __launch_bounds__(256, MINB) k_mb_band(const __grid_constant__ MbParams p)
 {
     const int l = (int)blockIdx.z + 1;
     const int X0 = (blockIdx.x * 32 + threadIdx.x) * 4, Y = blockIdx.y * 8 + threadIdx.y;
@@ -571,7 +647,7 @@ __global__ void __launch_bounds__(256) k_mb_collapse(const __grid_constant__ MbP
 //      band (k_mb_band with l = 0: Laplacian, weighting, accumulation over the cameras, normalisation), adds pyrUp(dst_1)
 //      (the last collapse step), masks, narrows to 8 bit and stores RGB / YUV 4:2:0.  Pixels outside the result roi are
 //      black.  Saves the 8 B/px write + read of dst_0 and one launch. ----
-__global__ void __launch_bounds__(256) k_mb_final(const __grid_constant__ MbParams p)
+template <int MINB> __global__ void __launch_bounds__(256, MINB) k_mb_final(const __grid_constant__ MbParams p)
 {
     const int X0 = (blockIdx.x * 32 + threadIdx.x) * 4, Y = p.oy0 + blockIdx.y * 8 + threadIdx.y;
     // cameras with a non-zero level-0 weight somewhere under this CTA (128 x 8 output pixels = up to 5 x 2 weight tiles)
@@ -749,6 +825,14 @@ Multiband* multiband_create(octvr_mapper& m, const octvr_template& t,
     std::vector<uint2> coords;
     std::vector<float> wts;
     size_t g0_total = 0, g_total = 0;
+    // staged warp tables (k_mb_warp_staged); given up for the whole mapper if a tile's footprint does not fit the stage or a
+    // source width is not a multiple of 4 pixels (TMA: 16-byte row pitch), or when OCTVR_MB_WARP=direct
+    bool staged = true;
+    for (int i = 0; i < n; i++) staged = staged && m.in_w[i] % 4 == 0;
+    if (const char* e = getenv("OCTVR_MB_WARP")) staged = staged && std::string(e) != "direct";
+    std::vector<MbWarpJob> wjobs;
+    std::vector<uint32_t> wentries;
+    std::map<uint64_t, int> tmap_index;                     // (camera, box w, box h) -> descriptor slot
     for (int i = 0; i < n; i++) {
         const TInput& in = t.inputs[i];
         MbCam& c = p.cam[i];
@@ -777,6 +861,8 @@ Multiband* multiband_create(octvr_mapper& m, const octvr_template& t,
         const float inv255 = (float)(1. / 255.);
         coords.resize(coords.size() + (size_t)width * ch);
         uint2* ce = coords.data() + c.off_g[0];
+        std::vector<int16_t> qx, qy;                            // integer tap position of every valid pixel (staged warp)
+        if (staged) { qx.assign((size_t)width * ch, 0); qy.assign((size_t)width * ch, 0); }
         for (int y = 0; y < height; y++) {
             const int ly = mirror(y - top, in.roi.h);
             const bool in_y = y - top >= 0 && y - top < in.roi.h;
@@ -784,10 +870,50 @@ Multiband* multiband_create(octvr_mapper& m, const octvr_template& t,
             if (!in_win && !in_y) continue;
             for (int x = 0; x < width; x++) {
                 const int lx = mirror(x - left, in.roi.w);
-                if (in_win) ce[(size_t)(y - ys) * width + x] = mk_entry(sx[i].row(ly)[lx], sy[i].row(ly)[lx], m.in_w[i], m.in_h[i], in.mask.row(ly)[lx] != 0);
+                if (in_win) {
+                    const int32_t fsx = sx[i].row(ly)[lx], fsy = sy[i].row(ly)[lx];
+                    const size_t at = (size_t)(y - ys) * width + x;
+                    ce[at] = mk_entry(fsx, fsy, m.in_w[i], m.in_h[i], in.mask.row(ly)[lx] != 0);
+                    if (staged) { qx[at] = (int16_t)std::min(32767, std::max(-32768, fsx >> 5)); qy[at] = (int16_t)std::min(32767, std::max(-32768, fsy >> 5)); }
+                }
                 if (in_y && x - left >= 0 && x - left < in.roi.w) wmap.row(y)[x] = seams[i].row(y - top)[x - left] * inv255 + 0.f;
             }
         }
+        // staged warp: one job per 32 x 16 tile of the rectangle that has a valid pixel
+        for (int ty = 0; staged && ty < (ch + TILE_H - 1) / TILE_H; ty++)
+            for (int tx = 0; staged && tx < (width + TILE_W - 1) / TILE_W; tx++) {
+                int xmin = INT32_MAX, xmax = INT32_MIN, ymin = INT32_MAX, ymax = INT32_MIN;
+                for (int py = ty * TILE_H; py < std::min(ch, (ty + 1) * TILE_H); py++)
+                    for (int px = tx * TILE_W; px < std::min(width, (tx + 1) * TILE_W); px++) {
+                        const size_t at = (size_t)py * width + px;
+                        if (!(ce[at].y & C_VALID)) continue;
+                        xmin = std::min(xmin, (int)qx[at]); xmax = std::max(xmax, qx[at] + 1); ymin = std::min(ymin, (int)qy[at]); ymax = std::max(ymax, qy[at] + 1);
+                    }
+                if (xmin > xmax) continue;                          // nothing valid: the tile keeps the zeros of the one-time memset
+                auto size_class = [](int v) { return v <= 64 ? (v + 7) / 8 * 8 : v <= 128 ? (v + 15) / 16 * 16 : (v + 31) / 32 * 32; };
+                MbWarpJob job;
+                memset(&job, 0, sizeof(job));
+                job.bx0 = (int)std::floor(xmin / 4.0) * 4; job.by0 = ymin;          // TMA: the innermost start coordinate must be 16-byte aligned
+                const int bw = size_class(xmax - job.bx0 + 1), bh = size_class(ymax - ymin + 1);
+                if (bw > 256 || bh > 256 || (int64_t)bw * bh > MB_STAGE || tx > 65535 || ty > 65535) { staged = false; break; }
+                job.bw = (uint16_t)bw; job.bh = (uint16_t)bh; job.cam = (uint16_t)i; job.tx = (uint16_t)tx; job.ty = (uint16_t)ty;
+                const uint64_t key = ((uint64_t)i << 32) | ((uint64_t)bw << 16) | (uint64_t)bh;
+                auto it = tmap_index.find(key);
+                if (it == tmap_index.end()) it = tmap_index.emplace(key, (int)tmap_index.size()).first;
+                job.tmap = (uint16_t)it->second;
+                if (tmap_index.size() > 65535) { staged = false; break; }
+                const size_t e0 = wentries.size();
+                wentries.resize(e0 + TILE_PX, 0u);
+                for (int py = ty * TILE_H; py < std::min(ch, (ty + 1) * TILE_H); py++)
+                    for (int px = tx * TILE_W; px < std::min(width, (tx + 1) * TILE_W); px++) {
+                        const size_t at = (size_t)py * width + px;
+                        if (!(ce[at].y & C_VALID)) continue;
+                        const uint32_t off = (uint32_t)((qy[at] - job.by0) * bw + (qx[at] - job.bx0));
+                        wentries[e0 + (size_t)(py - ty * TILE_H) * TILE_W + (px - tx * TILE_W)] =
+                            off | ((ce[at].y >> 5) & 31u) << 13 | (ce[at].y & 31u) << 18 | MBW_VALID;      // fy, fx of the table entry
+                    }
+                wjobs.push_back(job);
+            }
         for (size_t k = 0; k < ((size_t)width * ch + 255) / 256; k++) {
             bool any = false;
             for (size_t e = k * 256; e < std::min((k + 1) * 256, (size_t)width * ch) && !any; e++) any = (ce[e].y & C_VALID) != 0;
@@ -812,6 +938,21 @@ Multiband* multiband_create(octvr_mapper& m, const octvr_template& t,
             xt /= 2; yt /= 2;
         }
     }
+    if (staged && !wjobs.empty()) {
+        std::vector<uint8_t> tmaps(tmap_index.size() * 128);
+        for (auto& kv : tmap_index) {
+            const int cam = (int)(kv.first >> 32), bw = (int)((kv.first >> 16) & 0xFFFF), bh = (int)(kv.first & 0xFFFF);
+            encode_rgbx_tensor_map(tmaps.data() + (size_t)kv.second * 128, m.d_rgbx[cam], m.in_w[cam], m.in_h[cam], bw, bh);
+        }
+        void* dt = nullptr;
+        OB_CUDA(cudaMalloc(&dt, tmaps.size()));
+        OB_CUDA(cudaMemcpy(dt, tmaps.data(), tmaps.size(), cudaMemcpyHostToDevice));
+        mb->d_wtmaps = dt;
+        mb->d_wjobs = upload(wjobs); mb->d_wentries = upload(wentries); mb->n_wjobs = (unsigned)wjobs.size();
+        p.wjobs = mb->d_wjobs; p.wentries = mb->d_wentries; p.wtmaps = mb->d_wtmaps;
+        coords.clear(); coords.shrink_to_fit();             // the 8-byte table is only read by the direct kernel
+        chunks.clear();
+    }
     mb->d_coords = upload(coords);
     mb->d_w = upload(wts);
     mb->d_dstw = upload(dstw);
@@ -832,7 +973,7 @@ Multiband* multiband_create(octvr_mapper& m, const octvr_template& t,
     p.wide = mb->d_wide; p.clear_wide = mb->force_wide ? 0 : 1;
     p.coords = mb->d_coords; p.g0 = mb->d_g0; p.g = mb->d_g; p.w = mb->d_w; p.dst = mb->d_dst; p.dstw = mb->d_dstw;
     for (int i = 0; i < n; i++) { p.rgbx[i] = m.d_rgbx[i]; p.src_pitch[i] = m.in_w[i]; }
-    m.table_bytes = (int64_t)(coords.size() * sizeof(uint2) + wts.size() * 4 + dstw.size() * 4);
+    m.table_bytes = (int64_t)(coords.size() * sizeof(uint2) + wentries.size() * 4 + wjobs.size() * sizeof(MbWarpJob) + wts.size() * 4 + dstw.size() * 4);
     mb->launches = 1 + nb + (nb >= 1 ? 1 : 0) + std::max(0, nb - 1) + 1;
     return mb.release();
 }
@@ -849,19 +990,30 @@ void multiband_stitch(octvr_mapper& m, const octvr_frame* out, cudaStream_t s)
     }
     p.rgb_out = m.rgb_this_frame ? m.d_rgb : nullptr; p.rgb_pitch = (uint32_t)m.out_w * 3;
     const int nb = p.nb, n = p.n;
-    if (mb.n_chunks) k_mb_warp<<<mb.n_chunks / MB_WARP_CHUNKS, 256, 0, s>>>(p);
+    static const int occ = [] { const char* e = getenv("OCTVR_MB_OCC"); return e ? atoi(e) : 4; }();   // resident CTAs / SM asked of band / final
+    if (mb.n_wjobs) k_mb_warp_staged<<<mb.n_wjobs, 256, 0, s>>>(p);
+    else if (mb.n_chunks) k_mb_warp<<<mb.n_chunks / MB_WARP_CHUNKS, 256, 0, s>>>(p);
     if (p.lh[0] > 0 && mb.max_bh > 0) {                    // an empty row window (a band outside the result roi) only writes black
         for (int l = 0; l < nb; l++) {
             const dim3 grid(((mb.max_bw >> (l + 1)) + 31) / 32, ((mb.max_bh >> (l + 1)) + 31) / 32, n);
             if (l == 0) k_mb_down<true><<<grid, dim3(32, 8), 0, s>>>(p, l);
             else k_mb_down<false><<<grid, dim3(32, 8), 0, s>>>(p, l);
         }
-        if (nb >= 1)                                        // levels 1 .. nb in one launch; level 0 is computed inside k_mb_final
-            k_mb_band<<<dim3((p.lw[1] + 127) / 128, (p.lh[1] + 7) / 8, nb), dim3(32, 8), 0, s>>>(p);
+        if (nb >= 1) {                                      // levels 1 .. nb in one launch; level 0 is computed inside k_mb_final
+            const dim3 grid((p.lw[1] + 127) / 128, (p.lh[1] + 7) / 8, nb);
+            if (occ == 6) k_mb_band<6><<<grid, dim3(32, 8), 0, s>>>(p);
+            else if (occ == 5) k_mb_band<5><<<grid, dim3(32, 8), 0, s>>>(p);
+            else k_mb_band<4><<<grid, dim3(32, 8), 0, s>>>(p);
+        }
         for (int l = nb; l >= 2; l--)
             k_mb_collapse<<<dim3((p.lw[l - 1] + 127) / 128, (p.lh[l - 1] + 7) / 8), dim3(32, 8), 0, s>>>(p, l);
     }
-    k_mb_final<<<dim3((p.out_w + 127) / 128, (p.oy1 - p.oy0 + 7) / 8), dim3(32, 8), 0, s>>>(p);
+    {
+        const dim3 grid((p.out_w + 127) / 128, (p.oy1 - p.oy0 + 7) / 8);
+        if (occ == 6) k_mb_final<6><<<grid, dim3(32, 8), 0, s>>>(p);
+        else if (occ == 5) k_mb_final<5><<<grid, dim3(32, 8), 0, s>>>(p);
+        else k_mb_final<4><<<grid, dim3(32, 8), 0, s>>>(p);
+    }
 }
 
 int multiband_launches(const octvr_mapper& m) { return m.mb ? m.mb->launches : 0; }
@@ -869,7 +1021,7 @@ int multiband_launches(const octvr_mapper& m) { return m.mb ? m.mb->launches : 0
 void multiband_destroy(Multiband* mb)
 {
     if (!mb) return;
-    cudaFree(mb->d_chunks); cudaFree(mb->d_tile_cams); cudaFree(mb->d_coords); cudaFree(mb->d_g0); cudaFree(mb->d_g); cudaFree(mb->d_w); cudaFree(mb->d_dst); cudaFree(mb->d_dstw); cudaFree(mb->d_wide);
+    cudaFree(mb->d_chunks); cudaFree(mb->d_tile_cams); cudaFree(mb->d_wjobs); cudaFree(mb->d_wentries); cudaFree(mb->d_wtmaps); cudaFree(mb->d_coords); cudaFree(mb->d_g0); cudaFree(mb->d_g); cudaFree(mb->d_w); cudaFree(mb->d_dst); cudaFree(mb->d_dstw); cudaFree(mb->d_wide);
     delete mb;
 }
 
