@@ -39,6 +39,7 @@ struct MbCam {
 // RGBX plane; the tile is (tx, ty) in units of 32 x 16 pixels of the camera's bordered level-0 rectangle
 struct MbWarpJob { int bx0, by0; uint16_t bw, bh; uint16_t tmap, cam; uint16_t tx, ty; uint32_t pad[3]; };
 constexpr int MB_STAGE = 6144;       // shared-memory stage of the staged warp, pixels (24 KB)
+constexpr int MB_STAGE_SMALL = 3072; // tiles whose box fits 12 KB run as 128-thread CTAs, twice as many resident
 constexpr uint32_t MBW_VALID = 0x80000000u;   // entry: stage offset (13 bits) | fy << 13 | fx << 18 | valid
 
 struct MbParams {
@@ -74,7 +75,8 @@ struct MbParams {
 struct Multiband {
     MbParams p;
     uint2* d_chunks = nullptr; uint16_t* d_tile_cams = nullptr; unsigned n_chunks = 0;
-    MbWarpJob* d_wjobs = nullptr; uint32_t* d_wentries = nullptr; void* d_wtmaps = nullptr; unsigned n_wjobs = 0;   // staged warp (0: direct)
+    MbWarpJob* d_wjobs = nullptr; uint32_t* d_wentries = nullptr; void* d_wtmaps = nullptr;
+    unsigned n_wjobs = 0, n_wsmall = 0;                     // staged warp (0: direct); the first n_wsmall jobs have boxes <= MB_STAGE_SMALL
     uint2* d_coords = nullptr; uint32_t* d_g0 = nullptr; short4* d_g = nullptr; float* d_w = nullptr;
     short4* d_dst = nullptr; float* d_dstw = nullptr; int* d_wide = nullptr; bool force_wide = false;
     int max_bw = 0, max_bh = 0;
@@ -341,41 +343,49 @@ __device__ __forceinline__ void mbw_wait(uint64_t* mbar)
         "bra MBW_WAIT;\n\t"
         "MBW_DONE:\n\t}" ::"r"((uint32_t)__cvta_generic_to_shared(mbar)), "r"(0x989680u) : "memory");
 }
-__global__ void __launch_bounds__(256) k_mb_warp_staged(const __grid_constant__ MbParams p)
+// THREADS x (512 / THREADS) pixels per CTA, STAGE_PX pixels of stage: the kernel is bound by the latency of a tile (job
+// record -> box copy -> taps -> store) times the tiles in flight per SM, so tiles whose box fits 12 KB run as 128-thread CTAs
+// (16 resident per SM instead of 8); the few larger ones take the 256-thread / 24 KB variant.
+template <int THREADS, int STAGE_PX>
+__global__ void __launch_bounds__(THREADS) k_mb_warp_staged(const __grid_constant__ MbParams p, const unsigned first_job)
 {
-    __shared__ __align__(128) uint32_t s_buf[MB_STAGE];
+    __shared__ __align__(128) uint32_t s_buf[STAGE_PX];
     __shared__ __align__(8) uint64_t s_mbar;
-    if (blockIdx.x == 0 && threadIdx.x < MB_MAX_LEVELS && p.clear_wide) p.wide[threadIdx.x] = 0;   // new frame: every level narrow until proven wide
+    if (blockIdx.x == 0 && first_job == 0 && threadIdx.x < MB_MAX_LEVELS && p.clear_wide) p.wide[threadIdx.x] = 0;   // new frame: every level narrow until proven wide
+    constexpr int ROWS = THREADS / 32, PPT = TILE_H / ROWS;   // rows of the tile covered at once, pixels per thread
     const int tid = threadIdx.x, lx = tid & 31, ly = tid >> 5;
-    const MbWarpJob job = p.wjobs[blockIdx.x];
+    const unsigned j = first_job + blockIdx.x;
+    const MbWarpJob job = p.wjobs[j];
     if (tid == 0) mbw_mbar_init(&s_mbar);
     __syncthreads();
     if (tid == 0) mbw_tma_box(s_buf, (const char*)p.wtmaps + (size_t)job.tmap * 128, job.bx0, job.by0, (uint32_t)job.bw * job.bh * 4u, &s_mbar);
-    const uint32_t* ent = p.wentries + (size_t)blockIdx.x * TILE_PX + tid;
-    const uint32_t e0 = __ldcs(ent), e1 = __ldcs(ent + 256);
+    const uint32_t* ent = p.wentries + (size_t)j * TILE_PX + tid;
+    uint32_t e[PPT];
+    #pragma unroll
+    for (int h = 0; h < PPT; h++) e[h] = __ldcs(ent + h * THREADS);
     const int c = job.cam;
     const MbCam& cam = p.cam[c];
     const bool use_lut = p.use_gain && __ldg(p.gain_flag + c) != 0;
     const float g32 = p.use_gain ? __ldg(p.gain_f32 + c) : 1.f;
     const uint8_t* lut = p.gain_lut + c * 256;
     const int bw = job.bw;
+    uint32_t* __restrict__ g0 = p.g0 + cam.off_g[0];
     if (tid < 32) mbw_wait(&s_mbar);                        // one warp polls, the others park at the barrier
     __syncthreads();
     #pragma unroll
-    for (int h = 0; h < 2; h++) {
-        const uint32_t e = h ? e1 : e0;
-        const int x = job.tx * TILE_W + lx, y = job.ty * TILE_H + ly + 8 * h;
+    for (int h = 0; h < PPT; h++) {
+        const int x = job.tx * TILE_W + lx, y = job.ty * TILE_H + ly + ROWS * h;
         if (x >= cam.bw || y >= cam.bh) continue;
         uint32_t px = 0;
-        if (e & MBW_VALID) {
-            const uint32_t off = e & 0x1FFFu;
+        if (e[h] & MBW_VALID) {
+            const uint32_t off = e[h] & 0x1FFFu;
             int r, g, b;
-            bilerp_rgbx(s_buf[off], s_buf[off + 1], s_buf[off + bw], s_buf[off + bw + 1], (e >> 18) & 31u, (e >> 13) & 31u, r, g, b);
+            bilerp_rgbx(s_buf[off], s_buf[off + 1], s_buf[off + bw], s_buf[off + bw + 1], (e[h] >> 18) & 31u, (e[h] >> 13) & 31u, r, g, b);
             if (use_lut) { r = __ldg(lut + r); g = __ldg(lut + g); b = __ldg(lut + b); }
             else if (p.use_gain) { r = (int)gain_apply_f32((float)r, g32); g = (int)gain_apply_f32((float)g, g32); b = (int)gain_apply_f32((float)b, g32); }
             px = (uint32_t)r | ((uint32_t)g << 8) | ((uint32_t)b << 16);
         }
-        p.g0[cam.off_g[0] + (size_t)y * cam.bw + x] = px;
+        g0[(size_t)y * cam.bw + x] = px;
     }
 }
 
@@ -948,6 +958,22 @@ Multiband* multiband_create(octvr_mapper& m, const octvr_template& t,
         OB_CUDA(cudaMalloc(&dt, tmaps.size()));
         OB_CUDA(cudaMemcpy(dt, tmaps.data(), tmaps.size(), cudaMemcpyHostToDevice));
         mb->d_wtmaps = dt;
+        {   // small-box jobs first (stable), entries moved along
+            std::vector<uint32_t> order(wjobs.size());
+            for (size_t k = 0; k < order.size(); k++) order[k] = (uint32_t)k;
+            auto small = [&](uint32_t k) { return (int)wjobs[k].bw * wjobs[k].bh <= MB_STAGE_SMALL; };
+            std::stable_partition(order.begin(), order.end(), small);
+            std::vector<MbWarpJob> j2(wjobs.size());
+            std::vector<uint32_t> e2(wentries.size());
+            unsigned ns = 0;
+            for (size_t k = 0; k < order.size(); k++) {
+                j2[k] = wjobs[order[k]];
+                memcpy(e2.data() + k * TILE_PX, wentries.data() + (size_t)order[k] * TILE_PX, TILE_PX * sizeof(uint32_t));
+                ns += small(order[k]) ? 1u : 0u;
+            }
+            wjobs.swap(j2); wentries.swap(e2);
+            mb->n_wsmall = ns;
+        }
         mb->d_wjobs = upload(wjobs); mb->d_wentries = upload(wentries); mb->n_wjobs = (unsigned)wjobs.size();
         p.wjobs = mb->d_wjobs; p.wentries = mb->d_wentries; p.wtmaps = mb->d_wtmaps;
         coords.clear(); coords.shrink_to_fit();             // the 8-byte table is only read by the direct kernel
@@ -974,7 +1000,7 @@ Multiband* multiband_create(octvr_mapper& m, const octvr_template& t,
     p.coords = mb->d_coords; p.g0 = mb->d_g0; p.g = mb->d_g; p.w = mb->d_w; p.dst = mb->d_dst; p.dstw = mb->d_dstw;
     for (int i = 0; i < n; i++) { p.rgbx[i] = m.d_rgbx[i]; p.src_pitch[i] = m.in_w[i]; }
     m.table_bytes = (int64_t)(coords.size() * sizeof(uint2) + wentries.size() * 4 + wjobs.size() * sizeof(MbWarpJob) + wts.size() * 4 + dstw.size() * 4);
-    mb->launches = 1 + nb + (nb >= 1 ? 1 : 0) + std::max(0, nb - 1) + 1;
+    mb->launches = (mb->n_wjobs ? (mb->n_wsmall ? 1 : 0) + (mb->n_wjobs > mb->n_wsmall ? 1 : 0) : 1) + nb + (nb >= 1 ? 1 : 0) + std::max(0, nb - 1) + 1;
     return mb.release();
 }
 
@@ -991,8 +1017,10 @@ void multiband_stitch(octvr_mapper& m, const octvr_frame* out, cudaStream_t s)
     p.rgb_out = m.rgb_this_frame ? m.d_rgb : nullptr; p.rgb_pitch = (uint32_t)m.out_w * 3;
     const int nb = p.nb, n = p.n;
     static const int occ = [] { const char* e = getenv("OCTVR_MB_OCC"); return e ? atoi(e) : 4; }();   // resident CTAs / SM asked of band / final
-    if (mb.n_wjobs) k_mb_warp_staged<<<mb.n_wjobs, 256, 0, s>>>(p);
-    else if (mb.n_chunks) k_mb_warp<<<mb.n_chunks / MB_WARP_CHUNKS, 256, 0, s>>>(p);
+    if (mb.n_wjobs) {
+        if (mb.n_wsmall) k_mb_warp_staged<128, MB_STAGE_SMALL><<<mb.n_wsmall, 128, 0, s>>>(p, 0u);
+        if (mb.n_wjobs > mb.n_wsmall) k_mb_warp_staged<256, MB_STAGE><<<mb.n_wjobs - mb.n_wsmall, 256, 0, s>>>(p, mb.n_wsmall);
+    } else if (mb.n_chunks) k_mb_warp<<<mb.n_chunks / MB_WARP_CHUNKS, 256, 0, s>>>(p);
     if (p.lh[0] > 0 && mb.max_bh > 0) {                    // an empty row window (a band outside the result roi) only writes black
         for (int l = 0; l < nb; l++) {
             const dim3 grid(((mb.max_bw >> (l + 1)) + 31) / 32, ((mb.max_bh >> (l + 1)) + 31) / 32, n);
