@@ -2,36 +2,7 @@
 #pragma once
 #include "common.h"
 
-#include <cstdlib>
-
 namespace ob {
-
-// ------------------------------------------------------------------------------------------------
-// Programmatic dependent launch (sm_90+).  A kernel started with launch_pdl() may become resident while its predecessor
-// in the stream drains: pdl_wait() blocks until the predecessor grid has completed and its writes are visible (a no-op for
-// a normal launch), pdl_trigger() allows the successor to be scheduled once every CTA of this grid has called it or
-// exited.  Every kernel of a chain calls both first thing: by the time all CTAs of a grid have started, the slots that
-// free up would idle anyway, so the successor's CTAs take them and wait -- the launch latency between the kernels of a
-// frame (13 launches for a multiband frame) disappears from the critical path.  OCTVR_PDL=0 turns the attribute off.
-// ------------------------------------------------------------------------------------------------
-__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
-__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
-inline bool pdl_enabled()
-{
-    static const bool on = [] { const char* e = getenv("OCTVR_PDL"); return !(e && atoi(e) == 0); }();
-    return on;
-}
-template <class... KArgs, class... Args>
-inline void launch_pdl(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t s, Args&&... args)
-{
-    cudaLaunchConfig_t cfg = {};
-    cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = s;
-    cudaLaunchAttribute at[1];
-    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-    at[0].val.programmaticStreamSerializationAllowed = 1;
-    cfg.attrs = at; cfg.numAttrs = pdl_enabled() ? 1 : 0;
-    OB_CUDA(cudaLaunchKernelEx(&cfg, kern, static_cast<KArgs>(args)...));
-}
 
 // ------------------------------------------------------------------------------------------------
 // shared device helpers

@@ -475,7 +475,6 @@ __global__ void __launch_bounds__(256, 6) k_convert_gain(const __grid_constant__
                                                          const unsigned interleave)
 {
     extern __shared__ double s_dyn_nrm[];
-    pdl_trigger(); pdl_wait();          // the previous frame's blend still reads the RGBX planes and the gain tables
     const unsigned b = blockIdx.x;
     if (interleave) {
         if (b < 3u * gain_blocks) {
@@ -493,7 +492,7 @@ void launch_convert_gain(const ConvertParams& cp, const GainParams* gp, cudaStre
     const unsigned gb = gp ? (unsigned)gp->grid : 0u, cb = (unsigned)(cp.grid_x * cp.grid_y * cp.n);
     const size_t smem = gp ? (size_t)gp->n * GAIN_PX * sizeof(double) : 0;
     static const int mode = [] { const char* e = getenv("OCTVR_GAIN_INTERLEAVE"); return e ? atoi(e) : 1; }();   // diagnostic: 0 = gain CTAs first
-    launch_pdl(k_convert_gain, dim3(gb + cb), dim3(256), smem, s, cp, gp ? *gp : none, gb, (mode && gb > 0 && cb >= 2u * gb) ? 1u : 0u);
+    k_convert_gain<<<gb + cb, 256, smem, s>>>(cp, gp ? *gp : none, gb, (mode && gb > 0 && cb >= 2u * gb) ? 1u : 0u);
 }
 void launch_gain_finalize(const GainParams& p, cudaStream_t s) { k_gain_finalize<<<1, 256, 0, s>>>(p); }
 
@@ -686,15 +685,8 @@ __global__ void __launch_bounds__(256, 7) k_blend_staged(const __grid_constant__
     const int tid = threadIdx.x, lx = tid & 31, ly = tid >> 5;
     const int tile = (blockIdx.y + p.tile_y0) * p.tiles_x + blockIdx.x;
     const JobMeta* rec = p.jobs + (size_t)tile * MAX_CAMS;
-    pdl_trigger();
     const int nj = __ldg(&rec->grp_nj) & 0xFF;
     const uint32_t j0 = (uint32_t)__ldg(&rec->j0);
-    // static tables (tile record, first entries) are fetched before the dependency wait: with a programmatic launch this
-    // prologue runs while the conversion kernel drains; the gains and the RGBX planes are only touched after pdl_wait()
-    const uint2* ep = p.entries + (size_t)j0 * TILE_PX + tid;
-    uint2 e0 = make_uint2(0, 0), e1 = make_uint2(0, 0);
-    if (nj > 0) { e0 = __ldcs(ep); e1 = __ldcs(ep + 256); }
-    pdl_wait();
     if (tid < nj) {
         const JobMeta jm = rec[tid];
         s_job[tid] = jm;
@@ -707,6 +699,9 @@ __global__ void __launch_bounds__(256, 7) k_blend_staged(const __grid_constant__
 
     // sums of floor(v * W) <= 255 * MAX_CAMS < 2^16: R and G of a pixel share one accumulator, the two blue sums another
     uint32_t arg0 = 0, arg1 = 0, abb = 0;
+    const uint2* ep = p.entries + (size_t)j0 * TILE_PX + tid;
+    uint2 e0 = make_uint2(0, 0), e1 = make_uint2(0, 0);
+    if (nj > 0) { e0 = __ldcs(ep); e1 = __ldcs(ep + 256); }
     int k = 0;
     uint32_t phase = 0;
     while (k < nj) {                                        // one pass per job group (almost always a single group)
@@ -791,8 +786,8 @@ __global__ void __launch_bounds__(256, 7) k_blend_staged(const __grid_constant__
 
 void launch_blend_staged(const StagedParams& p, cudaStream_t s)
 {
-    if (p.use_gain) launch_pdl(k_blend_staged<1>, dim3(p.tiles_x, p.tiles_y_run), dim3(256), 0, s, p);
-    else launch_pdl(k_blend_staged<0>, dim3(p.tiles_x, p.tiles_y_run), dim3(256), 0, s, p);
+    if (p.use_gain) k_blend_staged<1><<<dim3(p.tiles_x, p.tiles_y_run), 256, 0, s>>>(p);
+    else k_blend_staged<0><<<dim3(p.tiles_x, p.tiles_y_run), 256, 0, s>>>(p);
 }
 
 void launch_blend(const BlendParams& p, cudaStream_t s)

@@ -273,7 +273,6 @@ constexpr int MB_WARP_CHUNKS = 4;
 // chunk index 0xFFFFFFFF), so the source plane, pitch and gain are CTA-uniform and stay out of the per-pixel code.
 __global__ void __launch_bounds__(256) k_mb_warp(const __grid_constant__ MbParams p)
 {
-    pdl_trigger(); pdl_wait();
     if (blockIdx.x == 0 && threadIdx.x < MB_MAX_LEVELS && p.clear_wide) p.wide[threadIdx.x] = 0;   // new frame: every level narrow until proven wide
     const uint2* list = p.warp_chunks + (size_t)blockIdx.x * MB_WARP_CHUNKS;
     const int c = (int)__ldg(&list[0].x);
@@ -350,7 +349,6 @@ __device__ __forceinline__ void mbw_wait(uint64_t* mbar)
 template <int THREADS, int STAGE_PX>
 __global__ void __launch_bounds__(THREADS) k_mb_warp_staged(const __grid_constant__ MbParams p, const unsigned first_job)
 {
-    pdl_trigger(); pdl_wait();
     __shared__ __align__(128) uint32_t s_buf[STAGE_PX];
     __shared__ __align__(8) uint64_t s_mbar;
     if (blockIdx.x == 0 && first_job == 0 && threadIdx.x < MB_MAX_LEVELS && p.clear_wide) p.wide[threadIdx.x] = 0;   // new frame: every level narrow until proven wide
@@ -562,7 +560,6 @@ __device__ __forceinline__ void mb_down_strip_u8(const uint32_t* __restrict__ sr
 
 template <bool L0> __global__ void __launch_bounds__(256) k_mb_down(const __grid_constant__ MbParams p, int l)
 {
-    pdl_trigger(); pdl_wait();
     const MbCam& cam = p.cam[blockIdx.z];
     const int sw = cam.bw >> l, sh = cam.bh >> l, dw = sw >> 1, dh = sh >> 1;
     const int x = blockIdx.x * 32 + threadIdx.x, y0 = (blockIdx.y * 8 + threadIdx.y) * 4;
@@ -576,7 +573,6 @@ template <bool L0> __global__ void __launch_bounds__(256) k_mb_down(const __grid
 //      latency-bound on their own (15 us each for a few thousand pixels), hide under level 1.
 template <int MINB> __global__ void __launch_bounds__(256, MINB) k_mb_band(const __grid_constant__ MbParams p)
 {
-    pdl_trigger(); pdl_wait();
     const int l = (int)blockIdx.z + 1;
     const int X0 = (blockIdx.x * 32 + threadIdx.x) * 4, Y = blockIdx.y * 8 + threadIdx.y;
     const int lw = p.lw[l], lh = p.lh[l];
@@ -638,7 +634,6 @@ template <int MINB> __global__ void __launch_bounds__(256, MINB) k_mb_band(const
 // ---- k_mb_collapse: dst_{l-1} = sat(pyrUp(dst_l) + dst_{l-1}), l >= 2; four pixels per thread ----
 __global__ void __launch_bounds__(256) k_mb_collapse(const __grid_constant__ MbParams p, int l)
 {
-    pdl_trigger(); pdl_wait();
     const int X0 = (blockIdx.x * 32 + threadIdx.x) * 4, Y = blockIdx.y * 8 + threadIdx.y;
     const int w = p.lw[l - 1], h = p.lh[l - 1];
     if (X0 >= w || Y >= h) return;
@@ -664,7 +659,6 @@ __global__ void __launch_bounds__(256) k_mb_collapse(const __grid_constant__ MbP
 //      black.  Saves the 8 B/px write + read of dst_0 and one launch. ----
 template <int MINB> __global__ void __launch_bounds__(256, MINB) k_mb_final(const __grid_constant__ MbParams p)
 {
-    pdl_trigger(); pdl_wait();
     const int X0 = (blockIdx.x * 32 + threadIdx.x) * 4, Y = p.oy0 + blockIdx.y * 8 + threadIdx.y;
     // cameras with a non-zero level-0 weight somewhere under this CTA (128 x 8 output pixels = up to 5 x 2 weight tiles)
     unsigned cams = 0;
@@ -1022,22 +1016,32 @@ void multiband_stitch(octvr_mapper& m, const octvr_frame* out, cudaStream_t s)
     }
     p.rgb_out = m.rgb_this_frame ? m.d_rgb : nullptr; p.rgb_pitch = (uint32_t)m.out_w * 3;
     const int nb = p.nb, n = p.n;
+    static const int occ = [] { const char* e = getenv("OCTVR_MB_OCC"); return e ? atoi(e) : 4; }();   // resident CTAs / SM asked of band / final
     if (mb.n_wjobs) {
-        if (mb.n_wsmall) launch_pdl(k_mb_warp_staged<128, MB_STAGE_SMALL>, dim3(mb.n_wsmall), dim3(128), 0, s, p, 0u);
-        if (mb.n_wjobs > mb.n_wsmall) launch_pdl(k_mb_warp_staged<256, MB_STAGE>, dim3(mb.n_wjobs - mb.n_wsmall), dim3(256), 0, s, p, mb.n_wsmall);
-    } else if (mb.n_chunks) launch_pdl(k_mb_warp, dim3(mb.n_chunks / MB_WARP_CHUNKS), dim3(256), 0, s, p);
+        if (mb.n_wsmall) k_mb_warp_staged<128, MB_STAGE_SMALL><<<mb.n_wsmall, 128, 0, s>>>(p, 0u);
+        if (mb.n_wjobs > mb.n_wsmall) k_mb_warp_staged<256, MB_STAGE><<<mb.n_wjobs - mb.n_wsmall, 256, 0, s>>>(p, mb.n_wsmall);
+    } else if (mb.n_chunks) k_mb_warp<<<mb.n_chunks / MB_WARP_CHUNKS, 256, 0, s>>>(p);
     if (p.lh[0] > 0 && mb.max_bh > 0) {                    // an empty row window (a band outside the result roi) only writes black
         for (int l = 0; l < nb; l++) {
             const dim3 grid(((mb.max_bw >> (l + 1)) + 31) / 32, ((mb.max_bh >> (l + 1)) + 31) / 32, n);
-            if (l == 0) launch_pdl(k_mb_down<true>, grid, dim3(32, 8), 0, s, p, l);
-            else launch_pdl(k_mb_down<false>, grid, dim3(32, 8), 0, s, p, l);
+            if (l == 0) k_mb_down<true><<<grid, dim3(32, 8), 0, s>>>(p, l);
+            else k_mb_down<false><<<grid, dim3(32, 8), 0, s>>>(p, l);
         }
-        if (nb >= 1)                                        // levels 1 .. nb in one launch; level 0 is computed inside k_mb_final
-            launch_pdl(k_mb_band<4>, dim3((p.lw[1] + 127) / 128, (p.lh[1] + 7) / 8, nb), dim3(32, 8), 0, s, p);
+        if (nb >= 1) {                                      // levels 1 .. nb in one launch; level 0 is computed inside k_mb_final
+            const dim3 grid((p.lw[1] + 127) / 128, (p.lh[1] + 7) / 8, nb);
+            if (occ == 6) k_mb_band<6><<<grid, dim3(32, 8), 0, s>>>(p);
+            else if (occ == 5) k_mb_band<5><<<grid, dim3(32, 8), 0, s>>>(p);
+            else k_mb_band<4><<<grid, dim3(32, 8), 0, s>>>(p);
+        }
         for (int l = nb; l >= 2; l--)
-            launch_pdl(k_mb_collapse, dim3((p.lw[l - 1] + 127) / 128, (p.lh[l - 1] + 7) / 8), dim3(32, 8), 0, s, p, l);
+            k_mb_collapse<<<dim3((p.lw[l - 1] + 127) / 128, (p.lh[l - 1] + 7) / 8), dim3(32, 8), 0, s>>>(p, l);
     }
-    launch_pdl(k_mb_final<4>, dim3((p.out_w + 127) / 128, (p.oy1 - p.oy0 + 7) / 8), dim3(32, 8), 0, s, p);
+    {
+        const dim3 grid((p.out_w + 127) / 128, (p.oy1 - p.oy0 + 7) / 8);
+        if (occ == 6) k_mb_final<6><<<grid, dim3(32, 8), 0, s>>>(p);
+        else if (occ == 5) k_mb_final<5><<<grid, dim3(32, 8), 0, s>>>(p);
+        else k_mb_final<4><<<grid, dim3(32, 8), 0, s>>>(p);
+    }
 }
 
 int multiband_launches(const octvr_mapper& m) { return m.mb ? m.mb->launches : 0; }
