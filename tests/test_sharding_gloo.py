@@ -41,8 +41,9 @@ WORKER = textwrap.dedent("""
     for a, b in shares[r]:
         out2[a:b] = r + 1
     vr.sharding.collect_shares(out2, shares, dst=0)
-    print(json.dumps({"rank": r, "mine": mine, "t": t, "counts": counts, "bands": bands, "bcast": got, "rows": out[:, 0].tolist(),
-                      "set": [int(views[1][0, 0]), int(views2[0][5, 7])], "rows2": out2[:, 0].tolist()}))
+    # one write() per rank (< PIPE_BUF): the two ranks share the pipe and print()'s separate newline write can interleave
+    os.write(1, (json.dumps({"rank": r, "mine": mine, "t": t, "counts": counts, "bands": bands, "bcast": got, "rows": out[:, 0].tolist(),
+                             "set": [int(views[1][0, 0]), int(views2[0][5, 7])], "rows2": out2[:, 0].tolist()}) + chr(10)).encode())
     dist.destroy_process_group()
 """) % ROOT
 
