@@ -5,13 +5,16 @@
 //
 // Static per mapper (init, host): per-camera bordered rectangles (gap 3*2^bands, aligned to 2^bands, BORDER_REFLECT
 // baked into the remap table), f32 weight Gaussian pyramids of the seam masks, summed band weights.
-// Per frame (device, all integer-exact):
-//   k_mb_warp      remap + gain of every camera into its bordered level-0 image (RGBX8888)
-//   k_mb_down      Gaussian pyramid level l -> l+1 per camera ([1 4 6 4 1]^2, (v+128)>>8, REFLECT_101), 16S
-//   k_mb_band      per destination level: sum over cameras of (short)((G_l - pyrUp(G_{l+1})) * W_l), then
-//                  (short)(sum / (sumW + 1e-5))  -- Laplacian, weighting, accumulation and normalisation fused
-//   k_mb_collapse  dst_{l-1} += pyrUp(dst_l) (saturating), levels >= 1
-//   k_mb_final     level-0 band computed in registers + pyrUp(dst_1), mask, 8-bit narrowing, RGB / YUV 4:2:0 store
+// Per frame (device, all integer-exact; 14 launches for 5 bands):
+//   k_mb_warp_staged  remap + gain of every camera into its bordered level-0 image (RGBX8888): one TMA box copy of the
+//                     source footprint per 32 x 16 tile, taps from shared memory (k_mb_warp: direct-gather fallback)
+//   k_mb_down         Gaussian pyramid level l -> l+1 per camera ([1 4 6 4 1]^2, (v+128)>>8, REFLECT_101), 16S storage,
+//                     packed 16-bit-lane arithmetic (camera levels stay within [0, 255])
+//   k_mb_band         ONE launch for the destination levels 1..bands: sum over cameras of (short)((G_l - pyrUp(G_{l+1})) *
+//                     W_l), then (short)(sum / (sumW + 1e-5)) -- Laplacian, weighting, accumulation, normalisation fused
+//   k_mb_collapse     dst_{l-1} += pyrUp(dst_l) (saturating), levels >= 1
+//   k_mb_final        level-0 band computed in registers + pyrUp(dst_1), mask, 8-bit narrowing, RGB / YUV 4:2:0 store
+// Row-band mappers (multi-GPU partition of one frame) keep a row window of every table and pyramid: see multiband_create.
 #include "mapper.h"
 #include "prep.h"
 #include "device_common.cuh"
@@ -93,36 +96,10 @@ __device__ __forceinline__ int refl101(int p, int len)
 __device__ __forceinline__ int sat16(int v) { return min(max(v, -32768), 32767); }
 __device__ __forceinline__ int3 ld3(const short4* s, int idx) { const short4 v = __ldg(s + idx); return make_int3(v.x, v.y, v.z); }
 __device__ __forceinline__ int3 ld3(const uint32_t* s, int idx) { const uint32_t v = __ldg(s + idx); return make_int3(v & 255u, (v >> 8) & 255u, (v >> 16) & 255u); }
-__device__ __forceinline__ int3 madd3(int3 a, int3 b, int k) { return make_int3(a.x + b.x * k, a.y + b.y * k, a.z + b.z * k); }
-
-// pyramids.cpp:967-1060 (pyrUp_, FixPtCast<short,6>): value of the 2x up-sampled image at (x, y)
-template <class T> __device__ int3 pyrup_at(const T* s, int sw, int sh, int x, int y)
-{
-    const int kx = x >> 1, ky = y >> 1;
-    auto hrow = [&](int r) -> int3 {
-        const T* row = s + r * sw;
-        if (sw == 1) { const int3 a = ld3(row, 0); return make_int3(a.x * 8, a.y * 8, a.z * 8); }
-        if ((x & 1) == 0) {
-            if (kx == 0) return madd3(madd3(make_int3(0, 0, 0), ld3(row, 0), 6), ld3(row, 1), 2);
-            if (kx == sw - 1) return madd3(madd3(make_int3(0, 0, 0), ld3(row, kx - 1), 1), ld3(row, kx), 7);
-            return madd3(madd3(madd3(make_int3(0, 0, 0), ld3(row, kx - 1), 1), ld3(row, kx), 6), ld3(row, kx + 1), 1);
-        }
-        if (kx == sw - 1) return madd3(make_int3(0, 0, 0), ld3(row, kx), 8);
-        return madd3(madd3(make_int3(0, 0, 0), ld3(row, kx), 4), ld3(row, kx + 1), 4);
-    };
-    const int rp = refl101(2 * (ky + 1), 2 * sh) >> 1;
-    int3 v;
-    if ((y & 1) == 0) {
-        const int rm = refl101(2 * (ky - 1), 2 * sh) >> 1;
-        v = madd3(madd3(madd3(make_int3(0, 0, 0), hrow(rm), 1), hrow(ky), 6), hrow(rp), 1);
-    } else
-        v = madd3(madd3(make_int3(0, 0, 0), hrow(ky), 4), hrow(rp), 4);
-    return make_int3(sat16((v.x + 32) >> 6), sat16((v.y + 32) >> 6), sat16((v.z + 32) >> 6));
-}
 
 // ---- pyrUp of FOUR horizontally adjacent pixels by one thread ----
 // pyrUp_ (pyramids.cpp:967-1060) is a separable [1 6 1 | 4 4] filter whose border cases are index extensions: -1 maps to
-// 1 (0 for a single sample) and len maps to len - 1 -- exactly the special cases of pyrup_at above.  Four neighbours share
+// 1 (0 for a single sample) and len maps to len - 1 -- the border cases of the reference written out.  Four neighbours share
 // their source samples: 12 loads and a third of the arithmetic instead of 4 x 9 loads.  x0 may be even or odd.
 __device__ __forceinline__ int up_idx(int k, int len) { return k < 0 ? (len > 1 ? 1 : 0) : (k >= len ? len - 1 : k); }
 __device__ __forceinline__ int3 add3(int3 a, int3 b) { return make_int3(a.x + b.x, a.y + b.y, a.z + b.z); }
@@ -390,60 +367,15 @@ __global__ void __launch_bounds__(THREADS) k_mb_warp_staged(const __grid_constan
 }
 
 // ---- k_mb_down: level l -> l+1 for every camera.  grid (ceil(w/32), ceil(h/8), cameras) at level l+1 ----
-template <class T> __device__ __forceinline__ int3 pyrdown_at(const T* s, int sw, int sh, int x, int y)
-{
-    int xi[5], yi[5];
-    #pragma unroll
-    for (int k = 0; k < 5; k++) { xi[k] = refl101(2 * x + k - 2, sw); yi[k] = refl101(2 * y + k - 2, sh); }
-    const int kw[5] = { 1, 4, 6, 4, 1 };
-    int3 acc = make_int3(0, 0, 0);
-    #pragma unroll
-    for (int dy = 0; dy < 5; dy++) {
-        int3 row = make_int3(0, 0, 0);
-        #pragma unroll
-        for (int dx = 0; dx < 5; dx++) row = madd3(row, ld3(s, yi[dy] * sw + xi[dx]), kw[dx]);
-        acc = madd3(acc, row, kw[dy]);
-    }
-    return make_int3(sat16((acc.x + 128) >> 8), sat16((acc.y + 128) >> 8), sat16((acc.z + 128) >> 8));
-}
-
 // Column-strip version: a thread produces FOUR vertically adjacent pixels of level l+1.  It walks the 11 source rows they
 // depend on, forms the five-tap horizontal sum of each row once and scatters it (x 1, 4, 6, 4, 1) into the outputs that use
 // the row -- 55 loads for four outputs instead of 100, no shared memory, no barrier.  Integer arithmetic, so the separable
-// order gives the same numbers as the 5 x 5 form of pyrdown_at (pyramids.cpp:849-964).  Threads of a warp walk adjacent
+// order gives the same numbers as the 5 x 5 form of pyramids.cpp:849-964.  Threads of a warp walk adjacent
 // columns, so every load instruction is a contiguous (stride-2) row segment.
-template <class T> __device__ __forceinline__ void mb_down_strip(const T* __restrict__ src, short4* __restrict__ dst, int sw, int sh, int dw, int dh, int x, int y0)
-{
-    int xi[5];
-    #pragma unroll
-    for (int k = 0; k < 5; k++) xi[k] = refl101(2 * x + k - 2, sw);
-    int acc[4][3];
-    #pragma unroll
-    for (int j = 0; j < 4; j++) acc[j][0] = acc[j][1] = acc[j][2] = 0;
-    const bool inner_rows = 2 * y0 - 2 >= 0 && 2 * y0 + 8 < sh;       // no row reflection for any of the 11 rows
-    #pragma unroll
-    for (int r = 0; r < 11; r++) {
-        if (r >= 5 && y0 + (r - 3) / 2 >= dh) break;                  // rows only the missing outputs of a ragged strip would use
-        const T* row = src + (size_t)(inner_rows ? 2 * y0 - 2 + r : refl101(2 * y0 - 2 + r, sh)) * sw;
-        const int3 a = ld3(row, xi[0]), b = ld3(row, xi[1]), c = ld3(row, xi[2]), d = ld3(row, xi[3]), e = ld3(row, xi[4]);
-        const int hx = a.x + e.x + 4 * (b.x + d.x) + 6 * c.x, hy = a.y + e.y + 4 * (b.y + d.y) + 6 * c.y, hz = a.z + e.z + 4 * (b.z + d.z) + 6 * c.z;
-        #pragma unroll
-        for (int j = 0; j < 4; j++) {
-            const int t = r - 2 * j;                                  // tap of output j that reads this row
-            if (t < 0 || t > 4) continue;
-            const int kw = t == 2 ? 6 : (t == 1 || t == 3) ? 4 : 1;
-            acc[j][0] += kw * hx; acc[j][1] += kw * hy; acc[j][2] += kw * hz;
-        }
-    }
-    #pragma unroll
-    for (int j = 0; j < 4; j++)
-        if (y0 + j < dh)
-            dst[(size_t)(y0 + j) * dw + x] = make_short4((short)sat16((acc[j][0] + 128) >> 8), (short)sat16((acc[j][1] + 128) >> 8), (short)sat16((acc[j][2] + 128) >> 8), 0);
-}
-
+//
 // Levels >= 1 of a CAMERA pyramid: values within [0, 255] stored as short4 {R, G, B, 0}, so the words {R | G << 16, B} are
 // filtered as packed 16-bit lanes (5 x 5 sum <= 256 * 255 < 2^16) with 16-byte loads in the interior, rows fetched in
-// groups ahead of their use and no early exit (see mb_down_strip_u8).  The same integers as mb_down_strip<short4>.
+// groups ahead of their use and no early exit (see mb_down_strip_u8).  The same integers as the 5 x 5 form.
 __device__ __forceinline__ void mb_down_strip_p16(const short4* __restrict__ src, short4* __restrict__ dst, int sw, int sh, int dw, int dh, int x, int y0)
 {
     const bool interior = 2 * x - 2 >= 0 && 2 * x + 2 < sw;
@@ -497,7 +429,7 @@ __device__ __forceinline__ void mb_down_strip_p16(const short4* __restrict__ src
 // come from two 8-byte loads and one 4-byte load (interior columns), their bytes are transposed per channel with seven
 // PRMTs, the [1 4 6 4 | 1] row sums are two IDP.4A per channel (IMAD pipe), and R, B then travel as two 16-bit lanes: the
 // full 5 x 5 sum is at most 256 * 255 < 2^16, so no lane carries and ((sum + 128) >> 8) <= 255 needs no saturation.  The
-// same integers as mb_down_strip<uint32_t>.
+// same integers as the 5 x 5 form.
 __device__ __forceinline__ void mb_down_strip_u8(const uint32_t* __restrict__ src, short4* __restrict__ dst, int sw, int sh, int dw, int dh, int x, int y0)
 {
     const bool interior = 2 * x - 2 >= 0 && 2 * x + 2 < sw;           // no column reflection, 8-byte aligned pairs (sw is even)
@@ -571,7 +503,7 @@ template <bool L0> __global__ void __launch_bounds__(256) k_mb_down(const __grid
 // ---- k_mb_band: one thread per FOUR horizontally adjacent pixels of destination level l (CTA = 128 x 8 pixels) ----
 //      Levels do not depend on each other, so one launch covers all of them (blockIdx.z + 1 = level): the small levels,
 //      latency-bound on their own (15 us each for a few thousand pixels), hide under level 1.
-template <int MINB> __global__ void __launch_bounds__(256, MINB) k_mb_band(const __grid_constant__ MbParams p)
+__global__ void __launch_bounds__(256, 4) k_mb_band(const __grid_constant__ MbParams p)
 {
     const int l = (int)blockIdx.z + 1;
     const int X0 = (blockIdx.x * 32 + threadIdx.x) * 4, Y = blockIdx.y * 8 + threadIdx.y;
@@ -657,7 +589,7 @@ __global__ void __launch_bounds__(256) k_mb_collapse(const __grid_constant__ MbP
 //      band (k_mb_band with l = 0: Laplacian, weighting, accumulation over the cameras, normalisation), adds pyrUp(dst_1)
 //      (the last collapse step), masks, narrows to 8 bit and stores RGB / YUV 4:2:0.  Pixels outside the result roi are
 //      black.  Saves the 8 B/px write + read of dst_0 and one launch. ----
-template <int MINB> __global__ void __launch_bounds__(256, MINB) k_mb_final(const __grid_constant__ MbParams p)
+__global__ void __launch_bounds__(256, 4) k_mb_final(const __grid_constant__ MbParams p)
 {
     const int X0 = (blockIdx.x * 32 + threadIdx.x) * 4, Y = p.oy0 + blockIdx.y * 8 + threadIdx.y;
     // cameras with a non-zero level-0 weight somewhere under this CTA (128 x 8 output pixels = up to 5 x 2 weight tiles)
@@ -1016,7 +948,6 @@ void multiband_stitch(octvr_mapper& m, const octvr_frame* out, cudaStream_t s)
     }
     p.rgb_out = m.rgb_this_frame ? m.d_rgb : nullptr; p.rgb_pitch = (uint32_t)m.out_w * 3;
     const int nb = p.nb, n = p.n;
-    static const int occ = [] { const char* e = getenv("OCTVR_MB_OCC"); return e ? atoi(e) : 4; }();   // resident CTAs / SM asked of band / final
     if (mb.n_wjobs) {
         if (mb.n_wsmall) k_mb_warp_staged<128, MB_STAGE_SMALL><<<mb.n_wsmall, 128, 0, s>>>(p, 0u);
         if (mb.n_wjobs > mb.n_wsmall) k_mb_warp_staged<256, MB_STAGE><<<mb.n_wjobs - mb.n_wsmall, 256, 0, s>>>(p, mb.n_wsmall);
@@ -1027,21 +958,12 @@ void multiband_stitch(octvr_mapper& m, const octvr_frame* out, cudaStream_t s)
             if (l == 0) k_mb_down<true><<<grid, dim3(32, 8), 0, s>>>(p, l);
             else k_mb_down<false><<<grid, dim3(32, 8), 0, s>>>(p, l);
         }
-        if (nb >= 1) {                                      // levels 1 .. nb in one launch; level 0 is computed inside k_mb_final
-            const dim3 grid((p.lw[1] + 127) / 128, (p.lh[1] + 7) / 8, nb);
-            if (occ == 6) k_mb_band<6><<<grid, dim3(32, 8), 0, s>>>(p);
-            else if (occ == 5) k_mb_band<5><<<grid, dim3(32, 8), 0, s>>>(p);
-            else k_mb_band<4><<<grid, dim3(32, 8), 0, s>>>(p);
-        }
+        if (nb >= 1)                                        // levels 1 .. nb in one launch; level 0 is computed inside k_mb_final
+            k_mb_band<<<dim3((p.lw[1] + 127) / 128, (p.lh[1] + 7) / 8, nb), dim3(32, 8), 0, s>>>(p);
         for (int l = nb; l >= 2; l--)
             k_mb_collapse<<<dim3((p.lw[l - 1] + 127) / 128, (p.lh[l - 1] + 7) / 8), dim3(32, 8), 0, s>>>(p, l);
     }
-    {
-        const dim3 grid((p.out_w + 127) / 128, (p.oy1 - p.oy0 + 7) / 8);
-        if (occ == 6) k_mb_final<6><<<grid, dim3(32, 8), 0, s>>>(p);
-        else if (occ == 5) k_mb_final<5><<<grid, dim3(32, 8), 0, s>>>(p);
-        else k_mb_final<4><<<grid, dim3(32, 8), 0, s>>>(p);
-    }
+    k_mb_final<<<dim3((p.out_w + 127) / 128, (p.oy1 - p.oy0 + 7) / 8), dim3(32, 8), 0, s>>>(p);
 }
 
 int multiband_launches(const octvr_mapper& m) { return m.mb ? m.mb->launches : 0; }
