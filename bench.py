@@ -464,12 +464,15 @@ def run_stereo(args):
                 views[c].copy_(torch.from_numpy(np.concatenate([y, np.concatenate([u, v], 1)], 0)))
         ring.append(views)
         flats.append(flat)
-    out = torch.zeros((H * 3 // 2, W), dtype=torch.uint8, device="cuda")
-    pipe = vr.sharding.FramePipeline(st, src=0)
+    outs = [torch.zeros((H * 3 // 2, W), dtype=torch.uint8, device="cuda") for _ in range(2)]
+    out = outs[0]
+    pipe = vr.sharding.FramePipeline(st, src=0, defer_collect=os.environ.get("OCTVR_DEFER_COLLECT", "1") != "0")
 
     def step(k, last=False):
-        if world > 1:      # broadcast of step k + 1 runs under the stitch of step k; bands go to rank 0 point to point
-            pipe.step(flats[k % RING], ring[k % RING], out, next_flat=None if last else flats[(k + 1) % RING])
+        if world > 1:      # broadcast of step k + 1 and band collection of step k - 1 run under the stitch of step k
+            pipe.step(flats[k % RING], ring[k % RING], outs[k % 2], next_flat=None if last else flats[(k + 1) % RING])
+            if last:
+                pipe.flush()
         else:
             st.stitch_local(ring[k % RING], out)
 
@@ -521,7 +524,7 @@ def run_stereo(args):
         ref = torch.zeros_like(out)
         one.stitch_local(ring[(args.steps - 1) % RING], ref)
         torch.cuda.synchronize()
-        verified = bool(torch.equal(ref, out))
+        verified = bool(torch.equal(ref, outs[(args.steps - 1) % 2]))
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()

@@ -81,12 +81,14 @@ def band_slices(out, width, height, y0, y1, row0=0):
     return out[row0 + y0:row0 + y1], out[height + (row0 + y0) // 2:height + (row0 + y1) // 2]
 
 
-def collect_shares(out, shares, dst=0):
+def collect_shares(out, shares, dst=0, wait=True):
     """Row-band mode: `shares[r]` = list of (row_a, row_b) ranges of `out` (a packed frame tensor, rows are contiguous)
     that rank r produced.  Every rank sends its ranges to `dst` point to point (batched isend / irecv: NCCL send/recv over
-    NVLink on the GPU box); only the bands move, nothing is summed and `out` needs no zero fill."""
+    NVLink on the GPU box); only the bands move, nothing is summed and `out` needs no zero fill.
+    wait=False returns the work handles instead of waiting: the transfer then runs under whatever is enqueued next (the
+    caller must not touch `out` before waiting on them)."""
     if not (dist.is_initialized() and dist.get_world_size() > 1):
-        return out
+        return out if wait else []
     rank = dist.get_rank()
     ops = []
     for r, ranges in enumerate(shares):
@@ -99,9 +101,11 @@ def collect_shares(out, shares, dst=0):
                 ops.append(dist.P2POp(dist.isend, out[a:b], dst))
             elif rank == dst:
                 ops.append(dist.P2POp(dist.irecv, out[a:b], r))
-    if ops:
-        for w in dist.batch_isend_irecv(ops):
-            w.wait()
+    works = dist.batch_isend_irecv(ops) if ops else []
+    if not wait:
+        return works
+    for w in works:
+        w.wait()
     return out
 
 
@@ -200,11 +204,18 @@ class StereoRowBandStitcher:
 
 
 class FramePipeline:
-    """Row-band exchange with the input broadcast of time step k + 1 overlapped with the stitch of step k (SURVEY.md 8e:
-    "overlap with previous frame").  stitcher: RowBandStitcher or StereoRowBandStitcher."""
+    """Row-band exchange overlapped with the stitch ("overlap with previous frame"): the input broadcast of
+    time step k + 1 runs under the stitch of step k, and -- with defer_collect -- so does the band collection of step k - 1.
+    stitcher: RowBandStitcher or StereoRowBandStitcher.  With defer_collect the caller alternates between (at least) two
+    output buffers: a buffer is being read by its collection until the step after next begins (or flush() returns)."""
 
-    def __init__(self, stitcher, src=0):
-        self.st, self.src, self.pending = stitcher, src, {}
+    def __init__(self, stitcher, src=0, defer_collect=False):
+        self.st, self.src, self.pending, self.defer = stitcher, src, {}, defer_collect
+        self.collecting = {}                            # output buffer -> work handles of its band collection
+
+    def _wait_collect(self, out):
+        for w in self.collecting.pop(out.data_ptr(), []):
+            w.wait()
 
     def step(self, flat, frames, out, next_flat=None, collect=True):
         key = flat.data_ptr()
@@ -215,10 +226,20 @@ class FramePipeline:
             w.wait()                                   # the compute stream waits for the broadcast, the host does not
         if next_flat is not None:
             self.pending[next_flat.data_ptr()] = broadcast_frames(next_flat, self.src, async_op=True)
+        self._wait_collect(out)                        # an earlier frame may still be leaving this buffer
         if hasattr(self.st, "stitch_local"):
             self.st.stitch_local(frames, out)
         else:
             self.st.mapper.stitch_packed(frames, out)
         if collect:
-            collect_shares(out, self.st.shares(), self.src)
+            if self.defer:
+                self.collecting[out.data_ptr()] = collect_shares(out, self.st.shares(), self.src, wait=False)
+            else:
+                collect_shares(out, self.st.shares(), self.src)
         return out
+
+    def flush(self):
+        """Wait (on the current stream) for every band collection still in flight."""
+        for key in list(self.collecting):
+            for w in self.collecting.pop(key):
+                w.wait()

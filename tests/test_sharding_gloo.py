@@ -41,9 +41,29 @@ WORKER = textwrap.dedent("""
     for a, b in shares[r]:
         out2[a:b] = r + 1
     vr.sharding.collect_shares(out2, shares, dst=0)
+    # FramePipeline with deferred band collection: three time steps through two output buffers
+    class Fake:
+        def shares(self):
+            return shares
+        def stitch_local(self, frames, o):
+            for a, b in shares[r]:
+                o[a:b] = int(frames[0][0, 0]) + r            # depends on the (broadcast) frame and on the rank
+    sets = [vr.sharding.alloc_frame_set([(8, 4)], "cpu") for _ in range(3)]
+    if r == 0:
+        for k, (fl, _) in enumerate(sets):
+            fl.fill_(10 * (k + 1))
+    pipe = vr.sharding.FramePipeline(Fake(), src=0, defer_collect=True)
+    bufs = [torch.zeros((96, 4), dtype=torch.uint8) for _ in range(2)]
+    seen = []
+    for k in range(3):
+        pipe.step(sets[k][0], sets[k][1], bufs[k & 1], next_flat=sets[k + 1][0] if k < 2 else None)
+        if k >= 1:                                            # frame k - 1 is complete once its buffer is flushed / reused
+            pass
+    pipe.flush()
+    seen = [bufs[0][:, 0].tolist(), bufs[1][:, 0].tolist()]   # buffer 0 holds frame 2, buffer 1 frame 1
     # one write() per rank (< PIPE_BUF): the two ranks share the pipe and print()'s separate newline write can interleave
     os.write(1, (json.dumps({"rank": r, "mine": mine, "t": t, "counts": counts, "bands": bands, "bcast": got, "rows": out[:, 0].tolist(),
-                             "set": [int(views[1][0, 0]), int(views2[0][5, 7])], "rows2": out2[:, 0].tolist()}) + chr(10)).encode())
+                             "set": [int(views[1][0, 0]), int(views2[0][5, 7])], "rows2": out2[:, 0].tolist(), "pipe": seen}) + chr(10)).encode())
     dist.destroy_process_group()
 """) % ROOT
 
@@ -68,6 +88,9 @@ def test_two_rank_gloo_sharding(tmp_path):
     assert rows[0]["rows"] == [1] * 32 + [2] * 32                                 # the bands assembled on rank 0
     assert rows[0]["set"] == rows[1]["set"] == [7, 9]
     assert rows[0]["rows2"] == [1] * 32 + [2] * 32 + [1] * 16 + [2] * 16          # luma and chroma bands, point to point
+    # deferred collection: rank 0 ends with frame 2 (value 30) in buffer 0 and frame 1 (value 20) in buffer 1, both ranks' bands
+    assert rows[0]["pipe"][0] == [30] * 32 + [31] * 32 + [30] * 16 + [31] * 16
+    assert rows[0]["pipe"][1] == [20] * 32 + [21] * 32 + [20] * 16 + [21] * 16
 
 
 def test_row_bands_alignment():
