@@ -466,10 +466,10 @@ def run_stereo(args):
         flats.append(flat)
     outs = [torch.zeros((H * 3 // 2, W), dtype=torch.uint8, device="cuda") for _ in range(2)]
     out = outs[0]
-    pipe = vr.sharding.FramePipeline(st, src=0, defer_collect=os.environ.get("OCTVR_DEFER_COLLECT", "1") != "0")
+    pipe = vr.sharding.FramePipeline(st, src=0, defer_collect=os.environ.get("OCTVR_DEFER_COLLECT", "0") != "0")
 
     def step(k, last=False):
-        if world > 1:      # broadcast of step k + 1 and band collection of step k - 1 run under the stitch of step k
+        if world > 1:      # broadcast of step k + 1 runs under the stitch of step k (OCTVR_DEFER_COLLECT=1: the band collection of step k - 1 too)
             pipe.step(flats[k % RING], ring[k % RING], outs[k % 2], next_flat=None if last else flats[(k + 1) % RING])
             if last:
                 pipe.flush()
