@@ -343,26 +343,47 @@ __global__ void __launch_bounds__(THREADS) k_mb_warp_staged(const __grid_constan
     const int c = job.cam;
     const MbCam& cam = p.cam[c];
     const bool use_lut = p.use_gain && __ldg(p.gain_flag + c) != 0;
-    const float g32 = p.use_gain ? __ldg(p.gain_f32 + c) : 1.f;
+    const float g32 = p.use_gain ? __ldg(p.gain_f32 + c) : 1.f, gb = gain_bias_f32(g32);
     const uint8_t* lut = p.gain_lut + c * 256;
-    const int bw = job.bw;
-    uint32_t* __restrict__ g0 = p.g0 + cam.off_g[0];
+    const uint8_t* s0 = reinterpret_cast<const uint8_t*>(s_buf);
+    const uint8_t* s1 = s0 + job.bw * 4;
+    // whole tiles (all but the right / bottom edge of a rectangle) skip the per-pixel bounds checks
+    const int x = job.tx * TILE_W + lx, yb = job.ty * TILE_H + ly;
+    const bool whole = (job.tx + 1) * TILE_W <= cam.bw && (job.ty + 1) * TILE_H <= cam.bh;
+    uint32_t* __restrict__ orow = p.g0 + cam.off_g[0] + (size_t)yb * cam.bw + x;
+    const size_t ostep = (size_t)ROWS * cam.bw;
     if (tid < 32) mbw_wait(&s_mbar);                        // one warp polls, the others park at the barrier
     __syncthreads();
     #pragma unroll
-    for (int h = 0; h < PPT; h++) {
-        const int x = job.tx * TILE_W + lx, y = job.ty * TILE_H + ly + ROWS * h;
-        if (x >= cam.bw || y >= cam.bh) continue;
-        uint32_t px = 0;
-        if (e[h] & MBW_VALID) {
-            const uint32_t off = e[h] & 0x1FFFu;
-            int r, g, b;
-            bilerp_rgbx(s_buf[off], s_buf[off + 1], s_buf[off + bw], s_buf[off + bw + 1], (e[h] >> 18) & 31u, (e[h] >> 13) & 31u, r, g, b);
-            if (use_lut) { r = __ldg(lut + r); g = __ldg(lut + g); b = __ldg(lut + b); }
-            else if (p.use_gain) { r = (int)gain_apply_f32((float)r, g32); g = (int)gain_apply_f32((float)g, g32); b = (int)gain_apply_f32((float)b, g32); }
-            px = (uint32_t)r | ((uint32_t)g << 8) | ((uint32_t)b << 16);
+    for (int h = 0; h < PPT; h++, orow += ostep) {
+        if (!whole && (x >= cam.bw || yb + ROWS * h >= cam.bh)) continue;
+        // the gather of device_common.cuh (fused_pair) without the blend weight: IDP.2A bilinear with the +512 rounding term,
+        // floor(x / 1024) by a round-down fma that leaves 2^23 + v in the register, gain on that biased value.  An invalid
+        // entry reads the start of the stage and is masked at the end: no divergence inside the tile.
+        const uint32_t off = (e[h] & 0x1FFFu) << 2;
+        const uint32_t t00 = *reinterpret_cast<const uint32_t*>(s0 + off), t01 = *reinterpret_cast<const uint32_t*>(s0 + off + 4);
+        const uint32_t t10 = *reinterpret_cast<const uint32_t*>(s1 + off), t11 = *reinterpret_cast<const uint32_t*>(s1 + off + 4);
+        const uint32_t fx = (e[h] >> 18) & 31u, fy = (e[h] >> 13) & 31u;
+        const uint32_t wx = fx * 65535u + 32u;                 // (32-fx) | fx << 16
+        const uint32_t wb = wx * fy, wt = wx * 32u - wb;
+        const uint32_t rg0 = __byte_perm(t00, t01, 0x5140), bb0 = __byte_perm(t00, t01, 0x6262);
+        const uint32_t rg1 = __byte_perm(t10, t11, 0x5140), bb1 = __byte_perm(t10, t11, 0x6262);
+        const uint32_t r = __dp2a_lo(wb, rg1, __dp2a_lo(wt, rg0, 512u));
+        const uint32_t g = __dp2a_hi(wb, rg1, __dp2a_hi(wt, rg0, 512u));
+        const uint32_t b = __dp2a_lo(wb, bb1, __dp2a_lo(wt, bb0, 512u));
+        const float rf = __fmaf_rd(__uint2float_rn(r), 0.0009765625f, MAGIC_RD);   // bits = 0x4B000000 + floor(r / 1024)
+        const float gf = __fmaf_rd(__uint2float_rn(g), 0.0009765625f, MAGIC_RD);
+        const float bf = __fmaf_rd(__uint2float_rn(b), 0.0009765625f, MAGIC_RD);
+        uint32_t R = __float_as_uint(rf) & 255u, G = __float_as_uint(gf) & 255u, B = __float_as_uint(bf) & 255u;
+        if (use_lut) { R = __ldg(lut + R); G = __ldg(lut + G); B = __ldg(lut + B); }
+        else if (p.use_gain) {
+            // fma(2^23 + v, g, MAGIC_RN - 2^23 g) = MAGIC_RN + rint(v g) (gain_apply_biased): the integer sits in the mantissa
+            R = min(__float_as_uint(__fmaf_rn(rf, g32, gb)) - 0x4B400000u, 255u);
+            G = min(__float_as_uint(__fmaf_rn(gf, g32, gb)) - 0x4B400000u, 255u);
+            B = min(__float_as_uint(__fmaf_rn(bf, g32, gb)) - 0x4B400000u, 255u);
         }
-        g0[(size_t)y * cam.bw + x] = px;
+        const uint32_t px = R | (G << 8) | (B << 16);
+        *orow = (e[h] & MBW_VALID) ? px : 0u;
     }
 }
 
