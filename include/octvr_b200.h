@@ -102,7 +102,9 @@ octvr_status octvr_mapper_create(const octvr_template* t, const int* in_sizes_wh
 /* Row-band mapper for the multi-GPU partition of ONE large frame (no counterpart in the reference, which
  * runs a frame on one GPU): like octvr_mapper_create, but the mapper only holds the tables of, and only writes, output
  * rows [band_y0, band_y1) (multiples of 32, or the frame height).  The frames passed to stitch are still full size; every
- * rank reads all inputs (an NCCL broadcast in sharding.py) and computes the same gains.  Feather / no-blend only. */
+ * rank reads all inputs (an NCCL broadcast in sharding.py) and computes the same gains.  Multiband mappers keep a halo of
+ * 4 * 2^bands rows of every pyramid around the band, so the band's rows equal the full-frame result bit for bit.  Not
+ * available together with overlays or scale_output. */
 octvr_status octvr_mapper_create_band(const octvr_template* t, const int* in_sizes_wh, int n_in,
                                       int blend, int enable_gain, int band_y0, int band_y1,
                                       int device, octvr_mapper** out);
