@@ -241,7 +241,7 @@ def run_ours(args):
         "gpu_launches": st["launches_per_stitch"] * args.steps,
         "clocks": clocks, "e2e": e2e,
     }
-    if not args.no_cpu:
+    if not args.no_cpu and world == 1:      # the CPU baseline is timed on rank 0 at N = 1 only
         line["cpu_baseline"] = cpu_baseline(args.workload, budget_s=20.0)
     print(json.dumps(line))
 
