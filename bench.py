@@ -670,7 +670,8 @@ def main():
     ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS))
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
-    ap.add_argument("--concurrency", type=int, default=2, help="c5: CUDA streams (and Mappers) a rank serves its video streams on")
+    ap.add_argument("--concurrency", type=int, default=1, help="c5: CUDA streams (and Mappers) a rank serves its video streams on "
+                    "(measured on B200: 2-4 are 5 %% slower per frame than 1)")
     ap.add_argument("--verify", action="store_true", help="c4, N > 1: rank 0 also stitches the last frame whole and compares")
     ap.add_argument("--rowband", action="store_true", help="N > 1: all ranks stitch ONE stream, split by output row bands "
                     "(NCCL broadcast of the inputs + band collection inside the timed region; strong scaling)")
