@@ -134,6 +134,10 @@ octvr_status octvr_mapper_stats(const octvr_mapper* m, int64_t* pairs, int64_t* 
 octvr_status octvr_mapper_set_profiling(octvr_mapper* m, int on);
 /* %globaltimer stamps (ns) of the gain kernel's last CTA: start, ticket, reduced, solved, done (diagnostics). */
 octvr_status octvr_mapper_debug_gain_ns(octvr_mapper* m, unsigned long long* out5);
+/* Diagnostics / tests (host only, no device): the library's restatement of cv::fillPoly(img, {pts}, val) -- one contour,
+ * 8UC1, lineType 8 (imgproc/src/drawing.cpp:1195-1404) -- that draws the camera masks of a JSON config
+ * (octvr/src/camera.cpp:96-167).  pts_xy = {x0, y0, x1, y1, ...}. */
+octvr_status octvr_debug_fill_poly(uint8_t* h_img, int w, int h, const int* pts_xy, int npts, int val);
 octvr_status octvr_mapper_stage_ms(octvr_mapper* m, const char* stage, float* ms);
 void         octvr_mapper_destroy(octvr_mapper* m);
 

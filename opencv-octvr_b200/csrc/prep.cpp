@@ -315,4 +315,156 @@ void quantise_map(const Img<float>& map1, const Img<float>& map2, int src_w, int
     });
 }
 
+
+// ------------------------------------------------------------------------------------------------
+// fill_poly_u8: cv::fillPoly restated (drawing.cpp).  XY_SHIFT = 16.
+// ------------------------------------------------------------------------------------------------
+namespace {
+// cv::clipLine(Size, pt1, pt2), drawing.cpp:80-136
+bool clip_line(int w, int h, int& ax, int& ay, int& bx, int& by)
+{
+    if (w <= 0 || h <= 0) return false;
+    const int64_t right = w - 1, bottom = h - 1;
+    int64_t x1 = ax, y1 = ay, x2 = bx, y2 = by;
+    int c1 = (x1 < 0) + (x1 > right) * 2 + (y1 < 0) * 4 + (y1 > bottom) * 8;
+    int c2 = (x2 < 0) + (x2 > right) * 2 + (y2 < 0) * 4 + (y2 > bottom) * 8;
+    if ((c1 & c2) == 0 && (c1 | c2) != 0) {
+        int64_t a;
+        if (c1 & 12) { a = c1 < 8 ? 0 : bottom; x1 += (a - y1) * (x2 - x1) / (y2 - y1); y1 = a; c1 = (x1 < 0) + (x1 > right) * 2; }
+        if (c2 & 12) { a = c2 < 8 ? 0 : bottom; x2 += (a - y2) * (x2 - x1) / (y2 - y1); y2 = a; c2 = (x2 < 0) + (x2 > right) * 2; }
+        if ((c1 & c2) == 0 && (c1 | c2) != 0) {
+            if (c1) { a = c1 == 1 ? 0 : right; y1 += (a - x1) * (y2 - y1) / (x2 - x1); x1 = a; c1 = 0; }
+            if (c2) { a = c2 == 1 ? 0 : right; y2 += (a - x2) * (y2 - y1) / (x2 - x1); x2 = a; c2 = 0; }
+        }
+        ax = (int)x1; ay = (int)y1; bx = (int)x2; by = (int)y2;
+    }
+    return (c1 | c2) == 0;
+}
+// Line(img, pt1, pt2, color, 8) = cv::LineIterator(img, pt1, pt2, 8, left_to_right = true), drawing.cpp:142-236, 238-265:
+// a Bresenham walk along the major axis, drawn from the left end point
+void line8(uint8_t* img, int w, int h, int ax, int ay, int bx, int by, uint8_t val)
+{
+    if ((unsigned)ax >= (unsigned)w || (unsigned)bx >= (unsigned)w || (unsigned)ay >= (unsigned)h || (unsigned)by >= (unsigned)h)
+        if (!clip_line(w, h, ax, ay, bx, by)) return;
+    int dx = bx - ax, dy = by - ay;
+    if (dx < 0) { dx = -dx; dy = -dy; ax = bx; ay = by; }          // left to right
+    int x = ax, y = ay;
+    const int ystep = dy < 0 ? -1 : 1;
+    if (dy < 0) dy = -dy;
+    const bool steep = dy > dx;                                     // major axis = y: the roles of the two steps swap
+    const int major = steep ? dy : dx, minor = steep ? dx : dy;
+    int err = major - 2 * minor;
+    for (int i = 0; i <= major; i++) {
+        img[(size_t)y * w + x] = val;
+        const bool diag = err < 0;                                  // step along the minor axis as well
+        err += -2 * minor + (diag ? 2 * major : 0);
+        if (steep) { y += ystep; if (diag) x += 1; }
+        else { x += 1; if (diag) y += ystep; }
+    }
+}
+struct Edge { int y0, y1, x, dx; Edge* next; };
+}  // namespace
+
+void fill_poly_u8(uint8_t* img, int w, int h, const int* pts, int npts, uint8_t val)
+{
+    if (npts <= 0) return;
+    const int SH = 16, ONE = 1 << SH;
+    std::vector<Edge> edges;
+    edges.reserve((size_t)npts + 1);
+    // CollectPolyEdges, drawing.cpp:1195-1248 (shift = 0, no offset): outline + one table entry per non-horizontal edge
+    int px = pts[2 * (npts - 1)] << SH, py = pts[2 * (npts - 1) + 1];
+    for (int i = 0; i < npts; i++) {
+        const int qx = pts[2 * i] << SH, qy = pts[2 * i + 1];
+        line8(img, w, h, (px + (ONE >> 1)) >> SH, py, (qx + (ONE >> 1)) >> SH, qy, val);
+        if (py != qy) {
+            Edge e;
+            if (py < qy) { e.y0 = py; e.y1 = qy; e.x = px; } else { e.y0 = qy; e.y1 = py; e.x = qx; }
+            e.dx = (qx - px) / (qy - py);
+            e.next = nullptr;
+            edges.push_back(e);
+        }
+        px = qx; py = qy;
+    }
+    // FillEdgeCollection, drawing.cpp:1261-1404
+    const int total = (int)edges.size();
+    if (total < 2) return;
+    int y_max = INT_MIN, x_max = INT_MIN, y_min = INT_MAX, x_min = INT_MAX;
+    for (const Edge& e : edges) {
+        const int x1 = e.x + (e.y1 - e.y0) * e.dx;
+        y_min = std::min(y_min, e.y0); y_max = std::max(y_max, e.y1);
+        x_min = std::min(x_min, std::min(e.x, x1)); x_max = std::max(x_max, std::max(e.x, x1));
+    }
+    if (y_max < 0 || y_min >= h || x_max < 0 || x_min >= (w << SH)) return;
+    std::sort(edges.begin(), edges.end(), [](const Edge& a, const Edge& b) {
+        return a.y0 - b.y0 ? a.y0 < b.y0 : a.x - b.x ? a.x < b.x : a.dx < b.dx;
+    });
+    Edge head;                                   // list head of the active edges; also the sentinel appended to the table
+    head.y0 = INT_MAX; head.y1 = 0; head.x = 0; head.dx = 0; head.next = nullptr;
+    edges.push_back(head);                       // no insertion after this point: pointers into the vector stay valid
+    int i = 0;
+    Edge* e = &edges[0];
+    y_max = std::min(y_max, h);
+    for (int y = e->y0; y < y_max; y++) {
+        Edge *last, *prelast, *keep_prelast;
+        int sort_flag = 0, draw = 0;
+        const bool clipline = y < 0;
+        prelast = &head;
+        last = head.next;
+        while (last || e->y0 == y) {
+            if (last && last->y1 == y) {         // the edge ends on this row: drop it
+                prelast->next = last->next;
+                last = last->next;
+                continue;
+            }
+            keep_prelast = prelast;
+            if (last && (e->y0 > y || last->x < e->x)) {     // next edge of the active list
+                prelast = last;
+                last = last->next;
+            } else if (i < total) {              // an edge starts on this row: insert it
+                prelast->next = e;
+                e->next = last;
+                prelast = e;
+                e = &edges[++i];
+            } else
+                break;
+            if (draw) {
+                if (!clipline) {
+                    int x1 = keep_prelast->x, x2 = prelast->x;
+                    if (x1 > x2) std::swap(x1, x2);
+                    x1 = (x1 + ONE - 1) >> SH;
+                    x2 = x2 >> SH;
+                    if (x1 < w && x2 >= 0) {
+                        if (x1 < 0) x1 = 0;
+                        if (x2 >= w) x2 = w - 1;
+                        for (int x = x1; x <= x2; x++) img[(size_t)y * w + x] = val;
+                    }
+                }
+                keep_prelast->x += keep_prelast->dx;
+                prelast->x += prelast->dx;
+            }
+            draw ^= 1;
+        }
+        // keep the active list ordered by x (bubble sort, as in the reference: the order decides which spans pair up)
+        keep_prelast = nullptr;
+        do {
+            prelast = &head;
+            last = head.next;
+            while (last != keep_prelast && last->next != nullptr) {
+                Edge* te = last->next;
+                if (last->x > te->x) {
+                    prelast->next = te;
+                    last->next = te->next;
+                    te->next = last;
+                    prelast = te;
+                    sort_flag = 1;
+                } else {
+                    prelast = last;
+                    last = te;
+                }
+            }
+            keep_prelast = prelast;
+        } while (sort_flag && keep_prelast != head.next && keep_prelast != &head);
+    }
+}
+
 }  // namespace ob

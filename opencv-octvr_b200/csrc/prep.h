@@ -14,6 +14,11 @@ Img<float> resize_linear(const Img<float>& src, int dw, int dh);
 // per destination index: source offset (x: clamped to [0, src-1]; y: unclamped, imgwarp.cpp:3404-3447) and the two
 // 11-bit coefficients {round((1-f)*2048), round(f*2048)} of the 8-bit INTER_LINEAR path
 void resize_linear_tables(int src, int dst, bool clamp_ofs, std::vector<int>& ofs, std::vector<short>& coef);
+// cv::fillPoly(img, {pts}, val) for one contour on an 8UC1 image, lineType 8, shift 0 (imgproc/src/drawing.cpp:1195-1404:
+// outline by 8-connected lines through cv::LineIterator + cv::clipLine :80-236, interior by the 16.16 fixed-point scan-line
+// edge table).  Camera::Camera draws the `selection` rectangle and the polygonal exclude / include masks with it
+// (octvr/src/camera.cpp:96-167).
+void fill_poly_u8(uint8_t* img, int w, int h, const int* pts_xy, int npts, uint8_t val);
 // cv::pyrDown for 32FC1 (pyramids.cpp:849-964 incl. the SSE association of :143-185)
 Img<float> pyrdown_f32(const Img<float>& src);
 

@@ -200,6 +200,14 @@ octvr_status octvr_template_add_overlay(octvr_template* t, const int* roi, const
     });
 }
 
+octvr_status octvr_debug_fill_poly(uint8_t* img, int w, int h, const int* pts, int npts, int val)
+{
+    return guard([&] {
+        OB_CHECK(img && pts && w > 0 && h > 0 && npts >= 0, "bad argument");
+        fill_poly_u8(img, w, h, pts, npts, (uint8_t)val);
+    });
+}
+
 octvr_status octvr_template_create_masks(octvr_template* t)
 {
     return guard([&] { OB_CHECK(t, "null argument"); t->seam_masks = distance_seam_masks(t->inputs, t->out_w); });

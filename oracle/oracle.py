@@ -267,10 +267,16 @@ CAM_TYPES = {"normal": 0, "perspective": 1, "pinhole": 2, "fisheye": 3, "equirec
              "eqareanorthpole": 9, "eqareasouthpole": 10}
 
 
-def _fill_poly(mask, pts, val):
-    """cv::fillPoly restated via cv2 when available (mask drawing is init-time JSON plumbing)."""
-    import cv2
-    cv2.fillPoly(mask, [np.array(pts, np.int32).reshape(-1, 2)], int(val))
+def fill_poly(mask, pts, val):
+    """cv::fillPoly(mask, {pts}, val) in place (orc_fill_poly: drawing.cpp restated; pinned by tests/golden/fillpoly.npz).
+    cv2 4.x is NOT equivalent: it differs from the reference on every edge that is clipped by the image."""
+    assert mask.dtype == np.uint8 and mask.ndim == 2 and mask.strides[1] == 1
+    p = np.ascontiguousarray(np.array(pts, np.int32).reshape(-1))
+    lib().orc_fill_poly(_p(mask), C.c_ssize_t(mask.strides[0]), mask.shape[1], mask.shape[0], _p(p), len(p) // 2, int(val))
+    return mask
+
+
+_fill_poly = fill_poly
 
 
 def make_camera(typ, opts):

@@ -136,6 +136,9 @@ void orc_vignette_map(const float abcd[4], int width, int height, float* out);
 int orc_num_threads(void);
 void orc_set_num_threads(int n);
 
+/* cv::fillPoly, one contour, 8UC1, lineType 8 (drawing.cpp:80-265,1195-1404); pts = {x0,y0,x1,y1,...} */
+void orc_fill_poly(uint8_t* img, ptrdiff_t step, int w, int h, const int* pts, int npts, int val);
+
 #ifdef __cplusplus
 }
 #endif

@@ -314,3 +314,136 @@ void orc_dist_l2_3x3(const uint8_t* mask, ptrdiff_t mask_step, int w, int h,
     }
     free(temp);
 }
+
+
+/* ------------------------------------------------------------------------------------------------
+ * cv::fillPoly(img, {pts}, val): one contour, 8UC1, lineType 8, shift 0 (imgproc/src/drawing.cpp).
+ *   outline : CollectPolyEdges :1195-1248 -> Line :238-265 -> LineIterator :142-236 (8-connected, left to
+ *             right) after clipLine :80-136
+ *   interior: FillEdgeCollection :1261-1404, 16.16 fixed-point edge table, active list kept sorted by x
+ * Camera::Camera draws the selection rectangle and the polygonal exclude / include masks with it
+ * (modules/octvr/src/camera.cpp:96-167).  Pinned by tests/golden/fillpoly.npz (reference build).
+ * ------------------------------------------------------------------------------------------------ */
+static int orc_clip_line(int w, int h, int* ax, int* ay, int* bx, int* by)
+{
+    long long right = w - 1, bottom = h - 1, x1 = *ax, y1 = *ay, x2 = *bx, y2 = *by, a;
+    int c1, c2;
+    if (w <= 0 || h <= 0) return 0;
+    c1 = (x1 < 0) + (x1 > right) * 2 + (y1 < 0) * 4 + (y1 > bottom) * 8;
+    c2 = (x2 < 0) + (x2 > right) * 2 + (y2 < 0) * 4 + (y2 > bottom) * 8;
+    if ((c1 & c2) == 0 && (c1 | c2) != 0) {
+        if (c1 & 12) { a = c1 < 8 ? 0 : bottom; x1 += (a - y1) * (x2 - x1) / (y2 - y1); y1 = a; c1 = (x1 < 0) + (x1 > right) * 2; }
+        if (c2 & 12) { a = c2 < 8 ? 0 : bottom; x2 += (a - y2) * (x2 - x1) / (y2 - y1); y2 = a; c2 = (x2 < 0) + (x2 > right) * 2; }
+        if ((c1 & c2) == 0 && (c1 | c2) != 0) {
+            if (c1) { a = c1 == 1 ? 0 : right; y1 += (a - x1) * (y2 - y1) / (x2 - x1); x1 = a; c1 = 0; }
+            if (c2) { a = c2 == 1 ? 0 : right; y2 += (a - x2) * (y2 - y1) / (x2 - x1); x2 = a; c2 = 0; }
+        }
+        *ax = (int)x1; *ay = (int)y1; *bx = (int)x2; *by = (int)y2;
+    }
+    return (c1 | c2) == 0;
+}
+
+static void orc_line8(uint8_t* img, ptrdiff_t step, int w, int h, int ax, int ay, int bx, int by, uint8_t val)
+{
+    int dx, dy, sy, steep, major, minor, err, i, x, y;
+    if ((unsigned)ax >= (unsigned)w || (unsigned)bx >= (unsigned)w || (unsigned)ay >= (unsigned)h || (unsigned)by >= (unsigned)h)
+        if (!orc_clip_line(w, h, &ax, &ay, &bx, &by)) return;
+    dx = bx - ax; dy = by - ay;
+    if (dx < 0) { dx = -dx; dy = -dy; ax = bx; ay = by; }
+    sy = dy < 0 ? -1 : 1;
+    if (dy < 0) dy = -dy;
+    steep = dy > dx;
+    major = steep ? dy : dx; minor = steep ? dx : dy;
+    err = major - 2 * minor;
+    x = ax; y = ay;
+    for (i = 0; i <= major; i++) {
+        int both = err < 0;
+        img[(ptrdiff_t)y * step + x] = val;
+        err += -2 * minor + (both ? 2 * major : 0);
+        if (steep) { y += sy; x += both; } else { x += 1; if (both) y += sy; }
+    }
+}
+
+typedef struct OrcEdge { int y0, y1, x, dx; struct OrcEdge* next; } OrcEdge;
+static int orc_edge_cmp(const void* pa, const void* pb)
+{
+    const OrcEdge* a = (const OrcEdge*)pa; const OrcEdge* b = (const OrcEdge*)pb;
+    if (a->y0 != b->y0) return a->y0 < b->y0 ? -1 : 1;
+    if (a->x != b->x) return a->x < b->x ? -1 : 1;
+    if (a->dx != b->dx) return a->dx < b->dx ? -1 : 1;
+    return 0;
+}
+
+void orc_fill_poly(uint8_t* img, ptrdiff_t step, int w, int h, const int* pts, int npts, int val)
+{
+    OrcEdge* ed; OrcEdge head; OrcEdge* e;
+    int total = 0, i, y, px, py, y_max = INT_MIN, x_max = INT_MIN, y_min = INT_MAX, x_min = INT_MAX;
+    if (npts <= 0) return;
+    ed = (OrcEdge*)malloc(sizeof(OrcEdge) * ((size_t)npts + 1));
+    px = pts[2 * (npts - 1)] << 16; py = pts[2 * (npts - 1) + 1];
+    for (i = 0; i < npts; i++) {
+        int qx = pts[2 * i] << 16, qy = pts[2 * i + 1];
+        orc_line8(img, step, w, h, (px + 32768) >> 16, py, (qx + 32768) >> 16, qy, (uint8_t)val);
+        if (py != qy) {
+            OrcEdge* n = &ed[total++];
+            if (py < qy) { n->y0 = py; n->y1 = qy; n->x = px; } else { n->y0 = qy; n->y1 = py; n->x = qx; }
+            n->dx = (qx - px) / (qy - py);
+            n->next = 0;
+        }
+        px = qx; py = qy;
+    }
+    if (total < 2) { free(ed); return; }
+    for (i = 0; i < total; i++) {
+        int x1 = ed[i].x + (ed[i].y1 - ed[i].y0) * ed[i].dx;
+        if (ed[i].y0 < y_min) y_min = ed[i].y0;
+        if (ed[i].y1 > y_max) y_max = ed[i].y1;
+        if (ed[i].x < x_min) x_min = ed[i].x;
+        if (ed[i].x > x_max) x_max = ed[i].x;
+        if (x1 < x_min) x_min = x1;
+        if (x1 > x_max) x_max = x1;
+    }
+    if (y_max < 0 || y_min >= h || x_max < 0 || x_min >= (w << 16)) { free(ed); return; }
+    /* std::sort with CmpEdges is not stable, but elements that compare equal are identical edges */
+    qsort(ed, (size_t)total, sizeof(OrcEdge), orc_edge_cmp);
+    head.y0 = INT_MAX; head.y1 = 0; head.x = 0; head.dx = 0; head.next = 0;
+    ed[total] = head;
+    i = 0; e = &ed[0];
+    if (y_max > h) y_max = h;
+    for (y = e->y0; y < y_max; y++) {
+        OrcEdge *last = head.next, *prelast = &head, *keep;
+        int sorted_something = 0, draw = 0, clip = y < 0;
+        while (last || e->y0 == y) {
+            if (last && last->y1 == y) { prelast->next = last->next; last = last->next; continue; }
+            keep = prelast;
+            if (last && (e->y0 > y || last->x < e->x)) { prelast = last; last = last->next; }
+            else if (i < total) { prelast->next = e; e->next = last; prelast = e; e = &ed[++i]; }
+            else break;
+            if (draw) {
+                if (!clip) {
+                    int x1 = keep->x, x2 = prelast->x, x;
+                    if (x1 > x2) { int t = x1; x1 = x2; x2 = t; }
+                    x1 = (x1 + 65535) >> 16; x2 >>= 16;
+                    if (x1 < w && x2 >= 0) {
+                        if (x1 < 0) x1 = 0;
+                        if (x2 >= w) x2 = w - 1;
+                        for (x = x1; x <= x2; x++) img[(ptrdiff_t)y * step + x] = (uint8_t)val;
+                    }
+                }
+                keep->x += keep->dx;
+                prelast->x += prelast->dx;
+            }
+            draw ^= 1;
+        }
+        keep = 0;
+        do {
+            prelast = &head; last = head.next;
+            while (last != keep && last->next != 0) {
+                OrcEdge* te = last->next;
+                if (last->x > te->x) { prelast->next = te; last->next = te->next; te->next = last; prelast = te; sorted_something = 1; }
+                else { prelast = last; last = te; }
+            }
+            keep = prelast;
+        } while (sorted_something && keep != head.next && keep != &head);
+    }
+    free(ed);
+}

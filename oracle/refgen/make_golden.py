@@ -98,6 +98,31 @@ def main():
         np.savez_compressed(os.path.join(GOLD, "primitives.npz"), **read_container(gbin))
         print("primitives ok")
 
+    if not only or "fillpoly" in only:      # cv::fillPoly of the reference build on 310 polygons (camera masks)
+        rng = np.random.default_rng(11)
+        cases = [((64, 48), [(10, 10), (50, 12), (40, 40), (8, 30)]), ((64, 48), [(5, 5), (60, 5), (60, 40), (32, 15), (5, 40)]),
+                 ((64, 48), [(5, 5), (60, 40), (60, 5), (5, 40)]), ((64, 48), [(30, 20), (30, 20), (30, 20)]), ((64, 48), [(3, 7), (50, 7)]),
+                 ((64, 48), [(-20, -10), (90, 5), (70, 70), (-5, 40)]), ((64, 48), [(100, 100), (120, 100), (110, 130)]),
+                 ((320, 240), [(30, 20), (30, 219), (289, 219), (289, 20)]), ((320, 240), [(10, 10), (150, 30), (120, 200), (20, 180)]),
+                 ((320, 240), [(200, 60), (300, 80), (280, 200), (210, 170)])]
+        for _ in range(300):
+            w, h = int(rng.integers(8, 200)), int(rng.integers(8, 150))
+            n = int(rng.integers(1, 9))
+            cases.append(((w, h), [(int(rng.integers(-w // 2, w + w // 2)), int(rng.integers(-h // 2, h + h // 2))) for _ in range(n)]))
+        txt = os.path.join(TMP, "fillpoly_cases.txt")
+        with open(txt, "w") as f:
+            for (w, h), pts in cases:
+                f.write("%d %d %d %s\n" % (w, h, len(pts), " ".join("%d %d" % p for p in pts)))
+        fbin = os.path.join(TMP, "fillpoly.bin")
+        subprocess.check_call([compile_tool("ref_fillpoly"), txt, fbin])
+        c = read_container(fbin)
+        arrs = {"n": np.array(len(cases))}
+        for k, ((w, h), pts) in enumerate(cases):
+            arrs["p%d" % k] = np.array([w, h] + [v for p in pts for v in p], np.int32)
+            arrs["m%d" % k] = np.packbits(c["m%d" % k] == 200)
+        np.savez_compressed(os.path.join(GOLD, "fillpoly.npz"), **arrs)
+        print("fillpoly", len(cases))
+
     st = compile_tool("ref_stitch")
     cases = [  # name, rig, in_w, in_h, blend, gain, kind
         ("rig3_feather5_gain_noise", "rig3", 320, 240, -5, 1, "noise"),

@@ -78,3 +78,22 @@ def test_from_arrays_validates_shapes():
     bad[0]["roi"] = (0, 0, 4096, 64)
     with pytest.raises(vr.OctvrError):
         vr.MapperTemplate.from_arrays(size, bad, seams)
+
+
+def test_fill_poly_matches_the_reference_build():
+    """The host restatement of cv::fillPoly that draws the camera masks of a JSON config (selection rectangles, polygonal
+    exclude / include masks; octvr/src/camera.cpp:96-167) against masks drawn by the reference build itself
+    (tests/golden/fillpoly.npz, oracle/refgen/ref_fillpoly.cpp): convex, concave, self-intersecting, degenerate and partly /
+    fully off-image polygons.  (cv2 4.13 is not a usable oracle here: it differs from the reference on every clipped edge.)"""
+    L = vr.lib()
+    g = np.load(os.path.join(util.GOLD, "fillpoly.npz"))
+    n = int(g["n"])
+    assert n >= 300
+    for k in range(n):
+        p = g["p%d" % k]
+        w, h = int(p[0]), int(p[1])
+        pts = np.ascontiguousarray(p[2:])
+        want = np.unpackbits(g["m%d" % k])[:w * h].reshape(h, w).astype(bool)
+        got = np.full((h, w), 7, np.uint8)
+        assert L.octvr_debug_fill_poly(got.ctypes.data_as(C.c_void_p), w, h, pts.ctypes.data_as(C.c_void_p), len(pts) // 2, 200) == 0
+        assert np.array_equal(got == 200, want) and set(np.unique(got)) <= {7, 200}, (k, w, h, pts.tolist())

@@ -235,3 +235,14 @@ def test_after_blend_stages_bit_exact(case):
     assert np.array_equal(y, ry) and np.array_equal(u, ru) and np.array_equal(v, rv)
     if pw:
         assert np.array_equal(so.last_preview, g["preview_rgb"])
+
+
+def test_fill_poly_bit_exact():
+    """cv::fillPoly of the reference build (310 polygons incl. clipped, concave, degenerate; oracle/refgen/ref_fillpoly.cpp)."""
+    g = np.load(os.path.join(GOLD, "fillpoly.npz"))
+    for k in range(int(g["n"])):
+        p = g["p%d" % k]
+        w, h = int(p[0]), int(p[1])
+        want = np.unpackbits(g["m%d" % k])[:w * h].reshape(h, w).astype(bool)
+        got = O.fill_poly(np.full((h, w), 7, np.uint8), p[2:].reshape(-1, 2), 200)
+        assert np.array_equal(got == 200, want), (k, p.tolist())
