@@ -2,6 +2,7 @@
 // Follows vr::Camera::Camera (modules/octvr/src/camera.cpp:49-135) and the per-model constructors
 // (src/cameras/*.cpp|hpp); all set-up arithmetic is f64 like the reference.
 #include "camera.h"
+#include "prep.h"
 #include <cmath>
 #include <cstring>
 
@@ -83,15 +84,6 @@ CamType type_of(const std::string& t)
     return CAM_INVALID;
 }
 
-// inclusive axis-aligned rectangle, clipped (what cv::fillPoly draws for camera.cpp:100-112's four corners)
-void fill_rect(std::vector<uint8_t>& m, int w, int h, int x0, int y0, int x1, int y1, uint8_t v)
-{
-    if (x0 > x1) std::swap(x0, x1);
-    if (y0 > y1) std::swap(y0, y1);
-    for (int y = std::max(0, y0); y <= std::min(h - 1, y1); y++)
-        for (int x = std::max(0, x0); x <= std::min(w - 1, x1); x++) m[(size_t)y * w + x] = v;
-}
-
 }  // namespace
 
 CamHost camera_from_json(const std::string& type, const Json& o)
@@ -118,16 +110,45 @@ CamHost camera_from_json(const std::string& type, const Json& o)
         for (int k = 0; k < 9; k++) m.rot[k] = o.at("rotation_matrix").at(k).number();
     inv3(m.rot, m.rot_inv);
 
-    if (o.has("selection")) {                                          // camera.cpp:97-113
+    // exclude / include masks in the input image's pixel grid (octvr/src/camera.cpp:72-123,146-187), drawn with the
+    // reference's cv::fillPoly (prep.cpp fill_poly_u8)
+    auto prepare = [&](std::vector<uint8_t>& mk, uint8_t initial, int& mw, int& mh) {
         const int w = o.at("width").integer(), h = o.at("height").integer();
-        ch.exclude.assign((size_t)w * h, 255);
+        OB_CHECK(w > 0 && h > 0, "mask: width / height");
+        if (mk.empty()) { mk.assign((size_t)w * h, initial); mw = w; mh = h; }
+        else OB_CHECK(mw == w && mh == h, "mask size != width x height");
+    };
+    auto draw = [&](const Json& masks, std::vector<uint8_t>& target, int mw, int mh) {
+        for (size_t k = 0; k < masks.size(); k++) {
+            const Json& area = masks.at(k);
+            const std::string kind = area.at("type").string();
+            if (kind == "polygonal") {
+                const Json& a = area.at("args");
+                std::vector<int> pts;
+                for (size_t q = 0; q + 1 < a.size(); q += 2) { pts.push_back((int)a.at(q).number()); pts.push_back((int)a.at(q + 1).number()); }
+                fill_poly_u8(target.data(), mw, mh, pts.data(), (int)pts.size() / 2, 255);
+            } else if (kind == "png")
+                fail(OCTVR_ERR_UNSUPPORTED, "png exclude / include masks are not implemented (they need an image decoder)");
+            else
+                fail(OCTVR_ERR_FORMAT, "unknown mask type \"" + kind + "\"");
+        }
+    };
+    if (o.has("selection")) {                                          // camera.cpp:96-112: exclude everything but the rectangle
+        prepare(ch.exclude, 255, m.ex_w, m.ex_h);
         const Json& s = o.at("selection");
         const int left = s.at(0).integer(), right = s.at(1).integer(), top = s.at(2).integer(), bottom = s.at(3).integer();
-        fill_rect(ch.exclude, w, h, left, top, right - 1, bottom - 1, 0);
-        m.ex_w = w; m.ex_h = h;
+        const int pts[8] = { left, top, left, bottom - 1, right - 1, bottom - 1, right - 1, top };
+        fill_poly_u8(ch.exclude.data(), m.ex_w, m.ex_h, pts, 4, 0);
     }
-    if (o.has("exclude_masks") || o.has("include_masks"))
-        fail(OCTVR_ERR_UNSUPPORTED, "polygonal / png exclude_masks and include_masks are not implemented yet");
+    if (o.has("exclude_masks")) {                                      // camera.cpp:114-118 (PTGui)
+        prepare(ch.exclude, 0, m.ex_w, m.ex_h);
+        prepare(ch.include, 0, m.in_w, m.in_h);
+        draw(o.at("exclude_masks"), ch.exclude, m.ex_w, m.ex_h);
+    }
+    if (o.has("include_masks")) {                                      // camera.cpp:120-123 (Hugin)
+        prepare(ch.include, 0, m.in_w, m.in_h);
+        draw(o.at("include_masks"), ch.include, m.in_w, m.in_h);
+    }
     if (o.has("longitude_selection")) {
         m.min_lon = o.at("longitude_selection").at(0).number();
         m.max_lon = o.at("longitude_selection").at(1).number();

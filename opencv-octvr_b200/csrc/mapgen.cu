@@ -239,6 +239,7 @@ struct MapgenParams {
     int W, H;
     float* map1; float* map2; uint8_t* mask;
     const uint8_t* visible;      // W*H or null: pixels already claimed by an earlier include mask (template.cpp:86)
+    uint8_t* vis;                // W*H or null: Camera::get_include_mask of this input (camera.cpp:255-293)
     int* bbox;                   // min_w, min_h, max_w, max_h
 };
 
@@ -266,6 +267,17 @@ __global__ void __launch_bounds__(256) k_mapgen(const __grid_constant__ MapgenPa
             if (pt.x >= 0 && pt.x < 1 && pt.y >= 0 && pt.y < 1 && p.in.exclude_mask) {
                 const int ex = (int)(pt.x * p.in.ex_w), ey = (int)(pt.y * p.in.ex_h);
                 if (p.in.exclude_mask[(size_t)ey * p.in.ex_w + ex]) pt = nan2();
+            }
+            if (p.vis) {
+                // get_include_mask re-projects WITHOUT the longitude test, guards on the exclude mask being present and
+                // indexes the include mask with the exclude mask's size (camera.cpp:275-289) -- reproduced as is
+                const D2 pv = model_fwd(p.in, lli);
+                uint8_t v = 0;
+                if (pv.x >= 0 && pv.x < 1 && pv.y >= 0 && pv.y < 1 && p.in.exclude_mask) {
+                    const int ex = (int)(pv.x * p.in.ex_w), ey = (int)(pv.y * p.in.ex_h);
+                    if (p.in.include_mask[(size_t)ey * p.in.in_w + ex]) v = 1;
+                }
+                p.vis[idx] = v;
             }
         }
         const float x = (float)pt.x, y = (float)pt.y;           // narrow FIRST (template.cpp:82-83)
@@ -331,6 +343,9 @@ octvr_template* template_from_json(const std::string& json, int width, int heigh
     DevBuf<int> d_bbox(4);
     std::vector<float> h_m1(area), h_m2(area);
     std::vector<uint8_t> h_mask(area);
+    // MapperTemplate::visible_mask (template.cpp:41): output pixels an include mask has claimed so far
+    std::vector<uint8_t> visible;
+    std::unique_ptr<DevBuf<uint8_t>> d_visible, d_vis;
 
     auto add_input = [&](const Json& ji, bool overlay) {
         CamHost ic = camera_from_json(ji.at("type").string(), ji.at("options"));
@@ -340,9 +355,20 @@ octvr_template* template_from_json(const std::string& json, int width, int heigh
             OB_CUDA(cudaMemcpy(d_ex->p, ic.exclude.data(), ic.exclude.size(), cudaMemcpyHostToDevice));
             ic.m.exclude_mask = d_ex->p;
         }
+        std::unique_ptr<DevBuf<uint8_t>> d_in;
+        const bool batch = ic.m.type == CAM_PINHOLE || ic.m.type == CAM_FISHEYE;      // no obj_to_image_single: get_include_mask would throw
+        if (!ic.include.empty()) {
+            if (batch) fail(OCTVR_ERR_UNSUPPORTED, "include masks on a pinhole / fisheye input (NotImplemented in the reference, camera.hpp:92-103)");
+            d_in.reset(new DevBuf<uint8_t>(ic.include.size()));
+            OB_CUDA(cudaMemcpy(d_in->p, ic.include.data(), ic.include.size(), cudaMemcpyHostToDevice));
+            ic.m.include_mask = d_in->p;
+            if (!d_vis) d_vis.reset(new DevBuf<uint8_t>(area));
+        }
         MapgenParams p;
         p.out = oc.m; p.in = ic.m; p.W = width; p.H = height;
-        p.map1 = d_m1.p; p.map2 = d_m2.p; p.mask = d_mask.p; p.visible = nullptr; p.bbox = d_bbox.p;
+        p.map1 = d_m1.p; p.map2 = d_m2.p; p.mask = d_mask.p; p.bbox = d_bbox.p;
+        p.visible = d_visible ? d_visible->p : nullptr;
+        p.vis = !ic.include.empty() ? d_vis->p : nullptr;
         const int init[4] = { 0x3fffffff, 0x3fffffff, -1, -1 };
         OB_CUDA(cudaMemcpy(d_bbox.p, init, sizeof(init), cudaMemcpyHostToDevice));
         k_mapgen<<<dim3((width + 31) / 32, (height + 7) / 8), dim3(32, 8)>>>(p);
@@ -363,6 +389,26 @@ octvr_template* template_from_json(const std::string& json, int width, int heigh
         OB_CUDA(cudaMemcpy2D(in.map2.d.data(), (size_t)roi.w * 4, d_m2.p + off, (size_t)width * 4, (size_t)roi.w * 4, roi.h, cudaMemcpyDeviceToHost));
         OB_CUDA(cudaMemcpy2D(in.mask.d.data(), (size_t)roi.w, d_mask.p + off, (size_t)width, (size_t)roi.w, roi.h, cudaMemcpyDeviceToHost));
         if (ic.has_vignette) in.vignette = vignette_map(ic.vig, 512, 512);          // template.cpp:18-19,135-136
+        if (p.vis) {
+            // template.cpp:102-116: points this input's include mask makes visible for the first time are knocked out of
+            // every EARLIER input's mask (their ROIs stay as they were), then join the visible set
+            std::vector<uint8_t> vis(area);
+            OB_CUDA(cudaMemcpy(vis.data(), d_vis->p, area, cudaMemcpyDeviceToHost));
+            if (visible.empty()) visible.assign(area, 0);
+            for (int h = 0; h < height; h++)
+                for (int w = 0; w < width; w++) {
+                    const size_t idx = (size_t)h * width + w;
+                    if (!visible[idx] && vis[idx])
+                        for (auto& prior : t->inputs) {
+                            const Rect& r = prior.roi;
+                            if (h < r.y || h >= r.y + r.h || w < r.x || w >= r.x + r.w) continue;
+                            prior.mask.row(h - r.y)[w - r.x] = 0;
+                        }
+                    visible[idx] = visible[idx] || vis[idx];
+                }
+            if (!d_visible) d_visible.reset(new DevBuf<uint8_t>(area));
+            OB_CUDA(cudaMemcpy(d_visible->p, visible.data(), area, cudaMemcpyHostToDevice));
+        }
         (overlay ? t->overlays : t->inputs).push_back(std::move(in));
     };
     const Json& ins = cfg.at("inputs");

@@ -25,7 +25,7 @@ def _tool(name):
     return mod
 
 
-@pytest.mark.parametrize("rig", ["rig3", "rig3ov", "rig2s", "models"])
+@pytest.mark.parametrize("rig", ["rig3", "rig3ov", "rig2s", "models", "masks"])
 def test_octvr_dump_writes_the_reference_tools_bytes(rig, tmp_path):
     want = json.load(open(os.path.join(util.GOLD, "dat_sha256.json")))[rig]
     out = str(tmp_path / (rig + ".dat"))
