@@ -132,8 +132,12 @@ octvr_status octvr_mapper_stats(const octvr_mapper* m, int64_t* pairs, int64_t* 
 /* time (ms, CUDA events on the stitch stream) the named stage of the LAST stitch took; stage =
  * "convert" | "gain" | "blend" | "total".  Only valid when octvr_mapper_set_profiling(m, 1). */
 octvr_status octvr_mapper_set_profiling(octvr_mapper* m, int on);
-/* %globaltimer stamps (ns) of the gain kernel's last CTA: start, ticket, reduced, solved, done (diagnostics). */
-octvr_status octvr_mapper_debug_gain_ns(octvr_mapper* m, unsigned long long* out5);
+/* %globaltimer stamps (ns) of the gain kernel's last CTA: start, ticket, reduced, solved, done, and the start of the
+ * first gain CTA (diagnostics; SIX values). */
+octvr_status octvr_mapper_debug_gain_ns(octvr_mapper* m, unsigned long long* out6);
+/* Counters of the feather kernel's TMA ring (diagnostics; all zero unless the library is built with -DRING_DEBUG=1):
+ * jobs, ns waited for data, ns from TMA issue to first use, jobs waited for, ns issue -> complete over those; EIGHT values. */
+octvr_status octvr_mapper_debug_ring(octvr_mapper* m, unsigned long long* out8);
 /* Diagnostics / tests (host only, no device): the library's restatement of cv::fillPoly(img, {pts}, val) -- one contour,
  * 8UC1, lineType 8 (imgproc/src/drawing.cpp:1195-1404) -- that draws the camera masks of a JSON config
  * (octvr/src/camera.cpp:96-167).  pts_xy = {x0, y0, x1, y1, ...}. */

@@ -7,7 +7,7 @@ import os
 import subprocess
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "liboctvr_b200.so")
+LIB_PATH = os.environ.get("OCTVR_LIB") or os.path.join(_HERE, "liboctvr_b200.so")   # OCTVR_LIB: diagnostic A/B builds only
 
 OK, ERR_INVALID, ERR_FORMAT, ERR_CUDA, ERR_UNSUPPORTED = 0, -1, -2, -3, -4
 
@@ -32,7 +32,7 @@ SYMBOLS = [
     "octvr_template_out_size", "octvr_template_num_inputs", "octvr_template_num_overlays",
     "octvr_template_input", "octvr_template_destroy",
     "octvr_mapper_create", "octvr_mapper_stitch", "octvr_mapper_stitch_packed", "octvr_mapper_set_keep_rgb", "octvr_mapper_result_rgb",
-    "octvr_mapper_debug_gain_ns", "octvr_debug_fill_poly", "octvr_mapper_create_band",
+    "octvr_mapper_debug_gain_ns", "octvr_mapper_debug_ring", "octvr_debug_fill_poly", "octvr_mapper_create_band",
     "octvr_mapper_gains", "octvr_mapper_stats", "octvr_mapper_set_profiling", "octvr_mapper_stage_ms",
     "octvr_mapper_destroy",
     "octvr_async_create", "octvr_async_push", "octvr_async_pop", "octvr_async_fps", "octvr_async_preview", "octvr_async_destroy",

@@ -61,6 +61,14 @@ __device__ __forceinline__ float gain_apply_biased(float t, float g32, float c)
     return fminf(__fadd_rn(__fmaf_rn(t, g32, c), -MAGIC_RN), 255.f);
 }
 
+// The form K_blend_ring uses (bias 2^23, valid because v g >= 0): fma(2^23 + v, g, 2^23 - 2^23 g) = 2^23 + rint(v g) when
+// 2^23 - 2^23 g is exact in f32; verified per camera by gain_tables() like the two forms above.
+__device__ __forceinline__ float gain_apply_two23(float v, float g32)
+{
+    const float y = __fmaf_rn(__fadd_rn(8388608.f, v), g32, __fmaf_rn(-8388608.f, g32, 8388608.f));
+    return __fadd_rn(fminf(y, 8388608.f + 255.f), -8388608.f);
+}
+
 // RGB888 -> Y, U, V of cv::cvtColor(RGB2YUV_I420) (imgproc/src/color.cpp:6456-6481), no clamps needed:
 // the coefficient sums keep Y in [16,235] and U,V in [16,240] for 8-bit inputs.
 __device__ __forceinline__ uint32_t rgb_luma(int R, int G, int B)

@@ -327,7 +327,8 @@ __device__ void gain_tables(const GainParams& p)
             auto good = [&](int k) {
                 const int step = (k == 0) ? 0 : (k & 1) ? (k + 1) / 2 : -(k / 2);
                 const float gc = __int_as_float(__float_as_int(g0) + step);
-                return (int)gain_apply_f32((float)v, gc) == exact && (int)gain_apply_biased(MAGIC_RD + (float)v, gc, gain_bias_f32(gc)) == exact;
+                return (int)gain_apply_f32((float)v, gc) == exact && (int)gain_apply_biased(MAGIC_RD + (float)v, gc, gain_bias_f32(gc)) == exact &&
+                       (int)gain_apply_two23((float)v, gc) == exact;
             };
             ok = good(0) ? 0x1Fu : 0u;
             if (__syncthreads_or(ok == 0u)) {

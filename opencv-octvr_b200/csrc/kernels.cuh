@@ -101,6 +101,42 @@ struct StagedParams {
 };
 void launch_blend_staged(const StagedParams& p, cudaStream_t s);
 
+// ---- K_blend_ring (default feather / no-blend kernel; blend_ring.cu): persistent CTAs, a producer warp feeding a byte
+//      ring of shared memory with [4 KB of table entries | source box] per job by TMA, four consumer warps with four
+//      pixels per thread, packed-FP32 arithmetic, warp-private 4:2:0 epilogue with 128-bit stores. ----
+#ifndef RING_KB
+#define RING_KB 28
+#endif
+constexpr int RING_BYTES = RING_KB * 1024;          // shared-memory ring of a CTA (source boxes)
+constexpr int RING_ENT_BYTES = TILE_PX * 8;    // table entries of one job
+// job record (uint4), tile t owns records [t * nslot, (t + 1) * nslot) (nslot = cameras; unused slots are all zero):
+//   x = bx0 (s16) | by0 (s16) << 16 (top-left of the TMA box in the camera's RGBX plane), y = tensor map index | camera << 16,
+//   z = box bytes (bw * bh * 4, never 0 for a job), w = box pitch in px (bw, 12 bits) | job index << 12
+// entries: per job [2][128] uint4 {ex_a, ex_b, weight_a, weight_b}: thread t of the tile's 128 owns column t & 31 and
+//          rows 2w, 2w+1 (first uint4), 2w+8, 2w+9 (second) with w = t >> 5;
+//          ex = byte offset of the top-left tap inside the box << 16 | fy << 8 | fx
+struct RingParams {
+    const uint4* jobs;                // [tiles_x * tiles_y][nslot]
+    int nslot;
+    const uint4* entries;
+    const void* tmaps;                // CUtensorMap[...], 128 B each
+    unsigned int* counter;            // tile ticket (zero between launches; re-armed by the kernel)
+    unsigned long long* dbg;          // diagnostics (build with -DRING_DEBUG=1): [0] jobs, [1] sum ns waited for a job's data, [2] sum ns between TMA issue and first use,
+                                      //   [3] jobs waited for > 200 ns, [4] sum ns issue -> data complete over the jobs waited for
+    int tiles_x, out_w, out_h;
+    int tile0, ntiles;                // row band: tiles [tile0, tile0 + ntiles)
+    uint8_t* oy; uint8_t* ou; uint8_t* ov;
+    uint32_t oy_pitch, ou_pitch, ov_pitch;
+    int uv_step;
+    int fast_store;                   // planar 4:2:0 output with 16-byte aligned rows and no RGB result: 128-bit stores
+    uint8_t* rgb_out; uint32_t rgb_pitch;
+    const float* gain_f32; const int* gain_flag; const uint8_t* gain_lut;
+    int use_gain;
+    float inv_n;
+};
+int ring_ctas_per_sm();
+void launch_blend_ring(const RingParams& p, int grid, cudaStream_t s);
+
 // ---- K_stitch_fused: the whole feather / no-blend frame in ONE kernel, no intermediate image in HBM ----
 //      Persistent CTAs (4 per SM) walk a host-balanced list of 32x32 output tiles.  For every (tile, camera) job the
 //      CTA (1) converts the job's source blocks of the 4:2:0 input planes (L2-resident: 37 MB for the 6 x 2.7K rig)

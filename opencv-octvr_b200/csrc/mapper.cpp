@@ -94,6 +94,7 @@ octvr_mapper::~octvr_mapper()
     for (auto p : d_ov_coords) cudaFree(p);
     cudaFree(d_rgb_scaled); delete scale_plan; delete preview_plan;
     cudaFree(d_tile_job_start); cudaFree(d_job_cam); cudaFree(d_coords); cudaFree(d_weights); cudaFree(d_jobs); cudaFree(d_entries); cudaFree(d_tmaps); cudaFree(d_fjobs); cudaFree(d_fbins); cudaFree(d_fitems);
+    cudaFree(d_rjobs); cudaFree(d_rentries); cudaFree(d_ring_counter); cudaFree(d_dbg_ring);
     cudaFree(d_smask); cudaFree(d_gcoord); cudaFree(d_partial); cudaFree(d_ticket); cudaFree(d_gsamples); cudaFree(d_gchunks); cudaFree(d_gtotals);
     cudaFree(d_gains); cudaFree(d_gain_f32); cudaFree(d_gain_flag); cudaFree(d_gain_lut); cudaFree(d_rgb); cudaFree(d_dbg);
     if (h_gains) cudaFreeHost(h_gains);
@@ -443,7 +444,63 @@ static void build_mapper(octvr_mapper& m, const octvr_template& t, const int* in
             }
         }
         m.staged = staged;
-        if (staged) {
+        // K_blend_ring (default): the same boxes and tensor maps, entries regrouped for four pixels per thread, every
+        // job's [entries | box] must fit the shared-memory ring.  OCTVR_BLEND=staged keeps the one-tile-per-CTA kernel.
+        bool ring = staged;
+        if (const char* e = getenv("OCTVR_BLEND")) { if (std::string(e) == "staged") ring = false; }
+        for (size_t j = 0; j < njobs && ring; j++)
+            ring = (((size_t)meta[j].bw * meta[j].bh * 4 + 127) & ~(size_t)127) <= (size_t)RING_BYTES && meta[j].bw < 4096;
+        ring = ring && njobs < ((size_t)1 << 20);
+        if (ring) {
+            m.ring_ctas = ring_ctas_per_sm();
+            OB_CUDA(cudaDeviceGetAttribute(&m.sm_count, cudaDevAttrMultiProcessorCount, m.device));
+            if (m.ring_ctas <= 0) ring = false;
+        }
+        m.ring = ring;
+        if (ring) {
+            std::vector<uint4> entries(njobs * (TILE_PX / 2), make_uint4(0u, 0u, 0u, 0u));
+            std::vector<uint4> recs((size_t)ntiles * n, make_uint4(0u, 0u, 0u, 0u));
+            for (int tl = 0; tl < ntiles; tl++) {
+                for (uint32_t j = job_start[tl]; j < job_start[tl + 1]; j++) {
+                    const int i = job_cam[j];
+                    const TInput& in = t.inputs[i];
+                    const JobMeta& jm = meta[j];
+                    recs[(size_t)tl * n + (j - job_start[tl])] = make_uint4(((uint32_t)jm.bx0 & 0xFFFFu) | ((uint32_t)jm.by0 << 16), (uint32_t)jm.tmap | ((uint32_t)i << 16),
+                                                                            (uint32_t)(jm.bw * jm.bh * 4), (uint32_t)jm.bw | (j << 12));
+                    OB_CHECK(jm.bx0 >= -32768 && jm.bx0 < 32768 && jm.by0 >= -32768 && jm.by0 < 32768 && jm.tmap < 65536, "box origin out of range");
+                    uint32_t* ent = reinterpret_cast<uint32_t*>(entries.data() + (size_t)j * (TILE_PX / 2));
+                    for (int p = 0; p < TILE_PX; p++) {
+                        int lx, ly;
+                        if (!pixel_of(tl, p, i, lx, ly)) continue;
+                        const float w = W[i].row(ly)[lx];
+                        const int32_t fsx = sx[i].row(ly)[lx], fsy = sy[i].row(ly)[lx];
+                        const uint2 e = make_entry(fsx, fsy, m.in_w[i], m.in_h[i], in.mask.row(ly)[lx] != 0 && w != 0.f);
+                        if (!(e.y & C_VALID)) continue;
+                        const int ix = std::min(32767, std::max(-32768, fsx >> 5)), iy = std::min(32767, std::max(-32768, fsy >> 5));
+                        const uint32_t off = (uint32_t)(((iy - jm.by0) * jm.bw + (ix - jm.bx0)) * 4);       // bytes inside the box
+                        uint32_t wbits; memcpy(&wbits, &w, 4);
+                        // pixel (col, row) of the tile -> thread (row & 7) >> 1 << 5 | col, slot q = (row & 1) | (row >> 3) << 1
+                        const int col = p & (TILE_W - 1), row = p / TILE_W;
+                        const int tid = (((row & 7) >> 1) << 5) | col, q = (row & 1) | ((row >> 3) << 1);
+                        uint32_t* u4 = ent + ((size_t)(q >> 1) * 128 + tid) * 4;
+                        u4[q & 1] = (off << 16) | ((uint32_t)(fsy & 31) << 8) | (uint32_t)(fsx & 31);
+                        u4[2 + (q & 1)] = wbits;
+                    }
+                }
+            }
+            std::vector<CUtensorMap> tmaps(tmap_index.size());
+            for (auto& kv : tmap_index) {
+                const int cam = (int)(kv.first >> 32), bw = (int)((kv.first >> 16) & 0xFFFF), bh = (int)(kv.first & 0xFFFF);
+                encode_rgbx_tensor_map(&tmaps[kv.second], m.d_rgbx[cam], m.in_w[cam], m.in_h[cam], bw, bh);
+            }
+            m.d_tmaps = (void*)dev_upload(tmaps.data(), tmaps.size());
+            m.n_tmaps = (int)tmaps.size();
+            m.d_rjobs = dev_upload(recs.data(), recs.size());
+            m.d_rentries = dev_upload(entries.data(), entries.size());
+            m.d_ring_counter = dev_alloc<unsigned int>(1, true);
+            m.d_dbg_ring = dev_alloc<unsigned long long>(8, true);
+            m.table_bytes = (int64_t)(entries.size() * sizeof(uint4) + recs.size() * 16);
+        } else if (staged) {
             std::vector<uint2> entries(njobs * TILE_PX, make_uint2(0u, 0u));
             for (int tl = 0; tl < ntiles; tl++)
                 for (uint32_t j = job_start[tl]; j < job_start[tl + 1]; j++) {
@@ -709,6 +766,25 @@ void ob::mapper_stitch_internal(octvr_mapper& m, const octvr_frame* in, int n_in
         fp.use_gain = m.gain ? 1 : 0;
         fp.inv_n = m.inv_n;
         launch_stitch_fused(fp, m.fused_grid, s);
+    } else if (m.ring) {
+        RingParams rp;
+        memset(&rp, 0, sizeof(rp));
+        rp.jobs = m.d_rjobs; rp.nslot = m.n; rp.entries = m.d_rentries; rp.tmaps = m.d_tmaps; rp.counter = m.d_ring_counter; rp.dbg = m.d_dbg_ring;
+        rp.tiles_x = m.tiles_x; rp.out_w = m.out_w; rp.out_h = m.out_h;
+        const int ty0 = m.band_y0 / TILE_H, ty1 = (m.band_y1 + TILE_H - 1) / TILE_H;
+        rp.tile0 = ty0 * m.tiles_x; rp.ntiles = (ty1 - ty0) * m.tiles_x;
+        if (out) {
+            rp.oy = out->y; rp.ou = out->u; rp.ov = out->v;
+            rp.oy_pitch = (uint32_t)out->y_pitch; rp.ou_pitch = (uint32_t)out->u_pitch; rp.ov_pitch = (uint32_t)out->v_pitch;
+            rp.uv_step = out->uv_pixel_stride;
+        }
+        rp.rgb_out = m.rgb_this_frame ? m.d_rgb : nullptr; rp.rgb_pitch = (uint32_t)m.out_w * 3;
+        rp.fast_store = out && !rp.rgb_out && rp.uv_step == 1 && (uintptr_t)rp.oy % 16 == 0 && (uintptr_t)rp.ou % 16 == 0 && (uintptr_t)rp.ov % 16 == 0 &&
+                        rp.oy_pitch % 16 == 0 && rp.ou_pitch % 16 == 0 && rp.ov_pitch % 16 == 0;
+        rp.gain_f32 = m.d_gain_f32; rp.gain_flag = m.d_gain_flag; rp.gain_lut = m.d_gain_lut;
+        rp.use_gain = m.gain ? 1 : 0;
+        rp.inv_n = m.inv_n;
+        launch_blend_ring(rp, std::max(1, std::min(rp.ntiles, m.sm_count * m.ring_ctas)), s);
     } else if (m.staged) {
         StagedParams sp;
         memset(&sp, 0, sizeof(sp));
@@ -888,13 +964,24 @@ octvr_status octvr_mapper_stage_ms(octvr_mapper* m, const char* stage, float* ms
     });
 }
 
-octvr_status octvr_mapper_debug_gain_ns(octvr_mapper* m, unsigned long long* out5)
+octvr_status octvr_mapper_debug_gain_ns(octvr_mapper* m, unsigned long long* out6)
 {
     // diagnostics only
     return guard([&] {
-        OB_CHECK(m && out5 && m->d_dbg, "no gain stage");
+        OB_CHECK(m && out6 && m->d_dbg, "no gain stage");
         OB_CUDA(cudaDeviceSynchronize());
-        OB_CUDA(cudaMemcpy(out5, m->d_dbg, 6 * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
+        OB_CUDA(cudaMemcpy(out6, m->d_dbg, 6 * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
+    });
+}
+
+octvr_status octvr_mapper_debug_ring(octvr_mapper* m, unsigned long long* out8)
+{
+    // diagnostics only: counters of K_blend_ring when the library is built with -DRING_DEBUG=1 (zeroed by this call)
+    return guard([&] {
+        OB_CHECK(m && out8 && m->d_dbg_ring, "no ring kernel");
+        OB_CUDA(cudaDeviceSynchronize());
+        OB_CUDA(cudaMemcpy(out8, m->d_dbg_ring, 8 * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
+        OB_CUDA(cudaMemset(m->d_dbg_ring, 0, 8 * sizeof(unsigned long long)));
     });
 }
 

@@ -30,6 +30,14 @@ struct octvr_mapper {
     uint2* d_entries = nullptr;
     void* d_tmaps = nullptr;
     int n_tmaps = 0;
+    // ring layout (K_blend_ring, the default feather / no-blend kernel): d_tmaps as above
+    bool ring = false;
+    int ring_ctas = 0;                  // resident CTAs per SM (sizes the persistent grid)
+    int sm_count = 0;
+    uint4* d_rjobs = nullptr;
+    uint4* d_rentries = nullptr;
+    unsigned int* d_ring_counter = nullptr;
+    unsigned long long* d_dbg_ring = nullptr;
     // fused layout (K_stitch_fused)
     bool fused = false;
     int fused_grid = 0;

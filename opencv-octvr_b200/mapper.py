@@ -246,6 +246,12 @@ class Mapper:
         check(lib().octvr_mapper_debug_gain_ns(self._h, a))
         return list(a)
 
+    def debug_ring(self):
+        """counters of K_blend_ring's TMA ring (diagnostics; needs a -DRING_DEBUG=1 build)."""
+        a = (C.c_ulonglong * 8)()
+        check(lib().octvr_mapper_debug_ring(self._h, a))
+        return list(a)
+
     def __del__(self):
         try:
             if self._h:

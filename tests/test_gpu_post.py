@@ -23,7 +23,7 @@ def dev(a):
     return torch.from_numpy(np.ascontiguousarray(a)).cuda()
 
 
-@pytest.fixture(params=["staged", "fused", "direct"])
+@pytest.fixture(params=["ring", "staged", "fused", "direct"])
 def blend_path(request, monkeypatch):
     monkeypatch.setenv("OCTVR_BLEND", request.param)
     return request.param

@@ -52,3 +52,13 @@ try:
           % (d[1] - d[0], d[2] - d[1], d[3] - d[2], d[4] - d[3], d[0] - d[5], d[4] - d[5]))
 except Exception as ex:
     print("no gain stamps:", ex)
+try:
+    m.debug_ring()
+    for k in range(4):
+        m.stitch_packed(ring[k % 4], out)
+    d = m.debug_ring()
+    if d[0]:
+        print("ring: %d jobs (warp 0 view), mean wait %.0f ns, mean issue->use %.0f ns, %.1f %% of jobs waited > 200 ns, their mean issue->complete %.0f ns"
+              % (d[0], d[1] / d[0], d[2] / d[0], 100.0 * d[3] / d[0], d[4] / max(d[3], 1)))
+except Exception as ex:
+    print("no ring counters:", ex)

@@ -51,6 +51,10 @@ __global__ void __launch_bounds__(1024) name(uint32_t* out, long long* cyc, uint
 #define A_BFI    asm volatile("bfi.b32 %0, %1, %0, 8, 8;" : "+r"(x[i]) : "r"(c1));
 #define A_SHLADD asm volatile("mad.lo.u32 %0, %0, 256, %1;" : "+r"(x[i]) : "r"(c1));
 #define A_HFMA2  asm volatile("fma.rn.f16x2 %0, %0, %1, %2;" : "+r"(x[i]) : "r"(c1), "r"(c2));
+#define A_FFMA2  asm volatile("fma.rn.f32x2 %0, %0, %1, %2;" : "+l"(w[i]) : "l"(pk1), "l"(pk2));
+#define A_FADD2RM asm volatile("add.rm.f32x2 %0, %0, %1;" : "+l"(w[i]) : "l"(pk1));
+#define A_FMUL2  asm volatile("mul.rn.f32x2 %0, %0, %1;" : "+l"(w[i]) : "l"(pk1));
+#define PKINIT unsigned long long pk1, pk2; asm("mov.b64 %0, {%1, %2};" : "=l"(pk1) : "f"(g1), "f"(g2)); asm("mov.b64 %0, {%1, %2};" : "=l"(pk2) : "f"(g2), "f"(g1));
 #define A_VIMAX3 x[i] = (uint32_t)__vimax3_s32((int)x[i], (int)c1, (int)(c2 ^ x[i]));
 #define SMEM __shared__ uint32_t sm[1024]; sm[threadIdx.x] = threadIdx.x * 4; __syncthreads(); uint32_t sbase = (uint32_t)__cvta_generic_to_shared(sm);
 #define NOINIT
@@ -81,6 +85,13 @@ DEF_KERNEL(k_bfi, NOINIT, A_BFI)
 DEF_KERNEL(k_shladd, NOINIT, A_SHLADD)
 DEF_KERNEL(k_hfma2, NOINIT, A_HFMA2)
 DEF_KERNEL(k_vimax3, NOINIT, A_VIMAX3)
+DEF_KERNEL(k_ffma2, PKINIT, A_FFMA2)
+DEF_KERNEL(k_fadd2rm, PKINIT, A_FADD2RM)
+DEF_KERNEL(k_fmul2, PKINIT, A_FMUL2)
+DEF_KERNEL(k_ffma2_imad, PKINIT, A_FFMA2 A_IMAD)
+DEF_KERNEL(k_ffma2_lop, PKINIT, A_FFMA2 A_LOP)
+DEF_KERNEL(k_ffma2_ffma, PKINIT, A_FFMA2 A_FFMA)
+DEF_KERNEL(k_ffma2_imad_lop, PKINIT, A_FFMA2 A_IMAD A_LOP)
 // mixes: same pipe -> rates add; different pipes -> overlap
 DEF_KERNEL(k_imad_lop, NOINIT, A_IMAD A_LOP)
 DEF_KERNEL(k_imad_ffma, NOINIT, A_IMAD A_FFMA)
@@ -123,6 +134,8 @@ int main() {
         {"IMAD+PRMT", k_imad_prmt, 2}, {"LOP3+PRMT", k_lop_prmt, 2}, {"IMAD+VIMNMX", k_imad_mnmx, 2}, {"LOP3+VIMNMX", k_lop_mnmx, 2}, {"IMAD+I2F+xor", k_imad_i2f, 3}, {"LOP3+I2FP", k_lop_i2fp, 2}, {"IMAD+I2FP", k_imad_i2fp, 2},
         {"IMAD+IMAD.WIDE", k_imad_imadw, 2}, {"LOP3+IMAD.WIDE", k_lop_imadw, 2}, {"LOP3+FMNMX", k_lop_fmnmx, 2}, {"IMAD+FMNMX", k_imad_fmnmx, 2}, {"LOP3+FADD.RM", k_lop_faddrm, 2}, {"IMAD+FADD.RM", k_imad_faddrm, 2},
         {"LOP3+FMUL", k_lop_fmul, 2}, {"IMAD+LDS", k_imad_lds, 2}, {"IMAD+LOP3+LDS", k_imad_lop_lds, 3}, {"IMAD+LOP3+LOP3", k_imad_lop_lop, 3}, {"IMAD+IMAD+LOP3", k_imad_imad_lop, 3},
+        {"FFMA2", k_ffma2, 1}, {"FADD2.RM", k_fadd2rm, 1}, {"FMUL2", k_fmul2, 1}, {"FFMA2+IMAD", k_ffma2_imad, 2}, {"FFMA2+LOP3", k_ffma2_lop, 2},
+        {"FFMA2+FFMA", k_ffma2_ffma, 2}, {"FFMA2+IMAD+LOP3", k_ffma2_imad_lop, 3},
         {"LOP3+HFMA2", k_lop_hfma2, 2}, {"IMAD+HFMA2", k_imad_hfma2, 2}, {"LOP3+IMADx256", k_lop_shladd, 2}, {"LOP3+SHF", k_lop_shf, 2},
     };
     int nsm = 0; cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, 0);
