@@ -135,6 +135,9 @@ octvr_status octvr_mapper_set_profiling(octvr_mapper* m, int on);
 /* %globaltimer stamps (ns) of the gain kernel's last CTA: start, ticket, reduced, solved, done, and the start of the
  * first gain CTA (diagnostics; SIX values). */
 octvr_status octvr_mapper_debug_gain_ns(octvr_mapper* m, unsigned long long* out6);
+/* The whole stamp buffer (diagnostics): with OCTVR_GAIN_TRACE set [6], [7] = first start / last end of the conversion CTAs and
+ * [8 + 6c ..] = phase stamps of gain CTA c < 1024.  n <= 8 + 2 * 4096 words. */
+octvr_status octvr_mapper_debug_gain_trace(octvr_mapper* m, unsigned long long* out, int n);
 /* Counters of the feather kernel's TMA ring (diagnostics; all zero unless the library is built with -DRING_DEBUG=1):
  * jobs, ns waited for data, ns from TMA issue to first use, jobs waited for, ns issue -> complete over those; EIGHT values. */
 octvr_status octvr_mapper_debug_ring(octvr_mapper* m, unsigned long long* out8);

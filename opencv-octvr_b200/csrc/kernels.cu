@@ -236,15 +236,15 @@ __device__ void gain_solve_warp(int n, const double* Nm, const double* Im, doubl
     #undef ADD
 }
 
-// The same solve by the whole CTA for n > 3: one thread per element of the augmented matrix [A | b].  Every element
-// sees exactly the operations of matrix_decomp.cpp:52-109 in the same order (alpha = A[j][i] * d, A[j][k] += alpha *
-// A[i][k]; no FMA contraction), but a pivot step costs one division plus one multiply-add instead of a serial sweep.
-__device__ void gain_solve_cta(int n, const double* Nm, const double* Im, double* Aug, double* g)
+// The same solve for n > 3 by ONE WARP with the matrix in shared memory (lane = column of [A | b]): no CTA barriers, the
+// rows of an elimination step are independent so their loads overlap.  Every element sees exactly the operations of
+// matrix_decomp.cpp:52-109 in the same order (alpha = A[j][i] * d, A[j][k] += alpha * A[i][k]; no FMA contraction).
+__device__ void gain_solve_lu_warp(int n, const double* Nm, const double* Im, double* Aug, double* g)
 {
-    const int tid = threadIdx.x, nt = blockDim.x, ld = n + 1, ne = n * ld;
+    const int lane = threadIdx.x & 31, ld = n + 1;
     const double alpha = 0.01, beta = 100;
-    if (tid < n) {                                          // normal equations: thread = row (exposure_compensate.cpp:138-153)
-        const int i = tid;
+    if (lane < n) {                                         // normal equations: lane = row (exposure_compensate.cpp:138-153)
+        const int i = lane;
         double bi = 0, aii = 0;
         #pragma unroll 1
         for (int j = 0; j < n; j++) {
@@ -259,41 +259,37 @@ __device__ void gain_solve_cta(int n, const double* Nm, const double* Im, double
         }
         Aug[i * ld + i] = aii; Aug[i * ld + n] = bi;
     }
-    __syncthreads();
+    __syncwarp();
     #pragma unroll 1
     for (int i = 0; i < n; i++) {
-        int k = i;                                          // pivot: every thread scans the column (uniform result)
-        #pragma unroll 1
-        for (int j = i + 1; j < n; j++) if (fabs(Aug[j * ld + i]) > fabs(Aug[k * ld + i])) k = j;
-        if (k != i) {                                       // swap rows i and k from column i on (and b)
-            double t0 = 0, t1 = 0;
-            const int c = i + tid;
-            if (c <= n) { t0 = Aug[i * ld + c]; t1 = Aug[k * ld + c]; }
-            __syncthreads();
-            if (c <= n) { Aug[i * ld + c] = t1; Aug[k * ld + c] = t0; }
-            __syncthreads();
-        }
-        const double d = -1 / Aug[i * ld + i];
-        double upd[2]; int at[2] = { -1, -1 };
+        // pivot: the first row k >= i with the largest |A[k][i]| (the reference's strict '>' scan keeps the earliest)
+        double pv = (lane >= i && lane < n) ? fabs(Aug[lane * ld + i]) : -1.0;
+        int k = lane;
         #pragma unroll
-        for (int u = 0; u < 2; u++) {                       // up to two elements per thread (n = 16: 272 elements)
-            const int e = tid + u * nt;
-            if (e < ne) {
-                const int r = e / ld, c = e - r * ld;
-                if (r > i && c > i) {
-                    const double al = __dmul_rn(Aug[r * ld + i], d);
-                    upd[u] = __dadd_rn(Aug[e], __dmul_rn(al, Aug[i * ld + c]));
-                    at[u] = e;
-                }
+        for (int o = 16; o > 0; o >>= 1) {
+            const double ov = __shfl_xor_sync(0xffffffffu, pv, o);
+            const int ok = __shfl_xor_sync(0xffffffffu, k, o);
+            if (ov > pv || (ov == pv && ok < k)) { pv = ov; k = ok; }
+        }
+        if (k != i && lane >= i && lane <= n) {             // swap rows i and k from column i on (and b)
+            const double t0 = Aug[i * ld + lane], t1 = Aug[k * ld + lane];
+            Aug[i * ld + lane] = t1; Aug[k * ld + lane] = t0;
+        }
+        __syncwarp();
+        const double d = -1 / Aug[i * ld + i];
+        if (lane > i && lane <= n) {
+            const double pivot_c = Aug[i * ld + lane];
+            #pragma unroll 4
+            for (int r = i + 1; r < n; r++) {
+                const double al = __dmul_rn(Aug[r * ld + i], d);
+                Aug[r * ld + lane] = __dadd_rn(Aug[r * ld + lane], __dmul_rn(al, pivot_c));
             }
         }
-        __syncthreads();
-        #pragma unroll
-        for (int u = 0; u < 2; u++) if (at[u] >= 0) Aug[at[u]] = upd[u];
-        if (tid == 0) Aug[i * ld + i] = -d;
-        __syncthreads();
+        __syncwarp();
+        if (lane == 0) Aug[i * ld + i] = -d;
+        __syncwarp();
     }
-    if (tid == 0) {                                         // back substitution: a serial chain by definition
+    if (lane == 0) {                                        // back substitution: a serial chain by definition
         #pragma unroll 1
         for (int i = n - 1; i >= 0; i--) {
             double sacc = Aug[i * ld + n];
@@ -309,52 +305,63 @@ __device__ void gain_solve_cta(int n, const double* Nm, const double* Im, double
 // Per camera: the exact u8 gain LUT in f64, and an f32 multiplier for which the single-FMA formula of
 // gain_apply_f32() reproduces that LUT for all 256 inputs (searched within +-2 ulp of (float)g).
 // If none exists the camera is flagged and the blend kernel reads the LUT instead.  256 threads = 256 inputs.
-__device__ void gain_tables(const GainParams& p)
+// sg: the gains in shared memory (just solved by this CTA), or null: read them from p.gains (predefined / shared gains)
+__device__ void gain_tables(const GainParams& p, const double* sg)
 {
     __shared__ unsigned int s_ok[MAX_CAMS];
+    __shared__ unsigned int s_bad;                           // cameras for which (float)g itself does not reproduce the f64 rule
     const int v = threadIdx.x;                               // called by threads 0..255 only
     if (v < MAX_CAMS) s_ok[v] = 0x1Fu;
+    if (v == 0) s_bad = 0u;
     asm volatile("bar.sync 1, 256;");
+    // candidate k of a camera: (float)g + {0,+1,-1,+2,-2} ulp; it is good for input v if all three kernel forms give the f64 result
+    auto good = [&](float g0, int k, int exact) {
+        const int step = (k == 0) ? 0 : (k & 1) ? (k + 1) / 2 : -(k / 2);
+        const float gc = __int_as_float(__float_as_int(g0) + step);
+        return (int)gain_apply_f32((float)v, gc) == exact && (int)gain_apply_biased(MAGIC_RD + (float)v, gc, gain_bias_f32(gc)) == exact &&
+               (int)gain_apply_two23((float)v, gc) == exact;
+    };
+    // pass 1, no barrier inside (the loads of all cameras overlap): exact LUT + candidate 0.  Candidate 0 almost always works.
+    unsigned int bad = 0u;
+    #pragma unroll 4
     for (int c = 0; c < p.n; c++) {
-        const double g = __ldcg(p.gains + c);
+        const double g = sg ? sg[c] : __ldcg(p.gains + c);
         const int exact = clamp255(__double2int_rn((double)v * g));
         p.gain_lut[c * 256 + v] = (uint8_t)exact;
-        unsigned int ok = 0u;
-        if (g > 0. && g < 4096.) {
-            const float g0 = (float)g;
-            // candidate k: (float)g + {0,+1,-1,+2,-2} ulp.  Candidate 0 almost always reproduces the f64 rule for all 256
-            // inputs, so the others are only evaluated (by the whole CTA, uniformly) when some input rejects it
-            auto good = [&](int k) {
-                const int step = (k == 0) ? 0 : (k & 1) ? (k + 1) / 2 : -(k / 2);
-                const float gc = __int_as_float(__float_as_int(g0) + step);
-                return (int)gain_apply_f32((float)v, gc) == exact && (int)gain_apply_biased(MAGIC_RD + (float)v, gc, gain_bias_f32(gc)) == exact &&
-                       (int)gain_apply_two23((float)v, gc) == exact;
-            };
-            ok = good(0) ? 0x1Fu : 0u;
-            if (__syncthreads_or(ok == 0u)) {
-                ok = 0u;
-                #pragma unroll 1
-                for (int k = 0; k < 5; k++) if (good(k)) ok |= 1u << k;
-            }
-        } else
-            __syncthreads_or(0);
-        if (ok != 0x1Fu) atomicAnd(&s_ok[c], ok);
+        if (!(g > 0. && g < 4096.) || !good((float)g, 0, exact)) bad |= 1u << c;
     }
+    bad = __reduce_or_sync(0xffffffffu, bad);
+    if ((v & 31) == 0 && bad) atomicOr(&s_bad, bad);
     asm volatile("bar.sync 1, 256;");
+    bad = s_bad;
+    if (bad) {                                               // rare: search the other candidates for those cameras (uniform branch)
+        for (int c = 0; c < p.n; c++) {
+            if (!((bad >> c) & 1u)) continue;
+            const double g = sg ? sg[c] : __ldcg(p.gains + c);
+            const int exact = clamp255(__double2int_rn((double)v * g));
+            unsigned int ok = 0u;
+            if (g > 0. && g < 4096.) {
+                #pragma unroll 1
+                for (int k = 0; k < 5; k++) if (good((float)g, k, exact)) ok |= 1u << k;
+            }
+            if (ok != 0x1Fu) atomicAnd(&s_ok[c], ok);
+        }
+        asm volatile("bar.sync 1, 256;");
+    }
     if (v < p.n) {
         const unsigned int ok = s_ok[v];
         const int k = ok ? __ffs(ok) - 1 : 0;
         const int step = (k == 0) ? 0 : (k & 1) ? (k + 1) / 2 : -(k / 2);
-        p.gain_f32[v] = __int_as_float(__float_as_int((float)__ldcg(p.gains + v)) + step);
+        p.gain_f32[v] = __int_as_float(__float_as_int((float)(sg ? sg[v] : __ldcg(p.gains + v))) + step);
         p.gain_flag[v] = ok ? 0 : 1;
     }
 }
 
 // Working-scale statistics (mapper.cpp:94-99: a ~0.1 Mpix canvas) + gain solve in ONE launch, written for latency.
-// A CTA takes one chunk of the canvas: up to 128 pixels and the (at most 256) samples (pixel, camera) whose
+// A CTA takes one chunk of the canvas: up to 256 pixels and the (at most 512) samples (pixel, camera) whose
 // working-scale mask is 255 there (CPU compensator's intersect rule, exposure_compensate.cpp:71-78,112), listed by the
-// host.  Phase A: thread = sample; it remaps that one pixel (nearest-resized position, mapper.cpp:235-237) straight
-// from the input planes and stores ||rgb||_2 (f64) in shared memory -- every table and tap load of the chunk is in
+// host.  Phase A: thread = two samples; it remaps each pixel (nearest-resized position, mapper.cpp:235-237) straight
+// from the input planes and stores ||rgb||_2 (as exact 2^-52 fixed point) in shared memory -- every table and tap load of the chunk is in
 // flight at once.  Phase B: warp = camera pair, lanes = pixels.  The sums are accumulated EXACTLY: a norm is sqrt of
 // an integer >= 1 (or 0), i.e. an integer multiple of 2^-52 below 2^9, so its 61-bit fixed-point image is split into
 // two 64-bit integer accumulators (high / low 32 bits) that cannot overflow over 2^17 samples.  Integer addition is
@@ -363,9 +370,12 @@ __device__ void gain_tables(const GainParams& p)
 // The last CTA to finish (ticket) solves for the gains (one warp) and builds the gain tables.  Deterministic.
 constexpr int MAX_PAIRS = MAX_CAMS * (MAX_CAMS + 1) / 2;
 __device__ __forceinline__ unsigned long long gtime() { unsigned long long t; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t)); return t; }
-constexpr int GAIN_BLK = 256;                              // CTA size of the fused kernel = samples per chunk
-constexpr int GAIN_PX = 128;                               // canvas pixels per chunk
-__device__ __forceinline__ void gain_body(const GainParams& p, double* s_nrm, const unsigned gain_blocks, const unsigned chunk)   // s_nrm: [n][GAIN_PX]
+constexpr int GAIN_BLK = 256;                              // CTA size of the fused kernel
+constexpr int GAIN_SPT = 2;                                // samples per thread: a chunk holds up to GAIN_BLK * GAIN_SPT samples ...
+constexpr int GAIN_PX = 256;                               // ... of up to GAIN_PX canvas pixels (mapper.cpp builds the chunks with the same numbers)
+constexpr unsigned long long GAIN_NONE = ~0ull;
+// s_nrm: [n][GAIN_PX] fixed-point norms (2^52 x ||rgb||_2 < 2^61, exact), GAIN_NONE where a camera has no sample
+__device__ __forceinline__ void gain_body(const GainParams& p, unsigned long long* s_nrm, const unsigned gain_blocks, const unsigned chunk)
 {
     __shared__ double s_part[3 * MAX_PAIRS];
     __shared__ double Nm[MAX_CAMS * MAX_CAMS], Im[MAX_CAMS * MAX_CAMS], Aug[MAX_CAMS * (MAX_CAMS + 1)];
@@ -375,40 +385,76 @@ __device__ __forceinline__ void gain_body(const GainParams& p, double* s_nrm, co
     const int n = p.n, np = p.n_pairs;
     const unsigned long long T0 = gtime();
     if (chunk == 0 && tid == 0 && p.dbg) p.dbg[5] = T0;      // diagnostics: when the first gain CTA started
-    for (int q = tid; q < n * GAIN_PX; q += GAIN_BLK) s_nrm[q] = -1.0;
+    unsigned long long* const tr = (p.dbg_trace && tid == 0 && chunk < 1024u) ? p.dbg_trace + 8 + 6 * chunk : nullptr;   // phase stamps (OCTVR_GAIN_TRACE)
+    if (tr) tr[0] = T0;
+    uint4 sm[GAIN_SPT];                                      // entry.x, entry.y, camera | local pixel << 8 (all ones: empty slot)
+    #pragma unroll
+    for (int h = 0; h < GAIN_SPT; h++) sm[h] = __ldg(p.samples + ((size_t)chunk * GAIN_SPT + h) * GAIN_BLK + tid);
+    for (int q = tid; q < n * GAIN_PX; q += GAIN_BLK) s_nrm[q] = GAIN_NONE;
     if (tid == 0) { int q = 0; for (int i = 0; i < n; i++) for (int j = i; j < n; j++, q++) { s_pi[q] = (uint8_t)i; s_pj[q] = (uint8_t)j; } }
     __syncthreads();
+    if (tr) tr[1] = gtime() + (sm[0].x & 0u);              // (depends on the sample load)
     {
-        const uint4 sm = __ldg(p.samples + (size_t)chunk * GAIN_BLK + tid);      // entry.x, entry.y, camera | local pixel << 8 (all ones: empty slot)
-        if (sm.z != 0xFFFFFFFFu) {
-            const int c = (int)(sm.z & 255u), lp = (int)(sm.z >> 8);
-            uint32_t t00 = 0u, t01 = 0u, t10 = 0u, t11 = 0u;
-            if (sm.y & C_VALID) {
-                const CamSrc& sc = p.src[c];
-                const int ix = (int)(sm.x & 0xFFFFu) - 1, iy = (int)(sm.x >> 16) - 1;
-                const uint32_t bits = (sm.y & C_BORDER) ? (sm.y >> C_TAP_SHIFT) : 15u;
-                if (bits & 1u) t00 = source_px(sc, ix, iy);
-                if (bits & 2u) t01 = source_px(sc, ix + 1, iy);
-                if (bits & 4u) t10 = source_px(sc, ix, iy + 1);
-                if (bits & 8u) t11 = source_px(sc, ix + 1, iy + 1);
+        uint32_t t[GAIN_SPT][4];
+        // Every tap load of both samples is issued before the first one is used (24 byte loads in flight: one memory
+        // round trip instead of one per tap -- a load inside a conditional block is followed by its use, which stalls
+        // the warp before the next block's loads are issued).  Taps outside the source are loaded from a clamped
+        // position and zeroed afterwards (BORDER_CONSTANT).
+        uint8_t yv[GAIN_SPT][4], uv[GAIN_SPT][4], vv[GAIN_SPT][4];
+        uint32_t bits[GAIN_SPT];
+        bool slow[GAIN_SPT];
+        #pragma unroll
+        for (int h = 0; h < GAIN_SPT; h++) {
+            const bool valid = sm[h].z != 0xFFFFFFFFu && (sm[h].y & C_VALID);
+            const CamSrc& sc = p.src[valid ? (sm[h].z & 255u) : 0u];
+            slow[h] = valid && sc.vignette != nullptr;       // vignette maps: the per-tap path below
+            bits[h] = !valid || slow[h] ? 0u : (sm[h].y & C_BORDER) ? (sm[h].y >> C_TAP_SHIFT) : 15u;
+            const int ix = valid ? (int)(sm[h].x & 0xFFFFu) - 1 : 0, iy = valid ? (int)(sm[h].x >> 16) - 1 : 0;
+            #pragma unroll
+            for (int k = 0; k < 4; k++) {
+                const int x = min(max(ix + (k & 1), 0), sc.w - 1), y = min(max(iy + (k >> 1), 0), sc.h - 1);
+                yv[h][k] = __ldg(sc.y + (size_t)y * sc.y_pitch + x);
+                uv[h][k] = __ldg(sc.u + (size_t)(y >> 1) * sc.u_pitch + (size_t)(x >> 1) * sc.uv_step);
+                vv[h][k] = __ldg(sc.v + (size_t)(y >> 1) * sc.v_pitch + (size_t)(x >> 1) * sc.uv_step);
             }
-            int r, g, b;
-            bilerp_rgbx(t00, t01, t10, t11, sm.y & 31u, (sm.y >> 5) & 31u, r, g, b);
-            s_nrm[c * GAIN_PX + lp] = sqrt((double)(r * r + g * g + b * b));
         }
+        #pragma unroll
+        for (int h = 0; h < GAIN_SPT; h++) {
+            #pragma unroll
+            for (int k = 0; k < 4; k++) {
+                const int u = (int)uv[h][k] - 128, v = (int)vv[h][k] - 128;
+                const uint32_t px = yuv_px((uint32_t)yv[h][k], (1 << 19) + 1673527 * v, (1 << 19) - 852492 * v - 409993 * u, (1 << 19) + 2116026 * u);
+                t[h][k] = ((bits[h] >> k) & 1u) ? px : 0u;
+            }
+            if (slow[h]) {
+                const CamSrc& sc = p.src[sm[h].z & 255u];
+                const int ix = (int)(sm[h].x & 0xFFFFu) - 1, iy = (int)(sm[h].x >> 16) - 1;
+                const uint32_t bt = (sm[h].y & C_BORDER) ? (sm[h].y >> C_TAP_SHIFT) : 15u;
+                if (bt & 1u) t[h][0] = source_px(sc, ix, iy);
+                if (bt & 2u) t[h][1] = source_px(sc, ix + 1, iy);
+                if (bt & 4u) t[h][2] = source_px(sc, ix, iy + 1);
+                if (bt & 8u) t[h][3] = source_px(sc, ix + 1, iy + 1);
+            }
+        }
+        #pragma unroll
+        for (int h = 0; h < GAIN_SPT; h++)
+            if (sm[h].z != 0xFFFFFFFFu) {
+                int r, g, b;
+                bilerp_rgbx(t[h][0], t[h][1], t[h][2], t[h][3], sm[h].y & 31u, (sm[h].y >> 5) & 31u, r, g, b);
+                // x 2^52: exact (the norm is a multiple of 2^-52 below 2^9)
+                s_nrm[(sm[h].z & 255u) * GAIN_PX + (sm[h].z >> 8)] = __double2ull_rz(sqrt((double)(r * r + g * g + b * b)) * 4503599627370496.0);
+            }
     }
     __syncthreads();
+    if (tr) tr[2] = gtime();
     #pragma unroll 1
     for (int q = warp; q < np; q += GAIN_BLK / 32) {
-        const double* na = s_nrm + s_pi[q] * GAIN_PX, *nb = s_nrm + s_pj[q] * GAIN_PX;
+        const unsigned long long* na = s_nrm + s_pi[q] * GAIN_PX, *nb = s_nrm + s_pj[q] * GAIN_PX;
         unsigned long long cnt = 0, ha = 0, la = 0, hb = 0, lb = 0;
-        #pragma unroll 1
+        #pragma unroll 4
         for (int l = lane; l < GAIN_PX; l += 32) {
-            const double a = na[l], b = nb[l];
-            if (a >= 0 && b >= 0) {
-                const unsigned long long qa = __double2ull_rz(a * 4503599627370496.0), qb = __double2ull_rz(b * 4503599627370496.0);   // x 2^52: exact
-                cnt++; ha += qa >> 32; la += qa & 0xFFFFFFFFull; hb += qb >> 32; lb += qb & 0xFFFFFFFFull;
-            }
+            const unsigned long long qa = na[l], qb = nb[l];
+            if (qa != GAIN_NONE && qb != GAIN_NONE) { cnt++; ha += qa >> 32; la += qa & 0xFFFFFFFFull; hb += qb >> 32; lb += qb & 0xFFFFFFFFull; }
         }
         #pragma unroll 1
         for (int o = 16; o > 0; o >>= 1) {                  // integer sums: any order gives the same result
@@ -420,9 +466,11 @@ __device__ __forceinline__ void gain_body(const GainParams& p, double* s_nrm, co
             atomicAdd(o, cnt); atomicAdd(o + 1, ha); atomicAdd(o + 2, la); atomicAdd(o + 3, hb); atomicAdd(o + 4, lb);
         }
     }
+    if (tr) tr[3] = gtime();
     __threadfence();
     __syncthreads();
     if (tid == 0) {
+        if (tr) tr[4] = gtime();
         const unsigned int t = atomicInc(p.ticket, gain_blocks - 1);   // wraps to 0: self-resetting
         is_last = (t == gain_blocks - 1);
     }
@@ -456,42 +504,46 @@ __device__ __forceinline__ void gain_body(const GainParams& p, double* s_nrm, co
     }
     __syncthreads();
     const unsigned long long T2 = gtime();
-    if (n > 3) gain_solve_cta(n, Nm, Im, Aug, p.gains);        // uniform
-    else if (warp == 0) gain_solve_warp(n, Nm, Im, Aug, p.gains);
-    __threadfence();
+    __shared__ double s_g[MAX_CAMS];
+    if (warp == 0) { if (n > 3) gain_solve_lu_warp(n, Nm, Im, Aug, s_g); else gain_solve_warp(n, Nm, Im, Aug, s_g); }
     __syncthreads();
+    if (tid < n) p.gains[tid] = s_g[tid];                   // Mapper::gains(); the tables below take them from shared memory
     const unsigned long long T3 = gtime();
-    gain_tables(p);                         // 256 threads = the 256 input values
+    gain_tables(p, s_g);                    // 256 threads = the 256 input values
     if (tid == 0 && p.dbg) { p.dbg[0] = T0; p.dbg[1] = T1; p.dbg[2] = T2; p.dbg[3] = T3; p.dbg[4] = gtime(); }
 }
 
-__global__ void __launch_bounds__(256) k_gain_finalize(const GainParams p) { gain_tables(p); }
+__global__ void __launch_bounds__(256) k_gain_finalize(const GainParams p) { gain_tables(p, nullptr); }
 
 // Horizontally fused front end of a frame: `gain_blocks` CTAs compute the gain statistics and solve (they read the
 // input planes directly, so they do not depend on the conversion), all other CTAs convert the inputs to RGBX.  One
 // launch, both parts run concurrently, no cross-stream synchronisation.  The gain CTAs are latency-bound and light, the
 // conversion CTAs DRAM-bound: at the head of the grid they are interleaved 1 : 2, so the whole gain chain starts within
 // the first third of the conversion without ever holding more than a fraction of the resident CTA slots.
-__global__ void __launch_bounds__(256, 6) k_convert_gain(const __grid_constant__ ConvertParams cp, const __grid_constant__ GainParams gp, const unsigned gain_blocks,
+__global__ void __launch_bounds__(256, 4) k_convert_gain(const __grid_constant__ ConvertParams cp, const __grid_constant__ GainParams gp, const unsigned gain_blocks,
                                                          const unsigned interleave)
 {
-    extern __shared__ double s_dyn_nrm[];
+    extern __shared__ unsigned long long s_dyn_nrm[];
     const unsigned b = blockIdx.x;
+    struct Stamp {                                          // diagnostics (OCTVR_GAIN_TRACE): first start / last end of the conversion CTAs
+        unsigned long long* d; bool on;
+        __device__ Stamp(unsigned long long* dbg) : d(dbg), on(dbg && threadIdx.x == 0) { if (on) atomicMin(d + 6, gtime()); }
+        __device__ ~Stamp() { if (on) atomicMax(d + 7, gtime()); }
+    };
     if (interleave) {
         if (b < 3u * gain_blocks) {
             if (b % 3u == 0u) gain_body(gp, s_dyn_nrm, gain_blocks, b / 3u);
-            else convert_body(cp, (int)(b - (b / 3u + 1u)));
-        } else
-            convert_body(cp, (int)(b - gain_blocks));
+            else { Stamp st(gp.dbg_trace); convert_body(cp, (int)(b - (b / 3u + 1u))); }
+        } else { Stamp st(gp.dbg_trace); convert_body(cp, (int)(b - gain_blocks)); }
     } else if (b < gain_blocks) gain_body(gp, s_dyn_nrm, gain_blocks, b);
-    else convert_body(cp, (int)(b - gain_blocks));
+    else { Stamp st(gp.dbg_trace); convert_body(cp, (int)(b - gain_blocks)); }
 }
 
 void launch_convert_gain(const ConvertParams& cp, const GainParams* gp, cudaStream_t s)
 {
     static const GainParams none = {};
     const unsigned gb = gp ? (unsigned)gp->grid : 0u, cb = (unsigned)(cp.grid_x * cp.grid_y * cp.n);
-    const size_t smem = gp ? (size_t)gp->n * GAIN_PX * sizeof(double) : 0;
+    const size_t smem = gp ? (size_t)gp->n * GAIN_PX * sizeof(unsigned long long) : 0;
     static const int mode = [] { const char* e = getenv("OCTVR_GAIN_INTERLEAVE"); return e ? atoi(e) : 1; }();   // diagnostic: 0 = gain CTAs first
     k_convert_gain<<<gb + cb, 256, smem, s>>>(cp, gp ? *gp : none, gb, (mode && gb > 0 && cb >= 2u * gb) ? 1u : 0u);
 }

@@ -34,8 +34,8 @@ struct GainParams {
     uint32_t total;            // sum of sw*sh
     const uint8_t* smask;      // linearly resized masks (mapper.cpp:113-114)
     const uint2* gcoord;       // NEAREST-resized sample (mapper.cpp:235-237): x = (ix+1) | (iy+1)<<16 of the top-left tap, y = fx|fy<<5|flags
-    const uint4* samples;      // the same entries regrouped per canvas chunk: {entry.x, entry.y, camera | local pixel << 8, 0}
-    const int2* chunks;        // [grid]: {first sample, samples (<= 256)} of up to 128 consecutive canvas pixels
+    const uint4* samples;      // the same entries regrouped per canvas chunk (512 slots each): {entry.x, entry.y, camera | local pixel << 8, 0}
+    const int2* chunks;        // [grid] (unused)
     unsigned long long* totals;   // [n_pairs][5] exact integer sums (count, hi/lo of sum_i, hi/lo of sum_j); zeroed by the last CTA
     int cx0, cy0, cw, ch;      // working-scale canvas = union of the scaled ROIs
     int n_pairs, grid;         // pairs (i<=j); CTAs launched
@@ -45,7 +45,9 @@ struct GainParams {
     float* gain_f32;           // [n] verified f32 multiplier
     int* gain_flag;            // [n] 1 -> use the LUT
     uint8_t* gain_lut;         // [n][256] exact sat_u8(rint(v*g)) in f64
-    unsigned long long* dbg;   // optional: %globaltimer stamps of the last CTA (start, ticket, reduced, solved, done)
+    unsigned long long* dbg;   // optional: %globaltimer stamps of the last CTA (start, ticket, reduced, solved, done), [5] first gain CTA start,
+    unsigned long long* dbg_trace;   // == dbg when OCTVR_GAIN_TRACE is set: the conversion CTAs stamp [6] first start, [7] last end, gain CTA c < 1024 stamps
+                                     //   [8 + 6c ..]: start, samples loaded, norms done, pair sums done, fence done
 };
 // gp == nullptr: conversion only
 void launch_convert_gain(const ConvertParams& cp, const GainParams* gp, cudaStream_t s);

@@ -611,13 +611,23 @@ static void build_mapper(octvr_mapper& m, const octvr_template& t, const int* in
             x1 = std::max(x1, g.cam[i].sx + g.cam[i].sw); y1 = std::max(y1, g.cam[i].sy + g.cam[i].sh);
         }
         g.cx0 = x0; g.cy0 = y0; g.cw = x1 - x0; g.ch = y1 - y0;
-        // samples regrouped per canvas chunk (<= 128 pixels, <= 256 samples): one CTA per chunk, one thread per sample;
-        // every chunk owns 256 sample slots (empty ones all ones), so a thread finds its sample without a chunk table
+        // samples regrouped per canvas chunk (<= 256 pixels, <= 512 samples): one CTA per chunk, two samples per thread;
+        // every chunk owns 512 sample slots (empty ones all ones), so a thread finds its samples without a chunk table
+        constexpr int CH_PX = 256, CH_SAMPLES = 512;       // kernels.cu: GAIN_PX, GAIN_BLK * GAIN_SPT
         std::vector<uint4> samples;
         {
             const uint4 empty = make_uint4(0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu);
             size_t first = 0; int npx = 0, cnt = 0;
-            auto close = [&]() { if (cnt) { samples.resize(first + 256, empty); first = samples.size(); } npx = 0; cnt = 0; };
+            // a chunk's samples are stored camera by camera (pixels in canvas order within a camera): the 32 lanes of a warp then
+            // gather from one plane along one curve, i.e. from 2-3 cache lines per load instead of ~10 (the gather phase of the
+            // statistics is bound by L1 wavefronts: 24 scattered byte loads per thread)
+            auto close = [&]() {
+                if (cnt) {
+                    std::stable_sort(samples.begin() + first, samples.end(), [](const uint4& a, const uint4& b) { return (a.z & 255u) < (b.z & 255u); });
+                    samples.resize(first + CH_SAMPLES, empty); first = samples.size();
+                }
+                npx = 0; cnt = 0;
+            };
             std::vector<uint4> here;
             for (int pix = 0; pix < g.cw * g.ch; pix++) {
                 const int X = g.cx0 + pix % g.cw, Y = g.cy0 + pix / g.cw;
@@ -631,14 +641,14 @@ static void build_mapper(octvr_mapper& m, const octvr_template& t, const int* in
                     here.push_back(make_uint4(e.x, e.y, (uint32_t)i, 0u));
                 }
                 if (here.empty()) continue;
-                if (npx == 128 || cnt + (int)here.size() > 256) close();
+                if (npx == CH_PX || cnt + (int)here.size() > CH_SAMPLES) close();
                 for (uint4 s : here) { s.z |= (uint32_t)npx << 8; samples.push_back(s); cnt++; }
                 npx++;
             }
             close();
-            if (samples.empty()) samples.resize(256, empty);
+            if (samples.empty()) samples.resize(CH_SAMPLES, empty);
         }
-        std::vector<int2> chunks(samples.size() / 256, make_int2(0, 0));
+        std::vector<int2> chunks(samples.size() / CH_SAMPLES, make_int2(0, 0));
         g.grid = (int)chunks.size();
         m.d_smask = dev_upload(smask.data(), smask.size());
         m.d_gcoord = dev_upload(gcoord.data(), gcoord.size());
@@ -654,7 +664,8 @@ static void build_mapper(octvr_mapper& m, const octvr_template& t, const int* in
         m.d_gain_lut = dev_alloc<uint8_t>(MAX_CAMS * 256, true);
         OB_CUDA(cudaMallocHost(&m.h_gains, sizeof(double) * MAX_CAMS));
         g.smask = m.d_smask; g.gcoord = m.d_gcoord; g.partial = m.d_partial; g.ticket = m.d_ticket;
-        m.d_dbg = dev_alloc<unsigned long long>(8, true); g.dbg = m.d_dbg;
+        m.d_dbg = dev_alloc<unsigned long long>(8 + 2 * 4096, true); g.dbg = m.d_dbg;
+        g.dbg_trace = getenv("OCTVR_GAIN_TRACE") ? m.d_dbg : nullptr;
         g.gains = m.d_gains; g.gain_f32 = m.d_gain_f32; g.gain_flag = m.d_gain_flag; g.gain_lut = m.d_gain_lut;
         m.table_bytes += (int64_t)(samples.size() * sizeof(uint4) + chunks.size() * sizeof(int2));
     }
@@ -971,6 +982,19 @@ octvr_status octvr_mapper_debug_gain_ns(octvr_mapper* m, unsigned long long* out
         OB_CHECK(m && out6 && m->d_dbg, "no gain stage");
         OB_CUDA(cudaDeviceSynchronize());
         OB_CUDA(cudaMemcpy(out6, m->d_dbg, 6 * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
+    });
+}
+
+octvr_status octvr_mapper_debug_gain_trace(octvr_mapper* m, unsigned long long* out, int n)
+{
+    // diagnostics only: the first n (<= 8 + 2 * 4096) words of the gain kernel's stamp buffer; [6] is reset to "never"
+    return guard([&] {
+        OB_CHECK(m && out && m->d_dbg && n > 0 && n <= 8 + 2 * 4096, "no gain stage");
+        OB_CUDA(cudaDeviceSynchronize());
+        OB_CUDA(cudaMemcpy(out, m->d_dbg, (size_t)n * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
+        const unsigned long long never = ~0ull, zero = 0ull;
+        OB_CUDA(cudaMemcpy(m->d_dbg + 6, &never, 8, cudaMemcpyHostToDevice));
+        OB_CUDA(cudaMemcpy(m->d_dbg + 7, &zero, 8, cudaMemcpyHostToDevice));
     });
 }
 

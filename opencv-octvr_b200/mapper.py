@@ -246,6 +246,11 @@ class Mapper:
         check(lib().octvr_mapper_debug_gain_ns(self._h, a))
         return list(a)
 
+    def debug_gain_trace(self, n=8 + 2 * 4096):
+        a = (C.c_ulonglong * n)()
+        check(lib().octvr_mapper_debug_gain_trace(self._h, a, n))
+        return list(a)
+
     def debug_ring(self):
         """counters of K_blend_ring's TMA ring (diagnostics; needs a -DRING_DEBUG=1 build)."""
         a = (C.c_ulonglong * 8)()
