@@ -31,6 +31,7 @@ template <class F> inline octvr_status guard(F&& f)
     try { f(); return OCTVR_OK; }
     catch (const Error& e) { set_last_error(e.what()); return e.code; }
     catch (const std::exception& e) { set_last_error(e.what()); return OCTVR_ERR_INVALID; }
+    catch (...) { set_last_error("unknown exception"); return OCTVR_ERR_INVALID; }
 }
 
 // ---- host images ------------------------------------------------------------

@@ -1,6 +1,7 @@
 // csrc/json.h -- minimal JSON reader for the octvr camera configs (schema: apps/octvr/dump.cpp:71-96,
 // modules/octvr/src/camera.cpp:49-135 and the per-model constructors under src/cameras/).
 #pragma once
+#include <charconv>
 #include "common.h"
 #include <cctype>
 #include <cstdlib>
@@ -58,8 +59,12 @@ class JsonParser {
     const char* p; const char* e;
     void ws() { while (p < e && std::isspace((unsigned char)*p)) p++; }
     [[noreturn]] void bad(const char* m) { fail(OCTVR_ERR_FORMAT, std::string("config: JSON parse error: ") + m); }
+    int depth = 0;
+    struct Nest { int& d; explicit Nest(int& d_) : d(d_) { ++d; } ~Nest() { --d; } };
     Json value()
     {
+        Nest nest(depth);
+        if (depth > 64) bad("nesting deeper than 64 levels");          // recursion bound: a hostile config must not overflow the stack
         ws();
         if (p >= e) bad("unexpected end");
         Json j;
@@ -107,11 +112,23 @@ class JsonParser {
         else if (!strncmp_(p, "false")) { j.kind = Json::Bool; j.b = false; p += 5; }
         else if (!strncmp_(p, "null")) { j.kind = Json::Null; p += 4; }
         else {
-            char* end = nullptr;
+            // JSON number grammar only (no inf / nan / hex), parsed independently of the process locale (a host application
+            // may have called setlocale): std::from_chars is correctly rounded like rapidjson's full-precision parse
+            const char* q = p;
+            if (q < e && *q == '-') q++;
+            if (q >= e || !std::isdigit((unsigned char)*q)) bad("value expected");
+            while (q < e && std::isdigit((unsigned char)*q)) q++;
+            if (q < e && *q == '.') { q++; if (q >= e || !std::isdigit((unsigned char)*q)) bad("digit expected after '.'"); while (q < e && std::isdigit((unsigned char)*q)) q++; }
+            if (q < e && (*q == 'e' || *q == 'E')) {
+                q++;
+                if (q < e && (*q == '+' || *q == '-')) q++;
+                if (q >= e || !std::isdigit((unsigned char)*q)) bad("digit expected in exponent");
+                while (q < e && std::isdigit((unsigned char)*q)) q++;
+            }
             j.kind = Json::Num;
-            j.num = std::strtod(p, &end);        // correctly rounded, like rapidjson's full-precision parse of these configs
-            if (end == p) bad("value expected");
-            p = end;
+            const auto res = std::from_chars(p, q, j.num);
+            if (res.ec != std::errc() || res.ptr != q) bad("number out of range");
+            p = q;
         }
         return j;
     }

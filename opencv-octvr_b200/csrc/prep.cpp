@@ -2,6 +2,7 @@
 #include "prep.h"
 #include <algorithm>
 #include <climits>
+#include <cstring>
 #include <cmath>
 #include <thread>
 
@@ -317,28 +318,43 @@ void quantise_map(const Img<float>& map1, const Img<float>& map2, int src_w, int
 
 
 // ------------------------------------------------------------------------------------------------
-// fill_poly_u8: cv::fillPoly restated (drawing.cpp).  XY_SHIFT = 16.
+// fill_poly_u8: the pixels cv::fillPoly sets (imgproc/src/drawing.cpp), written as a plain scan-line rasteriser.
+// What has to match the reference, and is pinned by 310 reference-drawn polygons (tests/golden/fillpoly.npz):
+//   * edges live in 16.16 fixed point; an edge from (px, py) to (qx, qy), py != qy, starts at the x of its upper end and
+//     moves by trunc((qx - px) * 65536 / (qy - py)) per row; it covers the rows [min y, max y) (drawing.cpp:1195-1248);
+//   * on a row, the crossings are ordered by x; an edge that starts on the row goes in front of older crossings with
+//     the same x, later ties keep their order; consecutive crossings pair up into spans [ceil(xa), floor(xb)]
+//     (drawing.cpp:1261-1404);
+//   * rows above the image are walked (the crossings still move) but not drawn;
+//   * the outline is drawn with 8-connected lines through the integer vertices, clipped like cv::clipLine
+//     (drawing.cpp:80-136): an end point outside is first moved along the line onto the top / bottom image row it
+//     violates, then onto the left / right column, with truncating integer division at each move.
 // ------------------------------------------------------------------------------------------------
 namespace {
-// cv::clipLine(Size, pt1, pt2), drawing.cpp:80-136
+// Segment (ax, ay) - (bx, by) against [0, w) x [0, h).  false: nothing of it is inside.
 bool clip_line(int w, int h, int& ax, int& ay, int& bx, int& by)
 {
     if (w <= 0 || h <= 0) return false;
-    const int64_t right = w - 1, bottom = h - 1;
-    int64_t x1 = ax, y1 = ay, x2 = bx, y2 = by;
-    int c1 = (x1 < 0) + (x1 > right) * 2 + (y1 < 0) * 4 + (y1 > bottom) * 8;
-    int c2 = (x2 < 0) + (x2 > right) * 2 + (y2 < 0) * 4 + (y2 > bottom) * 8;
-    if ((c1 & c2) == 0 && (c1 | c2) != 0) {
-        int64_t a;
-        if (c1 & 12) { a = c1 < 8 ? 0 : bottom; x1 += (a - y1) * (x2 - x1) / (y2 - y1); y1 = a; c1 = (x1 < 0) + (x1 > right) * 2; }
-        if (c2 & 12) { a = c2 < 8 ? 0 : bottom; x2 += (a - y2) * (x2 - x1) / (y2 - y1); y2 = a; c2 = (x2 < 0) + (x2 > right) * 2; }
-        if ((c1 & c2) == 0 && (c1 | c2) != 0) {
-            if (c1) { a = c1 == 1 ? 0 : right; y1 += (a - x1) * (y2 - y1) / (x2 - x1); x1 = a; c1 = 0; }
-            if (c2) { a = c2 == 1 ? 0 : right; y2 += (a - x2) * (y2 - y1) / (x2 - x1); x2 = a; c2 = 0; }
-        }
-        ax = (int)x1; ay = (int)y1; bx = (int)x2; by = (int)y2;
+    const int64_t xmax = w - 1, ymax = h - 1;
+    struct P { int64_t x, y; } p{ ax, ay }, q{ bx, by };
+    enum { LEFT = 1, RIGHT = 2, ABOVE = 4, BELOW = 8 };
+    auto side_x = [&](const P& v) { return (v.x < 0 ? LEFT : 0) | (v.x > xmax ? RIGHT : 0); };
+    auto side_y = [&](const P& v) { return (v.y < 0 ? ABOVE : 0) | (v.y > ymax ? BELOW : 0); };
+    int cp = side_x(p) | side_y(p), cq = side_x(q) | side_y(q);
+    if (cp & cq) return false;                              // both beyond the same border
+    if ((cp | cq) == 0) return true;                        // both inside
+    // rows first: each end point that is above / below slides onto that row (the other end point as it is at that moment)
+    auto to_row = [&](P& v, const P& o, int code) { const int64_t row = (code & ABOVE) ? 0 : ymax; v.x += (row - v.y) * (o.x - v.x) / (o.y - v.y); v.y = row; };
+    if (cp & (ABOVE | BELOW)) { to_row(p, q, cp); cp = side_x(p); }
+    if (cq & (ABOVE | BELOW)) { to_row(q, p, cq); cq = side_x(q); }
+    if (cp & cq) return false;
+    if (cp | cq) {                                          // then columns
+        auto to_col = [&](P& v, const P& o, int code) { const int64_t col = (code & LEFT) ? 0 : xmax; v.y += (col - v.x) * (o.y - v.y) / (o.x - v.x); v.x = col; };
+        if (cp) to_col(p, q, cp);
+        if (cq) to_col(q, p, cq);
     }
-    return (c1 | c2) == 0;
+    ax = (int)p.x; ay = (int)p.y; bx = (int)q.x; by = (int)q.y;
+    return true;
 }
 // Line(img, pt1, pt2, color, 8) = cv::LineIterator(img, pt1, pt2, 8, left_to_right = true), drawing.cpp:142-236, 238-265:
 // a Bresenham walk along the major axis, drawn from the left end point
@@ -362,108 +378,70 @@ void line8(uint8_t* img, int w, int h, int ax, int ay, int bx, int by, uint8_t v
         else { x += 1; if (diag) y += ystep; }
     }
 }
-struct Edge { int y0, y1, x, dx; Edge* next; };
+struct Crossing { int x, step, y_end; };                  // an edge on the current row: 16.16 x, x step per row, first row it no longer covers
+struct PolyEdge { int y_begin, y_end, x, step; };
 }  // namespace
 
 void fill_poly_u8(uint8_t* img, int w, int h, const int* pts, int npts, uint8_t val)
 {
     if (npts <= 0) return;
-    const int SH = 16, ONE = 1 << SH;
-    std::vector<Edge> edges;
-    edges.reserve((size_t)npts + 1);
-    // CollectPolyEdges, drawing.cpp:1195-1248 (shift = 0, no offset): outline + one table entry per non-horizontal edge
-    int px = pts[2 * (npts - 1)] << SH, py = pts[2 * (npts - 1) + 1];
-    for (int i = 0; i < npts; i++) {
-        const int qx = pts[2 * i] << SH, qy = pts[2 * i + 1];
-        line8(img, w, h, (px + (ONE >> 1)) >> SH, py, (qx + (ONE >> 1)) >> SH, qy, val);
-        if (py != qy) {
-            Edge e;
-            if (py < qy) { e.y0 = py; e.y1 = qy; e.x = px; } else { e.y0 = qy; e.y1 = py; e.x = qx; }
-            e.dx = (qx - px) / (qy - py);
-            e.next = nullptr;
-            edges.push_back(e);
-        }
-        px = qx; py = qy;
+    constexpr int FRAC = 16, UNIT = 1 << FRAC;
+    // outline + edge table
+    std::vector<PolyEdge> table;
+    table.reserve((size_t)npts);
+    for (int i = 0, j = npts - 1; i < npts; j = i++) {      // edge j -> i
+        const int x0 = pts[2 * j], y0 = pts[2 * j + 1], x1 = pts[2 * i], y1 = pts[2 * i + 1];
+        line8(img, w, h, x0, y0, x1, y1, val);
+        if (y0 == y1) continue;                             // horizontal edges only contribute their outline
+        const int fx0 = x0 * UNIT, fx1 = x1 * UNIT;
+        PolyEdge e;
+        e.step = (fx1 - fx0) / (y1 - y0);
+        if (y0 < y1) { e.y_begin = y0; e.y_end = y1; e.x = fx0; } else { e.y_begin = y1; e.y_end = y0; e.x = fx1; }
+        table.push_back(e);
     }
-    // FillEdgeCollection, drawing.cpp:1261-1404
-    const int total = (int)edges.size();
-    if (total < 2) return;
-    int y_max = INT_MIN, x_max = INT_MIN, y_min = INT_MAX, x_min = INT_MAX;
-    for (const Edge& e : edges) {
-        const int x1 = e.x + (e.y1 - e.y0) * e.dx;
-        y_min = std::min(y_min, e.y0); y_max = std::max(y_max, e.y1);
-        x_min = std::min(x_min, std::min(e.x, x1)); x_max = std::max(x_max, std::max(e.x, x1));
+    if (table.size() < 2) return;
+    // bounding box of the edges as they will be walked; nothing to do if it misses the image
+    int top = INT_MAX, bottom = INT_MIN, left = INT_MAX, right = INT_MIN;
+    for (const PolyEdge& e : table) {
+        const int x_last = e.x + (e.y_end - e.y_begin) * e.step;
+        top = std::min(top, e.y_begin); bottom = std::max(bottom, e.y_end);
+        left = std::min(left, std::min(e.x, x_last)); right = std::max(right, std::max(e.x, x_last));
     }
-    if (y_max < 0 || y_min >= h || x_max < 0 || x_min >= (w << SH)) return;
-    std::sort(edges.begin(), edges.end(), [](const Edge& a, const Edge& b) {
-        return a.y0 - b.y0 ? a.y0 < b.y0 : a.x - b.x ? a.x < b.x : a.dx < b.dx;
+    if (bottom < 0 || top >= h || right < 0 || left >= w * UNIT) return;
+    std::sort(table.begin(), table.end(), [](const PolyEdge& a, const PolyEdge& b) {
+        if (a.y_begin != b.y_begin) return a.y_begin < b.y_begin;
+        if (a.x != b.x) return a.x < b.x;
+        return a.step < b.step;
     });
-    Edge head;                                   // list head of the active edges; also the sentinel appended to the table
-    head.y0 = INT_MAX; head.y1 = 0; head.x = 0; head.dx = 0; head.next = nullptr;
-    edges.push_back(head);                       // no insertion after this point: pointers into the vector stay valid
-    int i = 0;
-    Edge* e = &edges[0];
-    y_max = std::min(y_max, h);
-    for (int y = e->y0; y < y_max; y++) {
-        Edge *last, *prelast, *keep_prelast;
-        int sort_flag = 0, draw = 0;
-        const bool clipline = y < 0;
-        prelast = &head;
-        last = head.next;
-        while (last || e->y0 == y) {
-            if (last && last->y1 == y) {         // the edge ends on this row: drop it
-                prelast->next = last->next;
-                last = last->next;
-                continue;
-            }
-            keep_prelast = prelast;
-            if (last && (e->y0 > y || last->x < e->x)) {     // next edge of the active list
-                prelast = last;
-                last = last->next;
-            } else if (i < total) {              // an edge starts on this row: insert it
-                prelast->next = e;
-                e->next = last;
-                prelast = e;
-                e = &edges[++i];
-            } else
-                break;
-            if (draw) {
-                if (!clipline) {
-                    int x1 = keep_prelast->x, x2 = prelast->x;
-                    if (x1 > x2) std::swap(x1, x2);
-                    x1 = (x1 + ONE - 1) >> SH;
-                    x2 = x2 >> SH;
-                    if (x1 < w && x2 >= 0) {
-                        if (x1 < 0) x1 = 0;
-                        if (x2 >= w) x2 = w - 1;
-                        for (int x = x1; x <= x2; x++) img[(size_t)y * w + x] = val;
-                    }
-                }
-                keep_prelast->x += keep_prelast->dx;
-                prelast->x += prelast->dx;
-            }
-            draw ^= 1;
+    std::vector<Crossing> row, merged;
+    size_t next = 0;                                        // first edge of the table that has not started yet
+    for (int y = top; y < std::min(bottom, h); y++) {
+        // crossings of this row: the ones carried over that have not ended, merged (by x) with the edges starting here;
+        // a starting edge goes in front of carried crossings with the same x
+        merged.clear();
+        size_t c = 0;
+        auto skip_ended = [&]() { while (c < row.size() && row[c].y_end == y) c++; };
+        skip_ended();
+        while (c < row.size() || (next < table.size() && table[next].y_begin == y)) {
+            const bool starts = next < table.size() && table[next].y_begin == y;
+            if (c < row.size() && (!starts || row[c].x < table[next].x)) { merged.push_back(row[c++]); skip_ended(); }
+            else { merged.push_back(Crossing{ table[next].x, table[next].step, table[next].y_end }); next++; }
         }
-        // keep the active list ordered by x (bubble sort, as in the reference: the order decides which spans pair up)
-        keep_prelast = nullptr;
-        do {
-            prelast = &head;
-            last = head.next;
-            while (last != keep_prelast && last->next != nullptr) {
-                Edge* te = last->next;
-                if (last->x > te->x) {
-                    prelast->next = te;
-                    last->next = te->next;
-                    te->next = last;
-                    prelast = te;
-                    sort_flag = 1;
-                } else {
-                    prelast = last;
-                    last = te;
+        // spans between consecutive pairs; every paired crossing moves on to the next row
+        for (size_t k = 0; k + 1 < merged.size(); k += 2) {
+            Crossing& a = merged[k], &b = merged[k + 1];
+            if (y >= 0) {
+                const int lo = std::min(a.x, b.x), hi = std::max(a.x, b.x);
+                int xa = (lo + UNIT - 1) >> FRAC, xb = hi >> FRAC;
+                if (xa < w && xb >= 0) {
+                    xa = std::max(xa, 0); xb = std::min(xb, w - 1);
+                    if (xa <= xb) memset(img + (size_t)y * w + xa, val, (size_t)(xb - xa + 1));
                 }
             }
-            keep_prelast = prelast;
-        } while (sort_flag && keep_prelast != head.next && keep_prelast != &head);
+            a.x += a.step; b.x += b.step;
+        }
+        std::stable_sort(merged.begin(), merged.end(), [](const Crossing& a, const Crossing& b) { return a.x < b.x; });
+        row.swap(merged);
     }
 }
 

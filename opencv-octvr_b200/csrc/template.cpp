@@ -37,7 +37,9 @@ struct Reader {
     TInput input()
     {
         TInput in;
-        in.roi.x = (int)i64(); in.roi.y = (int)i64(); in.roi.w = (int)i64(); in.roi.h = (int)i64();
+        int64_t v[4];
+        for (auto& q : v) { q = i64(); if (q < 0 || q > (1 << 20)) fail(OCTVR_ERR_FORMAT, "Invalid data file (ROI out of range)"); }   // before narrowing
+        in.roi.x = (int)v[0]; in.roi.y = (int)v[1]; in.roi.w = (int)v[2]; in.roi.h = (int)v[3];
         in.map1 = mat<float>(5); in.map2 = mat<float>(5); in.mask = mat<uint8_t>(0); in.vignette = mat<float>(5);
         return in;
     }
@@ -67,7 +69,9 @@ octvr_template* template_from_dat(const uint8_t* bytes, size_t n)
     if (n < 5 || memcmp(bytes, "VRv11", 5) != 0) fail(OCTVR_ERR_FORMAT, "Invalid data file (version does not match)");
     Reader r{ bytes, n, 5 };
     std::unique_ptr<octvr_template> t(new octvr_template);
-    t->out_w = (int)r.i64(); t->out_h = (int)r.i64();
+    const int64_t ow = r.i64(), oh = r.i64();
+    if (ow <= 0 || oh <= 0 || ow > (1 << 20) || oh > (1 << 20)) fail(OCTVR_ERR_FORMAT, "Invalid data file (output size)");
+    t->out_w = (int)ow; t->out_h = (int)oh;
     int64_t ni = r.i64();
     if (ni < 0 || ni > 4096) fail(OCTVR_ERR_FORMAT, "Invalid data file (input count)");
     for (int64_t i = 0; i < ni; i++) t->inputs.push_back(r.input());
@@ -77,6 +81,11 @@ octvr_template* template_from_dat(const uint8_t* bytes, size_t n)
     for (int64_t i = 0; i < no; i++) t->overlays.push_back(r.input());
     for (auto& in : t->inputs) check_input(in, t->out_w, t->out_h);
     for (auto& in : t->overlays) check_input(in, t->out_w, t->out_h);
+    // a seam mask is indexed with ROI coordinates by the multiband set-up: it must be absent or exactly ROI-sized
+    for (size_t i = 0; i < t->inputs.size(); i++) {
+        const Img<uint8_t>& sm = t->seam_masks[i];
+        if (!sm.empty() && (sm.w != t->inputs[i].roi.w || sm.h != t->inputs[i].roi.h)) fail(OCTVR_ERR_FORMAT, "Invalid data file (seam mask size != ROI size)");
+    }
     return t.release();
 }
 
