@@ -83,6 +83,8 @@ void         octvr_template_destroy(octvr_template* t);
  * packed "U|V side by side under Y" layout of mapper.hpp:75-83: u = base + H*pitch, v = u + W/2,
  * all pitches = W); 2 = semi-planar NV12 (v = u + 1).  Width and height must be even
  * (async.cpp:44-46). */
+#define OCTVR_FMT_RGB24 3   /* uv_pixel_stride value: y = packed 8UC3 R,G,B rows (y_pitch >= 3 W), u / v ignored */
+#define OCTVR_FMT_BGR24 4   /* same with B,G,R byte order (cv::Mat CV_8UC3 as cv::imread / cv::VideoCapture deliver it) */
 typedef struct octvr_frame {
     uint8_t* y; uint8_t* u; uint8_t* v;
     size_t y_pitch, u_pitch, v_pitch;

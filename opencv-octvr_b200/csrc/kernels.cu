@@ -54,6 +54,12 @@ __device__ __forceinline__ uint32_t yuv_px(uint32_t Y, int ruv, int guv, int buv
 // one converted source pixel straight from the input planes (same arithmetic as K_convert) -- used by the gain kernel
 __device__ __forceinline__ uint32_t source_px(const CamSrc& c, int x, int y)
 {
+    if (c.rgb) {                                            // packed RGB24 / BGR24: no colour conversion
+        const size_t o = (size_t)y * c.y_pitch + 3 * (size_t)x;
+        uint32_t px = (uint32_t)__ldg(c.y + o) | ((uint32_t)__ldg(c.u + o) << 8) | ((uint32_t)__ldg(c.v + o) << 16);
+        if (c.vignette) px = vignette_rgbx(px, __ldg(c.vignette + (size_t)y * c.w + x));
+        return px;
+    }
     const int Y = __ldg(c.y + (size_t)y * c.y_pitch + x);
     const int u = (int)__ldg(c.u + (size_t)(y >> 1) * c.u_pitch + (size_t)(x >> 1) * c.uv_step) - 128;
     const int v = (int)__ldg(c.v + (size_t)(y >> 1) * c.v_pitch + (size_t)(x >> 1) * c.uv_step) - 128;
@@ -76,6 +82,26 @@ __device__ __forceinline__ void convert_body(const ConvertParams& p, int block)
     const int y0 = (by << 4) + (ty << 1);
     if (x0 >= c.w || y0 >= c.h) return;
     const int w = c.w;
+    if (c.rgb) {                                            // packed RGB24 / BGR24 -> RGBX: a byte shuffle (+ vignette)
+        #pragma unroll
+        for (int r = 0; r < 2; r++) {
+            uint32_t px[8];
+            #pragma unroll
+            for (int k = 0; k < 8; k++) {
+                const size_t o = (size_t)(y0 + r) * c.y_pitch + 3 * (size_t)min(x0 + k, w - 1);
+                px[k] = (uint32_t)__ldg(c.y + o) | ((uint32_t)__ldg(c.u + o) << 8) | ((uint32_t)__ldg(c.v + o) << 16);
+                if (c.vignette) px[k] = vignette_rgbx(px[k], __ldg(c.vignette + (size_t)(y0 + r) * w + min(x0 + k, w - 1)));
+            }
+            uint32_t* o = c.rgbx + (size_t)(y0 + r) * w + x0;
+            if (x0 + 8 <= w && w % 4 == 0) {
+                const uint64_t pol = policy_evict_last();
+                st_v4_hint(o, make_uint4(px[0], px[1], px[2], px[3]), pol);
+                st_v4_hint(o + 4, make_uint4(px[4], px[5], px[6], px[7]), pol);
+            } else
+                for (int k = 0; k < 8 && x0 + k < w; k++) o[k] = px[k];
+        }
+        return;
+    }
     const uint8_t* yr0 = c.y + (size_t)y0 * c.y_pitch + x0;
     const uint8_t* yr1 = yr0 + c.y_pitch;
     const uint8_t* ur = c.u + (size_t)(y0 >> 1) * c.u_pitch + (size_t)(x0 >> 1) * c.uv_step;
@@ -357,6 +383,20 @@ __device__ void gain_tables(const GainParams& p, const double* sg)
     }
 }
 
+// the four taps of a gain sample one by one (vignette maps, packed RGB input); kept out of line so that its registers do
+// not weigh on the common path
+__device__ __noinline__ uint4 gain_taps_slow(const CamSrc& sc, uint32_t ex, uint32_t ey)
+{
+    uint32_t t[4] = { 0u, 0u, 0u, 0u };
+    const int ix = (int)(ex & 0xFFFFu) - 1, iy = (int)(ex >> 16) - 1;
+    const uint32_t bt = (ey & C_BORDER) ? (ey >> C_TAP_SHIFT) : 15u;
+    if (bt & 1u) t[0] = source_px(sc, ix, iy);
+    if (bt & 2u) t[1] = source_px(sc, ix + 1, iy);
+    if (bt & 4u) t[2] = source_px(sc, ix, iy + 1);
+    if (bt & 8u) t[3] = source_px(sc, ix + 1, iy + 1);
+    return make_uint4(t[0], t[1], t[2], t[3]);
+}
+
 // Working-scale statistics (mapper.cpp:94-99: a ~0.1 Mpix canvas) + gain solve in ONE launch, written for latency.
 // A CTA takes one chunk of the canvas: up to 256 pixels and the (at most 512) samples (pixel, camera) whose
 // working-scale mask is 255 there (CPU compensator's intersect rule, exposure_compensate.cpp:71-78,112), listed by the
@@ -407,7 +447,7 @@ __device__ __forceinline__ void gain_body(const GainParams& p, unsigned long lon
         for (int h = 0; h < GAIN_SPT; h++) {
             const bool valid = sm[h].z != 0xFFFFFFFFu && (sm[h].y & C_VALID);
             const CamSrc& sc = p.src[valid ? (sm[h].z & 255u) : 0u];
-            slow[h] = valid && sc.vignette != nullptr;       // vignette maps: the per-tap path below
+            slow[h] = valid && (sc.vignette != nullptr || sc.rgb);   // vignette maps, packed RGB input: the per-tap path below
             bits[h] = !valid || slow[h] ? 0u : (sm[h].y & C_BORDER) ? (sm[h].y >> C_TAP_SHIFT) : 15u;
             const int ix = valid ? (int)(sm[h].x & 0xFFFFu) - 1 : 0, iy = valid ? (int)(sm[h].x >> 16) - 1 : 0;
             #pragma unroll
@@ -426,15 +466,7 @@ __device__ __forceinline__ void gain_body(const GainParams& p, unsigned long lon
                 const uint32_t px = yuv_px((uint32_t)yv[h][k], (1 << 19) + 1673527 * v, (1 << 19) - 852492 * v - 409993 * u, (1 << 19) + 2116026 * u);
                 t[h][k] = ((bits[h] >> k) & 1u) ? px : 0u;
             }
-            if (slow[h]) {
-                const CamSrc& sc = p.src[sm[h].z & 255u];
-                const int ix = (int)(sm[h].x & 0xFFFFu) - 1, iy = (int)(sm[h].x >> 16) - 1;
-                const uint32_t bt = (sm[h].y & C_BORDER) ? (sm[h].y >> C_TAP_SHIFT) : 15u;
-                if (bt & 1u) t[h][0] = source_px(sc, ix, iy);
-                if (bt & 2u) t[h][1] = source_px(sc, ix + 1, iy);
-                if (bt & 4u) t[h][2] = source_px(sc, ix, iy + 1);
-                if (bt & 8u) t[h][3] = source_px(sc, ix + 1, iy + 1);
-            }
+            if (slow[h]) { const uint4 q = gain_taps_slow(p.src[sm[h].z & 255u], sm[h].x, sm[h].y); t[h][0] = q.x; t[h][1] = q.y; t[h][2] = q.z; t[h][3] = q.w; }
         }
         #pragma unroll
         for (int h = 0; h < GAIN_SPT; h++)

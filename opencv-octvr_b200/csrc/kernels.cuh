@@ -8,7 +8,9 @@ namespace ob {
 struct CamSrc {
     const uint8_t* y; const uint8_t* u; const uint8_t* v;
     uint32_t y_pitch, u_pitch, v_pitch;
-    int uv_step;              // 1 planar, 2 NV12
+    int uv_step;              // 1 planar, 2 NV12; packed RGB24 / BGR24 input: 3, with y / u / v = the R / G / B byte of pixel 0 and all
+                              // three pitches = the row pitch (rgb = 1)
+    int rgb;
     int w, h;
     uint32_t* rgbx;           // w*h, pitch = w pixels
     const float* vignette;    // w*h f32 or null

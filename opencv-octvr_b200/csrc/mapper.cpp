@@ -673,8 +673,13 @@ static void build_mapper(octvr_mapper& m, const octvr_template& t, const int* in
 
 }
 
-static void check_frame(const octvr_frame& f, int w, int h, const char* what)
+static void check_frame(const octvr_frame& f, int w, int h, const char* what, bool allow_rgb = false)
 {
+    if (f.uv_pixel_stride == OCTVR_FMT_RGB24 || f.uv_pixel_stride == OCTVR_FMT_BGR24) {       // packed 8UC3 in the y plane
+        OB_CHECK(allow_rgb, "packed RGB / BGR frames are an input format only");
+        OB_CHECK(f.y && f.y_pitch >= (size_t)w * 3, what);
+        return;
+    }
     OB_CHECK(f.y && f.u && f.v, what);
     OB_CHECK(f.y_pitch >= (size_t)w && f.uv_pixel_stride >= 1 && f.uv_pixel_stride <= 2, what);
     OB_CHECK(f.u_pitch >= (size_t)(w / 2) * f.uv_pixel_stride && f.v_pitch >= (size_t)(w / 2) * f.uv_pixel_stride, what);
@@ -702,7 +707,7 @@ void ob::mapper_stitch_internal(octvr_mapper& m, const octvr_frame* in, int n_in
     const int n_all = m.n + m.n_ov;
     OB_CHECK(n_in == n_all, "wrong number of input frames");         // mapper.cpp:208
     OB_CUDA(cudaSetDevice(m.device));
-    for (int i = 0; i < n_all; i++) check_frame(in[i], m.in_w[i], m.in_h[i], "bad input frame");
+    for (int i = 0; i < n_all; i++) check_frame(in[i], m.in_w[i], m.in_h[i], "bad input frame", true);
     if (user_out) check_frame(*user_out, m.scaled_w, m.scaled_h, "bad output frame");
     OB_CHECK(user_out || m.keep_rgb || d_preview, "no output requested");
     if (d_preview) OB_CHECK(preview_w > 0 && preview_h > 0 && preview_pitch >= (size_t)preview_w * 3, "bad preview buffer");
@@ -722,6 +727,12 @@ void ob::mapper_stitch_internal(octvr_mapper& m, const octvr_frame* in, int n_in
         c.y = in[i].y; c.u = in[i].u; c.v = in[i].v;
         c.y_pitch = (uint32_t)in[i].y_pitch; c.u_pitch = (uint32_t)in[i].u_pitch; c.v_pitch = (uint32_t)in[i].v_pitch;
         c.uv_step = in[i].uv_pixel_stride; c.w = m.in_w[i]; c.h = m.in_h[i];
+        if (c.uv_step == OCTVR_FMT_RGB24 || c.uv_step == OCTVR_FMT_BGR24) {     // packed 8UC3 (cv::Mat CV_8UC3 as the tools read it: BGR)
+            OB_CHECK(!m.fused, "the single-kernel path (OCTVR_BLEND=fused) takes 4:2:0 input only");
+            const bool bgr = c.uv_step == OCTVR_FMT_BGR24;
+            c.y = in[i].y + (bgr ? 2 : 0); c.u = in[i].y + 1; c.v = in[i].y + (bgr ? 0 : 2);
+            c.u_pitch = c.v_pitch = c.y_pitch; c.uv_step = 3; c.rgb = 1;
+        }
         c.rgbx = m.fused ? nullptr : m.d_rgbx[i]; c.vignette = m.d_vig[i];
         const bool chroma_ok = c.uv_step == 1
             ? ((uintptr_t)c.u % 4 == 0 && (uintptr_t)c.v % 4 == 0 && c.u_pitch % 4 == 0 && c.v_pitch % 4 == 0)

@@ -150,6 +150,24 @@ def split_packed(t, w, h):
     return t[:h, :w], t[h:h + h // 2, :w // 2], t[h:h + h // 2, w // 2:w]
 
 
+class PackedRGB:
+    """An input frame as packed 8UC3: a (h, w, 3) u8 CUDA tensor in R,G,B (bgr=False) or B,G,R order (cv::Mat CV_8UC3 as
+    cv::imread / cv::VideoCapture deliver it; include/octvr_b200.h OCTVR_FMT_RGB24 / OCTVR_FMT_BGR24).  Accepted by
+    Mapper.stitch in place of a (y, u, v) triple."""
+
+    def __init__(self, tensor, bgr=False):
+        assert tensor.dim() == 3 and tensor.shape[2] == 3 and tensor.stride(2) == 1 and tensor.stride(1) == 3
+        self.tensor, self.bgr = tensor, bgr
+
+    def frame(self):
+        f = Frame()
+        f.y = self.tensor.data_ptr()
+        f.u = f.v = None
+        f.y_pitch, f.u_pitch, f.v_pitch = self.tensor.stride(0), 0, 0
+        f.uv_pixel_stride = 4 if self.bgr else 3
+        return f
+
+
 class Mapper:
     """vr::Mapper (mapper.hpp:29-95).  blend > 0 multiband, < 0 feather border, 0 none."""
 
@@ -183,7 +201,7 @@ class Mapper:
         Asynchronous on `stream` (default: torch's current stream)."""
         torch = self._torch
         s = stream if stream is not None else torch.cuda.current_stream(self.device)
-        fin = (Frame * len(inputs))(*[frame_from_planes(*p) for p in inputs])
+        fin = (Frame * len(inputs))(*[p.frame() if isinstance(p, PackedRGB) else frame_from_planes(*p) for p in inputs])
         fout = frame_from_planes(*output) if output is not None else None
         g = None
         ng = 0
@@ -289,7 +307,7 @@ class AsyncMultiMapper:
 
     def push(self, inputs, output):
         """inputs: list of (y,u,v) host u8 numpy arrays; output: (y,u,v) host arrays to be filled by the matching pop."""
-        fin = (Frame * len(inputs))(*[frame_from_planes(*p) for p in inputs])
+        fin = (Frame * len(inputs))(*[p.frame() if isinstance(p, PackedRGB) else frame_from_planes(*p) for p in inputs])
         fout = frame_from_planes(*output)
         self._keep.append((inputs, output))
         check(lib().octvr_async_push(self._h, fin, len(inputs), C.byref(fout)))
