@@ -2,6 +2,8 @@
 // Follows vr::Camera::Camera (modules/octvr/src/camera.cpp:49-135) and the per-model constructors
 // (src/cameras/*.cpp|hpp); all set-up arithmetic is f64 like the reference.
 #include "camera.h"
+#include <fstream>
+#include <charconv>
 #include "prep.h"
 #include <cmath>
 #include <cstring>
@@ -127,9 +129,21 @@ CamHost camera_from_json(const std::string& type, const Json& o)
                 std::vector<int> pts;
                 for (size_t q = 0; q + 1 < a.size(); q += 2) { pts.push_back((int)a.at(q).number()); pts.push_back((int)a.at(q + 1).number()); }
                 fill_poly_u8(target.data(), mw, mh, pts.data(), (int)pts.size() / 2, 255);
-            } else if (kind == "png")
-                fail(OCTVR_ERR_UNSUPPORTED, "png exclude / include masks are not implemented (they need an image decoder)");
-            else
+            } else if (kind == "png") {
+                // camera.cpp:169-187: cv::imdecode(args, 1); red != 0 -> excluded, green != 0 -> included, whichever list the entry is in
+                const Json& a = area.at("args");
+                std::vector<uint8_t> file(a.size());
+                for (size_t q = 0; q < a.size(); q++) file[q] = (uint8_t)a.at(q).integer();
+                int pw = 0, ph = 0;
+                std::vector<uint8_t> bgr;
+                png_decode_bgr(file.data(), file.size(), pw, ph, bgr);
+                OB_CHECK(!ch.exclude.empty() && pw == m.ex_w && ph == m.ex_h, "png mask: size != the camera's exclude mask (camera.cpp:175; list it under exclude_masks)");
+                OB_CHECK(!ch.include.empty() && m.in_w == pw && m.in_h == ph, "png mask: no include mask of that size");
+                for (size_t q = 0; q < (size_t)pw * ph; q++) {
+                    if (bgr[3 * q + 2]) ch.exclude[q] = 255;
+                    if (bgr[3 * q + 1]) ch.include[q] = 255;
+                }
+            } else
                 fail(OCTVR_ERR_FORMAT, "unknown mask type \"" + kind + "\"");
         }
     };
@@ -197,7 +211,40 @@ CamHost camera_from_json(const std::string& type, const Json& o)
         m.p[8] = correction_radius(rd);
         break; }
     case CAM_OCAM: {          // cameras/ocam_fisheye.cpp:82-110
-        if (o.has("file")) fail(OCTVR_ERR_UNSUPPORTED, "ocam_fisheye \"file\" option: pass pol/invpol inline");
+        if (o.has("file")) {
+            // get_ocam_model (cameras/ocam_fisheye.cpp:19-80), Scaramuzza's calib_results.txt: '#' comment lines, then n + n direct
+            // coefficients, m + m inverse coefficients, centre "xc yc", affine "c d e", image "height width"
+            std::ifstream f(o.at("file").string());
+            if (!f) fail(OCTVR_ERR_INVALID, "ocam_fisheye: cannot open " + o.at("file").string());
+            std::vector<double> v;
+            std::string line;
+            while (std::getline(f, line)) {
+                const size_t b = line.find_first_not_of(" \t\r");
+                if (b == std::string::npos || line[b] == '#') continue;
+                const char* q = line.c_str() + b;
+                for (;;) {
+                    while (*q == ' ' || *q == '\t' || *q == '\r') q++;
+                    if (!*q) break;
+                    const char* e = q;
+                    while (*e && *e != ' ' && *e != '\t' && *e != '\r') e++;
+                    double d = 0;
+                    const auto res = std::from_chars(q, e, d);
+                    if (res.ec != std::errc() || res.ptr != e) fail(OCTVR_ERR_FORMAT, "ocam_fisheye: bad number in the calibration file");
+                    v.push_back(d); q = e;
+                }
+            }
+            size_t k = 0;
+            auto next = [&]() { if (k >= v.size()) fail(OCTVR_ERR_FORMAT, "ocam_fisheye: calibration file too short"); return v[k++]; };
+            m.n_pol = (int)next();
+            OB_CHECK(m.n_pol > 0 && m.n_pol <= 64, "ocam polynomial length");
+            for (int i = 0; i < m.n_pol; i++) m.pol[i] = next();
+            m.n_invpol = (int)next();
+            OB_CHECK(m.n_invpol > 0 && m.n_invpol <= 64, "ocam polynomial length");
+            for (int i = 0; i < m.n_invpol; i++) m.invpol[i] = next();
+            m.p[0] = next(); m.p[1] = next(); m.p[2] = next(); m.p[3] = next(); m.p[4] = next();
+            m.ip[1] = (int)next(); m.ip[0] = (int)next();
+            break;
+        }
         const Json& pol = o.at("pol"); const Json& inv = o.at("invpol");
         m.n_pol = (int)pol.size(); m.n_invpol = (int)inv.size();
         OB_CHECK(m.n_pol > 0 && m.n_pol <= 64 && m.n_invpol > 0 && m.n_invpol <= 64, "ocam polynomial length");

@@ -73,6 +73,46 @@ __device__ D2 fullframe_fwd(const CamModel& c, D2 ll)
     return D2{ rx, ry };
 }
 
+// image_to_obj_single (cameras/fullframe_fisheye_cam.cpp:223-253) with do_reverse_radial_distort (:160-184).  The reference
+// takes the smallest positive real root of the quartic from cv::solvePoly and accepts it only below the correction radius;
+// on [0, r_corr) the polynomial P(r) = (((V3 r + V2) r + V1) r + V0) r rises monotonically from 0, so that root is the
+// solution of P(r) = s / V4 in (0, r_corr) when s / V4 < P(r_corr), and there is none otherwise.  Safeguarded Newton in
+// f64 (same steps as oracle/orc_camera.c ff_reverse_radius).  The crop must be the full image (CV_Assert, checked on the host).
+__device__ D2 fullframe_inv(const CamModel& c, D2 xy)
+{
+    xy.x -= 0.5; xy.y -= 0.5;
+    xy.x *= (double)c.ip[4]; xy.y *= (double)c.ip[5];
+    xy.x -= c.p[1]; xy.y -= c.p[2];
+    if (fabs(xy.x) < 1e-5 && fabs(xy.y) < 1e-5) return D2{ 0, 0 };
+    const double V0 = c.p[3], V1 = c.p[4], V2 = c.p[5], V3 = c.p[6], rc = c.p[8];
+    const double s = sqrt(xy.x * xy.x + xy.y * xy.y), t = s / c.p[7];
+    double r = -1;
+    const double prc = (((V3 * rc + V2) * rc + V1) * rc + V0) * rc;
+    if (t > 0 && t < prc) {
+        double lo = 0, hi = rc;
+        r = t < rc ? t : 0.5 * rc;
+        for (int it = 0; it < 100; it++) {
+            const double f = (((V3 * r + V2) * r + V1) * r + V0) * r - t;
+            if (f == 0) break;
+            if (f > 0) hi = r; else lo = r;
+            const double d = ((4 * V3 * r + 3 * V2) * r + 2 * V1) * r + V0;
+            double rn = r - f / d;
+            if (!(rn > lo && rn < hi)) rn = 0.5 * (lo + hi);
+            if (rn == r) break;
+            r = rn;
+        }
+    }
+    const double scale = (r > 0 && r < rc) ? s / c.p[7] / r : 1000.0;
+    xy.x = xy.x / scale; xy.y = xy.y / scale;
+    const double distance = (double)c.ip[4] / c.p[0];
+    const double alpha = atan2(-xy.y, xy.x);
+    double theta = -xy.y / distance / sin(alpha);
+    if (fabs(sin(alpha)) < 1e-3) theta = -xy.x / distance / cos(alpha);
+    const double lon = atan2(sin(theta) * cos(alpha), cos(theta));
+    const double lat = atan(tan(alpha) * sin(lon));
+    return D2{ lon, lat };
+}
+
 // cameras/ocam_fisheye.cpp:183-244 (world2cam) and :135-166 (cam2world)
 __device__ D2 ocam_fwd(const CamModel& c, D2 ll)
 {
@@ -192,6 +232,7 @@ __device__ D2 model_inv(const CamModel& c, D2 xy)
     case CAM_EQUIRECT:                         // cameras/equirectangular.cpp:31-35
         return D2{ (xy.x - 0.5) * PI_D * 2.0, (c.p[0] - c.p[1]) * xy.y + c.p[1] };
     case CAM_OCAM: return ocam_inv(c, xy);
+    case CAM_FULLFRAME_FISHEYE: return fullframe_inv(c, xy);
     case CAM_STUPIDOVAL: {                     // cameras/stupidoval.hpp:29-35
         const double lat = (0.5 - xy.y) * PI_D, lon = (xy.x - 0.5) * PI_D * 2.0 / cos(lat);
         if (lon < -PI_D || lon > PI_D) return nan2();
@@ -310,7 +351,7 @@ template <class T> struct DevBuf {
 };
 bool output_supported(int type)
 {
-    return type != CAM_PINHOLE && type != CAM_FISHEYE && type != CAM_FULLFRAME_FISHEYE;
+    return type != CAM_PINHOLE && type != CAM_FISHEYE;      // these two have no image_to_obj (camera.hpp:92-103: NotImplemented)
 }
 }  // namespace
 
@@ -324,9 +365,10 @@ octvr_template* template_from_json(const std::string& json, int width, int heigh
     const Json& jo = cfg.at("output");
     static const Json empty_obj = [] { Json j; j.kind = Json::Obj; return j; }();
     CamHost oc = camera_from_json(jo.at("type").string(), jo.has("options") ? jo.at("options") : empty_obj);
-    // pinhole / fisheye have no image_to_obj (throws NotImplemented, camera.hpp:92-103); the fullframe_fisheye
-    // inverse needs cv::solvePoly and is not implemented here
+    // pinhole / fisheye have no image_to_obj (throws NotImplemented, camera.hpp:92-103)
     if (!output_supported(oc.m.type)) fail(OCTVR_ERR_UNSUPPORTED, "this camera model cannot be used as the output model");
+    if (oc.m.type == CAM_FULLFRAME_FISHEYE && !(oc.m.ip[4] == oc.m.ip[0] && oc.m.ip[5] == oc.m.ip[1] && oc.m.ip[2] == 0 && oc.m.ip[3] == 0))
+        fail(OCTVR_ERR_INVALID, "fullframe_fisheye as the output model must not be cropped (fullframe_fisheye_cam.cpp:224)");
 
     // MapperTemplate::MapperTemplate (template.cpp:23-44)
     if (height <= 0 && width <= 0) fail(OCTVR_ERR_FORMAT, "Output width/height invalid");

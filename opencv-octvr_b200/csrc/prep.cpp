@@ -3,6 +3,8 @@
 #include <algorithm>
 #include <climits>
 #include <cstring>
+#include <zlib.h>
+#undef FAR
 #include <cmath>
 #include <thread>
 
@@ -442,6 +444,79 @@ void fill_poly_u8(uint8_t* img, int w, int h, const int* pts, int npts, uint8_t 
         }
         std::stable_sort(merged.begin(), merged.end(), [](const Crossing& a, const Crossing& b) { return a.x < b.x; });
         row.swap(merged);
+    }
+}
+
+
+// ------------------------------------------------------------------------------------------------
+// png_decode_bgr
+// ------------------------------------------------------------------------------------------------
+void png_decode_bgr(const uint8_t* bytes, size_t n, int& w, int& h, std::vector<uint8_t>& bgr)
+{
+    static const uint8_t magic[8] = { 0x89, 'P', 'N', 'G', 0x0D, 0x0A, 0x1A, 0x0A };
+    if (n < 8 || memcmp(bytes, magic, 8) != 0) fail(OCTVR_ERR_FORMAT, "png mask: not a PNG file");
+    auto be32 = [&](size_t o) { return ((uint32_t)bytes[o] << 24) | ((uint32_t)bytes[o + 1] << 16) | ((uint32_t)bytes[o + 2] << 8) | bytes[o + 3]; };
+    int depth = 0, ctype = -1, interlace = 0;
+    std::vector<uint8_t> idat, plte;
+    w = h = 0;
+    for (size_t o = 8; o + 12 <= n;) {
+        const uint32_t len = be32(o);
+        if (len > n - o - 12) fail(OCTVR_ERR_FORMAT, "png mask: truncated chunk");
+        const uint8_t* name = bytes + o + 4, *data = bytes + o + 8;
+        if (!memcmp(name, "IHDR", 4) && len >= 13) {
+            w = (int)be32(o + 8); h = (int)be32(o + 12); depth = data[8]; ctype = data[9]; interlace = data[12];
+        } else if (!memcmp(name, "PLTE", 4)) plte.assign(data, data + len);
+        else if (!memcmp(name, "IDAT", 4)) idat.insert(idat.end(), data, data + len);
+        else if (!memcmp(name, "IEND", 4)) break;
+        o += 12 + (size_t)len;
+    }
+    if (w <= 0 || h <= 0 || w > 65536 || h > 65536 || ctype < 0) fail(OCTVR_ERR_FORMAT, "png mask: bad header");
+    if (interlace) fail(OCTVR_ERR_UNSUPPORTED, "png mask: interlaced PNG files are not supported");
+    const int channels = ctype == 0 ? 1 : ctype == 2 ? 3 : ctype == 3 ? 1 : ctype == 4 ? 2 : ctype == 6 ? 4 : 0;
+    const bool depth_ok = depth == 8 || (depth == 16 && ctype != 3) || ((depth == 1 || depth == 2 || depth == 4) && (ctype == 0 || ctype == 3));
+    if (!channels || !depth_ok) fail(OCTVR_ERR_FORMAT, "png mask: unsupported colour type / bit depth");
+    const size_t bpp = std::max<size_t>(1, (size_t)channels * depth / 8);            // bytes per complete pixel (filter unit)
+    const size_t stride = ((size_t)w * channels * depth + 7) / 8;
+    std::vector<uint8_t> raw((stride + 1) * (size_t)h);
+    uLongf got = (uLongf)raw.size();
+    if (uncompress(raw.data(), &got, idat.data(), (uLong)idat.size()) != Z_OK || got != raw.size()) fail(OCTVR_ERR_FORMAT, "png mask: inflate failed");
+    // undo the row filters in place (PNG specification, section 9: None, Sub, Up, Average, Paeth)
+    std::vector<uint8_t> zero(stride, 0);
+    for (int y = 0; y < h; y++) {
+        uint8_t* cur = raw.data() + (size_t)y * (stride + 1) + 1;
+        const uint8_t* up = y ? cur - (stride + 1) : zero.data();
+        const int f = cur[-1];
+        for (size_t i = 0; i < stride; i++) {
+            const int a = i >= bpp ? cur[i - bpp] : 0, b = up[i], c = i >= bpp ? up[i - bpp] : 0;
+            int pred = 0;
+            if (f == 1) pred = a;
+            else if (f == 2) pred = b;
+            else if (f == 3) pred = (a + b) >> 1;
+            else if (f == 4) { const int q = a + b - c, pa = std::abs(q - a), pb = std::abs(q - b), pc = std::abs(q - c); pred = (pa <= pb && pa <= pc) ? a : (pb <= pc ? b : c); }
+            else if (f != 0) fail(OCTVR_ERR_FORMAT, "png mask: bad filter type");
+            cur[i] = (uint8_t)(cur[i] + pred);
+        }
+    }
+    bgr.assign((size_t)w * h * 3, 0);
+    for (int y = 0; y < h; y++) {
+        const uint8_t* row = raw.data() + (size_t)y * (stride + 1) + 1;
+        for (int x = 0; x < w; x++) {
+            auto sample = [&](int k) -> int {                                       // k-th sample of pixel x as 8 bits (palette: the index)
+                const size_t s = (size_t)x * channels + k;
+                if (depth == 8) return row[s];
+                if (depth == 16) return row[2 * s];
+                const int per = 8 / depth, v = (row[s / per] >> (8 - depth * (int)(s % per + 1))) & ((1 << depth) - 1);
+                return ctype == 3 ? v : v * 255 / ((1 << depth) - 1);
+            };
+            int r, g, b;
+            if (ctype == 3) {
+                const size_t i = (size_t)sample(0) * 3;
+                if (i + 2 >= plte.size()) { r = g = b = 0; } else { r = plte[i]; g = plte[i + 1]; b = plte[i + 2]; }
+            } else if (channels <= 2) r = g = b = sample(0);
+            else { r = sample(0); g = sample(1); b = sample(2); }
+            uint8_t* o = bgr.data() + ((size_t)y * w + x) * 3;
+            o[0] = (uint8_t)b; o[1] = (uint8_t)g; o[2] = (uint8_t)r;
+        }
     }
 }
 

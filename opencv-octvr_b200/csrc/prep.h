@@ -19,6 +19,11 @@ void resize_linear_tables(int src, int dst, bool clamp_ofs, std::vector<int>& of
 // edge table).  Camera::Camera draws the `selection` rectangle and the polygonal exclude / include masks with it
 // (octvr/src/camera.cpp:96-167).
 void fill_poly_u8(uint8_t* img, int w, int h, const int* pts_xy, int npts, uint8_t val);
+// The pixels cv::imdecode(bytes, IMREAD_COLOR) yields for a PNG file (camera.cpp:169-187 reads exclude / include masks that
+// way): 8-bit B,G,R per pixel.  Grey is replicated, a palette expanded, alpha dropped, 16-bit samples reduced to their
+// high byte, 1 / 2 / 4-bit grey scaled to 0..255 -- what libpng does for OpenCV.  Inflate comes from zlib; interlaced files
+// are rejected (OCTVR_ERR_UNSUPPORTED).
+void png_decode_bgr(const uint8_t* bytes, size_t n, int& w, int& h, std::vector<uint8_t>& bgr);
 // cv::pyrDown for 32FC1 (pyramids.cpp:849-964 incl. the SSE association of :143-185)
 Img<float> pyrdown_f32(const Img<float>& src);
 

@@ -279,6 +279,23 @@ def fill_poly(mask, pts, val):
 _fill_poly = fill_poly
 
 
+def read_ocam_file(path):
+    """get_ocam_model (cameras/ocam_fisheye.cpp:19-80): comment lines start with '#'; then, in order: n + n direct
+    coefficients, m + m inverse coefficients, centre "xc yc", affine "c d e", image "height width"."""
+    nums = []
+    for ln in open(path):
+        ln = ln.strip()
+        if ln and not ln.startswith("#"):
+            nums += ln.split()
+    it = iter(nums)
+    n = int(next(it)); pol = [float(next(it)) for _ in range(n)]
+    m = int(next(it)); inv = [float(next(it)) for _ in range(m)]
+    xc, yc = float(next(it)), float(next(it))
+    c, d, e = float(next(it)), float(next(it)), float(next(it))
+    h, w = int(next(it)), int(next(it))
+    return dict(pol=pol, invpol=inv, xc=xc, yc=yc, c=c, d=d, e=e, width=w, height=h)
+
+
 def make_camera(typ, opts):
     """camera.cpp:33-135 + per-model constructors.  Returns (struct, keepalive list)."""
     if typ not in CAM_TYPES:
@@ -320,8 +337,17 @@ def make_camera(typ, opts):
                 a = area["args"]
                 pts = [(int(a[i]), int(a[i + 1])) for i in range(0, len(a), 2)]
                 _fill_poly(inc if kind == "include" else ex, pts, 255)
+            elif area["type"] == "png":
+                # camera.cpp:169-187: cv::imdecode(args, 1) -> 8UC3 BGR; red channel != 0 -> exclude, green != 0 -> include,
+                # whichever list the entry sits in.  (cv2's decoder stands in for the reference's: PNG is lossless.)
+                import cv2
+                img = cv2.imdecode(np.asarray(area["args"], np.uint8), 1)
+                if ex is None or img is None or img.shape[:2] != ex.shape:
+                    raise ValueError("png mask: needs an exclude mask of the same size (camera.cpp:175)")
+                ex[img[:, :, 2] != 0] = 255
+                inc[img[:, :, 1] != 0] = 255
             else:
-                raise NotImplementedError("png masks need imdecode")
+                raise ValueError("unknown mask type")
     if ex is not None:
         keep.append(ex)
         cam.exclude_mask, cam.ex_w, cam.ex_h = ex.ctypes.data, ex.shape[1], ex.shape[0]
@@ -364,6 +390,8 @@ def make_camera(typ, opts):
         cam.p[3 + 4] = (cw if cw < ch else ch) / 2.0
         cam.p[3 + 5] = lib().orc_fisheye_correction_radius(rd)
     elif typ == "ocam_fisheye":
+        if "file" in opts:                 # cameras/ocam_fisheye.cpp:19-80: Scaramuzza's calib_results.txt
+            opts = dict(opts, **read_ocam_file(opts["file"]))
         pol, inv = [float(v) for v in opts["pol"]], [float(v) for v in opts["invpol"]]
         cam.n_pol, cam.n_invpol = len(pol), len(inv)
         for i, v in enumerate(pol):

@@ -159,6 +159,57 @@ static P2 ff_obj_to_image(const orc_camera* c, P2 ll)
     return ret;
 }
 
+/* image_to_obj_single (cameras/fullframe_fisheye_cam.cpp:223-253) with do_reverse_radial_distort (:160-184).
+ * The reference finds the radius with cv::solvePoly (Durand-Kerner on the quartic V3 r^4 + V2 r^3 + V1 r^2 + V0 r - s/V4,
+ * keeping the smallest positive real root, then rejecting it unless it is below the correction radius).  On [0, r_corr)
+ * the polynomial P(r) = (((V3 r + V2) r + V1) r + V0) r rises monotonically from 0 (r_corr is the first positive root of
+ * P'), so "smallest positive root, accepted only below r_corr" == "the root of P(r) = s/V4 in (0, r_corr) if
+ * s/V4 < P(r_corr), else none".  That root is computed here by safeguarded Newton to full f64 precision; solvePoly's
+ * own answer differs from it by its iteration tolerance only, hence this model as OUTPUT is pinned to the reference with
+ * the contract tolerance (1e-4 px) rather than bit for bit. */
+static double ff_reverse_radius(const orc_camera* c, double t)
+{
+    const double V0 = FF_VAR(c, 0), V1 = FF_VAR(c, 1), V2 = FF_VAR(c, 2), V3 = FF_VAR(c, 3), rc = FF_VAR(c, 5);
+    const double prc = (((V3 * rc + V2) * rc + V1) * rc + V0) * rc;
+    if (!(t > 0) || !(t < prc)) return -1;
+    double lo = 0, hi = rc, r = t < rc ? t : 0.5 * rc;
+    for (int it = 0; it < 100; it++) {
+        const double f = (((V3 * r + V2) * r + V1) * r + V0) * r - t;
+        if (f == 0) break;
+        if (f > 0) hi = r; else lo = r;
+        const double d = ((4 * V3 * r + 3 * V2) * r + 2 * V1) * r + V0;
+        double rn = r - f / d;
+        if (!(rn > lo && rn < hi)) rn = 0.5 * (lo + hi);
+        if (rn == r) break;
+        r = rn;
+    }
+    return r;
+}
+static P2 ff_image_to_obj(const orc_camera* c, P2 xy, int* ok)
+{
+    if (!(FF_CW(c) == FF_W(c) && FF_CH(c) == FF_H(c) && FF_CX(c) == 0 && FF_CY(c) == 0)) { *ok = 0; return NANP; }   /* CV_Assert */
+    xy.x -= 0.5; xy.y -= 0.5;
+    xy.x *= (double)FF_CW(c); xy.y *= (double)FF_CH(c);
+    xy.x -= c->p[1]; xy.y -= c->p[2];
+    if (fabs(xy.x) < 1e-5 && fabs(xy.y) < 1e-5) { P2 z = { 0, 0 }; return z; }
+    {
+        const double s = sqrt(xy.x * xy.x + xy.y * xy.y);
+        const double r = ff_reverse_radius(c, s / FF_VAR(c, 4));
+        const double scale = (r > 0 && r < FF_VAR(c, 5)) ? s / FF_VAR(c, 4) / r : 1000.0;
+        xy.x = xy.x / scale; xy.y = xy.y / scale;
+    }
+    {
+        const double distance = (double)FF_CW(c) / c->p[0];
+        const double alpha = atan2(-xy.y, xy.x);
+        double theta = -xy.y / distance / sin(alpha);
+        if (fabs(sin(alpha)) < 1e-3) theta = -xy.x / distance / cos(alpha);
+        const double lon = atan2(sin(theta) * cos(alpha), cos(theta));
+        const double lat = atan(tan(alpha) * sin(lon));
+        P2 r = { lon, lat };
+        return r;
+    }
+}
+
 /* ---- ocam (cameras/ocam_fisheye.cpp:135-244) ---- */
 static P2 ocam_obj_to_image(const orc_camera* c, P2 ll)
 {
@@ -292,6 +343,7 @@ static P2 image_to_obj_single(const orc_camera* c, P2 xy, int* ok)
     case ORC_CAM_PERSPECTIVE: {                    /* cameras/perspective.cpp:21-26 */
         P3 q = { 1.0 / c->p[1], 0.5 - xy.y, (0.5 - xy.x) * c->p[0] };
         return xyz_to_lonlat(q); }
+    case ORC_CAM_FULLFRAME_FISHEYE: return ff_image_to_obj(c, xy, ok);
     case ORC_CAM_EQUIRECT: {                       /* cameras/equirectangular.cpp:31-35 */
         P2 r = { (xy.x - 0.5) * M_PI * 2.0, (c->p[0] - c->p[1]) * xy.y + c->p[1] };
         return r; }

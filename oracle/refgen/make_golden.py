@@ -68,7 +68,8 @@ def main():
         if only and rig not in only:
             continue
         dat = os.path.join(TMP, rig + ".dat")
-        subprocess.check_call([dump, "-w", str(w), "-o", dat, os.path.join(rigs_dir, rig + ".json")],
+        # cwd = the rigs directory: an ocam_fisheye "file" option names its calibration file relative to it
+        subprocess.check_call([dump, "-w", str(w), "-o", dat, os.path.join(rigs_dir, rig + ".json")], cwd=rigs_dir,
                               stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
         t = O.load_dat(dat)
         arrs = {"out_size": np.array(t.out_size, np.int64), "n": np.array(len(t.inputs))}

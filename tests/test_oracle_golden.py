@@ -132,7 +132,8 @@ RIGS = sorted(os.path.basename(f)[5:-4] for f in glob.glob(os.path.join(GOLD, "t
 def test_template_tables_bit_exact(rig):
     """MapperTemplate + add_input + create_masks for all 11 camera models, in and out."""
     g = np.load(os.path.join(GOLD, "tmpl_%s.npz" % rig))
-    cfg = json.load(open(os.path.join(GOLD, "rigs", rig + ".json")))
+    import util
+    cfg = util.rig_json(rig)
     w = json.load(open(os.path.join(GOLD, "rigs", "widths.json")))[rig]
     t = O.build_template(cfg, w)
     assert tuple(g["out_size"]) == t.out_size

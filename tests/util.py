@@ -50,7 +50,11 @@ def i420_planes(f, w, h):
 
 
 def rig_json(name):
-    return json.load(open(os.path.join(GOLD, "rigs", name + ".json")))
+    cfg = json.load(open(os.path.join(GOLD, "rigs", name + ".json")))
+    for cam in [cfg["output"]] + cfg["inputs"]:          # an ocam_fisheye "file" option is relative to the rigs directory
+        if "file" in cam.get("options", {}):
+            cam["options"]["file"] = os.path.join(GOLD, "rigs", cam["options"]["file"])
+    return cfg
 
 
 def rig_width(name):
