@@ -537,9 +537,14 @@ def run_stereo(args, sub=False):
                 views[c].copy_(torch.from_numpy(np.concatenate([y, np.concatenate([u, v], 1)], 0)))
         ring.append(views)
         flats.append(flat)
-    outs = [torch.zeros((H * 3 // 2, W), dtype=torch.uint8, device="cuda") for _ in range(2)]
+    # N > 1: the two output frames live on rank 0 and are mapped into every rank (CUDA IPC over NVLink): each rank's blend
+    # kernels store their band straight into rank 0's frame, one 4-byte all-reduce per step says "frame complete".
+    # OCTVR_C4_COLLECT=nccl: private output buffers, bands sent to rank 0 by NCCL send / recv (the round-1 path).
+    peer = world > 1 and os.environ.get("OCTVR_C4_COLLECT", "peer") == "peer"
+    pfs = [vr.sharding.PeerFrame(H * 3 // 2, W, local, owner=0) for _ in range(2)] if peer else []
+    outs = [p.tensor for p in pfs] if peer else [torch.zeros((H * 3 // 2, W), dtype=torch.uint8, device="cuda") for _ in range(2)]
     out = outs[0]
-    pipe = vr.sharding.FramePipeline(st, src=0, defer_collect=os.environ.get("OCTVR_DEFER_COLLECT", "0") != "0")
+    pipe = vr.sharding.FramePipeline(st, src=0, defer_collect=os.environ.get("OCTVR_DEFER_COLLECT", "0") != "0", peer=peer)
 
     def step(k, last=False):
         if world > 1:      # broadcast of step k + 1 runs under the stitch of step k (OCTVR_DEFER_COLLECT=1: the band collection of step k - 1 too)
@@ -590,8 +595,10 @@ def run_stereo(args, sub=False):
             b.record()
             torch.cuda.synchronize()
             return vr.sharding.max_over_ranks(a.elapsed_time(b) / reps, device="cuda")
+        tok = torch.zeros(1, dtype=torch.int32, device="cuda")
         exchange = {"broadcast_ms": round(timed(lambda: vr.sharding.broadcast_frames(flats[0], 0)), 4),
-                    "collect_ms": round(timed(lambda: vr.sharding.collect_shares(out, st.shares(), 0)), 4)}
+                    ("frame_complete_allreduce_ms" if peer else "collect_ms"):
+                        round(timed((lambda: vr.sharding.frame_complete(tok)) if peer else (lambda: vr.sharding.collect_shares(out, st.shares(), 0))), 4)}
     verified = None
     if args.verify and world > 1 and rank == 0:      # the assembled frame of the last step == both eyes stitched whole on this GPU
         one = vr.sharding.StereoRowBandStitcher(vr, tmpls, [in_size] * n, blend, gain, local, rank=0, world=1)
@@ -600,7 +607,10 @@ def run_stereo(args, sub=False):
         torch.cuda.synchronize()
         verified = bool(torch.equal(ref, outs[(args.steps - 1) % 2]))
         del one, ref
+    src_rows = [[int(m.src_rows()[c][1] - m.src_rows()[c][0]) for c in range(n)] for _, _, m in st.jobs]
     del st, pipe, outs, out, ring, flats, tmpls
+    for pf in pfs:
+        pf.close()
     torch.cuda.empty_cache()
     if not sub:
         pg_done()
@@ -621,9 +631,11 @@ def run_stereo(args, sub=False):
                    "output": "%dx%d 4:2:0 top-bottom (two %dx%d eyes)" % (W, H, W, He),
                    "l2": "working set per step exceeds the 126 MB L2; no flush",
                    "sharding": ("row bands of one stream: per step ONE NCCL broadcast of the %d input frames (%.1f MB) from rank 0 (issued one step "
-                                "ahead, overlapping the previous stitch), (eye, band) stitch, bands sent to rank 0 by NCCL send/recv "
+                                "ahead, overlapping the previous stitch), (eye, band) stitch of the source rows the band reads "
                                 "(%.1f MB frame in total)" % (n, I / 1e6, W * H * 1.5 / 1e6)) if world > 1 else "single GPU, both eyes",
-                   "assignment_rank0": jobs_rank0,
+                   "assignment_rank0": jobs_rank0, "source_rows_converted_rank0": src_rows,
+                   "band_output": ("stored by the blend kernels straight into rank 0's frame over NVLink peer memory (CUDA IPC); one 4-byte "
+                                   "all-reduce per step = frame complete") if peer else ("NCCL send / recv to rank 0" if world > 1 else "local"),
                    "pairs_P_per_eye": stats[0]["pairs"], "roi_area_per_eye": stats[0]["roi_area"],
                    "template_build_s": round(t_tmpl, 2), "mapper_build_s": round(t_map, 2)},
         "alg_bytes_per_frame": int(B),
@@ -648,22 +660,38 @@ def run_stereo(args, sub=False):
 
 
 def run_e2e(vr, util, tmpl, cfg, in_size, blend, gain, device, steps, world):
-    """Same metric through AsyncMultiMapper.push/pop with HOST frames: H2D + stitch + D2H every step."""
+    """Same metric through AsyncMultiMapper.push/pop with HOST frames: H2D + stitch + D2H every step.  Headline figure: the
+    caller's planes are page-locked (DMA straight from / to them); `pageable` repeats it with ordinary malloc'ed planes, as an
+    ffmpeg filter would hand them over (the pipeline's threads stage them through pinned buffers, T1 / T5 of the reference)."""
+    res = e2e_once(vr, util, tmpl, cfg, in_size, blend, gain, device, steps, world, pinned=True)
+    try:
+        pg = e2e_once(vr, util, tmpl, cfg, in_size, blend, gain, device, max(10, steps // 2), world, pinned=False)
+        res["pageable"] = {k: pg[k] for k in ("value", "unit", "frames_per_s", "steps", "push_us_median")}
+    except vr.OctvrError as ex:
+        res["pageable"] = {"error": str(ex)}
+    return res
+
+
+def e2e_once(vr, util, tmpl, cfg, in_size, blend, gain, device, steps, world, pinned):
     import torch
     n = len(cfg["inputs"])
     iw, ih = in_size
     W, H = tmpl.out_size
     am = vr.AsyncMultiMapper([tmpl], [in_size] * n, (W, H), [blend], [0 if gain else -1], [(0.0, 0.0, 1.0, 1.0)], (0, 0), device=device)
     RING = 4
+
+    def host(a):
+        return torch.from_numpy(a).pin_memory().numpy() if pinned else np.ascontiguousarray(a)
     hin = []
     for k in range(RING):
         fr = []
         for c in range(n):
-            buf = torch.from_numpy(util.noise_frame(c, iw, ih, seed=99 + k)).pin_memory().numpy()
+            buf = host(util.noise_frame(c, iw, ih, seed=99 + k))
             fr.append(util.i420_planes(buf, iw, ih))
         hin.append(fr)
-    houts = [torch.zeros(W * H * 3 // 2, dtype=torch.uint8).pin_memory().numpy() for _ in range(RING)]
+    houts = [host(np.zeros(W * H * 3 // 2, np.uint8)) for _ in range(RING)]
     hout = [util.i420_planes(o, W, H) for o in houts]
+    push_s = []
     depth = 3
     for k in range(depth):      # warm-up / fill
         am.push(hin[k % RING], hout[k % RING])
@@ -672,7 +700,9 @@ def run_e2e(vr, util, tmpl, cfg, in_size, blend, gain, device, steps, world):
     t0 = time.perf_counter()
     inflight = 0
     for k in range(steps):
+        a0 = time.perf_counter()
         am.push(hin[k % RING], hout[k % RING])
+        push_s.append(time.perf_counter() - a0)
         inflight += 1
         if inflight == depth:
             am.pop()
@@ -685,7 +715,8 @@ def run_e2e(vr, util, tmpl, cfg, in_size, blend, gain, device, steps, world):
     dt = vr.sharding.max_over_ranks(dt, device="cuda")
     return {"value": round(W * H * steps * world / dt / 1e6, 1), "unit": "Mpix/s", "frames_per_s": round(steps * world / dt, 1),
             "h2d_bytes_per_step": n * iw * ih * 3 // 2, "d2h_bytes_per_step": W * H * 3 // 2,
-            "api": "AsyncMultiMapper.push/pop (pinned host planes, 3 frames in flight)", "steps": steps}
+            "api": "AsyncMultiMapper.push/pop (%s host planes, 3 frames in flight)" % ("pinned" if pinned else "pageable"), "steps": steps,
+            "push_us_median": round(1e6 * statistics.median(push_s), 1)}
 
 
 def cpu_baseline(workload, budget_s=20.0, steps=None, warmup=1):

@@ -121,6 +121,15 @@ octvr_status octvr_mapper_stitch(octvr_mapper* m, const octvr_frame* d_inputs, i
 octvr_status octvr_mapper_stitch_packed(octvr_mapper* m, const uint8_t* const* d_inputs, const size_t* in_pitch,
                                         int n_inputs, uint8_t* d_output, size_t out_pitch,
                                         const double* gains, int n_gains, void* stream);
+/* Row-band mode without a collection step: the rank that collects the frame allocates it with octvr_shared_alloc and
+ * hands the 64-byte handle to the other ranks of the node (any channel; the tests use torch.distributed), they map it with
+ * octvr_shared_open and pass pointers into it as the output frame of their band mapper: the blend kernels' stores then go
+ * straight to the collecting GPU over NVLink peer memory.  A frame is complete on the collecting rank once every rank's
+ * stitch has finished (the caller orders that, e.g. with one small NCCL all-reduce on the stitch streams).
+ * octvr_shared_close(ptr, opened): opened = 1 for a pointer from octvr_shared_open, 0 to free the owner's allocation. */
+octvr_status octvr_shared_alloc(size_t bytes, int device, void** d_ptr, unsigned char handle64[64]);
+octvr_status octvr_shared_open(const unsigned char handle64[64], int device, void** d_ptr);
+octvr_status octvr_shared_close(void* d_ptr, int opened);
 /* Keep the RGB888 result at template size (Mapper::result, mapper.hpp:66) in addition to / instead of the YUV output. */
 octvr_status octvr_mapper_set_keep_rgb(octvr_mapper* m, int on);
 /* RGB888 result of the last stitch, device->host copy, synchronous.  Needs octvr_mapper_set_keep_rgb(m, 1). */
@@ -131,6 +140,9 @@ octvr_status octvr_mapper_gains(octvr_mapper* m, double* out, int n);
  * packed device tables one stitch reads, kernels launched per stitch. */
 octvr_status octvr_mapper_stats(const octvr_mapper* m, int64_t* pairs, int64_t* roi_area,
                                 int64_t* table_bytes, int* launches_per_stitch);
+/* Per blended input the source rows [lo, hi) this mapper converts and reads (the whole image unless it is a row-band
+ * mapper); rows_lo_hi = {lo0, hi0, lo1, hi1, ...}, n = number of blended inputs. */
+octvr_status octvr_mapper_source_rows(const octvr_mapper* m, int* rows_lo_hi, int n);
 /* time (ms, CUDA events on the stitch stream) the named stage of the LAST stitch took; stage =
  * "convert" | "gain" | "blend" | "total".  Only valid when octvr_mapper_set_profiling(m, 1). */
 octvr_status octvr_mapper_set_profiling(octvr_mapper* m, int on);

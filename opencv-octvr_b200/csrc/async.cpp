@@ -1,15 +1,21 @@
 // csrc/async.cpp -- vr::AsyncMultiMapper (modules/octvr/include/octvr.hpp:103-121, src/async.{hpp,cpp}) behind
 // the C ABI: host planes in, host planes out, BUF_SIZE = 3 frames in flight (async.cpp:261).
 //
-// The reference runs five host threads (copy-in, upload, map, download, copy-out; async.cpp:32-172,337-349).
-// Here the same five stages are expressed as CUDA stream work: push() stages the frame (or DMAs straight from
-// the caller's planes when they are already page-locked), enqueues H2D on the upload stream, the stitch of
-// every output region on the compute stream and D2H on the download stream, chained with events; pop() waits
-// for the oldest frame's last event and finishes the copy-out.  No stage ever blocks the GPU on the host.
+// The reference runs five host threads (copy-in, upload, map, download, copy-out; async.cpp:32-172,337-349) and its
+// push() only enqueues (async.cpp:174-189).  Same contract here with two threads, because the three middle stages are
+// CUDA stream work chained by events and need no thread of their own:
+//   front thread  T1 + T2 + T3 + T4: takes a pushed frame, waits for a free buffer set, copies pageable planes into
+//                 pinned staging (page-locked caller planes are DMA'd directly), then enqueues H2D on the upload stream,
+//                 the stitch of every output region on the compute stream and D2H on the download stream;
+//   back thread   T5: waits for the oldest frame's last event, copies staged output planes to the caller's (pageable)
+//                 planes, marks the frame complete and frees its buffer set.
+// push() validates and enqueues, whatever the planes are; pop() blocks until the oldest frame is complete.  An error
+// inside a thread is reported by the pop() of that frame.
 #include "mapper.h"
 #include <chrono>
 #include <cmath>
 #include <cstring>
+#include <condition_variable>
 #include <deque>
 #include <memory>
 #include <mutex>
@@ -32,8 +38,13 @@ struct Slot {
     uint8_t* h_preview = nullptr;     // pinned copy of it, valid after pop()
     cudaEvent_t uploaded = nullptr, stitched = nullptr, done = nullptr;
     bool busy = false;
-    octvr_frame user_out{};           // caller's output planes (filled by pop when staged)
+    octvr_frame user_out{};           // caller's output planes (filled by the back thread when staged)
     bool out_staged = false;
+};
+
+struct Job {                          // one pushed frame: shallow copies of the caller's plane headers (async.cpp:187-188)
+    std::vector<octvr_frame> in;
+    octvr_frame out;
 };
 
 bool is_pinned(const void* p)
@@ -44,18 +55,18 @@ bool is_pinned(const void* p)
 }
 
 // copy a w x h byte plane (host) with up to 8 helper threads for big planes
-void host_copy_plane(uint8_t* dst, size_t dpitch, const uint8_t* src, size_t spitch, int w, int h, int pix_step)
+void host_copy_plane(uint8_t* dst, size_t dpitch, const uint8_t* src, size_t spitch, int w, int h, int pix_step, int dst_step = 1)
 {
     auto rows = [=](int y0, int y1) {
         for (int y = y0; y < y1; y++) {
             const uint8_t* s = src + (size_t)y * spitch;
             uint8_t* d = dst + (size_t)y * dpitch;
-            if (pix_step == 1) memcpy(d, s, (size_t)w);
-            else for (int x = 0; x < w; x++) d[x] = s[(size_t)x * pix_step];
+            if (pix_step == 1 && dst_step == 1) memcpy(d, s, (size_t)w);
+            else for (int x = 0; x < w; x++) d[(size_t)x * dst_step] = s[(size_t)x * pix_step];
         }
     };
     const size_t bytes = (size_t)w * h;
-    const int nt = bytes > (1u << 20) ? 4 : 1;
+    const int nt = bytes > (2u << 20) ? 8 : bytes > (1u << 19) ? 4 : 1;
     if (nt == 1) { rows(0, h); return; }
     std::vector<std::thread> th;
     for (int t = 0; t < nt; t++) th.emplace_back(rows, h * t / nt, h * (t + 1) / nt);
@@ -75,15 +86,28 @@ struct octvr_async {
     const uint8_t* last_preview = nullptr;     // h_preview of the frame popped last
     static constexpr int BUF = 3;              // async.cpp:261
     Slot slots[BUF];
-    uint64_t pushed = 0, popped = 0;
+    uint64_t pushed = 0, issued = 0, completed = 0, popped = 0;   // frames: push() accepted / CUDA work enqueued / copy-out done / pop() returned
+    std::deque<Job> queue;                     // pushed, not yet issued
+    std::deque<int> status;                    // per completed, not yet popped frame: OCTVR_OK or the error of its stage
+    std::string worker_error;
     cudaStream_t s_up = nullptr, s_run = nullptr, s_down = nullptr;
     std::mutex mtx;
+    std::condition_variable cv;
+    std::thread front, back;
+    bool stop = false;
+    void front_loop();
+    void back_loop();
+    void issue(Slot& s, const Job& job);
     // fps over the last 10 frames (async.cpp:141-147)
     std::deque<std::chrono::steady_clock::time_point> stamps;
     double fps = 0;
 
     ~octvr_async()
     {
+        { std::lock_guard<std::mutex> lk(mtx); stop = true; }
+        cv.notify_all();
+        if (front.joinable()) front.join();
+        if (back.joinable()) back.join();
         cudaSetDevice(device);
         if (s_up) cudaStreamSynchronize(s_up);
         if (s_run) cudaStreamSynchronize(s_run);
@@ -199,121 +223,193 @@ octvr_status octvr_async_create(const octvr_template* const* tmpls, int n_out, c
             OB_CUDA(cudaEventCreateWithFlags(&s.stitched, cudaEventDisableTiming));
             OB_CUDA(cudaEventCreateWithFlags(&s.done, cudaEventDisableTiming));
         }
+        OB_CUDA(cudaDeviceSynchronize());       // the fills above ran on the legacy stream; the pipeline's streams are non-blocking
+        a->front = std::thread([p = a.get()] { p->front_loop(); });
+        a->back = std::thread([p = a.get()] { p->back_loop(); });
         *out = a.release();
     });
 }
 
 octvr_status octvr_async_push(octvr_async* a, const octvr_frame* in, int n_inputs, const octvr_frame* out)
 {
+    // async.cpp:174-189: shape checks, then the frame is queued; the caller keeps the planes alive until the matching pop()
     return guard([&] {
         OB_CHECK(a && in && out, "null argument");
         OB_CHECK(n_inputs == a->n_in, "wrong number of input frames (async.cpp:176)");
-        std::lock_guard<std::mutex> lk(a->mtx);
-        OB_CHECK(a->pushed - a->popped < (uint64_t)octvr_async::BUF, "pipeline full: pop() before pushing more than 3 frames");
-        OB_CUDA(cudaSetDevice(a->device));
-        Slot& s = a->slots[a->pushed % octvr_async::BUF];
-        // T1 + T2: caller planes -> (pinned staging ->) device, on the upload stream
         for (int i = 0; i < a->n_in; i++) {
-            const int w = a->in_w[i], h = a->in_h[i];
             const octvr_frame& f = in[i];
-            OB_CHECK(f.y && f.u && f.v && f.y_pitch >= (size_t)w, "bad input frame");
-            uint8_t* d = s.d_in[i]; uint8_t* hs = s.h_in[i];
-            const size_t ysz = (size_t)w * h, csz = (size_t)(w / 2) * (h / 2);
-            if (f.uv_pixel_stride == 1 && f.y_pitch == (size_t)w && f.u_pitch == (size_t)w / 2 && f.v_pitch == (size_t)w / 2 &&
-                f.u == f.y + ysz && f.v == f.u + csz && is_pinned(f.y)) {
-                OB_CUDA(cudaMemcpyAsync(d, f.y, ysz + 2 * csz, cudaMemcpyHostToDevice, a->s_up));       // contiguous pinned I420
-                continue;
-            }
-            upload_plane(d, hs, f.y, f.y_pitch, 1, w, h, a->s_up);
-            upload_plane(d + ysz, hs + ysz, f.u, f.u_pitch, f.uv_pixel_stride, w / 2, h / 2, a->s_up);
-            upload_plane(d + ysz + csz, hs + ysz + csz, f.v, f.v_pitch, f.uv_pixel_stride, w / 2, h / 2, a->s_up);
+            const size_t w = (size_t)a->in_w[i];
+            OB_CHECK(f.y && f.u && f.v && f.y_pitch >= w && (f.uv_pixel_stride == 1 || f.uv_pixel_stride == 2) &&
+                     f.u_pitch >= w / 2 * f.uv_pixel_stride && f.v_pitch >= w / 2 * f.uv_pixel_stride, "bad input frame");
         }
-        OB_CUDA(cudaEventRecord(s.uploaded, a->s_up));
-        // T3: every output region on the compute stream (async.cpp:70-91)
-        OB_CUDA(cudaStreamWaitEvent(a->s_run, s.uploaded, 0));
-        std::vector<octvr_frame> fin(a->n_in);
-        for (int i = 0; i < a->n_in; i++) fin[i] = i420_frame(s.d_in[i], a->in_w[i], a->in_h[i]);
-        const octvr_frame whole = i420_frame(s.d_out, a->out_w, a->out_h);
-        for (int r = 0; r < a->n_out; r++) {
-            const Rect& px = a->regions[r];
-            octvr_frame o = whole;
-            o.y += (size_t)px.y * whole.y_pitch + px.x;
-            o.u += (size_t)(px.y / 2) * whole.u_pitch + px.x / 2;
-            o.v += (size_t)(px.y / 2) * whole.v_pitch + px.x / 2;
-            const int gm = a->gain_modes[r];
-            const double* shared = (gm >= 0 && gm != r) ? a->mappers[gm]->d_gains : nullptr;   // gains of an earlier output
-            uint8_t* pv = nullptr;                                          // this output's part of the preview frame (async.cpp:78-79)
-            int pvw = 0, pvh = 0;
-            if (a->preview_w) {
-                const Rect& pr = a->preview_regions[r];
-                pv = s.d_preview + ((size_t)pr.y * a->preview_w + pr.x) * 3; pvw = pr.w; pvh = pr.h;
-            }
-            mapper_stitch_internal(*a->mappers[r], fin.data(), a->n_in, &o, nullptr, 0, shared, a->s_run, pv, (size_t)a->preview_w * 3, pvw, pvh);
+        const size_t W = (size_t)a->out_w;
+        OB_CHECK(out->y && out->u && out->v && out->y_pitch >= W && (out->uv_pixel_stride == 1 || out->uv_pixel_stride == 2) &&
+                 out->u_pitch >= W / 2 * out->uv_pixel_stride && out->v_pitch >= W / 2 * out->uv_pixel_stride, "bad output frame");
+        Job job;
+        job.in.assign(in, in + n_inputs);
+        job.out = *out;
+        {
+            std::lock_guard<std::mutex> lk(a->mtx);
+            a->queue.push_back(std::move(job));
+            a->pushed++;
         }
-        OB_CUDA(cudaEventRecord(s.stitched, a->s_run));
-        // T4: device -> host on the download stream; straight into the caller's planes when they are pinned
-        OB_CUDA(cudaStreamWaitEvent(a->s_down, s.stitched, 0));
-        const int W = a->out_w, H = a->out_h;
-        const bool direct = out->uv_pixel_stride == 1 && is_pinned(out->y) && is_pinned(out->u) && is_pinned(out->v);
-        s.out_staged = !direct;
-        s.user_out = *out;
-        const bool tight = out->y_pitch == (size_t)W && out->u_pitch == (size_t)W / 2 && out->v_pitch == (size_t)W / 2;
-        if (direct && tight && out->u == out->y + (size_t)W * H && out->v == out->u + (size_t)(W / 2) * (H / 2)) {
-            OB_CUDA(cudaMemcpyAsync(out->y, s.d_out, (size_t)W * H * 3 / 2, cudaMemcpyDeviceToHost, a->s_down));      // contiguous I420
-        } else if (direct && tight) {
-            OB_CUDA(cudaMemcpyAsync(out->y, whole.y, (size_t)W * H, cudaMemcpyDeviceToHost, a->s_down));
-            OB_CUDA(cudaMemcpyAsync(out->u, whole.u, (size_t)(W / 2) * (H / 2), cudaMemcpyDeviceToHost, a->s_down));
-            OB_CUDA(cudaMemcpyAsync(out->v, whole.v, (size_t)(W / 2) * (H / 2), cudaMemcpyDeviceToHost, a->s_down));
-        } else if (direct) {
-            OB_CUDA(cudaMemcpy2DAsync(out->y, out->y_pitch, whole.y, whole.y_pitch, (size_t)W, (size_t)H, cudaMemcpyDeviceToHost, a->s_down));
-            OB_CUDA(cudaMemcpy2DAsync(out->u, out->u_pitch, whole.u, whole.u_pitch, (size_t)W / 2, (size_t)H / 2, cudaMemcpyDeviceToHost, a->s_down));
-            OB_CUDA(cudaMemcpy2DAsync(out->v, out->v_pitch, whole.v, whole.v_pitch, (size_t)W / 2, (size_t)H / 2, cudaMemcpyDeviceToHost, a->s_down));
-        } else {
-            OB_CUDA(cudaMemcpyAsync(s.h_out, s.d_out, (size_t)W * H * 3 / 2, cudaMemcpyDeviceToHost, a->s_down));
-        }
-        if (a->preview_w)
-            OB_CUDA(cudaMemcpyAsync(s.h_preview, s.d_preview, (size_t)a->preview_w * a->preview_h * 3, cudaMemcpyDeviceToHost, a->s_down));
-        OB_CUDA(cudaEventRecord(s.done, a->s_down));
-        // the next frame's upload into this slot's device buffers must not start before this stitch has read them;
-        // slots are reused only after pop(), which waits for `done` (ordered after `stitched`)
-        s.busy = true;
-        a->pushed++;
+        a->cv.notify_all();
     });
+}
+
+// T1 .. T4 of one frame (front thread): staging copies, then everything else as stream work
+void octvr_async::issue(Slot& s, const Job& job)
+{
+    octvr_async* a = this;
+    const octvr_frame* in = job.in.data();
+    const octvr_frame* out = &job.out;
+    // T1 + T2: caller planes -> (pinned staging ->) device, on the upload stream
+    for (int i = 0; i < a->n_in; i++) {
+        const int w = a->in_w[i], h = a->in_h[i];
+        const octvr_frame& f = in[i];
+        uint8_t* d = s.d_in[i]; uint8_t* hs = s.h_in[i];
+        const size_t ysz = (size_t)w * h, csz = (size_t)(w / 2) * (h / 2);
+        if (f.uv_pixel_stride == 1 && f.y_pitch == (size_t)w && f.u_pitch == (size_t)w / 2 && f.v_pitch == (size_t)w / 2 &&
+            f.u == f.y + ysz && f.v == f.u + csz && is_pinned(f.y)) {
+            OB_CUDA(cudaMemcpyAsync(d, f.y, ysz + 2 * csz, cudaMemcpyHostToDevice, a->s_up));       // contiguous pinned I420
+            continue;
+        }
+        upload_plane(d, hs, f.y, f.y_pitch, 1, w, h, a->s_up);
+        upload_plane(d + ysz, hs + ysz, f.u, f.u_pitch, f.uv_pixel_stride, w / 2, h / 2, a->s_up);
+        upload_plane(d + ysz + csz, hs + ysz + csz, f.v, f.v_pitch, f.uv_pixel_stride, w / 2, h / 2, a->s_up);
+    }
+    OB_CUDA(cudaEventRecord(s.uploaded, a->s_up));
+    // T3: every output region on the compute stream (async.cpp:70-91)
+    OB_CUDA(cudaStreamWaitEvent(a->s_run, s.uploaded, 0));
+    std::vector<octvr_frame> fin(a->n_in);
+    for (int i = 0; i < a->n_in; i++) fin[i] = i420_frame(s.d_in[i], a->in_w[i], a->in_h[i]);
+    const octvr_frame whole = i420_frame(s.d_out, a->out_w, a->out_h);
+    for (int r = 0; r < a->n_out; r++) {
+        const Rect& px = a->regions[r];
+        octvr_frame o = whole;
+        o.y += (size_t)px.y * whole.y_pitch + px.x;
+        o.u += (size_t)(px.y / 2) * whole.u_pitch + px.x / 2;
+        o.v += (size_t)(px.y / 2) * whole.v_pitch + px.x / 2;
+        const int gm = a->gain_modes[r];
+        const double* shared = (gm >= 0 && gm != r) ? a->mappers[gm]->d_gains : nullptr;   // gains of an earlier output
+        uint8_t* pv = nullptr;                                          // this output's part of the preview frame (async.cpp:78-79)
+        int pvw = 0, pvh = 0;
+        if (a->preview_w) {
+            const Rect& pr = a->preview_regions[r];
+            pv = s.d_preview + ((size_t)pr.y * a->preview_w + pr.x) * 3; pvw = pr.w; pvh = pr.h;
+        }
+        mapper_stitch_internal(*a->mappers[r], fin.data(), a->n_in, &o, nullptr, 0, shared, a->s_run, pv, (size_t)a->preview_w * 3, pvw, pvh);
+    }
+    OB_CUDA(cudaEventRecord(s.stitched, a->s_run));
+    // T4: device -> host on the download stream; straight into the caller's planes when they are pinned
+    OB_CUDA(cudaStreamWaitEvent(a->s_down, s.stitched, 0));
+    const int W = a->out_w, H = a->out_h;
+    const bool direct = out->uv_pixel_stride == 1 && is_pinned(out->y) && is_pinned(out->u) && is_pinned(out->v);
+    s.out_staged = !direct;
+    s.user_out = *out;
+    const bool tight = out->y_pitch == (size_t)W && out->u_pitch == (size_t)W / 2 && out->v_pitch == (size_t)W / 2;
+    if (direct && tight && out->u == out->y + (size_t)W * H && out->v == out->u + (size_t)(W / 2) * (H / 2)) {
+        OB_CUDA(cudaMemcpyAsync(out->y, s.d_out, (size_t)W * H * 3 / 2, cudaMemcpyDeviceToHost, a->s_down));      // contiguous I420
+    } else if (direct && tight) {
+        OB_CUDA(cudaMemcpyAsync(out->y, whole.y, (size_t)W * H, cudaMemcpyDeviceToHost, a->s_down));
+        OB_CUDA(cudaMemcpyAsync(out->u, whole.u, (size_t)(W / 2) * (H / 2), cudaMemcpyDeviceToHost, a->s_down));
+        OB_CUDA(cudaMemcpyAsync(out->v, whole.v, (size_t)(W / 2) * (H / 2), cudaMemcpyDeviceToHost, a->s_down));
+    } else if (direct) {
+        OB_CUDA(cudaMemcpy2DAsync(out->y, out->y_pitch, whole.y, whole.y_pitch, (size_t)W, (size_t)H, cudaMemcpyDeviceToHost, a->s_down));
+        OB_CUDA(cudaMemcpy2DAsync(out->u, out->u_pitch, whole.u, whole.u_pitch, (size_t)W / 2, (size_t)H / 2, cudaMemcpyDeviceToHost, a->s_down));
+        OB_CUDA(cudaMemcpy2DAsync(out->v, out->v_pitch, whole.v, whole.v_pitch, (size_t)W / 2, (size_t)H / 2, cudaMemcpyDeviceToHost, a->s_down));
+    } else {
+        OB_CUDA(cudaMemcpyAsync(s.h_out, s.d_out, (size_t)W * H * 3 / 2, cudaMemcpyDeviceToHost, a->s_down));
+    }
+    if (a->preview_w)
+        OB_CUDA(cudaMemcpyAsync(s.h_preview, s.d_preview, (size_t)a->preview_w * a->preview_h * 3, cudaMemcpyDeviceToHost, a->s_down));
+    OB_CUDA(cudaEventRecord(s.done, a->s_down));
+}
+
+void octvr_async::front_loop()
+{
+    cudaSetDevice(device);
+    for (;;) {
+        Job job;
+        Slot* s;
+        {
+            std::unique_lock<std::mutex> lk(mtx);
+            // a buffer set is free again once its frame has been copied out (T5), as in the reference's free-buffer queues
+            cv.wait(lk, [&] { return stop || (!queue.empty() && !slots[issued % BUF].busy); });
+            if (stop) return;
+            job = std::move(queue.front());
+            queue.pop_front();
+            s = &slots[issued % BUF];
+            s->busy = true;
+        }
+        int st = OCTVR_OK;
+        std::string msg;
+        try { issue(*s, job); }
+        catch (const Error& e) { st = e.code; msg = e.what(); }
+        catch (const std::exception& e) { st = OCTVR_ERR_INVALID; msg = e.what(); }
+        {
+            std::lock_guard<std::mutex> lk(mtx);
+            s->out_staged = s->out_staged && st == OCTVR_OK;
+            if (st != OCTVR_OK) { s->user_out = octvr_frame{}; worker_error = msg; }
+            status.push_back(st);
+            issued++;
+        }
+        cv.notify_all();
+    }
+}
+
+void octvr_async::back_loop()
+{
+    cudaSetDevice(device);
+    for (;;) {
+        Slot* s;
+        int st;
+        {
+            std::unique_lock<std::mutex> lk(mtx);
+            cv.wait(lk, [&] { return stop || completed < issued; });
+            if (stop && completed >= issued) return;
+            s = &slots[completed % BUF];
+            st = status[completed - popped];
+        }
+        if (st == OCTVR_OK) {
+            if (cudaEventSynchronize(s->done) != cudaSuccess) st = OCTVR_ERR_CUDA;
+            else if (s->out_staged) {              // T5 (async.cpp:113-172): staged planes -> the caller's planes
+                const int W = out_w, H = out_h;
+                const octvr_frame& o = s->user_out;
+                const uint8_t* hy = s->h_out; const uint8_t* hu = hy + (size_t)W * H; const uint8_t* hv = hu + (size_t)(W / 2) * (H / 2);
+                host_copy_plane(o.y, o.y_pitch, hy, (size_t)W, W, H, 1);
+                host_copy_plane(o.u, o.u_pitch, hu, (size_t)W / 2, W / 2, H / 2, 1, o.uv_pixel_stride);
+                host_copy_plane(o.v, o.v_pitch, hv, (size_t)W / 2, W / 2, H / 2, 1, o.uv_pixel_stride);
+            }
+        }
+        {
+            std::lock_guard<std::mutex> lk(mtx);
+            status[completed - popped] = st;
+            s->busy = false;
+            last_preview = s->h_preview;
+            completed++;
+            auto now = std::chrono::steady_clock::now();
+            stamps.push_back(now);
+            if (stamps.size() > 11) stamps.pop_front();
+            if (stamps.size() >= 2)
+                fps = (double)(stamps.size() - 1) / std::chrono::duration<double>(stamps.back() - stamps.front()).count();
+        }
+        cv.notify_all();
+    }
 }
 
 octvr_status octvr_async_pop(octvr_async* a)
 {
+    // async.cpp:191-193: blocks until the oldest pushed frame has left the last stage
     return guard([&] {
         OB_CHECK(a, "null argument");
-        Slot* sp;
-        {
-            std::lock_guard<std::mutex> lk(a->mtx);
-            OB_CHECK(a->popped < a->pushed, "pop() without a matching push()");
-            sp = &a->slots[a->popped % octvr_async::BUF];
-        }
-        Slot& s = *sp;
-        OB_CUDA(cudaSetDevice(a->device));
-        OB_CUDA(cudaEventSynchronize(s.done));
-        if (s.out_staged) {                      // T5 (async.cpp:113-172)
-            const int W = a->out_w, H = a->out_h;
-            const octvr_frame& o = s.user_out;
-            const uint8_t* hy = s.h_out; const uint8_t* hu = hy + (size_t)W * H; const uint8_t* hv = hu + (size_t)(W / 2) * (H / 2);
-            host_copy_plane(o.y, o.y_pitch, hy, (size_t)W, W, H, 1);
-            for (int y = 0; y < H / 2; y++)
-                for (int x = 0; x < W / 2; x++) {
-                    o.u[(size_t)y * o.u_pitch + (size_t)x * o.uv_pixel_stride] = hu[(size_t)y * (W / 2) + x];
-                    o.v[(size_t)y * o.v_pitch + (size_t)x * o.uv_pixel_stride] = hv[(size_t)y * (W / 2) + x];
-                }
-        }
-        std::lock_guard<std::mutex> lk(a->mtx);
-        s.busy = false;
-        a->last_preview = s.h_preview;
+        std::unique_lock<std::mutex> lk(a->mtx);
+        OB_CHECK(a->popped < a->pushed, "pop() without a matching push()");
+        a->cv.wait(lk, [&] { return a->completed > a->popped; });
+        const int st = a->status.front();
+        a->status.pop_front();
         a->popped++;
-        auto now = std::chrono::steady_clock::now();
-        a->stamps.push_back(now);
-        if (a->stamps.size() > 11) a->stamps.pop_front();
-        if (a->stamps.size() >= 2)
-            a->fps = (double)(a->stamps.size() - 1) / std::chrono::duration<double>(a->stamps.back() - a->stamps.front()).count();
+        if (st != OCTVR_OK) fail(st, "a pipeline stage failed: " + a->worker_error);
     });
 }
 

@@ -11,6 +11,7 @@ struct CamSrc {
     int uv_step;              // 1 planar, 2 NV12; packed RGB24 / BGR24 input: 3, with y / u / v = the R / G / B byte of pixel 0 and all
                               // three pitches = the row pitch (rgb = 1)
     int rgb;
+    int row0, row1;           // rows [row0, row1) are converted (row0 even); the whole image unless the mapper is a row-band mapper
     int w, h;
     uint32_t* rgbx;           // w*h, pitch = w pixels
     const float* vignette;    // w*h f32 or null

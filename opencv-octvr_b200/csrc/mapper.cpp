@@ -325,6 +325,21 @@ static void build_mapper(octvr_mapper& m, const octvr_template& t, const int* in
         for (uint8_t v : t.inputs[i].mask.d) m.pairs += v != 0;
     }
 
+    // source rows a row-band mapper touches (feather / no blend: the taps of its own output rows; the multiband set-up
+    // widens this to its row window)
+    m.src_row0.assign(n + n_ov, 0);
+    for (int i = 0; i < n + n_ov; i++) m.src_row1.push_back(m.in_h[i]);
+    if (m.band_y0 != 0 || m.band_y1 != t.out_h)
+        for (int i = 0; i < n; i++) {
+            const TInput& in = t.inputs[i];
+            int lo = INT32_MAX, hi = INT32_MIN;
+            for (int y = std::max(0, m.band_y0 - in.roi.y); y < std::min(in.roi.h, m.band_y1 - in.roi.y); y++)
+                for (int x = 0; x < in.roi.w; x++)
+                    if (in.mask.row(y)[x]) { const int iy = sy[i].row(y)[x] >> 5; lo = std::min(lo, iy); hi = std::max(hi, iy + 1); }
+            if (lo > hi) { m.src_row0[i] = m.src_row1[i] = 0; continue; }
+            m.src_row0[i] = std::max(0, lo) & ~1; m.src_row1[i] = std::min(m.in_h[i], hi + 1);
+        }
+
     std::vector<Img<float>> W;
     if (blend <= 0) {
         W = blend < 0 ? feather_weights(t.inputs, -blend) : overwrite_weights(t.inputs);
@@ -738,8 +753,9 @@ void ob::mapper_stitch_internal(octvr_mapper& m, const octvr_frame* in, int n_in
             ? ((uintptr_t)c.u % 4 == 0 && (uintptr_t)c.v % 4 == 0 && c.u_pitch % 4 == 0 && c.v_pitch % 4 == 0)
             : ((uintptr_t)c.u % 8 == 0 && c.u_pitch % 8 == 0 && c.v == c.u + 1);
         c.aligned4 = ((uintptr_t)c.y % 8 == 0) && (c.y_pitch % 8 == 0) && (c.w % 4 == 0) && chroma_ok;
+        c.row0 = m.src_row0[i]; c.row1 = m.src_row1[i];
         cp.grid_x = std::max(cp.grid_x, (c.w + 255) / 256);
-        cp.grid_y = std::max(cp.grid_y, (c.h + 15) / 16);
+        cp.grid_y = std::max(cp.grid_y, (c.row1 - c.row0 + 15) / 16);
     }
     // one launch: gain statistics + solve (reading the input planes directly) in the first CTAs, conversion in the rest
     // (fused path: no conversion pass at all, the launch only carries the gain CTAs)
@@ -967,6 +983,14 @@ octvr_status octvr_mapper_stats(const octvr_mapper* m, int64_t* pairs, int64_t* 
     });
 }
 
+octvr_status octvr_mapper_source_rows(const octvr_mapper* m, int* rows_lo_hi, int n)
+{
+    return guard([&] {
+        OB_CHECK(m && rows_lo_hi && n == m->n, "bad argument");
+        for (int i = 0; i < n; i++) { rows_lo_hi[2 * i] = m->src_row0[i]; rows_lo_hi[2 * i + 1] = m->src_row1[i]; }
+    });
+}
+
 octvr_status octvr_mapper_set_profiling(octvr_mapper* m, int on)
 {
     return guard([&] { OB_CHECK(m, "null argument"); m->profiling = on != 0; });
@@ -1017,6 +1041,45 @@ octvr_status octvr_mapper_debug_ring(octvr_mapper* m, unsigned long long* out8)
         OB_CUDA(cudaDeviceSynchronize());
         OB_CUDA(cudaMemcpy(out8, m->d_dbg_ring, 8 * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
         OB_CUDA(cudaMemset(m->d_dbg_ring, 0, 8 * sizeof(unsigned long long)));
+    });
+}
+
+// ---- device buffers shared between the processes of one node (row-band mode: every rank stores its band of the frame
+//      straight into the collecting rank's buffer over NVLink peer memory; no collection step) ----
+octvr_status octvr_shared_alloc(size_t bytes, int device, void** d_ptr, unsigned char handle64[64])
+{
+    return guard([&] {
+        OB_CHECK(bytes > 0 && d_ptr && handle64, "bad argument");
+        static_assert(sizeof(cudaIpcMemHandle_t) == 64, "cudaIpcMemHandle_t is 64 bytes");
+        OB_CUDA(cudaSetDevice(device));
+        void* p = nullptr;
+        OB_CUDA(cudaMalloc(&p, bytes));
+        cudaIpcMemHandle_t h;
+        cudaError_t e = cudaIpcGetMemHandle(&h, p);
+        if (e != cudaSuccess) { cudaFree(p); fail(OCTVR_ERR_CUDA, std::string("cudaIpcGetMemHandle: ") + cudaGetErrorString(e)); }
+        OB_CUDA(cudaMemset(p, 0, bytes));
+        OB_CUDA(cudaDeviceSynchronize());
+        memcpy(handle64, &h, 64);
+        *d_ptr = p;
+    });
+}
+
+octvr_status octvr_shared_open(const unsigned char handle64[64], int device, void** d_ptr)
+{
+    return guard([&] {
+        OB_CHECK(handle64 && d_ptr, "bad argument");
+        OB_CUDA(cudaSetDevice(device));
+        cudaIpcMemHandle_t h;
+        memcpy(&h, handle64, 64);
+        OB_CUDA(cudaIpcOpenMemHandle(d_ptr, h, cudaIpcMemLazyEnablePeerAccess));
+    });
+}
+
+octvr_status octvr_shared_close(void* d_ptr, int opened)
+{
+    return guard([&] {
+        if (!d_ptr) return;
+        if (opened) OB_CUDA(cudaIpcCloseMemHandle(d_ptr)); else OB_CUDA(cudaFree(d_ptr));
     });
 }
 

@@ -19,6 +19,8 @@ struct octvr_mapper {
     // tile-compacted tables (feather / no-blend)
     int tiles_x = 0, tiles_y = 0;
     int band_y0 = 0, band_y1 = 0;       // output rows this mapper produces (multi-GPU row-band mode); default: all rows
+    std::vector<int> src_row0, src_row1; // per camera: the source rows [row0, row1) some table entry of this mapper reads (a row-band mapper
+                                        // converts only those to RGBX); default: all rows
     size_t njobs = 0;
     uint32_t* d_tile_job_start = nullptr;
     uint8_t* d_job_cam = nullptr;

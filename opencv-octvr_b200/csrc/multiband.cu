@@ -25,6 +25,8 @@
 #include <map>
 #include <memory>
 #include <string>
+#include <thread>
+#include <exception>
 #include <climits>
 
 namespace ob {
@@ -796,6 +798,17 @@ Multiband* multiband_create(octvr_mapper& m, const octvr_template& t,
     std::vector<MbWarpJob> wjobs;
     std::vector<uint32_t> wentries;
     std::map<uint64_t, int> tmap_index;                     // (camera, box w, box h) -> descriptor slot
+
+    // ---- phase 0 (sequential, cheap): geometry of every camera rectangle, offsets into the shared arrays ----
+    struct CamBuild {
+        int top = 0, left = 0, width = 0, height = 0, ys = 0, ye = 0, ch = 0;
+        std::vector<MbWarpJob> jobs; std::vector<uint32_t> entries; std::vector<uint64_t> keys;   // job.tmap = index into keys
+        std::vector<uint2> chunks;
+        std::vector<Img<float>> wl;                         // weight pyramid of the full rectangle, levels 0 .. nb
+        bool staged_ok = true;
+        int src_lo = INT32_MAX, src_hi = INT32_MIN;
+    };
+    std::vector<CamBuild> cb(n);
     for (int i = 0; i < n; i++) {
         const TInput& in = t.inputs[i];
         MbCam& c = p.cam[i];
@@ -809,23 +822,32 @@ Multiband* multiband_create(octvr_mapper& m, const octvr_template& t,
         bnx = tnx + width; bny = tny + height;
         const int dy = std::max(bny - (Rf.y + PH), 0), dx = std::max(bnx - (Rf.x + PW), 0);
         tnx -= dx; bnx -= dx; tny -= dy; bny -= dy;
-        const int top = in.roi.y - tny, left = in.roi.x - tnx;
+        CamBuild& b = cb[i];
+        b.top = in.roi.y - tny; b.left = in.roi.x - tnx; b.width = width; b.height = height;
         // rows [ys, ye) of the full rectangle fall inside the row window (all of it without row bands)
         const int fy0 = tny - Rf.y;
-        const int ys = std::min(height, std::max(0, E0 - fy0)), ye = std::max(ys, std::min(height, E1 - fy0));
-        const int ch = ye - ys;
-        c.x0 = tnx - Rf.x; c.y0 = fy0 + ys - E0; c.bw = width; c.bh = ch;
-        if (ch > 0) { mb->max_bw = std::max(mb->max_bw, width); mb->max_bh = std::max(mb->max_bh, ch); }
-        c.off_g[0] = g0_total; g0_total += (size_t)width * ch;
+        b.ys = std::min(height, std::max(0, E0 - fy0)); b.ye = std::max(b.ys, std::min(height, E1 - fy0));
+        b.ch = b.ye - b.ys;
+        c.x0 = tnx - Rf.x; c.y0 = fy0 + b.ys - E0; c.bw = width; c.bh = b.ch;
+        if (b.ch > 0) { mb->max_bw = std::max(mb->max_bw, width); mb->max_bh = std::max(mb->max_bh, b.ch); }
+        c.off_g[0] = g0_total; g0_total += (size_t)width * b.ch;
         // every level starts at an even element: 16-byte aligned rows for the vector loads of mb_down_strip_p16
-        for (int l = 1; l <= nb; l++) { c.off_g[l] = g_total; g_total += (size_t)(width >> l) * (ch >> l); g_total += g_total & 1; }
-        // level-0 remap table with BORDER_REFLECT baked in, and the f32 weight map (BORDER_CONSTANT 0)
+        for (int l = 1; l <= nb; l++) { c.off_g[l] = g_total; g_total += (size_t)(width >> l) * (b.ch >> l); g_total += g_total & 1; }
+    }
+    coords.resize(g0_total);
+
+    // ---- phase 1 (one host thread per camera): level-0 remap table with BORDER_REFLECT baked in, the f32 weight map
+    //      (BORDER_CONSTANT 0) and its Gaussian pyramid, the staged warp jobs of the camera ----
+    const bool want_staged = staged;
+    auto build_cam = [&](int i) {
+        const TInput& in = t.inputs[i];
+        CamBuild& b = cb[i];
+        const int width = b.width, height = b.height, ys = b.ys, ye = b.ye, ch = b.ch, top = b.top, left = b.left;
         Img<float> wmap(width, height, 0.f);
         const float inv255 = (float)(1. / 255.);
-        coords.resize(coords.size() + (size_t)width * ch);
-        uint2* ce = coords.data() + c.off_g[0];
+        uint2* ce = coords.data() + p.cam[i].off_g[0];
         std::vector<int16_t> qx, qy;                            // integer tap position of every valid pixel (staged warp)
-        if (staged) { qx.assign((size_t)width * ch, 0); qy.assign((size_t)width * ch, 0); }
+        if (want_staged) { qx.assign((size_t)width * ch, 0); qy.assign((size_t)width * ch, 0); }
         for (int y = 0; y < height; y++) {
             const int ly = mirror(y - top, in.roi.h);
             const bool in_y = y - top >= 0 && y - top < in.roi.h;
@@ -837,14 +859,16 @@ Multiband* multiband_create(octvr_mapper& m, const octvr_template& t,
                     const int32_t fsx = sx[i].row(ly)[lx], fsy = sy[i].row(ly)[lx];
                     const size_t at = (size_t)(y - ys) * width + x;
                     ce[at] = mk_entry(fsx, fsy, m.in_w[i], m.in_h[i], in.mask.row(ly)[lx] != 0);
-                    if (staged) { qx[at] = (int16_t)std::min(32767, std::max(-32768, fsx >> 5)); qy[at] = (int16_t)std::min(32767, std::max(-32768, fsy >> 5)); }
+                    if (ce[at].y & C_VALID) { b.src_lo = std::min(b.src_lo, fsy >> 5); b.src_hi = std::max(b.src_hi, (fsy >> 5) + 1); }
+                    if (want_staged) { qx[at] = (int16_t)std::min(32767, std::max(-32768, fsx >> 5)); qy[at] = (int16_t)std::min(32767, std::max(-32768, fsy >> 5)); }
                 }
                 if (in_y && x - left >= 0 && x - left < in.roi.w) wmap.row(y)[x] = seams[i].row(y - top)[x - left] * inv255 + 0.f;
             }
         }
         // staged warp: one job per 32 x 16 tile of the rectangle that has a valid pixel
-        for (int ty = 0; staged && ty < (ch + TILE_H - 1) / TILE_H; ty++)
-            for (int tx = 0; staged && tx < (width + TILE_W - 1) / TILE_W; tx++) {
+        std::map<uint64_t, int> local_keys;
+        for (int ty = 0; want_staged && b.staged_ok && ty < (ch + TILE_H - 1) / TILE_H; ty++)
+            for (int tx = 0; b.staged_ok && tx < (width + TILE_W - 1) / TILE_W; tx++) {
                 int xmin = INT32_MAX, xmax = INT32_MIN, ymin = INT32_MAX, ymax = INT32_MIN;
                 for (int py = ty * TILE_H; py < std::min(ch, (ty + 1) * TILE_H); py++)
                     for (int px = tx * TILE_W; px < std::min(width, (tx + 1) * TILE_W); px++) {
@@ -858,49 +882,102 @@ Multiband* multiband_create(octvr_mapper& m, const octvr_template& t,
                 memset(&job, 0, sizeof(job));
                 job.bx0 = (int)std::floor(xmin / 4.0) * 4; job.by0 = ymin;          // TMA: the innermost start coordinate must be 16-byte aligned
                 const int bw = size_class(xmax - job.bx0 + 1), bh = size_class(ymax - ymin + 1);
-                if (bw > 256 || bh > 256 || (int64_t)bw * bh > MB_STAGE || tx > 65535 || ty > 65535) { staged = false; break; }
+                if (bw > 256 || bh > 256 || (int64_t)bw * bh > MB_STAGE || tx > 65535 || ty > 65535) { b.staged_ok = false; break; }
                 job.bw = (uint16_t)bw; job.bh = (uint16_t)bh; job.cam = (uint16_t)i; job.tx = (uint16_t)tx; job.ty = (uint16_t)ty;
                 const uint64_t key = ((uint64_t)i << 32) | ((uint64_t)bw << 16) | (uint64_t)bh;
-                auto it = tmap_index.find(key);
-                if (it == tmap_index.end()) it = tmap_index.emplace(key, (int)tmap_index.size()).first;
-                job.tmap = (uint16_t)it->second;
-                if (tmap_index.size() > 65535) { staged = false; break; }
-                const size_t e0 = wentries.size();
-                wentries.resize(e0 + TILE_PX, 0u);
+                auto it = local_keys.find(key);
+                if (it == local_keys.end()) { it = local_keys.emplace(key, (int)b.keys.size()).first; b.keys.push_back(key); }
+                job.tmap = (uint16_t)it->second;                    // local index; renumbered when the cameras are merged
+                if (b.keys.size() > 60000) { b.staged_ok = false; break; }
+                const size_t e0 = b.entries.size();
+                b.entries.resize(e0 + TILE_PX, 0u);
                 for (int py = ty * TILE_H; py < std::min(ch, (ty + 1) * TILE_H); py++)
                     for (int px = tx * TILE_W; px < std::min(width, (tx + 1) * TILE_W); px++) {
                         const size_t at = (size_t)py * width + px;
                         if (!(ce[at].y & C_VALID)) continue;
                         const uint32_t off = (uint32_t)((qy[at] - job.by0) * bw + (qx[at] - job.bx0));
-                        wentries[e0 + (size_t)(py - ty * TILE_H) * TILE_W + (px - tx * TILE_W)] =
+                        b.entries[e0 + (size_t)(py - ty * TILE_H) * TILE_W + (px - tx * TILE_W)] =
                             off | ((ce[at].y >> 5) & 31u) << 13 | (ce[at].y & 31u) << 18 | MBW_VALID;      // fy, fx of the table entry
                     }
-                wjobs.push_back(job);
+                b.jobs.push_back(job);
             }
         for (size_t k = 0; k < ((size_t)width * ch + 255) / 256; k++) {
             bool any = false;
             for (size_t e = k * 256; e < std::min((k + 1) * 256, (size_t)width * ch) && !any; e++) any = (ce[e].y & C_VALID) != 0;
-            if (any) chunks.push_back(make_uint2((uint32_t)i, (uint32_t)k));
+            if (any) b.chunks.push_back(make_uint2((uint32_t)i, (uint32_t)k));
         }
-        while (chunks.size() % MB_WARP_CHUNKS) chunks.push_back(make_uint2((uint32_t)i, 0xFFFFFFFFu));   // a CTA's chunks share a camera
-        Img<float> wl = std::move(wmap);
-        int xt = c.x0, yt = c.y0;
+        while (b.chunks.size() % MB_WARP_CHUNKS) b.chunks.push_back(make_uint2((uint32_t)i, 0xFFFFFFFFu));   // a CTA's chunks share a camera
+        b.wl.resize(nb + 1);
+        b.wl[0] = std::move(wmap);
+        for (int l = 1; l <= nb; l++) b.wl[l] = pyrdown_f32(b.wl[l - 1]);
+    };
+    {
+        std::vector<std::thread> th;
+        std::vector<std::exception_ptr> errs(n);
+        for (int i = 0; i < n; i++)
+            th.emplace_back([&, i] { try { build_cam(i); } catch (...) { errs[i] = std::current_exception(); } });
+        for (auto& q : th) q.join();
+        for (auto& e : errs) if (e) std::rethrow_exception(e);
+    }
+
+    // ---- phase 2 (sequential): merge in camera order ----
+    for (int i = 0; i < n; i++) staged = staged && cb[i].staged_ok;
+    for (int i = 0; i < n; i++) {
+        CamBuild& b = cb[i];
+        MbCam& c = p.cam[i];
+        if (m.band_y0 != 0 || m.band_y1 != t.out_h) {          // row-band mapper: only these source rows need converting
+            if (b.src_lo > b.src_hi) m.src_row0[i] = m.src_row1[i] = 0;
+            else { m.src_row0[i] = std::max(0, b.src_lo) & ~1; m.src_row1[i] = std::min(m.in_h[i], b.src_hi + 1); }
+        }
+        if (staged) {
+            std::vector<int> slot(b.keys.size());
+            for (size_t k = 0; k < b.keys.size(); k++) {
+                auto it = tmap_index.find(b.keys[k]);
+                if (it == tmap_index.end()) it = tmap_index.emplace(b.keys[k], (int)tmap_index.size()).first;
+                slot[k] = it->second;
+            }
+            if (tmap_index.size() > 65535) staged = false;
+            for (MbWarpJob& j : b.jobs) j.tmap = (uint16_t)slot[j.tmap];
+            wjobs.insert(wjobs.end(), b.jobs.begin(), b.jobs.end());
+            wentries.insert(wentries.end(), b.entries.begin(), b.entries.end());
+        }
+        std::vector<MbWarpJob>().swap(b.jobs); std::vector<uint32_t>().swap(b.entries);
+        chunks.insert(chunks.end(), b.chunks.begin(), b.chunks.end());
         for (int l = 0; l <= nb; l++) {
             c.off_w[l] = wts.size();
-            const int r0 = ys >> l, r1 = ye >> l;                   // the window's rows of the full level-l weight map
-            wts.insert(wts.end(), wl.d.begin() + (size_t)r0 * wl.w, wl.d.begin() + (size_t)r1 * wl.w);
-            for (int y = 0; y < r1 - r0; y++) {                     // dst_band_weights_[l](rc) += weight (blenders.cpp:421)
-                float* dr = dstw.data() + p.off_d[l] + (size_t)(yt + y) * p.lw[l] + xt;
-                const float* wr = wl.row(r0 + y);
-                for (int x = 0; x < wl.w; x++) {
-                    dr[x] += wr[x];
-                    if (wr[x] != 0.f) tile_cams[p.off_t[l] + (size_t)((yt + y) / 8) * ((p.lw[l] + 31) / 32) + (xt + x) / 32] |= (uint16_t)(1u << i);
-                }
-            }
-            if (l < nb) wl = pyrdown_f32(wl);
-            xt /= 2; yt /= 2;
+            const int r0 = b.ys >> l, r1 = b.ye >> l;               // the window's rows of the full level-l weight map
+            wts.insert(wts.end(), b.wl[l].d.begin() + (size_t)r0 * b.wl[l].w, b.wl[l].d.begin() + (size_t)r1 * b.wl[l].w);
         }
     }
+    if (!staged) { wjobs.clear(); wentries.clear(); tmap_index.clear(); }
+    // dst_band_weights_[l](rc) += weight (blenders.cpp:421), cameras in order for every element; threads split the dst rows
+    for (int l = 0; l <= nb; l++) {
+        const int rows = p.lh[l];
+        const int nt = std::max(1, std::min(16, rows / 64));
+        std::vector<std::thread> th;
+        for (int q = 0; q < nt; q++)
+            th.emplace_back([&, q] {
+                // whole 8-row groups per thread: tile_cams words are not shared between threads
+                const int g0 = (rows + 7) / 8 * q / nt * 8, g1 = std::min(rows, (rows + 7) / 8 * (q + 1) / nt * 8);
+                for (int i = 0; i < n; i++) {
+                    const CamBuild& b = cb[i];
+                    const MbCam& c = p.cam[i];
+                    const int xt = c.x0 >> l, yt = c.y0 >> l, r0 = b.ys >> l, r1 = b.ye >> l;
+                    const Img<float>& wl = b.wl[l];
+                    for (int y = std::max(0, g0 - yt); y < std::min(r1 - r0, g1 - yt); y++) {
+                        float* dr = dstw.data() + p.off_d[l] + (size_t)(yt + y) * p.lw[l] + xt;
+                        const float* wr = wl.row(r0 + y);
+                        uint16_t* tc = tile_cams.data() + p.off_t[l] + (size_t)((yt + y) / 8) * ((p.lw[l] + 31) / 32);
+                        for (int x = 0; x < wl.w; x++) {
+                            dr[x] += wr[x];
+                            if (wr[x] != 0.f) tc[(xt + x) / 32] |= (uint16_t)(1u << i);
+                        }
+                    }
+                }
+            });
+        for (auto& q : th) q.join();
+    }
+    cb.clear();
     if (staged && !wjobs.empty()) {
         std::vector<uint8_t> tmaps(tmap_index.size() * 128);
         for (auto& kv : tmap_index) {

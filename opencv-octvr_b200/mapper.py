@@ -250,6 +250,13 @@ class Mapper:
         check(lib().octvr_mapper_stats(self._h, C.byref(pairs), C.byref(roi), C.byref(tb), C.byref(ln)))
         return dict(pairs=pairs.value, roi_area=roi.value, table_bytes=tb.value, launches_per_stitch=ln.value)
 
+    def src_rows(self):
+        """per blended input: the source rows (lo, hi) this mapper converts and reads (all rows unless it is a row-band mapper)."""
+        n = self.tmpl.num_inputs
+        a = (C.c_int * (2 * n))()
+        check(lib().octvr_mapper_source_rows(self._h, a, n))
+        return [(a[2 * i], a[2 * i + 1]) for i in range(n)]
+
     def set_profiling(self, on=True):
         check(lib().octvr_mapper_set_profiling(self._h, int(on)))
 
@@ -309,8 +316,8 @@ class AsyncMultiMapper:
         """inputs: list of (y,u,v) host u8 numpy arrays; output: (y,u,v) host arrays to be filled by the matching pop."""
         fin = (Frame * len(inputs))(*[p.frame() if isinstance(p, PackedRGB) else frame_from_planes(*p) for p in inputs])
         fout = frame_from_planes(*output)
-        self._keep.append((inputs, output))
         check(lib().octvr_async_push(self._h, fin, len(inputs), C.byref(fout)))
+        self._keep.append((inputs, output))           # only an accepted push owns a pop: keep the planes alive until then
 
     def pop(self):
         check(lib().octvr_async_pop(self._h))

@@ -117,6 +117,57 @@ def collect_bands(out, dst=0):
     return out
 
 
+class PeerFrame:
+    """A packed output frame (rows x width u8) that lives on rank `owner` and is mapped into every rank of the node
+    (octvr_shared_alloc / octvr_shared_open: CUDA IPC, NVLink peer access).  `tensor` is a torch view of it on every rank;
+    a band mapper that is given this view as its output stores its rows straight into the owner's memory, so the row-band
+    mode needs no collection step.  Collective constructor (the handle travels by all_gather_object)."""
+
+    def __init__(self, rows, width, device, owner=0):
+        import ctypes as C
+        from .capi import lib, check
+        self._C, self._lib, self._check = C, lib, check
+        self.rank = dist.get_rank() if dist.is_initialized() else 0
+        world = dist.get_world_size() if dist.is_initialized() else 1
+        self.owner, self.opened = owner, self.rank != owner
+        self.nbytes = rows * width
+        ptr = C.c_void_p()
+        handle = (C.c_ubyte * 64)()
+        if self.rank == owner:
+            check(lib().octvr_shared_alloc(C.c_size_t(self.nbytes), int(device), C.byref(ptr), handle))
+        blobs = [None] * world
+        if world > 1:
+            dist.all_gather_object(blobs, bytes(handle) if self.rank == owner else None)
+        if self.rank != owner:
+            handle = (C.c_ubyte * 64).from_buffer_copy(blobs[owner])
+            check(lib().octvr_shared_open(handle, int(device), C.byref(ptr)))
+        self.ptr = ptr.value
+
+        class _Iface:                                   # torch.as_tensor reads __cuda_array_interface__
+            pass
+        holder = _Iface()
+        holder.__cuda_array_interface__ = {"shape": (rows, width), "typestr": "|u1", "data": (self.ptr, False), "version": 3, "strides": None}
+        self._holder = holder
+        self.tensor = torch.as_tensor(holder, device=torch.device("cuda", device))
+
+    def close(self):
+        if self.ptr:
+            torch.cuda.synchronize()
+            if dist.is_initialized() and dist.get_world_size() > 1:
+                dist.barrier()                          # nobody may still be storing into the owner's memory
+            self.tensor = None
+            self._check(self._lib().octvr_shared_close(self._C.c_void_p(self.ptr), int(self.opened)))
+            self.ptr = None
+
+
+def frame_complete(token):
+    """Row-band mode with PeerFrame outputs: the frame on the owner is complete when every rank's stitch has finished.
+    One 4-byte all-reduce enqueued behind the stitch on every rank; the owner's stream is past it only when all are."""
+    if dist.is_initialized() and dist.get_world_size() > 1:
+        dist.all_reduce(token)
+    return token
+
+
 class RowBandStitcher:
     """One large frame split over the ranks by output row bands (BASELINE config C4's partition; feather / no blend).
     Every rank constructs it with the same template; stitch() is collective."""
@@ -209,9 +260,12 @@ class FramePipeline:
     stitcher: RowBandStitcher or StereoRowBandStitcher.  With defer_collect the caller alternates between (at least) two
     output buffers: a buffer is being read by its collection until the step after next begins (or flush() returns)."""
 
-    def __init__(self, stitcher, src=0, defer_collect=False):
-        self.st, self.src, self.pending, self.defer = stitcher, src, {}, defer_collect
+    def __init__(self, stitcher, src=0, defer_collect=False, peer=False):
+        """peer=True: `out` passed to step() is a PeerFrame.tensor (the owner's memory mapped on every rank): the bands are
+        stored there directly, and the collection is replaced by frame_complete()."""
+        self.st, self.src, self.pending, self.defer, self.peer = stitcher, src, {}, defer_collect, peer
         self.collecting = {}                            # output buffer -> work handles of its band collection
+        self.token = None
 
     def _wait_collect(self, out):
         for w in self.collecting.pop(out.data_ptr(), []):
@@ -231,7 +285,11 @@ class FramePipeline:
             self.st.stitch_local(frames, out)
         else:
             self.st.mapper.stitch_packed(frames, out)
-        if collect:
+        if collect and self.peer:
+            if self.token is None:
+                self.token = torch.zeros(1, dtype=torch.int32, device=out.device)
+            frame_complete(self.token)
+        elif collect:
             if self.defer:
                 self.collecting[out.data_ptr()] = collect_shares(out, self.st.shares(), self.src, wait=False)
             else:

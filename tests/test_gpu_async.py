@@ -65,6 +65,46 @@ def test_async_push_pop_matches_oracle_in_order(pinned):
     am.close()
 
 
+def test_async_push_only_enqueues_pageable_planes():
+    """Reference contract (async.cpp:174-189): push() validates and queues, the copies into pinned staging (T1) and out of
+    it (T5) happen on the pipeline's own threads.  So push() with PAGEABLE planes returns in a small fraction of a frame
+    time, any number of frames can be queued ahead (only three are in flight inside), and results come back in order."""
+    import time
+    cfg, width, in_size = util.named_rig("rig2")               # 2 x 1920x1080 -> 2048x1024: 6.2 MB in, 3.1 MB out per frame
+    t = vr.MapperTemplate.from_json(cfg, width)
+    W, H = t.out_size
+    n = 2
+    am = vr.AsyncMultiMapper([t], [in_size] * n, (W, H), [-1], [0], [(0.0, 0.0, 1.0, 1.0)])
+    n_frames = 8
+    frames = [[util.noise_frame(c, *in_size, seed=900 + k) for c in range(n)] for k in range(n_frames)]        # pageable numpy
+    outs = [np.zeros(W * H * 3 // 2, np.uint8) for _ in range(n_frames)]
+    am.push([util.i420_planes(f, *in_size) for f in frames[0]], util.i420_planes(outs[0], W, H)); am.pop()     # warm up
+    t0 = time.perf_counter()
+    push_s = []
+    for k in range(n_frames):                                  # all eight queued before the first pop
+        a = time.perf_counter()
+        am.push([util.i420_planes(f, *in_size) for f in frames[k]], util.i420_planes(outs[k], W, H))
+        push_s.append(time.perf_counter() - a)
+    for k in range(n_frames):
+        am.pop()
+    per_frame = (time.perf_counter() - t0) / n_frames
+    print("push %.0f us (median), frame %.0f us" % (1e6 * float(np.median(push_s)), 1e6 * per_frame))
+    assert float(np.median(push_s)) < 0.25 * per_frame, (push_s, per_frame)
+    # in order and correct: every frame equals the synchronous Mapper on the same planes
+    m = vr.Mapper(t, [in_size] * n, blend=-1, enable_gain_compensator=True)
+    for k in (0, 3, 7):
+        ins = []
+        for f in frames[k]:
+            y, u, v = util.i420_planes(f, *in_size)
+            ins.append(torch.from_numpy(np.concatenate([y, np.concatenate([u, v], 1)], 0)).cuda())
+        o = torch.zeros((H * 3 // 2, W), dtype=torch.uint8, device="cuda")
+        m.stitch_packed(ins, o)
+        ry, ru, rv = [p.cpu().numpy() for p in vr.split_packed(o, W, H)]
+        y, u, v = util.i420_planes(outs[k], W, H)
+        assert np.array_equal(y, ry) and np.array_equal(u, ru) and np.array_equal(v, rv), "frame %d" % k
+    am.close()
+
+
 def test_async_two_regions_share_gains():
     """Stereo top-bottom style: two templates into the top and bottom halves of one frame; the second
     region reuses the gains computed by the first (gain_modes = [0, 0], async.cpp:75-86)."""
@@ -109,4 +149,8 @@ def test_async_rejects_bad_arguments():
     out = np.zeros(128 * 64 * 3 // 2, np.uint8)
     with pytest.raises(vr.OctvrError):
         am.push([util.i420_planes(f, 192, 108)], util.i420_planes(out, 128, 64))                # wrong input count
+    with pytest.raises(vr.OctvrError):                                                           # output planes narrower than the frame
+        am.push([util.i420_planes(f, 192, 108)] * 2, util.i420_planes(np.zeros(64 * 32 * 3 // 2, np.uint8), 64, 32))
+    with pytest.raises(vr.OctvrError):
+        am.pop()                                                                                 # the rejected pushes left nothing behind
     am.close()
