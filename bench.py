@@ -278,7 +278,7 @@ def measure_single(args, workload, steps, warmup, with_e2e):
 
 
 def sub_summary(line, keys=("value", "unit", "ms_per_step", "frames_per_s", "n_gpus", "steps", "warmup", "scaling", "frac_of_hbm_roofline", "roofline",
-                            "stage_ms", "stage_ms_rank0", "stitch_only_ms_max_over_ranks", "assembled_frame_equals_single_gpu_result",
+                            "stage_ms", "stage_ms_rank0", "stitch_only_ms_max_over_ranks", "host_enqueue_ms_per_step_rank0", "assembled_frame_equals_single_gpu_result",
                             "exchange_alone_ms", "gpu_launches", "ms_per_frame_per_gpu", "clocks")):
     if line is None:
         return None
@@ -574,9 +574,11 @@ def run_stereo(args, sub=False):
     sampler = ClockSampler(local) if rank == 0 else None
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
+    t_host = time.perf_counter()
     for k in range(args.steps):
         step(k, last=(k == args.steps - 1))
     e1.record()
+    host_enqueue_ms = (time.perf_counter() - t_host) * 1e3 / args.steps      # host time to enqueue a step (a floor for the step time)
     torch.cuda.synchronize()
     clocks = sampler.stop() if sampler else None
     ms = vr.sharding.max_over_ranks(e0.elapsed_time(e1), device="cuda")
@@ -641,7 +643,7 @@ def run_stereo(args, sub=False):
         "alg_bytes_per_frame": int(B),
         "frac_of_hbm_roofline": {"whole_step_vs_measured_%.0f_x%d" % (peak, world): round(B / (ms_per_step * 1e-3) / 1e9 / (peak * world), 4)},
         "stage_ms_rank0": {k: round(statistics.median(v), 5) for k, v in stage.items()},
-        "stitch_only_ms_max_over_ranks": round(local_ms, 5),
+        "stitch_only_ms_max_over_ranks": round(local_ms, 5), "host_enqueue_ms_per_step_rank0": round(host_enqueue_ms, 4),
         "gpu_launches": sum(s_["launches_per_stitch"] for s_ in stats) * args.steps,
         "clocks": clocks,
     }
