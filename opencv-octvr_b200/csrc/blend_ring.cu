@@ -22,6 +22,7 @@
 //   * the FP32 part of an entry pair runs on packed FFMA2 / FMUL2 / FADD2 (sm_100 f32x2, with directed rounding);
 //     the bilinear sum is produced directly as the mantissa of a float (IDP.2A accumulating onto bits(2^23)): no I2F.
 #include "kernels.cuh"
+#include <cstdlib>
 #include "device_common.cuh"
 
 namespace ob {
@@ -223,6 +224,11 @@ __global__ void __launch_bounds__(RG_THREADS, RG_MIN_CTAS) k_blend_ring(const __
 
     if (warp == RG_CONS_WARPS) {
         // ------------------------------------------------------------------ producer warp
+        // Programmatic dependent launch: this grid may become resident while the previous kernel of the stream (conversion + gain
+        // chain) is still finishing; everything above touched only this CTA's shared memory.  From here on the producer reads what
+        // that kernel wrote (gains, RGBX planes through TMA), so it waits for it to complete.  The consumers only ever read data
+        // that the producer published, static tables, and write the output frame.
+        asm volatile("griddepcontrol.wait;" ::: "memory");
         uint32_t gword = 0u, gclamp = 0u;                  // lane c: gain word of camera c (0: none, f32 bits, all ones: LUT)
         if (GAIN && lane < MAX_CAMS) {
             if (__ldg(p.gain_flag + lane) == 0) {
@@ -440,8 +446,17 @@ int ring_ctas_per_sm()
 
 void launch_blend_ring(const RingParams& p, int grid, cudaStream_t s)
 {
-    if (p.use_gain) k_blend_ring<1><<<grid, RG_THREADS, RS_TOTAL, s>>>(p);
-    else k_blend_ring<0><<<grid, RG_THREADS, RS_TOTAL, s>>>(p);
+    // Programmatic dependent launch behind k_convert_gain (which signals launch_dependents): the persistent CTAs set themselves
+    // up under the tail of the gain chain (measured on C2: 103.3 -> 101.1 us per frame).  OCTVR_PDL=0 launches normally.
+    static const bool pdl = [] { const char* e = getenv("OCTVR_PDL"); return !e || atoi(e) != 0; }();
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)grid); cfg.blockDim = dim3(RG_THREADS); cfg.dynamicSmemBytes = RS_TOTAL; cfg.stream = s;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = at; cfg.numAttrs = pdl ? 1 : 0;
+    if (p.use_gain) cudaLaunchKernelEx(&cfg, k_blend_ring<1>, p);
+    else cudaLaunchKernelEx(&cfg, k_blend_ring<0>, p);
 }
 
 }  // namespace ob

@@ -552,11 +552,14 @@ __global__ void __launch_bounds__(256) k_gain_finalize(const GainParams p) { gai
 // launch, both parts run concurrently, no cross-stream synchronisation.  The gain CTAs are latency-bound and light, the
 // conversion CTAs DRAM-bound: at the head of the grid they are interleaved 1 : 2, so the whole gain chain starts within
 // the first third of the conversion without ever holding more than a fraction of the resident CTA slots.
-__global__ void __launch_bounds__(256, 4) k_convert_gain(const __grid_constant__ ConvertParams cp, const __grid_constant__ GainParams gp, const unsigned gain_blocks,
+__global__ void __launch_bounds__(256, 5) k_convert_gain(const __grid_constant__ ConvertParams cp, const __grid_constant__ GainParams gp, const unsigned gain_blocks,
                                                          const unsigned interleave)
 {
     extern __shared__ unsigned long long s_dyn_nrm[];
     const unsigned b = blockIdx.x;
+    // the next kernel of the stream (K_blend_ring, when launched with programmatic stream serialisation) may start its prologue
+    // once every CTA of this grid has got this far; it still waits for this grid to complete before reading anything we write
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
     struct Stamp {                                          // diagnostics (OCTVR_GAIN_TRACE): first start / last end of the conversion CTAs
         unsigned long long* d; bool on;
         __device__ Stamp(unsigned long long* dbg) : d(dbg), on(dbg && threadIdx.x == 0) { if (on) atomicMin(d + 6, gtime()); }
