@@ -30,6 +30,17 @@ int main(int argc, char** argv)
             }
             return 0;
         }
+        if (argc >= 7 && !strcmp(argv[1], "--incremental")) {
+            // stitch_demo --incremental TO TO_OPTS_JSON WIDTH OUT.dat FROM FROM_OPTS_JSON [FROM FROM_OPTS_JSON ...]
+            // the reference's own sequence (apps/octvr/dump.cpp:98-127): constructor, add_input per camera, create_masks, dump(ofstream)
+            vr::MapperTemplate mt(argv[2], argv[3], atoi(argv[4]), -1);
+            for (int k = 6; k + 1 < argc; k += 2) mt.add_input(argv[k], argv[k + 1]);
+            mt.create_masks();
+            std::ofstream out(argv[5], std::ios::binary);
+            mt.dump(out);
+            printf("out %dx%d inputs %zu seams %zu\n", mt.out_size.width, mt.out_size.height, mt.inputs.size(), mt.seam_masks.size());
+            return 0;
+        }
         if (argc >= 8 && !strcmp(argv[1], "--config")) {
             std::ifstream f(argv[2]);
             std::stringstream ss; ss << f.rdbuf();

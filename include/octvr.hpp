@@ -3,13 +3,17 @@
 // Mirrors modules/octvr/include/octvr.hpp (vr::MapperTemplate :48-91, vr::AsyncMultiMapper :103-121) and
 // modules/octvr/src/mapper.hpp (vr::Mapper :29-95): same class and method names, argument meaning and error
 // behaviour (std::string thrown for bad camera type / size / .dat magic -- template.cpp:30,33,53,262;
-// exceptions for shape violations where the reference CV_Asserts).  OpenCV-free: planes are vr::Plane views;
-// define OCTVR_WITH_OPENCV before including to get cv::Mat / cv::Size overloads identical to the reference's
-// signatures.
+// exceptions for shape violations where the reference CV_Asserts).  OpenCV-free: planes are vr::Plane views, sizes vr::Size,
+// camera options the text of their JSON object; define OCTVR_WITH_OPENCV before including to add the cv::Mat / cv::Size /
+// cv::Rect_<double> overloads of push() and New() with the reference's exact signatures.  Differences that remain: the
+// options are JSON text, not rapidjson::Value; Input holds pointers, not cv::Mat; morph_controlpoints is not provided.
 #pragma once
 #include "octvr_b200.h"
 #include <array>
+#include <cstdio>
+#include <cstdlib>
 #include <fstream>
+#include <unistd.h>
 #include <iterator>
 #include <stdexcept>
 #include <string>
@@ -62,6 +66,26 @@ public:
         const float* vignette = nullptr; Size vignette_size;
     };
     Size out_size;
+    // octvr.hpp:64-67: tables of the blended inputs, of the overlay inputs, and the seam masks of the blended inputs.  Views
+    // into memory owned by the template, refreshed by every call that changes it.
+    std::vector<Input> inputs, overlay_inputs;
+    std::vector<const uint8_t*> seam_masks;
+
+    // MapperTemplate(const std::string& to, const rapidjson::Value& to_opts, int width, int height) (octvr.hpp:72-74); the
+    // options are the text of the JSON object here (the shim has no rapidjson dependency).  Throws std::string for an unknown
+    // camera type or an invalid size, like the reference (template.cpp:30,33).
+    MapperTemplate(const std::string& to, const std::string& to_opts_json, int width, int height, int device = 0)
+    {
+        check(octvr_template_create(to.c_str(), to_opts_json.c_str(), width, height, device, &h_));
+        refresh();
+    }
+    // void add_input(const std::string& from, const rapidjson::Value& from_opts, bool overlay = false, bool use_roi = true)
+    // (octvr.hpp:75-78, template.cpp:46-153); the projection of every output pixel runs as a CUDA kernel
+    void add_input(const std::string& from, const std::string& from_opts_json, bool overlay = false, bool use_roi = true)
+    {
+        check(octvr_template_add_input(h_, from.c_str(), from_opts_json.c_str(), overlay, use_roi));
+        refresh();
+    }
 
     // MapperTemplate(to, to_opts, width, height) + add_input(...) for every entry of the config
     // (apps/octvr/dump.cpp:71-127); the projection runs as a CUDA kernel.
@@ -80,8 +104,21 @@ public:
         check(octvr_template_load_dat(buf.data(), buf.size(), &h_));
         refresh();
     }
-    void create_masks() { check(octvr_template_create_masks(h_)); }                       // template.cpp:155-204
+    void create_masks() { check(octvr_template_create_masks(h_)); refresh(); }            // template.cpp:155-204 (no images: DistanceSeamFinder)
     void dump(const std::string& path) { check(octvr_template_dump_file(h_, path.c_str())); }  // template.cpp:206-256
+    // void dump(std::ofstream& f) (octvr.hpp:84): the same bytes appended to an open stream
+    void dump(std::ofstream& f)
+    {
+        char name[] = "/tmp/octvr_dump_XXXXXX";
+        const int fd = mkstemp(name);
+        if (fd < 0) throw Error(OCTVR_ERR_INVALID, "cannot create a temporary file");
+        close(fd);
+        try { dump(std::string(name)); } catch (...) { std::remove(name); throw; }
+        std::ifstream in(name, std::ios::binary);
+        f << in.rdbuf();
+        in.close();
+        std::remove(name);
+    }
     size_t num_inputs() const { return (size_t)octvr_template_num_inputs(h_); }
     Input input(int i) const
     {
@@ -93,15 +130,32 @@ public:
     }
     const octvr_template* handle() const { return h_; }
 
-    MapperTemplate(MapperTemplate&& o) noexcept : out_size(o.out_size), h_(o.h_) { o.h_ = nullptr; }
-    MapperTemplate& operator=(MapperTemplate&& o) noexcept { if (this != &o) { octvr_template_destroy(h_); h_ = o.h_; out_size = o.out_size; o.h_ = nullptr; } return *this; }
+    MapperTemplate(MapperTemplate&& o) noexcept : out_size(o.out_size), inputs(std::move(o.inputs)), overlay_inputs(std::move(o.overlay_inputs)),
+                                                  seam_masks(std::move(o.seam_masks)), h_(o.h_) { o.h_ = nullptr; }
+    MapperTemplate& operator=(MapperTemplate&& o) noexcept
+    {
+        if (this != &o) {
+            octvr_template_destroy(h_); h_ = o.h_; out_size = o.out_size; o.h_ = nullptr;
+            inputs = std::move(o.inputs); overlay_inputs = std::move(o.overlay_inputs); seam_masks = std::move(o.seam_masks);
+        }
+        return *this;
+    }
     MapperTemplate(const MapperTemplate&) = delete;
     MapperTemplate& operator=(const MapperTemplate&) = delete;
     ~MapperTemplate() { octvr_template_destroy(h_); }
 
 private:
     MapperTemplate() {}
-    void refresh() { check(octvr_template_out_size(h_, &out_size.width, &out_size.height)); }
+    void refresh()
+    {
+        check(octvr_template_out_size(h_, &out_size.width, &out_size.height));
+        const int n = octvr_template_num_inputs(h_), no = octvr_template_num_overlays(h_);
+        inputs.clear(); overlay_inputs.clear(); seam_masks.clear();
+        for (int i = 0; i < n + no; i++) {
+            const Input in = input(i);
+            if (i < n) { inputs.push_back(in); seam_masks.push_back(in.seam_mask); } else overlay_inputs.push_back(in);
+        }
+    }
     octvr_template* h_ = nullptr;
 };
 
@@ -178,6 +232,28 @@ public:
         if (st != OCTVR_OK) { delete a; check(st); }
         return a;
     }
+    // static AsyncMultiMapper* New(const std::vector<MapperTemplate>& mts, ...) (octvr.hpp:105-111): the reference's container type
+    static AsyncMultiMapper* New(const std::vector<MapperTemplate>& mts, std::vector<Size> in_sizes, Size out_size,
+                                 std::vector<int> blend_modes, std::vector<int> gain_modes,
+                                 std::vector<RectD> output_regions, Size preview_size = Size(), int device = 0)
+    {
+        std::vector<const MapperTemplate*> ptrs;
+        for (auto& t : mts) ptrs.push_back(&t);
+        return New(ptrs, in_sizes, out_size, blend_modes, gain_modes, output_regions, preview_size, device);
+    }
+#ifdef OCTVR_WITH_OPENCV
+    // the reference's exact signature (cv::Size, cv::Rect_<double>)
+    static AsyncMultiMapper* New(const std::vector<MapperTemplate>& mts, std::vector<cv::Size> in_sizes, cv::Size out_size,
+                                 std::vector<int> blend_modes, std::vector<int> gain_modes,
+                                 std::vector<cv::Rect_<double>> output_regions, cv::Size preview_size)
+    {
+        std::vector<Size> is;
+        for (auto& s : in_sizes) is.push_back(Size{ s.width, s.height });
+        std::vector<RectD> rs;
+        for (auto& r : output_regions) rs.push_back(RectD{ r.x, r.y, r.width, r.height });
+        return New(mts, is, Size{ out_size.width, out_size.height }, blend_modes, gain_modes, rs, Size{ preview_size.width, preview_size.height });
+    }
+#endif
     // Push one frame, in YUV420P format: HOST planes; keep them alive and untouched until the matching pop()
     virtual void push(std::vector<YUV>& inputs, YUV& output)
     {

@@ -52,6 +52,16 @@ octvr_status octvr_template_dump_file(octvr_template* t, const char* path);
 octvr_status octvr_template_build_json(const char* json, int width, int height, int use_roi,
                                        int with_seam_masks, int device, octvr_template** out);
 
+/* The same, incrementally, as the reference class is used (octvr.hpp:72-79):
+ *   MapperTemplate(const std::string& to, const rapidjson::Value& to_opts, int width, int height)   -> octvr_template_create
+ *   void add_input(const std::string& from, const rapidjson::Value& from_opts, bool overlay, bool use_roi) -> octvr_template_add_input
+ * followed by octvr_template_create_masks().  Options are passed as the text of the JSON object (NULL / "" = {});
+ * width or height <= 0 is derived from the output model's aspect ratio (template.cpp:23-44). */
+octvr_status octvr_template_create(const char* to_type, const char* to_opts_json, int width, int height, int device,
+                                   octvr_template** out);
+octvr_status octvr_template_add_input(octvr_template* t, const char* from_type, const char* from_opts_json,
+                                      int overlay, int use_roi);
+
 /* Assemble a template from caller-made tables (what a reference-side shim holding a
  * vr::MapperTemplate passes in): per input i roi = rois_xywh[4i..], map1/map2 (f32, roi_h x roi_w,
  * normalised [0,1), -1 = no source), mask (u8), optional seam mask (u8, may be NULL array or NULL

@@ -355,42 +355,54 @@ bool output_supported(int type)
 }
 }  // namespace
 
-octvr_template* template_from_json(const std::string& json, int width, int height, bool use_roi, bool with_seams, int device)
+namespace {
+const Json& empty_object()
+{
+    static const Json e = [] { Json j; j.kind = Json::Obj; return j; }();
+    return e;
+}
+octvr_template* create_from(const std::string& type, const Json& opts, int width, int height, int device)
 {
     int count = 0;
     if (cudaGetDeviceCount(&count) != cudaSuccess || count <= 0 || device < 0 || device >= count)
         fail(OCTVR_ERR_CUDA, "no usable CUDA device (map generation has no CPU fallback)");
     OB_CUDA(cudaSetDevice(device));
-    const Json cfg = JsonParser::parse(json);
-    const Json& jo = cfg.at("output");
-    static const Json empty_obj = [] { Json j; j.kind = Json::Obj; return j; }();
-    CamHost oc = camera_from_json(jo.at("type").string(), jo.has("options") ? jo.at("options") : empty_obj);
+    std::shared_ptr<CamHost> oc = std::make_shared<CamHost>(camera_from_json(type, opts));
     // pinhole / fisheye have no image_to_obj (throws NotImplemented, camera.hpp:92-103)
-    if (!output_supported(oc.m.type)) fail(OCTVR_ERR_UNSUPPORTED, "this camera model cannot be used as the output model");
-    if (oc.m.type == CAM_FULLFRAME_FISHEYE && !(oc.m.ip[4] == oc.m.ip[0] && oc.m.ip[5] == oc.m.ip[1] && oc.m.ip[2] == 0 && oc.m.ip[3] == 0))
+    if (!output_supported(oc->m.type)) fail(OCTVR_ERR_UNSUPPORTED, "this camera model cannot be used as the output model");
+    if (oc->m.type == CAM_FULLFRAME_FISHEYE && !(oc->m.ip[4] == oc->m.ip[0] && oc->m.ip[5] == oc->m.ip[1] && oc->m.ip[2] == 0 && oc->m.ip[3] == 0))
         fail(OCTVR_ERR_INVALID, "fullframe_fisheye as the output model must not be cropped (fullframe_fisheye_cam.cpp:224)");
-
     // MapperTemplate::MapperTemplate (template.cpp:23-44)
     if (height <= 0 && width <= 0) fail(OCTVR_ERR_FORMAT, "Output width/height invalid");
-    const double ar = camera_aspect_ratio(oc.m);
+    const double ar = camera_aspect_ratio(oc->m);
     if (height <= 0) height = int(double(width) / ar);
     if (width <= 0) width = int(double(height) * ar);
     OB_CHECK(width > 0 && height > 0 && (int64_t)width * height < ((int64_t)1 << 31), "output size");
-
     std::unique_ptr<octvr_template> t(new octvr_template);
-    t->out_w = width; t->out_h = height;
+    t->out_w = width; t->out_h = height; t->out_cam = oc; t->device = device;
+    return t.release();
+}
+// MapperTemplate::add_input (template.cpp:46-153): the projection of every output pixel runs as a CUDA kernel
+void add_input_from(octvr_template& tt, const std::string& type, const Json& opts, bool overlay, bool use_roi)
+{
+    octvr_template* t = &tt;
+    if (!t->out_cam) fail(OCTVR_ERR_INVALID, "add_input needs a template made by MapperTemplate(to, to_opts, width, height)");
+    const CamHost& oc = *static_cast<const CamHost*>(t->out_cam.get());
+    OB_CUDA(cudaSetDevice(t->device));
+    const int width = t->out_w, height = t->out_h;
     const size_t area = (size_t)width * height;
     DevBuf<float> d_m1(area), d_m2(area);
     DevBuf<uint8_t> d_mask(area);
     DevBuf<int> d_bbox(4);
-    std::vector<float> h_m1(area), h_m2(area);
-    std::vector<uint8_t> h_mask(area);
     // MapperTemplate::visible_mask (template.cpp:41): output pixels an include mask has claimed so far
-    std::vector<uint8_t> visible;
+    std::vector<uint8_t>& visible = t->visible;
     std::unique_ptr<DevBuf<uint8_t>> d_visible, d_vis;
-
-    auto add_input = [&](const Json& ji, bool overlay) {
-        CamHost ic = camera_from_json(ji.at("type").string(), ji.at("options"));
+    if (!visible.empty()) {
+        d_visible.reset(new DevBuf<uint8_t>(area));
+        OB_CUDA(cudaMemcpy(d_visible->p, visible.data(), area, cudaMemcpyHostToDevice));
+    }
+    {
+        CamHost ic = camera_from_json(type, opts);
         std::unique_ptr<DevBuf<uint8_t>> d_ex;
         if (!ic.exclude.empty()) {
             d_ex.reset(new DevBuf<uint8_t>(ic.exclude.size()));
@@ -404,7 +416,7 @@ octvr_template* template_from_json(const std::string& json, int width, int heigh
             d_in.reset(new DevBuf<uint8_t>(ic.include.size()));
             OB_CUDA(cudaMemcpy(d_in->p, ic.include.data(), ic.include.size(), cudaMemcpyHostToDevice));
             ic.m.include_mask = d_in->p;
-            if (!d_vis) d_vis.reset(new DevBuf<uint8_t>(area));
+            d_vis.reset(new DevBuf<uint8_t>(area));
         }
         MapgenParams p;
         p.out = oc.m; p.in = ic.m; p.W = width; p.H = height;
@@ -448,16 +460,36 @@ octvr_template* template_from_json(const std::string& json, int width, int heigh
                         }
                     visible[idx] = visible[idx] || vis[idx];
                 }
-            if (!d_visible) d_visible.reset(new DevBuf<uint8_t>(area));
-            OB_CUDA(cudaMemcpy(d_visible->p, visible.data(), area, cudaMemcpyHostToDevice));
         }
         (overlay ? t->overlays : t->inputs).push_back(std::move(in));
-    };
+    }
+    t->seam_masks.clear();                     // stale once the set of inputs changes; create_masks() rebuilds them
+}
+}  // namespace
+
+octvr_template* template_create(const std::string& to, const std::string& to_opts_json, int width, int height, int device)
+{
+    const Json opts = to_opts_json.empty() ? empty_object() : JsonParser::parse(to_opts_json);
+    return create_from(to, opts, width, height, device);
+}
+
+void template_add_input(octvr_template& t, const std::string& from, const std::string& from_opts_json, bool overlay, bool use_roi)
+{
+    const Json opts = from_opts_json.empty() ? empty_object() : JsonParser::parse(from_opts_json);
+    add_input_from(t, from, opts, overlay, use_roi);
+}
+
+// the whole config at once (apps/octvr/dump.cpp:71-127): MapperTemplate(to, ...) + add_input per entry + create_masks()
+octvr_template* template_from_json(const std::string& json, int width, int height, bool use_roi, bool with_seams, int device)
+{
+    const Json cfg = JsonParser::parse(json);
+    const Json& jo = cfg.at("output");
+    std::unique_ptr<octvr_template> t(create_from(jo.at("type").string(), jo.has("options") ? jo.at("options") : empty_object(), width, height, device));
     const Json& ins = cfg.at("inputs");
     OB_CHECK(ins.kind == Json::Arr && ins.size() >= 1, "config: \"inputs\" must be a non-empty array");
-    for (size_t i = 0; i < ins.size(); i++) add_input(ins.at(i), false);
+    for (size_t i = 0; i < ins.size(); i++) add_input_from(*t, ins.at(i).at("type").string(), ins.at(i).at("options"), false, use_roi);
     if (cfg.has("overlays"))
-        for (size_t i = 0; i < cfg.at("overlays").size(); i++) add_input(cfg.at("overlays").at(i), true);
+        for (size_t i = 0; i < cfg.at("overlays").size(); i++) add_input_from(*t, cfg.at("overlays").at(i).at("type").string(), cfg.at("overlays").at(i).at("options"), true, use_roi);
     if (with_seams) t->seam_masks = distance_seam_masks(t->inputs, t->out_w);      // create_masks(), template.cpp:155-204
     return t.release();
 }

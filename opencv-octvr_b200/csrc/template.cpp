@@ -151,6 +151,22 @@ octvr_status octvr_template_build_json(const char* json, int width, int height, 
     });
 }
 
+octvr_status octvr_template_create(const char* to_type, const char* to_opts_json, int width, int height, int device, octvr_template** out)
+{
+    return guard([&] {
+        OB_CHECK(to_type && out, "null argument");
+        *out = template_create(to_type, to_opts_json ? to_opts_json : "", width, height, device);
+    });
+}
+
+octvr_status octvr_template_add_input(octvr_template* t, const char* from_type, const char* from_opts_json, int overlay, int use_roi)
+{
+    return guard([&] {
+        OB_CHECK(t && from_type, "null argument");
+        template_add_input(*t, from_type, from_opts_json ? from_opts_json : "", overlay != 0, use_roi != 0);
+    });
+}
+
 octvr_status octvr_template_from_arrays(int out_w, int out_h, int n, const int* rois,
                                         const float* const* map1, const float* const* map2,
                                         const uint8_t* const* mask, const uint8_t* const* seam,

@@ -38,6 +38,17 @@ class MapperTemplate:
         return cls(h)
 
     @classmethod
+    def create(cls, to, to_opts, width, height=-1, device=0):
+        """MapperTemplate(to, to_opts, width, height) (octvr.hpp:72-74); add inputs with add_input(), then create_masks()."""
+        h = C.c_void_p()
+        check(lib().octvr_template_create(to.encode(), json.dumps(to_opts or {}).encode(), int(width), int(height), int(device), C.byref(h)))
+        return cls(h)
+
+    def add_input(self, frm, from_opts, overlay=False, use_roi=True):
+        """add_input(from, from_opts, overlay, use_roi) (octvr.hpp:75-78): the projection runs as a CUDA kernel."""
+        check(lib().octvr_template_add_input(self._h, frm.encode(), json.dumps(from_opts or {}).encode(), int(overlay), int(use_roi)))
+
+    @classmethod
     def from_json(cls, cfg, width, height=-1, use_roi=True, with_seam_masks=True, device=0):
         """MapperTemplate(to, to_opts, w, h) + add_input per camera (+ create_masks), maps generated on the GPU."""
         if not isinstance(cfg, str):

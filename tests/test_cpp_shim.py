@@ -50,3 +50,21 @@ def test_shim_async_stitch_matches_oracle(demo, tmp_path):
     frames = [util.i420_planes(util.noise_frame(c, 192, 108, seed=1234 + 2), 192, 108) for c in range(2)]
     y, u, v = so.stitch(frames)
     assert np.array_equal(got, np.concatenate([y.ravel(), u.ravel(), v.ravel()]))
+
+
+@pytest.mark.gpu
+def test_shim_incremental_template_writes_the_reference_tools_bytes(demo, tmp_path):
+    """MapperTemplate(to, to_opts, w, h) + add_input(...) per camera + create_masks() + dump(std::ofstream&) -- the call
+    sequence of the reference's octvr_dump (apps/octvr/dump.cpp:98-127) -- yields the very file the reference tool wrote."""
+    import hashlib
+    import json
+    cfg = util.rig_json("rig3")
+    args = [demo, "--incremental", cfg["output"]["type"], json.dumps(cfg["output"].get("options", {})), str(util.rig_width("rig3")), str(tmp_path / "t.dat")]
+    for inp in cfg["inputs"]:
+        args += [inp["type"], json.dumps(inp["options"])]
+    r = subprocess.run(args, capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    assert "inputs 3 seams 3" in r.stdout
+    ref = json.load(open(os.path.join(util.GOLD, "dat_sha256.json")))["rig3"]
+    data = open(tmp_path / "t.dat", "rb").read()
+    assert len(data) == ref["bytes"] and hashlib.sha256(data).hexdigest() == ref["sha256"]
