@@ -77,6 +77,9 @@ octvr_status octvr_template_add_overlay(octvr_template* t, const int* roi_xywh, 
                                         const uint8_t* mask, const float* vignette, int vig_w, int vig_h);
 /* MapperTemplate::create_masks() with no images (DistanceSeamFinder), template.cpp:155-204 */
 octvr_status octvr_template_create_masks(octvr_template* t);
+/* Diagnostics: which code made the most recent set of seam masks -- 1 = the CUDA kernels of csrc/seam.cu (always, when a
+ * device is present), 0 = the host routine (processes without a device), -1 = none made yet. */
+int          octvr_debug_seam_backend(void);
 
 octvr_status octvr_template_out_size(const octvr_template* t, int* w, int* h);
 int          octvr_template_num_inputs(const octvr_template* t);

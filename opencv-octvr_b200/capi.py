@@ -28,7 +28,7 @@ class Frame(C.Structure):
 SYMBOLS = [
     "octvr_last_error", "octvr_version",
     "octvr_template_load_dat", "octvr_template_load_file", "octvr_template_dump_file",
-    "octvr_template_build_json", "octvr_template_create", "octvr_template_add_input", "octvr_template_from_arrays", "octvr_template_add_overlay", "octvr_template_create_masks",
+    "octvr_template_build_json", "octvr_template_create", "octvr_template_add_input", "octvr_template_from_arrays", "octvr_template_add_overlay", "octvr_template_create_masks", "octvr_debug_seam_backend",
     "octvr_template_out_size", "octvr_template_num_inputs", "octvr_template_num_overlays",
     "octvr_template_input", "octvr_template_destroy",
     "octvr_mapper_create", "octvr_mapper_stitch", "octvr_mapper_stitch_packed", "octvr_mapper_set_keep_rgb", "octvr_mapper_result_rgb",

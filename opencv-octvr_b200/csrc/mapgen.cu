@@ -490,7 +490,7 @@ octvr_template* template_from_json(const std::string& json, int width, int heigh
     for (size_t i = 0; i < ins.size(); i++) add_input_from(*t, ins.at(i).at("type").string(), ins.at(i).at("options"), false, use_roi);
     if (cfg.has("overlays"))
         for (size_t i = 0; i < cfg.at("overlays").size(); i++) add_input_from(*t, cfg.at("overlays").at(i).at("type").string(), cfg.at("overlays").at(i).at("options"), true, use_roi);
-    if (with_seams) t->seam_masks = distance_seam_masks(t->inputs, t->out_w);      // create_masks(), template.cpp:155-204
+    if (with_seams) t->seam_masks = distance_seam_masks(t->inputs, t->out_w, device);      // create_masks(), template.cpp:155-204
     return t.release();
 }
 

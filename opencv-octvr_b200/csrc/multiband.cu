@@ -742,7 +742,7 @@ Multiband* multiband_create(octvr_mapper& m, const octvr_template& t,
     std::vector<Img<uint8_t>> seams = t.seam_masks;
     bool have = (int)seams.size() == n;
     for (auto& s : seams) have = have && !s.empty();
-    if (!have) seams = distance_seam_masks(t.inputs, t.out_w);       // Mapper requires mt.seam_masks (mapper.cpp:106)
+    if (!have) seams = distance_seam_masks(t.inputs, t.out_w, m.device);     // Mapper requires mt.seam_masks (mapper.cpp:106)
 
     std::unique_ptr<Multiband> mb(new Multiband);
     MbParams& p = mb->p;

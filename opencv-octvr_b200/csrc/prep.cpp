@@ -253,7 +253,17 @@ std::vector<Img<float>> overwrite_weights(const std::vector<TInput>& in)
     return w;
 }
 
-std::vector<Img<uint8_t>> distance_seam_masks(const std::vector<TInput>& in, int out_w)
+namespace { int g_seam_backend = -1; }
+int seam_backend() { return g_seam_backend; }
+std::vector<Img<uint8_t>> distance_seam_masks(const std::vector<TInput>& in, int out_w, int device)
+{
+    std::vector<Img<uint8_t>> out;
+    if (distance_seam_masks_gpu(in, out_w, device, out)) { g_seam_backend = 1; return out; }
+    g_seam_backend = 0;
+    return distance_seam_masks_host(in, out_w);
+}
+
+std::vector<Img<uint8_t>> distance_seam_masks_host(const std::vector<TInput>& in, int out_w)
 {
     const int n = (int)in.size();
     const double scale = std::min(1.0, 960.0 / out_w);

@@ -32,7 +32,12 @@ std::vector<Img<float>> feather_weights(const std::vector<TInput>& in, int borde
 // blend == 0: masked copies in camera order (mapper.cpp:269-275) == weight 1 for the LAST covering camera
 std::vector<Img<float>> overwrite_weights(const std::vector<TInput>& in);
 // MapperTemplate::create_masks() without images (template.cpp:155-204, seam_finders.cpp:86-133)
-std::vector<Img<uint8_t>> distance_seam_masks(const std::vector<TInput>& in, int out_w);
+// distance_seam_masks: on the GPU (seam.cu) whenever a CUDA device is present; the host routine only serves processes without
+// a device (loading / dumping .dat files needs none).  seam_backend() tells which one made the last set (1 = GPU, 0 = host).
+std::vector<Img<uint8_t>> distance_seam_masks(const std::vector<TInput>& in, int out_w, int device = -1);
+std::vector<Img<uint8_t>> distance_seam_masks_host(const std::vector<TInput>& in, int out_w);
+bool distance_seam_masks_gpu(const std::vector<TInput>& in, int out_w, int device, std::vector<Img<uint8_t>>& out);
+int seam_backend();
 
 // cv::remap coordinate quantisation for planar f32 maps (imgwarp.cpp:4383-4442) applied to
 // fl32(map * size) (template.cpp:175-176).  Returns 1/32-px fixed point sx, sy.

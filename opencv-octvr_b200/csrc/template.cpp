@@ -93,7 +93,7 @@ void template_ensure_seams(octvr_template& t)
 {
     bool have = t.seam_masks.size() == t.inputs.size();
     for (auto& m : t.seam_masks) have = have && !m.empty();
-    if (!have) t.seam_masks = distance_seam_masks(t.inputs, t.out_w);
+    if (!have) t.seam_masks = distance_seam_masks(t.inputs, t.out_w, t.device);
 }
 
 void template_to_dat(octvr_template& t, const std::string& path)
@@ -235,8 +235,10 @@ octvr_status octvr_debug_fill_poly(uint8_t* img, int w, int h, const int* pts, i
 
 octvr_status octvr_template_create_masks(octvr_template* t)
 {
-    return guard([&] { OB_CHECK(t, "null argument"); t->seam_masks = distance_seam_masks(t->inputs, t->out_w); });
+    return guard([&] { OB_CHECK(t, "null argument"); t->seam_masks = distance_seam_masks(t->inputs, t->out_w, t->device); });
 }
+
+int octvr_debug_seam_backend(void) { return seam_backend(); }
 
 octvr_status octvr_template_out_size(const octvr_template* t, int* w, int* h)
 {
