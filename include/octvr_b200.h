@@ -175,6 +175,27 @@ octvr_status octvr_debug_fill_poly(uint8_t* h_img, int w, int h, const int* pts_
 octvr_status octvr_mapper_stage_ms(octvr_mapper* m, const char* stage, float* ms);
 void         octvr_mapper_destroy(octvr_mapper* m);
 
+/* ----------------------------------------------------------------- FastMapper
+ * vr::FastMapper (include/octvr.hpp:123-144, src/mapper_fast.cpp): the NV12 path that never leaves 4:2:0 -- u8 feather
+ * weights (border 5, no gain), full-resolution tables for luma and half-resolution tables for chroma, 16-bit accumulation,
+ * / 255 (cv::remap_weighted, imgproc/src/opencl/remap_weighted.cl:20-77).  One CUDA launch per frame (csrc/fast.cu). */
+typedef struct octvr_fast octvr_fast;
+/* FastMapper(mt, in_sizes), mapper_fast.cpp:27-109.  The template must have no overlay inputs (:31) and full-frame inputs
+ * (:50-51: build it with use_roi = 0, `octvr_dump -n`), else OCTVR_ERR_INVALID / OCTVR_ERR_UNSUPPORTED. */
+octvr_status octvr_fast_create(const octvr_template* t, const int* in_sizes_wh, int n_inputs, int device, octvr_fast** out);
+/* stitch_nv12(inputs, output), mapper_fast.cpp:153-195.  d_inputs[i]: device pointer to an (in_h + in_h / 2) x pitch NV12
+ * frame (luma rows, then interleaved chroma rows -- the cv::UMat layout the reference asserts at :156-160); d_output:
+ * (H + H / 2) x out_pitch, same layout.  As in the reference, output chroma byte 0 comes from input chroma byte 1 and
+ * vice versa (:179-180).  Asynchronous on `stream`. */
+octvr_status octvr_fast_stitch_nv12(octvr_fast* f, const uint8_t* const* d_inputs, const size_t* pitches, int n_inputs,
+                                    uint8_t* d_output, size_t out_pitch, void* stream);
+/* output size, contributing (pixel, camera) pairs of the luma / chroma tables, bytes of device tables; any pointer may be NULL */
+octvr_status octvr_fast_info(const octvr_fast* f, int* out_w, int* out_h, long long* pairs_luma, long long* pairs_chroma, long long* table_bytes);
+/* Tests: host copy of one of the constructor's tables for camera `cam`.  which: 0 map1s (W x H x 2 int16), 1 half_map1s,
+ * 2 map2s (W x H uint16), 3 half_map2s, 4 feather_masks (u8), 5 half_feather_masks (mapper_fast.cpp:41-101). */
+octvr_status octvr_fast_debug_table(const octvr_fast* f, int cam, int which, void* h_out);
+void         octvr_fast_destroy(octvr_fast* f);
+
 /* ---------------------------------------------------------------------- async
  * vr::AsyncMultiMapper (include/octvr.hpp:103-121, src/async.cpp). Host planes in, host planes out. */
 typedef struct octvr_async octvr_async;

@@ -6,5 +6,5 @@ the thin Python mirror of the reference's mapper API used by the tests and bench
 name has a hyphen; import it as `import octvr_b200` (alias module at the repo root).
 """
 from .capi import OctvrError, Frame, lib, build, LIB_PATH, SYMBOLS  # noqa: F401
-from .mapper import MapperTemplate, Mapper, AsyncMultiMapper, PackedRGB, frame_from_planes, split_packed  # noqa: F401
+from .mapper import MapperTemplate, Mapper, AsyncMultiMapper, FastMapper, PackedRGB, frame_from_planes, split_packed  # noqa: F401
 from . import sharding  # noqa: F401,E402

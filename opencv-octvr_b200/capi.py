@@ -28,7 +28,7 @@ class Frame(C.Structure):
 SYMBOLS = [
     "octvr_last_error", "octvr_version",
     "octvr_template_load_dat", "octvr_template_load_file", "octvr_template_dump_file",
-    "octvr_template_build_json", "octvr_template_create", "octvr_template_add_input", "octvr_template_from_arrays", "octvr_template_add_overlay", "octvr_template_create_masks", "octvr_debug_seam_backend",
+    "octvr_template_build_json", "octvr_template_create", "octvr_template_add_input", "octvr_template_from_arrays", "octvr_template_add_overlay", "octvr_template_create_masks", "octvr_debug_seam_backend", "octvr_fast_create", "octvr_fast_stitch_nv12", "octvr_fast_info", "octvr_fast_debug_table", "octvr_fast_destroy",
     "octvr_template_out_size", "octvr_template_num_inputs", "octvr_template_num_overlays",
     "octvr_template_input", "octvr_template_destroy",
     "octvr_mapper_create", "octvr_mapper_stitch", "octvr_mapper_stitch_packed", "octvr_mapper_set_keep_rgb", "octvr_mapper_result_rgb",
@@ -60,6 +60,11 @@ def lib():
         L.octvr_template_destroy.restype = None
         L.octvr_mapper_destroy.restype = None
         L.octvr_async_destroy.restype = None
+        L.octvr_fast_destroy.restype = None
+        L.octvr_fast_destroy.argtypes = [C.c_void_p]
+        L.octvr_fast_create.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.POINTER(C.c_void_p)]
+        L.octvr_fast_stitch_nv12.argtypes = [C.c_void_p, C.POINTER(C.c_void_p), C.POINTER(C.c_size_t), C.c_int, C.c_void_p, C.c_size_t, C.c_void_p]
+        L.octvr_fast_debug_table.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p]
         L.octvr_mapper_stitch.argtypes = [C.c_void_p, C.POINTER(Frame), C.c_int, C.POINTER(Frame), C.c_void_p, C.c_size_t,
                                           C.c_int, C.c_int, C.POINTER(C.c_double), C.c_int, C.c_void_p]
         L.octvr_mapper_stitch_packed.argtypes = [C.c_void_p, C.POINTER(C.c_void_p), C.POINTER(C.c_size_t), C.c_int,

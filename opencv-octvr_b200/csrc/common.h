@@ -34,6 +34,14 @@ template <class F> inline octvr_status guard(F&& f)
     catch (...) { set_last_error("unknown exception"); return OCTVR_ERR_INVALID; }
 }
 
+// ---- init-time trace (OCTVR_INIT_TRACE=1: stage times of template / mapper construction on stderr) ----------
+struct InitTrace {
+    const char* what; bool on; double t0;
+    static double now();
+    explicit InitTrace(const char* w);
+    void lap(const char* stage);
+};
+
 // ---- host images ------------------------------------------------------------
 template <class T> struct Img {
     int w = 0, h = 0;

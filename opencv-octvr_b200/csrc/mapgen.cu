@@ -389,6 +389,7 @@ void add_input_from(octvr_template& tt, const std::string& type, const Json& opt
     if (!t->out_cam) fail(OCTVR_ERR_INVALID, "add_input needs a template made by MapperTemplate(to, to_opts, width, height)");
     const CamHost& oc = *static_cast<const CamHost*>(t->out_cam.get());
     OB_CUDA(cudaSetDevice(t->device));
+    InitTrace tr("add_input");
     const int width = t->out_w, height = t->out_h;
     const size_t area = (size_t)width * height;
     DevBuf<float> d_m1(area), d_m2(area);
@@ -402,7 +403,9 @@ void add_input_from(octvr_template& tt, const std::string& type, const Json& opt
         OB_CUDA(cudaMemcpy(d_visible->p, visible.data(), area, cudaMemcpyHostToDevice));
     }
     {
+        tr.lap("alloc");
         CamHost ic = camera_from_json(type, opts);
+        tr.lap("camera_from_json");
         std::unique_ptr<DevBuf<uint8_t>> d_ex;
         if (!ic.exclude.empty()) {
             d_ex.reset(new DevBuf<uint8_t>(ic.exclude.size()));
@@ -429,6 +432,7 @@ void add_input_from(octvr_template& tt, const std::string& type, const Json& opt
         OB_CUDA(cudaGetLastError());
         int bb[4];
         OB_CUDA(cudaMemcpy(bb, d_bbox.p, sizeof(bb), cudaMemcpyDeviceToHost));
+        tr.lap("k_mapgen");
         // CV_Assert(min_h <= max_h && min_w <= max_w), template.cpp:123
         if (bb[2] < 0 || bb[3] < 0) fail(OCTVR_ERR_INVALID, "input does not cover any output pixel (min_h <= max_h && min_w <= max_w)");
         int min_w = std::max(0, bb[0] - 8), min_h = std::max(0, bb[1] - 8);
@@ -442,7 +446,9 @@ void add_input_from(octvr_template& tt, const std::string& type, const Json& opt
         OB_CUDA(cudaMemcpy2D(in.map1.d.data(), (size_t)roi.w * 4, d_m1.p + off, (size_t)width * 4, (size_t)roi.w * 4, roi.h, cudaMemcpyDeviceToHost));
         OB_CUDA(cudaMemcpy2D(in.map2.d.data(), (size_t)roi.w * 4, d_m2.p + off, (size_t)width * 4, (size_t)roi.w * 4, roi.h, cudaMemcpyDeviceToHost));
         OB_CUDA(cudaMemcpy2D(in.mask.d.data(), (size_t)roi.w, d_mask.p + off, (size_t)width, (size_t)roi.w, roi.h, cudaMemcpyDeviceToHost));
+        tr.lap("copy tables to host");
         if (ic.has_vignette) in.vignette = vignette_map(ic.vig, 512, 512);          // template.cpp:18-19,135-136
+        tr.lap("vignette");
         if (p.vis) {
             // template.cpp:102-116: points this input's include mask makes visible for the first time are knocked out of
             // every EARLIER input's mask (their ROIs stay as they were), then join the visible set

@@ -281,6 +281,7 @@ static bool build_fused(octvr_mapper& m, const octvr_template& t, const std::vec
 static void build_mapper(octvr_mapper& m, const octvr_template& t, const int* in_sizes, int n_in,
                          int blend, bool enable_gain, int scale_w, int scale_h, int band_y0, int band_y1)
 {
+    InitTrace tr("build_mapper");
     const int n = (int)t.inputs.size();
     const int n_ov = (int)t.overlays.size();
     OB_CHECK(n >= 1 && n + n_ov <= MAX_CAMS, "1..16 inputs (including overlays) supported");
@@ -319,6 +320,7 @@ static void build_mapper(octvr_mapper& m, const octvr_template& t, const int* in
     // ---- fixed-point coordinates and blend weights per ROI pixel ----
     std::vector<Img<int32_t>> sx(n), sy(n);
     for (int i = 0; i < n; i++) quantise_map(t.inputs[i].map1, t.inputs[i].map2, m.in_w[i], m.in_h[i], sx[i], sy[i]);
+    tr.lap("vignette + quantise_map");
     m.pairs = 0; m.roi_area = 0;
     for (int i = 0; i < n; i++) {
         m.roi_area += (int64_t)t.inputs[i].roi.w * t.inputs[i].roi.h;
@@ -340,9 +342,11 @@ static void build_mapper(octvr_mapper& m, const octvr_template& t, const int* in
             m.src_row0[i] = std::max(0, lo) & ~1; m.src_row1[i] = std::min(m.in_h[i], hi + 1);
         }
 
+    tr.lap("pairs + source rows");
     std::vector<Img<float>> W;
     if (blend <= 0) {
         W = blend < 0 ? feather_weights(t.inputs, -blend) : overwrite_weights(t.inputs);
+        tr.lap("feather / overwrite weights");
         m.inv_n = blend < 0 ? (float)(1.0 / n) : 1.f;
         // OCTVR_BLEND=fused selects the single-kernel path (K_stitch_fused: no RGBX image in HBM, half the DRAM traffic, but
         // measured slower per frame than convert + staged blend because the conversion no longer hides the latency of the
@@ -370,8 +374,10 @@ static void build_mapper(octvr_mapper& m, const octvr_template& t, const int* in
         m.d_rgb_scaled = dev_alloc<uint8_t>((size_t)m.scaled_w * m.scaled_h * 3, true);
     }
 
+    tr.lap("planes + overlays");
     if (blend > 0) {
         m.mb = ob::multiband_create(m, t, sx, sy);
+        tr.lap("multiband_create");
     } else {
         if (!m.fused) {
         // ---- tile-compacted tables ----
@@ -459,6 +465,7 @@ static void build_mapper(octvr_mapper& m, const octvr_template& t, const int* in
             }
         }
         m.staged = staged;
+        tr.lap("tile jobs + boxes");
         // K_blend_ring (default): the same boxes and tensor maps, entries regrouped for four pixels per thread, every
         // job's [entries | box] must fit the shared-memory ring.  OCTVR_BLEND=staged keeps the one-tile-per-CTA kernel.
         bool ring = staged;
@@ -583,6 +590,7 @@ static void build_mapper(octvr_mapper& m, const octvr_template& t, const int* in
             m.table_bytes = (int64_t)(coords.size() * sizeof(uint2) + weights.size() * sizeof(float) + job_cam.size() + job_start.size() * 4);
         }
         }   // !fused
+        tr.lap("entries + upload");
     }
 
     // ---- gain compensation tables (mapper.cpp:94-99,113-114,235-237) ----
@@ -684,6 +692,7 @@ static void build_mapper(octvr_mapper& m, const octvr_template& t, const int* in
         g.gains = m.d_gains; g.gain_f32 = m.d_gain_f32; g.gain_flag = m.d_gain_flag; g.gain_lut = m.d_gain_lut;
         m.table_bytes += (int64_t)(samples.size() * sizeof(uint4) + chunks.size() * sizeof(int2));
     }
+    tr.lap("gain tables");
     for (auto& e : m.ev) OB_CUDA(cudaEventCreate(&e));
 
 }

@@ -8,7 +8,20 @@
 #include <cmath>
 #include <thread>
 
+#include <chrono>
+#include <cstdlib>
+
 namespace ob {
+
+double InitTrace::now() { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); }
+InitTrace::InitTrace(const char* w) : what(w), on(getenv("OCTVR_INIT_TRACE") != nullptr), t0(on ? now() : 0.) {}
+void InitTrace::lap(const char* stage)
+{
+    if (!on) return;
+    const double t = now();
+    fprintf(stderr, "[octvr init] %s: %s %.1f ms\n", what, stage, (t - t0) * 1e3);
+    t0 = t;
+}
 
 namespace {
 inline int round_he(float v) { return (int)lrintf(v); }        // cvRound: round-half-even

@@ -357,3 +357,57 @@ class AsyncMultiMapper:
             self.close()
         except Exception:
             pass
+
+
+class FastMapper:
+    """vr::FastMapper (octvr.hpp:123-144, mapper_fast.cpp): NV12 frames in, NV12-shaped frame out, one CUDA launch."""
+
+    def __init__(self, tmpl, in_sizes, device=0):
+        import torch
+        self._torch = torch
+        self.tmpl, self.device = tmpl, device
+        self.in_sizes = [tuple(s) for s in in_sizes]
+        sz = np.ascontiguousarray(np.array(self.in_sizes, np.int32).reshape(-1, 2))
+        h = C.c_void_p()
+        check(lib().octvr_fast_create(tmpl._h, sz.ctypes.data_as(C.c_void_p), len(self.in_sizes), int(device), C.byref(h)))
+        self._h = h
+        self.out_size = tmpl.out_size
+
+    def stitch_nv12(self, inputs, output, stream=None):
+        """inputs: (in_h + in_h // 2, in_w) u8 CUDA tensors (luma rows, then interleaved chroma rows); output:
+        (H + H // 2, W) u8 CUDA tensor, written in place.  Asynchronous on `stream` (default: torch's current stream)."""
+        torch = self._torch
+        s = stream if stream is not None else torch.cuda.current_stream(self.device)
+        W, H = self.out_size
+        for t, (iw, ih) in zip(inputs, self.in_sizes):        # CV_Assert(inputs[i].rows == h + h / 2 && cols == w && type == CV_8U)
+            if tuple(t.shape) != (ih + ih // 2, iw) or t.dtype != torch.uint8 or t.stride(1) != 1:
+                raise OctvrError(capi.ERR_INVALID, "stitch_nv12: input must be a (h + h / 2, w) u8 frame")
+        if tuple(output.shape) != (H + H // 2, W) or output.dtype != torch.uint8 or output.stride(1) != 1:
+            raise OctvrError(capi.ERR_INVALID, "stitch_nv12: output must be a (H + H / 2, W) u8 frame")
+        ptrs = (C.c_void_p * len(inputs))(*[t.data_ptr() for t in inputs])
+        pitches = (C.c_size_t * len(inputs))(*[t.stride(0) for t in inputs])
+        check(lib().octvr_fast_stitch_nv12(self._h, ptrs, pitches, len(inputs), C.c_void_p(output.data_ptr()),
+                                           C.c_size_t(output.stride(0)), C.c_void_p(s.cuda_stream)))
+
+    def info(self):
+        w, h = C.c_int(), C.c_int()
+        pl, pc, tb = C.c_longlong(), C.c_longlong(), C.c_longlong()
+        check(lib().octvr_fast_info(self._h, C.byref(w), C.byref(h), C.byref(pl), C.byref(pc), C.byref(tb)))
+        return dict(out_size=(w.value, h.value), pairs_luma=pl.value, pairs_chroma=pc.value, table_bytes=tb.value)
+
+    def table(self, cam, name):
+        """Host copy of one of the constructor's tables (tests): map1, half_map1, map2, half_map2, feather, half_feather."""
+        which = ["map1", "half_map1", "map2", "half_map2", "feather", "half_feather"].index(name)
+        W, H = self.out_size
+        w, h = (W // 2, H // 2) if which % 2 else (W, H)
+        a = np.empty((h, w, 2), np.int16) if which < 2 else np.empty((h, w), np.uint16 if which < 4 else np.uint8)
+        check(lib().octvr_fast_debug_table(self._h, int(cam), which, a.ctypes.data_as(C.c_void_p)))
+        return a
+
+    def __del__(self):
+        try:
+            if self._h:
+                lib().octvr_fast_destroy(self._h)
+                self._h = None
+        except Exception:
+            pass

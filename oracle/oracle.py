@@ -639,3 +639,118 @@ class StitchOracle:
         if self.scale_output != tuple(self.t.out_size):
             result = resize_rgb(result, self.scale_output[0], self.scale_output[1])
         return rgb_to_yuv420(result)
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# vr::FastMapper (modules/octvr/src/mapper_fast.cpp): NV12 in, NV12-shaped out, u8 feather weights, no RGB round trip.
+# ---------------------------------------------------------------------------------------------------------------------
+def convert_maps_16sc2(mapx, mapy):
+    """cv::convertMaps(mapx, mapy, CV_16SC2, nninterpolate = false) (imgwarp.cpp:4900-4960): ix = cvRound(x * 32),
+    map1 = saturate_cast<short>(ix >> 5), map2 = (iy & 31) * 32 + (ix & 31)."""
+    ix = np.rint(np.asarray(mapx, np.float32) * np.float32(32)).astype(np.int64)
+    iy = np.rint(np.asarray(mapy, np.float32) * np.float32(32)).astype(np.int64)
+    ix = np.clip(ix, -2 ** 31, 2 ** 31 - 1)
+    iy = np.clip(iy, -2 ** 31, 2 ** 31 - 1)
+    m1 = np.stack([np.clip(ix >> 5, -32768, 32767), np.clip(iy >> 5, -32768, 32767)], -1).astype(np.int16)
+    m2 = ((iy & 31) * 32 + (ix & 31)).astype(np.uint16)
+    return m1, m2
+
+
+def resize_half(src):
+    """cv::resize(src, Size(cols / 2, rows / 2)) (INTER_LINEAR) as the FastMapper constructor calls it on maps, masks and
+    feather masks (mapper_fast.cpp:57-58,70,98-99): an exact 2x reduction goes through the INTER_AREA fast path
+    (imgwarp.cpp:3299-3303) -- u8: (a + b + c + d + 2) >> 2 (:2349-2390); f32: ((a + b) + (c + d)) * 0.25f in the SSE body
+    (:2283-2318, dx <= w - 4) and (((a + b) + c) + d) * 0.25f in the scalar tail (:2425-2437) -- anything else through the
+    bilinear resize."""
+    src = np.ascontiguousarray(src)
+    sh, sw = src.shape
+    dw, dh = sw // 2, sh // 2
+    if sw != 2 * dw or sh != 2 * dh:
+        return resize_linear(src, dw, dh)
+    a, b, c, d = src[0::2, 0::2], src[0::2, 1::2], src[1::2, 0::2], src[1::2, 1::2]
+    if src.dtype == np.uint8:
+        return ((a.astype(np.int32) + b + c + d + 2) >> 2).astype(np.uint8)
+    out = ((a + b) + (c + d)) * np.float32(0.25)
+    body = dw & ~3
+    out[:, body:] = ((((np.float32(0) + a[:, body:]) + b[:, body:]) + c[:, body:]) + d[:, body:]) * np.float32(0.25)
+    return out.astype(np.float32)
+
+
+def remap_weighted(src, acc, map1, map2, weight):
+    """cv::remap_weighted's OpenCL kernel (imgproc/src/opencl/remap_weighted.cl:20-77) for SRC_T = uchar, DST_T = ushort,
+    WT = float: bilinear taps outside the source read 0, the 5-bit fractions weight them in float (exact), the product with
+    the u8 weight is rounded once, converted with convert_ushort_sat_rte and ADDED to acc (16-bit wrap)."""
+    sh, sw = src.shape
+    ax = map1[..., 0].astype(np.int64)
+    ay = map1[..., 1].astype(np.int64)
+    m2 = map2.astype(np.int64) & 1023
+    ux = ((m2 & 31).astype(np.float32)) / np.float32(32)
+    uy = ((m2 >> 5).astype(np.float32)) / np.float32(32)
+
+    def pix(gx, gy):
+        ok = (gx >= 0) & (gy >= 0) & (gx < sw) & (gy < sh)
+        v = src[np.clip(gy, 0, sh - 1), np.clip(gx, 0, sw - 1)].astype(np.float32)
+        return np.where(ok, v, np.float32(0))
+    one = np.float32(1)
+    a, b, c, d = pix(ax, ay), pix(ax + 1, ay), pix(ax, ay + 1), pix(ax + 1, ay + 1)
+    v = a * (one - ux) * (one - uy) + b * ux * (one - uy) + c * (one - ux) * uy + d * ux * uy
+    p = (v * weight.astype(np.float32)).astype(np.float32)
+    q = np.clip(np.rint(p), 0, 65535).astype(np.uint16)
+    acc += q                                      # uint16: wraps like the kernel's `dst[0] += ...`
+
+
+class FastMapperOracle:
+    """vr::FastMapper: constructor mapper_fast.cpp:27-109, stitch_nv12 :153-195."""
+
+    def __init__(self, tmpl, in_sizes):
+        assert not getattr(tmpl, "overlay_inputs", [])                      # CV_Assert(mt.overlay_inputs.size() == 0)
+        W, H = tmpl.out_size
+        self.out_size, self.in_sizes = (W, H), [tuple(s) for s in in_sizes]
+        self.map1, self.map2, self.hmap1, self.hmap2 = [], [], [], []
+        for d, (iw, ih) in zip(tmpl.inputs, self.in_sizes):
+            assert tuple(d["roi"]) == (0, 0, W, H), "FastMapper does not support ROI (mapper_fast.cpp:50-51)"
+            m1, m2 = convert_maps_16sc2(scale_map(d["map1"], iw), scale_map(d["map2"], ih))
+            self.map1.append(m1), self.map2.append(m2)
+            h1, h2 = convert_maps_16sc2(scale_map(resize_half(d["map1"]), iw // 2), scale_map(resize_half(d["map2"]), ih // 2))
+            self.hmap1.append(h1), self.hmap2.append(h2)
+        # feather masks (mapper_fast.cpp:76-101): max(DT - 5, 0) / (1e-5 + sum), x 255 rounded to u8, and their half-size copies
+        total = np.full((H, W), 1e-5, np.float32)
+        ws = []
+        for d in tmpl.inputs:
+            w = dist_l2_3x3(d["mask"]) - np.float32(5)
+            w = np.where(w > 0, w, np.float32(0)).astype(np.float32)
+            total = (w + total).astype(np.float32)
+            ws.append(w)
+        self.feather = [np.clip(np.rint((w / total).astype(np.float32) * np.float32(255.0)), 0, 255).astype(np.uint8) for w in ws]
+        self.hfeather = [resize_half(f) for f in self.feather]
+
+    def stitch_nv12(self, frames):
+        """frames: (1.5 h, w) u8 arrays, luma rows then interleaved chroma rows.  Returns the (1.5 H, W) output frame.
+        As in the reference, output chroma channel 0 is remapped from input chroma channel 1 and vice versa (:179-180)."""
+        W, H = self.out_size
+        acc0 = np.zeros((H, W), np.uint16)
+        acc1 = [np.zeros((H // 2, W // 2), np.uint16), np.zeros((H // 2, W // 2), np.uint16)]
+        for i, (f, (iw, ih)) in enumerate(zip(frames, self.in_sizes)):
+            assert f.shape == (ih + ih // 2, iw) and f.dtype == np.uint8
+            c0 = f[:ih]
+            c12 = f[ih:].reshape(ih // 2, iw // 2, 2)
+            remap_weighted(c0, acc0, self.map1[i], self.map2[i], self.feather[i])
+            remap_weighted(c12[..., 1], acc1[0], self.hmap1[i], self.hmap2[i], self.hfeather[i])
+            remap_weighted(c12[..., 0], acc1[1], self.hmap1[i], self.hmap2[i], self.hfeather[i])
+        self.last_acc0 = acc0
+        k = np.float32(1.0 / 255.0)                                            # convertTo(CV_8U, 1.0 / 255.0): float scale, cvRound
+        out = np.empty((H + H // 2, W), np.uint8)
+        out[:H] = np.clip(np.rint(acc0.astype(np.float32) * k), 0, 255).astype(np.uint8)
+        uv = np.stack(acc1, -1).astype(np.float32) * k
+        out[H:] = np.clip(np.rint(uv), 0, 255).astype(np.uint8).reshape(H // 2, W)
+        return out
+
+
+def fast_noise_frame(cam, w, h):
+    """The NV12-shaped noise frame of oracle/refgen/ref_fast.cpp."""
+    o = np.arange((h + h // 2) * w, dtype=np.uint64)
+    x = (np.uint64(0xFA57) ^ (np.uint64(cam) << np.uint64(32)) ^ o) + np.uint64(0x9E3779B97F4A7C15)
+    x = (x ^ (x >> np.uint64(30))) * np.uint64(0xBF58476D1CE4E5B9)
+    x = (x ^ (x >> np.uint64(27))) * np.uint64(0x94D049BB133111EB)
+    x = x ^ (x >> np.uint64(31))
+    return (x & np.uint64(0xFF)).astype(np.uint8).reshape(h + h // 2, w)

@@ -124,6 +124,29 @@ def main():
         np.savez_compressed(os.path.join(GOLD, "fillpoly.npz"), **arrs)
         print("fillpoly", len(cases))
 
+    # vr::FastMapper (mapper_fast.cpp): the reference constructor's tables + the NV12 frame (oracle/refgen/ref_fast.cpp) on
+    # full-frame templates (octvr_dump -n); the second case has an odd output height, so the half-size tables come from the
+    # generic bilinear resize instead of the 2x area path
+    fast_cases = [("rig3", 256, 320, 240), ("models", 190, 200, 120)]
+    if not only or "fast" in only:
+        ft = compile_tool("ref_fast")
+        for rig, w, iw, ih in fast_cases:
+            dat = os.path.join(TMP, rig + "_n.dat")
+            subprocess.check_call([dump, "-n", "-w", str(w), "-o", dat, os.path.join(rigs_dir, rig + ".json")], cwd=rigs_dir,
+                                  stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
+            out = os.path.join(TMP, "fast_%s.bin" % rig)
+            subprocess.check_call([ft, dat, str(iw), str(ih), out], stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
+            c = read_container(out)
+            t = O.load_dat(dat)
+            c["out_size"], c["n"], c["in_size"] = np.array(t.out_size, np.int64), np.array(len(t.inputs)), np.array([iw, ih], np.int64)
+            for i, d in enumerate(t.inputs):
+                assert tuple(d["roi"]) == (0, 0) + tuple(t.out_size)
+                c["t_map1_%d" % i], c["t_map2_%d" % i], c["t_mask%d" % i] = d["map1"], d["map2"], d["mask"]
+            np.savez_compressed(os.path.join(GOLD, "fast_%s.npz" % rig), **c)
+            print("fast", rig, t.out_size, c["result"].shape)
+    if only and set(only) <= {"fast"}:
+        return
+
     st = compile_tool("ref_stitch")
     cases = [  # name, rig, in_w, in_h, blend, gain, kind
         ("rig3_feather5_gain_noise", "rig3", 320, 240, -5, 1, "noise"),

@@ -247,3 +247,26 @@ def test_fill_poly_bit_exact():
         want = np.unpackbits(g["m%d" % k])[:w * h].reshape(h, w).astype(bool)
         got = O.fill_poly(np.full((h, w), 7, np.uint8), p[2:].reshape(-1, 2), 200)
         assert np.array_equal(got == 200, want), (k, p.tolist())
+
+
+@pytest.mark.parametrize("rig", ["rig3", "models"])
+def test_fast_mapper_oracle_vs_reference_fixture(rig):
+    """vr::FastMapper: the oracle's tables == the tables the reference's own constructor built, and its frame == the frame
+    the OpenCL kernel's arithmetic gives on them (oracle/refgen/ref_fast.cpp); second rig: odd output height, so the
+    half-size tables go through the generic bilinear resize instead of the 2x area path."""
+    g = np.load(os.path.join(GOLD, "fast_%s.npz" % rig))
+    t = O.Template()
+    t.out_size = tuple(int(v) for v in g["out_size"])
+    W, H = t.out_size
+    n = int(g["n"])
+    for i in range(n):
+        t.inputs.append(dict(roi=(0, 0, W, H), map1=g["t_map1_%d" % i], map2=g["t_map2_%d" % i], mask=g["t_mask%d" % i], vignette=None))
+    iw, ih = (int(v) for v in g["in_size"])
+    fo = O.FastMapperOracle(t, [(iw, ih)] * n)
+    for i in range(n):
+        for key, tab in (("map1_", fo.map1), ("map2_", fo.map2), ("hmap1_", fo.hmap1), ("hmap2_", fo.hmap2), ("feather", fo.feather), ("hfeather", fo.hfeather)):
+            assert np.array_equal(g[key + str(i)], tab[i]), (rig, key, i)
+    with np.errstate(over="ignore"):
+        out = fo.stitch_nv12([O.fast_noise_frame(i, iw, ih) for i in range(n)])
+    assert np.array_equal(fo.last_acc0, g["acc_c0"])
+    assert np.array_equal(out, g["result"])
