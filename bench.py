@@ -546,6 +546,12 @@ def run_stereo(args, sub=False):
     out = outs[0]
     pipe = vr.sharding.FramePipeline(st, src=0, defer_collect=os.environ.get("OCTVR_DEFER_COLLECT", "0") != "0", peer=peer)
 
+    nobcast = os.environ.get("OCTVR_C4_NOBCAST", "0") != "0"      # diagnostic: frames taken as already resident on every rank
+    if nobcast and world > 1:
+        for fl in flats:
+            dist.broadcast(fl, 0)
+        vr.sharding.broadcast_frames = lambda *a, **k: []
+
     def step(k, last=False):
         if world > 1:      # broadcast of step k + 1 runs under the stitch of step k (OCTVR_DEFER_COLLECT=1: the band collection of step k - 1 too)
             pipe.step(flats[k % RING], ring[k % RING], outs[k % 2], next_flat=None if last else flats[(k + 1) % RING])
@@ -583,6 +589,9 @@ def run_stereo(args, sub=False):
     clocks = sampler.stop() if sampler else None
     ms = vr.sharding.max_over_ranks(e0.elapsed_time(e1), device="cuda")
     local_ms = vr.sharding.max_over_ranks(statistics.median(stage["total"]), device="cuda")
+    if world > 1 and pipe.trace is not None:
+        rows = pipe.trace_report()[-min(args.steps, 12):]
+        sys.stderr.write("[c4 trace] rank %d (wait for inputs, stitch, signal) ms: %s\n" % (rank, " ".join("%.3f/%.3f/%.3f" % r for r in rows)))
     stats = [m.stats() for _, _, m in st.jobs]
     jobs_rank0 = [(j[0], list(j[1])) for j in st.jobs]
     exchange = None

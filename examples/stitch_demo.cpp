@@ -3,11 +3,21 @@
 //   stitch_demo --config JSON W IN_W IN_H BLEND OUT.i420
 //        build the template on the GPU, push/pop three synthetic frames through AsyncMultiMapper,
 //        write the last output frame (standard I420) to OUT.i420
+//   stitch_demo --fast JSON W IN_W IN_H OUT.nv12
+//        vr::FastMapper: full-frame template (use_roi = false), one stitch_nv12 of synthetic NV12 frames on the device
 #include "octvr.hpp"
 #include <cstdio>
 #include <cstring>
 #include <memory>
 #include <sstream>
+
+// the CUDA runtime calls the --fast mode needs for its device frames (declared here so the demo builds without CUDA headers)
+extern "C" {
+int cudaMalloc(void** p, size_t n);
+int cudaMemcpy(void* dst, const void* src, size_t n, int kind);
+int cudaDeviceSynchronize(void);
+int cudaFree(void* p);
+}
 
 static uint64_t splitmix64(uint64_t x)
 {
@@ -70,6 +80,35 @@ int main(int argc, char** argv)
             fwrite(out.data(), 1, out.size(), fo);
             fclose(fo);
             printf("ok %dx%d fps %.1f\n", W, H, am->fps());
+            return 0;
+        }
+        if (argc >= 7 && !strcmp(argv[1], "--fast")) {
+            std::ifstream f(argv[2]);
+            std::stringstream ss; ss << f.rdbuf();
+            const int W = atoi(argv[3]), iw = atoi(argv[4]), ih = atoi(argv[5]);
+            vr::MapperTemplate mt = vr::MapperTemplate::from_config(ss.str(), W, -1, /*use_roi=*/false, /*create_masks=*/false);
+            const int n = (int)mt.num_inputs(), H = mt.out_size.height;
+            vr::FastMapper fm(mt, std::vector<vr::Size>(n, vr::Size{ iw, ih }));
+            const size_t in_bytes = (size_t)iw * (ih + ih / 2), out_bytes = (size_t)W * (H + H / 2);
+            std::vector<const uint8_t*> d_in(n);
+            std::vector<uint8_t> h(in_bytes);
+            for (int c = 0; c < n; c++) {
+                for (size_t o = 0; o < in_bytes; o++) h[o] = (uint8_t)(splitmix64(0xFA57ull ^ ((uint64_t)c << 32) ^ o) & 0xFF);
+                void* d = nullptr;
+                if (cudaMalloc(&d, in_bytes) || cudaMemcpy(d, h.data(), in_bytes, 1)) throw std::runtime_error("cudaMalloc / cudaMemcpy");
+                d_in[c] = (const uint8_t*)d;
+            }
+            void* d_out = nullptr;
+            if (cudaMalloc(&d_out, out_bytes)) throw std::runtime_error("cudaMalloc");
+            fm.stitch_nv12(d_in, std::vector<size_t>(n, (size_t)iw), (uint8_t*)d_out, (size_t)W);
+            std::vector<uint8_t> out(out_bytes);
+            if (cudaDeviceSynchronize() || cudaMemcpy(out.data(), d_out, out_bytes, 2)) throw std::runtime_error("cudaMemcpy");
+            for (auto p : d_in) cudaFree((void*)p);
+            cudaFree(d_out);
+            FILE* fo = fopen(argv[6], "wb");
+            fwrite(out.data(), 1, out.size(), fo);
+            fclose(fo);
+            printf("ok fast %dx%d\n", W, H);
             return 0;
         }
         fprintf(stderr, "usage: see source\n");

@@ -1,6 +1,6 @@
 // include/octvr.hpp -- header-only C++ shim with the reference's names over the C ABI (octvr_b200.h).
 //
-// Mirrors modules/octvr/include/octvr.hpp (vr::MapperTemplate :48-91, vr::AsyncMultiMapper :103-121) and
+// Mirrors modules/octvr/include/octvr.hpp (vr::MapperTemplate :48-91, vr::AsyncMultiMapper :103-121, vr::FastMapper :123-144) and
 // modules/octvr/src/mapper.hpp (vr::Mapper :29-95): same class and method names, argument meaning and error
 // behaviour (std::string thrown for bad camera type / size / .dat magic -- template.cpp:30,33,53,262;
 // exceptions for shape violations where the reference CV_Asserts).  OpenCV-free: planes are vr::Plane views, sizes vr::Size,
@@ -288,6 +288,29 @@ public:
 private:
     AsyncMultiMapper() {}
     octvr_async* h_ = nullptr;
+};
+
+// octvr.hpp:123-144, mapper_fast.cpp.  NV12 frames as DEVICE pointers to (rows + rows / 2) x step bytes (the reference's
+// cv::UMat of that shape: luma rows, then interleaved chroma rows).  stitch() throws like the reference's ("not supported yet").
+class FastMapper {
+public:
+    FastMapper(const MapperTemplate& mt, std::vector<Size> in_sizes, int device = 0)
+    {
+        std::vector<int> wh;
+        for (auto& s : in_sizes) { wh.push_back(s.width); wh.push_back(s.height); }
+        check(octvr_fast_create(mt.handle(), wh.data(), (int)in_sizes.size(), device, &h_));
+    }
+    void stitch(const std::vector<const uint8_t*>&, uint8_t*) { throw "not supported yet"; }      // mapper_fast.cpp:149
+    void stitch_nv12(const std::vector<const uint8_t*>& inputs, const std::vector<size_t>& steps, uint8_t* output, size_t out_step, void* stream = nullptr)
+    {
+        if (inputs.size() != steps.size()) throw Error(OCTVR_ERR_INVALID, "one step per input");
+        check(octvr_fast_stitch_nv12(h_, inputs.data(), steps.data(), (int)inputs.size(), output, out_step, stream));
+    }
+    FastMapper(const FastMapper&) = delete;
+    FastMapper& operator=(const FastMapper&) = delete;
+    ~FastMapper() { octvr_fast_destroy(h_); }
+private:
+    octvr_fast* h_ = nullptr;
 };
 
 }  // namespace vr

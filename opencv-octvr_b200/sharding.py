@@ -10,6 +10,7 @@ Multi-GPU partitioning of the stitch path.
     and, within an eye, by row bands.  Multiband band mappers carry their own halo rows (csrc/multiband.cu).
 Works with any backend (NCCL on the GPU box, gloo in the CPU tests).
 """
+import os
 import torch
 import torch.distributed as dist
 
@@ -277,6 +278,7 @@ class FramePipeline:
         self.st, self.src, self.pending, self.defer, self.peer = stitcher, src, {}, defer_collect, peer
         self.collecting = {}                            # output buffer -> work handles of its band collection
         self.token = None
+        self.trace = [] if os.environ.get("OCTVR_C4_TRACE") else None
         if peer:
             signal_group()                              # collective: every rank builds the pipeline
 
@@ -291,6 +293,8 @@ class FramePipeline:
             works = broadcast_frames(flat, self.src, async_op=True)
         for w in works:
             w.wait()                                   # the compute stream waits for the broadcast, the host does not
+        if self.trace is not None:
+            self._mark("inputs")
         if next_flat is not None:
             self.pending[next_flat.data_ptr()] = broadcast_frames(next_flat, self.src, async_op=True)
         self._wait_collect(out)                        # an earlier frame may still be leaving this buffer
@@ -298,6 +302,8 @@ class FramePipeline:
             self.st.stitch_local(frames, out)
         else:
             self.st.mapper.stitch_packed(frames, out)
+        if self.trace is not None:
+            self._mark("stitch")
         if collect and self.peer:
             if self.token is None:
                 self.token = torch.zeros(1, dtype=torch.int32, device=out.device)
@@ -307,7 +313,25 @@ class FramePipeline:
                 self.collecting[out.data_ptr()] = collect_shares(out, self.st.shares(), self.src, wait=False)
             else:
                 collect_shares(out, self.st.shares(), self.src)
+        if self.trace is not None:
+            self._mark("done")
         return out
+
+    def _mark(self, what):
+        e = torch.cuda.Event(enable_timing=True)
+        e.record()
+        self.trace.append((what, e))
+
+    def trace_report(self):
+        """OCTVR_C4_TRACE: per step, ms the compute stream spent waiting for the input broadcast, in the stitch, and in the
+        completion signal (CUDA events on the compute stream; call after a synchronize)."""
+        rows, prev = [], None
+        ev = self.trace
+        for i in range(0, len(ev) - 2, 3):
+            a, b, c = ev[i][1], ev[i + 1][1], ev[i + 2][1]
+            rows.append((prev.elapsed_time(a) if prev is not None else 0.0, a.elapsed_time(b), b.elapsed_time(c)))
+            prev = c
+        return rows
 
     def flush(self):
         """Wait (on the current stream) for every band collection still in flight."""

@@ -22,7 +22,7 @@ def demo(tmp_path_factory):
     cuda_lib = "/usr/local/cuda/lib64"
     subprocess.check_call(["/usr/bin/g++", "-std=c++17", "-O1", "-I" + os.path.join(ROOT, "include"),
                            os.path.join(ROOT, "examples", "stitch_demo.cpp"), "-o", exe, "-L" + libdir, "-loctvr_b200",
-                           "-Wl,-rpath," + libdir, "-Wl,-rpath," + cuda_lib])
+                           "-L" + cuda_lib, "-lcudart", "-Wl,-rpath," + libdir, "-Wl,-rpath," + cuda_lib])
     return exe
 
 
@@ -68,3 +68,14 @@ def test_shim_incremental_template_writes_the_reference_tools_bytes(demo, tmp_pa
     ref = json.load(open(os.path.join(util.GOLD, "dat_sha256.json")))["rig3"]
     data = open(tmp_path / "t.dat", "rb").read()
     assert len(data) == ref["bytes"] and hashlib.sha256(data).hexdigest() == ref["sha256"]
+
+
+@pytest.mark.gpu
+def test_shim_fast_mapper_matches_oracle(demo, tmp_path):
+    """vr::FastMapper(mt, in_sizes) + stitch_nv12 through the C++ shim == the FastMapper oracle."""
+    cfg = os.path.join(util.GOLD, "rigs", "rig3.json")
+    outp = str(tmp_path / "o.nv12")
+    r = subprocess.run([demo, "--fast", cfg, "256", "320", "240", outp], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    got = np.fromfile(outp, np.uint8).reshape(192, 256)
+    assert np.array_equal(got, np.load(os.path.join(util.GOLD, "fast_rig3.npz"))["result"])

@@ -72,11 +72,11 @@ def test_fast_mapper_vs_oracle_larger(name, width, in_size):
 
 
 def test_fast_mapper_error_behaviour():
-    cfg = util.rig_json("rig3")
-    t = vr.MapperTemplate.from_json(cfg, 256)                     # ROI-cropped inputs: "does not support ROI yet"
+    tm = vr.MapperTemplate.from_json(util.rig_json("models"), 192)   # ROI-cropped inputs: "does not support ROI yet"
     with pytest.raises(vr.OctvrError) as e:
-        vr.FastMapper(t, [(320, 240)] * 3)
+        vr.FastMapper(tm, [(320, 240)] * tm.num_inputs)
     assert e.value.code == vr.capi.ERR_UNSUPPORTED
+    cfg = util.rig_json("rig3")
     t = vr.MapperTemplate.from_json(cfg, 256, use_roi=False)
     with pytest.raises(vr.OctvrError):
         vr.FastMapper(t, [(320, 240)] * 2)                        # input count
