@@ -590,8 +590,12 @@ def run_stereo(args, sub=False):
     ms = vr.sharding.max_over_ranks(e0.elapsed_time(e1), device="cuda")
     local_ms = vr.sharding.max_over_ranks(statistics.median(stage["total"]), device="cuda")
     if world > 1 and pipe.trace is not None:
-        rows = pipe.trace_report()[-min(args.steps, 12):]
-        sys.stderr.write("[c4 trace] rank %d (wait for inputs, stitch, signal) ms: %s\n" % (rank, " ".join("%.3f/%.3f/%.3f" % r for r in rows)))
+        rows = pipe.trace_report()[-args.steps:]
+        tot = [sum(r) for r in rows]
+        slow = sorted(range(len(tot)), key=lambda i: -tot[i])[:4]
+        sys.stderr.write("[c4 trace] rank %d: %d timed steps, sum %.3f ms (events %.3f ms), median step %.3f, slowest %s; last 6 (wait for inputs / stitch / signal): %s\n"
+                         % (rank, len(rows), sum(tot), e0.elapsed_time(e1), statistics.median(tot), ["#%d %.3f" % (i, tot[i]) for i in slow],
+                            " ".join("%.3f/%.3f/%.3f" % r for r in rows[-6:])))
     stats = [m.stats() for _, _, m in st.jobs]
     jobs_rank0 = [(j[0], list(j[1])) for j in st.jobs]
     exchange = None

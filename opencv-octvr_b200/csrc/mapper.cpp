@@ -318,20 +318,43 @@ static void build_mapper(octvr_mapper& m, const octvr_template& t, const int* in
     }
 
     // ---- fixed-point coordinates and blend weights per ROI pixel ----
-    std::vector<Img<int32_t>> sx(n), sy(n);
-    for (int i = 0; i < n; i++) quantise_map(t.inputs[i].map1, t.inputs[i].map2, m.in_w[i], m.in_h[i], sx[i], sy[i]);
-    tr.lap("vignette + quantise_map");
     m.pairs = 0; m.roi_area = 0;
     for (int i = 0; i < n; i++) {
         m.roi_area += (int64_t)t.inputs[i].roi.w * t.inputs[i].roi.h;
         for (uint8_t v : t.inputs[i].mask.d) m.pairs += v != 0;
     }
+    // OCTVR_BLEND=fused selects the single-kernel path (K_stitch_fused: no RGBX image in HBM, half the DRAM traffic, but
+    // measured slower per frame than convert + blend because the conversion no longer hides the latency of the gain
+    // launch -- DESIGN.md section 4); default: K_convert(+gain) then K_blend_ring
+    const char* mode = getenv("OCTVR_BLEND");
+    const bool want_fused = blend <= 0 && mode && std::string(mode) == "fused" && n_ov == 0;   // overlays need the RGBX planes
+    // RGBX planes written by K_convert: only the two-kernel and multiband paths need them
+    if (!want_fused)
+        for (int i = 0; i < n + n_ov; i++) m.d_rgbx.push_back(dev_alloc<uint32_t>((size_t)m.in_w[i] * m.in_h[i] + 4));
+    m.src_row0.assign(n + n_ov, 0);
+    for (int i = 0; i < n + n_ov; i++) m.src_row1.push_back(m.in_h[i]);
+    tr.lap("vignette + pairs + planes");
+    // default layout (K_blend_ring): quantisation, feather weights, job list, boxes and entries by CUDA kernels (pack.cu)
+    const bool is_band = m.band_y0 != 0 || m.band_y1 != t.out_h;
+    const bool gpu_packed = blend <= 0 && !want_fused && pack_ring_gpu(m, t, blend);
+    // host copies of the fixed-point coordinates: only where host code still walks them (multiband set-up, the source rows of
+    // a row band, the non-default layouts); the gain tables sample a few thousand positions through fixed_at()
+    std::vector<Img<int32_t>> sx(n), sy(n);
+    const bool host_xy = blend > 0 || !gpu_packed || is_band;
+    if (host_xy) {
+        for (int i = 0; i < n; i++) quantise_map(t.inputs[i].map1, t.inputs[i].map2, m.in_w[i], m.in_h[i], sx[i], sy[i]);
+        tr.lap("quantise_map (host)");
+    }
+    auto fixed_at = [&](int i, int lx, int ly, int32_t& fsx, int32_t& fsy) {
+        if (host_xy) { fsx = sx[i].row(ly)[lx]; fsy = sy[i].row(ly)[lx]; return; }
+        const float fw = (float)(double)m.in_w[i], fh = (float)(double)m.in_h[i];      // quantise_map, one pixel
+        const float px = t.inputs[i].map1.row(ly)[lx] * fw + 0.f, py = t.inputs[i].map2.row(ly)[lx] * fh + 0.f;
+        fsx = (int32_t)lrintf(px * 32.f); fsy = (int32_t)lrintf(py * 32.f);
+    };
 
     // source rows a row-band mapper touches (feather / no blend: the taps of its own output rows; the multiband set-up
     // widens this to its row window)
-    m.src_row0.assign(n + n_ov, 0);
-    for (int i = 0; i < n + n_ov; i++) m.src_row1.push_back(m.in_h[i]);
-    if (m.band_y0 != 0 || m.band_y1 != t.out_h)
+    if (is_band)
         for (int i = 0; i < n; i++) {
             const TInput& in = t.inputs[i];
             int lo = INT32_MAX, hi = INT32_MIN;
@@ -342,21 +365,15 @@ static void build_mapper(octvr_mapper& m, const octvr_template& t, const int* in
             m.src_row0[i] = std::max(0, lo) & ~1; m.src_row1[i] = std::min(m.in_h[i], hi + 1);
         }
 
-    tr.lap("pairs + source rows");
     std::vector<Img<float>> W;
-    if (blend <= 0) {
+    if (blend <= 0 && !gpu_packed) {
         W = blend < 0 ? feather_weights(t.inputs, -blend) : overwrite_weights(t.inputs);
-        tr.lap("feather / overwrite weights");
+        tr.lap("feather / overwrite weights (host)");
         m.inv_n = blend < 0 ? (float)(1.0 / n) : 1.f;
-        // OCTVR_BLEND=fused selects the single-kernel path (K_stitch_fused: no RGBX image in HBM, half the DRAM traffic, but
-        // measured slower per frame than convert + staged blend because the conversion no longer hides the latency of the
-        // gain launch -- DESIGN.md section 4); default: K_convert(+gain) then K_blend_staged, or K_blend (OCTVR_BLEND=direct)
-        const char* mode = getenv("OCTVR_BLEND");
-        if (mode && std::string(mode) == "fused" && n_ov == 0) build_fused(m, t, sx, sy, W);   // overlays need the RGBX planes
+        if (want_fused) build_fused(m, t, sx, sy, W);
+        if (want_fused && !m.fused)      // the fused layout did not apply: the two-kernel path needs its planes after all
+            for (int i = 0; i < n + n_ov; i++) m.d_rgbx.push_back(dev_alloc<uint32_t>((size_t)m.in_w[i] * m.in_h[i] + 4));
     }
-    // RGBX planes written by K_convert: only the two-kernel and multiband paths need them
-    if (!m.fused)
-        for (int i = 0; i < n + n_ov; i++) m.d_rgbx.push_back(dev_alloc<uint32_t>((size_t)m.in_w[i] * m.in_h[i] + 4));
     // overlay inputs: one table entry per roi pixel (cv::remap fixed point; valid <=> mask), mapper.cpp:116-127
     for (int k = 0; k < n_ov; k++) {
         const TInput& in = t.overlays[k];
@@ -378,7 +395,7 @@ static void build_mapper(octvr_mapper& m, const octvr_template& t, const int* in
     if (blend > 0) {
         m.mb = ob::multiband_create(m, t, sx, sy);
         tr.lap("multiband_create");
-    } else {
+    } else if (!gpu_packed) {
         if (!m.fused) {
         // ---- tile-compacted tables ----
         const int tiles_x = (t.out_w + TILE_W - 1) / TILE_W, tiles_y = (t.out_h + TILE_H - 1) / TILE_H;
@@ -615,9 +632,11 @@ static void build_mapper(octvr_mapper& m, const octvr_template& t, const int* in
                 const int ly = std::min((int)std::floor(dy * ify), in.roi.h - 1);
                 for (int dx = 0; dx < c.sw; dx++) {
                     const int lx = std::min((int)std::floor(dx * ifx), in.roi.w - 1);
-                    uint2 e = make_entry(sx[i].row(ly)[lx], sy[i].row(ly)[lx], m.in_w[i], m.in_h[i], in.mask.row(ly)[lx] != 0);
+                    int32_t fsx, fsy;
+                    fixed_at(i, lx, ly, fsx, fsy);
+                    uint2 e = make_entry(fsx, fsy, m.in_w[i], m.in_h[i], in.mask.row(ly)[lx] != 0);
                     if (e.y & C_VALID) {        // the gain kernel reads the input planes directly: keep (ix, iy), not a plane offset
-                        const int ix = std::min(32767, std::max(-32768, sx[i].row(ly)[lx] >> 5)), iy = std::min(32767, std::max(-32768, sy[i].row(ly)[lx] >> 5));
+                        const int ix = std::min(32767, std::max(-32768, fsx >> 5)), iy = std::min(32767, std::max(-32768, fsy >> 5));
                         e.x = (uint32_t)(ix + 1) | ((uint32_t)(iy + 1) << 16);
                     }
                     if (sm.row(dy)[dx] != 255) e = make_uint2(0xFFFFFFFFu, 0u);     // CPU compensator's intersect rule: mask == 255

@@ -79,6 +79,9 @@ struct octvr_mapper {
 namespace ob {
 // mapper.cpp: CUtensorMap (128 bytes, written to out128) over an RGBX plane for box_w x box_h boxes, zero fill outside
 void encode_rgbx_tensor_map(void* out128, const uint32_t* plane, int plane_w, int plane_h, int box_w, int box_h);
+// pack.cu: the default feather / no-blend tables (K_blend_ring layout) packed by CUDA kernels; false = not applicable
+// (then build_mapper's host packer runs).  m.d_rgbx must be allocated.
+bool pack_ring_gpu(octvr_mapper& m, const octvr_template& t, int blend);
 // multiband.cu
 Multiband* multiband_create(octvr_mapper& m, const octvr_template& t,
                             const std::vector<Img<int32_t>>& sx, const std::vector<Img<int32_t>>& sy);

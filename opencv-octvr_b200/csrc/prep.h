@@ -38,6 +38,8 @@ std::vector<Img<uint8_t>> distance_seam_masks(const std::vector<TInput>& in, int
 std::vector<Img<uint8_t>> distance_seam_masks_host(const std::vector<TInput>& in, int out_w);
 bool distance_seam_masks_gpu(const std::vector<TInput>& in, int out_w, int device, std::vector<Img<uint8_t>>& out);
 int seam_backend();
+// seam.cu: d_dist[i] = cv::distanceTransform(d_mask[i], DIST_L2, 3) for n DEVICE images (one CTA each, widths <= 8192)
+void chamfer_l2_gpu_batch(const uint8_t* const* d_mask, const int* w, const int* h, float* const* d_dist, int n);
 
 // cv::remap coordinate quantisation for planar f32 maps (imgwarp.cpp:4383-4442) applied to
 // fl32(map * size) (template.cpp:175-176).  Returns 1/32-px fixed point sx, sy.

@@ -188,6 +188,26 @@ void resize_u8(const uint8_t* d_src, int sw, int sh, uint8_t* d_dst, int dw, int
 }
 }  // namespace
 
+// d_dist[i] = cv::distanceTransform(d_mask[i], DIST_L2, 3) for n device images (one CTA each, widths <= 8192)
+void chamfer_l2_gpu_batch(const uint8_t* const* d_mask, const int* w, const int* h, float* const* d_dist, int n)
+{
+    std::vector<ChamferJob> jobs(n);
+    std::vector<std::unique_ptr<Dev<int>>> tmp(n);
+    int max_w = 0;
+    for (int i = 0; i < n; i++) {
+        OB_CHECK(w[i] > 0 && h[i] > 0 && w[i] <= CH_THREADS * CH_ITEMS, "chamfer: image width");
+        tmp[i].reset(new Dev<int>((size_t)w[i] * h[i]));
+        jobs[i] = ChamferJob{ d_mask[i], w[i], h[i], 1, tmp[i]->p, d_dist[i] };
+        max_w = std::max(max_w, w[i]);
+    }
+    Dev<ChamferJob> d_jobs(jobs.data(), jobs.size());
+    const size_t smem = (size_t)(2 * (max_w + 2) + 64) * sizeof(int);
+    OB_CUDA(cudaFuncSetAttribute(k_chamfer, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    k_chamfer<<<n, CH_THREADS, smem>>>(d_jobs.p);
+    OB_CUDA(cudaGetLastError());
+    OB_CUDA(cudaDeviceSynchronize());                         // tmp and the job list are freed on return
+}
+
 bool distance_seam_masks_gpu(const std::vector<TInput>& in, int out_w, int device, std::vector<Img<uint8_t>>& out)
 {
     const int n = (int)in.size();
