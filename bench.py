@@ -211,12 +211,12 @@ def measure_single(args, workload, steps, warmup, with_e2e):
         for s in stage:
             stage[s].append(m.stage_ms(s))
     m.set_profiling(False)
+    # (the sampler starts BEFORE the barrier, see run_stereo)
+    sampler = ClockSampler(local) if rank == 0 else None
     torch.cuda.synchronize()
-
     if world > 1:
         dist.barrier()
     torch.cuda.synchronize()
-    sampler = ClockSampler(local) if rank == 0 else None
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record(stream)
     for k in range(steps):
@@ -442,11 +442,13 @@ def run_streams(args, sub=False):
         for s_ in stage:
             stage[s_].append(mappers[0].stage_ms(s_))
     mappers[0].set_profiling(False)
+    # (the sampler starts BEFORE the barrier: its start-up on rank 0 must not fall between the barrier and the first timed step,
+    # where the other ranks of a collective workload would wait for it inside their timed region)
+    sampler = ClockSampler(local) if rank == 0 else None
     torch.cuda.synchronize()
     if world > 1:
         dist.barrier()
     torch.cuda.synchronize()
-    sampler = ClockSampler(local) if rank == 0 else None
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record(main)
     fork()
@@ -573,11 +575,13 @@ def run_stereo(args, sub=False):
             stage[s_].append(sum(m.stage_ms(s_) for _, _, m in st.jobs))
     for _, _, m in st.jobs:
         m.set_profiling(False)
+    # (the sampler starts BEFORE the barrier: its start-up on rank 0 must not fall between the barrier and the first timed step,
+    # where the other ranks of a collective workload would wait for it inside their timed region)
+    sampler = ClockSampler(local) if rank == 0 else None
     torch.cuda.synchronize()
     if world > 1:
         dist.barrier()
     torch.cuda.synchronize()
-    sampler = ClockSampler(local) if rank == 0 else None
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     t_host = time.perf_counter()
