@@ -33,6 +33,7 @@ WORKLOADS = {
     "c3": ("rig6", 64, True, "C3 6x2704x1520 -> 4096x2048 equirect, gain + 5-band multiband"),
     "c4": (("rig8L", "rig8R"), 64, True, "C4 8x3840x2160 fisheye -> 7680x3840 stereo top-bottom, gain + 5-band multiband"),
     "c5": ("rig6", -1, True, "C5 16 independent streams of the C2 rig (6x2704x1520 -> 4096x2048, gain + feather(1)), frame-sharded"),
+    "fast": ("rig6", -5, False, "FastMapper (NV12, u8 feather weights) on the C2 rig: 6x2704x1520 NV12 -> 4096x2048 NV12"),
     "c2ng": ("rig6", -1, False, "C2 rig without gain compensation: 6x2704x1520 -> 4096x2048 equirect, feather(1) (diagnostic)"),
 }
 
@@ -309,6 +310,8 @@ def run_ours(args):
         guarded("c3", lambda: measure_single(args, "c3", max(10, min(args.steps, 100)), max(3, min(args.warmup, 10)), with_e2e=False))
         a5 = _ap.Namespace(**vars(args)); a5.workload = "c5"; a5.steps = max(3, min(args.steps, 8)); a5.warmup = 3
         guarded("c5", lambda: run_streams(a5, sub=True))
+        af = _ap.Namespace(**vars(args)); af.workload = "fast"; af.steps = max(10, min(args.steps, 100))
+        guarded("fast_nv12", lambda: run_fast(af, sub=True))
         a4 = _ap.Namespace(**vars(args)); a4.workload = "c4"; a4.steps = max(5, min(args.steps, 30)); a4.warmup = 3; a4.verify = world > 1
         guarded("c4_rowband", lambda: run_stereo(a4, sub=True))
     pg_done()
@@ -318,6 +321,76 @@ def run_ours(args):
     if not args.no_cpu and world == 1:      # the CPU baseline is timed on rank 0 at N = 1 only
         line["cpu_baseline"] = cpu_baseline(args.workload, budget_s=20.0)
     print(json.dumps(line))
+
+
+def run_fast(args, sub=False):
+    """vr::FastMapper (mapper_fast.cpp) on the C2 rig with full-frame tables (the reference's FastMapper takes no ROI): NV12
+    frames resident in HBM, one launch of k_fast_nv12 per frame.  Frame-sharded like the headline workload (each rank its own
+    stream, no data-path collective).  Algorithmic bytes per frame: I + 8 * (P_luma + P_chroma) + O (8-byte table entries for
+    the contributing (pixel, camera) pairs of the luma and the chroma tables)."""
+    import torch
+    import torch.distributed as dist
+    import octvr_b200 as vr
+    import util
+    world, rank, local = int(os.environ.get("WORLD_SIZE", "1")), int(os.environ.get("RANK", "0")), int(os.environ.get("LOCAL_RANK", "0"))
+    pg_init(local)
+    torch.cuda.set_device(local)
+    rig, _, _, desc = WORKLOADS["fast"]
+    cfg, width, in_size = util.named_rig(rig)
+    n = len(cfg["inputs"])
+    iw, ih = in_size
+    t0 = time.time()
+    tmpl = vr.MapperTemplate.from_json(cfg, width, -1, use_roi=False, with_seam_masks=False, device=local)
+    t_tmpl = time.time() - t0
+    t0 = time.time()
+    fm = vr.FastMapper(tmpl, [in_size] * n, device=local)
+    t_map = time.time() - t0
+    W, H = tmpl.out_size
+    RING = 8
+    gen = torch.Generator(device="cuda").manual_seed(1234 + rank)
+    frames = [[torch.randint(0, 256, (ih + ih // 2, iw), dtype=torch.uint8, device="cuda", generator=gen) for c in range(n)] for k in range(RING)]
+    out = torch.zeros((H + H // 2, W), dtype=torch.uint8, device="cuda")
+    for k in range(max(3, args.warmup)):
+        fm.stitch_nv12(frames[k % RING], out)
+    sampler = ClockSampler(local) if rank == 0 else None
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for k in range(args.steps):
+        fm.stitch_nv12(frames[k % RING], out)
+    e1.record()
+    torch.cuda.synchronize()
+    clocks = sampler.stop() if sampler else None
+    ms = vr.sharding.max_over_ranks(e0.elapsed_time(e1), device="cuda")
+    info = fm.info()
+    del fm, frames, out
+    torch.cuda.empty_cache()
+    if not sub:
+        pg_done()
+    if rank != 0:
+        return None
+    peak, how = peaks()
+    I, O_ = n * iw * (ih + ih // 2), W * (H + H // 2)
+    B = I + 8 * (info["pairs_luma"] + info["pairs_chroma"]) + O_
+    ms_per_step = ms / args.steps
+    ach = B / (ms_per_step * 1e-3) / 1e9
+    return {
+        "metric": "equirect output Mpix/s", "value": round(world * W * H / (ms_per_step * 1e-3) / 1e6, 1), "unit": "Mpix/s", "n_gpus": world,
+        "steps": args.steps, "warmup": max(3, args.warmup), "ms_per_step": round(ms_per_step, 5), "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "u8", "data": "synthetic", "frames_per_s": round(world * args.steps / (ms * 1e-3), 1),
+        "config": {"workload": desc, "inputs": "%dx%dx%d NV12, ring of %d noise frames per camera resident in HBM" % (n, iw, ih, RING),
+                   "output": "%dx%d NV12" % (W, H), "l2": "tables (%.0f MB) + frames exceed the 126 MB L2; no flush" % (info["table_bytes"] / 1e6),
+                   "pairs_luma": info["pairs_luma"], "pairs_chroma": info["pairs_chroma"], "sharding": "one stream per GPU, no data-path collective",
+                   "template_build_s": round(t_tmpl, 2), "mapper_build_s": round(t_map, 2)},
+        "alg_bytes_per_frame": int(B),
+        "roofline": {"bound": "hbm", "kernel": "k_fast_nv12", "achieved": round(ach, 1), "peak": peak, "peak_source": how, "unit": "GB/s",
+                     "frac": round(ach / peak, 4), "traffic": ncu_traffic("fast", 0) if ncu_traffic("fast", 0) else None,
+                     "alg_bytes_per_launch": int(B), "ms_per_launch": round(ms_per_step, 5)},
+        "gpu_launches": args.steps, "clocks": clocks,
+    }
 
 
 def run_rowband(args):
@@ -525,7 +598,8 @@ def run_stereo(args, sub=False):
     t_tmpl = time.time() - t0
     iw, ih = in_size
     t0 = time.time()
-    st = vr.sharding.StereoRowBandStitcher(vr, tmpls, [in_size] * n, blend, gain, local)
+    peer = world > 1 and os.environ.get("OCTVR_C4_COLLECT", "peer") == "peer"
+    st = vr.sharding.StereoRowBandStitcher(vr, tmpls, [in_size] * n, blend, gain, local, split="auto" if peer or world == 1 else "rows")
     t_map = time.time() - t0
     W, He = st.eye_w, st.eye_h
     H = 2 * He
@@ -542,7 +616,6 @@ def run_stereo(args, sub=False):
     # N > 1: the two output frames live on rank 0 and are mapped into every rank (CUDA IPC over NVLink): each rank's blend
     # kernels store their band straight into rank 0's frame, one 4-byte all-reduce per step says "frame complete".
     # OCTVR_C4_COLLECT=nccl: private output buffers, bands sent to rank 0 by NCCL send / recv (the round-1 path).
-    peer = world > 1 and os.environ.get("OCTVR_C4_COLLECT", "peer") == "peer"
     pfs = [vr.sharding.PeerFrame(H * 3 // 2, W, local, owner=0) for _ in range(2)] if peer else []
     outs = [p.tensor for p in pfs] if peer else [torch.zeros((H * 3 // 2, W), dtype=torch.uint8, device="cuda") for _ in range(2)]
     out = outs[0]
@@ -627,6 +700,7 @@ def run_stereo(args, sub=False):
         verified = bool(torch.equal(ref, outs[(args.steps - 1) % 2]))
         del one, ref
     src_rows = [[int(m.src_rows()[c][1] - m.src_rows()[c][0]) for c in range(n)] for _, _, m in st.jobs]
+    st_split = st.split
     del st, pipe, outs, out, ring, flats, tmpls
     for pf in pfs:
         pf.close()
@@ -649,7 +723,7 @@ def run_stereo(args, sub=False):
         "config": {"workload": desc, "inputs": "%dx%dx%d I420 (octvr packed layout), ring of %d noise frames resident on rank 0" % (n, iw, ih, RING),
                    "output": "%dx%d 4:2:0 top-bottom (two %dx%d eyes)" % (W, H, W, He),
                    "l2": "working set per step exceeds the 126 MB L2; no flush",
-                   "sharding": ("row bands of one stream: per step ONE NCCL broadcast of the %d input frames (%.1f MB) from rank 0 (issued one step "
+                   "sharding": (("column" if st_split == "cols" else "row") + " bands of one stream: per step ONE NCCL broadcast of the %d input frames (%.1f MB) from rank 0 (issued one step "
                                 "ahead, overlapping the previous stitch), (eye, band) stitch of the source rows the band reads "
                                 "(%.1f MB frame in total)" % (n, I / 1e6, W * H * 1.5 / 1e6)) if world > 1 else "single GPU, both eyes",
                    "assignment_rank0": jobs_rank0, "source_rows_converted_rank0": src_rows,
@@ -817,6 +891,10 @@ def main():
         run_stereo(args)
     elif args.workload == "c5":
         run_streams(args)
+    elif args.workload == "fast":
+        line = run_fast(args)
+        if line is not None:
+            print(json.dumps(line))
     elif args.rowband and int(os.environ.get("WORLD_SIZE", "1")) > 1:
         run_rowband(args)
     else:

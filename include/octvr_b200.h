@@ -123,6 +123,13 @@ octvr_status octvr_mapper_create(const octvr_template* t, const int* in_sizes_wh
 octvr_status octvr_mapper_create_band(const octvr_template* t, const int* in_sizes_wh, int n_in,
                                       int blend, int enable_gain, int band_y0, int band_y1,
                                       int device, octvr_mapper** out);
+/* The same with a window of output columns [x0, x1) x rows [y0, y1) (each range a multiple of 32 or the frame edge; 0, 0 =
+ * the whole axis).  Column windows are a multiband (blend > 0) partition: the halo of 4 * 2^bands columns either side is a
+ * far smaller share of a 7680-wide eye than a row halo is of its 1920 rows (BASELINE config C4).  Feather / no-blend
+ * mappers split by rows only (OCTVR_ERR_UNSUPPORTED). */
+octvr_status octvr_mapper_create_window(const octvr_template* t, const int* in_sizes_wh, int n_in,
+                                        int blend, int enable_gain, int x0, int x1, int y0, int y1,
+                                        int device, octvr_mapper** out);
 /* void Mapper::stitch(std::vector<GpuMat>& inputs, GpuMat& output, GpuMat& preview, std::vector<double> gains)
  * mapper.cpp:193-323.  DEVICE pointers; asynchronous on `stream` (a cudaStream_t, NULL = default).
  * gains = NULL computes gains from this frame (when enabled); otherwise n_gains predefined gains

@@ -279,7 +279,7 @@ static bool build_fused(octvr_mapper& m, const octvr_template& t, const std::vec
 }
 
 static void build_mapper(octvr_mapper& m, const octvr_template& t, const int* in_sizes, int n_in,
-                         int blend, bool enable_gain, int scale_w, int scale_h, int band_y0, int band_y1)
+                         int blend, bool enable_gain, int scale_w, int scale_h, int band_y0, int band_y1, int band_x0 = 0, int band_x1 = 0)
 {
     InitTrace tr("build_mapper");
     const int n = (int)t.inputs.size();
@@ -298,6 +298,14 @@ static void build_mapper(octvr_mapper& m, const octvr_template& t, const int* in
     OB_CHECK(band_y0 >= 0 && band_y0 < band_y1 && band_y1 <= t.out_h, "row band must lie inside the output");
     OB_CHECK(band_y0 % 32 == 0 && (band_y1 % 32 == 0 || band_y1 == t.out_h), "row bands must be aligned to 32 output rows");
     m.band_y0 = band_y0; m.band_y1 = band_y1;
+    if (band_x0 == 0 && band_x1 == 0) band_x1 = t.out_w;
+    OB_CHECK(band_x0 >= 0 && band_x0 < band_x1 && band_x1 <= t.out_w, "column band must lie inside the output");
+    OB_CHECK(band_x0 % 32 == 0 && (band_x1 % 32 == 0 || band_x1 == t.out_w), "column bands must be aligned to 32 output columns");
+    if (band_x0 != 0 || band_x1 != t.out_w) {
+        if (n_ov > 0 || scaled) fail(OCTVR_ERR_UNSUPPORTED, "band mappers do not take overlays or scale_output");
+        if (blend <= 0 || n == 1) fail(OCTVR_ERR_UNSUPPORTED, "column bands are a multiband (blend > 0) partition; feather / no-blend mappers split by rows");
+    }
+    m.band_x0 = band_x0; m.band_x1 = band_x1;
     OB_CHECK(t.out_w % 2 == 0 && t.out_h % 2 == 0, "output size must be even (4:2:0)");
     for (int i = 0; i < n + n_ov; i++) {
         int w = in_sizes[2 * i], h = in_sizes[2 * i + 1];
@@ -939,6 +947,23 @@ octvr_status octvr_mapper_create_band(const octvr_template* t, const int* in_siz
         std::unique_ptr<octvr_mapper> m(new octvr_mapper);
         m->device = device;
         build_mapper(*m, *t, in_sizes_wh, n_in, blend, enable_gain != 0, 0, 0, band_y0, band_y1);
+        *out = m.release();
+    });
+}
+
+octvr_status octvr_mapper_create_window(const octvr_template* t, const int* in_sizes_wh, int n_in, int blend, int enable_gain,
+                                        int x0, int x1, int y0, int y1, int device, octvr_mapper** out)
+{
+    return guard([&] {
+        OB_CHECK(t && in_sizes_wh && out, "null argument");
+        int count = 0;
+        cudaError_t e = cudaGetDeviceCount(&count);
+        if (e != cudaSuccess || count <= 0 || device < 0 || device >= count)
+            fail(OCTVR_ERR_CUDA, "no usable CUDA device (the stitch path has no CPU fallback)");
+        OB_CUDA(cudaSetDevice(device));
+        std::unique_ptr<octvr_mapper> m(new octvr_mapper);
+        m->device = device;
+        build_mapper(*m, *t, in_sizes_wh, n_in, blend, enable_gain != 0, 0, 0, y0, y1, x0, x1);
         *out = m.release();
     });
 }

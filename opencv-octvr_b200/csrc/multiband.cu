@@ -73,6 +73,7 @@ struct MbParams {
     int rx, ry, rw, rh;               // final result roi in the output frame (dst_roi_final_); row-band mappers: the part inside the row window
     int out_w, out_h;
     int oy0, oy1;                     // output rows this mapper writes (row-band mode; default 0 .. out_h)
+    int ox0, ox1;                     // output columns this mapper writes (column-band mode; default 0 .. out_w)
     uint8_t* oy; uint8_t* ou; uint8_t* ov; uint32_t oy_pitch, ou_pitch, ov_pitch; int uv_step;
     uint8_t* rgb_out; uint32_t rgb_pitch;
 };
@@ -614,19 +615,19 @@ __global__ void __launch_bounds__(256) k_mb_collapse(const __grid_constant__ MbP
 //      black.  Saves the 8 B/px write + read of dst_0 and one launch. ----
 __global__ void __launch_bounds__(256, 4) k_mb_final(const __grid_constant__ MbParams p)
 {
-    const int X0 = (blockIdx.x * 32 + threadIdx.x) * 4, Y = p.oy0 + blockIdx.y * 8 + threadIdx.y;
+    const int X0 = p.ox0 + (blockIdx.x * 32 + threadIdx.x) * 4, Y = p.oy0 + blockIdx.y * 8 + threadIdx.y;
     // cameras with a non-zero level-0 weight somewhere under this CTA (128 x 8 output pixels = up to 5 x 2 weight tiles)
     unsigned cams = 0;
     {
         const int tiles_x = (p.lw[0] + 31) / 32, tiles_y = (p.lh[0] + 7) / 8;
-        const int xs = (int)blockIdx.x * 128 - p.rx, ys = p.oy0 + (int)blockIdx.y * 8 - p.ry;
+        const int xs = p.ox0 + (int)blockIdx.x * 128 - p.rx, ys = p.oy0 + (int)blockIdx.y * 8 - p.ry;
         const int tx0 = max(xs, 0) >> 5, tx1 = min((xs + 127) >> 5, tiles_x - 1);
         const int ty0 = max(ys, 0) >> 3, ty1 = min((ys + 7) >> 3, tiles_y - 1);
-        if (xs + 127 >= 0 && ys + 7 >= 0)
+        if (xs + 127 >= 0 && ys + 7 >= 0 && tiles_x > 0 && tiles_y > 0)
             for (int ty = ty0; ty <= ty1; ty++)
                 for (int tx = tx0; tx <= tx1; tx++) cams |= __ldg(p.tile_cams + p.off_t[0] + (size_t)ty * tiles_x + tx);
     }
-    if (X0 >= p.out_w || Y >= p.oy1) return;
+    if (X0 >= p.ox1 || Y >= p.oy1) return;
     int R[4], G[4], B[4];
     #pragma unroll
     for (int q = 0; q < 4; q++) R[q] = G[q] = B[q] = 0;
@@ -683,21 +684,21 @@ __global__ void __launch_bounds__(256, 4) k_mb_final(const __grid_constant__ MbP
             }
         }
     }
-    const bool full = X0 + 3 < p.out_w;
+    const bool full = X0 + 3 < p.ox1;
     if (p.rgb_out) {
         uint8_t* o = p.rgb_out + (size_t)Y * p.rgb_pitch + 3 * X0;
         #pragma unroll
-        for (int q = 0; q < 4; q++) if (X0 + q < p.out_w) { o[3 * q] = (uint8_t)R[q]; o[3 * q + 1] = (uint8_t)G[q]; o[3 * q + 2] = (uint8_t)B[q]; }
+        for (int q = 0; q < 4; q++) if (X0 + q < p.ox1) { o[3 * q] = (uint8_t)R[q]; o[3 * q + 1] = (uint8_t)G[q]; o[3 * q + 2] = (uint8_t)B[q]; }
     }
     if (p.oy) {
         uint8_t* oyp = p.oy + (size_t)Y * p.oy_pitch + X0;
         const uint32_t l4 = rgb_luma(R[0], G[0], B[0]) | (rgb_luma(R[1], G[1], B[1]) << 8) | (rgb_luma(R[2], G[2], B[2]) << 16) | (rgb_luma(R[3], G[3], B[3]) << 24);
         if (full && (((uintptr_t)oyp) & 3) == 0) *reinterpret_cast<uint32_t*>(oyp) = l4;
-        else for (int q = 0; q < 4 && X0 + q < p.out_w; q++) oyp[q] = (uint8_t)(l4 >> (8 * q));
+        else for (int q = 0; q < 4 && X0 + q < p.ox1; q++) oyp[q] = (uint8_t)(l4 >> (8 * q));
         if ((Y & 1) == 0) {                                            // X0 is even: chroma from pixels 0 and 2 of the group
             #pragma unroll
             for (int q = 0; q < 4; q += 2) {
-                if (X0 + q >= p.out_w) break;
+                if (X0 + q >= p.ox1) break;
                 const size_t co = (size_t)((X0 + q) >> 1) * p.uv_step;
                 p.ou[(size_t)(Y >> 1) * p.ou_pitch + co] = (uint8_t)rgb_cb(R[q], G[q], B[q]);
                 p.ov[(size_t)(Y >> 1) * p.ov_pitch + co] = (uint8_t)rgb_cr(R[q], G[q], B[q]);
@@ -763,20 +764,28 @@ Multiband* multiband_create(octvr_mapper& m, const octvr_template& t,
     // Laplacian levels (pyrUp reads one coarser row either side) and r_l = 2 r_{l+1} + 2 rows of the collapsed levels, i.e.
     // 2^(bands+2) - 2 rows at level 0; a halo of 4 * 2^bands rows therefore leaves the band itself bit-identical to the
     // full-frame result.  Weights are computed on the full rectangles and cropped, so they are exact everywhere.
-    int E0 = 0, E1 = PH;
-    if (m.band_y0 != 0 || m.band_y1 != t.out_h) {
+    // A column-band mapper does the same with a column window [F0, F1): for frames wider than tall (C4's 7680 x 1920 eyes)
+    // the halos of column bands are a much smaller share of the work than those of row bands.
+    int E0 = 0, E1 = PH, F0 = 0, F1 = PW;
+    {
         const int halo = 4 * al;
         auto fl = [&](int v) { return v >= 0 ? v / al * al : -((-v + al - 1) / al * al); };
-        E0 = std::min(PH, std::max(0, fl(m.band_y0 - Rf.y - halo)));
-        E1 = std::min(PH, std::max(0, fl(m.band_y1 - Rf.y + halo + al - 1)));
-        if (E1 <= E0) E0 = E1 = 0;
+        if (m.band_y0 != 0 || m.band_y1 != t.out_h) {
+            E0 = std::min(PH, std::max(0, fl(m.band_y0 - Rf.y - halo)));
+            E1 = std::min(PH, std::max(0, fl(m.band_y1 - Rf.y + halo + al - 1)));
+        }
+        if (m.band_x0 != 0 || m.band_x1 != t.out_w) {
+            F0 = std::min(PW, std::max(0, fl(m.band_x0 - Rf.x - halo)));
+            F1 = std::min(PW, std::max(0, fl(m.band_x1 - Rf.x + halo + al - 1)));
+        }
+        if (E1 <= E0 || F1 <= F0) { E0 = E1 = 0; F0 = F1 = 0; }
     }
-    const int WH = E1 - E0;
-    p.rx = Rf.x; p.ry = Rf.y + E0; p.rw = Rf.w; p.rh = std::min(Rf.h, E1) - E0; p.out_w = t.out_w; p.out_h = t.out_h;
-    p.oy0 = m.band_y0; p.oy1 = m.band_y1;
+    const int WH = E1 - E0, WW = F1 - F0;
+    p.rx = Rf.x + F0; p.ry = Rf.y + E0; p.rw = std::max(0, std::min(Rf.w, F1) - F0); p.rh = std::max(0, std::min(Rf.h, E1) - E0); p.out_w = t.out_w; p.out_h = t.out_h;
+    p.oy0 = m.band_y0; p.oy1 = m.band_y1; p.ox0 = m.band_x0; p.ox1 = m.band_x1;
     size_t doff = 0;
     for (int l = 0; l <= nb; l++) {
-        p.lw[l] = l == 0 ? PW : (p.lw[l - 1] + 1) / 2; p.lh[l] = l == 0 ? WH : (p.lh[l - 1] + 1) / 2;
+        p.lw[l] = l == 0 ? WW : (p.lw[l - 1] + 1) / 2; p.lh[l] = l == 0 ? WH : (p.lh[l - 1] + 1) / 2;
         p.off_d[l] = doff; doff += (size_t)p.lw[l] * p.lh[l];
     }
     std::vector<float> dstw(doff, 0.f);
@@ -801,7 +810,7 @@ Multiband* multiband_create(octvr_mapper& m, const octvr_template& t,
 
     // ---- phase 0 (sequential, cheap): geometry of every camera rectangle, offsets into the shared arrays ----
     struct CamBuild {
-        int top = 0, left = 0, width = 0, height = 0, ys = 0, ye = 0, ch = 0;
+        int top = 0, left = 0, width = 0, height = 0, ys = 0, ye = 0, ch = 0, xs = 0, xe = 0, cw = 0;
         std::vector<MbWarpJob> jobs; std::vector<uint32_t> entries; std::vector<uint64_t> keys;   // job.tmap = index into keys
         std::vector<uint2> chunks;
         std::vector<Img<float>> wl;                         // weight pyramid of the full rectangle, levels 0 .. nb
@@ -825,14 +834,17 @@ Multiband* multiband_create(octvr_mapper& m, const octvr_template& t,
         CamBuild& b = cb[i];
         b.top = in.roi.y - tny; b.left = in.roi.x - tnx; b.width = width; b.height = height;
         // rows [ys, ye) of the full rectangle fall inside the row window (all of it without row bands)
-        const int fy0 = tny - Rf.y;
+        // and columns [xs, xe) inside the column window
+        const int fy0 = tny - Rf.y, fx0 = tnx - Rf.x;
         b.ys = std::min(height, std::max(0, E0 - fy0)); b.ye = std::max(b.ys, std::min(height, E1 - fy0));
-        b.ch = b.ye - b.ys;
-        c.x0 = tnx - Rf.x; c.y0 = fy0 + b.ys - E0; c.bw = width; c.bh = b.ch;
-        if (b.ch > 0) { mb->max_bw = std::max(mb->max_bw, width); mb->max_bh = std::max(mb->max_bh, b.ch); }
-        c.off_g[0] = g0_total; g0_total += (size_t)width * b.ch;
+        b.xs = std::min(width, std::max(0, F0 - fx0)); b.xe = std::max(b.xs, std::min(width, F1 - fx0));
+        if (b.xe == b.xs) { b.ye = b.ys; b.xs = 0; b.xe = width; }      // nothing of this camera in the window: same state as an empty row range
+        b.ch = b.ye - b.ys; b.cw = b.xe - b.xs;
+        c.x0 = fx0 + b.xs - F0; c.y0 = fy0 + b.ys - E0; c.bw = b.cw; c.bh = b.ch;
+        if (b.ch > 0) { mb->max_bw = std::max(mb->max_bw, b.cw); mb->max_bh = std::max(mb->max_bh, b.ch); }
+        c.off_g[0] = g0_total; g0_total += (size_t)b.cw * b.ch;
         // every level starts at an even element: 16-byte aligned rows for the vector loads of mb_down_strip_p16
-        for (int l = 1; l <= nb; l++) { c.off_g[l] = g_total; g_total += (size_t)(width >> l) * (b.ch >> l); g_total += g_total & 1; }
+        for (int l = 1; l <= nb; l++) { c.off_g[l] = g_total; g_total += (size_t)(b.cw >> l) * (b.ch >> l); g_total += g_total & 1; }
     }
     coords.resize(g0_total);
 
@@ -842,22 +854,22 @@ Multiband* multiband_create(octvr_mapper& m, const octvr_template& t,
     auto build_cam = [&](int i) {
         const TInput& in = t.inputs[i];
         CamBuild& b = cb[i];
-        const int width = b.width, height = b.height, ys = b.ys, ye = b.ye, ch = b.ch, top = b.top, left = b.left;
+        const int width = b.width, height = b.height, ys = b.ys, ye = b.ye, ch = b.ch, top = b.top, left = b.left, xs = b.xs, xe = b.xe, cw = b.cw;
         Img<float> wmap(width, height, 0.f);
         const float inv255 = (float)(1. / 255.);
         uint2* ce = coords.data() + p.cam[i].off_g[0];
         std::vector<int16_t> qx, qy;                            // integer tap position of every valid pixel (staged warp)
-        if (want_staged) { qx.assign((size_t)width * ch, 0); qy.assign((size_t)width * ch, 0); }
+        if (want_staged) { qx.assign((size_t)cw * ch, 0); qy.assign((size_t)cw * ch, 0); }
         for (int y = 0; y < height; y++) {
             const int ly = mirror(y - top, in.roi.h);
             const bool in_y = y - top >= 0 && y - top < in.roi.h;
-            const bool in_win = y >= ys && y < ye;
-            if (!in_win && !in_y) continue;
+            const bool in_rows = y >= ys && y < ye;
+            if (!in_rows && !in_y) continue;
             for (int x = 0; x < width; x++) {
                 const int lx = mirror(x - left, in.roi.w);
-                if (in_win) {
+                if (in_rows && x >= xs && x < xe) {
                     const int32_t fsx = sx[i].row(ly)[lx], fsy = sy[i].row(ly)[lx];
-                    const size_t at = (size_t)(y - ys) * width + x;
+                    const size_t at = (size_t)(y - ys) * cw + (x - xs);
                     ce[at] = mk_entry(fsx, fsy, m.in_w[i], m.in_h[i], in.mask.row(ly)[lx] != 0);
                     if (ce[at].y & C_VALID) { b.src_lo = std::min(b.src_lo, fsy >> 5); b.src_hi = std::max(b.src_hi, (fsy >> 5) + 1); }
                     if (want_staged) { qx[at] = (int16_t)std::min(32767, std::max(-32768, fsx >> 5)); qy[at] = (int16_t)std::min(32767, std::max(-32768, fsy >> 5)); }
@@ -868,11 +880,11 @@ Multiband* multiband_create(octvr_mapper& m, const octvr_template& t,
         // staged warp: one job per 32 x 16 tile of the rectangle that has a valid pixel
         std::map<uint64_t, int> local_keys;
         for (int ty = 0; want_staged && b.staged_ok && ty < (ch + TILE_H - 1) / TILE_H; ty++)
-            for (int tx = 0; b.staged_ok && tx < (width + TILE_W - 1) / TILE_W; tx++) {
+            for (int tx = 0; b.staged_ok && tx < (cw + TILE_W - 1) / TILE_W; tx++) {
                 int xmin = INT32_MAX, xmax = INT32_MIN, ymin = INT32_MAX, ymax = INT32_MIN;
                 for (int py = ty * TILE_H; py < std::min(ch, (ty + 1) * TILE_H); py++)
-                    for (int px = tx * TILE_W; px < std::min(width, (tx + 1) * TILE_W); px++) {
-                        const size_t at = (size_t)py * width + px;
+                    for (int px = tx * TILE_W; px < std::min(cw, (tx + 1) * TILE_W); px++) {
+                        const size_t at = (size_t)py * cw + px;
                         if (!(ce[at].y & C_VALID)) continue;
                         xmin = std::min(xmin, (int)qx[at]); xmax = std::max(xmax, qx[at] + 1); ymin = std::min(ymin, (int)qy[at]); ymax = std::max(ymax, qy[at] + 1);
                     }
@@ -892,8 +904,8 @@ Multiband* multiband_create(octvr_mapper& m, const octvr_template& t,
                 const size_t e0 = b.entries.size();
                 b.entries.resize(e0 + TILE_PX, 0u);
                 for (int py = ty * TILE_H; py < std::min(ch, (ty + 1) * TILE_H); py++)
-                    for (int px = tx * TILE_W; px < std::min(width, (tx + 1) * TILE_W); px++) {
-                        const size_t at = (size_t)py * width + px;
+                    for (int px = tx * TILE_W; px < std::min(cw, (tx + 1) * TILE_W); px++) {
+                        const size_t at = (size_t)py * cw + px;
                         if (!(ce[at].y & C_VALID)) continue;
                         const uint32_t off = (uint32_t)((qy[at] - job.by0) * bw + (qx[at] - job.bx0));
                         b.entries[e0 + (size_t)(py - ty * TILE_H) * TILE_W + (px - tx * TILE_W)] =
@@ -901,9 +913,9 @@ Multiband* multiband_create(octvr_mapper& m, const octvr_template& t,
                     }
                 b.jobs.push_back(job);
             }
-        for (size_t k = 0; k < ((size_t)width * ch + 255) / 256; k++) {
+        for (size_t k = 0; k < ((size_t)cw * ch + 255) / 256; k++) {
             bool any = false;
-            for (size_t e = k * 256; e < std::min((k + 1) * 256, (size_t)width * ch) && !any; e++) any = (ce[e].y & C_VALID) != 0;
+            for (size_t e = k * 256; e < std::min((k + 1) * 256, (size_t)cw * ch) && !any; e++) any = (ce[e].y & C_VALID) != 0;
             if (any) b.chunks.push_back(make_uint2((uint32_t)i, (uint32_t)k));
         }
         while (b.chunks.size() % MB_WARP_CHUNKS) b.chunks.push_back(make_uint2((uint32_t)i, 0xFFFFFFFFu));   // a CTA's chunks share a camera
@@ -925,7 +937,7 @@ Multiband* multiband_create(octvr_mapper& m, const octvr_template& t,
     for (int i = 0; i < n; i++) {
         CamBuild& b = cb[i];
         MbCam& c = p.cam[i];
-        if (m.band_y0 != 0 || m.band_y1 != t.out_h) {          // row-band mapper: only these source rows need converting
+        if (m.band_y0 != 0 || m.band_y1 != t.out_h || m.band_x0 != 0 || m.band_x1 != t.out_w) {   // band mapper: only these source rows need converting
             if (b.src_lo > b.src_hi) m.src_row0[i] = m.src_row1[i] = 0;
             else { m.src_row0[i] = std::max(0, b.src_lo) & ~1; m.src_row1[i] = std::min(m.in_h[i], b.src_hi + 1); }
         }
@@ -945,8 +957,8 @@ Multiband* multiband_create(octvr_mapper& m, const octvr_template& t,
         chunks.insert(chunks.end(), b.chunks.begin(), b.chunks.end());
         for (int l = 0; l <= nb; l++) {
             c.off_w[l] = wts.size();
-            const int r0 = b.ys >> l, r1 = b.ye >> l;               // the window's rows of the full level-l weight map
-            wts.insert(wts.end(), b.wl[l].d.begin() + (size_t)r0 * b.wl[l].w, b.wl[l].d.begin() + (size_t)r1 * b.wl[l].w);
+            const int r0 = b.ys >> l, r1 = b.ye >> l, c0 = b.xs >> l, c1 = b.xe >> l;      // the window's part of the full level-l weight map
+            for (int r = r0; r < r1; r++) wts.insert(wts.end(), b.wl[l].row(r) + c0, b.wl[l].row(r) + c1);
         }
     }
     if (!staged) { wjobs.clear(); wentries.clear(); tmap_index.clear(); }
@@ -962,13 +974,13 @@ Multiband* multiband_create(octvr_mapper& m, const octvr_template& t,
                 for (int i = 0; i < n; i++) {
                     const CamBuild& b = cb[i];
                     const MbCam& c = p.cam[i];
-                    const int xt = c.x0 >> l, yt = c.y0 >> l, r0 = b.ys >> l, r1 = b.ye >> l;
+                    const int xt = c.x0 >> l, yt = c.y0 >> l, r0 = b.ys >> l, r1 = b.ye >> l, c0 = b.xs >> l, c1 = b.xe >> l;
                     const Img<float>& wl = b.wl[l];
                     for (int y = std::max(0, g0 - yt); y < std::min(r1 - r0, g1 - yt); y++) {
                         float* dr = dstw.data() + p.off_d[l] + (size_t)(yt + y) * p.lw[l] + xt;
-                        const float* wr = wl.row(r0 + y);
+                        const float* wr = wl.row(r0 + y) + c0;
                         uint16_t* tc = tile_cams.data() + p.off_t[l] + (size_t)((yt + y) / 8) * ((p.lw[l] + 31) / 32);
-                        for (int x = 0; x < wl.w; x++) {
+                        for (int x = 0; x < c1 - c0; x++) {
                             dr[x] += wr[x];
                             if (wr[x] != 0.f) tc[(xt + x) / 32] |= (uint16_t)(1u << i);
                         }
@@ -1050,7 +1062,7 @@ void multiband_stitch(octvr_mapper& m, const octvr_frame* out, cudaStream_t s)
         if (mb.n_wsmall) k_mb_warp_staged<128, MB_STAGE_SMALL><<<mb.n_wsmall, 128, 0, s>>>(p, 0u);
         if (mb.n_wjobs > mb.n_wsmall) k_mb_warp_staged<256, MB_STAGE><<<mb.n_wjobs - mb.n_wsmall, 256, 0, s>>>(p, mb.n_wsmall);
     } else if (mb.n_chunks) k_mb_warp<<<mb.n_chunks / MB_WARP_CHUNKS, 256, 0, s>>>(p);
-    if (p.lh[0] > 0 && mb.max_bh > 0) {                    // an empty row window (a band outside the result roi) only writes black
+    if (p.lh[0] > 0 && p.lw[0] > 0 && mb.max_bh > 0) {     // an empty window (a band outside the result roi) only writes black
         for (int l = 0; l < nb; l++) {
             const dim3 grid(((mb.max_bw >> (l + 1)) + 31) / 32, ((mb.max_bh >> (l + 1)) + 31) / 32, n);
             if (l == 0) k_mb_down<true><<<grid, dim3(32, 8), 0, s>>>(p, l);
@@ -1061,7 +1073,7 @@ void multiband_stitch(octvr_mapper& m, const octvr_frame* out, cudaStream_t s)
         for (int l = nb; l >= 2; l--)
             k_mb_collapse<<<dim3((p.lw[l - 1] + 127) / 128, (p.lh[l - 1] + 7) / 8), dim3(32, 8), 0, s>>>(p, l);
     }
-    k_mb_final<<<dim3((p.out_w + 127) / 128, (p.oy1 - p.oy0 + 7) / 8), dim3(32, 8), 0, s>>>(p);
+    k_mb_final<<<dim3((p.ox1 - p.ox0 + 127) / 128, (p.oy1 - p.oy0 + 7) / 8), dim3(32, 8), 0, s>>>(p);
 }
 
 int multiband_launches(const octvr_mapper& m) { return m.mb ? m.mb->launches : 0; }

@@ -182,9 +182,10 @@ class PackedRGB:
 class Mapper:
     """vr::Mapper (mapper.hpp:29-95).  blend > 0 multiband, < 0 feather border, 0 none."""
 
-    def __init__(self, tmpl, in_sizes, blend=128, enable_gain_compensator=True, scale_output=(0, 0), device=0, band=None):
+    def __init__(self, tmpl, in_sizes, blend=128, enable_gain_compensator=True, scale_output=(0, 0), device=0, band=None, cols=None):
         """band=(y0, y1): row-band mapper (multi-GPU partition of one frame, sharding.RowBandStitcher): only output rows
-        [y0, y1) are produced; frames passed to stitch() stay full size."""
+        [y0, y1) are produced; frames passed to stitch() stay full size.  cols=(x0, x1): the same for output columns
+        (multiband only)."""
         import torch
         self._torch = torch
         self.tmpl = tmpl
@@ -193,7 +194,13 @@ class Mapper:
         self.in_sizes = [tuple(s) for s in in_sizes]
         sz = np.ascontiguousarray(np.array(self.in_sizes, np.int32).reshape(-1, 2))
         h = C.c_void_p()
-        if band is None:
+        self.cols = cols
+        if cols is not None:
+            y0, y1 = band if band is not None else (0, 0)
+            check(lib().octvr_mapper_create_window(tmpl._h, sz.ctypes.data_as(C.c_void_p), len(self.in_sizes), int(blend),
+                                                   int(bool(enable_gain_compensator)), int(cols[0]), int(cols[1]), int(y0), int(y1),
+                                                   int(device), C.byref(h)))
+        elif band is None:
             check(lib().octvr_mapper_create(tmpl._h, sz.ctypes.data_as(C.c_void_p), len(self.in_sizes), int(blend),
                                             int(bool(enable_gain_compensator)), int(scale_output[0]), int(scale_output[1]),
                                             int(device), C.byref(h)))

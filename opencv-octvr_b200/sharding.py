@@ -220,7 +220,11 @@ class StereoRowBandStitcher:
     """Two eye templates of equal size -> one top-bottom frame, partitioned over the ranks by (eye, row band).
     Every rank constructs it with the same templates; stitch() is collective (input broadcast, band collection)."""
 
-    def __init__(self, vr, tmpls, in_sizes, blend, enable_gain, device, align=32, rank=None, world=None):
+    def __init__(self, vr, tmpls, in_sizes, blend, enable_gain, device, align=32, rank=None, world=None, split="auto"):
+        """split: how an eye is cut when several ranks share it -- "rows" (bands of output rows), "cols" (bands of output
+        columns; multiband only) or "auto": columns for multiband eyes that are wider than tall, because every band carries
+        a halo of 4 * 2^bands pixels either side of the cut (C4, 8 GPUs: 480 + 2 * 128 of 1920 rows = 1.53 x the work, but
+        1920 + 2 * 128 of 7680 columns = 1.13 x)."""
         assert len(tmpls) == 2 and tuple(tmpls[0].out_size) == tuple(tmpls[1].out_size)
         self.vr = vr
         self.rank = rank if rank is not None else (dist.get_rank() if dist.is_initialized() else 0)
@@ -228,12 +232,20 @@ class StereoRowBandStitcher:
         self.eye_w, self.eye_h = tmpls[0].out_size
         self.align = align
         self.in_sizes = [tuple(s) for s in in_sizes]
+        if split == "auto":
+            split = os.environ.get("OCTVR_C4_SPLIT", "cols" if blend > 0 and self.eye_w > self.eye_h else "rows")
+        assert split in ("rows", "cols")
+        self.split = split
         self.jobs = []
         for eye, b, per in stereo_assignment(self.world)[self.rank]:
-            band = row_bands(self.eye_h, per, align)[b]
+            band, cols = (0, self.eye_h), None
+            if per > 1 and split == "rows":
+                band = row_bands(self.eye_h, per, align)[b]
+            elif per > 1:
+                cols = row_bands(self.eye_w, per, align)[b]
             m = vr.Mapper(tmpls[eye], in_sizes, blend=blend, enable_gain_compensator=enable_gain, device=device,
-                          band=None if per == 1 else band)
-            self.jobs.append((eye, band, m))
+                          band=None if (per == 1 or cols is not None) else band, cols=cols)
+            self.jobs.append((eye, band if cols is None else ("cols",) + tuple(cols), m))
 
     def stitch_local(self, frames_packed, out_packed, stream=None):
         """This rank's share: frames in Mapper's packed layout, out_packed the full top-bottom frame (W x 1.5 * 2 * eye_h)."""
@@ -246,6 +258,8 @@ class StereoRowBandStitcher:
 
     def shares(self):
         """Row ranges of the packed top-bottom frame produced by every rank (for collect_shares)."""
+        if self.split != "rows" and self.world > 2:
+            raise NotImplementedError("column bands are stored straight into the collecting rank's frame (PeerFrame); there is no send / recv collection for them")
         He, H = self.eye_h, 2 * self.eye_h
         out = []
         for jobs in stereo_assignment(self.world):
