@@ -813,9 +813,14 @@ def e2e_once(vr, util, tmpl, cfg, in_size, blend, gain, device, steps, world, pi
 
 
 def cpu_baseline(workload, budget_s=20.0, steps=None, warmup=1):
-    """The reference's CPU path (oracle port: oracle/liborc.so, OpenMP on all host cores) on the same workload."""
+    """The reference's CPU path on the same workload, on every host core.  kind "reference": oracle/_ref/libocvref.so, the
+    UNMODIFIED reference CPU build (SURVEY.md Appendix A) behind oracle/refgen/ref_arm.cpp -- cv::cvtColor / cv::remap /
+    GainCompensator / the octvr feather recipe or MultiBandBlender / cv::cvtColor, compiled from the reference's sources; kind
+    "port": the C restatement oracle/liborc.so (OpenMP), used when the reference build did not travel (OCTVR_CPU_ARM=port
+    forces it)."""
     sys.path.insert(0, os.path.join(ROOT, "oracle"))
     import oracle as O
+    import refarm
     import util
     rig, blend, gain, desc = WORKLOADS[workload]
     if not isinstance(rig, str):
@@ -828,15 +833,33 @@ def cpu_baseline(workload, budget_s=20.0, steps=None, warmup=1):
     except Exception:                     # noqa: BLE001
         pass
     ot = O.build_template(cfg, width)
-    so = O.StitchOracle(ot, [in_size] * n, blend=blend, enable_gain=gain)
-    frames = [util.i420_planes(util.noise_frame(c, iw, ih), iw, ih) for c in range(n)]
+    use_ref = refarm.available() and os.environ.get("OCTVR_CPU_ARM", "reference") != "port"
+    if use_ref:
+        import tempfile
+        with tempfile.TemporaryDirectory() as td:
+            dat = os.path.join(td, "t.dat")
+            O.dump_dat(ot, dat)           # "VRv11" file, byte-identical to the reference tool's (tests/test_oracle_golden.py)
+            arm = refarm.RefArm(dat, in_size, blend, gain)
+        full = [util.noise_frame(c, iw, ih) for c in range(n)]
+        run = lambda: arm.stitch(full)
+        cores, kind = arm.threads(), "reference"
+        note = ("reference CPU path = the unmodified reference CPU build (static libs compiled from the reference's own sources, SURVEY.md "
+                "Appendix A) behind oracle/refgen/ref_arm.cpp: cvtColor -> remap -> GainCompensator -> feather / MultiBandBlender -> cvtColor, "
+                "OpenCV's pthreads parallel_for_ + one thread per camera; built by oracle/build_ref.sh into oracle/_ref/")
+    else:
+        so = O.StitchOracle(ot, [in_size] * n, blend=blend, enable_gain=gain)
+        frames = [util.i420_planes(util.noise_frame(c, iw, ih), iw, ih) for c in range(n)]
+        run = lambda: so.stitch(frames)
+        cores, kind = O.num_threads(), "port"
+        note = ("reference CPU path = the C restatement under oracle/ (OpenMP over all host cores), pinned bit-exact against the unmodified "
+                "reference build; oracle/_ref/libocvref.so (the reference build itself, oracle/build_ref.sh) was not available on this box")
     for _ in range(warmup):
-        so.stitch(frames)
+        run()
     times = []
     t_start = time.perf_counter()
     while True:
         t0 = time.perf_counter()
-        so.stitch(frames)
+        run()
         times.append(time.perf_counter() - t0)
         if steps is not None and (len(times) >= steps or time.perf_counter() - t_start > budget_s):
             break
@@ -844,12 +867,10 @@ def cpu_baseline(workload, budget_s=20.0, steps=None, warmup=1):
             break
     W, H = ot.out_size
     med = statistics.median(times)
-    return {"value": round(W * H / med / 1e6, 2), "unit": "Mpix/s", "cores": O.num_threads(), "kind": "port",
+    return {"value": round(W * H / med / 1e6, 2), "unit": "Mpix/s", "cores": cores, "kind": kind,
             "frames_per_s": round(1.0 / med, 3), "ms_per_frame": round(med * 1e3, 1), "steps_timed": len(times),
             "sample": "%d full frames of %s (median), after %d warm-up" % (len(times), desc, warmup),
-            "note": "reference CPU path = the C restatement under oracle/ (OpenMP over all host cores), pinned bit-exact against the unmodified "
-                    "reference build; the reference itself builds only through its CMake tree (SURVEY.md Appendix A), which the allowed "
-                    "recipe excludes, so there is no oracle/_ref binary"}
+            "note": note}
 
 
 def run_reference(args):

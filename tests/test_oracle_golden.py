@@ -270,3 +270,28 @@ def test_fast_mapper_oracle_vs_reference_fixture(rig):
         out = fo.stitch_nv12([O.fast_noise_frame(i, iw, ih) for i in range(n)])
     assert np.array_equal(fo.last_acc0, g["acc_c0"])
     assert np.array_equal(out, g["result"])
+
+
+@pytest.mark.parametrize("blend,gain", [(-5, True), (16, True), (0, False)])
+def test_reference_cpu_arm_equals_the_oracle(blend, gain, tmp_path):
+    """oracle/_ref/libocvref.so (the unmodified reference CPU build behind oracle/refgen/ref_arm.cpp; bench.py's reference arm)
+    composes the same frame as the oracle, byte for byte, gains to 1e-12.  Skipped where the reference build is absent."""
+    import refarm
+    import sys
+    sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+    import util
+    if not refarm.available():
+        pytest.skip("oracle/_ref/libocvref.so not built (needs the reference CPU build, oracle/build_ref.sh)")
+    ot = util.template_from_gold(O, "rig3")
+    for d in ot.inputs:
+        d["vignette"] = None
+    dat = str(tmp_path / "t.dat")
+    O.dump_dat(ot, dat)
+    arm = refarm.RefArm(dat, (320, 240), blend, gain)
+    frames = [util.noise_frame(i, 320, 240) for i in range(3)]
+    (y, u, v), g = arm.stitch(frames)
+    so = O.StitchOracle(ot, [(320, 240)] * 3, blend=blend, enable_gain=gain)
+    ry, ru, rv = so.stitch([util.i420_planes(f, 320, 240) for f in frames])
+    assert np.array_equal(y, ry) and np.array_equal(u, ru) and np.array_equal(v, rv)
+    if gain:
+        assert np.allclose(g, so.last_gains, rtol=1e-12)
