@@ -87,6 +87,8 @@ struct Multiband {
     short4* d_dst = nullptr; float* d_dstw = nullptr; int* d_wide = nullptr; bool force_wide = false;
     int max_bw = 0, max_bh = 0;
     int launches = 0;
+    // the small-level chain (down 2.., band 2.., collapse ..3) runs on a side stream next to the level-1 band
+    cudaStream_t side = nullptr; cudaEvent_t ev_fork = nullptr, ev_join = nullptr; bool fork = false;
 };
 
 // ------------------------------------------------------------------------------------------------ device
@@ -527,9 +529,9 @@ template <bool L0> __global__ void __launch_bounds__(256) k_mb_down(const __grid
 // ---- k_mb_band: one thread per FOUR horizontally adjacent pixels of destination level l (CTA = 128 x 8 pixels) ----
 //      Levels do not depend on each other, so one launch covers all of them (blockIdx.z + 1 = level): the small levels,
 //      latency-bound on their own (15 us each for a few thousand pixels), hide under level 1.
-__global__ void __launch_bounds__(256, 4) k_mb_band(const __grid_constant__ MbParams p)
+__global__ void __launch_bounds__(256, 4) k_mb_band(const __grid_constant__ MbParams p, const int first_level)
 {
-    const int l = (int)blockIdx.z + 1;
+    const int l = (int)blockIdx.z + first_level;
     const int X0 = (blockIdx.x * 32 + threadIdx.x) * 4, Y = blockIdx.y * 8 + threadIdx.y;
     const int lw = p.lw[l], lh = p.lh[l];
     if ((int)blockIdx.x * 128 >= lw || (int)blockIdx.y * 8 >= lh) return;
@@ -1039,10 +1041,21 @@ Multiband* multiband_create(octvr_mapper& m, const octvr_template& t,
         OB_CUDA(cudaMemcpy(mb->d_wide, init.data(), init.size() * sizeof(int), cudaMemcpyHostToDevice));
     }
     p.wide = mb->d_wide; p.clear_wide = mb->force_wide ? 0 : 1;
+    {   // side stream for the small-level chain (OCTVR_MB_FORK=0: everything on the caller's stream)
+        const char* e = getenv("OCTVR_MB_FORK");
+        mb->fork = !(e && atoi(e) == 0);
+        if (mb->fork) {
+            int lo = 0, hi = 0;
+            OB_CUDA(cudaDeviceGetStreamPriorityRange(&lo, &hi));
+            OB_CUDA(cudaStreamCreateWithPriority(&mb->side, cudaStreamNonBlocking, hi));
+            OB_CUDA(cudaEventCreateWithFlags(&mb->ev_fork, cudaEventDisableTiming));
+            OB_CUDA(cudaEventCreateWithFlags(&mb->ev_join, cudaEventDisableTiming));
+        }
+    }
     p.coords = mb->d_coords; p.g0 = mb->d_g0; p.g = mb->d_g; p.w = mb->d_w; p.dst = mb->d_dst; p.dstw = mb->d_dstw;
     for (int i = 0; i < n; i++) { p.rgbx[i] = m.d_rgbx[i]; p.src_pitch[i] = m.in_w[i]; }
     m.table_bytes = (int64_t)(coords.size() * sizeof(uint2) + wentries.size() * 4 + wjobs.size() * sizeof(MbWarpJob) + wts.size() * 4 + dstw.size() * 4);
-    mb->launches = (mb->n_wjobs ? (mb->n_wsmall ? 1 : 0) + (mb->n_wjobs > mb->n_wsmall ? 1 : 0) : 1) + nb + (nb >= 1 ? 1 : 0) + std::max(0, nb - 1) + 1;
+    mb->launches = (mb->n_wjobs ? (mb->n_wsmall ? 1 : 0) + (mb->n_wjobs > mb->n_wsmall ? 1 : 0) : 1) + nb + (nb >= 1 ? 1 : 0) + (mb->fork && nb >= 3 ? 1 : 0) + std::max(0, nb - 1) + 1;
     return mb.release();
 }
 
@@ -1063,15 +1076,36 @@ void multiband_stitch(octvr_mapper& m, const octvr_frame* out, cudaStream_t s)
         if (mb.n_wjobs > mb.n_wsmall) k_mb_warp_staged<256, MB_STAGE><<<mb.n_wjobs - mb.n_wsmall, 256, 0, s>>>(p, mb.n_wsmall);
     } else if (mb.n_chunks) k_mb_warp<<<mb.n_chunks / MB_WARP_CHUNKS, 256, 0, s>>>(p);
     if (p.lh[0] > 0 && p.lw[0] > 0 && mb.max_bh > 0) {     // an empty window (a band outside the result roi) only writes black
-        for (int l = 0; l < nb; l++) {
+        auto down = [&](int l, cudaStream_t st) {
             const dim3 grid(((mb.max_bw >> (l + 1)) + 31) / 32, ((mb.max_bh >> (l + 1)) + 31) / 32, n);
-            if (l == 0) k_mb_down<true><<<grid, dim3(32, 8), 0, s>>>(p, l);
-            else k_mb_down<false><<<grid, dim3(32, 8), 0, s>>>(p, l);
+            if (l == 0) k_mb_down<true><<<grid, dim3(32, 8), 0, st>>>(p, l);
+            else k_mb_down<false><<<grid, dim3(32, 8), 0, st>>>(p, l);
+        };
+        auto band = [&](int l0, int l1, cudaStream_t st) {      // destination levels l0 .. l1 in one launch (level 0 is computed inside k_mb_final)
+            k_mb_band<<<dim3((p.lw[l0] + 127) / 128, (p.lh[l0] + 7) / 8, l1 - l0 + 1), dim3(32, 8), 0, st>>>(p, l0);
+        };
+        auto collapse = [&](int l, cudaStream_t st) {
+            k_mb_collapse<<<dim3((p.lw[l - 1] + 127) / 128, (p.lh[l - 1] + 7) / 8), dim3(32, 8), 0, st>>>(p, l);
+        };
+        if (mb.fork && nb >= 3) {
+            // The levels >= 2 are a chain of small, latency-bound launches (for C3: down 10 + 8 + 8 us, collapse 5 + 5 + 8 us).
+            // They depend on level 1 only through G_2, and level 1's own band (the large one) does not depend on them: the chain
+            // runs on a side stream next to it and joins before the last collapse step.
+            down(0, s); down(1, s);
+            cudaEventRecord(mb.ev_fork, s);
+            cudaStreamWaitEvent(mb.side, mb.ev_fork, 0);
+            for (int l = 2; l < nb; l++) down(l, mb.side);
+            band(2, nb, mb.side);
+            for (int l = nb; l >= 3; l--) collapse(l, mb.side);
+            cudaEventRecord(mb.ev_join, mb.side);
+            band(1, 1, s);
+            cudaStreamWaitEvent(s, mb.ev_join, 0);
+            collapse(2, s);
+        } else {
+            for (int l = 0; l < nb; l++) down(l, s);
+            if (nb >= 1) band(1, nb, s);
+            for (int l = nb; l >= 2; l--) collapse(l, s);
         }
-        if (nb >= 1)                                        // levels 1 .. nb in one launch; level 0 is computed inside k_mb_final
-            k_mb_band<<<dim3((p.lw[1] + 127) / 128, (p.lh[1] + 7) / 8, nb), dim3(32, 8), 0, s>>>(p);
-        for (int l = nb; l >= 2; l--)
-            k_mb_collapse<<<dim3((p.lw[l - 1] + 127) / 128, (p.lh[l - 1] + 7) / 8), dim3(32, 8), 0, s>>>(p, l);
     }
     k_mb_final<<<dim3((p.ox1 - p.ox0 + 127) / 128, (p.oy1 - p.oy0 + 7) / 8), dim3(32, 8), 0, s>>>(p);
 }
@@ -1081,6 +1115,9 @@ int multiband_launches(const octvr_mapper& m) { return m.mb ? m.mb->launches : 0
 void multiband_destroy(Multiband* mb)
 {
     if (!mb) return;
+    if (mb->side) cudaStreamDestroy(mb->side);
+    if (mb->ev_fork) cudaEventDestroy(mb->ev_fork);
+    if (mb->ev_join) cudaEventDestroy(mb->ev_join);
     cudaFree(mb->d_chunks); cudaFree(mb->d_tile_cams); cudaFree(mb->d_wjobs); cudaFree(mb->d_wentries); cudaFree(mb->d_wtmaps); cudaFree(mb->d_coords); cudaFree(mb->d_g0); cudaFree(mb->d_g); cudaFree(mb->d_w); cudaFree(mb->d_dst); cudaFree(mb->d_dstw); cudaFree(mb->d_wide);
     delete mb;
 }

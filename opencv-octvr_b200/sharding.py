@@ -222,9 +222,8 @@ class StereoRowBandStitcher:
 
     def __init__(self, vr, tmpls, in_sizes, blend, enable_gain, device, align=32, rank=None, world=None, split="auto"):
         """split: how an eye is cut when several ranks share it -- "rows" (bands of output rows), "cols" (bands of output
-        columns; multiband only) or "auto": columns for multiband eyes that are wider than tall, because every band carries
-        a halo of 4 * 2^bands pixels either side of the cut (C4, 8 GPUs: 480 + 2 * 128 of 1920 rows = 1.53 x the work, but
-        1920 + 2 * 128 of 7680 columns = 1.13 x)."""
+        columns; multiband only) or "auto" (rows unless OCTVR_C4_SPLIT says otherwise).  Every band carries a halo of
+        4 * 2^bands pixels either side of the cut (C4, 8 GPUs: 480 + 2 * 128 of 1920 rows, or 1920 + 2 * 128 of 7680 columns)."""
         assert len(tmpls) == 2 and tuple(tmpls[0].out_size) == tuple(tmpls[1].out_size)
         self.vr = vr
         self.rank = rank if rank is not None else (dist.get_rank() if dist.is_initialized() else 0)
@@ -233,7 +232,9 @@ class StereoRowBandStitcher:
         self.align = align
         self.in_sizes = [tuple(s) for s in in_sizes]
         if split == "auto":
-            split = os.environ.get("OCTVR_C4_SPLIT", "cols" if blend > 0 and self.eye_w > self.eye_h else "rows")
+            # measured on 8 B200s (C4): column bands cut the multiband stage per rank from 0.292 to 0.259 ms but every rank then
+            # converts all rows of (nearly) all cameras (0.068 -> 0.107 ms): 0.511 vs 0.512 ms per frame -- rows stay the default
+            split = os.environ.get("OCTVR_C4_SPLIT", "rows")
         assert split in ("rows", "cols")
         self.split = split
         self.jobs = []
