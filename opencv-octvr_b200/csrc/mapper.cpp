@@ -348,13 +348,16 @@ static void build_mapper(octvr_mapper& m, const octvr_template& t, const int* in
     // host copies of the fixed-point coordinates: only where host code still walks them (multiband set-up, the source rows of
     // a row band, the non-default layouts); the gain tables sample a few thousand positions through fixed_at()
     std::vector<Img<int32_t>> sx(n), sy(n);
-    const bool host_xy = blend > 0 || !gpu_packed || is_band;
-    if (host_xy) {
+    bool host_xy = false;
+    auto ensure_host_xy = [&]() {
+        if (host_xy) return;
         for (int i = 0; i < n; i++) quantise_map(t.inputs[i].map1, t.inputs[i].map2, m.in_w[i], m.in_h[i], sx[i], sy[i]);
+        host_xy = true;
         tr.lap("quantise_map (host)");
-    }
+    };
+    if (blend <= 0 && (!gpu_packed || is_band)) ensure_host_xy();
     auto fixed_at = [&](int i, int lx, int ly, int32_t& fsx, int32_t& fsy) {
-        if (host_xy) { fsx = sx[i].row(ly)[lx]; fsy = sy[i].row(ly)[lx]; return; }
+        if (host_xy && !sx[i].empty()) { fsx = sx[i].row(ly)[lx]; fsy = sy[i].row(ly)[lx]; return; }
         const float fw = (float)(double)m.in_w[i], fh = (float)(double)m.in_h[i];      // quantise_map, one pixel
         const float px = t.inputs[i].map1.row(ly)[lx] * fw + 0.f, py = t.inputs[i].map2.row(ly)[lx] * fh + 0.f;
         fsx = (int32_t)lrintf(px * 32.f); fsy = (int32_t)lrintf(py * 32.f);
@@ -401,7 +404,12 @@ static void build_mapper(octvr_mapper& m, const octvr_template& t, const int* in
 
     tr.lap("planes + overlays");
     if (blend > 0) {
-        m.mb = ob::multiband_create(m, t, sx, sy);
+        // (the host set-up takes the coordinates over: nothing after it walks them)
+        m.mb = ob::multiband_create(m, t, [&](std::vector<Img<int32_t>>& ox, std::vector<Img<int32_t>>& oy) {
+            ensure_host_xy();
+            ox = std::move(sx); oy = std::move(sy);
+            sx.assign(n, Img<int32_t>()); sy.assign(n, Img<int32_t>()); host_xy = false;
+        });
         tr.lap("multiband_create");
     } else if (!gpu_packed) {
         if (!m.fused) {

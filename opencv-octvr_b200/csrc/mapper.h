@@ -1,6 +1,7 @@
 // csrc/mapper.h -- state behind octvr_mapper (vr::Mapper, modules/octvr/src/mapper.hpp:29-95).
 #pragma once
 #include "common.h"
+#include <functional>
 #include "kernels.cuh"
 #include "template.h"
 #include "post.h"
@@ -84,8 +85,9 @@ void encode_rgbx_tensor_map(void* out128, const uint32_t* plane, int plane_w, in
 // (then build_mapper's host packer runs).  m.d_rgbx must be allocated.
 bool pack_ring_gpu(octvr_mapper& m, const octvr_template& t, int blend);
 // multiband.cu
+// host_xy(sx, sy) fills the host copies of the fixed-point coordinates; called only when the tables cannot be packed on the device
 Multiband* multiband_create(octvr_mapper& m, const octvr_template& t,
-                            const std::vector<Img<int32_t>>& sx, const std::vector<Img<int32_t>>& sy);
+                            const std::function<void(std::vector<Img<int32_t>>&, std::vector<Img<int32_t>>&)>& host_xy);
 void multiband_stitch(octvr_mapper& m, const octvr_frame* out, cudaStream_t s);
 int multiband_launches(const octvr_mapper& m);
 void multiband_destroy(Multiband* mb);

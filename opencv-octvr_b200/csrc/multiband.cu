@@ -738,10 +738,324 @@ uint2 mk_entry(int32_t sx, int32_t sy, int src_w, int src_h, bool valid)
 }
 }  // namespace
 
+
+// ------------------------------------------------------------------------------------------------ device-side set-up
+// The static tables of a multiband mapper packed by CUDA kernels (the host code below does the same and stays for mappers
+// whose warp cannot be staged, and for OCTVR_PACK=host): fixed-point coordinates, staged-warp jobs / boxes / entries of every
+// camera rectangle (BORDER_REFLECT baked in), the f32 weight pyramids of the seam masks (cv::pyrDown's float arithmetic in
+// its exact association, prep.cpp pyrdown_f32), the summed band weights and the per-tile camera sets.
+struct MbGeom { int top, left, width, height, ys, ye, ch, xs, xe, cw; };      // one camera rectangle and its window (multiband_create, phase 0)
+namespace {
+struct MbpCam {
+    const float* map1; const float* map2; const uint8_t* mask; const uint8_t* seam; int2* sxy;
+    int roi_w, roi_h, src_w, src_h;
+    MbGeom g;
+    float* wfull[MB_MAX_LEVELS];      // weight pyramid of the FULL rectangle (temporary)
+};
+struct MbpParams { MbpCam cam[MAX_CAMS]; int n, nb; };
+
+__device__ __forceinline__ int mbp_mirror(int p, int len)      // BORDER_REFLECT (fedcba|abcdefgh|hgfedcb)
+{
+    if (len == 1) return 0;
+    while (p < 0 || p >= len) p = p < 0 ? -p - 1 : 2 * len - 1 - p;
+    return p;
+}
+__device__ __forceinline__ int mbp_mirror101(int p, int len)
+{
+    if (len == 1) return 0;
+    while (p < 0 || p >= len) p = p < 0 ? -p : 2 * len - 2 - p;
+    return p;
+}
+__global__ void __launch_bounds__(256) k_mbp_quantise(const __grid_constant__ MbpParams p, int c)
+{
+    const MbpCam& k = p.cam[c];
+    const size_t i = (size_t)blockIdx.x * 256 + threadIdx.x;
+    if (i >= (size_t)k.roi_w * k.roi_h) return;
+    const float fw = (float)(double)k.src_w, fh = (float)(double)k.src_h;
+    const float px = __fadd_rn(__fmul_rn(k.map1[i], fw), 0.f), py = __fadd_rn(__fmul_rn(k.map2[i], fh), 0.f);
+    k.sxy[i] = make_int2(__float2int_rn(__fmul_rn(px, 32.f)), __float2int_rn(__fmul_rn(py, 32.f)));
+}
+// table entry of window pixel (x, y) of camera k: valid (mk_entry's C_VALID), integer tap position, fractions
+__device__ __forceinline__ bool mbp_entry(const MbpCam& k, int x, int y, int& ix, int& iy, int& fx, int& fy)
+{
+    const int ly = mbp_mirror(y + k.g.ys - k.g.top, k.roi_h), lx = mbp_mirror(x + k.g.xs - k.g.left, k.roi_w);
+    const size_t o = (size_t)ly * k.roi_w + lx;
+    if (!k.mask[o]) return false;
+    const int2 s = k.sxy[o];
+    ix = min(32767, max(-32768, s.x >> 5)); iy = min(32767, max(-32768, s.y >> 5));
+    fx = s.x & 31; fy = s.y & 31;
+    const bool x0 = ix >= 0 && ix < k.src_w, x1 = ix + 1 >= 0 && ix + 1 < k.src_w, y0 = iy >= 0 && iy < k.src_h, y1 = iy + 1 >= 0 && iy + 1 < k.src_h;
+    return (x0 || x1) && (y0 || y1);
+}
+// one CTA per 32 x 16 tile of camera c's window: {xmin, xmax, ymin, ymax} of the taps of its valid pixels (xmin > xmax: none);
+// rows[0 / 1] = min / max source row over the camera's valid entries
+__global__ void __launch_bounds__(128) k_mbp_boxes(const __grid_constant__ MbpParams p, int c, int tiles_x, int4* boxes, int* rows)
+{
+    __shared__ int s[4];
+    const MbpCam& k = p.cam[c];
+    const int tx = blockIdx.x % tiles_x, ty = blockIdx.x / tiles_x;
+    if (threadIdx.x == 0) { s[0] = INT_MAX; s[1] = INT_MIN; s[2] = INT_MAX; s[3] = INT_MIN; }
+    __syncthreads();
+    int xmin = INT_MAX, xmax = INT_MIN, ymin = INT_MAX, ymax = INT_MIN;
+    #pragma unroll
+    for (int h = 0; h < 4; h++) {
+        const int px = threadIdx.x + h * 128, x = tx * TILE_W + (px & (TILE_W - 1)), y = ty * TILE_H + px / TILE_W;
+        int ix, iy, fx, fy;
+        if (x >= k.g.cw || y >= k.g.ch || !mbp_entry(k, x, y, ix, iy, fx, fy)) continue;
+        xmin = min(xmin, ix); xmax = max(xmax, ix + 1); ymin = min(ymin, iy); ymax = max(ymax, iy + 1);
+    }
+    xmin = __reduce_min_sync(0xffffffffu, xmin); xmax = __reduce_max_sync(0xffffffffu, xmax);
+    ymin = __reduce_min_sync(0xffffffffu, ymin); ymax = __reduce_max_sync(0xffffffffu, ymax);
+    if ((threadIdx.x & 31) == 0) { atomicMin(&s[0], xmin); atomicMax(&s[1], xmax); atomicMin(&s[2], ymin); atomicMax(&s[3], ymax); }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        boxes[blockIdx.x] = make_int4(s[0], s[1], s[2], s[3]);
+        if (s[0] <= s[1]) { atomicMin(rows + 2 * c, s[2]); atomicMax(rows + 2 * c + 1, s[3]); }
+    }
+}
+// the 512 four-byte entries of staged-warp job j (final order): stage offset | fy << 13 | fx << 18 | valid
+__global__ void __launch_bounds__(128) k_mbp_entries(const __grid_constant__ MbpParams p, const MbWarpJob* jobs, uint32_t* entries)
+{
+    const MbWarpJob job = jobs[blockIdx.x];
+    const MbpCam& k = p.cam[job.cam];
+    #pragma unroll
+    for (int h = 0; h < 4; h++) {
+        const int px = threadIdx.x + h * 128, x = job.tx * TILE_W + (px & (TILE_W - 1)), y = job.ty * TILE_H + px / TILE_W;
+        int ix, iy, fx, fy;
+        uint32_t e = 0u;
+        if (x < k.g.cw && y < k.g.ch && mbp_entry(k, x, y, ix, iy, fx, fy))
+            e = (uint32_t)((iy - job.by0) * job.bw + (ix - job.bx0)) | ((uint32_t)fy << 13) | ((uint32_t)fx << 18) | MBW_VALID;
+        entries[(size_t)blockIdx.x * TILE_PX + px] = e;
+    }
+}
+// level-0 weight map of the full rectangle: seam mask / 255 inside the roi, 0 in the border (BORDER_CONSTANT), blenders.cpp:345-366
+__global__ void __launch_bounds__(256) k_mbp_w0(const __grid_constant__ MbpParams p, int c)
+{
+    const MbpCam& k = p.cam[c];
+    const int x = blockIdx.x * 32 + threadIdx.x, y = blockIdx.y * 8 + threadIdx.y;
+    if (x >= k.g.width || y >= k.g.height) return;
+    const int lx = x - k.g.left, ly = y - k.g.top;
+    float w = 0.f;
+    if (lx >= 0 && ly >= 0 && lx < k.roi_w && ly < k.roi_h) w = __fadd_rn(__fmul_rn((float)k.seam[(size_t)ly * k.roi_w + lx], (float)(1. / 255.)), 0.f);
+    k.wfull[0][(size_t)y * k.g.width + x] = w;
+}
+// cv::pyrDown for 32FC1 (pyramids.cpp:849-964 incl. the SSE association of :143-185) -- prep.cpp pyrdown_f32
+__device__ __forceinline__ float mbp_hrow(const float* __restrict__ s, int sw, int c)
+{
+    const float a = __fmul_rn(s[c], 6.f), b = __fmul_rn(__fadd_rn(s[mbp_mirror101(c - 1, sw)], s[mbp_mirror101(c + 1, sw)]), 4.f);
+    return __fadd_rn(__fadd_rn(__fadd_rn(a, b), s[mbp_mirror101(c - 2, sw)]), s[mbp_mirror101(c + 2, sw)]);
+}
+__global__ void __launch_bounds__(256) k_mbp_pyrdown(const float* __restrict__ src, int sw, int sh, float* __restrict__ dst)
+{
+    const int dw = (sw + 1) / 2, dh = (sh + 1) / 2;
+    const int x = blockIdx.x * 32 + threadIdx.x, y = blockIdx.y * 8 + threadIdx.y;
+    if (x >= dw || y >= dh) return;
+    const float r0 = mbp_hrow(src + (size_t)mbp_mirror101(2 * y - 2, sh) * sw, sw, 2 * x), r1 = mbp_hrow(src + (size_t)mbp_mirror101(2 * y - 1, sh) * sw, sw, 2 * x);
+    const float r2 = mbp_hrow(src + (size_t)(2 * y) * sw, sw, 2 * x);
+    const float r3 = mbp_hrow(src + (size_t)mbp_mirror101(2 * y + 1, sh) * sw, sw, 2 * x), r4 = mbp_hrow(src + (size_t)mbp_mirror101(2 * y + 2, sh) * sw, sw, 2 * x);
+    float v;
+    if (x < (dw & ~7)) {
+        const float a = __fadd_rn(__fadd_rn(r0, r4), __fadd_rn(r2, r2)), b = __fadd_rn(__fadd_rn(r1, r3), r2);
+        v = __fmul_rn(__fadd_rn(a, __fmul_rn(b, 4.f)), 1.f / 256);
+    } else
+        v = __fmul_rn(__fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(r2, 6.f), __fmul_rn(__fadd_rn(r1, r3), 4.f)), r0), r4), (float)(1. / 256));
+    dst[(size_t)y * dw + x] = v;
+}
+// window (c0.., r0..) of a full-rectangle weight level -> the packed weight pool
+__global__ void __launch_bounds__(256) k_mbp_crop(const float* __restrict__ src, int sw, int c0, int r0, float* __restrict__ dst, int dw, int dh)
+{
+    const int x = blockIdx.x * 32 + threadIdx.x, y = blockIdx.y * 8 + threadIdx.y;
+    if (x >= dw || y >= dh) return;
+    dst[(size_t)y * dw + x] = src[(size_t)(r0 + y) * sw + c0 + x];
+}
+// dst_band_weights_[l] (cameras added in order, blenders.cpp:421) and the camera set of every 32 x 8 tile of level l
+__global__ void __launch_bounds__(256) k_mbp_dstw(const __grid_constant__ MbParams p, int l, float* dstw, uint16_t* tile_cams)
+{
+    __shared__ unsigned s_cams;
+    const int x = blockIdx.x * 32 + threadIdx.x, y = blockIdx.y * 8 + threadIdx.y;
+    if (threadIdx.x == 0 && threadIdx.y == 0) s_cams = 0u;
+    __syncthreads();
+    const int lw = p.lw[l], lh = p.lh[l];
+    unsigned cams = 0;
+    if (x < lw && y < lh) {
+        float sum = 0.f;
+        for (int c = 0; c < p.n; c++) {
+            const MbCam& cam = p.cam[c];
+            const int cx = x - (cam.x0 >> l), cy = y - (cam.y0 >> l), wl = cam.bw >> l, hl = cam.bh >> l;
+            if (cx < 0 || cy < 0 || cx >= wl || cy >= hl) continue;
+            const float w = p.w[cam.off_w[l] + (size_t)cy * wl + cx];
+            sum = __fadd_rn(sum, w);
+            if (w != 0.f) cams |= 1u << c;
+        }
+        dstw[p.off_d[l] + (size_t)y * lw + x] = sum;
+    }
+    cams = __reduce_or_sync(0xffffffffu, cams);
+    if (threadIdx.x == 0 && cams) atomicOr(&s_cams, cams);
+    __syncthreads();
+    if (threadIdx.x == 0 && threadIdx.y == 0) tile_cams[p.off_t[l] + (size_t)blockIdx.y * ((lw + 31) / 32) + blockIdx.x] = (uint16_t)s_cams;
+}
+template <class T> struct MbpBuf {
+    T* p = nullptr;
+    MbpBuf() {}
+    explicit MbpBuf(size_t n) { OB_CUDA(cudaMalloc(&p, std::max<size_t>(n, 1) * sizeof(T))); }
+    MbpBuf(const T* h, size_t n) : MbpBuf(n) { if (n) OB_CUDA(cudaMemcpy(p, h, n * sizeof(T), cudaMemcpyHostToDevice)); }
+    ~MbpBuf() { cudaFree(p); }
+    MbpBuf(const MbpBuf&) = delete;
+    T* release() { T* q = p; p = nullptr; return q; }
+};
+}  // namespace
+
+// false: not applicable (a tile's footprint does not fit the stage ...) -- the caller runs the host set-up instead
+static bool multiband_pack_gpu(octvr_mapper& m, const octvr_template& t, const std::vector<Img<uint8_t>>& seams, const std::vector<MbGeom>& geo,
+                               Multiband& mb, size_t dst_floats, size_t n_tiles, int64_t& table_bytes)
+{
+    InitTrace tr("multiband_pack_gpu");
+    MbParams& p = mb.p;
+    const int n = p.n, nb = p.nb;
+    MbpParams q;
+    memset(&q, 0, sizeof(q));
+    q.n = n; q.nb = nb;
+    std::vector<std::unique_ptr<MbpBuf<float>>> d_m1(n), d_m2(n);
+    std::vector<std::unique_ptr<MbpBuf<uint8_t>>> d_mask(n), d_seam(n);
+    std::vector<std::unique_ptr<MbpBuf<int2>>> d_sxy(n);
+    std::vector<std::unique_ptr<MbpBuf<float>>> d_wfull(n);
+    size_t w_total = 0;
+    for (int i = 0; i < n; i++) {
+        const TInput& in = t.inputs[i];
+        const size_t px = (size_t)in.roi.w * in.roi.h;
+        d_m1[i].reset(new MbpBuf<float>(in.map1.d.data(), px)); d_m2[i].reset(new MbpBuf<float>(in.map2.d.data(), px));
+        d_mask[i].reset(new MbpBuf<uint8_t>(in.mask.d.data(), px)); d_seam[i].reset(new MbpBuf<uint8_t>(seams[i].d.data(), px));
+        d_sxy[i].reset(new MbpBuf<int2>(px));
+        MbpCam& k = q.cam[i];
+        k.map1 = d_m1[i]->p; k.map2 = d_m2[i]->p; k.mask = d_mask[i]->p; k.seam = d_seam[i]->p; k.sxy = d_sxy[i]->p;
+        k.roi_w = in.roi.w; k.roi_h = in.roi.h; k.src_w = m.in_w[i]; k.src_h = m.in_h[i]; k.g = geo[i];
+        // full-rectangle weight pyramid (temporary): levels packed one after the other
+        size_t tot = 0; int w = geo[i].width, h = geo[i].height;
+        for (int l = 0; l <= nb; l++) { tot += (size_t)w * h; w = (w + 1) / 2; h = (h + 1) / 2; }
+        d_wfull[i].reset(new MbpBuf<float>(tot));
+        size_t off = 0; w = geo[i].width; h = geo[i].height;
+        for (int l = 0; l <= nb; l++) { k.wfull[l] = d_wfull[i]->p + off; off += (size_t)w * h; w = (w + 1) / 2; h = (h + 1) / 2; }
+        for (int l = 0; l <= nb; l++) { p.cam[i].off_w[l] = w_total; w_total += (size_t)(geo[i].cw >> l) * (geo[i].ch >> l); }
+    }
+    tr.lap("upload maps + masks");
+    for (int i = 0; i < n; i++) k_mbp_quantise<<<(unsigned)(((size_t)t.inputs[i].roi.w * t.inputs[i].roi.h + 255) / 256), 256>>>(q, i);
+    OB_CUDA(cudaGetLastError());
+    // ---- staged warp: per camera the tiles of its window, their tap boxes
+    MbpBuf<int> d_rows(2 * MAX_CAMS);
+    {
+        std::vector<int> init(2 * MAX_CAMS);
+        for (int i = 0; i < MAX_CAMS; i++) { init[2 * i] = INT_MAX; init[2 * i + 1] = INT_MIN; }
+        OB_CUDA(cudaMemcpy(d_rows.p, init.data(), init.size() * sizeof(int), cudaMemcpyHostToDevice));
+    }
+    std::vector<std::vector<int4>> boxes(n);
+    for (int i = 0; i < n; i++) {
+        const int tiles_x = (geo[i].cw + TILE_W - 1) / TILE_W, tiles_y = (geo[i].ch + TILE_H - 1) / TILE_H;
+        const size_t nt = (size_t)tiles_x * tiles_y;
+        if (geo[i].ch <= 0 || nt == 0) continue;
+        if (tiles_x > 65535 || tiles_y > 65535) return false;
+        MbpBuf<int4> d_box(nt);
+        k_mbp_boxes<<<(unsigned)nt, 128>>>(q, i, tiles_x, d_box.p, d_rows.p);
+        OB_CUDA(cudaGetLastError());
+        boxes[i].resize(nt);
+        OB_CUDA(cudaMemcpy(boxes[i].data(), d_box.p, nt * sizeof(int4), cudaMemcpyDeviceToHost));
+    }
+    std::vector<int> rows(2 * MAX_CAMS);
+    OB_CUDA(cudaMemcpy(rows.data(), d_rows.p, rows.size() * sizeof(int), cudaMemcpyDeviceToHost));
+    tr.lap("quantise + tile boxes");
+    // jobs in the host packer's order: cameras in order, tiles row by row; size classes, tensor-map slots
+    std::vector<MbWarpJob> wjobs;
+    std::map<uint64_t, int> tmap_index;
+    auto size_class = [](int v) { return v <= 64 ? (v + 7) / 8 * 8 : v <= 128 ? (v + 15) / 16 * 16 : (v + 31) / 32 * 32; };
+    for (int i = 0; i < n; i++) {
+        const int tiles_x = (geo[i].cw + TILE_W - 1) / TILE_W;
+        size_t keys_of_cam = 0;
+        for (size_t k = 0; k < boxes[i].size(); k++) {
+            const int4 b = boxes[i][k];
+            if (b.x > b.y) continue;
+            MbWarpJob job;
+            memset(&job, 0, sizeof(job));
+            job.bx0 = (int)std::floor(b.x / 4.0) * 4; job.by0 = b.z;
+            const int bw = size_class(b.y - job.bx0 + 1), bh = size_class(b.w - b.z + 1);
+            if (bw > 256 || bh > 256 || (int64_t)bw * bh > MB_STAGE) return false;
+            job.bw = (uint16_t)bw; job.bh = (uint16_t)bh; job.cam = (uint16_t)i; job.tx = (uint16_t)(k % tiles_x); job.ty = (uint16_t)(k / tiles_x);
+            const uint64_t key = ((uint64_t)i << 32) | ((uint64_t)bw << 16) | (uint64_t)bh;
+            auto it = tmap_index.find(key);
+            if (it == tmap_index.end()) { it = tmap_index.emplace(key, (int)tmap_index.size()).first; keys_of_cam++; }
+            if (keys_of_cam > 60000 || tmap_index.size() > 65535) return false;
+            job.tmap = (uint16_t)it->second;
+            wjobs.push_back(job);
+        }
+    }
+    if (wjobs.empty()) return false;
+    {   // small-box jobs first (stable), as the host packer orders them
+        std::vector<MbWarpJob> j2;
+        j2.reserve(wjobs.size());
+        auto small = [&](const MbWarpJob& j) { return (int)j.bw * j.bh <= MB_STAGE_SMALL; };
+        for (auto& j : wjobs) if (small(j)) j2.push_back(j);
+        mb.n_wsmall = (unsigned)j2.size();
+        for (auto& j : wjobs) if (!small(j)) j2.push_back(j);
+        wjobs.swap(j2);
+    }
+    MbpBuf<MbWarpJob> d_jobs(wjobs.data(), wjobs.size());
+    MbpBuf<uint32_t> d_entries(wjobs.size() * TILE_PX);
+    k_mbp_entries<<<(unsigned)wjobs.size(), 128>>>(q, d_jobs.p, d_entries.p);
+    OB_CUDA(cudaGetLastError());
+    tr.lap("jobs + entries");
+    // ---- weights: full-rectangle pyramids, windows cropped into the pool, summed band weights, tile camera sets
+    MbpBuf<float> d_w(w_total), d_dstw(dst_floats);
+    MbpBuf<uint16_t> d_tc(n_tiles);
+    OB_CUDA(cudaMemset(d_dstw.p, 0, std::max<size_t>(dst_floats, 1) * sizeof(float)));
+    OB_CUDA(cudaMemset(d_tc.p, 0, std::max<size_t>(n_tiles, 1) * sizeof(uint16_t)));
+    for (int i = 0; i < n; i++) {
+        const MbGeom& g = geo[i];
+        k_mbp_w0<<<dim3((g.width + 31) / 32, (g.height + 7) / 8), dim3(32, 8)>>>(q, i);
+        int w = g.width, h = g.height;
+        for (int l = 1; l <= nb; l++) {
+            k_mbp_pyrdown<<<dim3(((w + 1) / 2 + 31) / 32, ((h + 1) / 2 + 7) / 8), dim3(32, 8)>>>(q.cam[i].wfull[l - 1], w, h, q.cam[i].wfull[l]);
+            w = (w + 1) / 2; h = (h + 1) / 2;
+        }
+        w = g.width;
+        for (int l = 0; l <= nb; l++) {
+            const int dw = g.cw >> l, dh = g.ch >> l;
+            if (dw > 0 && dh > 0)
+                k_mbp_crop<<<dim3((dw + 31) / 32, (dh + 7) / 8), dim3(32, 8)>>>(q.cam[i].wfull[l], w, g.xs >> l, g.ys >> l, d_w.p + p.cam[i].off_w[l], dw, dh);
+            w = (w + 1) / 2;
+        }
+    }
+    OB_CUDA(cudaGetLastError());
+    p.w = d_w.p;
+    for (int l = 0; l <= nb; l++)
+        if (p.lw[l] > 0 && p.lh[l] > 0) k_mbp_dstw<<<dim3((p.lw[l] + 31) / 32, (p.lh[l] + 7) / 8), dim3(32, 8)>>>(p, l, d_dstw.p, d_tc.p);
+    OB_CUDA(cudaGetLastError());
+    OB_CUDA(cudaDeviceSynchronize());
+    tr.lap("weight pyramids + band weights");
+    // ---- commit
+    std::vector<uint8_t> tmaps(tmap_index.size() * 128);
+    for (auto& kv : tmap_index) {
+        const int cam = (int)(kv.first >> 32), bw = (int)((kv.first >> 16) & 0xFFFF), bh = (int)(kv.first & 0xFFFF);
+        encode_rgbx_tensor_map(tmaps.data() + (size_t)kv.second * 128, m.d_rgbx[cam], m.in_w[cam], m.in_h[cam], bw, bh);
+    }
+    MbpBuf<uint8_t> d_tm(tmaps.data(), tmaps.size());
+    mb.d_wtmaps = d_tm.release();
+    mb.d_wjobs = d_jobs.release(); mb.d_wentries = d_entries.release(); mb.n_wjobs = (unsigned)wjobs.size();
+    mb.d_w = d_w.release(); mb.d_dstw = d_dstw.release(); mb.d_tile_cams = d_tc.release();
+    p.wjobs = mb.d_wjobs; p.wentries = mb.d_wentries; p.wtmaps = mb.d_wtmaps;
+    if (m.band_y0 != 0 || m.band_y1 != t.out_h || m.band_x0 != 0 || m.band_x1 != t.out_w)
+        for (int i = 0; i < n; i++) {
+            const int lo = rows[2 * i], hi = rows[2 * i + 1];
+            if (lo > hi) m.src_row0[i] = m.src_row1[i] = 0;
+            else { m.src_row0[i] = std::max(0, lo) & ~1; m.src_row1[i] = std::min(m.in_h[i], hi + 1); }
+        }
+    table_bytes = (int64_t)(wjobs.size() * TILE_PX * 4 + wjobs.size() * sizeof(MbWarpJob) + w_total * 4 + dst_floats * 4);
+    return true;
+}
+
 Multiband* multiband_create(octvr_mapper& m, const octvr_template& t,
-                            const std::vector<Img<int32_t>>& sx, const std::vector<Img<int32_t>>& sy)
+                            const std::function<void(std::vector<Img<int32_t>>&, std::vector<Img<int32_t>>&)>& host_xy)
 {
     const int n = m.n;
+    InitTrace tr("multiband_create");
+    std::vector<Img<int32_t>> sx, sy;                       // fixed-point coordinates on the host: only the host set-up needs them
     std::vector<Img<uint8_t>> seams = t.seam_masks;
     bool have = (int)seams.size() == n;
     for (auto& s : seams) have = have && !s.empty();
@@ -848,6 +1162,26 @@ Multiband* multiband_create(octvr_mapper& m, const octvr_template& t,
         // every level starts at an even element: 16-byte aligned rows for the vector loads of mb_down_strip_p16
         for (int l = 1; l <= nb; l++) { c.off_g[l] = g_total; g_total += (size_t)(b.cw >> l) * (b.ch >> l); g_total += g_total & 1; }
     }
+    std::vector<MbGeom> geo(n);
+    for (int i = 0; i < n; i++) geo[i] = MbGeom{ cb[i].top, cb[i].left, cb[i].width, cb[i].height, cb[i].ys, cb[i].ye, cb[i].ch, cb[i].xs, cb[i].xe, cb[i].cw };
+    // ---- the tables packed by CUDA kernels (default); the host set-up below when that does not apply ----
+    bool on_device = false;
+    {
+        const char* e = getenv("OCTVR_PACK");
+        if (staged && !(e && std::string(e) == "host")) {
+            int64_t tb = 0;
+            on_device = multiband_pack_gpu(m, t, seams, geo, *mb, doff, tile_cams.size(), tb);
+            if (on_device) m.table_bytes = tb;
+            else {      // partial state of a failed attempt
+                cudaFree(mb->d_wjobs); cudaFree(mb->d_wentries); cudaFree(mb->d_wtmaps); cudaFree(mb->d_w); cudaFree(mb->d_dstw); cudaFree(mb->d_tile_cams);
+                mb->d_wjobs = nullptr; mb->d_wentries = nullptr; mb->d_wtmaps = nullptr; mb->d_w = nullptr; mb->d_dstw = nullptr; mb->d_tile_cams = nullptr;
+                mb->n_wjobs = mb->n_wsmall = 0; p.w = nullptr; p.wjobs = nullptr; p.wentries = nullptr; p.wtmaps = nullptr;
+            }
+        }
+    }
+    tr.lap(on_device ? "tables packed on the device" : "device packing not applicable");
+    if (!on_device) {
+    host_xy(sx, sy);
     coords.resize(g0_total);
 
     // ---- phase 1 (one host thread per camera): level-0 remap table with BORDER_REFLECT baked in, the f32 weight map
@@ -1028,6 +1362,9 @@ Multiband* multiband_create(octvr_mapper& m, const octvr_template& t,
     mb->d_dstw = upload(dstw);
     mb->d_chunks = upload(chunks); mb->n_chunks = (unsigned)chunks.size();
     mb->d_tile_cams = upload(tile_cams);
+    m.table_bytes = (int64_t)(coords.size() * sizeof(uint2) + wentries.size() * 4 + wjobs.size() * sizeof(MbWarpJob) + wts.size() * 4 + dstw.size() * 4);
+    tr.lap("tables packed on the host");
+    }   // !on_device
     p.warp_chunks = mb->d_chunks; p.tile_cams = mb->d_tile_cams;
     OB_CUDA(cudaMalloc(&mb->d_g0, std::max<size_t>(g0_total, 1) * sizeof(uint32_t)));
     OB_CUDA(cudaMemset(mb->d_g0, 0, std::max<size_t>(g0_total, 1) * sizeof(uint32_t)));       // chunks without valid entries stay 0
@@ -1054,7 +1391,6 @@ Multiband* multiband_create(octvr_mapper& m, const octvr_template& t,
     }
     p.coords = mb->d_coords; p.g0 = mb->d_g0; p.g = mb->d_g; p.w = mb->d_w; p.dst = mb->d_dst; p.dstw = mb->d_dstw;
     for (int i = 0; i < n; i++) { p.rgbx[i] = m.d_rgbx[i]; p.src_pitch[i] = m.in_w[i]; }
-    m.table_bytes = (int64_t)(coords.size() * sizeof(uint2) + wentries.size() * 4 + wjobs.size() * sizeof(MbWarpJob) + wts.size() * 4 + dstw.size() * 4);
     mb->launches = (mb->n_wjobs ? (mb->n_wsmall ? 1 : 0) + (mb->n_wjobs > mb->n_wsmall ? 1 : 0) : 1) + nb + (nb >= 1 ? 1 : 0) + (mb->fork && nb >= 3 ? 1 : 0) + std::max(0, nb - 1) + 1;
     return mb.release();
 }
