@@ -365,7 +365,7 @@ static void build_mapper(octvr_mapper& m, const octvr_template& t, const int* in
 
     // source rows a row-band mapper touches (feather / no blend: the taps of its own output rows; the multiband set-up
     // widens this to its row window)
-    if (is_band)
+    if (is_band && blend <= 0)
         for (int i = 0; i < n; i++) {
             const TInput& in = t.inputs[i];
             int lo = INT32_MAX, hi = INT32_MIN;
