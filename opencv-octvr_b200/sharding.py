@@ -172,12 +172,14 @@ def signal_group():
     return _SIGNAL_GROUP["g"]
 
 
-def frame_complete(token):
+def frame_complete(token, async_op=False):
     """Row-band mode with PeerFrame outputs: the frame on the owner is complete when every rank's stitch has finished.
-    One 4-byte all-reduce enqueued behind the stitch on every rank; the owner's stream is past it only when all are."""
+    One 4-byte all-reduce enqueued behind the stitch on every rank; the owner's stream is past it only when all are.
+    async_op=True returns the work handle: the all-reduce then runs on its communicator's stream behind this rank's stitch
+    while the compute stream goes on with the next frame; wait() on the handle before the frame is read or its buffer reused."""
     if dist.is_initialized() and dist.get_world_size() > 1:
-        dist.all_reduce(token, group=signal_group())
-    return token
+        return dist.all_reduce(token, group=signal_group(), async_op=async_op)
+    return None
 
 
 class RowBandStitcher:
@@ -293,6 +295,10 @@ class FramePipeline:
         self.st, self.src, self.pending, self.defer, self.peer = stitcher, src, {}, defer_collect, peer
         self.collecting = {}                            # output buffer -> work handles of its band collection
         self.token = None
+        # peer mode: the completion signal of frame k is waited for when its output buffer is next written (or in flush()), not
+        # right behind the stitch: it then costs the compute stream nothing (OCTVR_C4_SIGNAL=sync: wait at once, 0.02 ms per step)
+        self.signal_sync = os.environ.get("OCTVR_C4_SIGNAL", "deferred") == "sync"
+        self.signals, self.tokens = {}, {}
         self.trace = [] if os.environ.get("OCTVR_C4_TRACE") else None
         if peer:
             signal_group()                              # collective: every rank builds the pipeline
@@ -313,6 +319,9 @@ class FramePipeline:
         if next_flat is not None:
             self.pending[next_flat.data_ptr()] = broadcast_frames(next_flat, self.src, async_op=True)
         self._wait_collect(out)                        # an earlier frame may still be leaving this buffer
+        w = self.signals.pop(out.data_ptr(), None)     # ... or its "frame complete" signal may still be in flight
+        if w is not None:
+            w.wait()
         if hasattr(self.st, "stitch_local"):
             self.st.stitch_local(frames, out)
         else:
@@ -320,9 +329,13 @@ class FramePipeline:
         if self.trace is not None:
             self._mark("stitch")
         if collect and self.peer:
-            if self.token is None:
-                self.token = torch.zeros(1, dtype=torch.int32, device=out.device)
-            frame_complete(self.token)
+            if self.signal_sync:
+                if self.token is None:
+                    self.token = torch.zeros(1, dtype=torch.int32, device=out.device)
+                frame_complete(self.token)
+            else:
+                tok = self.tokens.setdefault(out.data_ptr(), torch.zeros(1, dtype=torch.int32, device=out.device))
+                self.signals[out.data_ptr()] = frame_complete(tok, async_op=True)
         elif collect:
             if self.defer:
                 self.collecting[out.data_ptr()] = collect_shares(out, self.st.shares(), self.src, wait=False)
@@ -349,7 +362,11 @@ class FramePipeline:
         return rows
 
     def flush(self):
-        """Wait (on the current stream) for every band collection still in flight."""
+        """Wait (on the current stream) for every band collection and completion signal still in flight."""
         for key in list(self.collecting):
             for w in self.collecting.pop(key):
+                w.wait()
+        for key in list(self.signals):
+            w = self.signals.pop(key)
+            if w is not None:
                 w.wait()
