@@ -144,6 +144,118 @@ __global__ void __launch_bounds__(FT_THREADS) k_fast_nv12(const __grid_constant_
     }
 }
 
+
+// ---- k_fast_staged (default): the same arithmetic with the taps read from shared memory ------------------------------------
+// Tiles of 16 rows x 16 threads (luma: 64 x 16 pixels, a thread owns 4; chroma: 32 x 16 positions, a thread owns 2).  Per job
+// the source footprint of the tile -- rows [by0, by0 + bh) x bytes [bx0, bx0 + 16 bwc) of the camera's plane, <= 16 KB -- is
+// copied into one of two shared-memory stages with 16-byte cp.async (zero-filled where it leaves the plane: that IS the
+// OUTSIDE() rule of the OpenCL kernel), the next job's copy in flight while this job's pixels are gathered.  Entries shrink
+// to 4 bytes: stage offset (14 bits) | fx << 14 | fy << 19 | weight << 24.
+constexpr int FS_ROWS = 16, FS_STAGE = 16384;
+struct FsJob { short bx0, by0; unsigned short bwc, bh; uint32_t entry_ofs; uint32_t cam; };      // entry_ofs in uint32 units
+static_assert(sizeof(FsJob) == 16, "FsJob");
+struct FsParams {
+    FastCam cam[MAX_CAMS];
+    const uint32_t* tile_job_start; const FsJob* jobs; const uint32_t* entries;
+    uint8_t* out; int out_pitch, W, H;
+    int luma_tiles_x, luma_tiles, chroma_tiles_x;
+};
+__device__ __forceinline__ void fs_issue(const FsJob& job, const uint8_t* __restrict__ plane, int pitch, int wbytes, int h, uint8_t* stage)
+{
+    const int n = (int)job.bwc * job.bh;
+    for (int c = threadIdx.x; c < n; c += FT_THREADS) {
+        const int r = c / job.bwc, k = c - r * job.bwc;
+        const int gy = job.by0 + r, gx = job.bx0 + 16 * k;
+        int valid = (gy >= 0 && gy < h && gx >= 0) ? min(max(wbytes - gx, 0), 16) : 0;
+        const uint8_t* src = valid ? plane + (size_t)gy * pitch + gx : plane;
+        const uint32_t dst = (uint32_t)__cvta_generic_to_shared(stage + c * 16);
+        asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" :: "r"(dst), "l"(src), "r"(valid) : "memory");
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+}
+__device__ __forceinline__ uint32_t fs_q(int V, float fw)
+{
+    return (uint32_t)__float2int_rn(__fmul_rn(__int2float_rn(V), fw) * 0.0009765625f);
+}
+__global__ void __launch_bounds__(FT_THREADS) k_fast_staged(const __grid_constant__ FsParams p)
+{
+    __shared__ __align__(16) uint8_t s_stage[2][FS_STAGE];
+    const int tile = blockIdx.x, tid = threadIdx.x, lane_x = tid & 15, row = tid >> 4;
+    const uint32_t j0 = __ldg(p.tile_job_start + tile), j1 = __ldg(p.tile_job_start + tile + 1);
+    const bool luma = tile < p.luma_tiles;
+    uint32_t acc[4] = { 0, 0, 0, 0 };                  // luma: four pixels; chroma: {pos 0 ch 0, pos 0 ch 1, pos 1 ch 0, pos 1 ch 1}
+    FsJob cur, nxt;
+    if (j0 < j1) {
+        cur = p.jobs[j0];
+        const FastCam& c = p.cam[cur.cam];
+        fs_issue(cur, luma ? c.y : c.uv, luma ? c.y_pitch : c.uv_pitch, luma ? c.w : 2 * (c.w / 2), luma ? c.h : c.h / 2, s_stage[0]);
+    }
+    for (uint32_t j = j0; j < j1; j++) {
+        const int buf = (int)(j - j0) & 1;
+        if (j + 1 < j1) {
+            nxt = p.jobs[j + 1];
+            const FastCam& c = p.cam[nxt.cam];
+            fs_issue(nxt, luma ? c.y : c.uv, luma ? c.y_pitch : c.uv_pitch, luma ? c.w : 2 * (c.w / 2), luma ? c.h : c.h / 2, s_stage[buf ^ 1]);
+        }
+        const uint8_t* st = s_stage[buf];
+        const int sp = (int)cur.bwc * 16;
+        if (luma) {
+            const uint4 e4 = __ldg(reinterpret_cast<const uint4*>(p.entries + cur.entry_ofs) + tid);
+            if (j + 1 < j1) asm volatile("cp.async.wait_group 1;" ::: "memory"); else asm volatile("cp.async.wait_group 0;" ::: "memory");
+            __syncthreads();
+            const uint32_t e[4] = { e4.x, e4.y, e4.z, e4.w };
+            #pragma unroll
+            for (int k = 0; k < 4; k++) {
+                const uint32_t wgt = e[k] >> 24;
+                const int off = e[k] & 0x3FFF, fx = (e[k] >> 14) & 31, fy = (e[k] >> 19) & 31;
+                const int a = st[off], b = st[off + 1], c2 = st[off + sp], d = st[off + sp + 1];
+                const int V = (a * (32 - fx) + b * fx) * (32 - fy) + (c2 * (32 - fx) + d * fx) * fy;
+                acc[k] += fs_q(V, (float)wgt);         // weight 0 (no contribution): q = 0 whatever the taps are
+            }
+        } else {
+            const uint2 e2 = __ldg(reinterpret_cast<const uint2*>(p.entries + cur.entry_ofs) + tid);
+            if (j + 1 < j1) asm volatile("cp.async.wait_group 1;" ::: "memory"); else asm volatile("cp.async.wait_group 0;" ::: "memory");
+            __syncthreads();
+            const uint32_t e[2] = { e2.x, e2.y };
+            #pragma unroll
+            for (int k = 0; k < 2; k++) {
+                const float fw = (float)(e[k] >> 24);
+                const int off = e[k] & 0x3FFF, fx = (e[k] >> 14) & 31, fy = (e[k] >> 19) & 31;
+                const uint32_t a = *reinterpret_cast<const uint16_t*>(st + off), b = *reinterpret_cast<const uint16_t*>(st + off + 2);
+                const uint32_t c2 = *reinterpret_cast<const uint16_t*>(st + off + sp), d = *reinterpret_cast<const uint16_t*>(st + off + sp + 2);
+                const int k00 = (32 - fx) * (32 - fy), k01 = fx * (32 - fy), k10 = (32 - fx) * fy, k11 = fx * fy;
+                const int V0 = (int)(a & 0xFF) * k00 + (int)(b & 0xFF) * k01 + (int)(c2 & 0xFF) * k10 + (int)(d & 0xFF) * k11;
+                const int V1 = (int)(a >> 8) * k00 + (int)(b >> 8) * k01 + (int)(c2 >> 8) * k10 + (int)(d >> 8) * k11;
+                acc[2 * k] += fs_q(V0, fw); acc[2 * k + 1] += fs_q(V1, fw);
+            }
+        }
+        __syncthreads();                               // everyone is done with this stage before the job after next overwrites it
+        cur = nxt;
+    }
+    if (luma) {
+        const int tx = tile % p.luma_tiles_x, ty = tile / p.luma_tiles_x;
+        const int x = tx * 64 + lane_x * 4, y = ty * FS_ROWS + row;
+        if (y >= p.H || x >= p.W) return;
+        uint32_t o[4];
+        #pragma unroll
+        for (int k = 0; k < 4; k++) o[k] = min(fast_out(acc[k]), 255u);
+        uint8_t* d = p.out + (size_t)y * p.out_pitch + x;
+        if (x + 3 < p.W && ((p.out_pitch & 3) == 0)) *reinterpret_cast<uint32_t*>(d) = o[0] | (o[1] << 8) | (o[2] << 16) | (o[3] << 24);
+        else for (int k = 0; k < 4 && x + k < p.W; k++) d[k] = (uint8_t)o[k];
+    } else {
+        const int ct = tile - p.luma_tiles;
+        const int tx = ct % p.chroma_tiles_x, ty = ct / p.chroma_tiles_x;
+        const int cw = p.W / 2, ch = p.H / 2;
+        const int x = tx * 32 + lane_x * 2, y = ty * FS_ROWS + row;
+        if (y >= ch || x >= cw) return;
+        // output channel 0 <- input channel 1, output channel 1 <- input channel 0 (mapper_fast.cpp:179-180)
+        const uint32_t o[4] = { min(fast_out(acc[1]), 255u), min(fast_out(acc[0]), 255u), min(fast_out(acc[3]), 255u), min(fast_out(acc[2]), 255u) };
+        uint8_t* d = p.out + (size_t)(p.H + y) * p.out_pitch + 2 * x;
+        if (x + 1 < cw && ((p.out_pitch & 3) == 0)) *reinterpret_cast<uint32_t*>(d) = o[0] | (o[1] << 8) | (o[2] << 16) | (o[3] << 24);
+        else { d[0] = (uint8_t)o[0]; d[1] = (uint8_t)o[1]; if (x + 1 < cw) { d[2] = (uint8_t)o[2]; d[3] = (uint8_t)o[3]; } }
+    }
+}
+
 // cv::resize(src, Size(cols / 2, rows / 2)) INTER_LINEAR as the FastMapper constructor calls it (mapper_fast.cpp:57-58,70,98-99):
 // exact 2x goes through the INTER_AREA fast path (imgwarp.cpp:3299-3303); f32: SSE body ((a + b) + (c + d)) * 0.25f for
 // dx <= w - 4 (:2283-2318), scalar tail (((0 + a) + b) + c + d) * 0.25f (:2425-2437); u8: (a + b + c + d + 2) >> 2
@@ -225,6 +337,60 @@ void pack_plane(const std::vector<FastTable>& tb, int W, int H, int px, int sw_d
         }
 }
 
+
+// staged tables of one plane pass (k_fast_staged).  px: positions per thread (4 luma, 2 chroma); unit: bytes per source position
+// (1 luma, 2 interleaved chroma).  false: some job's footprint does not fit the stage -> the direct kernel serves the mapper.
+bool pack_plane_staged(const std::vector<FastTable>& tb, int W, int H, int px, int unit, int sdiv, const std::vector<int>& in_w, const std::vector<int>& in_h,
+                       std::vector<uint32_t>& tile_job_start, std::vector<FsJob>& jobs, std::vector<uint32_t>& entries, int& tiles_x, int64_t& pairs)
+{
+    const int n = (int)tb.size(), tile_w = 16 * px;
+    tiles_x = (W + tile_w - 1) / tile_w;
+    const int tiles_y = (H + FS_ROWS - 1) / FS_ROWS;
+    for (int ty = 0; ty < tiles_y; ty++)
+        for (int tx = 0; tx < tiles_x; tx++) {
+            for (int c = 0; c < n; c++) {
+                const int sw = in_w[c] / sdiv, sh = in_h[c] / sdiv;
+                int xmin = INT32_MAX, xmax = INT32_MIN, ymin = INT32_MAX, ymax = INT32_MIN;
+                auto tap = [&](int x, int y, int& ax, int& ay) {
+                    if (!tb[c].wgt.row(y)[x]) return false;
+                    ax = sat16(tb[c].sx.row(y)[x] >> 5); ay = sat16(tb[c].sy.row(y)[x] >> 5);
+                    return ax + 1 >= 0 && ay + 1 >= 0 && ax < sw && ay < sh;              // at least one tap inside
+                };
+                for (int y = ty * FS_ROWS; y < std::min(H, (ty + 1) * FS_ROWS); y++)
+                    for (int x = tx * tile_w; x < std::min(W, (tx + 1) * tile_w); x++) {
+                        int ax, ay;
+                        if (!tap(x, y, ax, ay)) continue;
+                        xmin = std::min(xmin, ax); xmax = std::max(xmax, ax + 1); ymin = std::min(ymin, ay); ymax = std::max(ymax, ay + 1);
+                    }
+                if (xmin > xmax) continue;
+                const int x0b = unit * xmin, x1b = unit * xmax + unit - 1;               // byte range of the taps in a source row
+                const int bx0 = (int)std::floor(x0b / 16.0) * 16, bwc = (x1b - bx0) / 16 + 1, bh = ymax - ymin + 1;
+                if ((int64_t)bwc * bh * 16 > FS_STAGE || bx0 < -32768 || ymin < -32768 || ymin > 32767 || bwc > 65535 || bh > 65535) return false;
+                FsJob job;
+                job.bx0 = (short)bx0; job.by0 = (short)ymin; job.bwc = (unsigned short)bwc; job.bh = (unsigned short)bh;
+                job.entry_ofs = (uint32_t)entries.size(); job.cam = (uint32_t)c;
+                const size_t base = entries.size();
+                entries.resize(base + (size_t)FT_THREADS * px, 0u);
+                for (int r = 0; r < FS_ROWS; r++) {
+                    const int y = ty * FS_ROWS + r;
+                    if (y >= H) break;
+                    for (int l = 0; l < 16; l++)
+                        for (int k = 0; k < px; k++) {
+                            const int x = tx * tile_w + l * px + k;
+                            int ax, ay;
+                            if (x >= W || !tap(x, y, ax, ay)) continue;
+                            pairs++;
+                            const uint32_t off = (uint32_t)((ay - ymin) * bwc * 16 + (unit * ax - bx0));
+                            entries[base + (size_t)(r * 16 + l) * px + k] = off | ((uint32_t)(tb[c].sx.row(y)[x] & 31) << 14) | ((uint32_t)(tb[c].sy.row(y)[x] & 31) << 19) |
+                                                                            ((uint32_t)tb[c].wgt.row(y)[x] << 24);
+                        }
+                }
+                jobs.push_back(job);
+            }
+            tile_job_start.push_back((uint32_t)jobs.size());
+        }
+    return true;
+}
 }  // namespace
 }  // namespace ob
 
@@ -238,8 +404,35 @@ struct octvr_fast {
     uint32_t* d_tile_job_start = nullptr; uint8_t* d_job_cam = nullptr; uint32_t* d_job_ofs = nullptr; uint4* d_entries = nullptr;
     int luma_tiles_x = 0, luma_tiles = 0, chroma_tiles_x = 0, tiles = 0;
     int64_t pairs_luma = 0, pairs_chroma = 0, table_bytes = 0;
-    ~octvr_fast() { cudaFree(d_tile_job_start); cudaFree(d_job_cam); cudaFree(d_job_ofs); cudaFree(d_entries); }
+    // staged layout (k_fast_staged, the default); the direct tables above are built only when it does not apply
+    bool staged = false;
+    uint32_t* d_s_tile_job_start = nullptr; FsJob* d_s_jobs = nullptr; uint32_t* d_s_entries = nullptr;
+    int s_luma_tiles_x = 0, s_luma_tiles = 0, s_chroma_tiles_x = 0, s_tiles = 0;
+    void build_direct();
+    ~octvr_fast() { cudaFree(d_tile_job_start); cudaFree(d_job_cam); cudaFree(d_job_ofs); cudaFree(d_entries); cudaFree(d_s_tile_job_start); cudaFree(d_s_jobs); cudaFree(d_s_entries); }
 };
+
+
+void octvr_fast::build_direct()
+{
+    if (d_entries) return;
+    std::vector<uint32_t> tjs{ 0 }, job_ofs;
+    std::vector<uint8_t> job_cam;
+    std::vector<uint4> entries;
+    int64_t pl = 0, pc = 0;
+    pack_plane(full, W, H, 4, 1, in_w, in_h, tjs, job_cam, job_ofs, entries, luma_tiles_x, pl);
+    luma_tiles = (int)tjs.size() - 1;
+    pack_plane(half, W / 2, H / 2, 2, 2, in_w, in_h, tjs, job_cam, job_ofs, entries, chroma_tiles_x, pc);
+    tiles = (int)tjs.size() - 1;
+    if (job_cam.empty()) fail(OCTVR_ERR_INVALID, "FastMapper: no camera contributes to the output");
+    OB_CUDA(cudaSetDevice(device));
+    auto up = [](auto*& d, const auto& v) {
+        OB_CUDA(cudaMalloc(&d, v.size() * sizeof(v[0])));
+        OB_CUDA(cudaMemcpy(d, v.data(), v.size() * sizeof(v[0]), cudaMemcpyHostToDevice));
+    };
+    up(d_tile_job_start, tjs); up(d_job_cam, job_cam); up(d_job_ofs, job_ofs); up(d_entries, entries);
+    if (!staged) { pairs_luma = pl; pairs_chroma = pc; table_bytes = (int64_t)(entries.size() * 16 + job_ofs.size() * 4 + job_cam.size() + tjs.size() * 4); }
+}
 
 extern "C" {
 
@@ -291,22 +484,28 @@ octvr_status octvr_fast_create(const octvr_template* t, const int* in_sizes_wh, 
             }
             f->half[i].wgt = resize_half(f->full[i].wgt);
         }
-        // ---- device tables
-        std::vector<uint32_t> tjs{ 0 }, job_ofs;
-        std::vector<uint8_t> job_cam;
-        std::vector<uint4> entries;
-        pack_plane(f->full, W, H, 4, 1, f->in_w, f->in_h, tjs, job_cam, job_ofs, entries, f->luma_tiles_x, f->pairs_luma);
-        f->luma_tiles = (int)tjs.size() - 1;
-        pack_plane(f->half, W / 2, H / 2, 2, 2, f->in_w, f->in_h, tjs, job_cam, job_ofs, entries, f->chroma_tiles_x, f->pairs_chroma);
-        f->tiles = (int)tjs.size() - 1;
-        if (job_cam.empty()) fail(OCTVR_ERR_INVALID, "FastMapper: no camera contributes to the output");
+        // ---- device tables: staged layout when every footprint fits the stage (OCTVR_FAST=direct forces the direct-gather tables)
         OB_CUDA(cudaSetDevice(device));
         auto up = [](auto*& d, const auto& v) {
-            OB_CUDA(cudaMalloc(&d, v.size() * sizeof(v[0])));
-            OB_CUDA(cudaMemcpy(d, v.data(), v.size() * sizeof(v[0]), cudaMemcpyHostToDevice));
+            OB_CUDA(cudaMalloc(&d, std::max<size_t>(v.size(), 1) * sizeof(v[0])));
+            if (!v.empty()) OB_CUDA(cudaMemcpy(d, v.data(), v.size() * sizeof(v[0]), cudaMemcpyHostToDevice));
         };
-        up(f->d_tile_job_start, tjs); up(f->d_job_cam, job_cam); up(f->d_job_ofs, job_ofs); up(f->d_entries, entries);
-        f->table_bytes = (int64_t)(entries.size() * 16 + job_ofs.size() * 4 + job_cam.size() + tjs.size() * 4);
+        const char* mode = getenv("OCTVR_FAST");
+        if (!(mode && std::string(mode) == "direct")) {
+            std::vector<uint32_t> tjs{ 0 }, entries;
+            std::vector<FsJob> jobs;
+            int64_t pl = 0, pc = 0;
+            bool ok = pack_plane_staged(f->full, W, H, 4, 1, 1, f->in_w, f->in_h, tjs, jobs, entries, f->s_luma_tiles_x, pl);
+            f->s_luma_tiles = (int)tjs.size() - 1;
+            ok = ok && pack_plane_staged(f->half, W / 2, H / 2, 2, 2, 2, f->in_w, f->in_h, tjs, jobs, entries, f->s_chroma_tiles_x, pc);
+            f->s_tiles = (int)tjs.size() - 1;
+            if (ok && !jobs.empty()) {
+                up(f->d_s_tile_job_start, tjs); up(f->d_s_jobs, jobs); up(f->d_s_entries, entries);
+                f->staged = true; f->pairs_luma = pl; f->pairs_chroma = pc;
+                f->table_bytes = (int64_t)(entries.size() * 4 + jobs.size() * sizeof(FsJob) + tjs.size() * 4);
+            }
+        }
+        if (!f->staged) f->build_direct();
         *out = f.release();
     });
 }
@@ -317,17 +516,33 @@ octvr_status octvr_fast_stitch_nv12(octvr_fast* f, const uint8_t* const* d_input
     return guard([&] {
         OB_CHECK(f && d_inputs && pitches && d_output, "null argument");
         OB_CHECK(n_inputs == f->n, "input count");                                   // mapper_fast.cpp:156-160
-        FastParams p;
-        memset(&p, 0, sizeof(p));
+        OB_CHECK(out_pitch >= (size_t)f->W, "output pitch");
+        bool aligned = true;                              // the staged kernel copies 16-byte chunks
         for (int i = 0; i < f->n; i++) {
             OB_CHECK(d_inputs[i] && pitches[i] >= (size_t)f->in_w[i] && (pitches[i] % 2) == 0 && ((uintptr_t)d_inputs[i] % 2) == 0, "input frame");
-            p.cam[i] = FastCam{ d_inputs[i], d_inputs[i] + (size_t)f->in_h[i] * pitches[i], (int)pitches[i], (int)pitches[i], f->in_w[i], f->in_h[i] };
+            aligned = aligned && (pitches[i] % 16) == 0 && ((uintptr_t)d_inputs[i] % 16) == 0;
         }
-        OB_CHECK(out_pitch >= (size_t)f->W, "output pitch");
+        OB_CUDA(cudaSetDevice(f->device));
+        if (f->staged && aligned) {
+            FsParams p;
+            memset(&p, 0, sizeof(p));
+            for (int i = 0; i < f->n; i++)
+                p.cam[i] = FastCam{ d_inputs[i], d_inputs[i] + (size_t)f->in_h[i] * pitches[i], (int)pitches[i], (int)pitches[i], f->in_w[i], f->in_h[i] };
+            p.tile_job_start = f->d_s_tile_job_start; p.jobs = f->d_s_jobs; p.entries = f->d_s_entries;
+            p.out = d_output; p.out_pitch = (int)out_pitch; p.W = f->W; p.H = f->H;
+            p.luma_tiles_x = f->s_luma_tiles_x; p.luma_tiles = f->s_luma_tiles; p.chroma_tiles_x = f->s_chroma_tiles_x;
+            k_fast_staged<<<f->s_tiles, FT_THREADS, 0, (cudaStream_t)stream>>>(p);
+            OB_CUDA(cudaGetLastError());
+            return;
+        }
+        f->build_direct();                                // frames that are not 16-byte aligned: direct-gather tables, built on first use
+        FastParams p;
+        memset(&p, 0, sizeof(p));
+        for (int i = 0; i < f->n; i++)
+            p.cam[i] = FastCam{ d_inputs[i], d_inputs[i] + (size_t)f->in_h[i] * pitches[i], (int)pitches[i], (int)pitches[i], f->in_w[i], f->in_h[i] };
         p.tile_job_start = f->d_tile_job_start; p.job_cam = f->d_job_cam; p.entries = f->d_entries; p.job_entry_ofs = f->d_job_ofs;
         p.out = d_output; p.out_pitch = (int)out_pitch; p.W = f->W; p.H = f->H;
         p.luma_tiles_x = f->luma_tiles_x; p.luma_tiles = f->luma_tiles; p.chroma_tiles_x = f->chroma_tiles_x;
-        OB_CUDA(cudaSetDevice(f->device));
         k_fast_nv12<<<f->tiles, FT_THREADS, 0, (cudaStream_t)stream>>>(p);
         OB_CUDA(cudaGetLastError());
     });

@@ -23,8 +23,13 @@ def _template(g):
     return (W, H), inputs
 
 
+@pytest.mark.parametrize("mode", ["staged", "direct"])
 @pytest.mark.parametrize("rig", ["rig3", "models"])
-def test_fast_mapper_matches_reference_fixture(rig):
+def test_fast_mapper_matches_reference_fixture(rig, mode, monkeypatch):
+    """Two device paths behind octvr_fast_stitch_nv12: k_fast_staged (source footprints copied into shared memory with cp.async;
+    default for 16-byte aligned frames -- rig3) and the direct-gather k_fast_nv12 (OCTVR_FAST=direct, unaligned frames -- the
+    200-pixel-wide frames of the `models` case -- or footprints larger than the stage)."""
+    monkeypatch.setenv("OCTVR_FAST", mode)
     g = np.load(os.path.join(util.GOLD, "fast_%s.npz" % rig))
     (W, H), inputs = _template(g)
     iw, ih = (int(v) for v in g["in_size"])
