@@ -152,19 +152,20 @@ __global__ void __launch_bounds__(FT_THREADS) k_fast_nv12(const __grid_constant_
 // OUTSIDE() rule of the OpenCL kernel), the next job's copy in flight while this job's pixels are gathered.  Entries shrink
 // to 4 bytes: stage offset (14 bits) | fx << 14 | fy << 19 | weight << 24.
 constexpr int FS_ROWS = 16, FS_STAGE = 16384;
-struct FsJob { short bx0, by0; unsigned short bwc, bh; uint32_t entry_ofs; uint32_t cam; };      // entry_ofs in uint32 units
+struct FsJob { short bx0, by0; unsigned short bwc, bh; uint32_t rcp; uint32_t cam; };      // rcp = floor(2^32 / bwc) + 1: c / bwc == __umulhi(c, rcp) for c < 2^16
 static_assert(sizeof(FsJob) == 16, "FsJob");
 struct FsParams {
     FastCam cam[MAX_CAMS];
-    const uint32_t* tile_job_start; const FsJob* jobs; const uint32_t* entries;
+    const uint32_t* tile_job_start; const FsJob* jobs; const uint32_t* entries;      // job j owns 1024 (luma) / 512 (chroma) entries, in job order
     uint8_t* out; int out_pitch, W, H;
     int luma_tiles_x, luma_tiles, chroma_tiles_x;
+    uint32_t luma_jobs;
 };
 __device__ __forceinline__ void fs_issue(const FsJob& job, const uint8_t* __restrict__ plane, int pitch, int wbytes, int h, uint8_t* stage)
 {
     const int n = (int)job.bwc * job.bh;
     for (int c = threadIdx.x; c < n; c += FT_THREADS) {
-        const int r = c / job.bwc, k = c - r * job.bwc;
+        const int r = (int)__umulhi((unsigned)c, job.rcp), k = c - r * job.bwc;
         const int gy = job.by0 + r, gx = job.bx0 + 16 * k;
         int valid = (gy >= 0 && gy < h && gx >= 0) ? min(max(wbytes - gx, 0), 16) : 0;
         const uint8_t* src = valid ? plane + (size_t)gy * pitch + gx : plane;
@@ -173,9 +174,14 @@ __device__ __forceinline__ void fs_issue(const FsJob& job, const uint8_t* __rest
     }
     asm volatile("cp.async.commit_group;" ::: "memory");
 }
+// q = rte(fl32(V * w) / 1024) without the XU pipe (I2F / F2I run at a quarter of the FP32 rate): V < 2^18 and w < 2^8 become
+// floats by the 2^23 bias trick (exact), the product is rounded once (the OpenCL kernel's rounding), the scaling by 2^-10 is
+// exact, and adding 1.5 * 2^23 rounds to nearest even into the low mantissa bits (one FFMA: x * 2^-10 is exact, so the fused
+// rounding is the rounding of the sum).  Returns q + 0x4B400000; the caller subtracts the bias when it accumulates.
+__device__ __forceinline__ float fs_float(uint32_t v) { return __fsub_rn(__uint_as_float(0x4B000000u | v), 8388608.f); }
 __device__ __forceinline__ uint32_t fs_q(int V, float fw)
 {
-    return (uint32_t)__float2int_rn(__fmul_rn(__int2float_rn(V), fw) * 0.0009765625f);
+    return __float_as_uint(__fmaf_rn(__fmul_rn(fs_float((uint32_t)V), fw), 0.0009765625f, 12582912.f)) - 0x4B400000u;
 }
 __global__ void __launch_bounds__(FT_THREADS) k_fast_staged(const __grid_constant__ FsParams p)
 {
@@ -200,7 +206,7 @@ __global__ void __launch_bounds__(FT_THREADS) k_fast_staged(const __grid_constan
         const uint8_t* st = s_stage[buf];
         const int sp = (int)cur.bwc * 16;
         if (luma) {
-            const uint4 e4 = __ldg(reinterpret_cast<const uint4*>(p.entries + cur.entry_ofs) + tid);
+            const uint4 e4 = __ldg(reinterpret_cast<const uint4*>(p.entries + (size_t)j * 1024) + tid);
             if (j + 1 < j1) asm volatile("cp.async.wait_group 1;" ::: "memory"); else asm volatile("cp.async.wait_group 0;" ::: "memory");
             __syncthreads();
             const uint32_t e[4] = { e4.x, e4.y, e4.z, e4.w };
@@ -210,16 +216,16 @@ __global__ void __launch_bounds__(FT_THREADS) k_fast_staged(const __grid_constan
                 const int off = e[k] & 0x3FFF, fx = (e[k] >> 14) & 31, fy = (e[k] >> 19) & 31;
                 const int a = st[off], b = st[off + 1], c2 = st[off + sp], d = st[off + sp + 1];
                 const int V = (a * (32 - fx) + b * fx) * (32 - fy) + (c2 * (32 - fx) + d * fx) * fy;
-                acc[k] += fs_q(V, (float)wgt);         // weight 0 (no contribution): q = 0 whatever the taps are
+                acc[k] += fs_q(V, fs_float(wgt));       // weight 0 (no contribution): q = 0 whatever the taps are
             }
         } else {
-            const uint2 e2 = __ldg(reinterpret_cast<const uint2*>(p.entries + cur.entry_ofs) + tid);
+            const uint2 e2 = __ldg(reinterpret_cast<const uint2*>(p.entries + (size_t)p.luma_jobs * 1024 + (size_t)(j - p.luma_jobs) * 512) + tid);
             if (j + 1 < j1) asm volatile("cp.async.wait_group 1;" ::: "memory"); else asm volatile("cp.async.wait_group 0;" ::: "memory");
             __syncthreads();
             const uint32_t e[2] = { e2.x, e2.y };
             #pragma unroll
             for (int k = 0; k < 2; k++) {
-                const float fw = (float)(e[k] >> 24);
+                const float fw = fs_float(e[k] >> 24);
                 const int off = e[k] & 0x3FFF, fx = (e[k] >> 14) & 31, fy = (e[k] >> 19) & 31;
                 const uint32_t a = *reinterpret_cast<const uint16_t*>(st + off), b = *reinterpret_cast<const uint16_t*>(st + off + 2);
                 const uint32_t c2 = *reinterpret_cast<const uint16_t*>(st + off + sp), d = *reinterpret_cast<const uint16_t*>(st + off + sp + 2);
@@ -364,11 +370,11 @@ bool pack_plane_staged(const std::vector<FastTable>& tb, int W, int H, int px, i
                     }
                 if (xmin > xmax) continue;
                 const int x0b = unit * xmin, x1b = unit * xmax + unit - 1;               // byte range of the taps in a source row
-                const int bx0 = (int)std::floor(x0b / 16.0) * 16, bwc = (x1b - bx0) / 16 + 1, bh = ymax - ymin + 1;
+                const int bx0 = (int)std::floor(x0b / 16.0) * 16, bwc = std::max(2, (x1b - bx0) / 16 + 1), bh = ymax - ymin + 1;      // >= 2: rcp below must fit 32 bits
                 if ((int64_t)bwc * bh * 16 > FS_STAGE || bx0 < -32768 || ymin < -32768 || ymin > 32767 || bwc > 65535 || bh > 65535) return false;
                 FsJob job;
                 job.bx0 = (short)bx0; job.by0 = (short)ymin; job.bwc = (unsigned short)bwc; job.bh = (unsigned short)bh;
-                job.entry_ofs = (uint32_t)entries.size(); job.cam = (uint32_t)c;
+                job.rcp = (uint32_t)(0x100000000ull / (uint64_t)bwc) + 1u; job.cam = (uint32_t)c;
                 const size_t base = entries.size();
                 entries.resize(base + (size_t)FT_THREADS * px, 0u);
                 for (int r = 0; r < FS_ROWS; r++) {
@@ -407,7 +413,7 @@ struct octvr_fast {
     // staged layout (k_fast_staged, the default); the direct tables above are built only when it does not apply
     bool staged = false;
     uint32_t* d_s_tile_job_start = nullptr; FsJob* d_s_jobs = nullptr; uint32_t* d_s_entries = nullptr;
-    int s_luma_tiles_x = 0, s_luma_tiles = 0, s_chroma_tiles_x = 0, s_tiles = 0;
+    int s_luma_tiles_x = 0, s_luma_tiles = 0, s_chroma_tiles_x = 0, s_tiles = 0; uint32_t s_luma_jobs = 0;
     void build_direct();
     ~octvr_fast() { cudaFree(d_tile_job_start); cudaFree(d_job_cam); cudaFree(d_job_ofs); cudaFree(d_entries); cudaFree(d_s_tile_job_start); cudaFree(d_s_jobs); cudaFree(d_s_entries); }
 };
@@ -496,7 +502,7 @@ octvr_status octvr_fast_create(const octvr_template* t, const int* in_sizes_wh, 
             std::vector<FsJob> jobs;
             int64_t pl = 0, pc = 0;
             bool ok = pack_plane_staged(f->full, W, H, 4, 1, 1, f->in_w, f->in_h, tjs, jobs, entries, f->s_luma_tiles_x, pl);
-            f->s_luma_tiles = (int)tjs.size() - 1;
+            f->s_luma_tiles = (int)tjs.size() - 1; f->s_luma_jobs = (uint32_t)jobs.size();
             ok = ok && pack_plane_staged(f->half, W / 2, H / 2, 2, 2, 2, f->in_w, f->in_h, tjs, jobs, entries, f->s_chroma_tiles_x, pc);
             f->s_tiles = (int)tjs.size() - 1;
             if (ok && !jobs.empty()) {
@@ -530,7 +536,7 @@ octvr_status octvr_fast_stitch_nv12(octvr_fast* f, const uint8_t* const* d_input
                 p.cam[i] = FastCam{ d_inputs[i], d_inputs[i] + (size_t)f->in_h[i] * pitches[i], (int)pitches[i], (int)pitches[i], f->in_w[i], f->in_h[i] };
             p.tile_job_start = f->d_s_tile_job_start; p.jobs = f->d_s_jobs; p.entries = f->d_s_entries;
             p.out = d_output; p.out_pitch = (int)out_pitch; p.W = f->W; p.H = f->H;
-            p.luma_tiles_x = f->s_luma_tiles_x; p.luma_tiles = f->s_luma_tiles; p.chroma_tiles_x = f->s_chroma_tiles_x;
+            p.luma_tiles_x = f->s_luma_tiles_x; p.luma_tiles = f->s_luma_tiles; p.chroma_tiles_x = f->s_chroma_tiles_x; p.luma_jobs = f->s_luma_jobs;
             k_fast_staged<<<f->s_tiles, FT_THREADS, 0, (cudaStream_t)stream>>>(p);
             OB_CUDA(cudaGetLastError());
             return;
