@@ -117,14 +117,14 @@ def blend_kernel_name():
     return {"fused": "k_stitch_fused", "direct": "k_blend", "staged": "k_blend_staged"}.get(os.environ.get("OCTVR_BLEND", ""), "k_blend_ring")
 
 
-def ncu_traffic(workload, blend):
+def ncu_traffic(workload, blend, kernel=None):
     """dram__bytes_read.sum + dram__bytes_write.sum of the dominant kernel, per launch.  NOT measured in this run (ncu is
     never active while timing): read from the committed ncu --set full capture of this workload
     (profiles/r02_traffic.json, else r01_traffic.json; written from the .ncu-rep)."""
     for name in ("r02_traffic.json", "r01_traffic.json"):
         try:
             t = json.load(open(os.path.join(ROOT, "profiles", name)))
-            v = t.get("%s:%s" % (workload, blend_kernel_name() if blend <= 0 else "multiband"))
+            v = t.get("%s:%s" % (workload, kernel or (blend_kernel_name() if blend <= 0 else "multiband")))
             if v is not None:
                 return v
         except Exception:                    # noqa: BLE001
@@ -377,6 +377,7 @@ def run_fast(args, sub=False):
     B = I + 8 * (info["pairs_luma"] + info["pairs_chroma"]) + O_
     ms_per_step = ms / args.steps
     ach = B / (ms_per_step * 1e-3) / 1e9
+    fast_kernel = "k_fast_nv12" if os.environ.get("OCTVR_FAST", "") == "direct" else "k_fast_staged"
     return {
         "metric": "equirect output Mpix/s", "value": round(world * W * H / (ms_per_step * 1e-3) / 1e6, 1), "unit": "Mpix/s", "n_gpus": world,
         "steps": args.steps, "warmup": max(3, args.warmup), "ms_per_step": round(ms_per_step, 5), "higher_is_better": True, "scaling": "weak",
@@ -386,8 +387,9 @@ def run_fast(args, sub=False):
                    "pairs_luma": info["pairs_luma"], "pairs_chroma": info["pairs_chroma"], "sharding": "one stream per GPU, no data-path collective",
                    "template_build_s": round(t_tmpl, 2), "mapper_build_s": round(t_map, 2)},
         "alg_bytes_per_frame": int(B),
-        "roofline": {"bound": "hbm", "kernel": "k_fast_nv12", "achieved": round(ach, 1), "peak": peak, "peak_source": how, "unit": "GB/s",
-                     "frac": round(ach / peak, 4), "traffic": ncu_traffic("fast", 0) if ncu_traffic("fast", 0) else None,
+        "roofline": {"bound": "hbm", "kernel": fast_kernel, "achieved": round(ach, 1), "peak": peak, "peak_source": how, "unit": "GB/s",
+                     "frac": round(ach / peak, 4), "traffic": ncu_traffic("fast", 0, fast_kernel),
+                     "traffic_source": "committed ncu --set full capture under profiles/ (not measured in this run)",
                      "alg_bytes_per_launch": int(B), "ms_per_launch": round(ms_per_step, 5)},
         "gpu_launches": args.steps, "clocks": clocks,
     }
