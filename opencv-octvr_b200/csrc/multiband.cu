@@ -88,7 +88,7 @@ struct Multiband {
     int max_bw = 0, max_bh = 0;
     int launches = 0;
     // the small-level chain (down 2.., band 2.., collapse ..3) runs on a side stream next to the level-1 band
-    cudaStream_t side = nullptr; cudaEvent_t ev_fork = nullptr, ev_join = nullptr; bool fork = false, tails = false;
+    cudaStream_t side = nullptr; cudaEvent_t ev_fork = nullptr, ev_join = nullptr; bool fork = false;
 };
 
 // ------------------------------------------------------------------------------------------------ device
@@ -99,10 +99,8 @@ __device__ __forceinline__ int refl101(int p, int len)
     return p;
 }
 __device__ __forceinline__ int sat16(int v) { return min(max(v, -32768), 32767); }
-// COH = true: data written earlier in the SAME launch by other CTAs (the cluster tail kernels): L2 loads (ld.global.cg) instead
-// of the read-only path
-template <bool COH = false> __device__ __forceinline__ int3 ld3(const short4* s, int idx) { const short4 v = COH ? __ldcg(s + idx) : __ldg(s + idx); return make_int3(v.x, v.y, v.z); }
-template <bool COH = false> __device__ __forceinline__ int3 ld3(const uint32_t* s, int idx) { const uint32_t v = __ldg(s + idx); return make_int3(v & 255u, (v >> 8) & 255u, (v >> 16) & 255u); }
+__device__ __forceinline__ int3 ld3(const short4* s, int idx) { const short4 v = __ldg(s + idx); return make_int3(v.x, v.y, v.z); }
+__device__ __forceinline__ int3 ld3(const uint32_t* s, int idx) { const uint32_t v = __ldg(s + idx); return make_int3(v & 255u, (v >> 8) & 255u, (v >> 16) & 255u); }
 
 // ---- pyrUp of FOUR horizontally adjacent pixels by one thread ----
 // pyrUp_ (pyramids.cpp:967-1060) is a separable [1 6 1 | 4 4] filter whose border cases are index extensions: -1 maps to
@@ -111,27 +109,27 @@ template <bool COH = false> __device__ __forceinline__ int3 ld3(const uint32_t* 
 __device__ __forceinline__ int up_idx(int k, int len) { return k < 0 ? (len > 1 ? 1 : 0) : (k >= len ? len - 1 : k); }
 __device__ __forceinline__ int3 add3(int3 a, int3 b) { return make_int3(a.x + b.x, a.y + b.y, a.z + b.z); }
 __device__ __forceinline__ int3 mul3(int3 a, int k) { return make_int3(a.x * k, a.y * k, a.z * k); }
-template <bool COH = false, class T> __device__ __forceinline__ void pyrup_row4(const T* __restrict__ s, int sw, int r, int x0, int3 (&h)[4])
+template <class T> __device__ __forceinline__ void pyrup_row4(const T* __restrict__ s, int sw, int r, int x0, int3 (&h)[4])
 {
     const T* row = s + (size_t)r * sw;
     const int k = x0 >> 1;
     if ((x0 & 1) == 0) {
-        const int3 a = ld3<COH>(row, up_idx(k - 1, sw)), b = ld3<COH>(row, up_idx(k, sw)), c = ld3<COH>(row, up_idx(k + 1, sw)), d = ld3<COH>(row, up_idx(k + 2, sw));
+        const int3 a = ld3(row, up_idx(k - 1, sw)), b = ld3(row, up_idx(k, sw)), c = ld3(row, up_idx(k + 1, sw)), d = ld3(row, up_idx(k + 2, sw));
         h[0] = add3(add3(a, mul3(b, 6)), c); h[1] = mul3(add3(b, c), 4); h[2] = add3(add3(b, mul3(c, 6)), d); h[3] = mul3(add3(c, d), 4);
     } else {
-        const int3 a = ld3<COH>(row, up_idx(k, sw)), b = ld3<COH>(row, up_idx(k + 1, sw)), c = ld3<COH>(row, up_idx(k + 2, sw)), d = ld3<COH>(row, up_idx(k + 3, sw));
+        const int3 a = ld3(row, up_idx(k, sw)), b = ld3(row, up_idx(k + 1, sw)), c = ld3(row, up_idx(k + 2, sw)), d = ld3(row, up_idx(k + 3, sw));
         h[0] = mul3(add3(a, b), 4); h[1] = add3(add3(a, mul3(b, 6)), c); h[2] = mul3(add3(b, c), 4); h[3] = add3(add3(b, mul3(c, 6)), d);
     }
 }
-template <bool COH = false, class T> __device__ __forceinline__ void pyrup4(const T* __restrict__ s, int sw, int sh, int x0, int y, int3 (&out)[4])
+template <class T> __device__ __forceinline__ void pyrup4(const T* __restrict__ s, int sw, int sh, int x0, int y, int3 (&out)[4])
 {
     const int ky = y >> 1;
     int3 h1[4], h2[4];
-    pyrup_row4<COH>(s, sw, up_idx(ky, sh), x0, h1);
-    pyrup_row4<COH>(s, sw, up_idx(ky + 1, sh), x0, h2);
+    pyrup_row4(s, sw, up_idx(ky, sh), x0, h1);
+    pyrup_row4(s, sw, up_idx(ky + 1, sh), x0, h2);
     if ((y & 1) == 0) {
         int3 h0[4];
-        pyrup_row4<COH>(s, sw, up_idx(ky - 1, sh), x0, h0);
+        pyrup_row4(s, sw, up_idx(ky - 1, sh), x0, h0);
         #pragma unroll
         for (int q = 0; q < 4; q++) out[q] = add3(add3(h0[q], mul3(h1[q], 6)), h2[q]);
     } else {
@@ -148,10 +146,7 @@ template <bool COH = false, class T> __device__ __forceinline__ void pyrup4(cons
 // Gaussian levels of 8-bit images stay within [0, 255] (pyrDown is a rounded convex combination), so a camera's short4
 // {R, G, B, 0} is filtered as two words of two 16-bit lanes: the largest intermediate is 64 * 255 + 32 < 2^16, no lane
 // carries into its neighbour, no unpacking, and (v + 32) >> 6 <= 255 needs no saturation.  Same integers as pyrup4.
-template <bool COH = false> __device__ __forceinline__ uint2 ldp(const short4* __restrict__ s, int idx)
-{
-    return COH ? __ldcg(reinterpret_cast<const uint2*>(s) + idx) : __ldg(reinterpret_cast<const uint2*>(s) + idx);
-}
+__device__ __forceinline__ uint2 ldp(const short4* __restrict__ s, int idx) { return __ldg(reinterpret_cast<const uint2*>(s) + idx); }
 __device__ __forceinline__ uint2 p_add(uint2 a, uint2 b) { return make_uint2(a.x + b.x, a.y + b.y); }
 __device__ __forceinline__ uint2 p_161(uint2 a, uint2 b, uint2 c) { return make_uint2(a.x + 6u * b.x + c.x, a.y + 6u * b.y + c.y); }
 __device__ __forceinline__ uint2 p_44(uint2 a, uint2 b) { return make_uint2(4u * (a.x + b.x), 4u * (a.y + b.y)); }
@@ -202,32 +197,32 @@ __device__ __forceinline__ void lap_weight_acc(int gr, int gg, int gb, uint2 up,
 // integers as pyrup4<short4>.  v + 512 = (v ^ 0x200) & 0x3FF for a 16-bit two's complement v in range.  Whether a level
 // is in range is recorded by the kernels that write it (MbParams::wide); out-of-range levels (possible in principle:
 // |collapsed value| <= 255 * levels) take the 32-bit path.
-template <bool COH = false> __device__ __forceinline__ uint2 ldp_biased(const short4* __restrict__ s, int idx)
+__device__ __forceinline__ uint2 ldp_biased(const short4* __restrict__ s, int idx)
 {
-    const uint2 v = ldp<COH>(s, idx);
+    const uint2 v = ldp(s, idx);
     return make_uint2((v.x ^ 0x02000200u) & 0x03FF03FFu, (v.y ^ 0x00000200u) & 0x000003FFu);
 }
-template <bool COH = false> __device__ __forceinline__ void pyrup_row4_biased(const short4* __restrict__ s, int sw, int r, int x0, uint2 (&h)[4])
+__device__ __forceinline__ void pyrup_row4_biased(const short4* __restrict__ s, int sw, int r, int x0, uint2 (&h)[4])
 {
     const short4* row = s + (size_t)r * sw;
     const int k = x0 >> 1;
     if ((x0 & 1) == 0) {
-        const uint2 a = ldp_biased<COH>(row, up_idx(k - 1, sw)), b = ldp_biased<COH>(row, up_idx(k, sw)), c = ldp_biased<COH>(row, up_idx(k + 1, sw)), d = ldp_biased<COH>(row, up_idx(k + 2, sw));
+        const uint2 a = ldp_biased(row, up_idx(k - 1, sw)), b = ldp_biased(row, up_idx(k, sw)), c = ldp_biased(row, up_idx(k + 1, sw)), d = ldp_biased(row, up_idx(k + 2, sw));
         h[0] = p_161(a, b, c); h[1] = p_44(b, c); h[2] = p_161(b, c, d); h[3] = p_44(c, d);
     } else {
-        const uint2 a = ldp_biased<COH>(row, up_idx(k, sw)), b = ldp_biased<COH>(row, up_idx(k + 1, sw)), c = ldp_biased<COH>(row, up_idx(k + 2, sw)), d = ldp_biased<COH>(row, up_idx(k + 3, sw));
+        const uint2 a = ldp_biased(row, up_idx(k, sw)), b = ldp_biased(row, up_idx(k + 1, sw)), c = ldp_biased(row, up_idx(k + 2, sw)), d = ldp_biased(row, up_idx(k + 3, sw));
         h[0] = p_44(a, b); h[1] = p_161(a, b, c); h[2] = p_44(b, c); h[3] = p_161(b, c, d);
     }
 }
-template <bool COH = false> __device__ __forceinline__ void pyrup4_narrow(const short4* __restrict__ s, int sw, int sh, int x0, int y, int3 (&out)[4])
+__device__ __forceinline__ void pyrup4_narrow(const short4* __restrict__ s, int sw, int sh, int x0, int y, int3 (&out)[4])
 {
     const int ky = y >> 1;
     uint2 h1[4], h2[4], o[4];
-    pyrup_row4_biased<COH>(s, sw, up_idx(ky, sh), x0, h1);
-    pyrup_row4_biased<COH>(s, sw, up_idx(ky + 1, sh), x0, h2);
+    pyrup_row4_biased(s, sw, up_idx(ky, sh), x0, h1);
+    pyrup_row4_biased(s, sw, up_idx(ky + 1, sh), x0, h2);
     if ((y & 1) == 0) {
         uint2 h0[4];
-        pyrup_row4_biased<COH>(s, sw, up_idx(ky - 1, sh), x0, h0);
+        pyrup_row4_biased(s, sw, up_idx(ky - 1, sh), x0, h0);
         #pragma unroll
         for (int q = 0; q < 4; q++) o[q] = p_161(h0[q], h1[q], h2[q]);
     } else {
@@ -241,10 +236,10 @@ template <bool COH = false> __device__ __forceinline__ void pyrup4_narrow(const 
     }
 }
 // pyrUp of a blended level: packed when the level is known to be narrow, 32-bit otherwise (uniform over the grid)
-template <bool COH = false> __device__ __forceinline__ void pyrup4_dst(const MbParams& p, int l, int x0, int y, int3 (&out)[4])
+__device__ __forceinline__ void pyrup4_dst(const MbParams& p, int l, int x0, int y, int3 (&out)[4])
 {
-    if ((COH ? __ldcg(p.wide + l) : __ldg(p.wide + l)) == 0) pyrup4_narrow<COH>(p.dst + p.off_d[l], p.lw[l], p.lh[l], x0, y, out);
-    else pyrup4<COH>(p.dst + p.off_d[l], p.lw[l], p.lh[l], x0, y, out);
+    if (__ldg(p.wide + l) == 0) pyrup4_narrow(p.dst + p.off_d[l], p.lw[l], p.lh[l], x0, y, out);
+    else pyrup4(p.dst + p.off_d[l], p.lw[l], p.lh[l], x0, y, out);
 }
 __device__ __forceinline__ void note_range(const MbParams& p, int l, int r, int g, int b)
 {
@@ -407,7 +402,6 @@ __global__ void __launch_bounds__(THREADS) k_mb_warp_staged(const __grid_constan
 // Levels >= 1 of a CAMERA pyramid: values within [0, 255] stored as short4 {R, G, B, 0}, so the words {R | G << 16, B} are
 // filtered as packed 16-bit lanes (5 x 5 sum <= 256 * 255 < 2^16) with 16-byte loads in the interior, rows fetched in
 // groups ahead of their use and no early exit (see mb_down_strip_u8).  The same integers as the 5 x 5 form.
-template <bool COH = false>
 __device__ __forceinline__ void mb_down_strip_p16(const short4* __restrict__ src, short4* __restrict__ dst, int sw, int sh, int dw, int dh, int x, int y0)
 {
     const bool interior = 2 * x - 2 >= 0 && 2 * x + 2 < sw;
@@ -427,13 +421,12 @@ __device__ __forceinline__ void mb_down_strip_p16(const short4* __restrict__ src
             if (r >= 11) break;
             const short4* row = src + (size_t)(inner_rows ? 2 * y0 - 2 + r : refl101(2 * y0 - 2 + r, sh)) * sw;
             if (interior) {
-                const uint4 ab = COH ? __ldcg(reinterpret_cast<const uint4*>(row + 2 * x - 2)) : __ldg(reinterpret_cast<const uint4*>(row + 2 * x - 2));
-                const uint4 cd = COH ? __ldcg(reinterpret_cast<const uint4*>(row + 2 * x)) : __ldg(reinterpret_cast<const uint4*>(row + 2 * x));
+                const uint4 ab = __ldg(reinterpret_cast<const uint4*>(row + 2 * x - 2)), cd = __ldg(reinterpret_cast<const uint4*>(row + 2 * x));
                 P[i][0] = make_uint2(ab.x, ab.y); P[i][1] = make_uint2(ab.z, ab.w); P[i][2] = make_uint2(cd.x, cd.y); P[i][3] = make_uint2(cd.z, cd.w);
-                P[i][4] = ldp<COH>(row, 2 * x + 2);
+                P[i][4] = ldp(row, 2 * x + 2);
             } else {
                 #pragma unroll
-                for (int k = 0; k < 5; k++) P[i][k] = ldp<COH>(row, xi[k]);
+                for (int k = 0; k < 5; k++) P[i][k] = ldp(row, xi[k]);
             }
         }
         #pragma unroll
@@ -615,56 +608,6 @@ __global__ void __launch_bounds__(256) k_mb_collapse(const __grid_constant__ MbP
         const int r = sat16(up[q].x + cur.x), g = sat16(up[q].y + cur.y), b = sat16(up[q].z + cur.z);
         note_range(p, l - 1, r, g, b);
         p.dst[di] = make_short4((short)r, (short)g, (short)b, 0);
-    }
-}
-
-
-// ---- the small levels in two cluster kernels --------------------------------------------------------------------------------
-// Levels >= 2 are a chain of launches that are each too small to fill the GPU (a few microseconds of dependent loads plus the
-// launch itself).  k_mb_down_tail does pyrDown levels first .. nb - 1 of every camera in ONE launch: a cluster of 8 CTAs per
-// camera walks the levels with a cluster barrier between them (a level fits the cluster: <= 1/16 of the level-0 rectangle);
-// k_mb_collapse_tail does the collapse steps nb .. 3 of the blended pyramid the same way with one cluster.  Data written
-// earlier in the launch is read with L2 loads (COH).
-constexpr int MB_TAIL_CTAS = 8, MB_TAIL_THREADS = 512;
-__device__ __forceinline__ void mb_cluster_sync()
-{
-    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
-}
-__global__ void __launch_bounds__(MB_TAIL_THREADS) k_mb_down_tail(const __grid_constant__ MbParams p, const int first)
-{
-    const MbCam& cam = p.cam[blockIdx.x / MB_TAIL_CTAS];
-    const int rank = blockIdx.x % MB_TAIL_CTAS;
-    for (int l = first; l < p.nb; l++) {
-        const int sw = cam.bw >> l, sh = cam.bh >> l, dw = sw >> 1, dh = sh >> 1;
-        const int strips = (dh + 3) / 4, items = dw * strips;
-        for (int it = rank * MB_TAIL_THREADS + threadIdx.x; it < items; it += MB_TAIL_CTAS * MB_TAIL_THREADS) {
-            const int sy = it / dw, x = it - sy * dw;
-            if (l == first) mb_down_strip_p16<false>(p.g + cam.off_g[l], p.g + cam.off_g[l + 1], sw, sh, dw, dh, x, sy * 4);
-            else mb_down_strip_p16<true>(p.g + cam.off_g[l], p.g + cam.off_g[l + 1], sw, sh, dw, dh, x, sy * 4);
-        }
-        if (l + 1 < p.nb) mb_cluster_sync();
-    }
-}
-__global__ void __launch_bounds__(MB_TAIL_THREADS) k_mb_collapse_tail(const __grid_constant__ MbParams p, const int last)
-{
-    for (int l = p.nb; l >= last; l--) {                            // dst_{l-1} = sat(pyrUp(dst_l) + dst_{l-1})
-        const int w = p.lw[l - 1], h = p.lh[l - 1], gw = (w + 3) / 4, items = gw * h;
-        for (int it = blockIdx.x * MB_TAIL_THREADS + threadIdx.x; it < items; it += MB_TAIL_CTAS * MB_TAIL_THREADS) {
-            const int Y = it / gw, X0 = (it - Y * gw) * 4;
-            short4 curv[4];
-            #pragma unroll
-            for (int q = 0; q < 4; q++) curv[q] = X0 + q < w ? __ldcg(p.dst + p.off_d[l - 1] + (size_t)Y * w + X0 + q) : make_short4(0, 0, 0, 0);
-            int3 up[4];
-            pyrup4_dst<true>(p, l, X0, Y, up);
-            #pragma unroll
-            for (int q = 0; q < 4; q++) {
-                if (X0 + q >= w) break;
-                const int r = sat16(up[q].x + curv[q].x), g = sat16(up[q].y + curv[q].y), b = sat16(up[q].z + curv[q].z);
-                note_range(p, l - 1, r, g, b);
-                p.dst[p.off_d[l - 1] + (size_t)Y * w + X0 + q] = make_short4((short)r, (short)g, (short)b, 0);
-            }
-        }
-        if (l > last) mb_cluster_sync();
     }
 }
 
@@ -1438,8 +1381,6 @@ Multiband* multiband_create(octvr_mapper& m, const octvr_template& t,
     {   // side stream for the small-level chain (OCTVR_MB_FORK=0: everything on the caller's stream)
         const char* e = getenv("OCTVR_MB_FORK");
         mb->fork = !(e && atoi(e) == 0);
-        const char* et = getenv("OCTVR_MB_TAIL");
-        mb->tails = mb->fork && !(et && atoi(et) == 0);
         if (mb->fork) {
             int lo = 0, hi = 0;
             OB_CUDA(cudaDeviceGetStreamPriorityRange(&lo, &hi));
@@ -1450,8 +1391,7 @@ Multiband* multiband_create(octvr_mapper& m, const octvr_template& t,
     }
     p.coords = mb->d_coords; p.g0 = mb->d_g0; p.g = mb->d_g; p.w = mb->d_w; p.dst = mb->d_dst; p.dstw = mb->d_dstw;
     for (int i = 0; i < n; i++) { p.rgbx[i] = m.d_rgbx[i]; p.src_pitch[i] = m.in_w[i]; }
-    mb->launches = (mb->n_wjobs ? (mb->n_wsmall ? 1 : 0) + (mb->n_wjobs > mb->n_wsmall ? 1 : 0) : 1) + nb + (nb >= 1 ? 1 : 0) + (mb->fork && nb >= 3 ? 1 : 0) + std::max(0, nb - 1) + 1
-                   - (mb->tails && nb >= 3 ? (nb - 2 - 1) + (nb - 2 - 1) : 0);      // the two cluster kernels replace nb - 2 launches each
+    mb->launches = (mb->n_wjobs ? (mb->n_wsmall ? 1 : 0) + (mb->n_wjobs > mb->n_wsmall ? 1 : 0) : 1) + nb + (nb >= 1 ? 1 : 0) + (mb->fork && nb >= 3 ? 1 : 0) + std::max(0, nb - 1) + 1;
     return mb.release();
 }
 
@@ -1490,23 +1430,9 @@ void multiband_stitch(octvr_mapper& m, const octvr_frame* out, cudaStream_t s)
             down(0, s); down(1, s);
             cudaEventRecord(mb.ev_fork, s);
             cudaStreamWaitEvent(mb.side, mb.ev_fork, 0);
-            if (mb.tails) {                             // levels 2 .. nb - 1 / collapse steps nb .. 3 as one cluster launch each
-                cudaLaunchConfig_t cfg;
-                memset(&cfg, 0, sizeof(cfg));
-                cudaLaunchAttribute at[1];
-                at[0].id = cudaLaunchAttributeClusterDimension;
-                at[0].val.clusterDim.x = MB_TAIL_CTAS; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
-                cfg.blockDim = dim3(MB_TAIL_THREADS); cfg.stream = mb.side; cfg.attrs = at; cfg.numAttrs = 1;
-                cfg.gridDim = dim3(n * MB_TAIL_CTAS);
-                cudaLaunchKernelEx(&cfg, k_mb_down_tail, p, 2);
-                band(2, nb, mb.side);
-                cfg.gridDim = dim3(MB_TAIL_CTAS);
-                cudaLaunchKernelEx(&cfg, k_mb_collapse_tail, p, 3);
-            } else {
-                for (int l = 2; l < nb; l++) down(l, mb.side);
-                band(2, nb, mb.side);
-                for (int l = nb; l >= 3; l--) collapse(l, mb.side);
-            }
+            for (int l = 2; l < nb; l++) down(l, mb.side);
+            band(2, nb, mb.side);
+            for (int l = nb; l >= 3; l--) collapse(l, mb.side);
             cudaEventRecord(mb.ev_join, mb.side);
             band(1, 1, s);
             cudaStreamWaitEvent(s, mb.ev_join, 0);
