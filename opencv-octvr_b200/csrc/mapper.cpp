@@ -288,6 +288,10 @@ static void build_mapper(octvr_mapper& m, const octvr_template& t, const int* in
     OB_CHECK(n_in == n + n_ov, "in_sizes must list every input and overlay");
     if (n == 1) { enable_gain = false; blend = 0; }        // mapper.cpp:78-82
     m.n = n; m.n_ov = n_ov; m.out_w = t.out_w; m.out_h = t.out_h; m.blend = blend; m.gain = enable_gain;
+    // Pixel-coordinate convention.  Default: source pixel index = u * W, as cv::remap on map * W (template.cpp:174-176) and
+    // every CPU path of the reference.  OCTVR_TEXEL_CENTER=1: u * W - 0.5, where the reference's CUDA Mapper samples (tex2D with
+    // normalised coordinates and linear filtering) -- for templates calibrated against that path.
+    if (const char* e = getenv("OCTVR_TEXEL_CENTER")) m.texel_shift = atoi(e) != 0 ? 0.5f : 0.f;
     // scaled_output_size = scale_output.area() == 0 ? mt.out_size : scale_output (mapper.cpp:68)
     const bool scaled = scale_w > 0 && scale_h > 0 && (scale_w != t.out_w || scale_h != t.out_h);
     m.scaled_w = scaled ? scale_w : t.out_w; m.scaled_h = scaled ? scale_h : t.out_h;
@@ -351,7 +355,7 @@ static void build_mapper(octvr_mapper& m, const octvr_template& t, const int* in
     bool host_xy = false;
     auto ensure_host_xy = [&]() {
         if (host_xy) return;
-        for (int i = 0; i < n; i++) quantise_map(t.inputs[i].map1, t.inputs[i].map2, m.in_w[i], m.in_h[i], sx[i], sy[i]);
+        for (int i = 0; i < n; i++) quantise_map(t.inputs[i].map1, t.inputs[i].map2, m.in_w[i], m.in_h[i], sx[i], sy[i], m.texel_shift);
         host_xy = true;
         tr.lap("quantise_map (host)");
     };
@@ -359,7 +363,8 @@ static void build_mapper(octvr_mapper& m, const octvr_template& t, const int* in
     auto fixed_at = [&](int i, int lx, int ly, int32_t& fsx, int32_t& fsy) {
         if (host_xy && !sx[i].empty()) { fsx = sx[i].row(ly)[lx]; fsy = sy[i].row(ly)[lx]; return; }
         const float fw = (float)(double)m.in_w[i], fh = (float)(double)m.in_h[i];      // quantise_map, one pixel
-        const float px = t.inputs[i].map1.row(ly)[lx] * fw + 0.f, py = t.inputs[i].map2.row(ly)[lx] * fh + 0.f;
+        float px = t.inputs[i].map1.row(ly)[lx] * fw + 0.f, py = t.inputs[i].map2.row(ly)[lx] * fh + 0.f;
+        if (m.texel_shift != 0.f) { px = px - m.texel_shift; py = py - m.texel_shift; }
         fsx = (int32_t)lrintf(px * 32.f); fsy = (int32_t)lrintf(py * 32.f);
     };
 
@@ -389,7 +394,7 @@ static void build_mapper(octvr_mapper& m, const octvr_template& t, const int* in
     for (int k = 0; k < n_ov; k++) {
         const TInput& in = t.overlays[k];
         Img<int32_t> ox, oy;
-        quantise_map(in.map1, in.map2, m.in_w[n + k], m.in_h[n + k], ox, oy);
+        quantise_map(in.map1, in.map2, m.in_w[n + k], m.in_h[n + k], ox, oy, m.texel_shift);
         std::vector<uint2> ce((size_t)in.roi.w * in.roi.h);
         for (int y = 0; y < in.roi.h; y++)
             for (int x = 0; x < in.roi.w; x++)

@@ -20,6 +20,7 @@ struct octvr_mapper {
     // tile-compacted tables (feather / no-blend)
     int tiles_x = 0, tiles_y = 0;
     int band_y0 = 0, band_y1 = 0;       // output rows this mapper produces (multi-GPU row-band mode); default: all rows
+    float texel_shift = 0.f;            // 0.5 with OCTVR_TEXEL_CENTER=1: sample at u * W - 0.5 (the reference's texture path) instead of u * W
     int band_x0 = 0, band_x1 = 0;       // output columns this mapper produces (column-band mode, multiband only); default: all columns
     std::vector<int> src_row0, src_row1; // per camera: the source rows [row0, row1) some table entry of this mapper reads (a row-band mapper
                                         // converts only those to RGBX); default: all rows

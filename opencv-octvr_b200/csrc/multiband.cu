@@ -752,7 +752,7 @@ struct MbpCam {
     MbGeom g;
     float* wfull[MB_MAX_LEVELS];      // weight pyramid of the FULL rectangle (temporary)
 };
-struct MbpParams { MbpCam cam[MAX_CAMS]; int n, nb; };
+struct MbpParams { MbpCam cam[MAX_CAMS]; int n, nb; float shift; };
 
 __device__ __forceinline__ int mbp_mirror(int p, int len)      // BORDER_REFLECT (fedcba|abcdefgh|hgfedcb)
 {
@@ -772,7 +772,8 @@ __global__ void __launch_bounds__(256) k_mbp_quantise(const __grid_constant__ Mb
     const size_t i = (size_t)blockIdx.x * 256 + threadIdx.x;
     if (i >= (size_t)k.roi_w * k.roi_h) return;
     const float fw = (float)(double)k.src_w, fh = (float)(double)k.src_h;
-    const float px = __fadd_rn(__fmul_rn(k.map1[i], fw), 0.f), py = __fadd_rn(__fmul_rn(k.map2[i], fh), 0.f);
+    float px = __fadd_rn(__fmul_rn(k.map1[i], fw), 0.f), py = __fadd_rn(__fmul_rn(k.map2[i], fh), 0.f);
+    if (p.shift != 0.f) { px = __fsub_rn(px, p.shift); py = __fsub_rn(py, p.shift); }
     k.sxy[i] = make_int2(__float2int_rn(__fmul_rn(px, 32.f)), __float2int_rn(__fmul_rn(py, 32.f)));
 }
 // table entry of window pixel (x, y) of camera k: valid (mk_entry's C_VALID), integer tap position, fractions
@@ -914,7 +915,7 @@ static bool multiband_pack_gpu(octvr_mapper& m, const octvr_template& t, const s
     const int n = p.n, nb = p.nb;
     MbpParams q;
     memset(&q, 0, sizeof(q));
-    q.n = n; q.nb = nb;
+    q.n = n; q.nb = nb; q.shift = m.texel_shift;
     std::vector<std::unique_ptr<MbpBuf<float>>> d_m1(n), d_m2(n);
     std::vector<std::unique_ptr<MbpBuf<uint8_t>>> d_mask(n), d_seam(n);
     std::vector<std::unique_ptr<MbpBuf<int2>>> d_sxy(n);

@@ -36,6 +36,7 @@ struct PackParams {
     int n, out_w, out_h, tiles_x, tiles_y, band_y0, band_y1;
     int Rx, Ry, Rw, Rh;         // union of the ROIs
     int border; float scale;    // feather: border > 0; no blend: border == 0
+    float shift;                // texel-centre convention: 0.5, else 0 (prep.h quantise_map)
 };
 
 __global__ void __launch_bounds__(256) k_pack_quantise(const __grid_constant__ PackParams p, int c)
@@ -44,7 +45,8 @@ __global__ void __launch_bounds__(256) k_pack_quantise(const __grid_constant__ P
     const size_t i = (size_t)blockIdx.x * 256 + threadIdx.x;
     if (i >= (size_t)k.rw * k.rh) return;
     const float fw = (float)(double)k.src_w, fh = (float)(double)k.src_h;
-    const float px = __fadd_rn(__fmul_rn(k.map1[i], fw), 0.f), py = __fadd_rn(__fmul_rn(k.map2[i], fh), 0.f);     // Mat * double -> f32 convertTo
+    float px = __fadd_rn(__fmul_rn(k.map1[i], fw), 0.f), py = __fadd_rn(__fmul_rn(k.map2[i], fh), 0.f);     // Mat * double -> f32 convertTo
+    if (p.shift != 0.f) { px = __fsub_rn(px, p.shift); py = __fsub_rn(py, p.shift); }
     k.sxy[i] = make_int2(__float2int_rn(__fmul_rn(px, 32.f)), __float2int_rn(__fmul_rn(py, 32.f)));
 }
 
@@ -211,7 +213,7 @@ bool pack_ring_gpu(octvr_mapper& m, const octvr_template& t, int blend)
     p.n = n; p.out_w = t.out_w; p.out_h = t.out_h;
     p.tiles_x = (t.out_w + TILE_W - 1) / TILE_W; p.tiles_y = (t.out_h + TILE_H - 1) / TILE_H;
     p.band_y0 = m.band_y0; p.band_y1 = m.band_y1;
-    p.border = blend < 0 ? -blend : 0; p.scale = (float)n;
+    p.border = blend < 0 ? -blend : 0; p.scale = (float)n; p.shift = m.texel_shift;
     const int ntiles = p.tiles_x * p.tiles_y;
     std::vector<std::unique_ptr<DBuf<float>>> d_m1(n), d_m2(n), d_w(n);
     std::vector<std::unique_ptr<DBuf<uint8_t>>> d_mask(n);

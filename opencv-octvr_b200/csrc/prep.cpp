@@ -323,7 +323,7 @@ std::vector<Img<uint8_t>> distance_seam_masks_host(const std::vector<TInput>& in
 }
 
 void quantise_map(const Img<float>& map1, const Img<float>& map2, int src_w, int src_h,
-                  Img<int32_t>& sx, Img<int32_t>& sy)
+                  Img<int32_t>& sx, Img<int32_t>& sy, float shift)
 {
     sx = Img<int32_t>(map1.w, map1.h);
     sy = Img<int32_t>(map1.w, map1.h);
@@ -334,6 +334,7 @@ void quantise_map(const Img<float>& map1, const Img<float>& map2, int src_w, int
             int32_t* ox = sx.row(y), *oy = sy.row(y);
             for (int x = 0; x < map1.w; x++) {
                 float px = a[x] * fw + 0.f, py = b[x] * fh + 0.f;     // Mat * double -> f32 convertTo
+                if (shift != 0.f) { px = px - shift; py = py - shift; }
                 ox[x] = round_he(px * 32.f);
                 oy[x] = round_he(py * 32.f);
             }

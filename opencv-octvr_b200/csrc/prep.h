@@ -43,7 +43,9 @@ void chamfer_l2_gpu_batch(const uint8_t* const* d_mask, const int* w, const int*
 
 // cv::remap coordinate quantisation for planar f32 maps (imgwarp.cpp:4383-4442) applied to
 // fl32(map * size) (template.cpp:175-176).  Returns 1/32-px fixed point sx, sy.
+// shift: subtracted from the pixel coordinate before it is quantised -- 0 (cv::remap's pixel-index convention, the default)
+// or 0.5 (the texel-centre convention of the reference's CUDA path: tex2D at u * W samples index u * W - 0.5)
 void quantise_map(const Img<float>& map1, const Img<float>& map2, int src_w, int src_h,
-                  Img<int32_t>& sx, Img<int32_t>& sy);
+                  Img<int32_t>& sx, Img<int32_t>& sy, float shift = 0.f);
 
 }  // namespace ob

@@ -543,8 +543,10 @@ def split_packed(frame, w, h):
 class StitchOracle:
     """CPU contract for Mapper::Mapper + Mapper::stitch (mapper.cpp:47-323), stage by stage per SURVEY 8(c)."""
 
-    def __init__(self, tmpl, in_sizes, blend=128, enable_gain=True, scale_output=(0, 0)):
-        """in_sizes: blended inputs, then overlay inputs (mapper.cpp:84-127); scale_output: (0, 0) keeps the template size."""
+    def __init__(self, tmpl, in_sizes, blend=128, enable_gain=True, scale_output=(0, 0), texel_center=False):
+        """in_sizes: blended inputs, then overlay inputs (mapper.cpp:84-127); scale_output: (0, 0) keeps the template size.
+        texel_center: sample at map * W - 0.5, where the reference's CUDA Mapper samples (tex2D, normalised coordinates, linear
+        filter: fast_remap.cu) instead of cv::remap's map * W -- the product's OCTVR_TEXEL_CENTER=1."""
         self.t = tmpl
         self.in_sizes = [tuple(s) for s in in_sizes]
         n = len(tmpl.inputs)
@@ -566,6 +568,10 @@ class StitchOracle:
         self.mapy = [scale_map(d["map2"], s[1]) for d, s in zip(tmpl.inputs, self.in_sizes)]
         self.vig = [resize_linear(d["vignette"], s[0], s[1]) if d["vignette"] is not None else None
                     for d, s in zip(tmpl.inputs, self.in_sizes)]
+        if texel_center:
+            half = np.float32(0.5)
+            self.mapx, self.mapy = [m - half for m in self.mapx], [m - half for m in self.mapy]
+            self.ov_mapx, self.ov_mapy = [m - half for m in self.ov_mapx], [m - half for m in self.ov_mapy]
         # mapper.cpp:94-99,113-114
         self.working_scale = min(1.0, math.sqrt(0.1 * 1e6 / (W * H)))
         ws = self.working_scale
