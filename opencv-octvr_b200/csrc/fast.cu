@@ -159,7 +159,7 @@ struct FsParams {
     const uint32_t* tile_job_start; const FsJob* jobs; const uint32_t* entries;      // job j owns 1024 (luma) / 512 (chroma) entries, in job order
     uint8_t* out; int out_pitch, W, H;
     int luma_tiles_x, luma_tiles, chroma_tiles_x;
-    uint32_t luma_jobs;
+    uint32_t luma_jobs; int stage_bytes;
 };
 __device__ __forceinline__ void fs_issue(const FsJob& job, const uint8_t* __restrict__ plane, int pitch, int wbytes, int h, uint8_t* stage)
 {
@@ -183,9 +183,10 @@ __device__ __forceinline__ uint32_t fs_q(int V, float fw)
 {
     return __float_as_uint(__fmaf_rn(__fmul_rn(fs_float((uint32_t)V), fw), 0.0009765625f, 12582912.f)) - 0x4B400000u;
 }
-__global__ void __launch_bounds__(FT_THREADS) k_fast_staged(const __grid_constant__ FsParams p)
+template <int MINB>
+__global__ void __launch_bounds__(FT_THREADS, MINB) k_fast_staged(const __grid_constant__ FsParams p)
 {
-    __shared__ __align__(16) uint8_t s_stage[2][FS_STAGE];
+    extern __shared__ __align__(16) uint8_t s_dyn[];          // two stages of p.stage_bytes (the mapper's largest footprint)
     const int tile = blockIdx.x, tid = threadIdx.x, lane_x = tid & 15, row = tid >> 4;
     const uint32_t j0 = __ldg(p.tile_job_start + tile), j1 = __ldg(p.tile_job_start + tile + 1);
     const bool luma = tile < p.luma_tiles;
@@ -194,16 +195,16 @@ __global__ void __launch_bounds__(FT_THREADS) k_fast_staged(const __grid_constan
     if (j0 < j1) {
         cur = p.jobs[j0];
         const FastCam& c = p.cam[cur.cam];
-        fs_issue(cur, luma ? c.y : c.uv, luma ? c.y_pitch : c.uv_pitch, luma ? c.w : 2 * (c.w / 2), luma ? c.h : c.h / 2, s_stage[0]);
+        fs_issue(cur, luma ? c.y : c.uv, luma ? c.y_pitch : c.uv_pitch, luma ? c.w : 2 * (c.w / 2), luma ? c.h : c.h / 2, s_dyn);
     }
     for (uint32_t j = j0; j < j1; j++) {
         const int buf = (int)(j - j0) & 1;
         if (j + 1 < j1) {
             nxt = p.jobs[j + 1];
             const FastCam& c = p.cam[nxt.cam];
-            fs_issue(nxt, luma ? c.y : c.uv, luma ? c.y_pitch : c.uv_pitch, luma ? c.w : 2 * (c.w / 2), luma ? c.h : c.h / 2, s_stage[buf ^ 1]);
+            fs_issue(nxt, luma ? c.y : c.uv, luma ? c.y_pitch : c.uv_pitch, luma ? c.w : 2 * (c.w / 2), luma ? c.h : c.h / 2, s_dyn + (buf ^ 1) * p.stage_bytes);
         }
-        const uint8_t* st = s_stage[buf];
+        const uint8_t* st = s_dyn + buf * p.stage_bytes;
         const int sp = (int)cur.bwc * 16;
         if (luma) {
             const uint4 e4 = __ldg(reinterpret_cast<const uint4*>(p.entries + (size_t)j * 1024) + tid);
@@ -347,7 +348,7 @@ void pack_plane(const std::vector<FastTable>& tb, int W, int H, int px, int sw_d
 // staged tables of one plane pass (k_fast_staged).  px: positions per thread (4 luma, 2 chroma); unit: bytes per source position
 // (1 luma, 2 interleaved chroma).  false: some job's footprint does not fit the stage -> the direct kernel serves the mapper.
 bool pack_plane_staged(const std::vector<FastTable>& tb, int W, int H, int px, int unit, int sdiv, const std::vector<int>& in_w, const std::vector<int>& in_h,
-                       std::vector<uint32_t>& tile_job_start, std::vector<FsJob>& jobs, std::vector<uint32_t>& entries, int& tiles_x, int64_t& pairs)
+                       std::vector<uint32_t>& tile_job_start, std::vector<FsJob>& jobs, std::vector<uint32_t>& entries, int& tiles_x, int64_t& pairs, int& max_box)
 {
     const int n = (int)tb.size(), tile_w = 16 * px;
     tiles_x = (W + tile_w - 1) / tile_w;
@@ -372,6 +373,7 @@ bool pack_plane_staged(const std::vector<FastTable>& tb, int W, int H, int px, i
                 const int x0b = unit * xmin, x1b = unit * xmax + unit - 1;               // byte range of the taps in a source row
                 const int bx0 = (int)std::floor(x0b / 16.0) * 16, bwc = std::max(2, (x1b - bx0) / 16 + 1), bh = ymax - ymin + 1;      // >= 2: rcp below must fit 32 bits
                 if ((int64_t)bwc * bh * 16 > FS_STAGE || bx0 < -32768 || ymin < -32768 || ymin > 32767 || bwc > 65535 || bh > 65535) return false;
+                max_box = std::max(max_box, bwc * bh * 16);
                 FsJob job;
                 job.bx0 = (short)bx0; job.by0 = (short)ymin; job.bwc = (unsigned short)bwc; job.bh = (unsigned short)bh;
                 job.rcp = (uint32_t)(0x100000000ull / (uint64_t)bwc) + 1u; job.cam = (uint32_t)c;
@@ -413,7 +415,7 @@ struct octvr_fast {
     // staged layout (k_fast_staged, the default); the direct tables above are built only when it does not apply
     bool staged = false;
     uint32_t* d_s_tile_job_start = nullptr; FsJob* d_s_jobs = nullptr; uint32_t* d_s_entries = nullptr;
-    int s_luma_tiles_x = 0, s_luma_tiles = 0, s_chroma_tiles_x = 0, s_tiles = 0; uint32_t s_luma_jobs = 0;
+    int s_luma_tiles_x = 0, s_luma_tiles = 0, s_chroma_tiles_x = 0, s_tiles = 0, s_stage_bytes = 0, s_occ = 6; uint32_t s_luma_jobs = 0;
     void build_direct();
     ~octvr_fast() { cudaFree(d_tile_job_start); cudaFree(d_job_cam); cudaFree(d_job_ofs); cudaFree(d_entries); cudaFree(d_s_tile_job_start); cudaFree(d_s_jobs); cudaFree(d_s_entries); }
 };
@@ -501,13 +503,16 @@ octvr_status octvr_fast_create(const octvr_template* t, const int* in_sizes_wh, 
             std::vector<uint32_t> tjs{ 0 }, entries;
             std::vector<FsJob> jobs;
             int64_t pl = 0, pc = 0;
-            bool ok = pack_plane_staged(f->full, W, H, 4, 1, 1, f->in_w, f->in_h, tjs, jobs, entries, f->s_luma_tiles_x, pl);
+            int max_box = 0;
+            bool ok = pack_plane_staged(f->full, W, H, 4, 1, 1, f->in_w, f->in_h, tjs, jobs, entries, f->s_luma_tiles_x, pl, max_box);
             f->s_luma_tiles = (int)tjs.size() - 1; f->s_luma_jobs = (uint32_t)jobs.size();
-            ok = ok && pack_plane_staged(f->half, W / 2, H / 2, 2, 2, 2, f->in_w, f->in_h, tjs, jobs, entries, f->s_chroma_tiles_x, pc);
+            ok = ok && pack_plane_staged(f->half, W / 2, H / 2, 2, 2, 2, f->in_w, f->in_h, tjs, jobs, entries, f->s_chroma_tiles_x, pc, max_box);
             f->s_tiles = (int)tjs.size() - 1;
             if (ok && !jobs.empty()) {
                 up(f->d_s_tile_job_start, tjs); up(f->d_s_jobs, jobs); up(f->d_s_entries, entries);
                 f->staged = true; f->pairs_luma = pl; f->pairs_chroma = pc;
+                f->s_stage_bytes = (max_box + 1023) / 1024 * 1024;
+                if (const char* e = getenv("OCTVR_FAST_OCC")) f->s_occ = atoi(e);
                 f->table_bytes = (int64_t)(entries.size() * 4 + jobs.size() * sizeof(FsJob) + tjs.size() * 4);
             }
         }
@@ -537,7 +542,11 @@ octvr_status octvr_fast_stitch_nv12(octvr_fast* f, const uint8_t* const* d_input
             p.tile_job_start = f->d_s_tile_job_start; p.jobs = f->d_s_jobs; p.entries = f->d_s_entries;
             p.out = d_output; p.out_pitch = (int)out_pitch; p.W = f->W; p.H = f->H;
             p.luma_tiles_x = f->s_luma_tiles_x; p.luma_tiles = f->s_luma_tiles; p.chroma_tiles_x = f->s_chroma_tiles_x; p.luma_jobs = f->s_luma_jobs;
-            k_fast_staged<<<f->s_tiles, FT_THREADS, 0, (cudaStream_t)stream>>>(p);
+            p.stage_bytes = f->s_stage_bytes;
+            const size_t smem = 2 * (size_t)f->s_stage_bytes;
+            if (f->s_occ >= 8) k_fast_staged<8><<<f->s_tiles, FT_THREADS, smem, (cudaStream_t)stream>>>(p);
+            else if (f->s_occ == 7) k_fast_staged<7><<<f->s_tiles, FT_THREADS, smem, (cudaStream_t)stream>>>(p);
+            else k_fast_staged<6><<<f->s_tiles, FT_THREADS, smem, (cudaStream_t)stream>>>(p);
             OB_CUDA(cudaGetLastError());
             return;
         }
