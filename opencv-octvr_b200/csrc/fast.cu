@@ -415,7 +415,9 @@ struct octvr_fast {
     // staged layout (k_fast_staged, the default); the direct tables above are built only when it does not apply
     bool staged = false;
     uint32_t* d_s_tile_job_start = nullptr; FsJob* d_s_jobs = nullptr; uint32_t* d_s_entries = nullptr;
-    int s_luma_tiles_x = 0, s_luma_tiles = 0, s_chroma_tiles_x = 0, s_tiles = 0, s_stage_bytes = 0, s_occ = 8;      // resident CTAs / SM asked of the staged kernel (measured on B200: 6 / 7 / 8 -> 70.3 / 64.3 / 64.2 us) uint32_t s_luma_jobs = 0;
+    int s_luma_tiles_x = 0, s_luma_tiles = 0, s_chroma_tiles_x = 0, s_tiles = 0, s_stage_bytes = 0;
+    int s_occ = 8;                      // resident CTAs / SM asked of the staged kernel (measured on B200: 6 / 7 / 8 -> 70.3 / 64.3 / 64.2 us)
+    uint32_t s_luma_jobs = 0;
     void build_direct();
     ~octvr_fast() { cudaFree(d_tile_job_start); cudaFree(d_job_cam); cudaFree(d_job_ofs); cudaFree(d_entries); cudaFree(d_s_tile_job_start); cudaFree(d_s_jobs); cudaFree(d_s_entries); }
 };
