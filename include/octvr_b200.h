@@ -163,6 +163,9 @@ octvr_status octvr_mapper_stats(const octvr_mapper* m, int64_t* pairs, int64_t* 
 /* Per blended input the source rows [lo, hi) this mapper converts and reads (the whole image unless it is a row-band
  * mapper); rows_lo_hi = {lo0, hi0, lo1, hi1, ...}, n = number of blended inputs. */
 octvr_status octvr_mapper_source_rows(const octvr_mapper* m, int* rows_lo_hi, int n);
+/* The same for source columns: [lo, hi) of every blended input that some table entry reads (a fisheye circle in a 16:9
+ * frame leaves the sides unused); only those columns are converted.  The whole width for the non-default blend layouts. */
+octvr_status octvr_mapper_source_cols(const octvr_mapper* m, int* cols_lo_hi, int n);
 /* time (ms, CUDA events on the stitch stream) the named stage of the LAST stitch took; stage =
  * "convert" | "gain" | "blend" | "total".  Only valid when octvr_mapper_set_profiling(m, 1). */
 octvr_status octvr_mapper_set_profiling(octvr_mapper* m, int on);

@@ -78,9 +78,9 @@ __device__ __forceinline__ void convert_body(const ConvertParams& p, int block)
     const int by = rem / p.grid_x, bx = rem - by * p.grid_x;
     const CamSrc& c = p.cam[cam];
     const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
-    const int x0 = (bx << 8) + (tx << 3);
+    const int x0 = c.col0 + (bx << 8) + (tx << 3);
     const int y0 = c.row0 + (by << 4) + (ty << 1);
-    if (x0 >= c.w || y0 >= c.row1) return;
+    if (x0 >= c.col1 || y0 >= c.row1) return;
     const int w = c.w;
     if (c.rgb) {                                            // packed RGB24 / BGR24 -> RGBX: a byte shuffle (+ vignette)
         #pragma unroll

@@ -344,7 +344,8 @@ static void build_mapper(octvr_mapper& m, const octvr_template& t, const int* in
     if (!want_fused)
         for (int i = 0; i < n + n_ov; i++) m.d_rgbx.push_back(dev_alloc<uint32_t>((size_t)m.in_w[i] * m.in_h[i] + 4));
     m.src_row0.assign(n + n_ov, 0);
-    for (int i = 0; i < n + n_ov; i++) m.src_row1.push_back(m.in_h[i]);
+    m.src_col0.assign(n + n_ov, 0);
+    for (int i = 0; i < n + n_ov; i++) { m.src_row1.push_back(m.in_h[i]); m.src_col1.push_back(m.in_w[i]); }
     tr.lap("vignette + pairs + planes");
     // default layout (K_blend_ring): quantisation, feather weights, job list, boxes and entries by CUDA kernels (pack.cu)
     const bool is_band = m.band_y0 != 0 || m.band_y1 != t.out_h;
@@ -803,7 +804,8 @@ void ob::mapper_stitch_internal(octvr_mapper& m, const octvr_frame* in, int n_in
             : ((uintptr_t)c.u % 8 == 0 && c.u_pitch % 8 == 0 && c.v == c.u + 1);
         c.aligned4 = ((uintptr_t)c.y % 8 == 0) && (c.y_pitch % 8 == 0) && (c.w % 4 == 0) && chroma_ok;
         c.row0 = m.src_row0[i]; c.row1 = m.src_row1[i];
-        cp.grid_x = std::max(cp.grid_x, (c.w + 255) / 256);
+        c.col0 = m.src_col0[i]; c.col1 = m.src_col1[i];
+        cp.grid_x = std::max(cp.grid_x, (c.col1 - c.col0 + 255) / 256);
         cp.grid_y = std::max(cp.grid_y, (c.row1 - c.row0 + 15) / 16);
     }
     // one launch: gain statistics + solve (reading the input planes directly) in the first CTAs, conversion in the rest
@@ -1060,6 +1062,14 @@ octvr_status octvr_mapper_source_rows(const octvr_mapper* m, int* rows_lo_hi, in
 octvr_status octvr_mapper_set_profiling(octvr_mapper* m, int on)
 {
     return guard([&] { OB_CHECK(m, "null argument"); m->profiling = on != 0; });
+}
+
+octvr_status octvr_mapper_source_cols(const octvr_mapper* m, int* cols_lo_hi, int n)
+{
+    return guard([&] {
+        OB_CHECK(m && cols_lo_hi && n == m->n, "bad argument");
+        for (int i = 0; i < n; i++) { cols_lo_hi[2 * i] = m->src_col0[i]; cols_lo_hi[2 * i + 1] = m->src_col1[i]; }
+    });
 }
 
 octvr_status octvr_mapper_stage_ms(octvr_mapper* m, const char* stage, float* ms)

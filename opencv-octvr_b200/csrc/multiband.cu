@@ -966,6 +966,7 @@ static bool multiband_pack_gpu(octvr_mapper& m, const octvr_template& t, const s
     // jobs in the host packer's order: cameras in order, tiles row by row; size classes, tensor-map slots
     std::vector<MbWarpJob> wjobs;
     std::map<uint64_t, int> tmap_index;
+    std::vector<int> col_lo(n, INT_MAX), col_hi(n, INT_MIN);      // source columns the taps of each camera touch
     auto size_class = [](int v) { return v <= 64 ? (v + 7) / 8 * 8 : v <= 128 ? (v + 15) / 16 * 16 : (v + 31) / 32 * 32; };
     for (int i = 0; i < n; i++) {
         const int tiles_x = (geo[i].cw + TILE_W - 1) / TILE_W;
@@ -973,6 +974,7 @@ static bool multiband_pack_gpu(octvr_mapper& m, const octvr_template& t, const s
         for (size_t k = 0; k < boxes[i].size(); k++) {
             const int4 b = boxes[i][k];
             if (b.x > b.y) continue;
+            col_lo[i] = std::min(col_lo[i], b.x); col_hi[i] = std::max(col_hi[i], b.y);
             MbWarpJob job;
             memset(&job, 0, sizeof(job));
             job.bx0 = (int)std::floor(b.x / 4.0) * 4; job.by0 = b.z;
@@ -1047,6 +1049,10 @@ static bool multiband_pack_gpu(octvr_mapper& m, const octvr_template& t, const s
             if (lo > hi) m.src_row0[i] = m.src_row1[i] = 0;
             else { m.src_row0[i] = std::max(0, lo) & ~1; m.src_row1[i] = std::min(m.in_h[i], hi + 1); }
         }
+    for (int i = 0; i < n; i++) {
+        if (col_lo[i] > col_hi[i]) { m.src_col0[i] = m.src_col1[i] = 0; continue; }
+        m.src_col0[i] = std::max(0, col_lo[i]) & ~7; m.src_col1[i] = std::min(m.in_w[i], col_hi[i] + 1);
+    }
     table_bytes = (int64_t)(wjobs.size() * TILE_PX * 4 + wjobs.size() * sizeof(MbWarpJob) + w_total * 4 + dst_floats * 4);
     return true;
 }

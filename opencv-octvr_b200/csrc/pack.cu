@@ -271,11 +271,13 @@ bool pack_ring_gpu(octvr_mapper& m, const octvr_template& t, int blend)
     std::map<uint64_t, int> tmap_index;
     std::vector<uint4> recs((size_t)ntiles * n, make_uint4(0u, 0u, 0u, 0u));
     auto size_class = [](int v) { return v <= 64 ? (v + 7) / 8 * 8 : v <= 128 ? (v + 15) / 16 * 16 : (v + 31) / 32 * 32; };
+    std::vector<int> col_lo(n, INT_MAX), col_hi(n, INT_MIN);      // source columns the taps of each camera touch
     for (int tl = 0; tl < ntiles; tl++)
         for (uint32_t j = job_start[tl]; j < job_start[tl + 1]; j++) {
             int xmin = boxes[j].x, xmax = boxes[j].y, ymin = boxes[j].z, ymax = boxes[j].w;
             if (xmin > xmax) { xmin = xmax = ymin = ymax = 0; }
             const int i = job_cam[j];
+            if (boxes[j].x <= boxes[j].y) { col_lo[i] = std::min(col_lo[i], xmin); col_hi[i] = std::max(col_hi[i], xmax); }
             const int bx0 = (int)std::floor(xmin / 4.0) * 4, by0 = ymin;
             const int bw = size_class(xmax - bx0 + 1), bh = size_class(ymax - ymin + 1);
             if (bw > 256 || bh > 256 || (int64_t)bw * bh > STAGE_CAP) return false;
@@ -319,6 +321,10 @@ bool pack_ring_gpu(octvr_mapper& m, const octvr_template& t, int blend)
     OB_CUDA(cudaMalloc(&m.d_ring_counter, sizeof(unsigned int))); OB_CUDA(cudaMemset(m.d_ring_counter, 0, sizeof(unsigned int)));
     OB_CUDA(cudaMalloc(&m.d_dbg_ring, 8 * sizeof(unsigned long long))); OB_CUDA(cudaMemset(m.d_dbg_ring, 0, 8 * sizeof(unsigned long long)));
     m.table_bytes = (int64_t)(njobs * (TILE_PX / 2) * sizeof(uint4) + recs.size() * 16);
+    for (int i = 0; i < n; i++) {
+        if (col_lo[i] > col_hi[i]) { m.src_col0[i] = m.src_col1[i] = 0; continue; }
+        m.src_col0[i] = std::max(0, col_lo[i]) & ~7; m.src_col1[i] = std::min(m.in_w[i], col_hi[i] + 1);
+    }
     tr.lap("commit");
     return true;
 }

@@ -268,6 +268,13 @@ class Mapper:
         check(lib().octvr_mapper_stats(self._h, C.byref(pairs), C.byref(roi), C.byref(tb), C.byref(ln)))
         return dict(pairs=pairs.value, roi_area=roi.value, table_bytes=tb.value, launches_per_stitch=ln.value)
 
+    def src_cols(self):
+        """per blended input: the source columns (lo, hi) some table entry reads (only those are converted)."""
+        n = self.tmpl.num_inputs
+        a = (C.c_int * (2 * n))()
+        check(lib().octvr_mapper_source_cols(self._h, a, n))
+        return [(a[2 * i], a[2 * i + 1]) for i in range(n)]
+
     def src_rows(self):
         """per blended input: the source rows (lo, hi) this mapper converts and reads (all rows unless it is a row-band mapper)."""
         n = self.tmpl.num_inputs
