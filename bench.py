@@ -623,6 +623,31 @@ def run_stereo(args, sub=False):
     out = outs[0]
     pipe = vr.sharding.FramePipeline(st, src=0, defer_collect=os.environ.get("OCTVR_DEFER_COLLECT", "0") != "0", peer=peer)
 
+    # N > 1: only the source columns some mapper reads travel (the C4 rig's fisheye circles use 56 % of each 3840-wide frame):
+    # per step rank 0 crops the full frames of the NEXT time step into a compact frame set (one launch, side stream) and that
+    # is what is broadcast; the mappers are told their frames start at the window's first column.  OCTVR_C4_CROP=0: full frames.
+    crop = world > 1 and os.environ.get("OCTVR_C4_CROP", "1") != "0"
+    bcast_bytes = sum(f.numel() for f in flats[:1])
+    if crop:
+        cols = st.source_cols()
+        lo = torch.tensor([c[0] for c in cols], dtype=torch.int32, device="cuda")
+        hi = torch.tensor([c[1] for c in cols], dtype=torch.int32, device="cuda")
+        dist.all_reduce(lo, op=dist.ReduceOp.MIN)
+        dist.all_reduce(hi, op=dist.ReduceOp.MAX)
+        windows = [(int(a) // 32 * 32, (int(b) + 31) // 32 * 32 - int(a) // 32 * 32) for a, b in zip(lo.tolist(), hi.tolist())]
+        st.set_input_windows(windows)
+        full_ring, full_flats = ring, flats
+        ring, flats = [], []
+        for k in range(RING):
+            flat, views = vr.sharding.alloc_frame_set([(cw, in_size[1]) for _, cw in windows], "cuda")
+            if rank == 0:
+                vr.sharding.crop_packed_frames(full_ring[k], views, [in_size] * n, windows)
+            dist.broadcast(flat, 0)                    # every rank starts with valid frames in every slot (warm-up, stage timing)
+            ring.append(views)
+            flats.append(flat)
+        by_ptr = {flats[k].data_ptr(): k for k in range(RING)}
+        pipe.prepare = lambda flat: vr.sharding.crop_packed_frames(full_ring[by_ptr[flat.data_ptr()]], ring[by_ptr[flat.data_ptr()]], [in_size] * n, windows)
+        bcast_bytes = flats[0].numel()
     nobcast = os.environ.get("OCTVR_C4_NOBCAST", "0") != "0"      # diagnostic: frames taken as already resident on every rank
     if nobcast and world > 1:
         for fl in flats:
@@ -697,11 +722,13 @@ def run_stereo(args, sub=False):
     if args.verify and world > 1 and rank == 0:      # the assembled frame of the last step == both eyes stitched whole on this GPU
         one = vr.sharding.StereoRowBandStitcher(vr, tmpls, [in_size] * n, blend, gain, local, rank=0, world=1)
         ref = torch.zeros_like(out)
-        one.stitch_local(ring[(args.steps - 1) % RING], ref)
+        one.stitch_local((full_ring if crop else ring)[(args.steps - 1) % RING], ref)
         torch.cuda.synchronize()
         verified = bool(torch.equal(ref, outs[(args.steps - 1) % 2]))
         del one, ref
     src_rows = [[int(m.src_rows()[c][1] - m.src_rows()[c][0]) for c in range(n)] for _, _, m in st.jobs]
+    bcast_mb = bcast_bytes / 1e6
+    crop_note = (": the source columns some mapper reads, %s of %d, cropped on rank 0 by one launch per step" % (sorted(set(w[1] for w in windows)), in_size[0])) if crop else ""
     st_split = st.split
     del st, pipe, outs, out, ring, flats, tmpls
     for pf in pfs:
@@ -725,9 +752,9 @@ def run_stereo(args, sub=False):
         "config": {"workload": desc, "inputs": "%dx%dx%d I420 (octvr packed layout), ring of %d noise frames resident on rank 0" % (n, iw, ih, RING),
                    "output": "%dx%d 4:2:0 top-bottom (two %dx%d eyes)" % (W, H, W, He),
                    "l2": "working set per step exceeds the 126 MB L2; no flush",
-                   "sharding": (("column" if st_split == "cols" else "row") + " bands of one stream: per step ONE NCCL broadcast of the %d input frames (%.1f MB) from rank 0 (issued one step "
+                   "sharding": (("column" if st_split == "cols" else "row") + " bands of one stream: per step ONE NCCL broadcast of the %d input frames (%.1f MB%s) from rank 0 (issued one step "
                                 "ahead, overlapping the previous stitch), (eye, band) stitch of the source rows the band reads "
-                                "(%.1f MB frame in total)" % (n, I / 1e6, W * H * 1.5 / 1e6)) if world > 1 else "single GPU, both eyes",
+                                "(%.1f MB frame in total)" % (n, bcast_mb, crop_note, W * H * 1.5 / 1e6)) if world > 1 else "single GPU, both eyes",
                    "assignment_rank0": jobs_rank0, "source_rows_converted_rank0": src_rows,
                    "band_output": ("stored by the blend kernels straight into rank 0's frame over NVLink peer memory (CUDA IPC); one 4-byte "
                                    "all-reduce per step = frame complete") if peer else ("NCCL send / recv to rank 0" if world > 1 else "local"),

@@ -166,6 +166,15 @@ octvr_status octvr_mapper_source_rows(const octvr_mapper* m, int* rows_lo_hi, in
 /* The same for source columns: [lo, hi) of every blended input that some table entry reads (a fisheye circle in a 16:9
  * frame leaves the sides unused); only those columns are converted.  The whole width for the non-default blend layouts. */
 octvr_status octvr_mapper_source_cols(const octvr_mapper* m, int* cols_lo_hi, int n);
+/* Declares that the frames of blended input `cam` passed to stitch hold source columns [col0, col0 + width) only (multiples of
+ * 8 that cover octvr_mapper_source_cols): plane pointers address column col0 of each row, pitches need only cover `width`.
+ * For callers that move frames between GPUs (row-band mode) or over PCIe and want to move only what is read. */
+octvr_status octvr_mapper_set_input_window(octvr_mapper* m, int cam, int col0, int width);
+/* The ingest side of input windows: source columns [col0[i], col0[i] + width[i]) of n packed (1.5 h x w) DEVICE frames (Mapper's
+ * W x 1.5H layout, mapper.hpp:75-83; wh = {w0, h0, w1, h1, ...}) copied into packed (1.5 h x width) frames, U and V halves
+ * cropped alike -- one launch.  Windows, widths and frame widths multiples of 32, pitches and pointers of 16. */
+octvr_status octvr_crop_packed_frames(int n, const uint8_t* const* d_src, const size_t* src_pitch, const int* wh, const int* col0,
+                                      const int* width, uint8_t* const* d_dst, const size_t* dst_pitch, void* stream);
 /* time (ms, CUDA events on the stitch stream) the named stage of the LAST stitch took; stage =
  * "convert" | "gain" | "blend" | "total".  Only valid when octvr_mapper_set_profiling(m, 1). */
 octvr_status octvr_mapper_set_profiling(octvr_mapper* m, int on);

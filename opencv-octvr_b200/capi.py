@@ -32,7 +32,7 @@ SYMBOLS = [
     "octvr_template_out_size", "octvr_template_num_inputs", "octvr_template_num_overlays",
     "octvr_template_input", "octvr_template_destroy",
     "octvr_mapper_create", "octvr_mapper_stitch", "octvr_mapper_stitch_packed", "octvr_mapper_set_keep_rgb", "octvr_mapper_result_rgb",
-    "octvr_mapper_source_rows", "octvr_mapper_source_cols", "octvr_shared_alloc", "octvr_shared_open", "octvr_shared_close", "octvr_mapper_debug_gain_ns", "octvr_mapper_debug_ring", "octvr_mapper_debug_gain_trace", "octvr_debug_fill_poly", "octvr_mapper_create_band", "octvr_mapper_create_window",
+    "octvr_mapper_source_rows", "octvr_mapper_source_cols", "octvr_mapper_set_input_window", "octvr_crop_packed_frames", "octvr_shared_alloc", "octvr_shared_open", "octvr_shared_close", "octvr_mapper_debug_gain_ns", "octvr_mapper_debug_ring", "octvr_mapper_debug_gain_trace", "octvr_debug_fill_poly", "octvr_mapper_create_band", "octvr_mapper_create_window",
     "octvr_mapper_gains", "octvr_mapper_stats", "octvr_mapper_set_profiling", "octvr_mapper_stage_ms",
     "octvr_mapper_destroy",
     "octvr_async_create", "octvr_async_push", "octvr_async_pop", "octvr_async_fps", "octvr_async_preview", "octvr_async_destroy",

@@ -345,7 +345,9 @@ static void build_mapper(octvr_mapper& m, const octvr_template& t, const int* in
         for (int i = 0; i < n + n_ov; i++) m.d_rgbx.push_back(dev_alloc<uint32_t>((size_t)m.in_w[i] * m.in_h[i] + 4));
     m.src_row0.assign(n + n_ov, 0);
     m.src_col0.assign(n + n_ov, 0);
-    for (int i = 0; i < n + n_ov; i++) { m.src_row1.push_back(m.in_h[i]); m.src_col1.push_back(m.in_w[i]); }
+    m.win_col0.assign(n + n_ov, 0);
+    for (int i = 0; i < n + n_ov; i++) { m.src_row1.push_back(m.in_h[i]); m.src_col1.push_back(m.in_w[i]); m.win_w.push_back(m.in_w[i]); }
+    m.gain_col0.assign(n, INT32_MAX); m.gain_col1.assign(n, INT32_MIN);
     tr.lap("vignette + pairs + planes");
     // default layout (K_blend_ring): quantisation, feather weights, job list, boxes and entries by CUDA kernels (pack.cu)
     const bool is_band = m.band_y0 != 0 || m.band_y1 != t.out_h;
@@ -660,6 +662,7 @@ static void build_mapper(octvr_mapper& m, const octvr_template& t, const int* in
                     if (e.y & C_VALID) {        // the gain kernel reads the input planes directly: keep (ix, iy), not a plane offset
                         const int ix = std::min(32767, std::max(-32768, fsx >> 5)), iy = std::min(32767, std::max(-32768, fsy >> 5));
                         e.x = (uint32_t)(ix + 1) | ((uint32_t)(iy + 1) << 16);
+                        if (sm.row(dy)[dx] == 255) { m.gain_col0[i] = std::min(m.gain_col0[i], std::max(0, ix)); m.gain_col1[i] = std::max(m.gain_col1[i], std::min(m.in_w[i], ix + 2)); }
                     }
                     if (sm.row(dy)[dx] != 255) e = make_uint2(0xFFFFFFFFu, 0u);     // CPU compensator's intersect rule: mask == 255
                     gcoord.push_back(e);
@@ -772,7 +775,7 @@ void ob::mapper_stitch_internal(octvr_mapper& m, const octvr_frame* in, int n_in
     const int n_all = m.n + m.n_ov;
     OB_CHECK(n_in == n_all, "wrong number of input frames");         // mapper.cpp:208
     OB_CUDA(cudaSetDevice(m.device));
-    for (int i = 0; i < n_all; i++) check_frame(in[i], m.in_w[i], m.in_h[i], "bad input frame", true);
+    for (int i = 0; i < n_all; i++) check_frame(in[i], m.win_w[i], m.in_h[i], "bad input frame", true);
     if (user_out) check_frame(*user_out, m.scaled_w, m.scaled_h, "bad output frame");
     OB_CHECK(user_out || m.keep_rgb || d_preview, "no output requested");
     if (d_preview) OB_CHECK(preview_w > 0 && preview_h > 0 && preview_pitch >= (size_t)preview_w * 3, "bad preview buffer");
@@ -797,6 +800,11 @@ void ob::mapper_stitch_internal(octvr_mapper& m, const octvr_frame* in, int n_in
             const bool bgr = c.uv_step == OCTVR_FMT_BGR24;
             c.y = in[i].y + (bgr ? 2 : 0); c.u = in[i].y + 1; c.v = in[i].y + (bgr ? 0 : 2);
             c.u_pitch = c.v_pitch = c.y_pitch; c.uv_step = 3; c.rgb = 1;
+        }
+        if (m.win_col0[i] != 0) {        // the frame holds source columns [win_col0, win_col0 + win_w): address column 0 virtually
+            const int c0 = m.win_col0[i];
+            if (c.rgb) { c.y -= 3 * (size_t)c0; c.u -= 3 * (size_t)c0; c.v -= 3 * (size_t)c0; }
+            else { c.y -= c0; c.u -= (size_t)(c0 / 2) * c.uv_step; c.v -= (size_t)(c0 / 2) * c.uv_step; }
         }
         c.rgbx = m.fused ? nullptr : m.d_rgbx[i]; c.vignette = m.d_vig[i];
         const bool chroma_ok = c.uv_step == 1
@@ -1002,7 +1010,7 @@ octvr_status octvr_mapper_stitch_packed(octvr_mapper* m, const uint8_t* const* d
         std::vector<octvr_frame> f(n_inputs);
         for (int i = 0; i < n_inputs; i++) {              // mapper.cpp:222-226
             uint8_t* b = const_cast<uint8_t*>(d_inputs[i]);
-            f[i].y = b; f[i].u = b + (size_t)m->in_h[i] * in_pitch[i]; f[i].v = f[i].u + m->in_w[i] / 2;
+            f[i].y = b; f[i].u = b + (size_t)m->in_h[i] * in_pitch[i]; f[i].v = f[i].u + m->win_w[i] / 2;
             f[i].y_pitch = f[i].u_pitch = f[i].v_pitch = in_pitch[i]; f[i].uv_pixel_stride = 1;
         }
         octvr_frame o;                                     // mapper.cpp:296-302
@@ -1068,7 +1076,28 @@ octvr_status octvr_mapper_source_cols(const octvr_mapper* m, int* cols_lo_hi, in
 {
     return guard([&] {
         OB_CHECK(m && cols_lo_hi && n == m->n, "bad argument");
-        for (int i = 0; i < n; i++) { cols_lo_hi[2 * i] = m->src_col0[i]; cols_lo_hi[2 * i + 1] = m->src_col1[i]; }
+        for (int i = 0; i < n; i++) {      // what the tables read (that is converted) and what the gain samples read
+            int lo = m->src_col0[i], hi = m->src_col1[i];
+            if (m->gain && m->gain_col0[i] <= m->gain_col1[i]) {
+                if (lo >= hi) { lo = m->gain_col0[i]; hi = m->gain_col1[i]; }
+                else { lo = std::min(lo, m->gain_col0[i]); hi = std::max(hi, m->gain_col1[i]); }
+            }
+            cols_lo_hi[2 * i] = lo; cols_lo_hi[2 * i + 1] = hi;
+        }
+    });
+}
+
+octvr_status octvr_mapper_set_input_window(octvr_mapper* m, int cam, int col0, int width)
+{
+    return guard([&] {
+        OB_CHECK(m && cam >= 0 && cam < m->n, "bad argument");
+        OB_CHECK(!m->fused, "input windows are not available on the single-kernel path (OCTVR_BLEND=fused)");
+        OB_CHECK(col0 >= 0 && width > 0 && col0 + width <= m->in_w[cam] && col0 % 8 == 0 && width % 8 == 0, "window must lie inside the frame, multiples of 8");
+        int need[2 * MAX_CAMS];
+        octvr_mapper_source_cols(m, need, m->n);
+        if (need[2 * cam] < need[2 * cam + 1])
+            OB_CHECK(col0 <= need[2 * cam] && need[2 * cam + 1] <= col0 + width, "window does not cover the source columns this mapper reads (octvr_mapper_source_cols)");
+        m->win_col0[cam] = col0; m->win_w[cam] = width;
     });
 }
 

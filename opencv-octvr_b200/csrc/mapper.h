@@ -22,6 +22,9 @@ struct octvr_mapper {
     int band_y0 = 0, band_y1 = 0;       // output rows this mapper produces (multi-GPU row-band mode); default: all rows
     float texel_shift = 0.f;            // 0.5 with OCTVR_TEXEL_CENTER=1: sample at u * W - 0.5 (the reference's texture path) instead of u * W
     int band_x0 = 0, band_x1 = 0;       // output columns this mapper produces (column-band mode, multiband only); default: all columns
+    std::vector<int> gain_col0, gain_col1; // per camera: the source columns the gain samples read
+    std::vector<int> win_col0, win_w;   // input window (octvr_mapper_set_input_window): the frames passed to stitch hold source columns
+                                        // [win_col0, win_col0 + win_w) only; default: the whole width
     std::vector<int> src_col0, src_col1; // per camera: the source columns [col0, col1) some table entry reads (only those are converted; a fisheye
                                         // circle in a 16:9 frame leaves the sides unused); default: all columns
     std::vector<int> src_row0, src_row1; // per camera: the source rows [row0, row1) some table entry of this mapper reads (a row-band mapper

@@ -151,4 +151,47 @@ void launch_rgb_to_yuv420(const uint8_t* rgb, size_t rgb_pitch, int w, int h, co
     k_rgb_to_yuv420<<<dim3((w / 2 + 31) / 32, (h / 2 + 7) / 8), dim3(32, 8), 0, s>>>(p);
 }
 
+// ---- k_crop_frames: source columns [col0, col0 + cw) of up to 16 packed (1.5 h x w) frames -> packed (1.5 h x cw) frames,
+//      one launch (the ingest side of octvr_mapper_set_input_window: only the columns that are read travel between GPUs) ----
+struct CropFrame { const uint8_t* src; uint8_t* dst; uint32_t src_pitch, dst_pitch; int w, h, col0, cw; };
+struct CropParams { CropFrame f[MAX_CAMS]; };
+__global__ void __launch_bounds__(256) k_crop_frames(const __grid_constant__ CropParams p)
+{
+    const CropFrame& f = p.f[blockIdx.z];
+    const int chunks = f.cw / 16, rows = f.h + f.h / 2;
+    const int c = blockIdx.x * 256 + threadIdx.x, r = blockIdx.y;
+    if (c >= chunks || r >= rows) return;
+    int sx = f.col0 + c * 16;                                       // luma row
+    if (r >= f.h) {                                                 // U | V halves side by side
+        const int half = f.cw / 2, x = c * 16;
+        sx = x < half ? f.col0 / 2 + x : f.w / 2 + f.col0 / 2 + (x - half);
+    }
+    const uint4 v = __ldg(reinterpret_cast<const uint4*>(f.src + (size_t)r * f.src_pitch + sx));
+    *reinterpret_cast<uint4*>(f.dst + (size_t)r * f.dst_pitch + c * 16) = v;
+}
+
 }  // namespace ob
+
+extern "C" octvr_status octvr_crop_packed_frames(int n, const uint8_t* const* d_src, const size_t* src_pitch, const int* wh, const int* col0,
+                                                 const int* width, uint8_t* const* d_dst, const size_t* dst_pitch, void* stream)
+{
+    using namespace ob;
+    return guard([&] {
+        OB_CHECK(n >= 1 && n <= MAX_CAMS && d_src && src_pitch && wh && col0 && width && d_dst && dst_pitch, "bad argument");
+        CropParams p;
+        memset(&p, 0, sizeof(p));
+        int max_chunks = 0, max_rows = 0;
+        for (int i = 0; i < n; i++) {
+            const int w = wh[2 * i], h = wh[2 * i + 1];
+            OB_CHECK(d_src[i] && d_dst[i] && col0[i] >= 0 && width[i] > 0 && col0[i] + width[i] <= w, "window outside the frame");
+            // 16-byte copies: the luma and both chroma segments must start on 16-byte boundaries
+            OB_CHECK(col0[i] % 32 == 0 && width[i] % 32 == 0 && w % 32 == 0 && src_pitch[i] % 16 == 0 && dst_pitch[i] % 16 == 0 &&
+                     (uintptr_t)d_src[i] % 16 == 0 && (uintptr_t)d_dst[i] % 16 == 0, "windows, widths and pitches must be multiples of 32 / 16 bytes");
+            OB_CHECK(src_pitch[i] >= (size_t)w && dst_pitch[i] >= (size_t)width[i] && h % 2 == 0, "pitch");
+            p.f[i] = CropFrame{ d_src[i], d_dst[i], (uint32_t)src_pitch[i], (uint32_t)dst_pitch[i], w, h, col0[i], width[i] };
+            max_chunks = std::max(max_chunks, width[i] / 16); max_rows = std::max(max_rows, h + h / 2);
+        }
+        k_crop_frames<<<dim3((max_chunks + 255) / 256, max_rows, n), 256, 0, (cudaStream_t)stream>>>(p);
+        OB_CUDA(cudaGetLastError());
+    });
+}

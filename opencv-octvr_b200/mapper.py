@@ -268,6 +268,11 @@ class Mapper:
         check(lib().octvr_mapper_stats(self._h, C.byref(pairs), C.byref(roi), C.byref(tb), C.byref(ln)))
         return dict(pairs=pairs.value, roi_area=roi.value, table_bytes=tb.value, launches_per_stitch=ln.value)
 
+    def set_input_window(self, cam, col0, width):
+        """The frames of input `cam` passed to stitch() hold source columns [col0, col0 + width) only (a (1.5h, width) packed
+        frame or planes whose first column is col0)."""
+        check(lib().octvr_mapper_set_input_window(self._h, int(cam), int(col0), int(width)))
+
     def src_cols(self):
         """per blended input: the source columns (lo, hi) some table entry reads (only those are converted)."""
         n = self.tmpl.num_inputs

@@ -65,6 +65,23 @@ def alloc_frame_set(in_sizes, device, torch_mod=None):
     return flat, views
 
 
+def crop_packed_frames(src_views, dst_views, in_sizes, windows, stream=None):
+    """Source columns [col0, col0 + width) of every packed (1.5 h, w) frame in src_views -> the packed (1.5 h, width) frames in
+    dst_views, one kernel launch (octvr_crop_packed_frames).  windows: [(col0, width)] per camera, multiples of 32."""
+    import ctypes as C
+    from .capi import lib, check
+    n = len(src_views)
+    s = stream if stream is not None else torch.cuda.current_stream()
+    srcp = (C.c_void_p * n)(*[t.data_ptr() for t in src_views])
+    dstp = (C.c_void_p * n)(*[t.data_ptr() for t in dst_views])
+    sp = (C.c_size_t * n)(*[t.stride(0) for t in src_views])
+    dp = (C.c_size_t * n)(*[t.stride(0) for t in dst_views])
+    wh = (C.c_int * (2 * n))(*[v for s_ in in_sizes for v in s_])
+    c0 = (C.c_int * n)(*[w[0] for w in windows])
+    cw = (C.c_int * n)(*[w[1] for w in windows])
+    check(lib().octvr_crop_packed_frames(n, srcp, sp, wh, c0, cw, dstp, dp, C.c_void_p(s.cuda_stream)))
+
+
 def broadcast_frames(frames, src=0, async_op=False):
     """Row-band mode: every rank needs every input frame.  `frames`: one flat tensor (alloc_frame_set) or a list of u8
     tensors, valid on `src`.  async_op=True returns the work handles (wait() before reading the frames)."""
@@ -250,11 +267,27 @@ class StereoRowBandStitcher:
                           band=None if (per == 1 or cols is not None) else band, cols=cols)
             self.jobs.append((eye, band if cols is None else ("cols",) + tuple(cols), m))
 
+    def source_cols(self):
+        """per camera: the source columns (lo, hi) this rank's mappers read (tables and gain samples)."""
+        cols = None
+        for _, _, m in self.jobs:
+            c = m.src_cols()
+            cols = c if cols is None else [(min(a[0], b[0]), max(a[1], b[1])) for a, b in zip(cols, c)]
+        return cols
+
+    def set_input_windows(self, windows):
+        """The frames passed to stitch_local() from now on are packed (1.5 h, width) frames holding source columns
+        [col0, col0 + width) of every camera only (octvr_mapper_set_input_window): windows = [(col0, width)] per camera."""
+        for _, _, m in self.jobs:
+            for c, (col0, width) in enumerate(windows):
+                m.set_input_window(c, col0, width)
+        self.frame_sizes = [(width, h) for (col0, width), (w, h) in zip(windows, self.in_sizes)]
+
     def stitch_local(self, frames_packed, out_packed, stream=None):
         """This rank's share: frames in Mapper's packed layout, out_packed the full top-bottom frame (W x 1.5 * 2 * eye_h)."""
         W, He = self.eye_w, self.eye_h
         oy, ou, ov = self.vr.split_packed(out_packed, W, 2 * He)
-        ins = [self.vr.split_packed(f, w, h) for f, (w, h) in zip(frames_packed, self.in_sizes)]
+        ins = [self.vr.split_packed(f, w, h) for f, (w, h) in zip(frames_packed, getattr(self, "frame_sizes", self.in_sizes))]
         for eye, band, m in self.jobs:
             m.stitch(ins, (oy[eye * He:(eye + 1) * He], ou[eye * He // 2:(eye + 1) * He // 2], ov[eye * He // 2:(eye + 1) * He // 2]),
                      stream=stream)
@@ -299,6 +332,7 @@ class FramePipeline:
         # right behind the stitch: it then costs the compute stream nothing (OCTVR_C4_SIGNAL=sync: wait at once, 0.02 ms per step)
         self.signal_sync = os.environ.get("OCTVR_C4_SIGNAL", "deferred") == "sync"
         self.signals, self.tokens = {}, {}
+        self.prepare, self.side = None, None           # prepare(flat): fills `flat` on the source rank right before it is broadcast
         self.trace = [] if os.environ.get("OCTVR_C4_TRACE") else None
         if peer:
             signal_group()                              # collective: every rank builds the pipeline
@@ -311,13 +345,13 @@ class FramePipeline:
         key = flat.data_ptr()
         works = self.pending.pop(key, None)
         if works is None:
-            works = broadcast_frames(flat, self.src, async_op=True)
+            works = self._broadcast(flat)
         for w in works:
             w.wait()                                   # the compute stream waits for the broadcast, the host does not
         if self.trace is not None:
             self._mark("inputs")
         if next_flat is not None:
-            self.pending[next_flat.data_ptr()] = broadcast_frames(next_flat, self.src, async_op=True)
+            self.pending[next_flat.data_ptr()] = self._broadcast(next_flat)
         self._wait_collect(out)                        # an earlier frame may still be leaving this buffer
         w = self.signals.pop(out.data_ptr(), None)     # ... or its "frame complete" signal may still be in flight
         if w is not None:
@@ -344,6 +378,19 @@ class FramePipeline:
         if self.trace is not None:
             self._mark("done")
         return out
+
+    def _broadcast(self, flat):
+        """Asynchronous broadcast of a frame set; on the source rank `prepare` (e.g. the crop of the full frames to the
+        columns that are read) runs first, on a side stream, so that neither it nor the broadcast waits behind the stitch."""
+        rank = dist.get_rank() if dist.is_initialized() else 0
+        if self.prepare is None or rank != self.src:
+            return broadcast_frames(flat, self.src, async_op=True)
+        if self.side is None:
+            self.side = torch.cuda.Stream()
+        self.side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(self.side):
+            self.prepare(flat)
+            return broadcast_frames(flat, self.src, async_op=True)
 
     def _mark(self, what):
         e = torch.cuda.Event(enable_timing=True)
