@@ -449,10 +449,10 @@ __device__ __forceinline__ void gain_body(const GainParams& p, unsigned long lon
             const CamSrc& sc = p.src[valid ? (sm[h].z & 255u) : 0u];
             slow[h] = valid && (sc.vignette != nullptr || sc.rgb);   // vignette maps, packed RGB input: the per-tap path below
             bits[h] = !valid || slow[h] ? 0u : (sm[h].y & C_BORDER) ? (sm[h].y >> C_TAP_SHIFT) : 15u;
-            const int ix = valid ? (int)(sm[h].x & 0xFFFFu) - 1 : 0, iy = valid ? (int)(sm[h].x >> 16) - 1 : 0;
+            const int ix = valid ? (int)(sm[h].x & 0xFFFFu) - 1 : sc.xlo, iy = valid ? (int)(sm[h].x >> 16) - 1 : 0;
             #pragma unroll
             for (int k = 0; k < 4; k++) {
-                const int x = min(max(ix + (k & 1), 0), sc.w - 1), y = min(max(iy + (k >> 1), 0), sc.h - 1);
+                const int x = min(max(ix + (k & 1), sc.xlo), sc.xhi), y = min(max(iy + (k >> 1), 0), sc.h - 1);
                 yv[h][k] = __ldg(sc.y + (size_t)y * sc.y_pitch + x);
                 uv[h][k] = __ldg(sc.u + (size_t)(y >> 1) * sc.u_pitch + (size_t)(x >> 1) * sc.uv_step);
                 vv[h][k] = __ldg(sc.v + (size_t)(y >> 1) * sc.v_pitch + (size_t)(x >> 1) * sc.uv_step);

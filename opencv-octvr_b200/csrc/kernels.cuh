@@ -12,6 +12,7 @@ struct CamSrc {
                               // three pitches = the row pitch (rgb = 1)
     int rgb;
     int row0, row1;           // rows [row0, row1) are converted (row0 even); the whole image unless the mapper is a row-band mapper
+    int xlo, xhi;             // addressable columns [xlo, xhi] of the frame (the whole width unless the mapper has an input window)
     int col0, col1;           // columns [col0, col1) are converted (col0 a multiple of 8): the part of the frame some table entry reads
     int w, h;
     uint32_t* rgbx;           // w*h, pitch = w pixels

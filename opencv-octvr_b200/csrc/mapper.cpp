@@ -813,6 +813,7 @@ void ob::mapper_stitch_internal(octvr_mapper& m, const octvr_frame* in, int n_in
         c.aligned4 = ((uintptr_t)c.y % 8 == 0) && (c.y_pitch % 8 == 0) && (c.w % 4 == 0) && chroma_ok;
         c.row0 = m.src_row0[i]; c.row1 = m.src_row1[i];
         c.col0 = m.src_col0[i]; c.col1 = m.src_col1[i];
+        c.xlo = m.win_col0[i]; c.xhi = m.win_col0[i] + m.win_w[i] - 1;
         cp.grid_x = std::max(cp.grid_x, (c.col1 - c.col0 + 255) / 256);
         cp.grid_y = std::max(cp.grid_y, (c.row1 - c.row0 + 15) / 16);
     }
