@@ -902,6 +902,29 @@ def cpu_baseline(workload, budget_s=20.0, steps=None, warmup=1):
             "note": note}
 
 
+def cpu_baseline_fast(width=None):
+    """FastMapper on the host: the numpy restatement of mapper_fast.cpp + remap_weighted.cl (oracle.FastMapperOracle, one thread)
+    on ONE frame of the `fast` workload.  The reference's own FastMapper needs an OpenCL device, so there is nothing else to time."""
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import oracle as O
+    import util
+    rig, _, _, desc = WORKLOADS["fast"]
+    cfg, w0, in_size = util.named_rig(rig)
+    width = width or w0
+    n = len(cfg["inputs"])
+    ot = O.build_template(cfg, width, use_roi=False, with_seams=False)
+    fo = O.FastMapperOracle(ot, [in_size] * n)
+    frames = [O.fast_noise_frame(c, *in_size) for c in range(n)]
+    t0 = time.perf_counter()
+    with np.errstate(over="ignore"):
+        fo.stitch_nv12(frames)
+    dt = time.perf_counter() - t0
+    W, H = ot.out_size
+    return {"value": round(W * H / dt / 1e6, 2), "unit": "Mpix/s", "cores": 1, "kind": "port", "frames_per_s": round(1.0 / dt, 3),
+            "ms_per_frame": round(dt * 1e3, 1), "steps_timed": 1, "sample": "1 full frame of %s at output width %d" % (desc, W),
+            "note": "numpy restatement of vr::FastMapper (oracle/oracle.py); the reference's FastMapper itself needs an OpenCL device"}
+
+
 def run_reference(args):
     """The reference's CPU path on the box's host cores, on the headline arm's workload / metric.  A step = one full output frame
     (the CPU port needs ~0.1 s for a C2 frame on 16 threads, so --steps K is honoured as given up to a wall-clock budget of
@@ -944,6 +967,8 @@ def main():
     elif args.workload == "fast":
         line = run_fast(args)
         if line is not None:
+            if not args.no_cpu and int(os.environ.get("WORLD_SIZE", "1")) == 1:
+                line["cpu_baseline"] = cpu_baseline_fast()
             print(json.dumps(line))
     elif args.rowband and int(os.environ.get("WORLD_SIZE", "1")) > 1:
         run_rowband(args)
