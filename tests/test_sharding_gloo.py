@@ -61,9 +61,20 @@ WORKER = textwrap.dedent("""
             pass
     pipe.flush()
     seen = [bufs[0][:, 0].tolist(), bufs[1][:, 0].tolist()]   # buffer 0 holds frame 2, buffer 1 frame 1
+    # peer mode (bands stored straight into the owner's frame, no collection): one "frame complete" all-reduce per step on its
+    # own group, waited for when the output buffer is next written or in flush() -- five steps through two buffers
+    pipe2 = vr.sharding.FramePipeline(Fake(), src=0, peer=True)
+    bufs2 = [torch.zeros((96, 4), dtype=torch.uint8) for _ in range(2)]
+    in_flight = []
+    for k in range(5):
+        pipe2.step(sets[k %% 3][0], sets[k %% 3][1], bufs2[k & 1], next_flat=sets[(k + 1) %% 3][0] if k < 4 else None)
+        in_flight.append(len(pipe2.signals))
+    pipe2.flush()
+    peer = {"in_flight": in_flight, "left": len(pipe2.signals), "tokens": sorted(int(t[0]) for t in pipe2.tokens.values()),
+            "mine": [int(bufs2[0][shares[r][0][0], 0]), int(bufs2[1][shares[r][0][0], 0])]}
     # one write() per rank (< PIPE_BUF): the two ranks share the pipe and print()'s separate newline write can interleave
     os.write(1, (json.dumps({"rank": r, "mine": mine, "t": t, "counts": counts, "bands": bands, "bcast": got, "rows": out[:, 0].tolist(),
-                             "set": [int(views[1][0, 0]), int(views2[0][5, 7])], "rows2": out2[:, 0].tolist(), "pipe": seen}) + chr(10)).encode())
+                             "set": [int(views[1][0, 0]), int(views2[0][5, 7])], "rows2": out2[:, 0].tolist(), "pipe": seen, "peer": peer}) + chr(10)).encode())
     dist.destroy_process_group()
 """) % ROOT
 
@@ -91,6 +102,13 @@ def test_two_rank_gloo_sharding(tmp_path):
     # deferred collection: rank 0 ends with frame 2 (value 30) in buffer 0 and frame 1 (value 20) in buffer 1, both ranks' bands
     assert rows[0]["pipe"][0] == [30] * 32 + [31] * 32 + [30] * 16 + [31] * 16
     assert rows[0]["pipe"][1] == [20] * 32 + [21] * 32 + [20] * 16 + [21] * 16
+
+
+    # peer mode: at most one signal per output buffer in flight, none left after flush(); each token was all-reduced (summed over
+    # the 2 ranks) once per use of its buffer: 3 uses of buffer 0, 2 of buffer 1 -> 0 * 2^3 = 0 stays 0 (the token carries no data)
+    for r in rows:
+        assert r["peer"]["in_flight"] == [1, 2, 2, 2, 2] and r["peer"]["left"] == 0 and r["peer"]["tokens"] == [0, 0]
+    assert rows[0]["peer"]["mine"] == [20, 10] and rows[1]["peer"]["mine"] == [21, 11]   # frames 4 (set 1) and 3 (set 0) of this rank's band
 
 
 def test_row_bands_alignment():
