@@ -5,11 +5,15 @@
 // and ADDED to a 16-bit accumulator plane), full-resolution tables for luma and half-resolution tables for the two chroma
 // planes, then convertTo(CV_8U, 1 / 255).  3 n + 6 launches and three 16-bit accumulator planes through memory per frame.
 //
-// Here: ONE launch.  The output is cut into tiles of 8 rows x 32 threads; a luma thread owns 4 consecutive pixels, a chroma
-// thread 2 consecutive chroma positions (both channels), so every thread ends with one 32-bit store.  A *job* is a
-// (tile, camera) pair with at least one non-zero weight; job j owns 256 x PX consecutive 8-byte entries
-//   { int16 ax, int16 ay, u8 fx, u8 fy, u8 weight, u8 flags }
-// laid out [job][thread][pixel], streamed with 16-byte loads.  The accumulators never leave registers.
+// Here: ONE launch, accumulators in registers, two device paths with the same arithmetic:
+//   k_fast_staged (default)  tiles of 16 rows x 16 threads; per (tile, camera) job the source footprint is copied into shared
+//                            memory (cp.async, zero fill outside the plane) and the taps are read from there; 4-byte entries.
+//   k_fast_nv12              tiles of 8 rows x 32 threads; taps gathered byte by byte through L1 / L2; 8-byte entries
+//                              { int16 ax, int16 ay, u8 fx, u8 fy, u8 weight, u8 flags }
+//                            laid out [job][thread][pixel], streamed with 16-byte loads.  Serves frames that are not 16-byte
+//                            aligned and mappers with a footprint larger than the 16 KB stage (OCTVR_FAST=direct forces it).
+// A luma thread owns 4 consecutive pixels, a chroma thread 2 consecutive chroma positions (both channels), so every thread
+// ends with one 32-bit store.  A *job* is a (tile, camera) pair with at least one non-zero weight.
 //
 // Arithmetic (bit-exact with the kernel above on any IEEE device, see oracle/refgen/ref_fast.cpp):
 //   V = a (32-fx)(32-fy) + b fx (32-fy) + c (32-fx) fy + d fx fy           (integer = 1024 x the float expression, exact)
