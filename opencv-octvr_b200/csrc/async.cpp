@@ -63,6 +63,7 @@ public:
     {
         for (int i = 0; i < n; i++) th_.emplace_back([this] { loop(); });
     }
+    int size() const { return (int)th_.size(); }
     ~CopyPool()
     {
         { std::lock_guard<std::mutex> lk(m_); stop_ = true; }
@@ -133,7 +134,7 @@ void host_copy_plane(CopyPool* pool, uint8_t* dst, size_t dpitch, const uint8_t*
         }
     };
     const size_t bytes = (size_t)w * h;
-    const int nt = !pool ? 1 : bytes > (2u << 20) ? 8 : bytes > (1u << 19) ? 4 : 1;
+    const int nt = !pool ? 1 : bytes > (2u << 20) ? pool->size() + 1 : bytes > (1u << 19) ? std::min(4, pool->size() + 1) : 1;
     if (nt == 1) { rows(0, h); return; }
     pool->run(nt, [&](int t) { rows(h * t / nt, h * (t + 1) / nt); });
 }
@@ -290,9 +291,10 @@ octvr_status octvr_async_create(const octvr_template* const* tmpls, int n_out, c
             OB_CUDA(cudaEventCreateWithFlags(&s.done, cudaEventDisableTiming));
         }
         OB_CUDA(cudaDeviceSynchronize());       // the fills above ran on the legacy stream; the pipeline's streams are non-blocking
-        const int helpers = (int)std::max(1u, std::min(7u, std::thread::hardware_concurrency() / 2));
-        a->pool_in.reset(new CopyPool(helpers));
-        a->pool_out.reset(new CopyPool(std::max(1, helpers / 2)));
+        // helpers of the two staging stages: most of the host's cores for the inputs (37 MB per C2 frame), a few for the output
+        const int hc = (int)std::max(2u, std::thread::hardware_concurrency());
+        a->pool_in.reset(new CopyPool(std::max(1, std::min(11, hc - 5))));
+        a->pool_out.reset(new CopyPool(std::max(1, std::min(3, hc / 4))));
         a->front = std::thread([p = a.get()] { p->front_loop(); });
         a->back = std::thread([p = a.get()] { p->back_loop(); });
         *out = a.release();
