@@ -443,19 +443,9 @@ void add_input_from(octvr_template& tt, const std::string& type, const Json& opt
         in.roi = roi;
         in.map1 = Img<float>(roi.w, roi.h); in.map2 = Img<float>(roi.w, roi.h); in.mask = Img<uint8_t>(roi.w, roi.h);
         const size_t off = (size_t)roi.y * width + roi.x;
-        if (roi.w == width) {            // full rows: one linear copy per table
-            OB_CUDA(cudaMemcpy(in.map1.d.data(), d_m1.p + off, (size_t)roi.w * roi.h * 4, cudaMemcpyDeviceToHost));
-            OB_CUDA(cudaMemcpy(in.map2.d.data(), d_m2.p + off, (size_t)roi.w * roi.h * 4, cudaMemcpyDeviceToHost));
-            OB_CUDA(cudaMemcpy(in.mask.d.data(), d_mask.p + off, (size_t)roi.w * roi.h, cudaMemcpyDeviceToHost));
-        } else {                         // the ROI is compacted on the device first: a pitched copy to pageable memory goes row by row
-            DevBuf<float> d_c((size_t)roi.w * roi.h);
-            OB_CUDA(cudaMemcpy2D(d_c.p, (size_t)roi.w * 4, d_m1.p + off, (size_t)width * 4, (size_t)roi.w * 4, roi.h, cudaMemcpyDeviceToDevice));
-            OB_CUDA(cudaMemcpy(in.map1.d.data(), d_c.p, (size_t)roi.w * roi.h * 4, cudaMemcpyDeviceToHost));
-            OB_CUDA(cudaMemcpy2D(d_c.p, (size_t)roi.w * 4, d_m2.p + off, (size_t)width * 4, (size_t)roi.w * 4, roi.h, cudaMemcpyDeviceToDevice));
-            OB_CUDA(cudaMemcpy(in.map2.d.data(), d_c.p, (size_t)roi.w * roi.h * 4, cudaMemcpyDeviceToHost));
-            OB_CUDA(cudaMemcpy2D(d_c.p, (size_t)roi.w, d_mask.p + off, (size_t)width, (size_t)roi.w, roi.h, cudaMemcpyDeviceToDevice));
-            OB_CUDA(cudaMemcpy(in.mask.d.data(), d_c.p, (size_t)roi.w * roi.h, cudaMemcpyDeviceToHost));
-        }
+        OB_CUDA(cudaMemcpy2D(in.map1.d.data(), (size_t)roi.w * 4, d_m1.p + off, (size_t)width * 4, (size_t)roi.w * 4, roi.h, cudaMemcpyDeviceToHost));
+        OB_CUDA(cudaMemcpy2D(in.map2.d.data(), (size_t)roi.w * 4, d_m2.p + off, (size_t)width * 4, (size_t)roi.w * 4, roi.h, cudaMemcpyDeviceToHost));
+        OB_CUDA(cudaMemcpy2D(in.mask.d.data(), (size_t)roi.w, d_mask.p + off, (size_t)width, (size_t)roi.w, roi.h, cudaMemcpyDeviceToHost));
         tr.lap("copy tables to host");
         if (ic.has_vignette) in.vignette = vignette_map(ic.vig, 512, 512);          // template.cpp:18-19,135-136
         tr.lap("vignette");
