@@ -97,3 +97,23 @@ def test_fill_poly_matches_the_reference_build():
         got = np.full((h, w), 7, np.uint8)
         assert L.octvr_debug_fill_poly(got.ctypes.data_as(C.c_void_p), w, h, pts.ctypes.data_as(C.c_void_p), len(pts) // 2, 200) == 0
         assert np.array_equal(got == 200, want) and set(np.unique(got)) <= {7, 200}, (k, w, h, pts.tolist())
+
+
+def test_product_entry_points_fail_loudly_without_a_device():
+    """No CPU fallback on the per-frame path: every constructor of a stitcher reports OCTVR_ERR_CUDA on a host without a GPU
+    (this test only runs its assertions there), and argument errors are caught before any device work."""
+    import torch
+    L = vr.lib()
+    assert L.octvr_crop_packed_frames(0, None, None, None, None, None, None, None, None) == vr.capi.ERR_INVALID
+    if torch.cuda.is_available():
+        pytest.skip("a CUDA device is present")
+    size, inputs, seams = _arrays("rig2s")
+    t = vr.MapperTemplate.from_arrays(size, inputs, seams)
+    n = len(inputs)
+    for make in (lambda: vr.Mapper(t, [(192, 108)] * n, blend=-3), lambda: vr.Mapper(t, [(192, 108)] * n, blend=16),
+                 lambda: vr.FastMapper(t, [(192, 108)] * n),
+                 lambda: vr.MapperTemplate.from_json(util.rig_json("rig2s"), 128)):
+        with pytest.raises(vr.OctvrError) as e:
+            make()
+        assert e.value.code == vr.capi.ERR_CUDA
+    assert L.octvr_debug_seam_backend() in (-1, 0)          # seam masks, if any were made here, came from the host routine
