@@ -443,6 +443,7 @@ void add_input_from(octvr_template& tt, const std::string& type, const Json& opt
         if (!use_roi) roi = Rect{ 0, 0, width, height };
         TInput in;
         in.roi = roi;
+        in.map1 = Img<float>(roi.w, roi.h); in.map2 = Img<float>(roi.w, roi.h); in.mask = Img<uint8_t>(roi.w, roi.h);
         const size_t off = (size_t)roi.y * width + roi.x;
         if (t->pinned_bytes < area * 4) {
             void* hp = nullptr;
@@ -450,19 +451,20 @@ void add_input_from(octvr_template& tt, const std::string& type, const Json& opt
             t->pinned.reset(hp, [](void* q) { cudaFreeHost(q); });
             t->pinned_bytes = area * 4;
         }
-        // device (pitched) -> page-locked bounce buffer (compact) -> the table.  The table's vector is built FROM the buffer: a
-        // value-initialised vector would touch (fault in) its 60 MB once to zero them and once more for the copy -- that, not the
-        // DMA, is what a 7680 x 1920 table costs on the host
-        auto to_host = [&](auto& img, const auto* d_src) {
-            using T = typename std::remove_reference<decltype(img.d[0])>::type;
-            const size_t row = (size_t)roi.w * sizeof(T);
-            OB_CUDA(cudaMemcpy2D(t->pinned.get(), row, d_src, (size_t)width * sizeof(T), row, roi.h, cudaMemcpyDeviceToHost));
-            img.w = roi.w; img.h = roi.h;
-            img.d.assign(static_cast<const T*>(t->pinned.get()), static_cast<const T*>(t->pinned.get()) + (size_t)roi.w * roi.h);
+        // device (pitched) -> page-locked bounce buffer (compact) -> the table, the last hop on a few threads
+        auto to_host = [&](void* dst, const void* d_src, size_t elem) {
+            const size_t row = (size_t)roi.w * elem, bytes = row * roi.h;
+            OB_CUDA(cudaMemcpy2D(t->pinned.get(), row, d_src, (size_t)width * elem, row, roi.h, cudaMemcpyDeviceToHost));
+            const int nt = bytes > (8u << 20) ? 8 : 1;
+            std::vector<std::thread> th;
+            for (int k = 1; k < nt; k++)
+                th.emplace_back([=] { memcpy((char*)dst + bytes * k / nt, (const char*)t->pinned.get() + bytes * k / nt, bytes * (k + 1) / nt - bytes * k / nt); });
+            memcpy(dst, t->pinned.get(), bytes / nt);
+            for (auto& q : th) q.join();
         };
-        to_host(in.map1, d_m1.p + off);
-        to_host(in.map2, d_m2.p + off);
-        to_host(in.mask, d_mask.p + off);
+        to_host(in.map1.d.data(), d_m1.p + off, 4);
+        to_host(in.map2.d.data(), d_m2.p + off, 4);
+        to_host(in.mask.d.data(), d_mask.p + off, 1);
         tr.lap("copy tables to host");
         if (ic.has_vignette) in.vignette = vignette_map(ic.vig, 512, 512);          // template.cpp:18-19,135-136
         tr.lap("vignette");
