@@ -5,8 +5,6 @@
 // pixel, evaluates the output model's inverse projection, both rotations and the input model's forward
 // projection in f64 (same operation order as the reference), narrows to f32 BEFORE the [0,1) validity test
 // (template.cpp:80-94) and writes map1/map2/mask; the ROI bounding box comes from warp-reduced atomics.
-#include <thread>
-#include <cstring>
 #include "camera.h"
 #include "prep.h"
 #include "template.h"
@@ -445,26 +443,9 @@ void add_input_from(octvr_template& tt, const std::string& type, const Json& opt
         in.roi = roi;
         in.map1 = Img<float>(roi.w, roi.h); in.map2 = Img<float>(roi.w, roi.h); in.mask = Img<uint8_t>(roi.w, roi.h);
         const size_t off = (size_t)roi.y * width + roi.x;
-        if (t->pinned_bytes < area * 4) {
-            void* hp = nullptr;
-            OB_CUDA(cudaMallocHost(&hp, area * 4));
-            t->pinned.reset(hp, [](void* q) { cudaFreeHost(q); });
-            t->pinned_bytes = area * 4;
-        }
-        // device (pitched) -> page-locked bounce buffer (compact) -> the table, the last hop on a few threads
-        auto to_host = [&](void* dst, const void* d_src, size_t elem) {
-            const size_t row = (size_t)roi.w * elem, bytes = row * roi.h;
-            OB_CUDA(cudaMemcpy2D(t->pinned.get(), row, d_src, (size_t)width * elem, row, roi.h, cudaMemcpyDeviceToHost));
-            const int nt = bytes > (8u << 20) ? 8 : 1;
-            std::vector<std::thread> th;
-            for (int k = 1; k < nt; k++)
-                th.emplace_back([=] { memcpy((char*)dst + bytes * k / nt, (const char*)t->pinned.get() + bytes * k / nt, bytes * (k + 1) / nt - bytes * k / nt); });
-            memcpy(dst, t->pinned.get(), bytes / nt);
-            for (auto& q : th) q.join();
-        };
-        to_host(in.map1.d.data(), d_m1.p + off, 4);
-        to_host(in.map2.d.data(), d_m2.p + off, 4);
-        to_host(in.mask.d.data(), d_mask.p + off, 1);
+        OB_CUDA(cudaMemcpy2D(in.map1.d.data(), (size_t)roi.w * 4, d_m1.p + off, (size_t)width * 4, (size_t)roi.w * 4, roi.h, cudaMemcpyDeviceToHost));
+        OB_CUDA(cudaMemcpy2D(in.map2.d.data(), (size_t)roi.w * 4, d_m2.p + off, (size_t)width * 4, (size_t)roi.w * 4, roi.h, cudaMemcpyDeviceToHost));
+        OB_CUDA(cudaMemcpy2D(in.mask.d.data(), (size_t)roi.w, d_mask.p + off, (size_t)width, (size_t)roi.w, roi.h, cudaMemcpyDeviceToHost));
         tr.lap("copy tables to host");
         if (ic.has_vignette) in.vignette = vignette_map(ic.vig, 512, 512);          // template.cpp:18-19,135-136
         tr.lap("vignette");
@@ -516,7 +497,6 @@ octvr_template* template_from_json(const std::string& json, int width, int heigh
     if (cfg.has("overlays"))
         for (size_t i = 0; i < cfg.at("overlays").size(); i++) add_input_from(*t, cfg.at("overlays").at(i).at("type").string(), cfg.at("overlays").at(i).at("options"), true, use_roi);
     if (with_seams) t->seam_masks = distance_seam_masks(t->inputs, t->out_w, device);      // create_masks(), template.cpp:155-204
-    t->pinned.reset(); t->pinned_bytes = 0;
     return t.release();
 }
 

@@ -235,11 +235,7 @@ octvr_status octvr_debug_fill_poly(uint8_t* img, int w, int h, const int* pts, i
 
 octvr_status octvr_template_create_masks(octvr_template* t)
 {
-    return guard([&] {
-        OB_CHECK(t, "null argument");
-        t->seam_masks = distance_seam_masks(t->inputs, t->out_w, t->device);
-        t->pinned.reset(); t->pinned_bytes = 0;              // the template is complete: add_input's bounce buffer goes
-    });
+    return guard([&] { OB_CHECK(t, "null argument"); t->seam_masks = distance_seam_masks(t->inputs, t->out_w, t->device); });
 }
 
 int octvr_debug_seam_backend(void) { return seam_backend(); }

@@ -11,9 +11,6 @@ struct octvr_template {
     // set by MapperTemplate(to, to_opts, width, height): the output camera model, kept for add_input (mapgen.cu)
     std::shared_ptr<void> out_cam;
     int device = -1;
-    // page-locked bounce buffer of add_input (one table plane): a copy from the device straight into pageable memory runs at
-    // ~2 GB/s; released once the template is complete (create_masks / the end of octvr_template_build_json)
-    std::shared_ptr<void> pinned; size_t pinned_bytes = 0;
 };
 
 namespace ob {
