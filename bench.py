@@ -589,11 +589,15 @@ def run_stereo(args, sub=False):
     todo = sorted({e for e, _, _ in vr.sharding.stereo_assignment(world)[rank]})
     if args.verify and rank == 0:
         todo = [0, 1]
-    for e, rig in enumerate(rigs):
-        cfg, width, in_size = util.named_rig(rig)
-        n = len(cfg["inputs"])
-        # only the eye(s) this rank stitches need tables; the other slot reuses the same template object (never stitched)
-        tmpls.append(vr.MapperTemplate.from_json(cfg, width, eye_h, use_roi=True, with_seam_masks=True, device=local) if e in todo else None)
+    from concurrent.futures import ThreadPoolExecutor
+    cfgs = [util.named_rig(rig) for rig in rigs]
+    n, in_size = len(cfgs[0][0]["inputs"]), cfgs[0][2]
+    # only the eye(s) this rank stitches need tables; the other slot reuses the same template object (never stitched).
+    # The two eyes are independent: built side by side (the C ABI calls release the GIL)
+    with ThreadPoolExecutor(max_workers=2) as ex:
+        futs = [ex.submit(vr.MapperTemplate.from_json, cfg, width, eye_h, True, True, local) if e in todo else None
+                for e, (cfg, width, _) in enumerate(cfgs)]
+        tmpls = [f.result() if f is not None else None for f in futs]
     for e in range(2):
         if tmpls[e] is None:
             tmpls[e] = tmpls[todo[0]]

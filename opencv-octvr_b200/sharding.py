@@ -256,8 +256,10 @@ class StereoRowBandStitcher:
             split = os.environ.get("OCTVR_C4_SPLIT", "rows")
         assert split in ("rows", "cols")
         self.split = split
-        self.jobs = []
-        for eye, b, per in stereo_assignment(self.world)[self.rank]:
+        from concurrent.futures import ThreadPoolExecutor
+
+        def make(job):
+            eye, b, per = job
             band, cols = (0, self.eye_h), None
             if per > 1 and split == "rows":
                 band = row_bands(self.eye_h, per, align)[b]
@@ -265,7 +267,10 @@ class StereoRowBandStitcher:
                 cols = row_bands(self.eye_w, per, align)[b]
             m = vr.Mapper(tmpls[eye], in_sizes, blend=blend, enable_gain_compensator=enable_gain, device=device,
                           band=None if (per == 1 or cols is not None) else band, cols=cols)
-            self.jobs.append((eye, band if cols is None else ("cols",) + tuple(cols), m))
+            return (eye, band if cols is None else ("cols",) + tuple(cols), m)
+        mine = stereo_assignment(self.world)[self.rank]
+        with ThreadPoolExecutor(max_workers=max(1, len(mine))) as ex:      # one rank, both eyes: the two mappers are built side by side
+            self.jobs = list(ex.map(make, mine))
 
     def source_cols(self):
         """per camera: the source columns (lo, hi) this rank's mappers read (tables and gain samples)."""
