@@ -10,8 +10,21 @@
 
 #include <chrono>
 #include <cstdlib>
+#include <new>
+#include <sys/mman.h>
 
 namespace ob {
+
+void* big_alloc(size_t bytes)
+{
+    constexpr size_t HUGE = (size_t)2 << 20;
+    if (bytes < 2 * HUGE) { void* p = malloc(bytes ? bytes : 1); if (!p) throw std::bad_alloc(); return p; }
+    void* p = aligned_alloc(HUGE, (bytes + HUGE - 1) & ~(HUGE - 1));
+    if (!p) throw std::bad_alloc();
+    madvise(p, bytes, MADV_HUGEPAGE);          // advisory: ignored where transparent huge pages are disabled
+    return p;
+}
+void big_free(void* p) { free(p); }
 
 double InitTrace::now() { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); }
 InitTrace::InitTrace(const char* w) : what(w), on(getenv("OCTVR_INIT_TRACE") != nullptr), t0(on ? now() : 0.) {}
